@@ -1,0 +1,183 @@
+/*
+ * slaf_b200.h -- C ABI of libslaf_b200.so: the B200 (sm_100a) implementation of SLAF's
+ * ML-dataloader hot path  (COO expression rows -> per-cell token tensors).
+ *
+ * The reference (slaf-project/slaf, package slafdb 0.5.2) is pure Python and has no FFI; the
+ * path it computes with polars + numpy is replaced by the entry points below.  Each entry
+ * point cites the reference interface it stands in for (paths relative to the reference
+ * checkout).  INTEGRATION.md shows the ctypes stub a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every function returns 0 (SLAFB_OK) or a negative slafb_status; slafb_last_error()
+ *     gives the text for the calling context.  Nothing aborts, nothing throws.
+ *   - the caller owns every pointer it passes.  Output tensors are DEVICE memory allocated by
+ *     the caller (PyTorch); the context owns only its scratch, staging buffers, side stream
+ *     and events.  After the first batch of a given size no allocation happens per batch.
+ *   - a context is single-threaded: one context per (feeder thread, device).
+ *   - `stream` is a cudaStream_t (NULL = legacy default stream); results are valid in
+ *     stream order after the call that produced them returns.
+ *   - there is NO CPU fallback: with no usable sm_100 device slafb_create fails.
+ */
+#ifndef SLAF_B200_H
+#define SLAF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SLAFB_ABI_VERSION 1
+
+typedef struct slafb_ctx slafb_ctx;
+
+typedef enum {
+    SLAFB_OK = 0,
+    SLAFB_ERR_INVALID = -1,      /* bad argument (dtype, NULL, size, alignment)                      */
+    SLAFB_ERR_CUDA = -2,         /* a CUDA runtime call failed; text in slafb_last_error             */
+    SLAFB_ERR_CAPACITY = -3,     /* more rows / cells than the context or output tensors can hold    */
+    SLAFB_ERR_BUSY = -4,         /* pipeline slot still in flight (collect it first)                  */
+    SLAFB_ERR_NO_DEVICE = -5,    /* no CUDA device of compute capability 10.x                         */
+    SLAFB_ERR_NONCONTIGUOUS = -6 /* a cell id occurs in two separated row runs (host must splice)     */
+} slafb_status;
+
+/* Column element types.  Input contract = expression.lance rows
+ * (slaf/data/converter.py:2748-2799): cell_integer_id uint32|int32, gene_integer_id
+ * uint16|int32|uint32, value uint16|float32.  No nulls, no NaN. */
+typedef enum { SLAFB_U16 = 0, SLAFB_I32 = 1, SLAFB_U32 = 2, SLAFB_F32 = 3 } slafb_dtype;
+
+/* Which window + tokenizer pair runs (slaf/ml/aggregators.py, slaf/ml/tokenizers.py). */
+typedef enum {
+    SLAFB_GENEFORMER = 0,     /* GeneformerWindow plain branch (aggregators.py:197-214) + GeneformerTokenizer.tokenize (tokenizers.py:635-722) */
+    SLAFB_GENEFORMER_PCT = 1, /* GeneformerWindow min_percentile branch (aggregators.py:167-196) + same tokenizer                           */
+    SLAFB_SCGPT_RAW = 2,      /* ScGPTWindow use_binned_expressions=False / SimpleWindow (aggregators.py:119-134,226-256) + ScGPTTokenizer  */
+    SLAFB_SCGPT_BINNED = 3    /* ScGPTWindow binned branch (aggregators.py:87-118) + ScGPTTokenizer.tokenize (tokenizers.py:375-479)        */
+} slafb_mode;
+
+typedef enum { SLAFB_LOC_DEVICE = 0, SLAFB_LOC_HOST = 1 } slafb_location;
+
+/* A batch of COO rows = the `complete_df` of slaf/ml/datasets.py:956.  Rows of one cell must
+ * be contiguous (the host feeder splices partial cells, datasets.py:880-888).  Column base
+ * pointers must be 16-byte aligned. */
+typedef struct {
+    const void *cell;
+    const void *gene;
+    const void *value;
+    int64_t n_rows;
+    int32_t cell_dtype;  /* SLAFB_U32 | SLAFB_I32 */
+    int32_t gene_dtype;  /* SLAFB_U16 | SLAFB_I32 | SLAFB_U32 */
+    int32_t value_dtype; /* SLAFB_U16 | SLAFB_F32 */
+    int32_t location;    /* slafb_location: device pointers, or host pointers (pinned for async H2D) */
+} slafb_coo;
+
+typedef enum {
+    SLAFB_SHUFFLE_NONE = 0, /* cells in order of first appearance                                           */
+    SLAFB_SHUFFLE_SEED = 1, /* CPython random.seed(seed); random.shuffle(chunks)  (slaf/ml/samplers.py:89-96) */
+    SLAFB_SHUFFLE_PERM = 2  /* explicit permutation supplied in `perm` (host, length = number of cells)      */
+} slafb_shuffle;
+
+typedef struct {
+    int32_t mode;          /* slafb_mode */
+    int32_t max_items;     /* Window.apply(max_items)  = tokenizer.max_genes in the dataloader (datasets.py:1041) */
+    int32_t max_genes;     /* SLAFTokenizer.max_genes: L = max_genes (Geneformer) or max_genes + 2 (scGPT)          */
+    int32_t n_bins;        /* n_expression_bins */
+    int64_t vocab_size;    /* ScGPTTokenizer.expr_bin_start (tokenizers.py:507) */
+    double min_percentile; /* SLAFB_GENEFORMER_PCT only; 0..100 */
+    int32_t shuffle;       /* slafb_shuffle */
+    int32_t reserved;
+    int64_t seed;          /* seed + batch_id + epoch*10000 (datasets.py:1016) */
+    const int32_t *perm;   /* SLAFB_SHUFFLE_PERM */
+    int64_t n_perm;
+} slafb_params;
+
+/* Output tensors (device, row-major, caller-allocated for `capacity_cells` rows):
+ *   input_ids      int64 [capacity_cells, L]
+ *   attention_mask uint8 [capacity_cells, L]   (torch.bool storage)
+ *   values         int64 [capacity_cells, L]   scGPT modes only, else NULL
+ *   cell_ids       int64 [capacity_cells]      grouped row order (datasets.py:1087-1089) */
+typedef struct {
+    int64_t *input_ids;
+    uint8_t *attention_mask;
+    int64_t *values;
+    int64_t *cell_ids;
+    int64_t capacity_cells;
+} slafb_out;
+
+/* Per-kernel device time accumulated since the last call (CUDA events on the launch stream). */
+typedef struct {
+    double csr_ms;      /* K1  slafb_csr_build                */
+    double tokenize_ms; /* K2  slafb_tokenize_cells           */
+    double slowpath_ms; /* K2s slafb_tokenize_cells_general   */
+    double h2d_ms;      /* staged host->device copies         */
+    int64_t batches;
+    int64_t kernel_launches; /* kernels launched since the last call */
+    int64_t cells;
+    int64_t rows;
+    int64_t slow_cells;      /* cells that needed the general (distinct-count) path */
+} slafb_timing;
+
+int slafb_version(void);
+
+/* Replaces the construction of the window/tokenizer compute state:
+ * SLAFTokenizer.__init__ -> create_window() (slaf/ml/tokenizers.py:42-76) and
+ * PrefetchBatchProcessor.__init__ (slaf/ml/datasets.py:312-435), compute part only.
+ * max_rows / max_cells bound one batch (prefetch_batch_size * n_scanners rows). */
+int slafb_create(slafb_ctx **ctx, int device, int64_t max_rows, int64_t max_cells);
+int slafb_destroy(slafb_ctx *ctx);
+const char *slafb_last_error(const slafb_ctx *ctx);
+
+/* The fused hot path, replacing slaf/ml/datasets.py:1011-1098
+ * (shuffle.apply -> tokenizer.window.apply -> .to_list() -> tokenizer.tokenize -> cell ids).
+ * Synchronous with respect to *n_cells; token tensors are complete in `stream` order.
+ * If out->capacity_cells is too small, returns SLAFB_ERR_CAPACITY with *n_cells set. */
+int slafb_tokenize(slafb_ctx *ctx, const slafb_coo *in, const slafb_params *p, const slafb_out *out,
+                   int64_t *n_cells, void *stream);
+
+/* Same path, pipelined (double buffered): submit() enqueues the H2D copy (host input) and the
+ * CSR build on the context's side stream and returns a slot; collect() waits for the cell
+ * count, applies the shuffle and launches the tokenizing kernels on `stream`.  Two slots:
+ * submit(i+1) may precede collect(i).  Replaces the AsyncPrefetcher hand-off
+ * (slaf/ml/datasets.py:1242-1294) for the device-side part of the work. */
+int slafb_submit(slafb_ctx *ctx, const slafb_coo *in, void *stream, int32_t *slot);
+int slafb_collect(slafb_ctx *ctx, int32_t slot, const slafb_params *p, const slafb_out *out,
+                  int64_t *n_cells, void *stream);
+
+/* Window facade: Window.apply(fragment_df, schema, max_items, **kwargs)
+ * (slaf/ml/aggregators.py:26-50; slaf/distributed/window.py:25-59).  Produces the grouped
+ * frame as flat list columns on the device:
+ *   cell_ids int64 [C], offsets int64 [C+1], gene_list int64 [<= n_rows],
+ *   expr_list float64 [<= n_rows] (raw value or expr_bin; NULL for Geneformer modes). */
+int slafb_window(slafb_ctx *ctx, const slafb_coo *in, const slafb_params *p, int64_t *cell_ids,
+                 int64_t *offsets, int64_t *gene_list, double *expr_list, int64_t capacity_cells,
+                 int64_t *n_cells, int64_t *n_items, void *stream);
+
+/* Tokenizer facade: SLAFTokenizer.tokenize(gene_sequences, expr_sequences)
+ * (slaf/ml/tokenizers.py:262-273, 375-479, 635-722) on already-windowed, flattened lists
+ * (device): offsets int64 [B+1], genes int64, exprs float64 (NULL for Geneformer).
+ * exprs_are_int selects the isinstance(exprs[0], int) branch (tokenizers.py:441). */
+int slafb_tokenize_lists(slafb_ctx *ctx, int32_t scgpt, const int64_t *offsets, const int64_t *genes,
+                         const double *exprs, int32_t exprs_are_int, int64_t n_lists,
+                         int32_t max_genes, int32_t n_bins, int64_t vocab_size, const slafb_out *out,
+                         void *stream);
+
+/* RandomShuffle.apply's chunk order (slaf/ml/samplers.py:89-96): bit-exact CPython
+ * random.seed(seed); random.shuffle(list(range(n))) computed on the host in C. */
+int slafb_shuffle_perm(int64_t seed, int64_t n, int32_t *perm);
+
+/* Extension (not in the reference; BASELINE.json config 4): per-gene nonzero sum and count
+ * accumulated INTO sum/cnt (uint64, device, length n_genes) so that ranks can all-reduce them. */
+int slafb_gene_stats(slafb_ctx *ctx, const slafb_coo *in, int64_t n_genes, uint64_t *sum,
+                     uint64_t *cnt, void *stream);
+
+/* Pinned host memory for the feeder's staging buffers (so H2D copies are truly async). */
+int slafb_host_alloc(void **ptr, size_t bytes);
+int slafb_host_free(void *ptr);
+
+/* Timing / counters since the previous call (synchronises the context's streams). */
+int slafb_get_timing(slafb_ctx *ctx, slafb_timing *t);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLAF_B200_H */

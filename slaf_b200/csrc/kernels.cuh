@@ -1,0 +1,866 @@
+// kernels.cuh -- sm_100a device code of the SLAF hot path.
+//
+//   K1  csr_build_kernel        COO cell column -> segment table (CSR offsets + cell ids), one pass,
+//                               warp-ballot/shuffle scans + decoupled look-back across tiles.
+//                               Stands in for polars partition_by / group_by(maintain_order=True)
+//                               (reference slaf/ml/samplers.py:93, slaf/ml/aggregators.py:111,190,208).
+//   K2  tokenize_cells_kernel   one CTA per output row: dense-rank<=k filter, row-order compaction,
+//                               log1p binning, token emission with CLS/SEP/PAD, attention mask and
+//                               cell id written straight into the batch tensors.
+//                               (aggregators.py:87-134,197-214 + tokenizers.py:407-479,666-722
+//                                + datasets.py:1087-1098)
+//   K2g tokenize_general_kernel same emission, but with the exact k-th-distinct-value machinery
+//                               (value bitmap for uint16, shared/global bitonic sort for float32);
+//                               runs over the (normally empty) work list K2 leaves behind, or over all
+//                               cells in percentile mode (aggregators.py:167-196).
+//   K3  window_*                Window.apply facade: kept-count, offsets, flat list columns.
+//   K4  tokenize_lists_kernel   SLAFTokenizer.tokenize facade on pre-windowed lists.
+//   K5  gene_stats_kernel       per-gene nonzero sum / count (extension, BASELINE.json config 4).
+//
+// All of it is HBM-bound integer/byte work: no tensor cores.  Loads are 128-bit, aligned to
+// 8-row groups of the column arrays; stores are coalesced 8/16-byte vectors.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace slafb {
+
+constexpr int kTokThreads = 256;
+constexpr int kGroup = 8;                           // rows per thread per chunk (one 128-bit load of u16)
+constexpr int kChunkRows = kTokThreads * kGroup;    // 2048 rows staged per iteration
+constexpr int kCsrThreads = 256;
+constexpr int kCsrItems = 16;
+constexpr int kCsrTile = kCsrThreads * kCsrItems;   // 4096 rows per tile
+constexpr int kBitmapWords = 65536 / 32;
+constexpr int kSortSmemKeys = 12288;                // general path: float keys sorted in shared memory up to here
+
+enum : int { MODE_GF = 0, MODE_GF_PCT = 1, MODE_SCGPT_RAW = 2, MODE_SCGPT_BINNED = 3 };
+
+// ------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += t;
+    }
+    return v;
+}
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
+#pragma unroll
+    for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+__device__ __forceinline__ uint32_t warp_min(uint32_t v) {
+#pragma unroll
+    for (int d = 16; d; d >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, d));
+    return v;
+}
+__device__ __forceinline__ uint32_t warp_max(uint32_t v) {
+#pragma unroll
+    for (int d = 16; d; d >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, d));
+    return v;
+}
+
+// Block-wide exclusive scan over kTokThreads threads.  `ws` = 16 words of shared scratch.
+// Two barriers; safe to call back to back (second barrier protects the scratch).
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *ws, uint32_t &total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = warp_incl_scan(v);
+    if (lane == 31) ws[warp] = inc;
+    __syncthreads();
+    uint32_t wv = (lane < kTokThreads / 32) ? ws[lane] : 0u;
+    uint32_t winc = warp_incl_scan(wv);
+    uint32_t wbase = __shfl_sync(0xffffffffu, winc - wv, warp);
+    total = __shfl_sync(0xffffffffu, winc, kTokThreads / 32 - 1);
+    __syncthreads();
+    return wbase + inc - v;
+}
+
+__device__ __forceinline__ void block_minmax(uint32_t &lo, uint32_t &hi, uint32_t *ws) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    lo = warp_min(lo);
+    hi = warp_max(hi);
+    if (lane == 0) { ws[warp] = lo; ws[8 + warp] = hi; }
+    __syncthreads();
+    uint32_t l = (lane < kTokThreads / 32) ? ws[lane] : 0xffffffffu;
+    uint32_t h = (lane < kTokThreads / 32) ? ws[8 + lane] : 0u;
+    lo = warp_min(l);
+    hi = warp_max(h);
+    __syncthreads();
+}
+
+// order-preserving 32-bit key of a value (dense rank compares keys)
+__device__ __forceinline__ uint32_t key_of(uint16_t v) { return (uint32_t)v; }
+__device__ __forceinline__ uint32_t key_of(float x) {
+    x = x + 0.0f;  // -0.0 -> +0.0 (equal under IEEE compare, must be one distinct value)
+    uint32_t u = __float_as_uint(x);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float float_of_key(uint32_t k) {
+    uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ uint32_t raw_bits(uint16_t v) { return (uint32_t)v; }
+__device__ __forceinline__ uint32_t raw_bits(float v) { return __float_as_uint(v); }
+
+// 8 consecutive elements starting at row r0 (r0 % 8 == 0, base 16-byte aligned); rows >= R read as 0.
+template <typename T>
+__device__ __forceinline__ void load8(const T *__restrict__ p, uint32_t r0, uint32_t R, T (&out)[8]) {
+    if (r0 + 8u <= R) {
+        if constexpr (sizeof(T) == 2) {
+            uint4 q = __ldg(reinterpret_cast<const uint4 *>(p + r0));
+            uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                uint16_t a = (uint16_t)(w[i] & 0xffffu), b = (uint16_t)(w[i] >> 16);
+                out[2 * i] = *reinterpret_cast<T *>(&a);
+                out[2 * i + 1] = *reinterpret_cast<T *>(&b);
+            }
+        } else {
+            uint4 q0 = __ldg(reinterpret_cast<const uint4 *>(p + r0));
+            uint4 q1 = __ldg(reinterpret_cast<const uint4 *>(p + r0) + 1);
+            uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+            for (int i = 0; i < 8; i++) out[i] = *reinterpret_cast<T *>(&w[i]);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            T z{};
+            out[i] = (r0 + i < R) ? __ldg(p + r0 + i) : z;
+        }
+    }
+}
+
+// numpy `.astype(int)` on x86-64: out-of-range / NaN -> INT64_MIN (cvttss2si "integer indefinite")
+__device__ __forceinline__ long long f32_to_i64_x86(float q) {
+    if (!(q >= -9223372036854775808.0f && q < 9223372036854775808.0f)) return (long long)0x8000000000000000ull;
+    return (long long)q;
+}
+// ScGPTTokenizer._expression_to_bin_vectorized on a float32 (tokenizers.py:521-543)
+__device__ __forceinline__ long long expr_bin_token(float x, float bin_size, int n_bins, long long vocab) {
+    float q = __fdiv_rn(x, bin_size);
+    long long b = f32_to_i64_x86(q);
+    b = b < 0 ? 0 : b;
+    b = b > (long long)(n_bins - 1) ? (long long)(n_bins - 1) : b;
+    return x > 0.0f ? vocab + b : 0ll;
+}
+
+// float32 log1p used by the binned window on float32 storage (polars keeps Float32 and calls libm
+// log1pf).  Computed as the float rounding of the double log1p: differs from glibc's (<1 ulp,
+// not correctly rounded) log1pf only where glibc itself is off by an ulp -- DESIGN.md "float32
+// binned window: parity unpinned at ulp level".
+__device__ __forceinline__ float log1pf_window(float x) { return (float)log1p((double)x); }
+
+// ------------------------------------------------------------------------------------------
+// K1: segmented CSR build from the COO cell column
+// ------------------------------------------------------------------------------------------
+struct CsrArgs {
+    const uint32_t *cell;   // uint32 or int32 bits
+    uint32_t n_rows;
+    uint32_t max_cells;
+    uint32_t *seg_start;    // [max_cells + 1]
+    uint32_t *seg_cell;     // [max_cells]
+    unsigned long long *tile_state;  // [n_tiles] : epoch<<34 | status<<32 | value
+    uint32_t *ticket;       // dynamic tile counter (never reset; host passes the base)
+    uint32_t ticket_base;
+    uint32_t epoch;         // 30-bit launch id, so tile_state needs no memset
+    uint32_t *n_cells_out;  // [0] = number of segments, [1] = error flags
+    uint32_t *work_counters;  // [0] = general-path count, [1] = general-path head  (reset here)
+};
+
+constexpr unsigned long long kStAgg = 1ull, kStPrefix = 2ull;
+__device__ __forceinline__ unsigned long long st_pack(uint32_t epoch, unsigned long long status, uint32_t v) {
+    return ((unsigned long long)epoch << 34) | (status << 32) | (unsigned long long)v;
+}
+
+__global__ void __launch_bounds__(kCsrThreads) csr_build_kernel(const CsrArgs a) {
+    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_warp_tot[kCsrThreads / 32];
+    __shared__ uint32_t s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(a.ticket, 1u) - a.ticket_base;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t n_tiles = (a.n_rows + kCsrTile - 1) / kCsrTile;
+    const uint32_t R = a.n_rows;
+
+    // each warp owns 512 consecutive rows of the tile: 4 iterations x (32 lanes x 4 rows)
+    const uint32_t warp_row0 = tile * kCsrTile + warp * (kCsrItems * 32);
+    uint32_t flags = 0;            // bit (it*4 + e): row is a segment head
+    uint32_t lane_excl[4];         // heads before this lane's rows inside the warp, per iteration
+    uint32_t warp_run = 0;
+#pragma unroll
+    for (int it = 0; it < 4; it++) {
+        const uint32_t r0 = warp_row0 + it * 128 + lane * 4;
+        uint32_t c[4] = {0, 0, 0, 0};
+        if (r0 + 4 <= R) {
+            uint4 q = __ldg(reinterpret_cast<const uint4 *>(a.cell + r0));
+            c[0] = q.x; c[1] = q.y; c[2] = q.z; c[3] = q.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; e++) if (r0 + e < R) c[e] = __ldg(a.cell + r0 + e);
+        }
+        uint32_t prev = __shfl_up_sync(0xffffffffu, c[3], 1);
+        if (lane == 0 && r0 > 0 && r0 < R) prev = __ldg(a.cell + r0 - 1);
+        uint32_t f = 0;
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const uint32_t r = r0 + e;
+            const uint32_t p = (e == 0) ? prev : c[e - 1];
+            if (r < R && (r == 0 || c[e] != p)) f |= 1u << e;
+        }
+        const uint32_t cnt = __popc(f);
+        const uint32_t inc = warp_incl_scan(cnt);
+        lane_excl[it] = warp_run + inc - cnt;
+        warp_run += __shfl_sync(0xffffffffu, inc, 31);
+        flags |= f << (4 * it);
+    }
+    if (lane == 0) s_warp_tot[warp] = warp_run;
+    __syncthreads();
+
+    // warp 0: tile aggregate, publish, decoupled look-back for the exclusive prefix
+    if (warp == 0) {
+        uint32_t wv = (lane < kCsrThreads / 32) ? s_warp_tot[lane] : 0u;
+        uint32_t winc = warp_incl_scan(wv);
+        const uint32_t tile_total = __shfl_sync(0xffffffffu, winc, kCsrThreads / 32 - 1);
+        if (lane < kCsrThreads / 32) s_warp_tot[lane] = winc - wv;  // exclusive warp bases
+        volatile unsigned long long *st = a.tile_state;
+        if (lane == 0) st[tile] = st_pack(a.epoch, tile == 0 ? kStPrefix : kStAgg, tile_total);
+        uint32_t excl = 0;
+        int look = (int)tile - 1;
+        while (look >= 0) {
+            const int idx = look - lane;
+            unsigned long long sv;
+            bool ready;
+            do {
+                sv = (idx >= 0) ? st[idx] : st_pack(a.epoch, kStPrefix, 0u);
+                ready = ((uint32_t)(sv >> 34) == a.epoch) && (((sv >> 32) & 3ull) != 0ull);
+            } while (!__all_sync(0xffffffffu, ready));
+            const bool is_prefix = ((sv >> 32) & 3ull) == kStPrefix;
+            const uint32_t pm = __ballot_sync(0xffffffffu, is_prefix);
+            const uint32_t val = (uint32_t)sv;
+            if (pm) {
+                const int first = __ffs(pm) - 1;  // nearest predecessor that already has a full prefix
+                excl += warp_sum(lane <= first ? val : 0u);
+                break;
+            }
+            excl += warp_sum(val);
+            look -= 32;
+        }
+        if (lane == 0) {
+            if (tile != 0) st[tile] = st_pack(a.epoch, kStPrefix, excl + tile_total);
+            s_base = excl;
+            if (tile == n_tiles - 1) {
+                const uint32_t total = excl + tile_total;
+                a.n_cells_out[0] = total;
+                a.n_cells_out[1] = (total > a.max_cells) ? 1u : 0u;
+                if (total <= a.max_cells) a.seg_start[total] = R;
+                a.work_counters[0] = 0u;
+                a.work_counters[1] = 0u;
+            }
+        }
+    }
+    __syncthreads();
+
+    // scatter the (sparse) segment heads in row order
+    if (flags) {
+        const uint32_t base = s_base + s_warp_tot[warp];
+#pragma unroll
+        for (int it = 0; it < 4; it++) {
+            uint32_t f = (flags >> (4 * it)) & 0xfu;
+            uint32_t g = base + lane_excl[it];
+            const uint32_t r0 = warp_row0 + it * 128 + lane * 4;
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                if (f & (1u << e)) {
+                    if (g < a.max_cells) {
+                        a.seg_start[g] = r0 + e;
+                        a.seg_cell[g] = __ldg(a.cell + r0 + e);
+                    }
+                    g++;
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: tokenization
+// ------------------------------------------------------------------------------------------
+struct TokArgs {
+    const void *gene;
+    const void *value;
+    uint32_t n_rows;
+    const uint32_t *seg_start;
+    const uint32_t *seg_cell;
+    const int32_t *perm;          // nullable: output row -> segment
+    uint32_t n_cells;
+    int cell_signed;              // cell ids are int32 (sign-extend into int64 cell_ids)
+    long long *ids;
+    uint8_t *mask;
+    long long *vals;
+    long long *cell_ids;
+    uint32_t max_items;
+    uint32_t max_genes;
+    uint32_t L;
+    int n_bins;
+    long long vocab;
+    double min_pct;
+    float bin_size;               // float32(1.0 / n_bins)
+    const double *log1p_lut;      // [65536] glibc log1p(double(v)), uploaded once
+    uint32_t *work_list;          // output rows deferred to the general kernel
+    uint32_t *work_counters;      // [0] count, [1] head
+    uint32_t *sort_scratch;       // [n_rows] keys, general path with > kSortSmemKeys float rows
+    int all_cells;                // general kernel: iterate every output row (percentile mode)
+};
+
+struct TokSmem {
+    uint32_t stage_gene[kChunkRows];
+    uint32_t stage_val[kChunkRows];
+    uint32_t ws[32];
+    uint32_t bcast[4];
+};
+
+// zero-fill int64 elements [A, B) of a flat array (8-byte aligned base), 16-byte stores inside
+__device__ __forceinline__ void fill_zero_i64(long long *base, size_t A, size_t B) {
+    if (A >= B) return;
+    size_t a2 = (A + 1) & ~(size_t)1, b2 = B & ~(size_t)1;
+    if (threadIdx.x == 0 && (A & 1)) base[A] = 0;
+    if (threadIdx.x == 1 && (B & 1) && B - 1 >= A) base[B - 1] = 0;
+    if (a2 < b2) {
+        ulonglong2 *v = reinterpret_cast<ulonglong2 *>(base + a2);
+        const size_t nv = (b2 - a2) >> 1;
+        for (size_t i = threadIdx.x; i < nv; i += blockDim.x) v[i] = make_ulonglong2(0ull, 0ull);
+    }
+}
+
+// attention mask bytes for flat range [A, A+L): 1 for the first t_len, then 0; 16-byte stores inside
+__device__ __forceinline__ void fill_mask(uint8_t *base, size_t A, uint32_t L, uint32_t t_len) {
+    const size_t B = A + L, ones_end = A + t_len;
+    const size_t c0 = A >> 4, c1 = (B + 15) >> 4;
+    for (size_t c = c0 + threadIdx.x; c < c1; c += blockDim.x) {
+        const size_t lo = c << 4;
+        if (lo >= A && lo + 16 <= B) {
+            uint32_t w[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                uint32_t x = 0;
+#pragma unroll
+                for (int b = 0; b < 4; b++) x |= (lo + q * 4 + b < ones_end ? 1u : 0u) << (8 * b);
+                w[q] = x;
+            }
+            *reinterpret_cast<uint4 *>(base + lo) = make_uint4(w[0], w[1], w[2], w[3]);
+        } else {
+            for (size_t i = (lo > A ? lo : A); i < lo + 16 && i < B; i++) base[i] = (i < ones_end) ? 1 : 0;
+        }
+    }
+}
+
+// value stream token for one kept row (scGPT modes)
+template <typename ValT, int MODE>
+__device__ __forceinline__ long long value_token(uint32_t raw, const TokArgs &a, double m_f64, float m_f32) {
+    if constexpr (MODE == MODE_SCGPT_RAW) {
+        if constexpr (sizeof(ValT) == 2) {
+            return (long long)raw + a.vocab;  // isinstance(int) branch, tokenizers.py:441-444
+        } else {
+            return expr_bin_token(__uint_as_float(raw), a.bin_size, a.n_bins, a.vocab);
+        }
+    } else {
+        float bin;
+        if constexpr (sizeof(ValT) == 2) {
+            const double lv = __ldg(a.log1p_lut + raw);
+            double b = 0.0;
+            if (lv > 0.0) {
+                b = floor(__ddiv_rn(__dmul_rn(lv, (double)a.n_bins), m_f64));
+                b = fmin(fmax(b, 0.0), (double)(a.n_bins - 1));
+            }
+            bin = (float)b;
+        } else {
+            const float lv = log1pf_window(__uint_as_float(raw));
+            float b = 0.0f;
+            if (lv > 0.0f) {
+                b = floorf(__fdiv_rn(__fmul_rn(lv, (float)a.n_bins), m_f32));
+                b = fminf(fmaxf(b, 0.0f), (float)(a.n_bins - 1));
+            }
+            bin = b;
+        }
+        return expr_bin_token(bin, a.bin_size, a.n_bins, a.vocab);  // float branch applied to the bin
+    }
+}
+
+// expr_bin of the binned window as double (facade output)
+template <typename ValT>
+__device__ __forceinline__ double window_bin(uint32_t raw, const TokArgs &a, double m_f64, float m_f32) {
+    if constexpr (sizeof(ValT) == 2) {
+        const double lv = __ldg(a.log1p_lut + raw);
+        double b = 0.0;
+        if (lv > 0.0) {
+            b = floor(__ddiv_rn(__dmul_rn(lv, (double)a.n_bins), m_f64));
+            b = fmin(fmax(b, 0.0), (double)(a.n_bins - 1));
+        }
+        return b;
+    } else {
+        const float lv = log1pf_window(__uint_as_float(raw));
+        float b = 0.0f;
+        if (lv > 0.0f) {
+            b = floorf(__fdiv_rn(__fmul_rn(lv, (float)a.n_bins), m_f32));
+            b = fminf(fmaxf(b, 0.0f), (float)(a.n_bins - 1));
+        }
+        return (double)b;
+    }
+}
+
+// ---- exact threshold machinery (general path) ------------------------------------------------
+// Target ascending dense rank a* in [1, D]: keep rows whose ascending rank >= a*.
+//   plain:       a* = D - min(k, D) + 1
+//   percentile:  additionally ascending rank >= ceil(p * D / 100)   (f64 compare, aggregators.py:184-188)
+__device__ __forceinline__ uint32_t target_asc_rank(uint32_t D, uint32_t k, bool pct, double p) {
+    const uint32_t q = k < D ? k : D;
+    uint32_t astar = D - q + 1;
+    if (pct) {
+        const double t = __ddiv_rn(__dmul_rn(p, (double)D), 100.0);
+        double ct = ceil(t);
+        uint32_t ap = ct < 1.0 ? 1u : (ct > 4294967295.0 ? 0xffffffffu : (uint32_t)ct);
+        if (ap > astar) astar = ap;
+    }
+    return astar;
+}
+
+// uint16 values: presence bitmap over [lo, hi]; returns the key of the a*-th distinct value (ascending)
+template <typename ValT>
+__device__ uint32_t threshold_bitmap(const ValT *__restrict__ value, uint32_t s, uint32_t e, uint32_t R,
+                                     uint32_t lo, uint32_t hi, uint32_t k, bool pct, double p,
+                                     uint32_t *bitmap, uint32_t *ws, uint32_t *bcast) {
+    const int tid = threadIdx.x;
+    const uint32_t w0 = lo >> 5, w1 = hi >> 5;
+    for (uint32_t w = w0 + tid; w <= w1; w += kTokThreads) bitmap[w] = 0u;
+    __syncthreads();
+    for (uint32_t g0 = s & ~7u; g0 < e; g0 += kChunkRows) {
+        const uint32_t r0 = g0 + tid * kGroup;
+        if (r0 < e) {
+            ValT v[8];
+            load8(value, r0, R, v);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const uint32_t r = r0 + i;
+                if (r >= s && r < e) {
+                    const uint32_t key = key_of(v[i]);
+                    atomicOr(&bitmap[key >> 5], 1u << (key & 31));
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // distinct count
+    uint32_t cnt = 0;
+    for (uint32_t w = w0 + tid; w <= w1; w += kTokThreads) cnt += __popc(bitmap[w]);
+    uint32_t D;
+    block_excl_scan(cnt, ws, D);
+    const uint32_t astar = target_asc_rank(D, k, pct, p);
+    // locate the a*-th set bit from the bottom
+    uint32_t run = 0;
+    for (uint32_t wb = w0; wb <= w1; wb += kTokThreads) {
+        const uint32_t w = wb + tid;
+        const uint32_t word = (w <= w1) ? bitmap[w] : 0u;
+        const uint32_t pc = __popc(word);
+        uint32_t tot;
+        const uint32_t ex = run + block_excl_scan(pc, ws, tot);
+        if (astar > ex && astar <= ex + pc) {
+            uint32_t x = word;
+            for (uint32_t i = ex + 1; i < astar; i++) x &= x - 1;  // drop lower set bits
+            bcast[0] = (w << 5) + (__ffs(x) - 1);
+        }
+        run += tot;
+        if (run >= astar) break;
+    }
+    __syncthreads();
+    const uint32_t thr = bcast[0];
+    __syncthreads();
+    return thr;
+}
+
+// float32 values: bitonic sort of the keys (shared memory, or global scratch when the cell is
+// larger than kSortSmemKeys), then the a*-th distinct key.  All compare-exchanges are ascending
+// (mirrored first step), so the virtual +inf padding above n never moves.
+__device__ void bitonic_sort_asc(uint32_t *keys, uint32_t n) {
+    const int tid = threadIdx.x;
+    uint32_t P = 1;
+    while (P < n) P <<= 1;
+    const uint32_t half = P >> 1;
+    for (uint32_t k = 2; k <= P; k <<= 1) {
+        const uint32_t hk = k >> 1;
+        for (uint32_t t = tid; t < half; t += kTokThreads) {
+            const uint32_t blk = t / hk, i = t - blk * hk;
+            const uint32_t lo = blk * k + i, hi = blk * k + k - 1 - i;
+            if (hi < n) {
+                const uint32_t x = keys[lo], y = keys[hi];
+                if (x > y) { keys[lo] = y; keys[hi] = x; }
+            }
+        }
+        __syncthreads();
+        for (uint32_t j = hk >> 1; j >= 1; j >>= 1) {
+            for (uint32_t t = tid; t < half; t += kTokThreads) {
+                const uint32_t lo = 2 * j * (t / j) + (t % j), hi = lo + j;
+                if (hi < n) {
+                    const uint32_t x = keys[lo], y = keys[hi];
+                    if (x > y) { keys[lo] = y; keys[hi] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+template <typename ValT>
+__device__ uint32_t threshold_sort(const ValT *__restrict__ value, uint32_t s, uint32_t e, uint32_t R,
+                                   uint32_t k, bool pct, double p, uint32_t *keys, uint32_t *ws,
+                                   uint32_t *bcast) {
+    const int tid = threadIdx.x;
+    const uint32_t n = e - s;
+    for (uint32_t i = tid; i < n; i += kTokThreads) keys[i] = key_of(__ldg(value + s + i));
+    __syncthreads();
+    bitonic_sort_asc(keys, n);
+    // distinct count
+    uint32_t cnt = 0;
+    for (uint32_t i = tid; i < n; i += kTokThreads) cnt += (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+    uint32_t D;
+    block_excl_scan(cnt, ws, D);
+    const uint32_t astar = target_asc_rank(D, k, pct, p);
+    uint32_t run = 0;
+    for (uint32_t ib = 0; ib < n; ib += kTokThreads) {
+        const uint32_t i = ib + tid;
+        const uint32_t head = (i < n && (i == 0 || keys[i] != keys[i - 1])) ? 1u : 0u;
+        uint32_t tot;
+        const uint32_t ex = run + block_excl_scan(head, ws, tot);
+        if (head && ex + 1 == astar) bcast[0] = keys[i];
+        run += tot;
+        if (run >= astar) break;
+    }
+    __syncthreads();
+    const uint32_t thr = bcast[0];
+    __syncthreads();
+    return thr;
+}
+
+// ---- one cell ------------------------------------------------------------------------------
+// SINK: 0 = token tensors (K2/K2g), 1 = count only (window pass A), 2 = flat lists (window pass B)
+struct WindowSink {
+    uint32_t *kept_count;      // [C]   pass A
+    const long long *offsets;  // [C+1] pass B (exclusive scan of kept_count)
+    long long *gene_list;
+    double *expr_list;
+};
+
+template <typename GeneT, typename ValT, int MODE, bool GENERAL, int SINK>
+__device__ bool process_cell(const TokArgs &a, const WindowSink &wsnk, uint32_t out_row, TokSmem &sm,
+                             uint32_t *bitmap, uint32_t *sort_smem) {
+    constexpr bool SCGPT = (MODE == MODE_SCGPT_RAW || MODE == MODE_SCGPT_BINNED);
+    constexpr bool BINNED = (MODE == MODE_SCGPT_BINNED);
+    constexpr bool PCT = (MODE == MODE_GF_PCT);
+    constexpr bool U16 = (sizeof(ValT) == 2);
+    const int tid = threadIdx.x;
+    const GeneT *__restrict__ gene = static_cast<const GeneT *>(a.gene);
+    const ValT *__restrict__ value = static_cast<const ValT *>(a.value);
+    const uint32_t c = a.perm ? (uint32_t)a.perm[out_row] : out_row;
+    const uint32_t s = __ldg(a.seg_start + c), e = __ldg(a.seg_start + c + 1);
+    const uint32_t n = e - s, R = a.n_rows, k = a.max_items;
+
+    // ---- pass 1: statistics the filter / binning needs ------------------------------------
+    bool keep_all = (n <= k) && !PCT;
+    uint32_t thr = 0;
+    uint32_t kmax = 0;
+    float m_f32 = 0.0f;
+    if (BINNED || !keep_all) {
+        uint32_t lo = 0xffffffffu, hi = 0u;
+        float lvmax = -INFINITY;
+        for (uint32_t g0 = s & ~7u; g0 < e; g0 += kChunkRows) {
+            const uint32_t r0 = g0 + tid * kGroup;
+            if (r0 < e) {
+                ValT v[8];
+                load8(value, r0, R, v);
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const uint32_t r = r0 + i;
+                    if (r >= s && r < e) {
+                        const uint32_t key = key_of(v[i]);
+                        lo = min(lo, key);
+                        hi = max(hi, key);
+                        if constexpr (BINNED && !U16) lvmax = fmaxf(lvmax, log1pf_window((float)v[i]));
+                    }
+                }
+            }
+        }
+        block_minmax(lo, hi, sm.ws);
+        kmax = hi;
+        if constexpr (BINNED && !U16) {
+            uint32_t lk = key_of(lvmax), dummy = 0xffffffffu;
+            block_minmax(dummy, lk, sm.ws);
+            m_f32 = float_of_key(lk);
+        }
+        if (!keep_all) {
+            if (!PCT && U16 && (hi - lo + 1u <= k)) {
+                keep_all = true;  // at most k distinct values can exist in [lo, hi]
+            } else {
+                if constexpr (!GENERAL) {
+                    if (tid == 0) a.work_list[atomicAdd(a.work_counters, 1u)] = out_row;
+                    return false;
+                } else {
+                    if constexpr (U16) {
+                        thr = threshold_bitmap<ValT>(value, s, e, R, lo, hi, k, PCT, a.min_pct, bitmap, sm.ws, sm.bcast);
+                    } else {
+                        uint32_t *keys = (n <= (uint32_t)kSortSmemKeys) ? sort_smem : (a.sort_scratch + s);
+                        thr = threshold_sort<ValT>(value, s, e, R, k, PCT, a.min_pct, keys, sm.ws, sm.bcast);
+                    }
+                }
+            }
+        }
+    }
+    double m_f64 = 0.0;
+    if constexpr (BINNED && U16) m_f64 = __ldg(a.log1p_lut + kmax);
+    // binned window: the max is taken over KEPT rows (aggregators.py:103); the cell maximum always
+    // has dense rank 1 <= max_items, so it equals the max over all rows of the cell.
+
+    // ---- pass 2: row-order compaction + emission ------------------------------------------
+    const uint32_t L = a.L;
+    const uint32_t limit = (SINK == 0) ? (SCGPT ? a.max_genes : (L - 1u)) : 0xffffffffu;
+    const size_t row_base = (size_t)out_row * L;
+    const long long list_base = (SINK == 2) ? wsnk.offsets[out_row] : 0;
+    uint32_t base = 0;
+    for (uint32_t g0 = s & ~7u; g0 < e && base < limit; g0 += kChunkRows) {
+        const uint32_t r0 = g0 + tid * kGroup;
+        GeneT g[8];
+        ValT v[8];
+        uint32_t flags = 0;
+        if (r0 < e) {
+            if constexpr (SINK != 1) load8(gene, r0, R, g);
+            if (SCGPT || !keep_all) load8(value, r0, R, v);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const uint32_t r = r0 + i;
+                bool kp = (r >= s && r < e);
+                if (!keep_all) kp = kp && (key_of(v[i]) >= thr);
+                flags |= (kp ? 1u : 0u) << i;
+            }
+        }
+        uint32_t chunk_total;
+        uint32_t off = block_excl_scan(__popc(flags), sm.ws, chunk_total);
+        if constexpr (SINK != 1) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                if (flags & (1u << i)) {
+                    sm.stage_gene[off] = (uint32_t)g[i];
+                    if constexpr (SCGPT) sm.stage_val[off] = raw_bits(v[i]);
+                    off++;
+                }
+            }
+            __syncthreads();
+            const uint32_t m = min(chunk_total, limit - base);
+            if constexpr (SINK == 0) {
+                long long *ids = a.ids + row_base + 1 + base;
+                for (uint32_t i = tid; i < m; i += kTokThreads) {
+                    long long gid;
+                    if constexpr (sizeof(GeneT) == 2) gid = (long long)sm.stage_gene[i];
+                    else gid = (long long)(int32_t)sm.stage_gene[i];
+                    ids[i] = gid + 4;                               // tokenizers.py:439,686
+                    if constexpr (SCGPT) a.vals[row_base + 1 + base + i] = value_token<ValT, MODE>(sm.stage_val[i], a, m_f64, m_f32);
+                }
+            } else {
+                for (uint32_t i = tid; i < m; i += kTokThreads) {
+                    long long gid;
+                    if constexpr (sizeof(GeneT) == 2) gid = (long long)sm.stage_gene[i];
+                    else gid = (long long)(int32_t)sm.stage_gene[i];
+                    wsnk.gene_list[list_base + base + i] = gid;
+                    if constexpr (SCGPT) {
+                        double x;
+                        if constexpr (BINNED) x = window_bin<ValT>(sm.stage_val[i], a, m_f64, m_f32);
+                        else if constexpr (U16) x = (double)sm.stage_val[i];
+                        else x = (double)__uint_as_float(sm.stage_val[i]);
+                        wsnk.expr_list[list_base + base + i] = x;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        base += chunk_total;
+    }
+
+    if constexpr (SINK == 1) {
+        if (tid == 0) wsnk.kept_count[out_row] = base;
+        return true;
+    } else if constexpr (SINK == 2) {
+        return true;
+    } else {
+        // ---- frame: CLS / SEP / PAD, value-stream PADs, attention mask, cell id -------------
+        const uint32_t n_emit = min(base, limit);
+        const uint32_t sep_pos = 1u + n_emit;
+        const uint32_t t_len = min(n_emit + 2u, L);
+        if (tid == 0) {
+            a.ids[row_base] = 1;                                   // CLS
+            if (sep_pos < L) a.ids[row_base + sep_pos] = 2;        // SEP (dropped when truncated, tokenizers.py:706)
+            if constexpr (SCGPT) a.vals[row_base] = 0;             // PAD under CLS
+            const uint32_t cid = __ldg(a.seg_cell + c);
+            a.cell_ids[out_row] = a.cell_signed ? (long long)(int32_t)cid : (long long)cid;
+        }
+        fill_zero_i64(a.ids, row_base + t_len, row_base + L);
+        if constexpr (SCGPT) fill_zero_i64(a.vals, row_base + sep_pos, row_base + L);
+        fill_mask(a.mask, row_base, L, t_len);
+        return true;
+    }
+}
+
+template <typename GeneT, typename ValT, int MODE>
+__global__ void __launch_bounds__(kTokThreads) tokenize_cells_kernel(const TokArgs a) {
+    __shared__ TokSmem sm;
+    WindowSink none{};
+    process_cell<GeneT, ValT, MODE, false, 0>(a, none, blockIdx.x, sm, nullptr, nullptr);
+}
+
+// general path: persistent CTAs over the work list (or over all cells)
+template <typename GeneT, typename ValT, int MODE, int SINK>
+__global__ void __launch_bounds__(kTokThreads) tokenize_general_kernel(const TokArgs a, const WindowSink wsnk) {
+    __shared__ TokSmem sm;
+    __shared__ uint32_t s_item;
+    extern __shared__ __align__(16) uint32_t dyn[];   // bitmap (u16) or sort keys (f32)
+    const uint32_t count = a.all_cells ? a.n_cells : a.work_counters[0];
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_item = atomicAdd(a.work_counters + 1, 1u);
+        __syncthreads();
+        const uint32_t it = s_item;
+        if (it >= count) break;
+        const uint32_t row = a.all_cells ? it : a.work_list[it];
+        process_cell<GeneT, ValT, MODE, true, SINK>(a, wsnk, row, sm, dyn, dyn);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// facade helpers
+// ------------------------------------------------------------------------------------------
+// exclusive scan of kept counts (one CTA; C is at most a few hundred thousand)
+__global__ void __launch_bounds__(1024) scan_counts_kernel(const uint32_t *cnt, long long *offsets, uint32_t n,
+                                                           long long *total_out) {
+    __shared__ unsigned long long wsum[32];
+    __shared__ unsigned long long carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry = 0ull;
+    __syncthreads();
+    for (uint32_t b = 0; b < n; b += 1024) {
+        const uint32_t i = b + tid;
+        unsigned long long v = (i < n) ? cnt[i] : 0ull;
+        unsigned long long inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned long long t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += t;
+        }
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long w = wsum[lane], winc = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                unsigned long long t = __shfl_up_sync(0xffffffffu, winc, d);
+                if (lane >= d) winc += t;
+            }
+            wsum[lane] = winc - w;
+        }
+        __syncthreads();
+        const unsigned long long ex = carry + wsum[warp] + inc - v;
+        if (i < n) offsets[i] = (long long)ex;
+        __syncthreads();
+        if (tid == 1023) carry = ex + v;
+        __syncthreads();
+    }
+    if (tid == 0) { offsets[n] = (long long)carry; *total_out = (long long)carry; }
+}
+
+__global__ void cell_ids_kernel(const uint32_t *seg_cell, const int32_t *perm, uint32_t n, int cell_signed,
+                                long long *cell_ids) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint32_t c = perm ? (uint32_t)perm[j] : j;
+    const uint32_t cid = seg_cell[c];
+    cell_ids[j] = cell_signed ? (long long)(int32_t)cid : (long long)cid;
+}
+
+// K4: SLAFTokenizer.tokenize on flattened pre-windowed lists: one CTA per list
+struct ListArgs {
+    const long long *offsets;
+    const long long *genes;
+    const double *exprs;
+    int exprs_are_int;
+    int scgpt;
+    uint32_t n_lists;
+    uint32_t max_genes;
+    uint32_t L;
+    int n_bins;
+    long long vocab;
+    float bin_size;
+    long long *ids;
+    uint8_t *mask;
+    long long *vals;
+};
+
+__global__ void __launch_bounds__(kTokThreads) tokenize_lists_kernel(const ListArgs a) {
+    const uint32_t row = blockIdx.x;
+    const long long s = a.offsets[row], e = a.offsets[row + 1];
+    const unsigned long long n = (unsigned long long)(e - s);
+    const uint32_t L = a.L;
+    const uint32_t limit = a.scgpt ? a.max_genes : (L - 1u);
+    const uint32_t n_emit = (uint32_t)(n < (unsigned long long)limit ? n : (unsigned long long)limit);
+    const size_t row_base = (size_t)row * L;
+    for (uint32_t i = threadIdx.x; i < n_emit; i += kTokThreads) {
+        a.ids[row_base + 1 + i] = a.genes[s + i] + 4;
+        if (a.scgpt) {
+            const double x = a.exprs[s + i];
+            a.vals[row_base + 1 + i] = a.exprs_are_int ? (long long)x + a.vocab
+                                                       : expr_bin_token((float)x, a.bin_size, a.n_bins, a.vocab);
+        }
+    }
+    const uint32_t sep_pos = 1u + n_emit, t_len = min(n_emit + 2u, L);
+    if (threadIdx.x == 0) {
+        a.ids[row_base] = 1;
+        if (sep_pos < L) a.ids[row_base + sep_pos] = 2;
+        if (a.scgpt) a.vals[row_base] = 0;
+    }
+    fill_zero_i64(a.ids, row_base + t_len, row_base + L);
+    if (a.scgpt) fill_zero_i64(a.vals, row_base + sep_pos, row_base + L);
+    fill_mask(a.mask, row_base, L, t_len);
+}
+
+// K5: per-gene nonzero sum / count (integer sums: identical for any rank count / order)
+template <typename GeneT, typename ValT>
+__global__ void __launch_bounds__(256) gene_stats_kernel(const GeneT *__restrict__ gene, const ValT *__restrict__ value,
+                                                         uint32_t n_rows, uint32_t n_genes,
+                                                         unsigned long long *sum, unsigned long long *cnt) {
+    const uint32_t stride = gridDim.x * blockDim.x * kGroup;
+    for (uint32_t r0 = (blockIdx.x * blockDim.x + threadIdx.x) * kGroup; r0 < n_rows; r0 += stride) {
+        GeneT g[8];
+        ValT v[8];
+        load8(gene, r0, n_rows, g);
+        load8(value, r0, n_rows, v);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if (r0 + i < n_rows) {
+                const uint32_t gi = (uint32_t)g[i];
+                if (gi < n_genes) {
+                    if constexpr (sizeof(ValT) == 2) {
+                        if (v[i] != 0) { atomicAdd(sum + gi, (unsigned long long)v[i]); atomicAdd(cnt + gi, 1ull); }
+                    } else {
+                        // float32 values: fixed-point 2^-20 accumulation keeps the reduction order-independent
+                        if (v[i] != 0.0f) {
+                            atomicAdd(sum + gi, (unsigned long long)llrintf(v[i] * 1048576.0f));
+                            atomicAdd(cnt + gi, 1ull);
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+}  // namespace slafb

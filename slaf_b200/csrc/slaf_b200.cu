@@ -1,0 +1,635 @@
+// slaf_b200.cu -- C-ABI implementation (see include/slaf_b200.h for the contract and the
+// reference interfaces each entry point replaces).
+//
+// Stream model.  Each context owns a side stream `s_in` and two pipeline slots.
+//   submit : [s_in]    wait(caller stream) -> H2D of the COO columns (host input) -> K1 CSR build
+//                      -> D2H of {n_cells, error flags} into pinned memory -> event `front`
+//   collect: [host]    wait `front`; build the shuffle permutation (CPython-exact, host C)
+//            [stream]  wait(front) -> H2D permutation -> K2 tokenize -> K2g general path -> event `done`
+// so the H2D copy and CSR build of batch i+1 overlap the tokenization of batch i, and the only
+// host<->device round trip per batch is the 8-byte cell count.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "../../include/slaf_b200.h"
+#include "kernels.cuh"
+#include "py_shuffle.h"
+
+using namespace slafb;
+
+namespace {
+
+constexpr int kSlots = 2;
+
+struct Slot {
+    bool in_flight = false;
+    // device scratch
+    uint32_t *seg_start = nullptr, *seg_cell = nullptr;
+    int32_t *perm_dev = nullptr;
+    uint32_t *work_list = nullptr;
+    uint32_t *counters = nullptr;   // [0] n_cells, [1] err, [2] work count, [3] work head
+    // staged copies of host input (lazy)
+    void *in_cell = nullptr, *in_gene = nullptr, *in_value = nullptr;
+    // pinned host
+    uint32_t *h_counters = nullptr; // [0] n_cells, [1] err, [2] cells deferred to the general kernel
+    bool all_general = false;
+    int32_t *h_perm = nullptr;
+    // batch description (device pointers actually used by the kernels)
+    const void *cell = nullptr, *gene = nullptr, *value = nullptr;
+    int64_t n_rows = 0;
+    int32_t cell_dtype = 0, gene_dtype = 0, value_dtype = 0;
+    cudaEvent_t ev_front = nullptr, ev_done = nullptr, ev_in = nullptr;
+    // timing events
+    cudaEvent_t t_h2d0 = nullptr, t_h2d1 = nullptr, t_k1a = nullptr, t_k1b = nullptr, t_k2a = nullptr, t_k2b = nullptr, t_k2c = nullptr;
+    bool timed_front = false, timed_back = false, timed_h2d = false;
+};
+
+}  // namespace
+
+struct slafb_ctx {
+    int device = 0;
+    int n_sm = 148;
+    int64_t max_rows = 0, max_cells = 0;
+    cudaStream_t s_in = nullptr;
+    Slot slot[kSlots];
+    int next_slot = 0;
+    unsigned long long *tile_state = nullptr;
+    uint32_t *ticket = nullptr;
+    uint32_t ticket_base = 0, epoch = 0;
+    double *log1p_lut = nullptr;
+    uint32_t *sort_scratch = nullptr;
+    // window facade scratch
+    uint32_t *kept_count = nullptr;
+    long long *total_dev = nullptr;
+    long long *h_total = nullptr;
+    slafb_timing acc{};
+    char err[512] = {0};
+};
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(slafb_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) snprintf(ctx->err, sizeof ctx->err, "%s", buf);
+    snprintf(g_err, sizeof g_err, "%s", buf);
+    return code;
+}
+
+#define CU(ctx, call)                                                                          \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            return fail(ctx, SLAFB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+size_t dtype_size(int dt) { return dt == SLAFB_U16 ? 2 : 4; }
+
+int check_coo(slafb_ctx *ctx, const slafb_coo *in) {
+    if (!in) return fail(ctx, SLAFB_ERR_INVALID, "coo is NULL");
+    if (in->n_rows < 0) return fail(ctx, SLAFB_ERR_INVALID, "n_rows < 0");
+    if (in->n_rows > ctx->max_rows) return fail(ctx, SLAFB_ERR_CAPACITY, "n_rows %lld exceeds context max_rows %lld", (long long)in->n_rows, (long long)ctx->max_rows);
+    if (in->cell_dtype != SLAFB_U32 && in->cell_dtype != SLAFB_I32) return fail(ctx, SLAFB_ERR_INVALID, "cell dtype must be uint32 or int32");
+    if (in->gene_dtype != SLAFB_U16 && in->gene_dtype != SLAFB_I32 && in->gene_dtype != SLAFB_U32) return fail(ctx, SLAFB_ERR_INVALID, "gene dtype must be uint16, int32 or uint32");
+    if (in->value_dtype != SLAFB_U16 && in->value_dtype != SLAFB_F32) return fail(ctx, SLAFB_ERR_INVALID, "value dtype must be uint16 or float32");
+    if (in->n_rows > 0) {
+        if (!in->cell || !in->gene || !in->value) return fail(ctx, SLAFB_ERR_INVALID, "NULL column pointer");
+        if (in->location == SLAFB_LOC_DEVICE &&
+            (((uintptr_t)in->cell | (uintptr_t)in->gene | (uintptr_t)in->value) & 15u))
+            return fail(ctx, SLAFB_ERR_INVALID, "device column pointers must be 16-byte aligned");
+    }
+    return SLAFB_OK;
+}
+
+int check_params(slafb_ctx *ctx, const slafb_params *p) {
+    if (!p) return fail(ctx, SLAFB_ERR_INVALID, "params is NULL");
+    if (p->mode < 0 || p->mode > 3) return fail(ctx, SLAFB_ERR_INVALID, "unknown mode %d", p->mode);
+    if (p->max_genes < 1) return fail(ctx, SLAFB_ERR_INVALID, "max_genes must be >= 1, got %d", p->max_genes);
+    if (p->max_items < 1) return fail(ctx, SLAFB_ERR_INVALID, "max_items must be >= 1, got %d", p->max_items);
+    if (p->mode >= SLAFB_SCGPT_RAW && p->n_bins < 1) return fail(ctx, SLAFB_ERR_INVALID, "n_bins must be >= 1");
+    if (p->mode == SLAFB_GENEFORMER_PCT && !(p->min_percentile >= 0.0 && p->min_percentile <= 100.0))
+        return fail(ctx, SLAFB_ERR_INVALID, "min_percentile must be within [0, 100]");
+    return SLAFB_OK;
+}
+
+// accumulate the event timings of a slot's previous use (events are complete: ev_done was waited on)
+void harvest(slafb_ctx *ctx, Slot &s) {
+    float ms;
+    if (s.timed_h2d && cudaEventElapsedTime(&ms, s.t_h2d0, s.t_h2d1) == cudaSuccess) ctx->acc.h2d_ms += ms;
+    if (s.timed_front && cudaEventElapsedTime(&ms, s.t_k1a, s.t_k1b) == cudaSuccess) ctx->acc.csr_ms += ms;
+    if (s.timed_back) {
+        if (cudaEventElapsedTime(&ms, s.t_k2a, s.t_k2b) == cudaSuccess) ctx->acc.tokenize_ms += ms;
+        if (cudaEventElapsedTime(&ms, s.t_k2b, s.t_k2c) == cudaSuccess) ctx->acc.slowpath_ms += ms;
+        ctx->acc.slow_cells += s.all_general ? (int64_t)s.h_counters[0] : (int64_t)s.h_counters[2];
+    }
+    s.timed_front = s.timed_back = s.timed_h2d = false;
+}
+
+int ensure_staging(slafb_ctx *ctx, Slot &s) {
+    if (s.in_cell) return SLAFB_OK;
+    const size_t n = (size_t)ctx->max_rows + 64;
+    CU(ctx, cudaMalloc(&s.in_cell, n * 4));
+    CU(ctx, cudaMalloc(&s.in_gene, n * 4));
+    CU(ctx, cudaMalloc(&s.in_value, n * 4));
+    return SLAFB_OK;
+}
+
+int ensure_sort_scratch(slafb_ctx *ctx) {
+    if (ctx->sort_scratch) return SLAFB_OK;
+    CU(ctx, cudaMalloc(&ctx->sort_scratch, ((size_t)ctx->max_rows + 64) * 4));
+    return SLAFB_OK;
+}
+
+// ---- kernel dispatch over (gene dtype, value dtype, mode) -------------------------------------
+template <typename GeneT, typename ValT, int MODE>
+int launch_fast(slafb_ctx *ctx, const TokArgs &a, cudaStream_t st) {
+    tokenize_cells_kernel<GeneT, ValT, MODE><<<a.n_cells, kTokThreads, 0, st>>>(a);
+    CU(ctx, cudaGetLastError());
+    ctx->acc.kernel_launches++;
+    return SLAFB_OK;
+}
+
+template <typename GeneT, typename ValT, int MODE, int SINK>
+int launch_general(slafb_ctx *ctx, const TokArgs &a, const WindowSink &w, cudaStream_t st) {
+    auto kern = tokenize_general_kernel<GeneT, ValT, MODE, SINK>;
+    const size_t dyn = (sizeof(ValT) == 2) ? (size_t)kBitmapWords * 4 : (size_t)kSortSmemKeys * 4;
+    static bool attr_set[64] = {false};  // per instantiation, per device
+    if (!attr_set[ctx->device & 63]) {
+        CU(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        attr_set[ctx->device & 63] = true;
+    }
+    uint32_t grid = (uint32_t)ctx->n_sm * 2u;
+    if (a.n_cells < grid) grid = a.n_cells;
+    if (grid == 0) grid = 1;
+    kern<<<grid, kTokThreads, dyn, st>>>(a, w);
+    CU(ctx, cudaGetLastError());
+    ctx->acc.kernel_launches++;
+    return SLAFB_OK;
+}
+
+template <typename GeneT, typename ValT>
+int dispatch_fast(slafb_ctx *ctx, int mode, const TokArgs &a, cudaStream_t st) {
+    switch (mode) {
+    case MODE_GF: return launch_fast<GeneT, ValT, MODE_GF>(ctx, a, st);
+    case MODE_SCGPT_RAW: return launch_fast<GeneT, ValT, MODE_SCGPT_RAW>(ctx, a, st);
+    case MODE_SCGPT_BINNED: return launch_fast<GeneT, ValT, MODE_SCGPT_BINNED>(ctx, a, st);
+    default: return SLAFB_OK;  // percentile mode has no fast kernel
+    }
+}
+template <typename GeneT, typename ValT, int SINK>
+int dispatch_general(slafb_ctx *ctx, int mode, const TokArgs &a, const WindowSink &w, cudaStream_t st) {
+    switch (mode) {
+    case MODE_GF: return launch_general<GeneT, ValT, MODE_GF, SINK>(ctx, a, w, st);
+    case MODE_GF_PCT: return launch_general<GeneT, ValT, MODE_GF_PCT, SINK>(ctx, a, w, st);
+    case MODE_SCGPT_RAW: return launch_general<GeneT, ValT, MODE_SCGPT_RAW, SINK>(ctx, a, w, st);
+    default: return launch_general<GeneT, ValT, MODE_SCGPT_BINNED, SINK>(ctx, a, w, st);
+    }
+}
+
+#define DISPATCH_TYPES(gene_dt, val_dt, CALL)                                                    \
+    do {                                                                                         \
+        if ((gene_dt) == SLAFB_U16) {                                                            \
+            if ((val_dt) == SLAFB_U16) { using GeneT = uint16_t; using ValT = uint16_t; CALL; } \
+            else { using GeneT = uint16_t; using ValT = float; CALL; }                           \
+        } else {                                                                                 \
+            if ((val_dt) == SLAFB_U16) { using GeneT = int32_t; using ValT = uint16_t; CALL; }  \
+            else { using GeneT = int32_t; using ValT = float; CALL; }                            \
+        }                                                                                        \
+    } while (0)
+
+void fill_tok_args(slafb_ctx *ctx, Slot &s, const slafb_params *p, TokArgs &a, uint32_t n_cells, bool use_perm) {
+    memset(&a, 0, sizeof a);
+    a.gene = s.gene;
+    a.value = s.value;
+    a.n_rows = (uint32_t)s.n_rows;
+    a.seg_start = s.seg_start;
+    a.seg_cell = s.seg_cell;
+    a.perm = use_perm ? s.perm_dev : nullptr;
+    a.n_cells = n_cells;
+    a.cell_signed = (s.cell_dtype == SLAFB_I32);
+    a.max_items = (uint32_t)p->max_items;
+    a.max_genes = (uint32_t)p->max_genes;
+    a.L = (p->mode >= SLAFB_SCGPT_RAW) ? (uint32_t)p->max_genes + 2u : (uint32_t)p->max_genes;
+    a.n_bins = p->n_bins;
+    a.vocab = p->vocab_size;
+    a.min_pct = p->min_percentile;
+    a.bin_size = (float)(1.0 / (double)(p->n_bins > 0 ? p->n_bins : 1));  // tokenizers.py:508 then float32 at :531
+    a.log1p_lut = ctx->log1p_lut;
+    a.work_list = s.work_list;
+    a.work_counters = s.counters + 2;
+    a.sort_scratch = ctx->sort_scratch;
+    a.all_cells = 0;
+}
+
+// front half: (H2D) + K1 + count read-back, on the side stream
+int front(slafb_ctx *ctx, Slot &s, const slafb_coo *in, cudaStream_t caller) {
+    int rc = check_coo(ctx, in);
+    if (rc) return rc;
+    if (s.ev_done) {
+        // the slot's scratch may still be read by the previous batch's tokenization
+        CU(ctx, cudaEventSynchronize(s.ev_done));
+        harvest(ctx, s);
+    }
+    s.n_rows = in->n_rows;
+    s.cell_dtype = in->cell_dtype;
+    s.gene_dtype = in->gene_dtype;
+    s.value_dtype = in->value_dtype;
+    s.h_counters[0] = 0;
+    s.h_counters[1] = 0;
+    if (in->n_rows == 0) {
+        CU(ctx, cudaEventRecord(s.ev_front, ctx->s_in));
+        return SLAFB_OK;
+    }
+    CU(ctx, cudaEventRecord(s.ev_in, caller));
+    CU(ctx, cudaStreamWaitEvent(ctx->s_in, s.ev_in, 0));
+    if (in->location == SLAFB_LOC_HOST) {
+        rc = ensure_staging(ctx, s);
+        if (rc) return rc;
+        CU(ctx, cudaEventRecord(s.t_h2d0, ctx->s_in));
+        CU(ctx, cudaMemcpyAsync(s.in_cell, in->cell, (size_t)in->n_rows * 4, cudaMemcpyHostToDevice, ctx->s_in));
+        CU(ctx, cudaMemcpyAsync(s.in_gene, in->gene, (size_t)in->n_rows * dtype_size(in->gene_dtype), cudaMemcpyHostToDevice, ctx->s_in));
+        CU(ctx, cudaMemcpyAsync(s.in_value, in->value, (size_t)in->n_rows * dtype_size(in->value_dtype), cudaMemcpyHostToDevice, ctx->s_in));
+        CU(ctx, cudaEventRecord(s.t_h2d1, ctx->s_in));
+        s.timed_h2d = true;
+        s.cell = s.in_cell; s.gene = s.in_gene; s.value = s.in_value;
+    } else {
+        s.cell = in->cell; s.gene = in->gene; s.value = in->value;
+    }
+    CsrArgs k{};
+    k.cell = static_cast<const uint32_t *>(s.cell);
+    k.n_rows = (uint32_t)in->n_rows;
+    k.max_cells = (uint32_t)ctx->max_cells;
+    k.seg_start = s.seg_start;
+    k.seg_cell = s.seg_cell;
+    k.tile_state = ctx->tile_state;
+    k.ticket = ctx->ticket;
+    k.ticket_base = ctx->ticket_base;
+    ctx->epoch = (ctx->epoch + 1u) & 0x3fffffffu;
+    if (ctx->epoch == 0) {  // 2^30 launches: restart the epoch space
+        const size_t n_tiles_max = ((size_t)ctx->max_rows + kCsrTile - 1) / kCsrTile + 1;
+        CU(ctx, cudaMemsetAsync(ctx->tile_state, 0, n_tiles_max * sizeof(unsigned long long), ctx->s_in));
+        ctx->epoch = 1;
+    }
+    k.epoch = ctx->epoch;
+    k.n_cells_out = s.counters;
+    k.work_counters = s.counters + 2;
+    const uint32_t n_tiles = (uint32_t)((in->n_rows + kCsrTile - 1) / kCsrTile);
+    CU(ctx, cudaEventRecord(s.t_k1a, ctx->s_in));
+    csr_build_kernel<<<n_tiles, kCsrThreads, 0, ctx->s_in>>>(k);
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaEventRecord(s.t_k1b, ctx->s_in));
+    s.timed_front = true;
+    ctx->ticket_base += n_tiles;
+    ctx->acc.kernel_launches++;
+    CU(ctx, cudaMemcpyAsync(s.h_counters, s.counters, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->s_in));
+    CU(ctx, cudaEventRecord(s.ev_front, ctx->s_in));
+    return SLAFB_OK;
+}
+
+// waits for the cell count; builds + uploads the permutation.  Returns n_cells through *n.
+int middle(slafb_ctx *ctx, Slot &s, const slafb_params *p, int64_t *n, cudaStream_t st, bool *use_perm) {
+    CU(ctx, cudaEventSynchronize(s.ev_front));
+    if (s.h_counters[1]) {
+        *n = s.h_counters[0];
+        return fail(ctx, SLAFB_ERR_CAPACITY, "batch has %u cells, context max_cells is %lld", s.h_counters[0], (long long)ctx->max_cells);
+    }
+    const int64_t C = s.h_counters[0];
+    *n = C;
+    *use_perm = false;
+    if (C == 0) return SLAFB_OK;
+    if (p->shuffle == SLAFB_SHUFFLE_SEED) {
+        py_shuffle_perm(p->seed, C, s.h_perm);
+        *use_perm = true;
+    } else if (p->shuffle == SLAFB_SHUFFLE_PERM) {
+        if (!p->perm || p->n_perm != C) return fail(ctx, SLAFB_ERR_INVALID, "perm length %lld != number of cells %lld", (long long)p->n_perm, (long long)C);
+        for (int64_t i = 0; i < C; i++) {
+            if (p->perm[i] < 0 || p->perm[i] >= C) return fail(ctx, SLAFB_ERR_INVALID, "perm[%lld] out of range", (long long)i);
+            s.h_perm[i] = p->perm[i];
+        }
+        *use_perm = true;
+    }
+    CU(ctx, cudaStreamWaitEvent(st, s.ev_front, 0));
+    if (*use_perm) CU(ctx, cudaMemcpyAsync(s.perm_dev, s.h_perm, (size_t)C * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    return SLAFB_OK;
+}
+
+int back(slafb_ctx *ctx, Slot &s, const slafb_params *p, const slafb_out *out, int64_t *n_cells, cudaStream_t st) {
+    int rc = check_params(ctx, p);
+    if (rc) return rc;
+    if (!out || !n_cells) return fail(ctx, SLAFB_ERR_INVALID, "out / n_cells is NULL");
+    bool use_perm = false;
+    rc = middle(ctx, s, p, n_cells, st, &use_perm);
+    if (rc) return rc;
+    const int64_t C = *n_cells;
+    if (C == 0) { CU(ctx, cudaEventRecord(s.ev_done, st)); return SLAFB_OK; }
+    if (C > out->capacity_cells) return fail(ctx, SLAFB_ERR_CAPACITY, "batch has %lld cells, output capacity is %lld", (long long)C, (long long)out->capacity_cells);
+    const bool scgpt = p->mode >= SLAFB_SCGPT_RAW;
+    if (!out->input_ids || !out->attention_mask || !out->cell_ids || (scgpt && !out->values))
+        return fail(ctx, SLAFB_ERR_INVALID, "NULL output tensor");
+    if (((uintptr_t)out->input_ids | (uintptr_t)out->attention_mask | (scgpt ? (uintptr_t)out->values : 0)) & 15u)
+        return fail(ctx, SLAFB_ERR_INVALID, "output tensors must be 16-byte aligned");
+    if (s.value_dtype == SLAFB_F32 || p->mode == SLAFB_GENEFORMER_PCT) {
+        rc = ensure_sort_scratch(ctx);
+        if (rc) return rc;
+    }
+    TokArgs a;
+    fill_tok_args(ctx, s, p, a, (uint32_t)C, use_perm);
+    a.ids = reinterpret_cast<long long *>(out->input_ids);
+    a.mask = out->attention_mask;
+    a.vals = reinterpret_cast<long long *>(out->values);
+    a.cell_ids = reinterpret_cast<long long *>(out->cell_ids);
+    WindowSink none{};
+    CU(ctx, cudaEventRecord(s.t_k2a, st));
+    if (p->mode != SLAFB_GENEFORMER_PCT) {
+        DISPATCH_TYPES(s.gene_dtype, s.value_dtype, rc = (dispatch_fast<GeneT, ValT>(ctx, p->mode, a, st)));
+        if (rc) return rc;
+    } else {
+        a.all_cells = 1;
+    }
+    CU(ctx, cudaEventRecord(s.t_k2b, st));
+    DISPATCH_TYPES(s.gene_dtype, s.value_dtype, rc = (dispatch_general<GeneT, ValT, 0>(ctx, p->mode, a, none, st)));
+    if (rc) return rc;
+    CU(ctx, cudaEventRecord(s.t_k2c, st));
+    CU(ctx, cudaMemcpyAsync(s.h_counters + 2, s.counters + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    s.all_general = (p->mode == SLAFB_GENEFORMER_PCT);
+    s.timed_back = true;
+    CU(ctx, cudaEventRecord(s.ev_done, st));
+    ctx->acc.batches++;
+    ctx->acc.cells += C;
+    ctx->acc.rows += s.n_rows;
+    return SLAFB_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int slafb_version(void) { return SLAFB_ABI_VERSION; }
+
+const char *slafb_last_error(const slafb_ctx *ctx) { return ctx ? ctx->err : g_err; }
+
+int slafb_shuffle_perm(int64_t seed, int64_t n, int32_t *perm) {
+    if (n < 0 || (n > 0 && !perm) || n > 0x7fffffff) return fail(nullptr, SLAFB_ERR_INVALID, "bad shuffle arguments");
+    py_shuffle_perm(seed, n, perm);
+    return SLAFB_OK;
+}
+
+int slafb_host_alloc(void **ptr, size_t bytes) {
+    if (!ptr) return fail(nullptr, SLAFB_ERR_INVALID, "ptr is NULL");
+    CU(nullptr, cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    return SLAFB_OK;
+}
+int slafb_host_free(void *ptr) {
+    if (ptr) CU(nullptr, cudaFreeHost(ptr));
+    return SLAFB_OK;
+}
+
+int slafb_create(slafb_ctx **out, int device, int64_t max_rows, int64_t max_cells) {
+    if (!out) return fail(nullptr, SLAFB_ERR_INVALID, "ctx out pointer is NULL");
+    *out = nullptr;
+    if (max_rows < 1 || max_rows > 0x7ffffff0ll) return fail(nullptr, SLAFB_ERR_INVALID, "max_rows must be in [1, 2^31)");
+    if (max_cells < 1 || max_cells > max_rows) max_cells = max_rows;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
+        return fail(nullptr, SLAFB_ERR_NO_DEVICE, "no CUDA device visible: libslaf_b200 has no CPU fallback");
+    if (device < 0 || device >= n_dev) return fail(nullptr, SLAFB_ERR_INVALID, "device %d out of range (%d visible)", device, n_dev);
+    cudaDeviceProp prop;
+    CU(nullptr, cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(nullptr, SLAFB_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    CU(nullptr, cudaSetDevice(device));
+    slafb_ctx *ctx = new (std::nothrow) slafb_ctx();
+    if (!ctx) return fail(nullptr, SLAFB_ERR_INVALID, "out of host memory");
+    ctx->device = device;
+    ctx->n_sm = prop.multiProcessorCount;
+    ctx->max_rows = max_rows;
+    ctx->max_cells = max_cells;
+#define CUC(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { int rc__ = fail(nullptr, SLAFB_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__)); slafb_destroy(ctx); return rc__; } } while (0)
+    CUC(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+    const size_t n_tiles_max = ((size_t)max_rows + kCsrTile - 1) / kCsrTile + 1;
+    CUC(cudaMalloc(&ctx->tile_state, n_tiles_max * sizeof(unsigned long long)));
+    CUC(cudaMemset(ctx->tile_state, 0, n_tiles_max * sizeof(unsigned long long)));
+    CUC(cudaMalloc(&ctx->ticket, sizeof(uint32_t)));
+    CUC(cudaMemset(ctx->ticket, 0, sizeof(uint32_t)));
+    // log1p table for uint16 values through the HOST libm (glibc log1p, the function Rust std /
+    // polars calls), so the binned window is bit-exact without trusting the device's log1p.
+    {
+        double *h = (double *)malloc(65536 * sizeof(double));
+        if (!h) { slafb_destroy(ctx); return fail(nullptr, SLAFB_ERR_INVALID, "out of host memory"); }
+        for (int i = 0; i < 65536; i++) h[i] = log1p((double)i);
+        cudaError_t e1 = cudaMalloc(&ctx->log1p_lut, 65536 * sizeof(double));
+        cudaError_t e2 = e1 == cudaSuccess ? cudaMemcpy(ctx->log1p_lut, h, 65536 * sizeof(double), cudaMemcpyHostToDevice) : e1;
+        free(h);
+        CUC(e2);
+    }
+    CUC(cudaMalloc(&ctx->kept_count, ((size_t)max_cells + 1) * sizeof(uint32_t)));
+    CUC(cudaMalloc(&ctx->total_dev, sizeof(long long)));
+    CUC(cudaHostAlloc(&ctx->h_total, sizeof(long long), cudaHostAllocDefault));
+    for (int i = 0; i < kSlots; i++) {
+        Slot &s = ctx->slot[i];
+        CUC(cudaMalloc(&s.seg_start, ((size_t)max_cells + 2) * sizeof(uint32_t)));
+        CUC(cudaMalloc(&s.seg_cell, ((size_t)max_cells + 1) * sizeof(uint32_t)));
+        CUC(cudaMalloc(&s.perm_dev, ((size_t)max_cells + 1) * sizeof(int32_t)));
+        CUC(cudaMalloc(&s.work_list, ((size_t)max_cells + 1) * sizeof(uint32_t)));
+        CUC(cudaMalloc(&s.counters, 4 * sizeof(uint32_t)));
+        CUC(cudaMemset(s.counters, 0, 4 * sizeof(uint32_t)));
+        CUC(cudaHostAlloc(&s.h_counters, 4 * sizeof(uint32_t), cudaHostAllocDefault));
+        CUC(cudaHostAlloc(&s.h_perm, ((size_t)max_cells + 1) * sizeof(int32_t), cudaHostAllocDefault));
+        cudaEvent_t *plain[] = {&s.ev_front, &s.ev_done, &s.ev_in};
+        for (auto e : plain) CUC(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        cudaEvent_t *timed[] = {&s.t_h2d0, &s.t_h2d1, &s.t_k1a, &s.t_k1b, &s.t_k2a, &s.t_k2b, &s.t_k2c};
+        for (auto e : timed) CUC(cudaEventCreate(e));
+        CUC(cudaEventRecord(s.ev_done, ctx->s_in));
+    }
+#undef CUC
+    *out = ctx;
+    return SLAFB_OK;
+}
+
+int slafb_destroy(slafb_ctx *ctx) {
+    if (!ctx) return SLAFB_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->s_in) cudaStreamSynchronize(ctx->s_in);
+    for (int i = 0; i < kSlots; i++) {
+        Slot &s = ctx->slot[i];
+        if (s.ev_done) cudaEventSynchronize(s.ev_done);
+        cudaFree(s.seg_start); cudaFree(s.seg_cell); cudaFree(s.perm_dev); cudaFree(s.work_list); cudaFree(s.counters);
+        cudaFree(s.in_cell); cudaFree(s.in_gene); cudaFree(s.in_value);
+        if (s.h_counters) cudaFreeHost(s.h_counters);
+        if (s.h_perm) cudaFreeHost(s.h_perm);
+        cudaEvent_t evs[] = {s.ev_front, s.ev_done, s.ev_in, s.t_h2d0, s.t_h2d1, s.t_k1a, s.t_k1b, s.t_k2a, s.t_k2b, s.t_k2c};
+        for (auto e : evs) if (e) cudaEventDestroy(e);
+    }
+    cudaFree(ctx->tile_state); cudaFree(ctx->ticket); cudaFree(ctx->log1p_lut); cudaFree(ctx->sort_scratch);
+    cudaFree(ctx->kept_count); cudaFree(ctx->total_dev);
+    if (ctx->h_total) cudaFreeHost(ctx->h_total);
+    if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+    delete ctx;
+    return SLAFB_OK;
+}
+
+int slafb_submit(slafb_ctx *ctx, const slafb_coo *in, void *stream, int32_t *slot) {
+    if (!ctx || !slot) return fail(ctx, SLAFB_ERR_INVALID, "ctx / slot is NULL");
+    CU(ctx, cudaSetDevice(ctx->device));
+    const int i = ctx->next_slot;
+    Slot &s = ctx->slot[i];
+    if (s.in_flight) return fail(ctx, SLAFB_ERR_BUSY, "pipeline slot %d not collected yet", i);
+    int rc = front(ctx, s, in, static_cast<cudaStream_t>(stream));
+    if (rc) return rc;
+    s.in_flight = true;
+    ctx->next_slot = (i + 1) % kSlots;
+    *slot = i;
+    return SLAFB_OK;
+}
+
+int slafb_collect(slafb_ctx *ctx, int32_t slot, const slafb_params *p, const slafb_out *out, int64_t *n_cells, void *stream) {
+    if (!ctx || slot < 0 || slot >= kSlots) return fail(ctx, SLAFB_ERR_INVALID, "bad ctx / slot");
+    CU(ctx, cudaSetDevice(ctx->device));
+    Slot &s = ctx->slot[slot];
+    if (!s.in_flight) return fail(ctx, SLAFB_ERR_INVALID, "slot %d has no submitted batch", slot);
+    const int rc = back(ctx, s, p, out, n_cells, static_cast<cudaStream_t>(stream));
+    // output tensors too small: the CSR of this slot is still valid, so the caller may
+    // re-collect with larger tensors; every other outcome releases the slot
+    const bool retryable = (rc == SLAFB_ERR_CAPACITY) && n_cells && (*n_cells <= ctx->max_cells);
+    if (!retryable) s.in_flight = false;
+    return rc;
+}
+
+int slafb_tokenize(slafb_ctx *ctx, const slafb_coo *in, const slafb_params *p, const slafb_out *out, int64_t *n_cells, void *stream) {
+    int32_t slot = -1;
+    int rc = slafb_submit(ctx, in, stream, &slot);
+    if (rc) return rc;
+    return slafb_collect(ctx, slot, p, out, n_cells, stream);
+}
+
+int slafb_window(slafb_ctx *ctx, const slafb_coo *in, const slafb_params *p, int64_t *cell_ids, int64_t *offsets,
+                 int64_t *gene_list, double *expr_list, int64_t capacity_cells, int64_t *n_cells, int64_t *n_items,
+                 void *stream) {
+    if (!ctx || !n_cells || !n_items) return fail(ctx, SLAFB_ERR_INVALID, "NULL argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = check_params(ctx, p);
+    if (rc) return rc;
+    Slot &s = ctx->slot[ctx->next_slot];
+    if (s.in_flight) return fail(ctx, SLAFB_ERR_BUSY, "pipeline slot busy");
+    rc = front(ctx, s, in, st);
+    if (rc) return rc;
+    bool use_perm = false;
+    rc = middle(ctx, s, p, n_cells, st, &use_perm);
+    if (rc) return rc;
+    const int64_t C = *n_cells;
+    *n_items = 0;
+    if (C == 0) { CU(ctx, cudaEventRecord(s.ev_done, st)); return SLAFB_OK; }
+    if (C > capacity_cells) return fail(ctx, SLAFB_ERR_CAPACITY, "batch has %lld cells, output capacity is %lld", (long long)C, (long long)capacity_cells);
+    const bool scgpt = p->mode >= SLAFB_SCGPT_RAW;
+    if (!cell_ids || !offsets || !gene_list || (scgpt && !expr_list)) return fail(ctx, SLAFB_ERR_INVALID, "NULL output");
+    rc = ensure_sort_scratch(ctx);
+    if (rc) return rc;
+    TokArgs a;
+    fill_tok_args(ctx, s, p, a, (uint32_t)C, use_perm);
+    a.all_cells = 1;
+    WindowSink w{};
+    w.kept_count = ctx->kept_count;
+    w.offsets = reinterpret_cast<const long long *>(offsets);
+    w.gene_list = reinterpret_cast<long long *>(gene_list);
+    w.expr_list = expr_list;
+    // pass A: kept rows per cell
+    CU(ctx, cudaMemsetAsync(s.counters + 3, 0, sizeof(uint32_t), st));
+    DISPATCH_TYPES(s.gene_dtype, s.value_dtype, rc = (dispatch_general<GeneT, ValT, 1>(ctx, p->mode, a, w, st)));
+    if (rc) return rc;
+    scan_counts_kernel<<<1, 1024, 0, st>>>(ctx->kept_count, reinterpret_cast<long long *>(offsets), (uint32_t)C, ctx->total_dev);
+    CU(ctx, cudaGetLastError());
+    // pass B: flat lists at the scanned offsets
+    CU(ctx, cudaMemsetAsync(s.counters + 3, 0, sizeof(uint32_t), st));
+    DISPATCH_TYPES(s.gene_dtype, s.value_dtype, rc = (dispatch_general<GeneT, ValT, 2>(ctx, p->mode, a, w, st)));
+    if (rc) return rc;
+    cell_ids_kernel<<<(unsigned)((C + 255) / 256), 256, 0, st>>>(s.seg_cell, use_perm ? s.perm_dev : nullptr, (uint32_t)C,
+                                                                 s.cell_dtype == SLAFB_I32, reinterpret_cast<long long *>(cell_ids));
+    CU(ctx, cudaGetLastError());
+    ctx->acc.kernel_launches += 2;
+    CU(ctx, cudaMemcpyAsync(ctx->h_total, ctx->total_dev, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaEventRecord(s.ev_done, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    *n_items = *ctx->h_total;
+    return SLAFB_OK;
+}
+
+int slafb_tokenize_lists(slafb_ctx *ctx, int32_t scgpt, const int64_t *offsets, const int64_t *genes, const double *exprs,
+                         int32_t exprs_are_int, int64_t n_lists, int32_t max_genes, int32_t n_bins, int64_t vocab_size,
+                         const slafb_out *out, void *stream) {
+    if (!ctx || !out) return fail(ctx, SLAFB_ERR_INVALID, "NULL argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (max_genes < 1) return fail(ctx, SLAFB_ERR_INVALID, "max_genes must be >= 1, got %d", max_genes);
+    if (n_lists < 0 || n_lists > out->capacity_cells) return fail(ctx, SLAFB_ERR_CAPACITY, "n_lists %lld exceeds output capacity %lld", (long long)n_lists, (long long)out->capacity_cells);
+    if (n_lists == 0) return SLAFB_OK;
+    if (!offsets || !genes || (scgpt && !exprs) || !out->input_ids || !out->attention_mask || (scgpt && !out->values))
+        return fail(ctx, SLAFB_ERR_INVALID, "NULL tensor");
+    if (scgpt && n_bins < 1) return fail(ctx, SLAFB_ERR_INVALID, "n_bins must be >= 1");
+    ListArgs a{};
+    a.offsets = reinterpret_cast<const long long *>(offsets);
+    a.genes = reinterpret_cast<const long long *>(genes);
+    a.exprs = exprs;
+    a.exprs_are_int = exprs_are_int;
+    a.scgpt = scgpt;
+    a.n_lists = (uint32_t)n_lists;
+    a.max_genes = (uint32_t)max_genes;
+    a.L = scgpt ? (uint32_t)max_genes + 2u : (uint32_t)max_genes;
+    a.n_bins = n_bins;
+    a.vocab = vocab_size;
+    a.bin_size = (float)(1.0 / (double)(n_bins > 0 ? n_bins : 1));
+    a.ids = reinterpret_cast<long long *>(out->input_ids);
+    a.mask = out->attention_mask;
+    a.vals = reinterpret_cast<long long *>(out->values);
+    tokenize_lists_kernel<<<(unsigned)n_lists, kTokThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    CU(ctx, cudaGetLastError());
+    ctx->acc.kernel_launches++;
+    return SLAFB_OK;
+}
+
+int slafb_gene_stats(slafb_ctx *ctx, const slafb_coo *in, int64_t n_genes, uint64_t *sum, uint64_t *cnt, void *stream) {
+    if (!ctx || !sum || !cnt) return fail(ctx, SLAFB_ERR_INVALID, "NULL argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    int rc = check_coo(ctx, in);
+    if (rc) return rc;
+    if (in->location != SLAFB_LOC_DEVICE) return fail(ctx, SLAFB_ERR_INVALID, "gene_stats takes device-resident columns");
+    if (n_genes < 1 || n_genes > 0x7fffffff) return fail(ctx, SLAFB_ERR_INVALID, "bad n_genes");
+    if (in->n_rows == 0) return SLAFB_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const unsigned grid = (unsigned)ctx->n_sm * 8u;
+    auto *usum = reinterpret_cast<unsigned long long *>(sum);
+    auto *ucnt = reinterpret_cast<unsigned long long *>(cnt);
+    DISPATCH_TYPES(in->gene_dtype, in->value_dtype,
+                   (gene_stats_kernel<GeneT, ValT><<<grid, 256, 0, st>>>(static_cast<const GeneT *>(in->gene), static_cast<const ValT *>(in->value),
+                                                                       (uint32_t)in->n_rows, (uint32_t)n_genes, usum, ucnt)));
+    CU(ctx, cudaGetLastError());
+    ctx->acc.kernel_launches++;
+    return SLAFB_OK;
+}
+
+int slafb_get_timing(slafb_ctx *ctx, slafb_timing *t) {
+    if (!ctx || !t) return fail(ctx, SLAFB_ERR_INVALID, "NULL argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(ctx->s_in));
+    for (int i = 0; i < kSlots; i++) {
+        Slot &s = ctx->slot[i];
+        if (s.in_flight) continue;
+        CU(ctx, cudaEventSynchronize(s.ev_done));
+        harvest(ctx, s);
+    }
+    *t = ctx->acc;
+    memset(&ctx->acc, 0, sizeof ctx->acc);
+    return SLAFB_OK;
+}
+
+}  // extern "C"

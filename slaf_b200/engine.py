@@ -1,0 +1,286 @@
+"""HotPathEngine: thin Python owner of one libslaf_b200 context.
+
+PyTorch is plumbing here -- it allocates the output tensors and supplies the CUDA stream;
+every computation of the hot path happens in the sm_100a kernels behind the C ABI
+(include/slaf_b200.h).  One engine per (feeder thread, device).
+"""
+
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Any
+
+import numpy as np
+import torch
+
+from . import _native as N
+
+_NP_DT = {np.dtype(np.uint16): N.U16, np.dtype(np.int32): N.I32, np.dtype(np.uint32): N.U32, np.dtype(np.float32): N.F32}
+_TORCH_DT = {torch.uint16: N.U16, torch.int32: N.I32, torch.uint32: N.U32, torch.float32: N.F32}
+MODES = {"geneformer": N.GENEFORMER, "geneformer_pct": N.GENEFORMER_PCT, "scgpt_raw": N.SCGPT_RAW, "scgpt_binned": N.SCGPT_BINNED}
+
+
+@dataclass
+class TokenizedBatch:
+    """Device-resident result of one prefetch batch (rows already in shuffled order)."""
+
+    input_ids: torch.Tensor              # int64 [C, L]
+    attention_mask: torch.Tensor         # bool  [C, L]
+    values: torch.Tensor | None          # int64 [C, L] (scGPT) or None
+    cell_ids: torch.Tensor               # int64 [C]
+    n_cells: int
+
+
+@dataclass
+class WindowResult:
+    cell_ids: torch.Tensor               # int64 [C]
+    offsets: torch.Tensor                # int64 [C+1]
+    genes: torch.Tensor                  # int64 [K]
+    exprs: torch.Tensor | None           # float64 [K]
+
+
+class _Column:
+    """pointer + dtype code + location of one COO column (numpy array or torch tensor)."""
+
+    def __init__(self, x: Any, allowed: tuple[int, ...], name: str):
+        if isinstance(x, torch.Tensor):
+            if not x.is_contiguous():
+                x = x.contiguous()
+            if x.dtype not in _TORCH_DT:
+                raise TypeError(f"{name}: unsupported dtype {x.dtype}")
+            self.code = _TORCH_DT[x.dtype]
+            self.ptr = x.data_ptr()
+            self.n = x.numel()
+            self.location = N.LOC_DEVICE if x.is_cuda else N.LOC_HOST
+            self.device_index = x.device.index if x.is_cuda else None
+        else:
+            x = np.ascontiguousarray(x)
+            if x.dtype not in _NP_DT:
+                raise TypeError(f"{name}: unsupported dtype {x.dtype}")
+            self.code = _NP_DT[x.dtype]
+            self.ptr = x.ctypes.data
+            self.n = x.size
+            self.location = N.LOC_HOST
+            self.device_index = None
+        if self.code not in allowed:
+            raise TypeError(f"{name}: dtype code {self.code} not allowed for this column")
+        self.keep = x
+
+
+def _coo(cell: Any, gene: Any, value: Any) -> tuple[N.Coo, tuple]:
+    c = _Column(cell, (N.U32, N.I32), "cell_integer_id")
+    g = _Column(gene, (N.U16, N.I32, N.U32), "gene_integer_id")
+    v = _Column(value, (N.U16, N.F32), "value")
+    if not (c.n == g.n == v.n):
+        raise ValueError(f"column lengths differ: {c.n}, {g.n}, {v.n}")
+    if not (c.location == g.location == v.location):
+        raise ValueError("COO columns must all be on the host or all on the device")
+    coo = N.Coo(c.ptr or None, g.ptr or None, v.ptr or None, c.n, c.code, g.code, v.code, c.location)
+    return coo, (c, g, v)
+
+
+class HotPathEngine:
+    """Owns a slafb_ctx.  Not thread-safe (the C context is single-threaded by contract)."""
+
+    def __init__(self, device: int | torch.device | str = 0, max_rows: int = 1 << 25, max_cells: int | None = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("slaf_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        dev = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
+        if dev.type != "cuda":
+            raise RuntimeError(f"slaf_b200 computes on CUDA devices only, got {dev}")
+        self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
+        self.max_rows = int(max_rows)
+        self.max_cells = int(max_cells if max_cells is not None else max_rows)
+        self._L = N.lib()
+        torch.cuda.init()
+        with torch.cuda.device(self.device):
+            torch.cuda.current_stream().synchronize()  # make sure the primary context exists
+            ctx = ctypes.c_void_p()
+            N.check(self._L.slafb_create(ctypes.byref(ctx), self.device.index, self.max_rows, self.max_cells))
+        self._ctx = ctx
+        self._cap_hint = 0
+        self._pending: dict[int, tuple] = {}
+
+    # ------------------------------------------------------------------ lifecycle
+    def close(self) -> None:
+        if getattr(self, "_ctx", None):
+            self._L.slafb_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    # ------------------------------------------------------------------ helpers
+    def _params(self, mode: str, max_genes: int, max_items: int | None, n_bins: int, vocab_size: int,
+                min_percentile: float | None, shuffle_seed: int | None, perm) -> tuple[N.Params, Any]:
+        if mode not in MODES:
+            raise ValueError(f"unknown mode {mode!r}")
+        if max_genes < 1:
+            raise ValueError(f"max_genes must be >= 1, got {max_genes}")
+        p = N.Params()
+        p.mode = MODES[mode]
+        p.max_genes = int(max_genes)
+        p.max_items = int(max_items if max_items is not None else max_genes)
+        p.n_bins = int(n_bins)
+        p.vocab_size = int(vocab_size)
+        p.min_percentile = float(min_percentile) if min_percentile is not None else 0.0
+        keep = None
+        if perm is not None:
+            keep = np.ascontiguousarray(np.asarray(perm, np.int32))
+            p.shuffle = N.SHUFFLE_PERM
+            p.perm = keep.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+            p.n_perm = keep.size
+        elif shuffle_seed is not None:
+            p.shuffle = N.SHUFFLE_SEED
+            p.seed = int(shuffle_seed)
+        else:
+            p.shuffle = N.SHUFFLE_NONE
+        return p, keep
+
+    def _alloc_out(self, cap: int, L: int, scgpt: bool):
+        dev = self.device
+        ids = torch.empty((cap, L), dtype=torch.int64, device=dev)
+        mask = torch.empty((cap, L), dtype=torch.bool, device=dev)
+        vals = torch.empty((cap, L), dtype=torch.int64, device=dev) if scgpt else None
+        cids = torch.empty((cap,), dtype=torch.int64, device=dev)
+        out = N.Out(ids.data_ptr(), mask.data_ptr(), vals.data_ptr() if scgpt else None, cids.data_ptr(), cap)
+        return out, (ids, mask, vals, cids)
+
+    # ------------------------------------------------------------------ the hot path
+    def submit(self, cell: Any, gene: Any, value: Any) -> int:
+        """Enqueue H2D (host columns) + CSR build on the side stream; returns the slot."""
+        coo, keep = _coo(cell, gene, value)
+        slot = ctypes.c_int32(-1)
+        with torch.cuda.device(self.device):
+            N.check(self._L.slafb_submit(self._ctx, ctypes.byref(coo), self._stream(), ctypes.byref(slot)), self._ctx)
+        self._pending[slot.value] = (keep, coo.n_rows)
+        return slot.value
+
+    def collect(self, slot: int, *, mode: str, max_genes: int, max_items: int | None = None, n_bins: int = 10,
+                vocab_size: int = 50000, min_percentile: float | None = None, shuffle_seed: int | None = None,
+                perm=None, capacity_cells: int | None = None) -> TokenizedBatch:
+        keep, n_rows = self._pending.pop(slot)
+        p, pkeep = self._params(mode, max_genes, max_items, n_bins, vocab_size, min_percentile, shuffle_seed, perm)
+        scgpt = p.mode >= N.SCGPT_RAW
+        L = max_genes + 2 if scgpt else max_genes
+        cap = capacity_cells or self._cap_hint or max(64, min(self.max_cells, n_rows // 256 + 64))
+        cap = max(1, min(cap, self.max_cells))
+        n = ctypes.c_int64(0)
+        with torch.cuda.device(self.device):
+            while True:
+                out, tensors = self._alloc_out(cap, L, scgpt)
+                rc = self._L.slafb_collect(self._ctx, slot, ctypes.byref(p), ctypes.byref(out), ctypes.byref(n), self._stream())
+                if rc == N.ERR_CAPACITY and cap < n.value <= self.max_cells:
+                    cap = int(n.value)  # outputs were too small: the slot kept its CSR, retry once
+                    continue
+                N.check(rc, self._ctx)
+                break
+        C = int(n.value)
+        self._cap_hint = max(self._cap_hint, min(self.max_cells, C + C // 8 + 16))
+        ids, mask, vals, cids = tensors
+        del keep, pkeep
+        return TokenizedBatch(ids[:C], mask[:C], vals[:C] if scgpt else None, cids[:C], C)
+
+    def tokenize(self, cell: Any, gene: Any, value: Any, **kw) -> TokenizedBatch:
+        """shuffle -> window -> tokenize -> cell ids for one batch of complete cells
+        (reference: slaf/ml/datasets.py:1011-1098)."""
+        return self.collect(self.submit(cell, gene, value), **kw)
+
+    # ------------------------------------------------------------------ facades
+    def window(self, cell: Any, gene: Any, value: Any, *, mode: str, max_items: int, n_bins: int = 10,
+               min_percentile: float | None = None, shuffle_seed: int | None = None, perm=None) -> WindowResult:
+        """Window.apply as flat list columns (reference: slaf/ml/aggregators.py:26-50)."""
+        coo, keep = _coo(cell, gene, value)
+        p, pkeep = self._params(mode, max_items, max_items, n_bins, 0, min_percentile, shuffle_seed, perm)
+        R = coo.n_rows
+        cap = max(1, min(self.max_cells, R))
+        dev = self.device
+        cids = torch.empty((cap,), dtype=torch.int64, device=dev)
+        offs = torch.zeros((cap + 1,), dtype=torch.int64, device=dev)
+        genes = torch.empty((max(R, 1),), dtype=torch.int64, device=dev)
+        scgpt = p.mode >= N.SCGPT_RAW
+        exprs = torch.empty((max(R, 1),), dtype=torch.float64, device=dev) if scgpt else None
+        n = ctypes.c_int64(0)
+        k = ctypes.c_int64(0)
+        with torch.cuda.device(self.device):
+            N.check(self._L.slafb_window(self._ctx, ctypes.byref(coo), ctypes.byref(p), cids.data_ptr(), offs.data_ptr(),
+                                         genes.data_ptr(), exprs.data_ptr() if scgpt else None, cap,
+                                         ctypes.byref(n), ctypes.byref(k), self._stream()), self._ctx)
+        del keep, pkeep
+        C, K = int(n.value), int(k.value)
+        return WindowResult(cids[:C], offs[: C + 1], genes[:K], exprs[:K] if scgpt else None)
+
+    def tokenize_lists(self, offsets: torch.Tensor, genes: torch.Tensor, exprs: torch.Tensor | None, *, scgpt: bool,
+                       exprs_are_int: bool, max_genes: int, n_bins: int = 10, vocab_size: int = 50000):
+        """SLAFTokenizer.tokenize on flattened device lists (reference: slaf/ml/tokenizers.py:375-479, 635-722)."""
+        B = offsets.numel() - 1
+        L = max_genes + 2 if scgpt else max_genes
+        out, (ids, mask, vals, _c) = self._alloc_out(max(B, 1), L, scgpt)
+        with torch.cuda.device(self.device):
+            N.check(self._L.slafb_tokenize_lists(self._ctx, int(scgpt), offsets.data_ptr(), genes.data_ptr(),
+                                                 exprs.data_ptr() if (scgpt and exprs is not None) else None,
+                                                 int(exprs_are_int), B, max_genes, n_bins, vocab_size,
+                                                 ctypes.byref(out), self._stream()), self._ctx)
+        return ids[:B], mask[:B], (vals[:B] if scgpt else None)
+
+    def gene_stats(self, gene: torch.Tensor, value: torch.Tensor, n_genes: int, sum_out: torch.Tensor | None = None,
+                   cnt_out: torch.Tensor | None = None):
+        """Accumulate per-gene nonzero sum / count into uint64-as-int64 device tensors (extension)."""
+        dev = self.device
+        if sum_out is None:
+            sum_out = torch.zeros(n_genes, dtype=torch.int64, device=dev)
+        if cnt_out is None:
+            cnt_out = torch.zeros(n_genes, dtype=torch.int64, device=dev)
+        cell_dummy = torch.empty(gene.numel(), dtype=torch.int32, device=dev)
+        coo, keep = _coo(cell_dummy, gene, value)
+        with torch.cuda.device(self.device):
+            N.check(self._L.slafb_gene_stats(self._ctx, ctypes.byref(coo), n_genes, sum_out.data_ptr(), cnt_out.data_ptr(),
+                                             self._stream()), self._ctx)
+        del keep
+        return sum_out, cnt_out
+
+    def timing(self) -> dict[str, float]:
+        t = N.Timing()
+        with torch.cuda.device(self.device):
+            N.check(self._L.slafb_get_timing(self._ctx, ctypes.byref(t)), self._ctx)
+        return {f: getattr(t, f) for f, _ in N.Timing._fields_}
+
+
+def shuffle_perm(seed: int, n: int) -> np.ndarray:
+    """CPython random.seed(seed); random.shuffle(list(range(n))) via the library's host C code."""
+    perm = np.empty(n, np.int32)
+    N.check(N.lib().slafb_shuffle_perm(int(seed), int(n), perm.ctypes.data))
+    return perm
+
+
+def pinned_empty(n: int, dtype) -> np.ndarray:
+    """numpy array over cudaHostAlloc'ed memory (freed when the array is garbage collected)."""
+    dtype = np.dtype(dtype)
+    ptr = ctypes.c_void_p()
+    nbytes = max(1, n * dtype.itemsize)
+    N.check(N.lib().slafb_host_alloc(ctypes.byref(ptr), nbytes))
+    buf = (ctypes.c_char * nbytes).from_address(ptr.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=n)
+
+    class _Owner:
+        def __init__(self, p):
+            self.p = p
+
+        def __del__(self):
+            try:
+                N.lib().slafb_host_free(self.p)
+            except Exception:
+                pass
+
+    _OWNERS[arr.ctypes.data] = _Owner(ptr)
+    return arr
+
+
+_OWNERS: dict[int, Any] = {}
