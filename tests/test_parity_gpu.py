@@ -1,0 +1,241 @@
+"""GPU parity tests: the sm_100a kernels, called through the C ABI, against the CPU oracle on
+the same seeded inputs.  Bit-exact (integer / byte / index work): no tolerance anywhere."""
+
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle
+from slaf_b200 import _native, synthetic
+from tests.util import adversarial_batch, assert_same
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = np.load(os.path.join(HERE, "golden", "tokenizer_golden.npz"))
+KATS = json.load(open(os.path.join(HERE, "golden", "window_kats.json")))["cases"]
+
+MODES = [("geneformer", None), ("geneformer_pct", 37.5), ("scgpt_raw", None), ("scgpt_binned", None)]
+
+
+def py_perm(seed, n):
+    random.seed(seed)
+    idx = list(range(n))
+    random.shuffle(idx)
+    return idx
+
+
+def to_dev(a):
+    return torch.from_numpy(a).cuda()
+
+
+def compare(batch, want, mode):
+    ids, mask, vals, cids = want
+    assert batch.n_cells == len(cids)
+    assert batch.input_ids.dtype == torch.int64 and batch.attention_mask.dtype == torch.bool
+    assert batch.cell_ids.dtype == torch.int64
+    assert_same(batch.cell_ids.cpu().numpy(), cids, "cell_ids")
+    assert_same(batch.input_ids.cpu().numpy(), ids, "input_ids")
+    assert_same(batch.attention_mask.cpu().numpy(), mask, "attention_mask")
+    if mode.startswith("scgpt"):
+        assert batch.values.dtype == torch.int64
+        assert_same(batch.values.cpu().numpy(), vals, "values")
+    else:
+        assert batch.values is None and vals is None
+
+
+@pytest.mark.parametrize("location", ["device", "host"])
+@pytest.mark.parametrize("gene_dtype,cell_dtype", [("uint16", "uint32"), ("int32", "int32")])
+@pytest.mark.parametrize("value_dtype", ["uint16", "float32"])
+@pytest.mark.parametrize("mode,pct", MODES)
+def test_adversarial_cells_all_modes(engine, mode, pct, value_dtype, gene_dtype, cell_dtype, location):
+    k = 64
+    cell, gene, value = adversarial_batch(11, value_dtype, gene_dtype, cell_dtype, k=k)
+    C = len(np.unique(cell))
+    seed = 42 + 17
+    want = c_oracle.tokenize(cell, gene, value, mode, k, perm=py_perm(seed, C), n_bins=51, vocab_size=65000, min_percentile=pct)
+    cols = (to_dev(cell), to_dev(gene), to_dev(value)) if location == "device" else (cell, gene, value)
+    got = engine.tokenize(*cols, mode=mode, max_genes=k, n_bins=51, vocab_size=65000, min_percentile=pct, shuffle_seed=seed)
+    compare(got, want, mode)
+
+
+@pytest.mark.parametrize("mode,pct", MODES)
+@pytest.mark.parametrize("k,max_genes", [(1, 1), (2, 7), (5, 3), (2048, 2048), (1200, 1200), (300, 2048)])
+def test_width_and_k_combinations(engine, mode, pct, k, max_genes):
+    """max_items != max_genes, tiny widths (CLS only / SEP dropped), odd L (unaligned rows)."""
+    cell, gene, value = adversarial_batch(5, "uint16", "uint16", "uint32", k=max(k, 8) if k < 1000 else 40, big=(k >= 300))
+    want = c_oracle.tokenize(cell, gene, value, mode, max_genes, max_items=k, n_bins=10, vocab_size=50000, min_percentile=pct)
+    got = engine.tokenize(to_dev(cell), to_dev(gene), to_dev(value), mode=mode, max_genes=max_genes, max_items=k,
+                          n_bins=10, vocab_size=50000, min_percentile=pct)
+    compare(got, want, mode)
+
+
+@pytest.mark.parametrize("n_bins", [1, 2, 3, 5, 10, 51, 1000])
+@pytest.mark.parametrize("value_dtype", ["uint16", "float32"])
+def test_binning_all_bin_counts(engine, n_bins, value_dtype):
+    cell, gene, value = adversarial_batch(23, value_dtype, "uint16", "uint32", k=32, big=False)
+    for mode in ("scgpt_binned", "scgpt_raw"):
+        want = c_oracle.tokenize(cell, gene, value, mode, 32, n_bins=n_bins, vocab_size=1000)
+        got = engine.tokenize(cell, gene, value, mode=mode, max_genes=32, n_bins=n_bins, vocab_size=1000)
+        compare(got, want, mode)
+
+
+def test_explicit_perm_and_identity(engine):
+    cell, gene, value = adversarial_batch(3, "uint16", "uint16", "uint32", k=16, big=False)
+    C = len(np.unique(cell))
+    perm = np.random.default_rng(0).permutation(C)
+    want = c_oracle.tokenize(cell, gene, value, "geneformer", 16, perm=perm)
+    got = engine.tokenize(cell, gene, value, mode="geneformer", max_genes=16, perm=perm)
+    compare(got, want, "geneformer")
+    want = c_oracle.tokenize(cell, gene, value, "geneformer", 16)
+    got = engine.tokenize(cell, gene, value, mode="geneformer", max_genes=16)
+    compare(got, want, "geneformer")
+
+
+@pytest.mark.parametrize("cfg", ["cfg1_geneformer", "cfg2_scgpt_binned", "scgpt_raw_default", "float32_geneformer"])
+def test_synthetic_configs_full_compare(engine, cfg):
+    """BASELINE.json configs 1 and 2 at a size the oracle finishes in seconds (every cell compared)."""
+    if cfg == "cfg1_geneformer":
+        b = synthetic.make_batch(1500, 20000, 2000, seed=1)
+        kw = dict(mode="geneformer", max_genes=2048)
+    elif cfg == "cfg2_scgpt_binned":
+        b = synthetic.make_batch(1500, 60000, 2000, seed=2)
+        kw = dict(mode="scgpt_binned", max_genes=1200, n_bins=51, vocab_size=65000)
+    elif cfg == "scgpt_raw_default":
+        b = synthetic.make_batch(1500, 60000, 2000, seed=4)
+        kw = dict(mode="scgpt_raw", max_genes=1200, n_bins=51, vocab_size=65000)
+    else:
+        b = synthetic.make_batch(800, 62000, 2500, seed=5, value_dtype="float32")
+        kw = dict(mode="geneformer", max_genes=2048)
+    seed = 42 + 0
+    okw = {("n_bins" if k == "n_bins" else k): v for k, v in kw.items() if k != "mode"}
+    want = c_oracle.tokenize(b.cell, b.gene, b.value, kw["mode"], perm=py_perm(seed, b.n_cells), **okw)
+    got = engine.tokenize(to_dev(b.cell), to_dev(b.gene), to_dev(b.value), shuffle_seed=seed, **kw)
+    compare(got, want, kw["mode"])
+    t = engine.timing()
+    assert t["kernel_launches"] >= 2
+
+
+def test_pipelined_submit_collect_two_in_flight(engine):
+    """submit(i+1) before collect(i): results must not depend on the overlap."""
+    batches = [synthetic.make_batch(300 + 50 * i, 30000, 600, seed=100 + i) for i in range(5)]
+    kw = dict(mode="scgpt_binned", max_genes=512, n_bins=51, vocab_size=65000)
+    slots = [engine.submit(batches[0].cell, batches[0].gene, batches[0].value)]
+    outs = []
+    for i in range(len(batches)):
+        if i + 1 < len(batches):
+            nb = batches[i + 1]
+            slots.append(engine.submit(nb.cell, nb.gene, nb.value))
+        outs.append(engine.collect(slots[i], shuffle_seed=42 + i, **kw))
+    for i, (b, got) in enumerate(zip(batches, outs)):
+        want = c_oracle.tokenize(b.cell, b.gene, b.value, "scgpt_binned", 512, perm=py_perm(42 + i, b.n_cells), n_bins=51, vocab_size=65000)
+        compare(got, want, "scgpt_binned")
+
+
+def test_output_capacity_retry_and_errors(engine):
+    b = synthetic.make_batch(200, 5000, 100, seed=9)
+    got = engine.collect(engine.submit(b.cell, b.gene, b.value), mode="geneformer", max_genes=64, capacity_cells=3)
+    want = c_oracle.tokenize(b.cell, b.gene, b.value, "geneformer", 64)
+    compare(got, want, "geneformer")
+    with pytest.raises(ValueError, match="max_genes must be >= 1"):
+        engine.tokenize(b.cell, b.gene, b.value, mode="geneformer", max_genes=0)
+    with pytest.raises(TypeError):
+        engine.tokenize(b.cell.astype(np.int64), b.gene, b.value, mode="geneformer", max_genes=8)
+    with pytest.raises(_native.SlafB200Error) as ei:
+        engine.tokenize(b.cell, b.gene, b.value, mode="geneformer_pct", max_genes=8, min_percentile=150.0)
+    assert ei.value.code == _native.ERR_INVALID
+    # empty frame -> zero rows, not an error (reference tests/test_aggregators.py:133-144)
+    e = engine.tokenize(np.zeros(0, np.uint32), np.zeros(0, np.uint16), np.zeros(0, np.uint16), mode="geneformer", max_genes=8)
+    assert e.n_cells == 0 and tuple(e.input_ids.shape) == (0, 8)
+
+
+# ------------------------------------------------------------------------ facades
+def _lists(offs, flat):
+    return [flat[offs[i]:offs[i + 1]].tolist() for i in range(len(offs) - 1)]
+
+
+@pytest.mark.parametrize("case", KATS, ids=[c["cite"][:48] for c in KATS])
+def test_window_facade_reference_kats(engine, case):
+    cell = np.asarray(case["cell"], np.int32)
+    gene = np.asarray(case["gene"], np.int32)
+    value = np.asarray(case["value"], case["value_dtype"])
+    w = engine.window(cell, gene, value, mode=case["mode"], max_items=case["max_items"], n_bins=case["n_bins"])
+    offs = w.offsets.cpu().numpy()
+    assert w.cell_ids.cpu().tolist() == case["expect_cells"]
+    assert _lists(offs, w.genes.cpu().numpy()) == case["expect_genes"]
+    if "expect_exprs" in case:
+        assert _lists(offs, w.exprs.cpu().numpy()) == [[float(x) for x in r] for r in case["expect_exprs"]]
+    if "expect_bin_range" in case:
+        lo, hi = case["expect_bin_range"]
+        assert all(lo <= x < hi for x in w.exprs.cpu().tolist())
+
+
+@pytest.mark.parametrize("value_dtype", ["uint16", "float32"])
+@pytest.mark.parametrize("mode,pct", MODES)
+def test_window_facade_vs_oracle(engine, mode, pct, value_dtype):
+    k = 48
+    cell, gene, value = adversarial_batch(31, value_dtype, "int32", "int32", k=k)
+    C = len(np.unique(cell))
+    perm = py_perm(7, C)
+    cids, offs, genes, exprs = c_oracle.window(cell, gene, value, mode, k, perm=perm, n_bins=51, min_percentile=pct)
+    w = engine.window(cell, gene, value, mode=mode, max_items=k, n_bins=51, min_percentile=pct, shuffle_seed=7)
+    assert_same(w.cell_ids.cpu().numpy(), cids, "cell ids")
+    assert_same(w.offsets.cpu().numpy(), offs, "offsets")
+    assert_same(w.genes.cpu().numpy(), genes, "genes")
+    if mode.startswith("scgpt"):
+        assert_same(w.exprs.cpu().numpy(), exprs, "exprs")
+
+
+@pytest.mark.parametrize("tag", ["gf8", "gf64", "gf2048"])
+def test_tokenizer_facade_reference_golden_geneformer(engine, tag):
+    offs, genes = to_dev(GOLD[f"{tag}_offsets"]), to_dev(GOLD[f"{tag}_genes"])
+    ids, mask, vals = engine.tokenize_lists(offs, genes, None, scgpt=False, exprs_are_int=True, max_genes=int(GOLD[f"{tag}_max_genes"]))
+    assert vals is None
+    assert_same(ids.cpu().numpy(), GOLD[f"{tag}_ids"], "ids")
+    assert_same(mask.cpu().numpy(), GOLD[f"{tag}_mask"], "mask")
+
+
+@pytest.mark.parametrize("tag,is_int", [("sgi4", True), ("sgi1200", True), ("sgf_bins", False), ("sgf_bins10", False),
+                                        ("sgf_raw", False), ("sgf_raw5", False)])
+def test_tokenizer_facade_reference_golden_scgpt(engine, tag, is_int):
+    mg, vocab, nb = (int(x) for x in GOLD[f"{tag}_cfg"])
+    offs, genes, exprs = to_dev(GOLD[f"{tag}_offsets"]), to_dev(GOLD[f"{tag}_genes"]), to_dev(GOLD[f"{tag}_exprs"])
+    ids, mask, vals = engine.tokenize_lists(offs, genes, exprs, scgpt=True, exprs_are_int=is_int, max_genes=mg, n_bins=nb, vocab_size=vocab)
+    assert_same(ids.cpu().numpy(), GOLD[f"{tag}_ids"], "ids")
+    assert_same(mask.cpu().numpy(), GOLD[f"{tag}_mask"], "mask")
+    assert_same(vals.cpu().numpy(), GOLD[f"{tag}_vals"], "vals")
+
+
+def test_gene_stats_vs_oracle(engine):
+    b = synthetic.make_batch(400, 3000, 300, seed=77)
+    s, c = engine.gene_stats(to_dev(b.gene), to_dev(b.value), 3000)
+    want_s = np.bincount(b.gene.astype(np.int64), weights=b.value.astype(np.float64), minlength=3000).astype(np.int64)
+    want_c = np.bincount(b.gene.astype(np.int64), minlength=3000)
+    assert_same(s.cpu().numpy(), want_s, "sum")
+    assert_same(c.cpu().numpy(), want_c, "count")
+
+
+# ------------------------------------------------------------------------ full-size properties
+def test_large_batch_properties_and_full_compare(engine):
+    """A 4M-row prefetch batch (reference default prefetch_batch_size): size-independent
+    properties on every row plus a full oracle comparison (the C oracle does this in seconds)."""
+    b = synthetic.make_batch(2000, 60000, 2000, seed=2)
+    kw = dict(mode="scgpt_binned", max_genes=1200, n_bins=51, vocab_size=65000)
+    got = engine.tokenize(to_dev(b.cell), to_dev(b.gene), to_dev(b.value), shuffle_seed=42, **kw)
+    ids, vals, mask = got.input_ids, got.values, got.attention_mask
+    assert (ids[:, 0] == 1).all()
+    assert ((ids != 0) == mask).all()
+    assert ((ids == 2).sum(1) == 1).all()                       # exactly one SEP per scGPT row
+    n_tok = mask.sum(1)
+    sep_pos = (ids == 2).float().argmax(1)
+    assert (sep_pos == n_tok - 1).all()                          # SEP is the last non-PAD token
+    assert (vals[:, 0] == 0).all() and (vals[~mask] == 0).all()
+    inner = vals[mask]
+    assert ((inner == 0) | (inner == 65000 + 50)).all()          # binned path collapses to {PAD, top bin}
+    assert sorted(got.cell_ids.cpu().tolist()) == list(range(2000))   # every cell exactly once
+    want = c_oracle.tokenize(b.cell, b.gene, b.value, "scgpt_binned", 1200, perm=py_perm(42, 2000), n_bins=51, vocab_size=65000)
+    compare(got, want, "scgpt_binned")
