@@ -71,6 +71,10 @@ class ClockSampler:
 
     def start(self):
         try:
+            probe = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                   capture_output=True, text=True, timeout=20)
+            if probe.returncode != 0 or "not a valid field" in (probe.stdout + probe.stderr).lower():
+                self.Q = self.Q.replace("clocks_event_reasons", "clocks_throttle_reasons")
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
@@ -258,20 +262,25 @@ def main():
     host_cols = [tuple(torch.from_numpy(a).pin_memory() for a in (b.cell, b.gene, b.value)) for b in batches]
     tot_rows = [b.n_rows for b in batches]
 
-    def run_steps(cols, n_steps, read_result):
-        """pipelined: submit(i+1) precedes collect(i).  Returns (#cells, #rows, d2h bytes)."""
+    def run_steps(cols, n_steps, read_result, depth=2):
+        """pipelined: up to `depth` submits (H2D + CSR build) run ahead of the collect of the
+        oldest batch.  Returns (#cells, #rows, d2h bytes)."""
+        from collections import deque
+
         cells = rows = d2h = 0
-        slot = eng.submit(*cols[0])
+        q = deque()
+        nxt = 0
         keep = None
         for i in range(n_steps):
-            nxt = eng.submit(*cols[(i + 1) % NB]) if i + 1 < n_steps else None
-            out = eng.collect(slot, shuffle_seed=42 + i, **kw)
+            while nxt < n_steps and len(q) <= depth:
+                q.append(eng.submit(*cols[nxt % NB]))
+                nxt += 1
+            out = eng.collect(q.popleft(), shuffle_seed=42 + i, **kw)
             cells += out.n_cells
             rows += tot_rows[i % NB]
             if read_result:
                 keep = out.cell_ids.to("cpu", non_blocking=False)   # D2H read of the step's result
                 d2h += 8 + 8 * out.n_cells
-            slot = nxt
         return cells, rows, d2h
 
     # ---- value: inputs resident in HBM

@@ -136,8 +136,8 @@ int slafb_tokenize(slafb_ctx *ctx, const slafb_coo *in, const slafb_params *p, c
 
 /* Same path, pipelined (double buffered): submit() enqueues the H2D copy (host input) and the
  * CSR build on the context's side stream and returns a slot; collect() waits for the cell
- * count, applies the shuffle and launches the tokenizing kernels on `stream`.  Two slots:
- * submit(i+1) may precede collect(i).  Replaces the AsyncPrefetcher hand-off
+ * count, applies the shuffle and launches the tokenizing kernels on `stream`.  Four slots:
+ * up to three submits may precede the collect of the oldest batch.  Replaces the AsyncPrefetcher hand-off
  * (slaf/ml/datasets.py:1242-1294) for the device-side part of the work. */
 int slafb_submit(slafb_ctx *ctx, const slafb_coo *in, void *stream, int32_t *slot);
 int slafb_collect(slafb_ctx *ctx, int32_t slot, const slafb_params *p, const slafb_out *out,

@@ -24,7 +24,7 @@ using namespace slafb;
 
 namespace {
 
-constexpr int kSlots = 2;
+constexpr int kSlots = 4;
 
 struct Slot {
     bool in_flight = false;

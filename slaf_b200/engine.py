@@ -191,6 +191,9 @@ class HotPathEngine:
     def tokenize(self, cell: Any, gene: Any, value: Any, **kw) -> TokenizedBatch:
         """shuffle -> window -> tokenize -> cell ids for one batch of complete cells
         (reference: slaf/ml/datasets.py:1011-1098)."""
+        probe = {k: kw.get(k) for k in ("max_items", "min_percentile", "shuffle_seed", "perm")}
+        self._params(kw["mode"], kw["max_genes"], probe["max_items"], kw.get("n_bins", 10), kw.get("vocab_size", 50000),
+                     probe["min_percentile"], probe["shuffle_seed"], probe["perm"])  # raises before a slot is taken
         return self.collect(self.submit(cell, gene, value), **kw)
 
     # ------------------------------------------------------------------ facades
