@@ -1,12 +1,18 @@
 // kernels.cuh -- sm_100a device code of the SLAF hot path.
 //
-//   K1  csr_build_kernel        COO cell column -> segment table (CSR offsets + cell ids), one pass,
-//                               warp-ballot/shuffle scans + decoupled look-back across tiles.
+//   K1  csr_build_kernel        COO cell column -> segment table (CSR offsets + cell ids), one pass:
+//                               every warp scans one contiguous span of rows (128-bit loads, head
+//                               detection with shuffles/ballots, heads kept in shared memory), one
+//                               decoupled look-back per CTA gives the global offsets.
 //                               Stands in for polars partition_by / group_by(maintain_order=True)
 //                               (reference slaf/ml/samplers.py:93, slaf/ml/aggregators.py:111,190,208).
-//   K2  tokenize_cells_kernel   one CTA per output row: dense-rank<=k filter, row-order compaction,
-//                               log1p binning, token emission with CLS/SEP/PAD, attention mask and
-//                               cell id written straight into the batch tensors.
+//   K2  tokenize_cells_kernel   persistent CTAs, one cell at a time, the NEXT cell's gene/value
+//                               segments staged into shared memory by TMA bulk copies
+//                               (cp.async.bulk + mbarrier, double buffered) while the current cell
+//                               is emitted: dense-rank<=k filter decided from the value range,
+//                               log1p-bin threshold from a per-context table, token pairs with
+//                               CLS/SEP/PAD, attention mask and cell id written straight into the
+//                               batch tensors with 128-bit stores.
 //                               (aggregators.py:87-134,197-214 + tokenizers.py:407-479,666-722
 //                                + datasets.py:1087-1098)
 //   K2g tokenize_general_kernel same emission, but with the exact k-th-distinct-value machinery
@@ -29,8 +35,10 @@ constexpr int kTokThreads = 256;
 constexpr int kGroup = 8;                           // rows per thread per chunk (one 128-bit load of u16)
 constexpr int kChunkRows = kTokThreads * kGroup;    // 2048 rows staged per iteration
 constexpr int kCsrThreads = 256;
-constexpr int kCsrItems = 16;
-constexpr int kCsrTile = kCsrThreads * kCsrItems;   // 4096 rows per tile
+constexpr int kCsrWarps = kCsrThreads / 32;
+constexpr int kCsrListCap = 512;                    // segment heads a warp can keep in shared memory
+constexpr int kFastThreads = 128;                   // K2: threads per persistent CTA
+constexpr int kFastWarps = kFastThreads / 32;
 constexpr int kBitmapWords = 65536 / 32;
 constexpr int kSortSmemKeys = 12288;                // general path: float keys sorted in shared memory up to here
 
@@ -162,10 +170,11 @@ struct CsrArgs {
     const uint32_t *cell;   // uint32 or int32 bits
     uint32_t n_rows;
     uint32_t max_cells;
+    uint32_t rows_per_warp; // multiple of 128
     uint32_t *seg_start;    // [max_cells + 1]
     uint32_t *seg_cell;     // [max_cells]
-    unsigned long long *tile_state;  // [n_tiles] : epoch<<34 | status<<32 | value
-    uint32_t *ticket;       // dynamic tile counter (never reset; host passes the base)
+    unsigned long long *tile_state;  // [grid] : epoch<<34 | status<<32 | value
+    uint32_t *ticket;       // dynamic span counter (never reset; host passes the base)
     uint32_t ticket_base;
     uint32_t epoch;         // 30-bit launch id, so tile_state needs no memset
     uint32_t *n_cells_out;  // [0] = number of segments, [1] = error flags
@@ -177,61 +186,107 @@ __device__ __forceinline__ unsigned long long st_pack(uint32_t epoch, unsigned l
     return ((unsigned long long)epoch << 34) | (status << 32) | (unsigned long long)v;
 }
 
+// head flags (4 bits) of rows r0..r0+3 held by this lane; `prev` = cell id of row r0-1
+__device__ __forceinline__ uint32_t head_flags4(const uint32_t (&c)[4], uint32_t prev, uint32_t r0, uint32_t R) {
+    uint32_t f = 0;
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        const uint32_t r = r0 + e;
+        const uint32_t p = (e == 0) ? prev : c[e - 1];
+        if (r < R && (r == 0 || c[e] != p)) f |= 1u << e;
+    }
+    return f;
+}
+
+__device__ __forceinline__ void load_cells4(const uint32_t *__restrict__ cell, uint32_t r0, uint32_t R, uint32_t (&c)[4]) {
+    if (r0 + 4 <= R) {
+        uint4 q = __ldcs(reinterpret_cast<const uint4 *>(cell + r0));
+        c[0] = q.x; c[1] = q.y; c[2] = q.z; c[3] = q.w;
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; e++) c[e] = (r0 + e < R) ? __ldg(cell + r0 + e) : 0u;
+    }
+}
+
+// Scan one warp's span [w0, w1): returns the number of heads; if `list` is given, the first
+// kCsrListCap head rows are stored in order; if `out_base` != ~0u, heads are written to the
+// segment table directly (replay for spans with more heads than the list holds).
+template <bool REPLAY>
+__device__ __forceinline__ uint32_t scan_span(const CsrArgs &a, uint32_t w0, uint32_t w1, uint32_t *list, uint32_t out_base) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t R = a.n_rows;
+    uint32_t run = 0;
+    for (uint32_t b0 = w0; b0 < w1; b0 += 512) {       // 4 x 128 rows per trip: 4 independent 128-bit loads in flight
+        uint32_t c[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint32_t r0 = b0 + u * 128 + lane * 4;
+            if (r0 < w1) load_cells4(a.cell, r0, R, c[u]);
+            else { c[u][0] = c[u][1] = c[u][2] = c[u][3] = 0u; }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint32_t r0 = b0 + u * 128 + lane * 4;
+            uint32_t prev = __shfl_up_sync(0xffffffffu, c[u][3], 1);   // lanes > 0: the previous lane's last row
+            uint32_t prev0;                                            // lane 0: last row of the previous 128-row block
+            if (u == 0) prev0 = (lane == 0 && r0 > 0 && r0 < R) ? __ldg(a.cell + r0 - 1) : 0u;
+            else prev0 = __shfl_sync(0xffffffffu, c[u > 0 ? u - 1 : 0][3], 31);
+            if (lane == 0) prev = prev0;
+            const uint32_t f = (r0 < w1) ? head_flags4(c[u], prev, r0, R) : 0u;
+            const uint32_t any = __ballot_sync(0xffffffffu, f != 0u);
+            if (any) {                                   // rare: about one head per ~2000 rows
+                const uint32_t cnt = __popc(f);
+                const uint32_t inc = warp_incl_scan(cnt);
+                uint32_t g = run + inc - cnt;
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    if (f & (1u << e)) {
+                        if constexpr (REPLAY) {
+                            const uint32_t o = out_base + g;
+                            if (o < a.max_cells) { a.seg_start[o] = r0 + e; a.seg_cell[o] = c[u][e]; }
+                        } else {
+                            if (g < (uint32_t)kCsrListCap) list[g] = r0 + e;
+                        }
+                        g++;
+                    }
+                }
+                run += __shfl_sync(0xffffffffu, inc, 31);
+            }
+        }
+    }
+    return run;
+}
+
 __global__ void __launch_bounds__(kCsrThreads) csr_build_kernel(const CsrArgs a) {
-    __shared__ uint32_t s_tile;
-    __shared__ uint32_t s_warp_tot[kCsrThreads / 32];
+    __shared__ uint32_t s_list[kCsrWarps][kCsrListCap];
+    __shared__ uint32_t s_cnt[kCsrWarps];
+    __shared__ uint32_t s_span;
     __shared__ uint32_t s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(a.ticket, 1u) - a.ticket_base;
+    if (tid == 0) s_span = atomicAdd(a.ticket, 1u) - a.ticket_base;
     __syncthreads();
-    const uint32_t tile = s_tile;
-    const uint32_t n_tiles = (a.n_rows + kCsrTile - 1) / kCsrTile;
+    const uint32_t span = s_span;
     const uint32_t R = a.n_rows;
+    const unsigned long long wbeg = ((unsigned long long)span * kCsrWarps + warp) * a.rows_per_warp;
+    const uint32_t w0 = wbeg < R ? (uint32_t)wbeg : R;
+    const uint32_t w1 = (wbeg + a.rows_per_warp < R) ? (uint32_t)(wbeg + a.rows_per_warp) : R;
 
-    // each warp owns 512 consecutive rows of the tile: 4 iterations x (32 lanes x 4 rows)
-    const uint32_t warp_row0 = tile * kCsrTile + warp * (kCsrItems * 32);
-    uint32_t flags = 0;            // bit (it*4 + e): row is a segment head
-    uint32_t lane_excl[4];         // heads before this lane's rows inside the warp, per iteration
-    uint32_t warp_run = 0;
-#pragma unroll
-    for (int it = 0; it < 4; it++) {
-        const uint32_t r0 = warp_row0 + it * 128 + lane * 4;
-        uint32_t c[4] = {0, 0, 0, 0};
-        if (r0 + 4 <= R) {
-            uint4 q = __ldg(reinterpret_cast<const uint4 *>(a.cell + r0));
-            c[0] = q.x; c[1] = q.y; c[2] = q.z; c[3] = q.w;
-        } else {
-#pragma unroll
-            for (int e = 0; e < 4; e++) if (r0 + e < R) c[e] = __ldg(a.cell + r0 + e);
-        }
-        uint32_t prev = __shfl_up_sync(0xffffffffu, c[3], 1);
-        if (lane == 0 && r0 > 0 && r0 < R) prev = __ldg(a.cell + r0 - 1);
-        uint32_t f = 0;
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-            const uint32_t r = r0 + e;
-            const uint32_t p = (e == 0) ? prev : c[e - 1];
-            if (r < R && (r == 0 || c[e] != p)) f |= 1u << e;
-        }
-        const uint32_t cnt = __popc(f);
-        const uint32_t inc = warp_incl_scan(cnt);
-        lane_excl[it] = warp_run + inc - cnt;
-        warp_run += __shfl_sync(0xffffffffu, inc, 31);
-        flags |= f << (4 * it);
-    }
-    if (lane == 0) s_warp_tot[warp] = warp_run;
+    // phase A: every warp counts (and remembers) the segment heads of its own contiguous span
+    const uint32_t wcount = scan_span<false>(a, w0, w1, s_list[warp], 0u);
+    if (lane == 0) s_cnt[warp] = wcount;
     __syncthreads();
 
-    // warp 0: tile aggregate, publish, decoupled look-back for the exclusive prefix
+    // phase B: CTA aggregate, publish, decoupled look-back over the preceding CTAs
     if (warp == 0) {
-        uint32_t wv = (lane < kCsrThreads / 32) ? s_warp_tot[lane] : 0u;
+        uint32_t wv = (lane < kCsrWarps) ? s_cnt[lane] : 0u;
         uint32_t winc = warp_incl_scan(wv);
-        const uint32_t tile_total = __shfl_sync(0xffffffffu, winc, kCsrThreads / 32 - 1);
-        if (lane < kCsrThreads / 32) s_warp_tot[lane] = winc - wv;  // exclusive warp bases
+        const uint32_t cta_total = __shfl_sync(0xffffffffu, winc, kCsrWarps - 1);
+        __syncwarp();
+        if (lane < kCsrWarps) s_cnt[lane] = winc - wv;  // exclusive warp bases
         volatile unsigned long long *st = a.tile_state;
-        if (lane == 0) st[tile] = st_pack(a.epoch, tile == 0 ? kStPrefix : kStAgg, tile_total);
+        if (lane == 0) st[span] = st_pack(a.epoch, span == 0 ? kStPrefix : kStAgg, cta_total);
         uint32_t excl = 0;
-        int look = (int)tile - 1;
+        int look = (int)span - 1;
         while (look >= 0) {
             const int idx = look - lane;
             unsigned long long sv;
@@ -252,10 +307,10 @@ __global__ void __launch_bounds__(kCsrThreads) csr_build_kernel(const CsrArgs a)
             look -= 32;
         }
         if (lane == 0) {
-            if (tile != 0) st[tile] = st_pack(a.epoch, kStPrefix, excl + tile_total);
+            if (span != 0) st[span] = st_pack(a.epoch, kStPrefix, excl + cta_total);
             s_base = excl;
-            if (tile == n_tiles - 1) {
-                const uint32_t total = excl + tile_total;
+            if (span == gridDim.x - 1) {
+                const uint32_t total = excl + cta_total;
                 a.n_cells_out[0] = total;
                 a.n_cells_out[1] = (total > a.max_cells) ? 1u : 0u;
                 if (total <= a.max_cells) a.seg_start[total] = R;
@@ -266,25 +321,19 @@ __global__ void __launch_bounds__(kCsrThreads) csr_build_kernel(const CsrArgs a)
     }
     __syncthreads();
 
-    // scatter the (sparse) segment heads in row order
-    if (flags) {
-        const uint32_t base = s_base + s_warp_tot[warp];
-#pragma unroll
-        for (int it = 0; it < 4; it++) {
-            uint32_t f = (flags >> (4 * it)) & 0xfu;
-            uint32_t g = base + lane_excl[it];
-            const uint32_t r0 = warp_row0 + it * 128 + lane * 4;
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-                if (f & (1u << e)) {
-                    if (g < a.max_cells) {
-                        a.seg_start[g] = r0 + e;
-                        a.seg_cell[g] = __ldg(a.cell + r0 + e);
-                    }
-                    g++;
-                }
+    // phase C: write this warp's heads at their global positions (row order is preserved)
+    const uint32_t base = s_base + s_cnt[warp];
+    if (wcount <= (uint32_t)kCsrListCap) {
+        for (uint32_t i = lane; i < wcount; i += 32) {
+            const uint32_t o = base + i;
+            if (o < a.max_cells) {
+                const uint32_t r = s_list[warp][i];
+                a.seg_start[o] = r;
+                a.seg_cell[o] = __ldg(a.cell + r);
             }
         }
+    } else {
+        scan_span<true>(a, w0, w1, nullptr, base);       // too many heads for the list: replay the span
     }
 }
 
@@ -712,11 +761,287 @@ __device__ bool process_cell(const TokArgs &a, const WindowSink &wsnk, uint32_t 
     }
 }
 
+// ---- K2 fast path: persistent CTAs, TMA-staged cell segments ------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// TMA bulk copy global -> shared (1-D, 16-byte aligned, size a multiple of 16), completion on `bar`
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+struct FastArgs {
+    TokArgs t;
+    uint32_t gcap;                // gene stage capacity (rows, multiple of 8)
+    uint32_t vcap;                // value stage capacity (rows, multiple of 8)
+    const uint32_t *vstar_table;  // [65536] smallest uint16 value whose window bin is >= 1, per cell maximum
+};
+
+struct CellDesc {
+    uint32_t s, e, c, a0;
+    uint32_t g_bulk, v_bulk;      // rows staged by the bulk copies, counted from a0 (multiples of 8)
+    uint32_t n_g, n_v;            // rows of the cell the stages must hold (from s)
+};
+
 template <typename GeneT, typename ValT, int MODE>
-__global__ void __launch_bounds__(kTokThreads) tokenize_cells_kernel(const TokArgs a) {
-    __shared__ TokSmem sm;
-    WindowSink none{};
-    process_cell<GeneT, ValT, MODE, false, 0>(a, none, blockIdx.x, sm, nullptr, nullptr);
+__device__ __forceinline__ void fast_issue(const FastArgs &fa, uint32_t c, uint32_t s, uint32_t e, CellDesc *d,
+                                           uint8_t *gstage, uint8_t *vstage, uint64_t *bar) {
+    constexpr bool SCGPT = (MODE == MODE_SCGPT_RAW || MODE == MODE_SCGPT_BINNED);
+    const TokArgs &a = fa.t;
+    const uint32_t n = e - s, a0 = s & ~7u, R8 = a.n_rows & ~7u;
+    const uint32_t limit = SCGPT ? a.max_genes : (a.L - 1u);
+    const bool need_val = SCGPT || (n > a.max_items);
+    const uint32_t n_g = min(n, limit);
+    const uint32_t n_v = need_val ? min(n, fa.vcap - 8u) : 0u;
+    const uint32_t g_end = min((s + n_g + 7u) & ~7u, R8), v_end = min((s + n_v + 7u) & ~7u, R8);
+    const uint32_t g_bulk = (n_g && g_end > a0) ? g_end - a0 : 0u;
+    const uint32_t v_bulk = (n_v && v_end > a0) ? v_end - a0 : 0u;
+    d->s = s; d->e = e; d->c = c; d->a0 = a0;
+    d->g_bulk = g_bulk; d->v_bulk = v_bulk; d->n_g = n_g; d->n_v = n_v;
+    const uint32_t bytes = g_bulk * (uint32_t)sizeof(GeneT) + v_bulk * (uint32_t)sizeof(ValT);
+    if (bytes == 0) {
+        mbar_arrive(bar);
+    } else {
+        mbar_arrive_expect_tx(bar, bytes);
+        if (g_bulk) bulk_g2s(gstage, static_cast<const GeneT *>(a.gene) + a0, g_bulk * (uint32_t)sizeof(GeneT), bar);
+        if (v_bulk) bulk_g2s(vstage, static_cast<const ValT *>(a.value) + a0, v_bulk * (uint32_t)sizeof(ValT), bar);
+    }
+}
+
+template <typename GeneT, typename ValT, int MODE>
+__global__ void __launch_bounds__(kFastThreads) tokenize_cells_kernel(const FastArgs fa) {
+    constexpr bool SCGPT = (MODE == MODE_SCGPT_RAW || MODE == MODE_SCGPT_BINNED);
+    constexpr bool BINNED = (MODE == MODE_SCGPT_BINNED);
+    constexpr bool U16 = (sizeof(ValT) == 2);
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ CellDesc s_desc[2];
+    __shared__ uint32_t s_ws[3 * kFastWarps];
+    const TokArgs &a = fa.t;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t gbytes = fa.gcap * (uint32_t)sizeof(GeneT), vbytes = fa.vcap * (uint32_t)sizeof(ValT);
+    const uint32_t stage_bytes = gbytes + vbytes;   // both multiples of 16
+    const GeneT *__restrict__ gene_g = static_cast<const GeneT *>(a.gene);
+    const ValT *__restrict__ value_g = static_cast<const ValT *>(a.value);
+    const uint32_t R = a.n_rows, R8 = R & ~7u, k = a.max_items, L = a.L;
+    const uint32_t limit = SCGPT ? a.max_genes : (L - 1u);
+
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    uint32_t j = blockIdx.x;
+    const uint32_t G = gridDim.x;
+    // thread 0 walks the segment table two cells ahead of the copies it issues, so neither the
+    // perm -> seg_start dependent loads nor the bulk copies are ever waited on in line
+    uint32_t c1 = 0, s1 = 0, e1 = 0;   // cell j + G
+    uint32_t c2 = 0;                   // permutation entry of cell j + 2G
+    if (tid == 0) {
+        if (j < a.n_cells) {
+            const uint32_t c0 = a.perm ? (uint32_t)__ldg(a.perm + j) : j;
+            fast_issue<GeneT, ValT, MODE>(fa, c0, __ldg(a.seg_start + c0), __ldg(a.seg_start + c0 + 1), &s_desc[0],
+                                          smem_raw, smem_raw + gbytes, &s_bar[0]);
+        }
+        if (j + G < a.n_cells) {
+            c1 = a.perm ? (uint32_t)__ldg(a.perm + j + G) : j + G;
+            s1 = __ldg(a.seg_start + c1);
+            e1 = __ldg(a.seg_start + c1 + 1);
+        }
+        if (j + 2 * G < a.n_cells) c2 = a.perm ? (uint32_t)__ldg(a.perm + j + 2 * G) : j + 2 * G;
+    }
+    uint32_t phase_bits = 0u;   // bit st = parity the next wait on stage st must see
+
+    for (uint32_t it = 0; j < a.n_cells; j += G, it++) {
+        const uint32_t st = it & 1u;
+        // stage st^1 was released by the barrier that ended the previous iteration
+        if (tid == 0) {
+            if (j + G < a.n_cells)
+                fast_issue<GeneT, ValT, MODE>(fa, c1, s1, e1, &s_desc[st ^ 1u], smem_raw + (st ^ 1u) * stage_bytes,
+                                              smem_raw + (st ^ 1u) * stage_bytes + gbytes, &s_bar[st ^ 1u]);
+            c1 = c2;
+            if (j + 2 * G < a.n_cells) { s1 = __ldg(a.seg_start + c1); e1 = __ldg(a.seg_start + c1 + 1); }
+            if (j + 3 * G < a.n_cells) c2 = a.perm ? (uint32_t)__ldg(a.perm + j + 3 * G) : j + 3 * G;
+        }
+        mbar_wait(&s_bar[st], (phase_bits >> st) & 1u);
+        phase_bits ^= 1u << st;
+        const CellDesc d = s_desc[st];
+        GeneT *sg = reinterpret_cast<GeneT *>(smem_raw + st * stage_bytes);
+        ValT *sv = reinterpret_cast<ValT *>(smem_raw + st * stage_bytes + gbytes);
+        const uint32_t s = d.s, e = d.e, n = e - s, a0 = d.a0, sh = s - a0;
+
+        // rows in the last partial 8-group of the column arrays cannot be bulk-copied (16-byte granules)
+        const bool patch = (s + max(d.n_g, d.n_v) > R8);
+        if (patch) {
+            if (tid < 8) {
+                const uint32_t r = R8 + tid;
+                if (r < R && r >= a0) {
+                    if (r < s + d.n_g) sg[r - a0] = gene_g[r];
+                    if (r < s + d.n_v) sv[r - a0] = value_g[r];
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---- statistics of the cell's values (range test for the dense-rank filter, max for the bins)
+        bool keep_all = (n <= k);
+        bool defer = false;
+        uint32_t kmax = 0;
+        float m_f32 = 0.0f;
+        if (BINNED || !keep_all) {
+            uint32_t lo = 0xffffffffu, hi = 0u;
+            float lvmax = -INFINITY;
+            const uint32_t ngroups = (sh + d.n_v + 7u) >> 3;
+            for (uint32_t gi = tid; gi < ngroups; gi += kFastThreads) {
+                const uint32_t r0 = a0 + gi * 8u;
+                if constexpr (U16) {
+                    const uint4 q = *reinterpret_cast<const uint4 *>(sv + gi * 8u);
+                    if (r0 >= s && r0 + 8u <= s + d.n_v) {
+                        uint32_t mn = __vminu2(__vminu2(q.x, q.y), __vminu2(q.z, q.w));
+                        uint32_t mx = __vmaxu2(__vmaxu2(q.x, q.y), __vmaxu2(q.z, q.w));
+                        lo = min(lo, min(mn & 0xffffu, mn >> 16));
+                        hi = max(hi, max(mx & 0xffffu, mx >> 16));
+                    } else {
+                        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            const uint32_t r = r0 + i;
+                            if (r >= s && r < s + d.n_v) {
+                                const uint32_t key = (w[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
+                                lo = min(lo, key);
+                                hi = max(hi, key);
+                            }
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const uint32_t r = r0 + i;
+                        if (r >= s && r < s + d.n_v) {
+                            const float x = sv[gi * 8u + i];
+                            const uint32_t key = key_of(x);
+                            lo = min(lo, key);
+                            hi = max(hi, key);
+                            if constexpr (BINNED) lvmax = fmaxf(lvmax, log1pf_window(x));
+                        }
+                    }
+                }
+            }
+            // rows beyond the value stage (cells larger than vcap): straight from global memory
+            for (uint32_t r = s + d.n_v + tid; r < e; r += kFastThreads) {
+                const ValT x = __ldg(value_g + r);
+                const uint32_t key = key_of(x);
+                lo = min(lo, key);
+                hi = max(hi, key);
+                if constexpr (BINNED && !U16) lvmax = fmaxf(lvmax, log1pf_window((float)x));
+            }
+            lo = __reduce_min_sync(0xffffffffu, lo);
+            hi = __reduce_max_sync(0xffffffffu, hi);
+            uint32_t lk = 0;
+            if constexpr (BINNED && !U16) lk = __reduce_max_sync(0xffffffffu, key_of(lvmax));
+            if (lane == 0) { s_ws[warp] = lo; s_ws[kFastWarps + warp] = hi; s_ws[2 * kFastWarps + warp] = lk; }
+            __syncthreads();
+#pragma unroll
+            for (int w = 0; w < kFastWarps; w++) {
+                lo = min(lo, s_ws[w]);
+                hi = max(hi, s_ws[kFastWarps + w]);
+                lk = max(lk, s_ws[2 * kFastWarps + w]);
+            }
+            if constexpr (BINNED && !U16) m_f32 = float_of_key(lk);   // max(log1pf) over the cell
+            kmax = hi;
+            if (!keep_all) {
+                if (U16 && (hi - lo + 1u <= k)) keep_all = true;   // at most k distinct values fit in [lo, hi]
+                else defer = true;                                  // exact k-th distinct value: general kernel
+            }
+        }
+
+        if (defer) {
+            if (tid == 0) a.work_list[atomicAdd(a.work_counters, 1u)] = j;
+        } else {
+            // ---- emission: token pairs (128-bit stores), value stream, PAD fill, mask, cell id
+            const uint32_t n_emit = min(n, limit);
+            const size_t A = (size_t)j * L;
+            double m_f64 = 0.0;
+            uint32_t vstar = 0xffffffffu;
+            const long long top = a.vocab + (long long)(a.n_bins - 1);
+            if constexpr (BINNED && U16) vstar = __ldg(fa.vstar_table + kmax);
+            (void)m_f64; (void)top; (void)vstar;
+            auto id_tok = [&](long long t) -> long long {
+                if (t == 0) return 1ll;                                        // CLS
+                if (t <= (long long)n_emit) {
+                    if constexpr (sizeof(GeneT) == 2) return (long long)sg[sh + (uint32_t)t - 1u] + 4ll;
+                    else return (long long)(int32_t)sg[sh + (uint32_t)t - 1u] + 4ll;
+                }
+                return (t == (long long)n_emit + 1) ? 2ll : 0ll;               // SEP, then PAD
+            };
+            auto val_tok = [&](long long t) -> long long {
+                if (t < 1 || t > (long long)n_emit) return 0ll;
+                const ValT x = sv[sh + (uint32_t)t - 1u];
+                if constexpr (BINNED && U16) return ((uint32_t)x >= vstar) ? top : 0ll;
+                else return value_token<ValT, MODE>(raw_bits(x), a, m_f64, m_f32);
+            };
+            const size_t q0 = A >> 1, q1 = (A + L + 1) >> 1;
+            for (size_t q = q0 + tid; q < q1; q += kFastThreads) {
+                const long long t0 = (long long)(2 * q) - (long long)A, t1 = t0 + 1;
+                const bool v0 = t0 >= 0, v1 = t1 < (long long)L;
+                const long long x0 = v0 ? id_tok(t0) : 0ll, x1 = v1 ? id_tok(t1) : 0ll;
+                if (v0 && v1) *reinterpret_cast<longlong2 *>(a.ids + 2 * q) = make_longlong2(x0, x1);
+                else if (v0) a.ids[2 * q] = x0;
+                else a.ids[2 * q + 1] = x1;
+                if constexpr (SCGPT) {
+                    const long long y0 = v0 ? val_tok(t0) : 0ll, y1 = v1 ? val_tok(t1) : 0ll;
+                    if (v0 && v1) *reinterpret_cast<longlong2 *>(a.vals + 2 * q) = make_longlong2(y0, y1);
+                    else if (v0) a.vals[2 * q] = y0;
+                    else a.vals[2 * q + 1] = y1;
+                }
+            }
+            fill_mask(a.mask, A, L, min(n_emit + 2u, L));
+            if (tid == 0) {
+                const uint32_t cid = __ldg(a.seg_cell + d.c);
+                a.cell_ids[j] = a.cell_signed ? (long long)(int32_t)cid : (long long)cid;
+            }
+        }
+        __syncthreads();   // every thread is done with stage `st` and the scratch before they are reused
+    }
+}
+
+// table for the binned window on uint16 storage: for a cell whose maximum value is vmax, the
+// smallest value v with  floor(log1p(v) * n_bins / log1p(vmax)) >= 1  (f64, evaluation order of
+// aggregators.py:100-105).  Every such row gets the token vocab + n_bins - 1, every other row PAD
+// (the float branch of ScGPTTokenizer applied to an integral bin >= 1 always clips to the top bin).
+__global__ void vstar_table_kernel(const double *__restrict__ lut, int n_bins, uint32_t *__restrict__ table) {
+    const uint32_t vmax = blockIdx.x * blockDim.x + threadIdx.x;
+    if (vmax > 65535u) return;
+    if (n_bins < 2 || vmax == 0u) { table[vmax] = 0xffffffffu; return; }
+    const double m = lut[vmax], nb = (double)n_bins;
+    uint32_t lo = 1u, hi = vmax;                 // the predicate holds at vmax and is monotone in v
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        const bool ok = __ddiv_rn(__dmul_rn(lut[mid], nb), m) >= 1.0;
+        if (ok) hi = mid; else lo = mid + 1u;
+    }
+    table[vmax] = lo;
 }
 
 // general path: persistent CTAs over the work list (or over all cells)

@@ -62,6 +62,8 @@ struct slafb_ctx {
     uint32_t *ticket = nullptr;
     uint32_t ticket_base = 0, epoch = 0;
     double *log1p_lut = nullptr;
+    uint32_t *vstar_table = nullptr;  // binned window on uint16 storage: bin>=1 threshold per cell maximum
+    int vstar_nbins = -1;
     uint32_t *sort_scratch = nullptr;
     // window facade scratch
     uint32_t *kept_count = nullptr;
@@ -151,11 +153,41 @@ int ensure_sort_scratch(slafb_ctx *ctx) {
 }
 
 // ---- kernel dispatch over (gene dtype, value dtype, mode) -------------------------------------
+// K2 fast path.  Returns 1 when the configuration does not fit the fast kernel (then every cell
+// goes through the general kernel).
 template <typename GeneT, typename ValT, int MODE>
-int launch_fast(slafb_ctx *ctx, const TokArgs &a, cudaStream_t st) {
-    tokenize_cells_kernel<GeneT, ValT, MODE><<<a.n_cells, kTokThreads, 0, st>>>(a);
+int launch_fast(slafb_ctx *ctx, const TokArgs &a, cudaStream_t st, bool *launched) {
+    *launched = false;
+    constexpr bool SCGPT = (MODE == MODE_SCGPT_RAW || MODE == MODE_SCGPT_BINNED);
+    const uint32_t limit = SCGPT ? a.max_genes : (a.L - 1u);
+    FastArgs fa;
+    fa.t = a;
+    fa.gcap = (limit + 15u + 7u) & ~7u;
+    fa.vcap = fa.gcap > 4104u ? fa.gcap : 4104u;
+    fa.vstar_table = ctx->vstar_table;
+    const size_t smem = 2 * ((size_t)fa.gcap * sizeof(GeneT) + (size_t)fa.vcap * sizeof(ValT));
+    if (smem > 200 * 1024) return SLAFB_OK;   // very wide rows: general kernel only
+    auto kern = tokenize_cells_kernel<GeneT, ValT, MODE>;
+    static bool attr_set[64] = {false};
+    if (!attr_set[ctx->device & 63]) {
+        CU(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set[ctx->device & 63] = true;
+    }
+    if (MODE == MODE_SCGPT_BINNED && sizeof(ValT) == 2 && ctx->vstar_nbins != a.n_bins) {
+        vstar_table_kernel<<<256, 256, 0, st>>>(ctx->log1p_lut, a.n_bins, ctx->vstar_table);
+        CU(ctx, cudaGetLastError());
+        ctx->vstar_nbins = a.n_bins;
+        ctx->acc.kernel_launches++;
+    }
+    size_t per_sm = (220 * 1024) / (smem + 1024);
+    if (per_sm > 8) per_sm = 8;
+    if (per_sm < 1) per_sm = 1;
+    uint32_t grid = (uint32_t)(ctx->n_sm * per_sm);
+    if (a.n_cells < grid) grid = a.n_cells;
+    kern<<<grid, kFastThreads, smem, st>>>(fa);
     CU(ctx, cudaGetLastError());
     ctx->acc.kernel_launches++;
+    *launched = true;
     return SLAFB_OK;
 }
 
@@ -178,12 +210,12 @@ int launch_general(slafb_ctx *ctx, const TokArgs &a, const WindowSink &w, cudaSt
 }
 
 template <typename GeneT, typename ValT>
-int dispatch_fast(slafb_ctx *ctx, int mode, const TokArgs &a, cudaStream_t st) {
+int dispatch_fast(slafb_ctx *ctx, int mode, const TokArgs &a, cudaStream_t st, bool *launched) {
     switch (mode) {
-    case MODE_GF: return launch_fast<GeneT, ValT, MODE_GF>(ctx, a, st);
-    case MODE_SCGPT_RAW: return launch_fast<GeneT, ValT, MODE_SCGPT_RAW>(ctx, a, st);
-    case MODE_SCGPT_BINNED: return launch_fast<GeneT, ValT, MODE_SCGPT_BINNED>(ctx, a, st);
-    default: return SLAFB_OK;  // percentile mode has no fast kernel
+    case MODE_GF: return launch_fast<GeneT, ValT, MODE_GF>(ctx, a, st, launched);
+    case MODE_SCGPT_RAW: return launch_fast<GeneT, ValT, MODE_SCGPT_RAW>(ctx, a, st, launched);
+    case MODE_SCGPT_BINNED: return launch_fast<GeneT, ValT, MODE_SCGPT_BINNED>(ctx, a, st, launched);
+    default: *launched = false; return SLAFB_OK;  // percentile mode has no fast kernel
     }
 }
 template <typename GeneT, typename ValT, int SINK>
@@ -276,20 +308,24 @@ int front(slafb_ctx *ctx, Slot &s, const slafb_coo *in, cudaStream_t caller) {
     k.ticket_base = ctx->ticket_base;
     ctx->epoch = (ctx->epoch + 1u) & 0x3fffffffu;
     if (ctx->epoch == 0) {  // 2^30 launches: restart the epoch space
-        const size_t n_tiles_max = ((size_t)ctx->max_rows + kCsrTile - 1) / kCsrTile + 1;
-        CU(ctx, cudaMemsetAsync(ctx->tile_state, 0, n_tiles_max * sizeof(unsigned long long), ctx->s_in));
+        CU(ctx, cudaMemsetAsync(ctx->tile_state, 0, (size_t)ctx->n_sm * 8 * sizeof(unsigned long long), ctx->s_in));
         ctx->epoch = 1;
     }
     k.epoch = ctx->epoch;
     k.n_cells_out = s.counters;
     k.work_counters = s.counters + 2;
-    const uint32_t n_tiles = (uint32_t)((in->n_rows + kCsrTile - 1) / kCsrTile);
+    // one contiguous span of rows per warp (multiple of 128 rows); ~4 CTAs per SM
+    uint32_t grid = (uint32_t)ctx->n_sm * 4u;
+    const uint64_t blocks128 = ((uint64_t)in->n_rows + 127) / 128;
+    if (blocks128 < (uint64_t)grid * kCsrWarps) grid = (uint32_t)((blocks128 + kCsrWarps - 1) / kCsrWarps);
+    const uint64_t warps = (uint64_t)grid * kCsrWarps;
+    k.rows_per_warp = (uint32_t)(((blocks128 + warps - 1) / warps) * 128);
     CU(ctx, cudaEventRecord(s.t_k1a, ctx->s_in));
-    csr_build_kernel<<<n_tiles, kCsrThreads, 0, ctx->s_in>>>(k);
+    csr_build_kernel<<<grid, kCsrThreads, 0, ctx->s_in>>>(k);
     CU(ctx, cudaGetLastError());
     CU(ctx, cudaEventRecord(s.t_k1b, ctx->s_in));
     s.timed_front = true;
-    ctx->ticket_base += n_tiles;
+    ctx->ticket_base += grid;
     ctx->acc.kernel_launches++;
     CU(ctx, cudaMemcpyAsync(s.h_counters, s.counters, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->s_in));
     CU(ctx, cudaEventRecord(s.ev_front, ctx->s_in));
@@ -350,18 +386,18 @@ int back(slafb_ctx *ctx, Slot &s, const slafb_params *p, const slafb_out *out, i
     a.cell_ids = reinterpret_cast<long long *>(out->cell_ids);
     WindowSink none{};
     CU(ctx, cudaEventRecord(s.t_k2a, st));
+    bool fast_launched = false;
     if (p->mode != SLAFB_GENEFORMER_PCT) {
-        DISPATCH_TYPES(s.gene_dtype, s.value_dtype, rc = (dispatch_fast<GeneT, ValT>(ctx, p->mode, a, st)));
+        DISPATCH_TYPES(s.gene_dtype, s.value_dtype, rc = (dispatch_fast<GeneT, ValT>(ctx, p->mode, a, st, &fast_launched)));
         if (rc) return rc;
-    } else {
-        a.all_cells = 1;
     }
+    if (!fast_launched) a.all_cells = 1;
     CU(ctx, cudaEventRecord(s.t_k2b, st));
     DISPATCH_TYPES(s.gene_dtype, s.value_dtype, rc = (dispatch_general<GeneT, ValT, 0>(ctx, p->mode, a, none, st)));
     if (rc) return rc;
     CU(ctx, cudaEventRecord(s.t_k2c, st));
     CU(ctx, cudaMemcpyAsync(s.h_counters + 2, s.counters + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    s.all_general = (p->mode == SLAFB_GENEFORMER_PCT);
+    s.all_general = !fast_launched;
     s.timed_back = true;
     CU(ctx, cudaEventRecord(s.ev_done, st));
     ctx->acc.batches++;
@@ -417,9 +453,10 @@ int slafb_create(slafb_ctx **out, int device, int64_t max_rows, int64_t max_cell
     ctx->max_cells = max_cells;
 #define CUC(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { int rc__ = fail(nullptr, SLAFB_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__)); slafb_destroy(ctx); return rc__; } } while (0)
     CUC(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
-    const size_t n_tiles_max = ((size_t)max_rows + kCsrTile - 1) / kCsrTile + 1;
+    const size_t n_tiles_max = (size_t)ctx->n_sm * 8;
     CUC(cudaMalloc(&ctx->tile_state, n_tiles_max * sizeof(unsigned long long)));
     CUC(cudaMemset(ctx->tile_state, 0, n_tiles_max * sizeof(unsigned long long)));
+    CUC(cudaMalloc(&ctx->vstar_table, 65536 * sizeof(uint32_t)));
     CUC(cudaMalloc(&ctx->ticket, sizeof(uint32_t)));
     CUC(cudaMemset(ctx->ticket, 0, sizeof(uint32_t)));
     // log1p table for uint16 values through the HOST libm (glibc log1p, the function Rust std /
@@ -471,7 +508,7 @@ int slafb_destroy(slafb_ctx *ctx) {
         cudaEvent_t evs[] = {s.ev_front, s.ev_done, s.ev_in, s.t_h2d0, s.t_h2d1, s.t_k1a, s.t_k1b, s.t_k2a, s.t_k2b, s.t_k2c};
         for (auto e : evs) if (e) cudaEventDestroy(e);
     }
-    cudaFree(ctx->tile_state); cudaFree(ctx->ticket); cudaFree(ctx->log1p_lut); cudaFree(ctx->sort_scratch);
+    cudaFree(ctx->tile_state); cudaFree(ctx->ticket); cudaFree(ctx->log1p_lut); cudaFree(ctx->vstar_table); cudaFree(ctx->sort_scratch);
     cudaFree(ctx->kept_count); cudaFree(ctx->total_dev);
     if (ctx->h_total) cudaFreeHost(ctx->h_total);
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
