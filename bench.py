@@ -60,46 +60,60 @@ def algorithmic_bytes(w, n_rows, n_cells):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / power / throttle reasons sampled through NVML while the timed regions run
+    (same fields as the nvidia-smi line in B200_PROFILING.md; nvidia-smi's own output is block
+    buffered on a pipe, so short runs would record nothing)."""
 
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, gpu_index: int):
-        self.gpu = gpu_index
-        self.rows: list[list[str]] = []
-        self.proc = None
+    def __init__(self, gpu_index: int, period_s: float = 0.02):
+        self.gpu, self.period = gpu_index, period_s
+        self.sm, self.power, self.bits = [], [], 0
+        self.sm_max = None
+        self._stop = threading.Event()
+        self._thr = None
+        self.err = None
 
     def start(self):
         try:
-            probe = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
-                                   capture_output=True, text=True, timeout=20)
-            if probe.returncode != 0 or "not a valid field" in (probe.stdout + probe.stderr).lower():
-                self.Q = self.Q.replace("clocks_event_reasons", "clocks_throttle_reasons")
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
+            import pynvml
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu]) if vis and vis.split(",")[self.gpu].isdigit() else self.gpu
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nv = pynvml
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                try:
+                    self.bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    self.bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            except Exception as e:
+                self.err = repr(e)
+                return
+            self._stop.wait(self.period)
 
     def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        sm, smax, reasons, power = [], [], set(), []
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); smax.append(float(r[2])); power.append(float(r[3]))
-            except Exception:
-                continue
-            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
-                if len(r) > col and r[col].lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join(timeout=2)
+        out = {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.sm_max,
+               "power_w_max": max(self.power) if self.power else None, "samples": len(self.sm),
+               "reasons": sorted(n for b, n in self.REASONS.items() if self.bits & b), "source": "nvml"}
+        if self.err:
+            out["error"] = self.err
+        return out
 
 
 # ----------------------------------------------------------------------------- CPU port arm
@@ -296,7 +310,6 @@ def main():
     e1.record()
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
-    clocks = sampler.stop() if rank == 0 else None
     tm = eng.timing()
     total_cells = sum_over_ranks(cells)
     value = total_cells / (ms / 1000.0)
@@ -318,6 +331,7 @@ def main():
                "d2h_bytes_per_step": d2h_e // args.steps, "ms_per_step": 1000.0 * dt / args.steps,
                "h2d_gbs_per_gpu": h2d_bytes / dt / 1e9, "h2d_copy_gbs": (h2d_bytes / (tme["h2d_ms"] / 1e3) / 1e9) if tme["h2d_ms"] else None}
 
+    clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

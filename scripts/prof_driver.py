@@ -21,6 +21,10 @@ else:
 bs = [synthetic.make_batch(cells, G, 2000, seed=10 + i) for i in range(2)]
 dev = [tuple(torch.from_numpy(a).cuda() for a in (b.cell, b.gene, b.value)) for b in bs]
 eng = HotPathEngine(0, max_rows=max(b.n_rows for b in bs) + 1024, max_cells=cells + 1024)
+for i in range(2):  # warm-up (module load, allocator)
+    eng.tokenize(*dev[i % 2], shuffle_seed=42 + i, **kw)
+torch.cuda.synchronize()
+eng.timing()
 for i in range(steps):
     out = eng.tokenize(*dev[i % 2], shuffle_seed=42 + i, **kw)
     torch.cuda.synchronize()

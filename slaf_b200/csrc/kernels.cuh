@@ -208,33 +208,48 @@ __device__ __forceinline__ void load_cells4(const uint32_t *__restrict__ cell, u
     }
 }
 
-// Scan one warp's span [w0, w1): returns the number of heads; if `list` is given, the first
-// kCsrListCap head rows are stored in order; if `out_base` != ~0u, heads are written to the
-// segment table directly (replay for spans with more heads than the list holds).
+// Scan one warp's span [w0, w1): returns the number of heads; the first kCsrListCap head rows are
+// stored in order in `list`, or (REPLAY) every head is written straight to the segment table at
+// out_base (spans with more heads than the list holds).  Loads are software pipelined: the next
+// 512 rows (4 x 128-bit per lane) are in flight while the current 512 are examined, and a block
+// of 128 rows with no boundary costs a handful of instructions (xor/or + one ballot).
 template <bool REPLAY>
 __device__ __forceinline__ uint32_t scan_span(const CsrArgs &a, uint32_t w0, uint32_t w1, uint32_t *list, uint32_t out_base) {
     const int lane = threadIdx.x & 31;
     const uint32_t R = a.n_rows;
     uint32_t run = 0;
-    for (uint32_t b0 = w0; b0 < w1; b0 += 512) {       // 4 x 128 rows per trip: 4 independent 128-bit loads in flight
+    uint32_t nxt[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        const uint32_t r0 = w0 + u * 128 + lane * 4;
+        if (r0 < w1) load_cells4(a.cell, r0, R, nxt[u]);
+        else { nxt[u][0] = nxt[u][1] = nxt[u][2] = nxt[u][3] = 0u; }
+    }
+    uint32_t carry = 0;   // cell id of the row before this 512-row trip (lane 31's last element of the previous trip)
+    for (uint32_t b0 = w0; b0 < w1; b0 += 512) {
         uint32_t c[4][4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-            const uint32_t r0 = b0 + u * 128 + lane * 4;
-            if (r0 < w1) load_cells4(a.cell, r0, R, c[u]);
-            else { c[u][0] = c[u][1] = c[u][2] = c[u][3] = 0u; }
+#pragma unroll
+            for (int e = 0; e < 4; e++) c[u][e] = nxt[u][e];
         }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {   // prefetch the next trip
+            const uint32_t r0 = b0 + 512 + u * 128 + lane * 4;
+            if (r0 < w1) load_cells4(a.cell, r0, R, nxt[u]);
+            else { nxt[u][0] = nxt[u][1] = nxt[u][2] = nxt[u][3] = 0u; }
+        }
+        if (b0 == w0) carry = (w0 > 0 && w0 < R) ? __ldg(a.cell + w0 - 1) : ~c[0][0];   // row 0 is always a head
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             const uint32_t r0 = b0 + u * 128 + lane * 4;
             uint32_t prev = __shfl_up_sync(0xffffffffu, c[u][3], 1);   // lanes > 0: the previous lane's last row
-            uint32_t prev0;                                            // lane 0: last row of the previous 128-row block
-            if (u == 0) prev0 = (lane == 0 && r0 > 0 && r0 < R) ? __ldg(a.cell + r0 - 1) : 0u;
-            else prev0 = __shfl_sync(0xffffffffu, c[u > 0 ? u - 1 : 0][3], 31);
+            const uint32_t prev0 = (u == 0) ? carry : __shfl_sync(0xffffffffu, c[u > 0 ? u - 1 : 0][3], 31);
             if (lane == 0) prev = prev0;
-            const uint32_t f = (r0 < w1) ? head_flags4(c[u], prev, r0, R) : 0u;
-            const uint32_t any = __ballot_sync(0xffffffffu, f != 0u);
+            const uint32_t diff = (c[u][0] ^ prev) | (c[u][1] ^ c[u][0]) | (c[u][2] ^ c[u][1]) | (c[u][3] ^ c[u][2]);
+            const uint32_t any = __ballot_sync(0xffffffffu, diff != 0u && r0 < w1);
             if (any) {                                   // rare: about one head per ~2000 rows
+                const uint32_t f = (r0 < w1) ? head_flags4(c[u], prev, r0, R) : 0u;
                 const uint32_t cnt = __popc(f);
                 const uint32_t inc = warp_incl_scan(cnt);
                 uint32_t g = run + inc - cnt;
@@ -253,11 +268,12 @@ __device__ __forceinline__ uint32_t scan_span(const CsrArgs &a, uint32_t w0, uin
                 run += __shfl_sync(0xffffffffu, inc, 31);
             }
         }
+        carry = __shfl_sync(0xffffffffu, c[3][3], 31);
     }
     return run;
 }
 
-__global__ void __launch_bounds__(kCsrThreads) csr_build_kernel(const CsrArgs a) {
+__global__ void __launch_bounds__(kCsrThreads, 4) csr_build_kernel(const CsrArgs a) {
     __shared__ uint32_t s_list[kCsrWarps][kCsrListCap];
     __shared__ uint32_t s_cnt[kCsrWarps];
     __shared__ uint32_t s_span;
@@ -389,23 +405,34 @@ __device__ __forceinline__ void fill_zero_i64(long long *base, size_t A, size_t 
 
 // attention mask bytes for flat range [A, A+L): 1 for the first t_len, then 0; 16-byte stores inside
 __device__ __forceinline__ void fill_mask(uint8_t *base, size_t A, uint32_t L, uint32_t t_len) {
-    const size_t B = A + L, ones_end = A + t_len;
-    const size_t c0 = A >> 4, c1 = (B + 15) >> 4;
-    for (size_t c = c0 + threadIdx.x; c < c1; c += blockDim.x) {
-        const size_t lo = c << 4;
-        if (lo >= A && lo + 16 <= B) {
+    const uint32_t lead = (uint32_t)((16u - (uint32_t)(A & 15)) & 15u);     // bytes before the first aligned chunk
+    // ragged head and tail: byte stores
+    const uint32_t head = lead < L ? lead : L;
+    const uint32_t body = (L - head) & ~15u;
+    const uint32_t tail0 = head + body;
+    for (uint32_t i = threadIdx.x; i < head + (L - tail0); i += blockDim.x) {
+        const uint32_t t = i < head ? i : tail0 + (i - head);
+        base[A + t] = (t < t_len) ? 1 : 0;
+    }
+    uint4 *chunks = reinterpret_cast<uint4 *>(base + A + head);
+    const uint32_t nchunks = body >> 4;
+    for (uint32_t c = threadIdx.x; c < nchunks; c += blockDim.x) {
+        const uint32_t t = head + (c << 4);                                   // first token of the chunk
+        uint4 v;
+        if (t + 16u <= t_len) v = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
+        else if (t >= t_len) v = make_uint4(0u, 0u, 0u, 0u);
+        else {
             uint32_t w[4];
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 uint32_t x = 0;
 #pragma unroll
-                for (int b = 0; b < 4; b++) x |= (lo + q * 4 + b < ones_end ? 1u : 0u) << (8 * b);
+                for (int b2 = 0; b2 < 4; b2++) x |= (t + q * 4 + b2 < t_len ? 1u : 0u) << (8 * b2);
                 w[q] = x;
             }
-            *reinterpret_cast<uint4 *>(base + lo) = make_uint4(w[0], w[1], w[2], w[3]);
-        } else {
-            for (size_t i = (lo > A ? lo : A); i < lo + 16 && i < B; i++) base[i] = (i < ones_end) ? 1 : 0;
+            v = make_uint4(w[0], w[1], w[2], w[3]);
         }
+        chunks[c] = v;
     }
 }
 
@@ -1001,19 +1028,63 @@ __global__ void __launch_bounds__(kFastThreads) tokenize_cells_kernel(const Fast
                 if constexpr (BINNED && U16) return ((uint32_t)x >= vstar) ? top : 0ll;
                 else return value_token<ValT, MODE>(raw_bits(x), a, m_f64, m_f32);
             };
-            const size_t q0 = A >> 1, q1 = (A + L + 1) >> 1;
-            for (size_t q = q0 + tid; q < q1; q += kFastThreads) {
-                const long long t0 = (long long)(2 * q) - (long long)A, t1 = t0 + 1;
-                const bool v0 = t0 >= 0, v1 = t1 < (long long)L;
-                const long long x0 = v0 ? id_tok(t0) : 0ll, x1 = v1 ? id_tok(t1) : 0ll;
-                if (v0 && v1) *reinterpret_cast<longlong2 *>(a.ids + 2 * q) = make_longlong2(x0, x1);
-                else if (v0) a.ids[2 * q] = x0;
-                else a.ids[2 * q + 1] = x1;
+            // Token t of the row lives at flat index A + t.  Pairs are 16-byte aligned in the flat
+            // array: pair p holds tokens t0 = 2p - off and t0 + 1, off = A & 1 (odd L only).
+            const uint32_t off = (uint32_t)(A & 1);
+            long long *ids_al = a.ids + (A - off);           // 16-byte aligned
+            long long *vals_al = SCGPT ? a.vals + (A - off) : nullptr;
+            const uint32_t n_pairs = (L + off + 1u) >> 1;
+            // interior pairs: both tokens are gene tokens (1 <= t0, t0 + 1 <= n_emit): no branches
+            const uint32_t p_lo = (off + 2u) >> 1;                       // smallest p with t0 >= 1
+            const uint32_t p_hi = n_emit >= 1u ? (n_emit - 1u + off) / 2u + 1u : 0u;   // one past the largest p with t0 + 1 <= n_emit
+            for (uint32_t p = p_lo + tid; p < p_hi; p += kFastThreads) {
+                const uint32_t gi = sh + 2u * p - off - 1u;              // stage index of token t0
+                long long x0, x1;
+                if constexpr (sizeof(GeneT) == 2) { x0 = (long long)sg[gi] + 4ll; x1 = (long long)sg[gi + 1] + 4ll; }
+                else { x0 = (long long)(int32_t)sg[gi] + 4ll; x1 = (long long)(int32_t)sg[gi + 1] + 4ll; }
+                *reinterpret_cast<longlong2 *>(ids_al + 2u * p) = make_longlong2(x0, x1);
                 if constexpr (SCGPT) {
-                    const long long y0 = v0 ? val_tok(t0) : 0ll, y1 = v1 ? val_tok(t1) : 0ll;
-                    if (v0 && v1) *reinterpret_cast<longlong2 *>(a.vals + 2 * q) = make_longlong2(y0, y1);
-                    else if (v0) a.vals[2 * q] = y0;
-                    else a.vals[2 * q + 1] = y1;
+                    long long y0, y1;
+                    if constexpr (BINNED && U16) {
+                        y0 = ((uint32_t)sv[gi] >= vstar) ? top : 0ll;
+                        y1 = ((uint32_t)sv[gi + 1] >= vstar) ? top : 0ll;
+                    } else {
+                        y0 = value_token<ValT, MODE>(raw_bits(sv[gi]), a, m_f64, m_f32);
+                        y1 = value_token<ValT, MODE>(raw_bits(sv[gi + 1]), a, m_f64, m_f32);
+                    }
+                    *reinterpret_cast<longlong2 *>(vals_al + 2u * p) = make_longlong2(y0, y1);
+                }
+            }
+            // PAD pairs: both tokens beyond SEP
+            const uint32_t p_pad = (n_emit + 2u + off + 1u) >> 1;         // smallest p with t0 >= n_emit + 2
+            const uint32_t p_full_end = (L + off) >> 1;                   // pairs whose second token is < L
+            for (uint32_t p = p_pad + tid; p < p_full_end; p += kFastThreads) {
+                *reinterpret_cast<longlong2 *>(ids_al + 2u * p) = make_longlong2(0ll, 0ll);
+                if constexpr (SCGPT) *reinterpret_cast<longlong2 *>(vals_al + 2u * p) = make_longlong2(0ll, 0ll);
+            }
+            // boundary pairs (CLS, the last gene / SEP / first PAD, row ends): generic, a handful per row
+            {
+                const uint32_t nb_head = min(p_lo, n_pairs);                          // pairs [0, p_lo)
+                const uint32_t mid_lo = max(p_hi, p_lo), mid_hi = min(max(p_pad, mid_lo), n_pairs);   // pairs [p_hi, p_pad)
+                const uint32_t tail_lo = max(p_full_end, mid_hi);                     // pairs [p_full_end, n_pairs)
+                const uint32_t n_b = nb_head + (mid_hi - mid_lo) + (n_pairs - tail_lo);
+                for (uint32_t i = tid; i < n_b; i += kFastThreads) {
+                    uint32_t p;
+                    if (i < nb_head) p = i;
+                    else if (i < nb_head + (mid_hi - mid_lo)) p = mid_lo + (i - nb_head);
+                    else p = tail_lo + (i - nb_head - (mid_hi - mid_lo));
+                    const long long t0 = (long long)(2u * p) - (long long)off, t1 = t0 + 1;
+                    const bool v0 = t0 >= 0, v1 = t1 < (long long)L;
+                    const long long x0 = v0 ? id_tok(t0) : 0ll, x1 = v1 ? id_tok(t1) : 0ll;
+                    if (v0 && v1) *reinterpret_cast<longlong2 *>(ids_al + 2u * p) = make_longlong2(x0, x1);
+                    else if (v0) ids_al[2u * p] = x0;
+                    else if (v1) ids_al[2u * p + 1] = x1;
+                    if constexpr (SCGPT) {
+                        const long long y0 = v0 ? val_tok(t0) : 0ll, y1 = v1 ? val_tok(t1) : 0ll;
+                        if (v0 && v1) *reinterpret_cast<longlong2 *>(vals_al + 2u * p) = make_longlong2(y0, y1);
+                        else if (v0) vals_al[2u * p] = y0;
+                        else if (v1) vals_al[2u * p + 1] = y1;
+                    }
                 }
             }
             fill_mask(a.mask, A, L, min(n_emit + 2u, L));
