@@ -368,6 +368,7 @@ def main():
                      "general_path": {"cells_per_step": tm["slow_cells"] / max(1, tm["batches"]), "avg_launch_ms": tm["slowpath_ms"] / max(1, tm["batches"])},
                      "whole_step_hbm_frac": ((k1_b + k2_b) / (ms / 1e3) / 1e9 / peak) if world == 1 else None},
         "gpu_launches": int(tm["kernel_launches"]),
+        "host_us_per_step": {k: round(1000.0 * tm[f"host_{k}_ms"] / max(1, tm["batches"]), 1) for k in ("submit", "collect", "wait", "shuffle")},
         "clocks": clocks,
     }
     if e2e:

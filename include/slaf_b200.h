@@ -115,6 +115,10 @@ typedef struct {
     int64_t cells;
     int64_t rows;
     int64_t slow_cells;      /* cells that needed the general (distinct-count) path */
+    double host_submit_ms;   /* host wall time spent inside slafb_submit                      */
+    double host_collect_ms;  /* host wall time spent inside slafb_collect (includes the two below) */
+    double host_wait_ms;     /* ... of which: waiting for the cell count (H2D + K1 to finish)   */
+    double host_shuffle_ms;  /* ... of which: building the CPython-exact permutation            */
 } slafb_timing;
 
 int slafb_version(void);

@@ -1,0 +1,85 @@
+// read_probe.cu -- which READ pattern/mechanism reaches the HBM ceiling for K1's 140 MB column scan?
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdint>
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *b, uint32_t c) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(c) : "memory"); }
+__device__ __forceinline__ void mbar_expect(uint64_t *b, uint32_t n) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(n) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t ph) {
+    asm volatile("{\n.reg .pred P1;\nLW:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n@P1 bra DN;\nbra LW;\nDN:\n}" ::"r"(smem_u32(b)), "r"(ph) : "memory");
+}
+__device__ __forceinline__ void bulk(void *d, const void *s, uint32_t n, uint64_t *b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(d)), "l"(s), "r"(n), "r"(smem_u32(b)) : "memory");
+}
+__global__ void p_flat(const uint4 *a, size_t n, unsigned *sink) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x, st = (size_t)gridDim.x * blockDim.x;
+    unsigned acc = 0;
+    for (; i < n; i += st) { uint4 v = __ldcs(a + i); acc |= v.x ^ v.y ^ v.z ^ v.w; }
+    if (acc == 0x12345678u) *sink = acc;
+}
+__global__ void p_span_ldg(const uint4 *a, size_t n, unsigned *sink) {
+    const size_t per = (n + gridDim.x - 1) / gridDim.x, b = blockIdx.x * per, e = min(b + per, n);
+    unsigned acc = 0;
+#pragma unroll 4
+    for (size_t i = b + threadIdx.x; i < e; i += blockDim.x) { uint4 v = __ldcs(a + i); acc |= v.x ^ v.y ^ v.z ^ v.w; }
+    if (acc == 0x12345678u) *sink = acc;
+}
+template <int STAGES, int TILE_U4, bool STRIDED>
+__global__ void p_tma(const uint4 *a, size_t n, unsigned *sink) {
+    __shared__ __align__(128) uint4 buf[STAGES][TILE_U4];
+    __shared__ __align__(8) uint64_t full[STAGES], empty[STAGES];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NC = blockDim.x - 32;
+    if (tid == 0) { for (int i = 0; i < STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], NC / 32); } asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncthreads();
+    const size_t n_tiles_all = n / TILE_U4;
+    const size_t per = (n_tiles_all + gridDim.x - 1) / gridDim.x;
+    size_t my_tiles = STRIDED ? (n_tiles_all > blockIdx.x ? (n_tiles_all - blockIdx.x + gridDim.x - 1) / gridDim.x : 0)
+                              : (blockIdx.x * per < n_tiles_all ? min(per, n_tiles_all - blockIdx.x * per) : 0);
+    auto tile_of = [&](size_t t) { return STRIDED ? blockIdx.x + t * gridDim.x : blockIdx.x * per + t; };
+    unsigned acc = 0;
+    if (warp == NC / 32) {
+        if (lane == 0) for (size_t t = 0; t < my_tiles; t++) {
+            int st = t % STAGES;
+            if (t >= STAGES) mbar_wait(&empty[st], ((t / STAGES) - 1) & 1);
+            mbar_expect(&full[st], TILE_U4 * 16);
+            bulk(buf[st], a + tile_of(t) * TILE_U4, TILE_U4 * 16, &full[st]);
+        }
+    } else {
+        for (size_t t = 0; t < my_tiles; t++) {
+            int st = t % STAGES;
+            mbar_wait(&full[st], (t / STAGES) & 1);
+            for (int i = tid; i < TILE_U4; i += NC) { uint4 v = buf[st][i]; acc |= v.x ^ v.y ^ v.z ^ v.w; }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[st]);
+        }
+    }
+    if (acc == 0x12345678u) *sink = acc;
+}
+int main() {
+    const size_t N = (size_t)35000000 * 4 / 16;   // 140 MB like the cfg2 cell column
+    uint4 *a; unsigned *sink; cudaMalloc(&a, N * 16 + (1 << 20)); cudaMalloc(&sink, 4); cudaMemset(a, 1, N * 16);
+    uint4 *flush; cudaMalloc(&flush, (size_t)256 << 20);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    auto run = [&](const char *name, auto launch) {
+        float best = 1e9f, sum = 0;
+        for (int r = 0; r < 6; r++) {
+            cudaMemsetAsync(flush, r, (size_t)256 << 20);   // evict the column from L2
+            cudaEventRecord(e0); launch(); cudaEventRecord(e1); cudaEventSynchronize(e1);
+            float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms; sum += ms;
+        }
+        printf("%-46s best %7.1f GB/s (%.1f us)  avg %.1f us\n", name, N * 16.0 / best / 1e6, best * 1e3, sum / 6 * 1e3);
+    };
+    run("flat grid-stride LDG.128, 1184x256", [&] { p_flat<<<1184, 256>>>(a, N, sink); });
+    run("flat grid-stride LDG.128, 4736x256", [&] { p_flat<<<4736, 256>>>(a, N, sink); });
+    run("per-CTA span LDG.128 x4, 592x256", [&] { p_span_ldg<<<592, 256>>>(a, N, sink); });
+    run("per-CTA span LDG.128 x4, 1184x256", [&] { p_span_ldg<<<1184, 256>>>(a, N, sink); });
+    run("TMA 4x8K span, 592x288", [&] { p_tma<4, 512, false><<<592, 288>>>(a, N, sink); });
+    run("TMA 4x8K strided, 592x288", [&] { p_tma<4, 512, true><<<592, 288>>>(a, N, sink); });
+    run("TMA 5x8K strided, 592x288", [&] { p_tma<5, 512, true><<<592, 288>>>(a, N, sink); });
+    run("TMA 2x16K strided, 592x288", [&] { p_tma<2, 1024, true><<<592, 288>>>(a, N, sink); });
+    run("TMA 4x8K strided, 740x288", [&] { p_tma<4, 512, true><<<740, 288>>>(a, N, sink); });
+    run("TMA 4x4K strided, 1184x288", [&] { p_tma<4, 256, true><<<1184, 288>>>(a, N, sink); });
+    run("TMA 4x4K span, 1184x288", [&] { p_tma<4, 256, false><<<1184, 288>>>(a, N, sink); });
+    printf("%s\n", cudaGetErrorString(cudaGetLastError()));
+}

@@ -63,6 +63,7 @@ class Timing(Structure):
         ("csr_ms", c_double), ("tokenize_ms", c_double), ("slowpath_ms", c_double), ("h2d_ms", c_double),
         ("batches", c_int64), ("kernel_launches", c_int64), ("cells", c_int64), ("rows", c_int64),
         ("slow_cells", c_int64),
+        ("host_submit_ms", c_double), ("host_collect_ms", c_double), ("host_wait_ms", c_double), ("host_shuffle_ms", c_double),
     ]
 
 

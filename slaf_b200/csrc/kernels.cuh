@@ -34,10 +34,8 @@ namespace slafb {
 constexpr int kTokThreads = 256;
 constexpr int kGroup = 8;                           // rows per thread per chunk (one 128-bit load of u16)
 constexpr int kChunkRows = kTokThreads * kGroup;    // 2048 rows staged per iteration
-constexpr int kCsrThreads = 256;
-constexpr int kCsrWarps = kCsrThreads / 32;
-constexpr int kCsrListCap = 512;                    // segment heads a warp can keep in shared memory
-constexpr int kFastThreads = 128;                   // K2: threads per persistent CTA
+constexpr int kCsrListCap = 1024;                   // segment heads a CTA keeps in shared memory (else: replay)
+constexpr int kFastThreads = 256;                   // K2: threads per persistent CTA
 constexpr int kFastWarps = kFastThreads / 32;
 constexpr int kBitmapWords = 65536 / 32;
 constexpr int kSortSmemKeys = 12288;                // general path: float keys sorted in shared memory up to here
@@ -164,13 +162,52 @@ __device__ __forceinline__ long long expr_bin_token(float x, float bin_size, int
 __device__ __forceinline__ float log1pf_window(float x) { return (float)log1p((double)x); }
 
 // ------------------------------------------------------------------------------------------
+// mbarrier / TMA bulk-copy primitives (PTX)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// TMA bulk copy global -> shared (1-D, 16-byte aligned, size a multiple of 16), completion on `bar`
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait_parity(uint64_t *bar, uint32_t parity) { mbar_wait(bar, parity); }
+
+// ------------------------------------------------------------------------------------------
 // K1: segmented CSR build from the COO cell column
 // ------------------------------------------------------------------------------------------
+// Each CTA owns one contiguous span of rows.  A producer warp streams the span through a ring of
+// shared-memory stages with TMA bulk copies (kCsrStages x 8 KiB in flight per CTA, ~19 MB over the
+// grid: the loaded DRAM latency is ~2.5 us, registers could not hold that much), eight consumer
+// warps test 8 rows per thread for a change of cell id (2 x LDS.128 + xor/or) and append the rare
+// segment heads to a per-CTA list.  Heads are row numbers, so sorting the (tiny) list restores row
+// order; a flat gather of the preceding CTAs' counts gives the global offset.
 struct CsrArgs {
     const uint32_t *cell;   // uint32 or int32 bits
     uint32_t n_rows;
     uint32_t max_cells;
-    uint32_t rows_per_warp; // multiple of 128
+    uint32_t rows_per_cta;  // multiple of kCsrStageRows
     uint32_t *seg_start;    // [max_cells + 1]
     uint32_t *seg_cell;     // [max_cells]
     unsigned long long *tile_state;  // [grid] : epoch<<34 | status<<32 | value
@@ -178,178 +215,187 @@ struct CsrArgs {
     uint32_t ticket_base;
     uint32_t epoch;         // 30-bit launch id, so tile_state needs no memset
     uint32_t *n_cells_out;  // [0] = number of segments, [1] = error flags
-    uint32_t *work_counters;  // [0] = general-path count, [1] = general-path head  (reset here)
+    uint32_t *work_counters;  // [0] general-path count, [1] general-path head, [2] K2 row ticket (reset here)
 };
 
-constexpr unsigned long long kStAgg = 1ull, kStPrefix = 2ull;
+constexpr unsigned long long kStAgg = 1ull;
 __device__ __forceinline__ unsigned long long st_pack(uint32_t epoch, unsigned long long status, uint32_t v) {
     return ((unsigned long long)epoch << 34) | (status << 32) | (unsigned long long)v;
 }
 
-// head flags (4 bits) of rows r0..r0+3 held by this lane; `prev` = cell id of row r0-1
-__device__ __forceinline__ uint32_t head_flags4(const uint32_t (&c)[4], uint32_t prev, uint32_t r0, uint32_t R) {
-    uint32_t f = 0;
-#pragma unroll
-    for (int e = 0; e < 4; e++) {
-        const uint32_t r = r0 + e;
-        const uint32_t p = (e == 0) ? prev : c[e - 1];
-        if (r < R && (r == 0 || c[e] != p)) f |= 1u << e;
-    }
-    return f;
-}
+constexpr int kCsrConsumers = 256;                 // 8 consumer warps
+constexpr int kCsrBlock = kCsrConsumers + 32;      // + 1 producer warp
+constexpr int kCsrStageRows = kCsrConsumers * 8;   // 2048 rows = 8 KiB per stage
+constexpr int kCsrStages = 4;
 
-__device__ __forceinline__ void load_cells4(const uint32_t *__restrict__ cell, uint32_t r0, uint32_t R, uint32_t (&c)[4]) {
-    if (r0 + 4 <= R) {
-        uint4 q = __ldcs(reinterpret_cast<const uint4 *>(cell + r0));
-        c[0] = q.x; c[1] = q.y; c[2] = q.z; c[3] = q.w;
+__global__ void __launch_bounds__(kCsrBlock) csr_build_kernel(const CsrArgs a) {
+    __shared__ __align__(128) uint32_t s_stage[kCsrStages][kCsrStageRows + 4];   // [0..3] = the 4 rows before the tile
+    __shared__ __align__(8) uint64_t s_full[kCsrStages], s_empty[kCsrStages];
+    __shared__ uint32_t s_list[kCsrListCap], s_sorted[kCsrListCap];
+    __shared__ uint32_t s_count, s_span, s_base, s_ws[16], s_part[kCsrBlock / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        s_span = atomicAdd(a.ticket, 1u) - a.ticket_base;
+        s_count = 0u;
+        for (int i = 0; i < kCsrStages; i++) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], kCsrConsumers / 32); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const uint32_t span = s_span, R = a.n_rows;
+    const unsigned long long sb = (unsigned long long)span * a.rows_per_cta;
+    const uint32_t r_beg = sb < R ? (uint32_t)sb : R;
+    const uint32_t r_end = (sb + a.rows_per_cta < R) ? (uint32_t)(sb + a.rows_per_cta) : R;
+    const uint32_t n_tiles = (r_end - r_beg + kCsrStageRows - 1) / kCsrStageRows;
+
+    if (warp == kCsrConsumers / 32) {
+        // ---------------- producer warp: keep kCsrStages bulk copies in flight
+        if (lane == 0) {
+            for (uint32_t t = 0; t < n_tiles; t++) {
+                const uint32_t st = t % kCsrStages;
+                if (t >= (uint32_t)kCsrStages) mbar_wait(&s_empty[st], ((t / kCsrStages) - 1u) & 1u);
+                const uint32_t t0 = r_beg + t * kCsrStageRows;
+                const uint32_t rows = min((uint32_t)kCsrStageRows, r_end - t0) & ~3u;   // 16-byte granules; a ragged tail is read directly
+                const uint32_t lead = t0 >= 4u ? 4u : 0u;                               // the row before the tile, for the first compare
+                const uint32_t bytes = (rows + lead) * 4u;
+                if (bytes) {
+                    mbar_arrive_expect_tx(&s_full[st], bytes);
+                    bulk_g2s(&s_stage[st][4u - lead], a.cell + t0 - lead, bytes, &s_full[st]);
+                } else {
+                    mbar_arrive(&s_full[st]);
+                }
+            }
+        }
     } else {
+        // ---------------- consumer warps
+        for (uint32_t t = 0; t < n_tiles; t++) {
+            const uint32_t st = t % kCsrStages;
+            mbar_wait(&s_full[st], (t / kCsrStages) & 1u);
+            const uint32_t t0 = r_beg + t * kCsrStageRows;
+            const uint32_t rows = min((uint32_t)kCsrStageRows, r_end - t0);
+            const uint32_t rows4 = rows & ~3u;
+            const uint32_t i0 = (uint32_t)tid * 8u;          // first of my 8 rows inside the tile
+            if (i0 < rows) {
+                uint32_t c[8], prev;
+                const uint32_t *sp = &s_stage[st][4u + i0];
+                if (i0 + 8u <= rows4) {
+                    const uint4 q0 = *reinterpret_cast<const uint4 *>(sp), q1 = *reinterpret_cast<const uint4 *>(sp + 4);
+                    c[0] = q0.x; c[1] = q0.y; c[2] = q0.z; c[3] = q0.w; c[4] = q1.x; c[5] = q1.y; c[6] = q1.z; c[7] = q1.w;
+                } else {
 #pragma unroll
-        for (int e = 0; e < 4; e++) c[e] = (r0 + e < R) ? __ldg(cell + r0 + e) : 0u;
-    }
-}
-
-// Scan one warp's span [w0, w1): returns the number of heads; the first kCsrListCap head rows are
-// stored in order in `list`, or (REPLAY) every head is written straight to the segment table at
-// out_base (spans with more heads than the list holds).  Loads are software pipelined: the next
-// 512 rows (4 x 128-bit per lane) are in flight while the current 512 are examined, and a block
-// of 128 rows with no boundary costs a handful of instructions (xor/or + one ballot).
-template <bool REPLAY>
-__device__ __forceinline__ uint32_t scan_span(const CsrArgs &a, uint32_t w0, uint32_t w1, uint32_t *list, uint32_t out_base) {
-    const int lane = threadIdx.x & 31;
-    const uint32_t R = a.n_rows;
-    uint32_t run = 0;
-    uint32_t nxt[4][4];
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-        const uint32_t r0 = w0 + u * 128 + lane * 4;
-        if (r0 < w1) load_cells4(a.cell, r0, R, nxt[u]);
-        else { nxt[u][0] = nxt[u][1] = nxt[u][2] = nxt[u][3] = 0u; }
-    }
-    uint32_t carry = 0;   // cell id of the row before this 512-row trip (lane 31's last element of the previous trip)
-    for (uint32_t b0 = w0; b0 < w1; b0 += 512) {
-        uint32_t c[4][4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-#pragma unroll
-            for (int e = 0; e < 4; e++) c[u][e] = nxt[u][e];
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++) {   // prefetch the next trip
-            const uint32_t r0 = b0 + 512 + u * 128 + lane * 4;
-            if (r0 < w1) load_cells4(a.cell, r0, R, nxt[u]);
-            else { nxt[u][0] = nxt[u][1] = nxt[u][2] = nxt[u][3] = 0u; }
-        }
-        if (b0 == w0) carry = (w0 > 0 && w0 < R) ? __ldg(a.cell + w0 - 1) : ~c[0][0];   // row 0 is always a head
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const uint32_t r0 = b0 + u * 128 + lane * 4;
-            uint32_t prev = __shfl_up_sync(0xffffffffu, c[u][3], 1);   // lanes > 0: the previous lane's last row
-            const uint32_t prev0 = (u == 0) ? carry : __shfl_sync(0xffffffffu, c[u > 0 ? u - 1 : 0][3], 31);
-            if (lane == 0) prev = prev0;
-            const uint32_t diff = (c[u][0] ^ prev) | (c[u][1] ^ c[u][0]) | (c[u][2] ^ c[u][1]) | (c[u][3] ^ c[u][2]);
-            const uint32_t any = __ballot_sync(0xffffffffu, diff != 0u && r0 < w1);
-            if (any) {                                   // rare: about one head per ~2000 rows
-                const uint32_t f = (r0 < w1) ? head_flags4(c[u], prev, r0, R) : 0u;
-                const uint32_t cnt = __popc(f);
-                const uint32_t inc = warp_incl_scan(cnt);
-                uint32_t g = run + inc - cnt;
-#pragma unroll
-                for (int e = 0; e < 4; e++) {
-                    if (f & (1u << e)) {
-                        if constexpr (REPLAY) {
-                            const uint32_t o = out_base + g;
-                            if (o < a.max_cells) { a.seg_start[o] = r0 + e; a.seg_cell[o] = c[u][e]; }
-                        } else {
-                            if (g < (uint32_t)kCsrListCap) list[g] = r0 + e;
-                        }
-                        g++;
+                    for (int e = 0; e < 8; e++) {
+                        const uint32_t i = i0 + e;
+                        c[e] = (i < rows4) ? sp[e] : ((i < rows) ? __ldg(a.cell + t0 + i) : 0u);
                     }
                 }
-                run += __shfl_sync(0xffffffffu, inc, 31);
+                const uint32_t r0 = t0 + i0;
+                if (r0 == 0u) prev = ~c[0];                                  // row 0 always opens a segment
+                else prev = sp[-1];                                          // previous row (lead rows for i0 == 0)
+                uint32_t diff = c[0] ^ prev;
+#pragma unroll
+                for (int e = 1; e < 8; e++) diff |= c[e] ^ c[e - 1];
+                if (diff) {                                                   // rare: ~1 segment head per 2000 rows
+                    uint32_t p = prev;
+#pragma unroll
+                    for (int e = 0; e < 8; e++) {
+                        if (i0 + e < rows && c[e] != p) {
+                            const uint32_t k = atomicAdd(&s_count, 1u);
+                            if (k < (uint32_t)kCsrListCap) s_list[k] = r0 + e;
+                        }
+                        p = c[e];
+                    }
+                }
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[st]);
         }
-        carry = __shfl_sync(0xffffffffu, c[3][3], 31);
     }
-    return run;
-}
-
-__global__ void __launch_bounds__(kCsrThreads, 4) csr_build_kernel(const CsrArgs a) {
-    __shared__ uint32_t s_list[kCsrWarps][kCsrListCap];
-    __shared__ uint32_t s_cnt[kCsrWarps];
-    __shared__ uint32_t s_span;
-    __shared__ uint32_t s_base;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_span = atomicAdd(a.ticket, 1u) - a.ticket_base;
-    __syncthreads();
-    const uint32_t span = s_span;
-    const uint32_t R = a.n_rows;
-    const unsigned long long wbeg = ((unsigned long long)span * kCsrWarps + warp) * a.rows_per_warp;
-    const uint32_t w0 = wbeg < R ? (uint32_t)wbeg : R;
-    const uint32_t w1 = (wbeg + a.rows_per_warp < R) ? (uint32_t)(wbeg + a.rows_per_warp) : R;
-
-    // phase A: every warp counts (and remembers) the segment heads of its own contiguous span
-    const uint32_t wcount = scan_span<false>(a, w0, w1, s_list[warp], 0u);
-    if (lane == 0) s_cnt[warp] = wcount;
     __syncthreads();
 
-    // phase B: CTA aggregate, publish, decoupled look-back over the preceding CTAs
-    if (warp == 0) {
-        uint32_t wv = (lane < kCsrWarps) ? s_cnt[lane] : 0u;
-        uint32_t winc = warp_incl_scan(wv);
-        const uint32_t cta_total = __shfl_sync(0xffffffffu, winc, kCsrWarps - 1);
-        __syncwarp();
-        if (lane < kCsrWarps) s_cnt[lane] = winc - wv;  // exclusive warp bases
-        volatile unsigned long long *st = a.tile_state;
-        if (lane == 0) st[span] = st_pack(a.epoch, span == 0 ? kStPrefix : kStAgg, cta_total);
-        uint32_t excl = 0;
-        int look = (int)span - 1;
-        while (look >= 0) {
-            const int idx = look - lane;
-            unsigned long long sv;
-            bool ready;
-            do {
-                sv = (idx >= 0) ? st[idx] : st_pack(a.epoch, kStPrefix, 0u);
-                ready = ((uint32_t)(sv >> 34) == a.epoch) && (((sv >> 32) & 3ull) != 0ull);
-            } while (!__all_sync(0xffffffffu, ready));
-            const bool is_prefix = ((sv >> 32) & 3ull) == kStPrefix;
-            const uint32_t pm = __ballot_sync(0xffffffffu, is_prefix);
-            const uint32_t val = (uint32_t)sv;
-            if (pm) {
-                const int first = __ffs(pm) - 1;  // nearest predecessor that already has a full prefix
-                excl += warp_sum(lane <= first ? val : 0u);
-                break;
-            }
-            excl += warp_sum(val);
-            look -= 32;
+    // ---------------- order the heads of this span
+    const uint32_t count = s_count;
+    const bool listed = count <= (uint32_t)kCsrListCap;
+    if (listed) {
+        for (uint32_t i = tid; i < count; i += kCsrBlock) {
+            const uint32_t v = s_list[i];
+            uint32_t rank = 0;
+            for (uint32_t k = 0; k < count; k++) rank += (s_list[k] < v) ? 1u : 0u;
+            s_sorted[rank] = v;
         }
-        if (lane == 0) {
-            if (span != 0) st[span] = st_pack(a.epoch, kStPrefix, excl + cta_total);
+    }
+
+    // ---------------- publish the count, gather the counts of all preceding CTAs
+    // (a few hundred CTAs that finish at about the same time: a flat gather is one or two L2 round
+    // trips, a chained look-back would serialise them.  Spinning is safe: spans are handed out by
+    // ticket, so every predecessor has already started.)
+    {
+        volatile unsigned long long *stt = a.tile_state;
+        if (tid == 0) stt[span] = st_pack(a.epoch, kStAgg, count);
+        uint32_t part = 0;
+        for (uint32_t i = tid; i < span; i += kCsrBlock) {
+            unsigned long long sv;
+            do { sv = stt[i]; } while ((uint32_t)(sv >> 34) != a.epoch || ((sv >> 32) & 3ull) == 0ull);
+            part += (uint32_t)sv;
+        }
+        part = warp_sum(part);
+        if (lane == 0) s_part[warp] = part;
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t excl = 0;
+#pragma unroll
+            for (int w = 0; w < kCsrBlock / 32; w++) excl += s_part[w];
             s_base = excl;
             if (span == gridDim.x - 1) {
-                const uint32_t total = excl + cta_total;
+                const uint32_t total = excl + count;
                 a.n_cells_out[0] = total;
                 a.n_cells_out[1] = (total > a.max_cells) ? 1u : 0u;
                 if (total <= a.max_cells) a.seg_start[total] = R;
                 a.work_counters[0] = 0u;
                 a.work_counters[1] = 0u;
+                a.work_counters[2] = 0u;   // K2 row ticket
             }
         }
+        __syncthreads();
     }
-    __syncthreads();
+    const uint32_t base = s_base;
 
-    // phase C: write this warp's heads at their global positions (row order is preserved)
-    const uint32_t base = s_base + s_cnt[warp];
-    if (wcount <= (uint32_t)kCsrListCap) {
-        for (uint32_t i = lane; i < wcount; i += 32) {
+    // ---------------- write the segment table rows of this span
+    if (listed) {
+        for (uint32_t i = tid; i < count; i += kCsrBlock) {
             const uint32_t o = base + i;
             if (o < a.max_cells) {
-                const uint32_t r = s_list[warp][i];
+                const uint32_t r = s_sorted[i];
                 a.seg_start[o] = r;
                 a.seg_cell[o] = __ldg(a.cell + r);
             }
         }
     } else {
-        scan_span<true>(a, w0, w1, nullptr, base);       // too many heads for the list: replay the span
+        // more heads than the list holds (very short cells): replay the span in row order with a
+        // block-wide scan per 2048-row tile.  Correct for any input, only slower.
+        uint32_t run = base;
+        for (uint32_t t0 = r_beg; t0 < r_end; t0 += kCsrStageRows) {
+            uint32_t flags = 0, c[8];
+            const uint32_t r0 = t0 + (uint32_t)tid * 8u;
+            if (tid < kCsrConsumers) {
+                uint32_t p = (r0 > 0u && r0 < r_end) ? __ldg(a.cell + r0 - 1) : 0u;
+#pragma unroll
+                for (int e = 0; e < 8; e++) {
+                    const uint32_t r = r0 + e;
+                    c[e] = (r < r_end) ? __ldg(a.cell + r) : 0u;
+                    if (r < r_end && (r == 0u || c[e] != p)) flags |= 1u << e;
+                    p = c[e];
+                }
+            }
+            uint32_t tot;
+            uint32_t off = run + block_excl_scan(__popc(flags), s_ws, tot);
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                if (flags & (1u << e)) {
+                    if (off < a.max_cells) { a.seg_start[off] = r0 + e; a.seg_cell[off] = c[e]; }
+                    off++;
+                }
+            }
+            run += tot;
+        }
     }
 }
 
@@ -789,52 +835,28 @@ __device__ bool process_cell(const TokArgs &a, const WindowSink &wsnk, uint32_t 
 }
 
 // ---- K2 fast path: persistent CTAs, TMA-staged cell segments ------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P1;\n\t"
-        "LAB_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
-        "@P1 bra DONE;\n\t"
-        "bra LAB_WAIT;\n\t"
-        "DONE:\n\t"
-        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-// TMA bulk copy global -> shared (1-D, 16-byte aligned, size a multiple of 16), completion on `bar`
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
 struct FastArgs {
     TokArgs t;
     uint32_t gcap;                // gene stage capacity (rows, multiple of 8)
     uint32_t vcap;                // value stage capacity (rows, multiple of 8)
     const uint32_t *vstar_table;  // [65536] smallest uint16 value whose window bin is >= 1, per cell maximum
+    uint32_t *ticket;             // dynamic row counter (zeroed by K1): rows are handed out in order
 };
 
 struct CellDesc {
+    uint32_t j;                   // output row (0xffffffff: no more work)
     uint32_t s, e, c, a0;
     uint32_t g_bulk, v_bulk;      // rows staged by the bulk copies, counted from a0 (multiples of 8)
     uint32_t n_g, n_v;            // rows of the cell the stages must hold (from s)
 };
 
 template <typename GeneT, typename ValT, int MODE>
-__device__ __forceinline__ void fast_issue(const FastArgs &fa, uint32_t c, uint32_t s, uint32_t e, CellDesc *d,
+__device__ __forceinline__ void fast_issue(const FastArgs &fa, uint32_t j, uint32_t c, uint32_t s, uint32_t e, CellDesc *d,
                                            uint8_t *gstage, uint8_t *vstage, uint64_t *bar) {
     constexpr bool SCGPT = (MODE == MODE_SCGPT_RAW || MODE == MODE_SCGPT_BINNED);
     const TokArgs &a = fa.t;
+    d->j = j;
+    if (j >= a.n_cells) { mbar_arrive(bar); return; }     // end marker for the consumers
     const uint32_t n = e - s, a0 = s & ~7u, R8 = a.n_rows & ~7u;
     const uint32_t limit = SCGPT ? a.max_genes : (a.L - 1u);
     const bool need_val = SCGPT || (n > a.max_items);
@@ -879,41 +901,54 @@ __global__ void __launch_bounds__(kFastThreads) tokenize_cells_kernel(const Fast
         mbar_fence_init();
     }
     __syncthreads();
-    uint32_t j = blockIdx.x;
-    const uint32_t G = gridDim.x;
-    // thread 0 walks the segment table two cells ahead of the copies it issues, so neither the
-    // perm -> seg_start dependent loads nor the bulk copies are ever waited on in line
-    uint32_t c1 = 0, s1 = 0, e1 = 0;   // cell j + G
-    uint32_t c2 = 0;                   // permutation entry of cell j + 2G
+    // Rows are handed out IN ORDER by an atomic ticket (first row = blockIdx.x), so the rows being
+    // written at any moment form one compact window of the output tensors -- measured 6.0 TB/s
+    // for this store pattern against 4.3-5.2 TB/s with a fixed stride (scripts/micro/store_probe.cu).
+    // Thread 0 runs three rows ahead: ticket -> permutation entry -> segment bounds -> bulk copy,
+    // one step per iteration, so none of those latencies is ever waited on in line.
+    const uint32_t G = gridDim.x, NONE = 0xffffffffu;
+    uint32_t j1 = NONE, c1 = 0, s1 = 0, e1 = 0;   // next row: segment known, copy issued at the top of the loop
+    uint32_t j2 = NONE, c2 = 0;                   // row after: permutation entry loaded
+    uint32_t j3 = NONE;                           // row after that: ticket drawn
     if (tid == 0) {
-        if (j < a.n_cells) {
-            const uint32_t c0 = a.perm ? (uint32_t)__ldg(a.perm + j) : j;
-            fast_issue<GeneT, ValT, MODE>(fa, c0, __ldg(a.seg_start + c0), __ldg(a.seg_start + c0 + 1), &s_desc[0],
+        const uint32_t j0 = blockIdx.x;
+        if (j0 < a.n_cells) {
+            const uint32_t c0 = a.perm ? (uint32_t)__ldg(a.perm + j0) : j0;
+            fast_issue<GeneT, ValT, MODE>(fa, j0, c0, __ldg(a.seg_start + c0), __ldg(a.seg_start + c0 + 1), &s_desc[0],
                                           smem_raw, smem_raw + gbytes, &s_bar[0]);
+        } else {
+            fast_issue<GeneT, ValT, MODE>(fa, NONE, 0, 0, 0, &s_desc[0], smem_raw, smem_raw + gbytes, &s_bar[0]);
         }
-        if (j + G < a.n_cells) {
-            c1 = a.perm ? (uint32_t)__ldg(a.perm + j + G) : j + G;
+        j1 = G + atomicAdd(fa.ticket, 1u);
+        j2 = G + atomicAdd(fa.ticket, 1u);
+        j3 = G + atomicAdd(fa.ticket, 1u);
+        if (j1 < a.n_cells) {
+            c1 = a.perm ? (uint32_t)__ldg(a.perm + j1) : j1;
             s1 = __ldg(a.seg_start + c1);
             e1 = __ldg(a.seg_start + c1 + 1);
         }
-        if (j + 2 * G < a.n_cells) c2 = a.perm ? (uint32_t)__ldg(a.perm + j + 2 * G) : j + 2 * G;
+        if (j2 < a.n_cells) c2 = a.perm ? (uint32_t)__ldg(a.perm + j2) : j2;
     }
     uint32_t phase_bits = 0u;   // bit st = parity the next wait on stage st must see
 
-    for (uint32_t it = 0; j < a.n_cells; j += G, it++) {
+    for (uint32_t it = 0;; it++) {
         const uint32_t st = it & 1u;
         // stage st^1 was released by the barrier that ended the previous iteration
         if (tid == 0) {
-            if (j + G < a.n_cells)
-                fast_issue<GeneT, ValT, MODE>(fa, c1, s1, e1, &s_desc[st ^ 1u], smem_raw + (st ^ 1u) * stage_bytes,
-                                              smem_raw + (st ^ 1u) * stage_bytes + gbytes, &s_bar[st ^ 1u]);
-            c1 = c2;
-            if (j + 2 * G < a.n_cells) { s1 = __ldg(a.seg_start + c1); e1 = __ldg(a.seg_start + c1 + 1); }
-            if (j + 3 * G < a.n_cells) c2 = a.perm ? (uint32_t)__ldg(a.perm + j + 3 * G) : j + 3 * G;
+            fast_issue<GeneT, ValT, MODE>(fa, j1 < a.n_cells ? j1 : NONE, c1, s1, e1, &s_desc[st ^ 1u],
+                                          smem_raw + (st ^ 1u) * stage_bytes, smem_raw + (st ^ 1u) * stage_bytes + gbytes,
+                                          &s_bar[st ^ 1u]);
+            j1 = j2; c1 = c2;
+            if (j1 < a.n_cells) { s1 = __ldg(a.seg_start + c1); e1 = __ldg(a.seg_start + c1 + 1); }
+            j2 = j3;
+            if (j2 < a.n_cells) c2 = a.perm ? (uint32_t)__ldg(a.perm + j2) : j2;
+            j3 = (j3 < a.n_cells) ? G + atomicAdd(fa.ticket, 1u) : NONE;
         }
         mbar_wait(&s_bar[st], (phase_bits >> st) & 1u);
         phase_bits ^= 1u << st;
         const CellDesc d = s_desc[st];
+        const uint32_t j = d.j;
+        if (j == NONE) break;                       // uniform: every thread reads the same descriptor
         GeneT *sg = reinterpret_cast<GeneT *>(smem_raw + st * stage_bytes);
         ValT *sv = reinterpret_cast<ValT *>(smem_raw + st * stage_bytes + gbytes);
         const uint32_t s = d.s, e = d.e, n = e - s, a0 = d.a0, sh = s - a0;
@@ -1037,13 +1072,19 @@ __global__ void __launch_bounds__(kFastThreads) tokenize_cells_kernel(const Fast
             // interior pairs: both tokens are gene tokens (1 <= t0, t0 + 1 <= n_emit): no branches
             const uint32_t p_lo = (off + 2u) >> 1;                       // smallest p with t0 >= 1
             const uint32_t p_hi = n_emit >= 1u ? (n_emit - 1u + off) / 2u + 1u : 0u;   // one past the largest p with t0 + 1 <= n_emit
+#pragma unroll 2
             for (uint32_t p = p_lo + tid; p < p_hi; p += kFastThreads) {
                 const uint32_t gi = sh + 2u * p - off - 1u;              // stage index of token t0
                 long long x0, x1;
                 if constexpr (sizeof(GeneT) == 2) { x0 = (long long)sg[gi] + 4ll; x1 = (long long)sg[gi + 1] + 4ll; }
                 else { x0 = (long long)(int32_t)sg[gi] + 4ll; x1 = (long long)(int32_t)sg[gi + 1] + 4ll; }
                 *reinterpret_cast<longlong2 *>(ids_al + 2u * p) = make_longlong2(x0, x1);
-                if constexpr (SCGPT) {
+            }
+            if constexpr (SCGPT) {
+                // the value stream second: the bin-threshold load above has landed by now
+#pragma unroll 2
+                for (uint32_t p = p_lo + tid; p < p_hi; p += kFastThreads) {
+                    const uint32_t gi = sh + 2u * p - off - 1u;
                     long long y0, y1;
                     if constexpr (BINNED && U16) {
                         y0 = ((uint32_t)sv[gi] >= vstar) ? top : 0ll;

@@ -10,6 +10,7 @@
 // O(n), ~4 ns per cell: this is control-plane work that stays on the host by design
 // (the permutation depends only on (seed, n_cells)); the device applies it as an indirection.
 #pragma once
+#include <cstddef>
 #include <cstdint>
 
 namespace slafb {
@@ -84,14 +85,41 @@ class PyRandom {
 };
 
 // perm[j] = index (in first-appearance order) of the cell emitted at output row j.
-inline void py_shuffle_perm(int64_t seed, int64_t n, int32_t *perm) {
+//
+// Same draws as random.shuffle, restructured for speed (this runs once per batch on the host,
+// between the CSR build and the tokenizing kernel):
+//   phase 1  walk i = n-1 .. 1 grouped by bit_length(i+1) (constant shift inside a group) and
+//            record the accepted draw j_i; rejection sampling is done branch-free (the draw is
+//            always stored, the index only advances when it is accepted), so the only branch left
+//            is the loop condition;
+//   phase 2  apply the swaps perm[i] <-> perm[j_i] in a tight loop.
+// `scratch` must hold n uint32 (the context keeps one per pipeline slot).
+inline void py_shuffle_perm(int64_t seed, int64_t n, int32_t *perm, uint32_t *scratch = nullptr) {
     for (int64_t i = 0; i < n; i++) perm[i] = (int32_t)i;
     if (n < 2) return;
     PyRandom rng(seed);
-    for (int64_t i = n - 1; i >= 1; i--) {
-        uint32_t j = rng.randbelow((uint32_t)(i + 1));
-        int32_t t = perm[i]; perm[i] = perm[j]; perm[j] = t;
+    uint32_t *jarr = scratch;
+    bool own = false;
+    if (!jarr) { jarr = new uint32_t[(size_t)n]; own = true; }
+    int64_t i = n - 1;
+    while (i >= 1) {
+        const int k = 32 - __builtin_clz((uint32_t)(i + 1));      // (i+1).bit_length()
+        const int64_t lo = ((int64_t)1 << (k - 1)) - 1;           // smallest i with the same bit length of i+1
+        const int64_t stop = lo < 1 ? 1 : lo;
+        const int sh = 32 - k;
+        while (i >= stop) {
+            const uint32_t r = rng.next_u32() >> sh;
+            jarr[i] = r;
+            i -= (r < (uint32_t)(i + 1)) ? 1 : 0;
+        }
     }
+    for (int64_t t = n - 1; t >= 1; t--) {
+        const uint32_t j = jarr[t];
+        const int32_t x = perm[t];
+        perm[t] = perm[j];
+        perm[j] = x;
+    }
+    if (own) delete[] jarr;
 }
 
 }  // namespace slafb

@@ -12,8 +12,10 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
+#include <chrono>
 #include <new>
 
 #include "../../include/slaf_b200.h"
@@ -32,13 +34,14 @@ struct Slot {
     uint32_t *seg_start = nullptr, *seg_cell = nullptr;
     int32_t *perm_dev = nullptr;
     uint32_t *work_list = nullptr;
-    uint32_t *counters = nullptr;   // [0] n_cells, [1] err, [2] work count, [3] work head
+    uint32_t *counters = nullptr;   // [0] n_cells, [1] err, [2] work count, [3] work head, [4] fast-kernel row ticket
     // staged copies of host input (lazy)
     void *in_cell = nullptr, *in_gene = nullptr, *in_value = nullptr;
     // pinned host
     uint32_t *h_counters = nullptr; // [0] n_cells, [1] err, [2] cells deferred to the general kernel
     bool all_general = false;
     int32_t *h_perm = nullptr;
+    uint32_t *h_draws = nullptr;    // scratch of the host shuffle (plain malloc)
     // batch description (device pointers actually used by the kernels)
     const void *cell = nullptr, *gene = nullptr, *value = nullptr;
     int64_t n_rows = 0;
@@ -76,6 +79,10 @@ struct slafb_ctx {
 namespace {
 
 thread_local char g_err[512] = "";
+
+double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 int fail(slafb_ctx *ctx, int code, const char *fmt, ...) {
     char buf[512];
@@ -165,6 +172,7 @@ int launch_fast(slafb_ctx *ctx, const TokArgs &a, cudaStream_t st, bool *launche
     fa.gcap = (limit + 15u + 7u) & ~7u;
     fa.vcap = fa.gcap > 4104u ? fa.gcap : 4104u;
     fa.vstar_table = ctx->vstar_table;
+    fa.ticket = a.work_counters + 2;   // slot counters[4], zeroed by K1 together with the work-list counters
     const size_t smem = 2 * ((size_t)fa.gcap * sizeof(GeneT) + (size_t)fa.vcap * sizeof(ValT));
     if (smem > 200 * 1024) return SLAFB_OK;   // very wide rows: general kernel only
     auto kern = tokenize_cells_kernel<GeneT, ValT, MODE>;
@@ -180,7 +188,12 @@ int launch_fast(slafb_ctx *ctx, const TokArgs &a, cudaStream_t st, bool *launche
         ctx->acc.kernel_launches++;
     }
     size_t per_sm = (220 * 1024) / (smem + 1024);
-    if (per_sm > 8) per_sm = 8;
+    size_t per_sm_max = 2048 / kFastThreads;
+    if (const char *env = getenv("SLAFB_FAST_CTAS_PER_SM")) {   // tuning knob
+        const long v = atol(env);
+        if (v >= 1 && v <= 32) per_sm_max = (size_t)v;
+    }
+    if (per_sm > per_sm_max) per_sm = per_sm_max;
     if (per_sm < 1) per_sm = 1;
     uint32_t grid = (uint32_t)(ctx->n_sm * per_sm);
     if (a.n_cells < grid) grid = a.n_cells;
@@ -314,14 +327,19 @@ int front(slafb_ctx *ctx, Slot &s, const slafb_coo *in, cudaStream_t caller) {
     k.epoch = ctx->epoch;
     k.n_cells_out = s.counters;
     k.work_counters = s.counters + 2;
-    // one contiguous span of rows per warp (multiple of 128 rows); ~4 CTAs per SM
-    uint32_t grid = (uint32_t)ctx->n_sm * 4u;
-    const uint64_t blocks128 = ((uint64_t)in->n_rows + 127) / 128;
-    if (blocks128 < (uint64_t)grid * kCsrWarps) grid = (uint32_t)((blocks128 + kCsrWarps - 1) / kCsrWarps);
-    const uint64_t warps = (uint64_t)grid * kCsrWarps;
-    k.rows_per_warp = (uint32_t)(((blocks128 + warps - 1) / warps) * 128);
+    // one contiguous span of rows per CTA (a whole number of 2048-row stages); ~4 CTAs per SM
+    uint32_t per_sm = 4;
+    if (const char *env = getenv("SLAFB_CSR_CTAS_PER_SM")) {   // tuning knob
+        const long v = atol(env);
+        if (v >= 1 && v <= 8) per_sm = (uint32_t)v;
+    }
+    uint32_t grid = (uint32_t)ctx->n_sm * per_sm;
+    const uint64_t tiles = ((uint64_t)in->n_rows + kCsrStageRows - 1) / kCsrStageRows;
+    if (tiles < grid) grid = (uint32_t)tiles;
+    k.rows_per_cta = (uint32_t)(((tiles + grid - 1) / grid) * kCsrStageRows);
+    grid = (uint32_t)(((uint64_t)in->n_rows + k.rows_per_cta - 1) / k.rows_per_cta);   // no empty spans
     CU(ctx, cudaEventRecord(s.t_k1a, ctx->s_in));
-    csr_build_kernel<<<grid, kCsrThreads, 0, ctx->s_in>>>(k);
+    csr_build_kernel<<<grid, kCsrBlock, 0, ctx->s_in>>>(k);
     CU(ctx, cudaGetLastError());
     CU(ctx, cudaEventRecord(s.t_k1b, ctx->s_in));
     s.timed_front = true;
@@ -334,7 +352,9 @@ int front(slafb_ctx *ctx, Slot &s, const slafb_coo *in, cudaStream_t caller) {
 
 // waits for the cell count; builds + uploads the permutation.  Returns n_cells through *n.
 int middle(slafb_ctx *ctx, Slot &s, const slafb_params *p, int64_t *n, cudaStream_t st, bool *use_perm) {
+    const double tw0 = now_ms();
     CU(ctx, cudaEventSynchronize(s.ev_front));
+    ctx->acc.host_wait_ms += now_ms() - tw0;
     if (s.h_counters[1]) {
         *n = s.h_counters[0];
         return fail(ctx, SLAFB_ERR_CAPACITY, "batch has %u cells, context max_cells is %lld", s.h_counters[0], (long long)ctx->max_cells);
@@ -344,7 +364,9 @@ int middle(slafb_ctx *ctx, Slot &s, const slafb_params *p, int64_t *n, cudaStrea
     *use_perm = false;
     if (C == 0) return SLAFB_OK;
     if (p->shuffle == SLAFB_SHUFFLE_SEED) {
-        py_shuffle_perm(p->seed, C, s.h_perm);
+        const double ts0 = now_ms();
+        py_shuffle_perm(p->seed, C, s.h_perm, s.h_draws);
+        ctx->acc.host_shuffle_ms += now_ms() - ts0;
         *use_perm = true;
     } else if (p->shuffle == SLAFB_SHUFFLE_PERM) {
         if (!p->perm || p->n_perm != C) return fail(ctx, SLAFB_ERR_INVALID, "perm length %lld != number of cells %lld", (long long)p->n_perm, (long long)C);
@@ -479,10 +501,12 @@ int slafb_create(slafb_ctx **out, int device, int64_t max_rows, int64_t max_cell
         CUC(cudaMalloc(&s.seg_cell, ((size_t)max_cells + 1) * sizeof(uint32_t)));
         CUC(cudaMalloc(&s.perm_dev, ((size_t)max_cells + 1) * sizeof(int32_t)));
         CUC(cudaMalloc(&s.work_list, ((size_t)max_cells + 1) * sizeof(uint32_t)));
-        CUC(cudaMalloc(&s.counters, 4 * sizeof(uint32_t)));
-        CUC(cudaMemset(s.counters, 0, 4 * sizeof(uint32_t)));
+        CUC(cudaMalloc(&s.counters, 8 * sizeof(uint32_t)));
+        CUC(cudaMemset(s.counters, 0, 8 * sizeof(uint32_t)));
         CUC(cudaHostAlloc(&s.h_counters, 4 * sizeof(uint32_t), cudaHostAllocDefault));
         CUC(cudaHostAlloc(&s.h_perm, ((size_t)max_cells + 1) * sizeof(int32_t), cudaHostAllocDefault));
+        s.h_draws = (uint32_t *)malloc(((size_t)max_cells + 1) * sizeof(uint32_t));
+        if (!s.h_draws) { slafb_destroy(ctx); return fail(nullptr, SLAFB_ERR_INVALID, "out of host memory"); }
         cudaEvent_t *plain[] = {&s.ev_front, &s.ev_done, &s.ev_in};
         for (auto e : plain) CUC(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
         cudaEvent_t *timed[] = {&s.t_h2d0, &s.t_h2d1, &s.t_k1a, &s.t_k1b, &s.t_k2a, &s.t_k2b, &s.t_k2c};
@@ -505,6 +529,7 @@ int slafb_destroy(slafb_ctx *ctx) {
         cudaFree(s.in_cell); cudaFree(s.in_gene); cudaFree(s.in_value);
         if (s.h_counters) cudaFreeHost(s.h_counters);
         if (s.h_perm) cudaFreeHost(s.h_perm);
+        free(s.h_draws);
         cudaEvent_t evs[] = {s.ev_front, s.ev_done, s.ev_in, s.t_h2d0, s.t_h2d1, s.t_k1a, s.t_k1b, s.t_k2a, s.t_k2b, s.t_k2c};
         for (auto e : evs) if (e) cudaEventDestroy(e);
     }
@@ -522,7 +547,9 @@ int slafb_submit(slafb_ctx *ctx, const slafb_coo *in, void *stream, int32_t *slo
     const int i = ctx->next_slot;
     Slot &s = ctx->slot[i];
     if (s.in_flight) return fail(ctx, SLAFB_ERR_BUSY, "pipeline slot %d not collected yet", i);
+    const double t0 = now_ms();
     int rc = front(ctx, s, in, static_cast<cudaStream_t>(stream));
+    ctx->acc.host_submit_ms += now_ms() - t0;
     if (rc) return rc;
     s.in_flight = true;
     ctx->next_slot = (i + 1) % kSlots;
@@ -535,7 +562,9 @@ int slafb_collect(slafb_ctx *ctx, int32_t slot, const slafb_params *p, const sla
     CU(ctx, cudaSetDevice(ctx->device));
     Slot &s = ctx->slot[slot];
     if (!s.in_flight) return fail(ctx, SLAFB_ERR_INVALID, "slot %d has no submitted batch", slot);
+    const double t0 = now_ms();
     const int rc = back(ctx, s, p, out, n_cells, static_cast<cudaStream_t>(stream));
+    ctx->acc.host_collect_ms += now_ms() - t0;
     // output tensors too small: the CSR of this slot is still valid, so the caller may
     // re-collect with larger tensors; every other outcome releases the slot
     const bool retryable = (rc == SLAFB_ERR_CAPACITY) && n_cells && (*n_cells <= ctx->max_cells);
