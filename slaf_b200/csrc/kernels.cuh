@@ -835,6 +835,28 @@ __device__ bool process_cell(const TokArgs &a, const WindowSink &wsnk, uint32_t 
 }
 
 // ---- K2 fast path: persistent CTAs, TMA-staged cell segments ------------------------------------
+// rows of the cell [s, e) whose uint16 value exceeds T: staged rows from shared memory, the rest
+// (cells larger than the value stage) from global memory.  Kept out of line: it runs for ~2% of
+// the cells and must not cost the common path registers.
+__device__ __noinline__ uint32_t count_above_u16(const uint16_t *sv, const uint16_t *__restrict__ value_g, uint32_t s,
+                                                 uint32_t e, uint32_t a0, uint32_t n_v, uint32_t T) {
+    uint32_t above = 0;
+    const uint32_t sh = s - a0, ngroups = (sh + n_v + 7u) >> 3;
+    for (uint32_t gi = threadIdx.x; gi < ngroups; gi += kFastThreads) {
+        const uint32_t r0 = a0 + gi * 8u;
+        const uint4 q = *reinterpret_cast<const uint4 *>(sv + gi * 8u);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t r = r0 + i;
+            const uint32_t key = (w[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
+            above += (r >= s && r < s + n_v && key > T) ? 1u : 0u;
+        }
+    }
+    for (uint32_t r = s + n_v + threadIdx.x; r < e; r += kFastThreads) above += ((uint32_t)__ldg(value_g + r) > T) ? 1u : 0u;
+    return above;
+}
+
 struct FastArgs {
     TokArgs t;
     uint32_t gcap;                // gene stage capacity (rows, multiple of 8)
@@ -878,7 +900,7 @@ __device__ __forceinline__ void fast_issue(const FastArgs &fa, uint32_t j, uint3
 }
 
 template <typename GeneT, typename ValT, int MODE>
-__global__ void __launch_bounds__(kFastThreads) tokenize_cells_kernel(const FastArgs fa) {
+__global__ void __launch_bounds__(kFastThreads, 2048 / kFastThreads) tokenize_cells_kernel(const FastArgs fa) {
     constexpr bool SCGPT = (MODE == MODE_SCGPT_RAW || MODE == MODE_SCGPT_BINNED);
     constexpr bool BINNED = (MODE == MODE_SCGPT_BINNED);
     constexpr bool U16 = (sizeof(ValT) == 2);
@@ -1033,13 +1055,32 @@ __global__ void __launch_bounds__(kFastThreads) tokenize_cells_kernel(const Fast
             if constexpr (BINNED && !U16) m_f32 = float_of_key(lk);   // max(log1pf) over the cell
             kmax = hi;
             if (!keep_all) {
-                if (U16 && (hi - lo + 1u <= k)) keep_all = true;   // at most k distinct values fit in [lo, hi]
-                else defer = true;                                  // exact k-th distinct value: general kernel
+                if (U16 && (hi - lo + 1u <= k)) {
+                    keep_all = true;                                // at most k distinct values fit in [lo, hi]
+                } else if (U16 && k >= 8u) {
+                    // Second sufficient test (count data has a handful of very large values): with
+                    // T = lo + k - 1 - M, the values <= T take at most k - M distinct values and the
+                    // rows above T at most one each, so  #rows(value > T) <= M  implies  #distinct <= k.
+                    const uint32_t M = min(64u, k >> 1);
+                    const uint32_t T = lo + (k - 1u - M);
+                    uint32_t above = count_above_u16(reinterpret_cast<const uint16_t *>(sv), reinterpret_cast<const uint16_t *>(value_g),
+                                                     s, e, a0, d.n_v, T);
+                    above = warp_sum(above);
+                    __syncthreads();                                // scratch rows are free again
+                    if (lane == 0) s_ws[warp] = above;
+                    __syncthreads();
+                    above = 0;
+#pragma unroll
+                    for (int w2 = 0; w2 < kFastWarps; w2++) above += s_ws[w2];
+                    if (above <= M) keep_all = true; else defer = true;
+                } else {
+                    defer = true;                                   // exact k-th distinct value: general kernel
+                }
             }
         }
 
         if (defer) {
-            if (tid == 0) a.work_list[atomicAdd(a.work_counters, 1u)] = j;
+            if (tid == 0) a.work_list[atomicAdd(a.work_counters, 1u)] = j;   // exact k-th distinct value: general kernel
         } else {
             // ---- emission: token pairs (128-bit stores), value stream, PAD fill, mask, cell id
             const uint32_t n_emit = min(n, limit);
