@@ -77,6 +77,9 @@ typedef enum {
     SLAFB_SHUFFLE_PERM = 2  /* explicit permutation supplied in `perm` (host, length = number of cells)      */
 } slafb_shuffle;
 
+/* params.flags */
+#define SLAFB_FLAG_CHECK_CONTIGUOUS 1 /* verify that no cell id occurs in two separated runs (one extra sync) */
+
 typedef struct {
     int32_t mode;          /* slafb_mode */
     int32_t max_items;     /* Window.apply(max_items)  = tokenizer.max_genes in the dataloader (datasets.py:1041) */
@@ -85,10 +88,13 @@ typedef struct {
     int64_t vocab_size;    /* ScGPTTokenizer.expr_bin_start (tokenizers.py:507) */
     double min_percentile; /* SLAFB_GENEFORMER_PCT only; 0..100 */
     int32_t shuffle;       /* slafb_shuffle */
-    int32_t reserved;
+    int32_t flags;         /* SLAFB_FLAG_* */
     int64_t seed;          /* seed + batch_id + epoch*10000 (datasets.py:1016) */
     const int32_t *perm;   /* SLAFB_SHUFFLE_PERM */
     int64_t n_perm;
+    int32_t window_n_bins; /* SLAFB_SCGPT_BINNED: n_expression_bins the WINDOW bins with (PrefetchBatchProcessor's,
+                              datasets.py:1025-1028) when it differs from the tokenizer's n_bins; 0 = same as n_bins */
+    int32_t reserved;
 } slafb_params;
 
 /* Output tensors (device, row-major, caller-allocated for `capacity_cells` rows):

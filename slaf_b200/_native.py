@@ -28,6 +28,7 @@ U16, I32, U32, F32 = 0, 1, 2, 3
 GENEFORMER, GENEFORMER_PCT, SCGPT_RAW, SCGPT_BINNED = 0, 1, 2, 3
 LOC_DEVICE, LOC_HOST = 0, 1
 SHUFFLE_NONE, SHUFFLE_SEED, SHUFFLE_PERM = 0, 1, 2
+FLAG_CHECK_CONTIGUOUS = 1
 
 EXPORTS = [
     "slafb_version", "slafb_create", "slafb_destroy", "slafb_last_error", "slafb_tokenize", "slafb_submit",
@@ -46,8 +47,9 @@ class Coo(Structure):
 class Params(Structure):
     _fields_ = [
         ("mode", c_int32), ("max_items", c_int32), ("max_genes", c_int32), ("n_bins", c_int32),
-        ("vocab_size", c_int64), ("min_percentile", c_double), ("shuffle", c_int32), ("reserved", c_int32),
+        ("vocab_size", c_int64), ("min_percentile", c_double), ("shuffle", c_int32), ("flags", c_int32),
         ("seed", c_int64), ("perm", POINTER(c_int32)), ("n_perm", c_int64),
+        ("window_n_bins", c_int32), ("reserved", c_int32),
     ]
 
 

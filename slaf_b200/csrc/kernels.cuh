@@ -418,7 +418,8 @@ struct TokArgs {
     uint32_t max_items;
     uint32_t max_genes;
     uint32_t L;
-    int n_bins;
+    int n_bins;                   // tokenizer bins (ScGPTTokenizer.n_expression_bins)
+    int w_bins;                   // window bins (ScGPTWindow n_expression_bins); normally == n_bins
     long long vocab;
     double min_pct;
     float bin_size;               // float32(1.0 / n_bins)
@@ -497,16 +498,16 @@ __device__ __forceinline__ long long value_token(uint32_t raw, const TokArgs &a,
             const double lv = __ldg(a.log1p_lut + raw);
             double b = 0.0;
             if (lv > 0.0) {
-                b = floor(__ddiv_rn(__dmul_rn(lv, (double)a.n_bins), m_f64));
-                b = fmin(fmax(b, 0.0), (double)(a.n_bins - 1));
+                b = floor(__ddiv_rn(__dmul_rn(lv, (double)a.w_bins), m_f64));
+                b = fmin(fmax(b, 0.0), (double)(a.w_bins - 1));
             }
             bin = (float)b;
         } else {
             const float lv = log1pf_window(__uint_as_float(raw));
             float b = 0.0f;
             if (lv > 0.0f) {
-                b = floorf(__fdiv_rn(__fmul_rn(lv, (float)a.n_bins), m_f32));
-                b = fminf(fmaxf(b, 0.0f), (float)(a.n_bins - 1));
+                b = floorf(__fdiv_rn(__fmul_rn(lv, (float)a.w_bins), m_f32));
+                b = fminf(fmaxf(b, 0.0f), (float)(a.w_bins - 1));
             }
             bin = b;
         }
@@ -521,16 +522,16 @@ __device__ __forceinline__ double window_bin(uint32_t raw, const TokArgs &a, dou
         const double lv = __ldg(a.log1p_lut + raw);
         double b = 0.0;
         if (lv > 0.0) {
-            b = floor(__ddiv_rn(__dmul_rn(lv, (double)a.n_bins), m_f64));
-            b = fmin(fmax(b, 0.0), (double)(a.n_bins - 1));
+            b = floor(__ddiv_rn(__dmul_rn(lv, (double)a.w_bins), m_f64));
+            b = fmin(fmax(b, 0.0), (double)(a.w_bins - 1));
         }
         return b;
     } else {
         const float lv = log1pf_window(__uint_as_float(raw));
         float b = 0.0f;
         if (lv > 0.0f) {
-            b = floorf(__fdiv_rn(__fmul_rn(lv, (float)a.n_bins), m_f32));
-            b = fminf(fmaxf(b, 0.0f), (float)(a.n_bins - 1));
+            b = floorf(__fdiv_rn(__fmul_rn(lv, (float)a.w_bins), m_f32));
+            b = fminf(fmaxf(b, 0.0f), (float)(a.w_bins - 1));
         }
         return (double)b;
     }
@@ -1263,6 +1264,22 @@ __global__ void cell_ids_kernel(const uint32_t *seg_cell, const int32_t *perm, u
     const uint32_t c = perm ? (uint32_t)perm[j] : j;
     const uint32_t cid = seg_cell[c];
     cell_ids[j] = cell_signed ? (long long)(int32_t)cid : (long long)cid;
+}
+
+// duplicate detection over the segment table's cell ids (a cell split into two separated row runs
+// would silently become two output rows): open-addressing hash set, 64-bit slots (1<<32 | id)
+__global__ void dup_check_kernel(const uint32_t *seg_cell, uint32_t n, unsigned long long *table, uint32_t mask, uint32_t *flag) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t id = seg_cell[i];
+    const unsigned long long key = (1ull << 32) | id;
+    uint32_t h = (id * 2654435761u) & mask;
+    for (;;) {
+        const unsigned long long old = atomicCAS(table + h, 0ull, key);
+        if (old == 0ull) return;
+        if (old == key) { *flag = 1u; return; }
+        h = (h + 1u) & mask;
+    }
 }
 
 // K4: SLAFTokenizer.tokenize on flattened pre-windowed lists: one CTA per list

@@ -68,6 +68,8 @@ struct slafb_ctx {
     uint32_t *vstar_table = nullptr;  // binned window on uint16 storage: bin>=1 threshold per cell maximum
     int vstar_nbins = -1;
     uint32_t *sort_scratch = nullptr;
+    unsigned long long *dup_table = nullptr;   // contiguity check (lazy, grow-only)
+    size_t dup_slots = 0;
     // window facade scratch
     uint32_t *kept_count = nullptr;
     long long *total_dev = nullptr;
@@ -126,6 +128,7 @@ int check_params(slafb_ctx *ctx, const slafb_params *p) {
     if (p->max_genes < 1) return fail(ctx, SLAFB_ERR_INVALID, "max_genes must be >= 1, got %d", p->max_genes);
     if (p->max_items < 1) return fail(ctx, SLAFB_ERR_INVALID, "max_items must be >= 1, got %d", p->max_items);
     if (p->mode >= SLAFB_SCGPT_RAW && p->n_bins < 1) return fail(ctx, SLAFB_ERR_INVALID, "n_bins must be >= 1");
+    if (p->window_n_bins < 0) return fail(ctx, SLAFB_ERR_INVALID, "window_n_bins must be >= 0");
     if (p->mode == SLAFB_GENEFORMER_PCT && !(p->min_percentile >= 0.0 && p->min_percentile <= 100.0))
         return fail(ctx, SLAFB_ERR_INVALID, "min_percentile must be within [0, 100]");
     return SLAFB_OK;
@@ -181,10 +184,10 @@ int launch_fast(slafb_ctx *ctx, const TokArgs &a, cudaStream_t st, bool *launche
         CU(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set[ctx->device & 63] = true;
     }
-    if (MODE == MODE_SCGPT_BINNED && sizeof(ValT) == 2 && ctx->vstar_nbins != a.n_bins) {
-        vstar_table_kernel<<<256, 256, 0, st>>>(ctx->log1p_lut, a.n_bins, ctx->vstar_table);
+    if (MODE == MODE_SCGPT_BINNED && sizeof(ValT) == 2 && ctx->vstar_nbins != a.w_bins) {
+        vstar_table_kernel<<<256, 256, 0, st>>>(ctx->log1p_lut, a.w_bins, ctx->vstar_table);
         CU(ctx, cudaGetLastError());
-        ctx->vstar_nbins = a.n_bins;
+        ctx->vstar_nbins = a.w_bins;
         ctx->acc.kernel_launches++;
     }
     size_t per_sm = (220 * 1024) / (smem + 1024);
@@ -266,6 +269,7 @@ void fill_tok_args(slafb_ctx *ctx, Slot &s, const slafb_params *p, TokArgs &a, u
     a.max_genes = (uint32_t)p->max_genes;
     a.L = (p->mode >= SLAFB_SCGPT_RAW) ? (uint32_t)p->max_genes + 2u : (uint32_t)p->max_genes;
     a.n_bins = p->n_bins;
+    a.w_bins = p->window_n_bins > 0 ? p->window_n_bins : p->n_bins;
     a.vocab = p->vocab_size;
     a.min_pct = p->min_percentile;
     a.bin_size = (float)(1.0 / (double)(p->n_bins > 0 ? p->n_bins : 1));  // tokenizers.py:508 then float32 at :531
@@ -363,6 +367,26 @@ int middle(slafb_ctx *ctx, Slot &s, const slafb_params *p, int64_t *n, cudaStrea
     *n = C;
     *use_perm = false;
     if (C == 0) return SLAFB_OK;
+    if (p->flags & SLAFB_FLAG_CHECK_CONTIGUOUS) {
+        size_t slots = 1024;
+        while (slots < (size_t)C * 4) slots <<= 1;
+        if (slots > ctx->dup_slots) {
+            if (ctx->dup_table) CU(ctx, cudaFree(ctx->dup_table));
+            ctx->dup_table = nullptr; ctx->dup_slots = 0;
+            CU(ctx, cudaMalloc(&ctx->dup_table, slots * sizeof(unsigned long long)));
+            ctx->dup_slots = slots;
+        }
+        CU(ctx, cudaStreamWaitEvent(st, s.ev_front, 0));
+        CU(ctx, cudaMemsetAsync(ctx->dup_table, 0, slots * sizeof(unsigned long long), st));
+        CU(ctx, cudaMemsetAsync(s.counters + 6, 0, sizeof(uint32_t), st));
+        dup_check_kernel<<<(unsigned)((C + 255) / 256), 256, 0, st>>>(s.seg_cell, (uint32_t)C, ctx->dup_table, (uint32_t)(slots - 1), s.counters + 6);
+        CU(ctx, cudaGetLastError());
+        ctx->acc.kernel_launches++;
+        CU(ctx, cudaMemcpyAsync(s.h_counters + 3, s.counters + 6, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CU(ctx, cudaStreamSynchronize(st));
+        if (s.h_counters[3])
+            return fail(ctx, SLAFB_ERR_NONCONTIGUOUS, "a cell id occurs in two separated row runs; splice partial cells on the host first");
+    }
     if (p->shuffle == SLAFB_SHUFFLE_SEED) {
         const double ts0 = now_ms();
         py_shuffle_perm(p->seed, C, s.h_perm, s.h_draws);
@@ -533,7 +557,7 @@ int slafb_destroy(slafb_ctx *ctx) {
         cudaEvent_t evs[] = {s.ev_front, s.ev_done, s.ev_in, s.t_h2d0, s.t_h2d1, s.t_k1a, s.t_k1b, s.t_k2a, s.t_k2b, s.t_k2c};
         for (auto e : evs) if (e) cudaEventDestroy(e);
     }
-    cudaFree(ctx->tile_state); cudaFree(ctx->ticket); cudaFree(ctx->log1p_lut); cudaFree(ctx->vstar_table); cudaFree(ctx->sort_scratch);
+    cudaFree(ctx->tile_state); cudaFree(ctx->ticket); cudaFree(ctx->log1p_lut); cudaFree(ctx->vstar_table); cudaFree(ctx->sort_scratch); cudaFree(ctx->dup_table);
     cudaFree(ctx->kept_count); cudaFree(ctx->total_dev);
     if (ctx->h_total) cudaFreeHost(ctx->h_total);
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);

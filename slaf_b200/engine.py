@@ -119,7 +119,8 @@ class HotPathEngine:
 
     # ------------------------------------------------------------------ helpers
     def _params(self, mode: str, max_genes: int, max_items: int | None, n_bins: int, vocab_size: int,
-                min_percentile: float | None, shuffle_seed: int | None, perm) -> tuple[N.Params, Any]:
+                min_percentile: float | None, shuffle_seed: int | None, perm, check_contiguous: bool = False,
+                window_n_bins: int | None = None) -> tuple[N.Params, Any]:
         if mode not in MODES:
             raise ValueError(f"unknown mode {mode!r}")
         if max_genes < 1:
@@ -131,6 +132,8 @@ class HotPathEngine:
         p.n_bins = int(n_bins)
         p.vocab_size = int(vocab_size)
         p.min_percentile = float(min_percentile) if min_percentile is not None else 0.0
+        p.flags = N.FLAG_CHECK_CONTIGUOUS if check_contiguous else 0
+        p.window_n_bins = int(window_n_bins) if window_n_bins else 0
         keep = None
         if perm is not None:
             keep = np.ascontiguousarray(np.asarray(perm, np.int32))
@@ -165,9 +168,11 @@ class HotPathEngine:
 
     def collect(self, slot: int, *, mode: str, max_genes: int, max_items: int | None = None, n_bins: int = 10,
                 vocab_size: int = 50000, min_percentile: float | None = None, shuffle_seed: int | None = None,
-                perm=None, capacity_cells: int | None = None) -> TokenizedBatch:
+                perm=None, capacity_cells: int | None = None, check_contiguous: bool = False,
+                window_n_bins: int | None = None) -> TokenizedBatch:
         keep, n_rows = self._pending.pop(slot)
-        p, pkeep = self._params(mode, max_genes, max_items, n_bins, vocab_size, min_percentile, shuffle_seed, perm)
+        p, pkeep = self._params(mode, max_genes, max_items, n_bins, vocab_size, min_percentile, shuffle_seed, perm,
+                                check_contiguous, window_n_bins)
         scgpt = p.mode >= N.SCGPT_RAW
         L = max_genes + 2 if scgpt else max_genes
         cap = capacity_cells or self._cap_hint or max(64, min(self.max_cells, n_rows // 256 + 64))
@@ -198,10 +203,11 @@ class HotPathEngine:
 
     # ------------------------------------------------------------------ facades
     def window(self, cell: Any, gene: Any, value: Any, *, mode: str, max_items: int, n_bins: int = 10,
-               min_percentile: float | None = None, shuffle_seed: int | None = None, perm=None) -> WindowResult:
+               min_percentile: float | None = None, shuffle_seed: int | None = None, perm=None,
+               check_contiguous: bool = False) -> WindowResult:
         """Window.apply as flat list columns (reference: slaf/ml/aggregators.py:26-50)."""
         coo, keep = _coo(cell, gene, value)
-        p, pkeep = self._params(mode, max_items, max_items, n_bins, 0, min_percentile, shuffle_seed, perm)
+        p, pkeep = self._params(mode, max_items, max_items, n_bins, 0, min_percentile, shuffle_seed, perm, check_contiguous)
         R = coo.n_rows
         cap = max(1, min(self.max_cells, R))
         dev = self.device
@@ -254,6 +260,21 @@ class HotPathEngine:
         with torch.cuda.device(self.device):
             N.check(self._L.slafb_get_timing(self._ctx, ctypes.byref(t)), self._ctx)
         return {f: getattr(t, f) for f, _ in N.Timing._fields_}
+
+
+def regroup_contiguous(cell: np.ndarray, gene: np.ndarray, value: np.ndarray):
+    """Host control-plane helper: make every cell's rows one contiguous run, cells in order of
+    first appearance, rows of a cell in row order -- what polars partition_by / group_by
+    (maintain_order=True) do implicitly (reference slaf/ml/samplers.py:93).  The device kernels
+    take contiguous cells; the host feeder calls this only when the library reports
+    SLAFB_ERR_NONCONTIGUOUS (partial cells re-joined after a fragment boundary,
+    reference slaf/ml/datasets.py:880-888)."""
+    cell = np.asarray(cell)
+    if cell.size == 0:
+        return cell, np.asarray(gene), np.asarray(value)
+    _, first, inv = np.unique(cell, return_index=True, return_inverse=True)
+    order = np.argsort(first[inv], kind="stable")
+    return cell[order], np.asarray(gene)[order], np.asarray(value)[order]
 
 
 def shuffle_perm(seed: int, n: int) -> np.ndarray:
