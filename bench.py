@@ -168,7 +168,7 @@ def run_reference(args, w):
     if rank != 0:
         return
     cores = len(os.sched_getaffinity(0))
-    sample = 256 * cores
+    sample = 1024 * cores
     rates = []
     for _ in range(args.warmup):
         cpu_port_rate(w, max(cores * 16, 64), cores)
@@ -184,7 +184,7 @@ def run_reference(args, w):
         "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
         "config": {"workload": w["name"], "cells_per_step": sample},
         "cpu_baseline": {"value": rate, "unit": "cells/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} steps x {sample} cells ({cores} processes x 256 cells), numpy window + per-cell Python tokenizer loop (reference structure; polars not installable)",
+                         "sample": f"{args.steps} steps x {sample} cells ({cores} processes x 1024 cells), numpy window + per-cell Python tokenizer loop (reference structure; polars not installable)",
                          "c_oracle_cells_per_s": c_rate, "c_oracle_threads": c_thr},
         "e2e": {"value": rate, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t_all,
@@ -375,7 +375,7 @@ def main():
         line["e2e"] = e2e
     if world == 1 and not args.no_cpu_baseline:
         cores = len(os.sched_getaffinity(0))
-        rate, n = cpu_port_rate(w, 192 * cores, cores)
+        rate, n = cpu_port_rate(w, 768 * cores, cores)
         c_rate, c_thr = c_oracle_rate(w, 2048)
         line["cpu_baseline"] = {"value": rate, "unit": "cells/s", "cores": cores, "kind": "port",
                                 "sample": f"{n} cells ({cores} processes x {n // cores}), numpy window + per-cell Python tokenizer loop (reference structure; polars not installable here)",

@@ -1,0 +1,144 @@
+"""CPU tests of the host-side control plane of the drop-in layer: frame adapters, the block
+shuffle (CPython-exact permutation applied to frames), schema objects, factories.  No kernel runs
+here; the window / tokenizer arithmetic is covered by the -m gpu tests."""
+
+import random
+
+import numpy as np
+import pyarrow as pa
+import pytest
+
+from oracle import py_restatement as pr
+from slaf_b200.core.tabular_schema import SLAF_LANCE_COO_SCHEMA, DataSchema
+from slaf_b200.engine import regroup_contiguous
+from slaf_b200.ml import frames
+from slaf_b200.ml.samplers import GenericShuffle, RandomShuffle, ShuffleType, StratifiedShuffle, create_shuffle
+
+
+def _coo(seed=0, n_cells=37, split=False):
+    rng = np.random.default_rng(seed)
+    ids = rng.choice(10_000, n_cells, replace=False)
+    lens = rng.integers(1, 9, n_cells)
+    cell = np.repeat(ids, lens).astype(np.uint32)
+    gene = rng.integers(0, 60000, cell.size).astype(np.uint16)
+    value = rng.integers(1, 50, cell.size).astype(np.uint16)
+    if split:  # move the tail of the first cell to the end (a cell in two separated runs)
+        k = int(lens[0])
+        order = np.r_[np.arange(0, max(1, k // 2)), np.arange(k, cell.size), np.arange(max(1, k // 2), k)]
+        cell, gene, value = cell[order], gene[order], value[order]
+    return {"cell_integer_id": cell, "gene_integer_id": gene, "value": value}
+
+
+@pytest.mark.parametrize("split", [False, True])
+@pytest.mark.parametrize("kind", ["dict", "arrow", "pandas"])
+@pytest.mark.parametrize("seed", [42, 43, 10042])
+def test_random_shuffle_matches_reference_semantics(seed, kind, split):
+    cols = _coo(seed, split=split)
+    df = cols if kind == "dict" else (pa.table(cols) if kind == "arrow" else __import__("pandas").DataFrame(cols))
+    out = RandomShuffle().apply(df, seed)
+    want = pr.apply_block_shuffle(cols["cell_integer_id"], cols["gene_integer_id"], cols["value"], seed)
+    for name, w in zip(("cell_integer_id", "gene_integer_id", "value"), want):
+        assert np.array_equal(frames.column(out, name), w), name
+
+
+def test_random_shuffle_chunked_mode():
+    cols = _coo(7, n_cells=23)
+    chunks = RandomShuffle().apply(cols, 99, batch_size=5)
+    assert len(chunks) == 5                                   # ceil(23 / 5)
+    per = [len(np.unique(c["cell_integer_id"])) for c in chunks]
+    assert per == [5, 5, 5, 5, 3]
+    whole = RandomShuffle().apply(cols, 99)
+    assert np.array_equal(np.concatenate([c["cell_integer_id"] for c in chunks]), whole["cell_integer_id"])
+    # chunk order is the CPython shuffle of the first-appearance order
+    ids = cols["cell_integer_id"][np.sort(np.unique(cols["cell_integer_id"], return_index=True)[1])]
+    random.seed(99)
+    order = list(ids)
+    random.shuffle(order)
+    first_seen = whole["cell_integer_id"][np.sort(np.unique(whole["cell_integer_id"], return_index=True)[1])]
+    assert first_seen.tolist() == [int(x) for x in order]
+
+
+def test_shuffle_empty_and_factories():
+    empty = {"cell_integer_id": np.zeros(0, np.uint32), "gene_integer_id": np.zeros(0, np.uint16), "value": np.zeros(0, np.uint16)}
+    assert RandomShuffle().apply(empty, 1) is empty
+    assert RandomShuffle().apply(empty, 1, batch_size=4) == []
+    assert isinstance(create_shuffle("random"), RandomShuffle)
+    assert isinstance(create_shuffle(ShuffleType.STRATIFIED), StratifiedShuffle)
+    with pytest.raises(ValueError, match="Unsupported shuffle type"):
+        create_shuffle("sorted")
+    # without a cell-type column the stratified strategy is the random one (samplers.py:140-142)
+    cols = _coo(3)
+    a = StratifiedShuffle().apply(cols, 5)
+    b = RandomShuffle().apply(cols, 5)
+    assert np.array_equal(a["cell_integer_id"], b["cell_integer_id"])
+
+
+def test_generic_shuffle_uses_schema_group_key():
+    cols = _coo(11)
+    df = {"g": cols["cell_integer_id"], "i": cols["gene_integer_id"], "v": cols["value"]}
+    schema = DataSchema(group_key="g", item_key="i", value_key="v")
+    out = GenericShuffle().apply(df, schema, 77)
+    want = pr.apply_block_shuffle(cols["cell_integer_id"], cols["gene_integer_id"], cols["value"], 77)
+    assert np.array_equal(out["g"], want[0]) and np.array_equal(out["i"], want[1])
+
+
+def test_regroup_contiguous_is_partition_by_order():
+    cell = np.array([5, 5, 9, 9, 5, 7, 9], np.int32)
+    gene = np.arange(7, dtype=np.int32)
+    value = np.arange(7, dtype=np.uint16)
+    c, g, v = regroup_contiguous(cell, gene, value)
+    assert c.tolist() == [5, 5, 5, 9, 9, 9, 7]
+    assert g.tolist() == [0, 1, 4, 2, 3, 6, 5]
+    assert v.tolist() == g.tolist()
+
+
+def test_schema_mirror():
+    s = SLAF_LANCE_COO_SCHEMA
+    assert (s.group_key, s.item_key, s.value_key, s.item_list_key, s.value_list_key) == (
+        "cell_integer_id", "gene_integer_id", "value", "gene_sequence", "expr_sequence")
+    d = DataSchema(group_key="a", item_key="b", value_key="c")
+    assert d.item_list_key == "item_list" and d.value_list_key is None and d.group_key_out is None
+
+
+def test_frame_extract_dtype_rules():
+    base = _coo(5)
+    # the storage dtypes pass through untouched (zero copy)
+    c = frames.extract(base, SLAF_LANCE_COO_SCHEMA)
+    assert c.cell.dtype == np.uint32 and c.gene.dtype == np.uint16 and c.value.dtype == np.uint16 and not c.value_is_float
+    # wide integer ids narrow exactly
+    wide = {"cell_integer_id": base["cell_integer_id"].astype(np.int64), "gene_integer_id": base["gene_integer_id"].astype(np.int64),
+            "value": base["value"].astype(np.int64)}
+    c = frames.extract(wide, SLAF_LANCE_COO_SCHEMA)
+    assert c.cell.dtype == np.uint32 and c.gene.dtype == np.int32 and c.value.dtype == np.uint16
+    assert c.cell_dtype == np.int64                                     # answers go back in the caller's dtype
+    # float64 integral counts take the exact uint16 path but stay "float" for the bin dtype
+    f = dict(base, value=base["value"].astype(np.float64))
+    c = frames.extract(f, SLAF_LANCE_COO_SCHEMA)
+    assert c.value.dtype == np.uint16 and c.value_is_float
+    # non-representable float64 is refused rather than silently rounded
+    bad = dict(base, value=np.full(base["value"].shape, 0.1, np.float64))
+    with pytest.raises(TypeError):
+        frames.extract(bad, SLAF_LANCE_COO_SCHEMA)
+    with pytest.raises(ValueError, match="NaN"):
+        frames.extract(dict(base, value=np.full(base["value"].shape, np.nan, np.float64)), SLAF_LANCE_COO_SCHEMA)
+    with pytest.raises(ValueError):
+        frames.extract(dict(base, value=np.full(base["value"].shape, 70000, np.int64)), SLAF_LANCE_COO_SCHEMA)
+    with pytest.raises(TypeError):
+        frames.frame_kind([1, 2, 3])
+
+
+def test_build_grouped_arrow_and_dict():
+    cols = frames.extract(_coo(2, n_cells=3), SLAF_LANCE_COO_SCHEMA)
+    cell_ids = np.array([7, 8, 9], np.int64)
+    offs = np.array([0, 2, 2, 5], np.int64)
+    genes = np.arange(5, dtype=np.int64)
+    exprs = np.array([1, 2, 3, 4, 5], np.float64)
+    out = frames.build_grouped(cols, SLAF_LANCE_COO_SCHEMA, cell_ids, offs, genes, exprs, expr_is_bins=True)
+    assert out.columns == ["cell_integer_id", "gene_sequence", "expr_sequence"] and len(out) == 3
+    assert [list(x) for x in out["gene_sequence"]] == [[0, 1], [], [2, 3, 4]]
+    assert out["expr_sequence"][2].dtype == np.float64                  # integer storage -> Float64 bins
+    cols.kind = "arrow"
+    t = frames.build_grouped(cols, SLAF_LANCE_COO_SCHEMA, cell_ids, offs, genes, None, expr_is_bins=False)
+    assert t.column_names == ["cell_integer_id", "gene_sequence"]
+    assert t.column("gene_sequence").to_pylist() == [[0, 1], [], [2, 3, 4]]
+    assert frames.list_column(t, "gene_sequence") == [[0, 1], [], [2, 3, 4]]
