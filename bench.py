@@ -49,14 +49,24 @@ WORKLOADS = {
 }
 
 
-def algorithmic_bytes(w, n_rows, n_cells):
-    """one read of the input, one write of the output, nothing else."""
+def algorithmic_bytes(w, nnz, value_bytes=2, gene_bytes=2):
+    """Bytes the algorithm has to move for cells with `nnz` rows each:
+    K1 reads the cell column once and writes the segment table; K2 reads every value (the rank
+    filter and the bin maximum need them all), the genes that can reach the output
+    (min(n, max_genes) per cell -- rows beyond the truncation point are never needed), the segment
+    table + permutation entry, and writes the output tensors once.  This is SURVEY.md section 8(d)'s
+    figure minus the gene bytes the truncation makes unnecessary, i.e. the conservative one."""
+    nnz = np.asarray(nnz, np.int64)
+    n_rows, n_cells = int(nnz.sum()), int(nnz.size)
     scgpt = w["tokenizer"] == "scgpt"
     L = w["max_genes"] + 2 if scgpt else w["max_genes"]
+    limit = w["max_genes"] if scgpt else w["max_genes"] - 1
     out_per_cell = (17 * L + 8) if scgpt else (9 * L + 8)
-    k1 = 4 * n_rows                                  # K1 reads the cell column
-    k2 = 4 * n_rows + 12 * n_cells + out_per_cell * n_cells   # K2: gene+value, seg table + perm, outputs
-    return k1, k2, 8 * n_rows                        # (K1, K2, H2D bytes)
+    need_values = scgpt | (nnz > w["max_genes"])          # Geneformer cells with n <= k never touch their values
+    k1 = 4 * n_rows + 8 * n_cells
+    k2 = int(value_bytes * nnz[need_values].sum() + gene_bytes * np.minimum(nnz, limit).sum()) + (12 + out_per_cell) * n_cells
+    h2d = (4 + gene_bytes + value_bytes) * n_rows
+    return k1, k2, h2d
 
 
 class ClockSampler:
@@ -275,6 +285,12 @@ def main():
     dev_cols = [(torch.from_numpy(b.cell).to(dev), torch.from_numpy(b.gene).to(dev), torch.from_numpy(b.value).to(dev)) for b in batches]
     host_cols = [tuple(torch.from_numpy(a).pin_memory() for a in (b.cell, b.gene, b.value)) for b in batches]
     tot_rows = [b.n_rows for b in batches]
+    vbytes = 2 if args.value_dtype == "uint16" else 4
+    gbytes = batches[0].gene.dtype.itemsize
+    per_batch = [algorithmic_bytes(w, np.diff(b.cell_start), vbytes, gbytes) for b in batches]
+
+    def bytes_over(n_steps):   # (K1, K2, H2D) algorithmic bytes of n_steps steps (batches are cycled)
+        return tuple(sum(per_batch[i % NB][j] for i in range(n_steps)) for j in range(3))
 
     def run_steps(cols, n_steps, read_result, depth=2):
         """pipelined: up to `depth` submits (H2D + CSR build) run ahead of the collect of the
@@ -326,7 +342,7 @@ def main():
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
         tme = eng.timing()
-        h2d_bytes = algorithmic_bytes(w, rows_e, cells_e)[2] if args.value_dtype == "uint16" else 10 * rows_e
+        h2d_bytes = bytes_over(args.steps)[2]
         e2e = {"value": sum_over_ranks(cells_e) / dt, "unit": "cells/s", "h2d_bytes_per_step": h2d_bytes // args.steps,
                "d2h_bytes_per_step": d2h_e // args.steps, "ms_per_step": 1000.0 * dt / args.steps,
                "h2d_gbs_per_gpu": h2d_bytes / dt / 1e9, "h2d_copy_gbs": (h2d_bytes / (tme["h2d_ms"] / 1e3) / 1e9) if tme["h2d_ms"] else None}
@@ -343,14 +359,13 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    k1_b, k2_b, _ = algorithmic_bytes(w, rows, cells)
-    if args.value_dtype != "uint16":
-        k2_b += 2 * rows
+    k1_b, k2_b, _ = bytes_over(args.steps)
     k2_gbs = k2_b / (tm["tokenize_ms"] / 1e3) / 1e9 if tm["tokenize_ms"] else None
     k1_gbs = k1_b / (tm["csr_ms"] / 1e3) / 1e9 if tm["csr_ms"] else None
     traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum of K2 from the committed ncu --set full capture, per cell
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{args.workload}:{args.value_dtype}")
+        traffic = int(tj["k2_dram_bytes_per_cell"] * cps) if tj else None
     except Exception:
         pass
     line = {
@@ -362,9 +377,9 @@ def main():
         "roofline": {"bound": "hbm", "kernel": "tokenize_cells_kernel", "achieved": k2_gbs, "peak": peak, "unit": "GB/s",
                      "frac": (k2_gbs / peak) if k2_gbs else None, "traffic": traffic,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s",
-                     "algorithmic_bytes_per_launch": k2_b // args.steps, "avg_launch_ms": tm["tokenize_ms"] / max(1, tm["batches"]),
+                     "algorithmic_bytes_per_launch": int(k2_b / args.steps), "avg_launch_ms": tm["tokenize_ms"] / max(1, tm["batches"]),
                      "csr_build_kernel": {"achieved": k1_gbs, "frac": (k1_gbs / peak) if k1_gbs else None,
-                                          "algorithmic_bytes_per_launch": k1_b // args.steps, "avg_launch_ms": tm["csr_ms"] / max(1, tm["batches"])},
+                                          "algorithmic_bytes_per_launch": int(k1_b / args.steps), "avg_launch_ms": tm["csr_ms"] / max(1, tm["batches"])},
                      "general_path": {"cells_per_step": tm["slow_cells"] / max(1, tm["batches"]), "avg_launch_ms": tm["slowpath_ms"] / max(1, tm["batches"])},
                      "whole_step_hbm_frac": ((k1_b + k2_b) / (ms / 1e3) / 1e9 / peak) if world == 1 else None},
         "gpu_launches": int(tm["kernel_launches"]),

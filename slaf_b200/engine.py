@@ -231,6 +231,10 @@ class HotPathEngine:
         """SLAFTokenizer.tokenize on flattened device lists (reference: slaf/ml/tokenizers.py:375-479, 635-722)."""
         B = offsets.numel() - 1
         L = max_genes + 2 if scgpt else max_genes
+        if genes.numel() == 0:       # all lists empty: the kernel never dereferences, but NULL is refused by the ABI
+            genes = torch.zeros(1, dtype=torch.int64, device=self.device)
+        if scgpt and (exprs is None or exprs.numel() == 0):
+            exprs = torch.zeros(1, dtype=torch.float64, device=self.device)
         out, (ids, mask, vals, _c) = self._alloc_out(max(B, 1), L, scgpt)
         with torch.cuda.device(self.device):
             N.check(self._L.slafb_tokenize_lists(self._ctx, int(scgpt), offsets.data_ptr(), genes.data_ptr(),
