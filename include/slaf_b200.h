@@ -74,7 +74,8 @@ typedef struct {
 typedef enum {
     SLAFB_SHUFFLE_NONE = 0, /* cells in order of first appearance                                           */
     SLAFB_SHUFFLE_SEED = 1, /* CPython random.seed(seed); random.shuffle(chunks)  (slaf/ml/samplers.py:89-96) */
-    SLAFB_SHUFFLE_PERM = 2  /* explicit permutation supplied in `perm` (host, length = number of cells)      */
+    SLAFB_SHUFFLE_PERM = 2  /* explicit order supplied in `perm` (host): output row j = segment perm[j]; n_perm may be
+                               smaller than the number of segments (a selection: the other cells are not emitted)  */
 } slafb_shuffle;
 
 /* params.flags */
@@ -152,6 +153,15 @@ int slafb_tokenize(slafb_ctx *ctx, const slafb_coo *in, const slafb_params *p, c
 int slafb_submit(slafb_ctx *ctx, const slafb_coo *in, void *stream, int32_t *slot);
 int slafb_collect(slafb_ctx *ctx, int32_t slot, const slafb_params *p, const slafb_out *out,
                   int64_t *n_cells, void *stream);
+
+/* The segment table K1 built for a submitted batch, copied to the host (blocks until the H2D copy
+ * and CSR build of that slot are done): n_cells segments in order of first appearance,
+ * seg_start[n_cells + 1] row offsets, seg_cell[n_cells] cell ids (uint32 bits of the cell column).
+ * The host feeder uses it for the reference's completeness check against _cell_start_index
+ * (slaf/ml/datasets.py:891-928) without scanning the rows itself, then collects with a
+ * SLAFB_SHUFFLE_PERM selection that leaves the incomplete boundary cells out. */
+int slafb_segments(slafb_ctx *ctx, int32_t slot, int64_t *n_cells, uint32_t *seg_start, uint32_t *seg_cell,
+                   int64_t capacity_cells);
 
 /* Window facade: Window.apply(fragment_df, schema, max_items, **kwargs)
  * (slaf/ml/aggregators.py:26-50; slaf/distributed/window.py:25-59).  Produces the grouped

@@ -32,7 +32,7 @@ FLAG_CHECK_CONTIGUOUS = 1
 
 EXPORTS = [
     "slafb_version", "slafb_create", "slafb_destroy", "slafb_last_error", "slafb_tokenize", "slafb_submit",
-    "slafb_collect", "slafb_window", "slafb_tokenize_lists", "slafb_shuffle_perm", "slafb_gene_stats",
+    "slafb_collect", "slafb_segments", "slafb_window", "slafb_tokenize_lists", "slafb_shuffle_perm", "slafb_gene_stats",
     "slafb_host_alloc", "slafb_host_free", "slafb_get_timing",
 ]
 
@@ -122,6 +122,7 @@ def lib() -> ctypes.CDLL:
     L.slafb_tokenize.argtypes = [c_void_p, POINTER(Coo), POINTER(Params), POINTER(Out), POINTER(c_int64), c_void_p]
     L.slafb_submit.argtypes = [c_void_p, POINTER(Coo), c_void_p, POINTER(c_int32)]
     L.slafb_collect.argtypes = [c_void_p, c_int32, POINTER(Params), POINTER(Out), POINTER(c_int64), c_void_p]
+    L.slafb_segments.argtypes = [c_void_p, c_int32, POINTER(c_int64), c_void_p, c_void_p, c_int64]
     L.slafb_window.argtypes = [c_void_p, POINTER(Coo), POINTER(Params), c_void_p, c_void_p, c_void_p, c_void_p,
                                c_int64, POINTER(c_int64), POINTER(c_int64), c_void_p]
     L.slafb_tokenize_lists.argtypes = [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int32,

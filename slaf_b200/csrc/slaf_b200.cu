@@ -393,15 +393,19 @@ int middle(slafb_ctx *ctx, Slot &s, const slafb_params *p, int64_t *n, cudaStrea
         ctx->acc.host_shuffle_ms += now_ms() - ts0;
         *use_perm = true;
     } else if (p->shuffle == SLAFB_SHUFFLE_PERM) {
-        if (!p->perm || p->n_perm != C) return fail(ctx, SLAFB_ERR_INVALID, "perm length %lld != number of cells %lld", (long long)p->n_perm, (long long)C);
-        for (int64_t i = 0; i < C; i++) {
+        // a permutation of all segments, or a SELECTION: fewer entries than segments emit only those
+        // cells (the host feeder drops incomplete boundary cells this way, datasets.py:891-928)
+        if (p->n_perm < 0 || p->n_perm > C || (p->n_perm > 0 && !p->perm))
+            return fail(ctx, SLAFB_ERR_INVALID, "perm length %lld exceeds the number of cells %lld", (long long)p->n_perm, (long long)C);
+        for (int64_t i = 0; i < p->n_perm; i++) {
             if (p->perm[i] < 0 || p->perm[i] >= C) return fail(ctx, SLAFB_ERR_INVALID, "perm[%lld] out of range", (long long)i);
             s.h_perm[i] = p->perm[i];
         }
         *use_perm = true;
+        *n = p->n_perm;
     }
     CU(ctx, cudaStreamWaitEvent(st, s.ev_front, 0));
-    if (*use_perm) CU(ctx, cudaMemcpyAsync(s.perm_dev, s.h_perm, (size_t)C * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    if (*use_perm && *n > 0) CU(ctx, cudaMemcpyAsync(s.perm_dev, s.h_perm, (size_t)(*n) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     return SLAFB_OK;
 }
 
@@ -594,6 +598,26 @@ int slafb_collect(slafb_ctx *ctx, int32_t slot, const slafb_params *p, const sla
     const bool retryable = (rc == SLAFB_ERR_CAPACITY) && n_cells && (*n_cells <= ctx->max_cells);
     if (!retryable) s.in_flight = false;
     return rc;
+}
+
+int slafb_segments(slafb_ctx *ctx, int32_t slot, int64_t *n_cells, uint32_t *seg_start, uint32_t *seg_cell, int64_t capacity_cells) {
+    if (!ctx || slot < 0 || slot >= kSlots || !n_cells) return fail(ctx, SLAFB_ERR_INVALID, "bad ctx / slot / n_cells");
+    CU(ctx, cudaSetDevice(ctx->device));
+    Slot &s = ctx->slot[slot];
+    if (!s.in_flight) return fail(ctx, SLAFB_ERR_INVALID, "slot %d has no submitted batch", slot);
+    const double tw0 = now_ms();
+    CU(ctx, cudaEventSynchronize(s.ev_front));
+    ctx->acc.host_wait_ms += now_ms() - tw0;
+    *n_cells = s.h_counters[0];
+    if (s.h_counters[1]) return fail(ctx, SLAFB_ERR_CAPACITY, "batch has %u cells, context max_cells is %lld", s.h_counters[0], (long long)ctx->max_cells);
+    const int64_t C = *n_cells;
+    if (C > capacity_cells) return fail(ctx, SLAFB_ERR_CAPACITY, "batch has %lld cells, host table capacity is %lld", (long long)C, (long long)capacity_cells);
+    if (C == 0) { if (seg_start) seg_start[0] = 0; return SLAFB_OK; }
+    if (!seg_start || !seg_cell) return fail(ctx, SLAFB_ERR_INVALID, "NULL table pointer");
+    CU(ctx, cudaMemcpyAsync(seg_start, s.seg_start, (size_t)(C + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->s_in));
+    CU(ctx, cudaMemcpyAsync(seg_cell, s.seg_cell, (size_t)C * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->s_in));
+    CU(ctx, cudaStreamSynchronize(ctx->s_in));
+    return SLAFB_OK;
 }
 
 int slafb_tokenize(slafb_ctx *ctx, const slafb_coo *in, const slafb_params *p, const slafb_out *out, int64_t *n_cells, void *stream) {

@@ -101,6 +101,7 @@ class HotPathEngine:
         self._ctx = ctx
         self._cap_hint = 0
         self._pending: dict[int, tuple] = {}
+        self._seg_buf = None
 
     # ------------------------------------------------------------------ lifecycle
     def close(self) -> None:
@@ -192,6 +193,31 @@ class HotPathEngine:
         ids, mask, vals, cids = tensors
         del keep, pkeep
         return TokenizedBatch(ids[:C], mask[:C], vals[:C] if scgpt else None, cids[:C], C)
+
+    def release(self, slot: int) -> None:
+        """Give a submitted slot back without tokenizing it (an empty selection emits no rows)."""
+        if slot in self._pending:
+            try:
+                self.collect(slot, mode="geneformer", max_genes=1, perm=np.zeros(0, np.int32), capacity_cells=1)
+            except N.SlafB200Error:
+                pass                                            # the library frees the slot on every non-retryable error
+
+    def segments(self, slot: int) -> tuple[np.ndarray, np.ndarray]:
+        """Segment table of a submitted batch on the host: (seg_start uint32 [C+1], seg_cell [C]) with
+        cells in order of first appearance.  Blocks until the slot's H2D copy + CSR build are done."""
+        keep, n_rows = self._pending[slot]
+        cap = max(1, min(self.max_cells, n_rows))
+        if self._seg_buf is None or self._seg_buf[0].size < cap + 1:
+            self._seg_buf = (np.empty(cap + 1, np.uint32), np.empty(cap, np.uint32))
+        start, cellid = self._seg_buf
+        n = ctypes.c_int64(0)
+        with torch.cuda.device(self.device):
+            N.check(self._L.slafb_segments(self._ctx, slot, ctypes.byref(n), start.ctypes.data, cellid.ctypes.data, cap), self._ctx)
+        C = int(n.value)
+        ids = cellid[:C].copy()
+        if keep[0].code == N.I32:
+            ids = ids.view(np.int32)
+        return start[: C + 1].copy(), ids
 
     def tokenize(self, cell: Any, gene: Any, value: Any, **kw) -> TokenizedBatch:
         """shuffle -> window -> tokenize -> cell ids for one batch of complete cells
@@ -289,26 +315,20 @@ def shuffle_perm(seed: int, n: int) -> np.ndarray:
 
 
 def pinned_empty(n: int, dtype) -> np.ndarray:
-    """numpy array over cudaHostAlloc'ed memory (freed when the array is garbage collected)."""
+    """numpy array over cudaHostAlloc'ed memory; freed when the last view of it is garbage collected."""
+    import weakref
+
     dtype = np.dtype(dtype)
     ptr = ctypes.c_void_p()
     nbytes = max(1, n * dtype.itemsize)
     N.check(N.lib().slafb_host_alloc(ctypes.byref(ptr), nbytes))
     buf = (ctypes.c_char * nbytes).from_address(ptr.value)
-    arr = np.frombuffer(buf, dtype=dtype, count=n)
-
-    class _Owner:
-        def __init__(self, p):
-            self.p = p
-
-        def __del__(self):
-            try:
-                N.lib().slafb_host_free(self.p)
-            except Exception:
-                pass
-
-    _OWNERS[arr.ctypes.data] = _Owner(ptr)
-    return arr
+    weakref.finalize(buf, _free_pinned, ptr.value)
+    return np.frombuffer(buf, dtype=dtype, count=n)
 
 
-_OWNERS: dict[int, Any] = {}
+def _free_pinned(address: int) -> None:
+    try:
+        N.lib().slafb_host_free(ctypes.c_void_p(address))
+    except Exception:
+        pass

@@ -1,0 +1,730 @@
+"""Prefetch batch processor, async prefetcher and iterable dataset: mirrors of the reference's
+``slaf.ml.datasets`` for the hot path (slaf/ml/datasets.py:240-296 containers, :299-1103
+``PrefetchBatchProcessor``, :1105-1459 ``AsyncPrefetcher``, :1462-1938 ``SLAFIterableDataset``).
+
+What changes against the reference:
+
+* the tokenized branch of ``load_prefetch_batch`` (shuffle -> window -> to_list -> tokenize,
+  datasets.py:1011-1098) is ONE fused device pass: the combined rows go to the GPU once
+  (pinned staging, async H2D on the engine's side stream), K1 builds the segment table, the host
+  does the reference's completeness check on that table (C entries, not R rows) against
+  ``_cell_start_index``, and K2 emits the token tensors of the complete cells in the CPython-exact
+  shuffled order.  The rows of incomplete boundary cells are kept on the host exactly like the
+  reference's ``partial_cell_data`` (datasets.py:891-953);
+* batches are device tensors (views of the prefetch batch); the queue hands over a CUDA event, the
+  consumer stream waits on it -- no host synchronisation per batch;
+* a full queue blocks the producer instead of silently dropping the batch (datasets.py:1277-1281).
+
+Reading fragments (Lance / Arrow decode), the mixture-of-scanners sampling and the boundary
+bookkeeping stay on the host, as in the reference.
+"""
+
+from __future__ import annotations
+
+import queue
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+from dataclasses import dataclass
+from typing import Any, Iterator
+
+import numpy as np
+import torch
+
+from .. import _native as N
+from ..core.tabular_schema import SLAF_LANCE_COO_SCHEMA
+from ..engine import HotPathEngine, pinned_empty, regroup_contiguous, shuffle_perm
+from . import frames
+from .samplers import RandomShuffle, StratifiedShuffle
+from .sources import CooChunk, ExpressionSource, concat_chunks, open_expression
+from .tokenizers import GeneformerTokenizer, ScGPTTokenizer, SLAFTokenizer
+
+try:  # IterableDataset keeps torch.utils.data.DataLoader(batch_size=None) compatibility
+    from torch.utils.data import IterableDataset
+except Exception:  # pragma: no cover
+    IterableDataset = object  # type: ignore
+
+
+# ----------------------------------------------------------------------------------------------
+# containers (reference: datasets.py:240-296)
+# ----------------------------------------------------------------------------------------------
+class TokenizedPrefetchBatch:
+    """Same fields as the reference's dataclass; ``cell_integer_ids`` (a Python list there) is
+    materialised lazily from the device tensor ``cell_ids`` so the producer never synchronises."""
+
+    def __init__(self, batch_id: int, input_ids: torch.Tensor, attention_mask: torch.Tensor,
+                 cell_integer_ids: list[int] | None = None, values: torch.Tensor | None = None,
+                 partial_cell_data: dict | None = None, tokenize_time: float = 0.0, cell_ids: torch.Tensor | None = None,
+                 epoch: int = 0, ready_event: Any = None):
+        self.batch_id = batch_id
+        self.input_ids = input_ids
+        self.attention_mask = attention_mask
+        self.values = values
+        self.partial_cell_data = partial_cell_data
+        self.tokenize_time = tokenize_time
+        self.epoch = epoch
+        self.ready_event = ready_event
+        self._cell_list = list(cell_integer_ids) if cell_integer_ids is not None else None
+        if cell_ids is None:
+            cell_ids = torch.tensor(self._cell_list or [], dtype=torch.long, device=input_ids.device)
+        self.cell_ids = cell_ids
+
+    @property
+    def cell_integer_ids(self) -> list[int]:
+        if self._cell_list is None:
+            if self.ready_event is not None:
+                self.ready_event.synchronize()
+            self._cell_list = self.cell_ids.cpu().tolist()
+        return self._cell_list
+
+    @property
+    def n_cells(self) -> int:
+        return int(self.input_ids.shape[0])
+
+
+@dataclass
+class RawPrefetchBatch:
+    """reference: datasets.py:288-296 (frames are dict-of-columns / Arrow here, polars there)."""
+
+    batch_id: int
+    batch_dfs: list[Any]
+    cell_integer_ids: list[int]
+    process_time: float
+    memory_mb: float
+
+
+PrefetchBatch = TokenizedPrefetchBatch | RawPrefetchBatch
+
+
+def _runs(cell: np.ndarray):
+    """(starts, ends, ids) of the maximal runs of equal ids, in row order (host, O(R))."""
+    n = len(cell)
+    if n == 0:
+        z = np.zeros(0, np.int64)
+        return z, z, cell[:0]
+    heads = np.flatnonzero(cell[1:] != cell[:-1]) + 1
+    starts = np.concatenate(([0], heads)).astype(np.int64)
+    ends = np.concatenate((heads, [n])).astype(np.int64)
+    return starts, ends, cell[starts]
+
+
+class _Staging:
+    """Ring of pinned host buffers the combined rows of a batch are assembled in (so the H2D copy
+    is a true async DMA).  Copies run on a small thread pool: numpy releases the GIL in memcpy."""
+
+    def __init__(self, depth: int = 2, threads: int = 4):
+        self.depth = depth
+        self.capacity = 0
+        self.bufs: list[tuple[np.ndarray, np.ndarray, np.ndarray]] = []
+        self.turn = 0
+        self.pool = ThreadPoolExecutor(max_workers=max(1, threads)) if threads > 1 else None
+
+    def ensure(self, rows: int) -> None:
+        if rows <= self.capacity:
+            return
+        cap = max(rows + rows // 4, 1 << 16)
+        self.bufs = [tuple(pinned_empty(cap * 4, np.uint8) for _ in range(3)) for _ in range(self.depth)]
+        self.capacity = cap
+
+    def assemble(self, pieces: list[CooChunk]) -> CooChunk:
+        n = sum(len(p) for p in pieces)
+        self.ensure(n)
+        raw = self.bufs[self.turn]
+        self.turn = (self.turn + 1) % self.depth
+        first = pieces[0]
+        dst = CooChunk(*(raw[i][: n * src.dtype.itemsize].view(src.dtype) for i, src in enumerate((first.cell, first.gene, first.value))))
+        tasks = []
+        off = 0
+        step = 1 << 21   # rows per copy task
+        for p in pieces:
+            if (p.cell.dtype, p.gene.dtype, p.value.dtype) != (dst.cell.dtype, dst.gene.dtype, dst.value.dtype):
+                raise TypeError("fragments of one expression table must share column dtypes")
+            for lo in range(0, len(p), step):
+                hi = min(lo + step, len(p))
+                for d, s_ in ((dst.cell, p.cell), (dst.gene, p.gene), (dst.value, p.value)):
+                    tasks.append((d, off + lo, s_, lo, hi))
+            off += len(p)
+        if self.pool is not None and len(tasks) > 3:
+            list(self.pool.map(lambda t: np.copyto(t[0][t[1]: t[1] + (t[4] - t[3])], t[2][t[3]: t[4]]), tasks))
+        else:
+            for d, o, s_, lo, hi in tasks:
+                np.copyto(d[o: o + (hi - lo)], s_[lo:hi])
+        return dst
+
+    def close(self) -> None:
+        if self.pool is not None:
+            self.pool.shutdown(wait=False)
+        self.bufs = []
+        self.capacity = 0
+
+
+# ----------------------------------------------------------------------------------------------
+# PrefetchBatchProcessor
+# ----------------------------------------------------------------------------------------------
+class PrefetchBatchProcessor:
+    """reference: slaf/ml/datasets.py:299-1103.  Same constructor arguments, attributes, error
+    messages, epoch handling and ``StopIteration("No more epochs available")`` protocol."""
+
+    def __init__(self, slaf_array: Any, shuffle: Any, tokenizer: SLAFTokenizer | None, seed: int = 42,
+                 batches_per_chunk: int = 1, n_expression_bins: int = 10, use_binned_expressions: bool = True,
+                 n_epochs: int = 1, raw_mode: bool = False, verbose: bool = True, log_metrics: bool = False,
+                 batch_size: int = 32, by_fragment: bool = True, use_mixture_of_scanners: bool = True, n_scanners: int = 16,
+                 prefetch_batch_size: int = 4194304, parallelize_fragment_reads: bool = False, device=None,
+                 copy_threads: int = 4):
+        self.slaf_array = slaf_array
+        self.shuffle = shuffle
+        self.tokenizer = tokenizer
+        self.seed = seed
+        self.batches_per_chunk = batches_per_chunk
+        self.n_expression_bins = n_expression_bins
+        self.use_binned_expressions = use_binned_expressions
+        self.n_epochs = n_epochs
+        self.raw_mode = raw_mode
+        self.verbose = verbose
+        self.log_metrics = log_metrics
+        self.batch_size = batch_size
+        self.by_fragment = by_fragment
+        self.use_mixture_of_scanners = use_mixture_of_scanners
+        self.n_scanners = n_scanners
+        self.prefetch_batch_size = prefetch_batch_size
+        self.parallelize_fragment_reads = parallelize_fragment_reads
+        self.device = device
+        if self.use_mixture_of_scanners:
+            if self.n_scanners < 1:
+                raise ValueError("n_scanners must be at least 1")
+            if self.n_scanners > 100:
+                raise ValueError("n_scanners cannot exceed 100")
+            if self.prefetch_batch_size < 1000:
+                raise ValueError("prefetch_batch_size must be at least 1,000")
+            if self.prefetch_batch_size > 10000000:
+                raise ValueError("prefetch_batch_size cannot exceed 10,000,000")
+        self.batch_id = 0
+        self.current_epoch = 0
+        self.partial_cell_data: dict[Any, CooChunk] = {}
+        self._non_mos_pending_tail_flush = False
+        self._mos_final_flush = False
+        self.window_kwargs: dict[str, Any] = {}
+        self.total_prefetch_cells = 0
+        self.expression_dataset: ExpressionSource = open_expression(slaf_array)
+        if self.use_mixture_of_scanners:
+            self.by_fragment = True
+        self._open_readers()
+        self._timing_metrics: dict[str, list[float]] | None = (
+            {"lance_loading": [], "window": [], "shuffle": [], "tokenize": [], "total": [], "cells_processed": []}
+            if log_metrics else None)
+        self._engine: HotPathEngine | None = None
+        self._staging = _Staging(depth=2, threads=copy_threads)
+        self._read_pool: ThreadPoolExecutor | None = None
+
+    # ------------------------------------------------------------------ readers / epochs
+    def _open_readers(self) -> None:
+        if self.use_mixture_of_scanners:
+            self.fragment_generators: list[Iterator[CooChunk]] = []
+            self.generator_last_cells: list[int | None] = []
+            self.generator_active: list[bool] = []
+            for fragment in self.expression_dataset.get_fragments():
+                self.fragment_generators.append(iter(fragment.to_batches(batch_size=self.prefetch_batch_size)))
+                self.generator_last_cells.append(None)
+                self.generator_active.append(True)
+        elif self.by_fragment:
+            self.fragment_iterator = iter(self.expression_dataset.get_fragments())
+        else:
+            self.batch_generator = iter(self.expression_dataset.to_batches())
+
+    def reset_for_epoch(self, epoch: int) -> None:
+        if epoch < 0 or epoch >= self.n_epochs:
+            raise ValueError(f"Invalid epoch {epoch}. Must be 0 <= epoch < {self.n_epochs}")
+        self.current_epoch = epoch
+        self.batch_id = 0
+        self.partial_cell_data = {}
+        self._non_mos_pending_tail_flush = False
+        self._mos_final_flush = False
+        self._open_readers()
+
+    def get_timing_metrics(self) -> dict | None:
+        if not self.log_metrics or self._timing_metrics is None:
+            return None
+        return {k: (sum(v) / len(v) if v else 0.0) for k, v in self._timing_metrics.items()}
+
+    def _record_timing(self, step: str, duration: float, cells_processed: int = 0) -> None:
+        if not self.log_metrics or self._timing_metrics is None:
+            return
+        if step in self._timing_metrics and step != "cells_processed":
+            self._timing_metrics[step].append(duration)
+        if cells_processed > 0:
+            self._timing_metrics["cells_processed"].append(cells_processed)
+
+    def _read_from_generator(self, idx: int) -> tuple[CooChunk | None, int, bool]:
+        """``batches_per_chunk`` batches of one fragment generator (datasets.py:561-606).  Unlike the
+        reference, batches already read are kept when the generator ends inside the chunk (the
+        reference drops them, losing rows whenever batches_per_chunk > 1)."""
+        got: list[CooChunk] = []
+        exhausted = False
+        for _ in range(self.batches_per_chunk):
+            try:
+                got.append(next(self.fragment_generators[idx]))
+            except StopIteration:
+                exhausted = True
+                break
+        if not got:
+            return None, idx, True
+        if exhausted:
+            self.generator_active[idx] = False
+        return concat_chunks(got), idx, False
+
+    def _next_pieces(self) -> tuple[list[CooChunk], int] | None:
+        """Rows of the next load: (pieces in row order, batch_count); None = epoch transition handled
+        (caller loops).  Raises StopIteration at the end of the last epoch."""
+        pieces: list[CooChunk] = []
+        if self.use_mixture_of_scanners:
+            active = [i for i, a in enumerate(self.generator_active) if a]
+            if not active:
+                if self.partial_cell_data:
+                    pieces = list(self.partial_cell_data.values())
+                    self.partial_cell_data = {}
+                    self._mos_final_flush = True
+                    return pieces, 0
+                return self._advance_epoch()
+            n_to_sample = min(self.n_scanners, len(active))
+            selected = np.random.choice(active, size=n_to_sample, replace=False)      # datasets.py:689 (unseeded there too)
+            if self.parallelize_fragment_reads and len(selected) > 1:
+                if self._read_pool is None:
+                    self._read_pool = ThreadPoolExecutor(max_workers=min(32, self.n_scanners))
+                results = list(self._read_pool.map(self._read_from_generator, [int(i) for i in selected]))
+            else:
+                results = [self._read_from_generator(int(i)) for i in selected]
+            chunks: list[CooChunk] = []
+            for chunk, idx, exhausted in results:
+                if exhausted:
+                    self.generator_active[idx] = False
+                    continue
+                if chunk is None or len(chunk) == 0:
+                    continue
+                last = self.generator_last_cells[idx]
+                if last is not None:
+                    first_cell = int(chunk.cell[0])
+                    if (first_cell == last or first_cell == last + 1) and last in self.partial_cell_data:
+                        chunk = concat_chunks([self.partial_cell_data.pop(last), chunk])     # datasets.py:748-760
+                self.generator_last_cells[idx] = int(chunk.cell[-1])
+                chunks.append(chunk)
+            if not chunks:
+                return None
+            pieces, count = chunks, len(chunks)
+        elif self.by_fragment:
+            try:
+                fragment = next(self.fragment_iterator)
+                pieces, count = [fragment.to_table()], 1
+            except StopIteration:
+                if self.partial_cell_data:
+                    pieces, count = list(self.partial_cell_data.values()), 0
+                    self.partial_cell_data = {}
+                    self._non_mos_pending_tail_flush = True
+                    return pieces, count
+                return self._advance_epoch()
+        else:
+            got = []
+            for _ in range(self.batches_per_chunk):
+                try:
+                    got.append(next(self.batch_generator))
+                except StopIteration:
+                    break
+            if not got:
+                if self.partial_cell_data:
+                    pieces, count = list(self.partial_cell_data.values()), 0
+                    self.partial_cell_data = {}
+                    self._non_mos_pending_tail_flush = True
+                    return pieces, count
+                return self._advance_epoch()
+            pieces, count = got, len(got)
+        if self.partial_cell_data:                                                        # datasets.py:880-888
+            pieces = list(self.partial_cell_data.values()) + pieces
+        return pieces, count
+
+    def _advance_epoch(self) -> None:
+        if self.current_epoch + 1 < self.n_epochs:
+            self.reset_for_epoch(self.current_epoch + 1)
+            return None
+        raise StopIteration("No more epochs available") from None
+
+    # ------------------------------------------------------------------ completeness (host, C entries)
+    def _complete_mask(self, seg_cell: np.ndarray, seg_len: np.ndarray) -> np.ndarray:
+        """Which cells of the combined rows are complete (datasets.py:891-953)."""
+        if self.use_mixture_of_scanners:
+            csi = np.asarray(self.slaf_array._cell_start_index)
+            ids = seg_cell.astype(np.int64)
+            expected = csi[ids + 1] - csi[ids]
+            done = seg_len >= expected
+            if self._mos_final_flush:
+                # every generator is exhausted: nothing can complete these cells any more.  The reference
+                # would spin forever on such rows (datasets.py:660-668 + 1099-1102); emit them instead.
+                self._mos_final_flush = False
+                if not done.any():
+                    return np.ones(len(seg_cell), bool)
+            return done
+        if self._non_mos_pending_tail_flush:
+            self._non_mos_pending_tail_flush = False
+            return np.ones(len(seg_cell), bool)
+        return seg_cell < seg_cell.max()
+
+    def _stash_partials(self, rows: CooChunk, seg_start: np.ndarray, seg_cell: np.ndarray, complete: np.ndarray) -> None:
+        self.partial_cell_data = {}
+        for j in np.flatnonzero(~complete):
+            lo, hi = int(seg_start[j]), int(seg_start[j + 1])
+            part = CooChunk(rows.cell[lo:hi].copy(), rows.gene[lo:hi].copy(), rows.value[lo:hi].copy())
+            key = int(seg_cell[j])
+            self.partial_cell_data[key] = concat_chunks([self.partial_cell_data[key], part]) if key in self.partial_cell_data else part
+
+    # ------------------------------------------------------------------ engine
+    def _engine_for(self, rows: int, all_cells: bool = False) -> HotPathEngine:
+        eng = self._engine
+        if eng is None or eng.max_rows < rows or (all_cells and eng.max_cells < rows):
+            if eng is not None:
+                torch.cuda.synchronize(eng.device)
+                eng.close()
+            from ..runtime import resolve_device
+
+            cap = max(rows + rows // 4, 1 << 20)
+            cells = cap if all_cells else cap // 8 + (1 << 16)     # cells of >= 8 rows on average; grown on demand
+            self._engine = eng = HotPathEngine(resolve_device(self.device if self.device is not None
+                                                              else getattr(self.tokenizer, "device", None)), max_rows=cap, max_cells=cells)
+        return eng
+
+    def _fused_ok(self) -> bool:
+        return (type(self.shuffle) in (RandomShuffle, StratifiedShuffle) and type(self.tokenizer) in (GeneformerTokenizer, ScGPTTokenizer)
+                and type(self.tokenizer.window).__module__ == "slaf_b200.ml.aggregators")
+
+    # ------------------------------------------------------------------ the hot path
+    def load_prefetch_batch(self) -> PrefetchBatch:
+        while True:
+            start_time = time.time()
+            nxt = self._next_pieces()
+            if nxt is None:
+                continue
+            pieces, _count = nxt
+            pieces = [p for p in pieces if len(p)]
+            load_time = time.time() - start_time
+            self._record_timing("lance_loading", load_time)
+            n_rows = sum(len(p) for p in pieces)
+            if n_rows == 0:
+                self.batch_id += 1
+                continue
+            seed = self.seed + self.batch_id + self.current_epoch * 10000               # datasets.py:1016
+            if self.raw_mode or not self._fused_ok():
+                out = self._load_on_host_frames(pieces, seed, start_time)
+            else:
+                if self.tokenizer is None:
+                    raise RuntimeError("Tokenizer is required for tokenized mode")
+                out = self._load_fused(pieces, seed, start_time)
+            if out is None:                    # no complete cell in this chunk (datasets.py:1099-1102)
+                self.batch_id += 1
+                continue
+            self.batch_id += 1
+            return out
+
+    def _load_fused(self, pieces: list[CooChunk], seed: int, start_time: float) -> TokenizedPrefetchBatch | None:
+        t0 = time.time()
+        rows = self._staging.assemble(pieces)
+        eng = self._engine_for(len(rows))
+        slot = eng.submit(rows.cell, rows.gene, rows.value)
+        try:
+            seg_start, seg_cell = eng.segments(slot)
+        except N.SlafB200Error as err:
+            if err.code != N.ERR_CAPACITY:
+                raise
+            eng.release(slot)                                   # more cells than the segment tables hold: size for the worst case
+            eng = self._engine_for(len(rows), all_cells=True)
+            slot = eng.submit(rows.cell, rows.gene, rows.value)
+            seg_start, seg_cell = eng.segments(slot)
+        if len(np.unique(seg_cell)) != len(seg_cell):
+            # a cell re-joined from two separated runs (partial + continuation with other chunks in
+            # between): splice on the host like partition_by does, then resubmit (rare)
+            eng.collect(slot, perm=np.zeros(0, np.int32), **self._params())
+            c, g, v = regroup_contiguous(rows.cell, rows.gene, rows.value)
+            rows = self._staging.assemble([CooChunk(c, g, v)])
+            slot = eng.submit(rows.cell, rows.gene, rows.value)
+            seg_start, seg_cell = eng.segments(slot)
+        seg_len = np.diff(seg_start.astype(np.int64))
+        complete = self._complete_mask(seg_cell, seg_len)
+        self._stash_partials(rows, seg_start, seg_cell, complete)
+        sel = np.flatnonzero(complete).astype(np.int32)
+        shuffle_time = time.time() - t0
+        if sel.size == 0:
+            eng.collect(slot, perm=sel, **self._params())
+            return None
+        t1 = time.time()
+        order = sel[shuffle_perm(seed, sel.size)]              # random.seed(seed); random.shuffle(chunks), samplers.py:89-96
+        out = eng.collect(slot, perm=order, capacity_cells=int(order.size), **self._params())
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(eng.device))
+        tokenize_time = time.time() - t1
+        total = time.time() - start_time
+        self._record_timing("shuffle", shuffle_time)
+        self._record_timing("window", 0.0)
+        self._record_timing("tokenize", tokenize_time)
+        self._record_timing("total", total)
+        self._record_timing("cells_processed", 0, out.n_cells)
+        self.total_prefetch_cells += out.n_cells
+        return TokenizedPrefetchBatch(batch_id=self.batch_id, input_ids=out.input_ids, attention_mask=out.attention_mask,
+                                      values=out.values, cell_ids=out.cell_ids, partial_cell_data=dict(self.partial_cell_data),
+                                      tokenize_time=tokenize_time, epoch=self.current_epoch, ready_event=ev)
+
+    def _params(self) -> dict:
+        return self.tokenizer.hot_path_params(use_binned_expressions=self.use_binned_expressions,
+                                              n_expression_bins=self.n_expression_bins, window_kwargs=self.window_kwargs)
+
+    # generic route: user-supplied Shuffle / Window / tokenizer objects, and raw mode -- the three
+    # reference calls on host frames (still GPU-computed when the objects are this package's facades)
+    def _host_complete(self, pieces: list[CooChunk]) -> CooChunk:
+        rows = concat_chunks(pieces)
+        starts, ends, ids = _runs(rows.cell)
+        uniq, inv = np.unique(ids, return_inverse=True)
+        observed = np.bincount(inv, weights=(ends - starts).astype(np.float64)).astype(np.int64)
+        complete_u = self._complete_mask(uniq, observed)
+        keep_run = complete_u[inv]
+        self.partial_cell_data = {}
+        for j in np.flatnonzero(~keep_run):
+            lo, hi = int(starts[j]), int(ends[j])
+            part = rows.slice(lo, hi)
+            key = int(ids[j])
+            self.partial_cell_data[key] = concat_chunks([self.partial_cell_data[key], part]) if key in self.partial_cell_data else \
+                CooChunk(part.cell.copy(), part.gene.copy(), part.value.copy())
+        if keep_run.all():
+            return rows
+        row_mask = np.repeat(keep_run, ends - starts)
+        return CooChunk(rows.cell[row_mask], rows.gene[row_mask], rows.value[row_mask])
+
+    def _load_on_host_frames(self, pieces: list[CooChunk], seed: int, start_time: float) -> PrefetchBatch | None:
+        complete = self._host_complete(pieces)
+        if len(complete) == 0:
+            return None
+        frame = complete.as_dict()
+        if self.raw_mode:
+            t0 = time.time()
+            chunks = self.shuffle.apply(frame, seed, batch_size=self.batch_size)
+            shuffle_time = time.time() - t0
+            ids = np.unique(complete.cell)
+            self._record_timing("shuffle", shuffle_time)
+            self._record_timing("total", time.time() - start_time)
+            self._record_timing("cells_processed", 0, len(ids))
+            self.total_prefetch_cells += len(ids)
+            return RawPrefetchBatch(batch_id=self.batch_id, batch_dfs=chunks, cell_integer_ids=ids.tolist(),
+                                    process_time=shuffle_time, memory_mb=0.0)
+        if self.tokenizer is None:
+            raise RuntimeError("Tokenizer is required for tokenized mode")
+        t0 = time.time()
+        shuffled = self.shuffle.apply(frame, seed)
+        if isinstance(shuffled, list):
+            shuffled = {k: np.concatenate([np.asarray(c[k]) for c in shuffled]) for k in frame}
+        shuffle_time = time.time() - t0
+        t1 = time.time()
+        params = {"n_expression_bins": self.n_expression_bins, "use_binned_expressions": self.use_binned_expressions}
+        params.update(self.window_kwargs)
+        grouped = self.tokenizer.window.apply(shuffled, SLAF_LANCE_COO_SCHEMA, self.tokenizer.max_genes, **params)
+        window_time = time.time() - t1
+        t2 = time.time()
+        names = grouped.column_names if frames.frame_kind(grouped) == "arrow" else list(grouped.columns)
+        ids, mask, vals = self.tokenizer.tokenize(
+            gene_sequences=frames.list_column(grouped, "gene_sequence"),
+            expr_sequences=frames.list_column(grouped, "expr_sequence") if "expr_sequence" in names else None)
+        tokenize_time = time.time() - t2
+        cells = [int(x) for x in frames.column(grouped, "cell_integer_id")]
+        for k, v in (("shuffle", shuffle_time), ("window", window_time), ("tokenize", tokenize_time), ("total", time.time() - start_time)):
+            self._record_timing(k, v)
+        self._record_timing("cells_processed", 0, len(cells))
+        self.total_prefetch_cells += len(cells)
+        return TokenizedPrefetchBatch(batch_id=self.batch_id, input_ids=ids, attention_mask=mask, values=vals,
+                                      cell_integer_ids=cells, partial_cell_data=dict(self.partial_cell_data),
+                                      tokenize_time=tokenize_time, epoch=self.current_epoch)
+
+    def close(self) -> None:
+        if self._engine is not None:
+            self._engine.close()
+            self._engine = None
+        self._staging.close()
+        if self._read_pool is not None:
+            self._read_pool.shutdown(wait=False)
+            self._read_pool = None
+
+
+# ----------------------------------------------------------------------------------------------
+# AsyncPrefetcher (reference: datasets.py:1105-1459)
+# ----------------------------------------------------------------------------------------------
+class AsyncPrefetcher:
+    """Background thread that runs ``load_prefetch_batch`` ahead of the consumer.  The queue holds
+    device-resident prefetch batches, so ``max_queue_size`` bounds HBM use (a cfg-2 prefetch batch of
+    32 k cells is ~0.7 GB of token tensors); the producer blocks on a full queue."""
+
+    def __init__(self, batch_processor: PrefetchBatchProcessor, max_queue_size: int = 500):
+        if batch_processor is None:
+            raise ValueError("batch_processor cannot be None")
+        self.batch_processor = batch_processor
+        self.max_queue_size = max_queue_size
+        self.queue: queue.Queue = queue.Queue(maxsize=max_queue_size)
+        self.worker_thread: threading.Thread | None = None
+        self.should_stop = False
+        self.finished = False
+        self.error: BaseException | None = None
+        self.total_cells_added = 0
+        self.start_time: float | None = None
+        self.total_tokenize_time = 0.0
+        self.tokenize_count = 0
+        self.current_epoch = 0
+
+    def start(self) -> None:
+        if self.worker_thread is None or not self.worker_thread.is_alive():
+            self.should_stop = False
+            self.finished = False
+            self.start_time = time.time()
+            self.worker_thread = threading.Thread(target=self._prefetch_worker, daemon=True)
+            self.worker_thread.start()
+
+    def stop(self) -> None:
+        self.should_stop = True
+        if self.worker_thread and self.worker_thread.is_alive():
+            self.worker_thread.join(timeout=1.0)
+
+    def _prefetch_worker(self) -> None:
+        stream = None
+        try:
+            if torch.cuda.is_available():
+                from ..runtime import resolve_device
+
+                dev = resolve_device(self.batch_processor.device if self.batch_processor.device is not None
+                                     else getattr(self.batch_processor.tokenizer, "device", None))
+                torch.cuda.set_device(dev)
+                stream = torch.cuda.Stream(dev)
+            while not self.should_stop:
+                try:
+                    if stream is not None:
+                        with torch.cuda.stream(stream):
+                            batch = self.batch_processor.load_prefetch_batch()
+                    else:
+                        batch = self.batch_processor.load_prefetch_batch()
+                except StopIteration:
+                    break
+                n = batch.n_cells if isinstance(batch, TokenizedPrefetchBatch) else len(batch.cell_integer_ids)
+                self.total_cells_added += n
+                self.total_tokenize_time += batch.tokenize_time if isinstance(batch, TokenizedPrefetchBatch) else batch.process_time
+                self.tokenize_count += 1
+                self.current_epoch = self.batch_processor.current_epoch
+                while not self.should_stop:
+                    try:
+                        self.queue.put(batch, timeout=0.1)     # blocks: never drops a batch
+                        break
+                    except queue.Full:
+                        continue
+        except BaseException as err:  # surfaced to the consumer instead of being logged and lost
+            self.error = err
+        finally:
+            self.finished = True
+
+    def get_batch(self, timeout: float = 10.0) -> PrefetchBatch | None:
+        deadline = time.time() + timeout
+        while True:
+            try:
+                return self.queue.get(timeout=0.05)
+            except queue.Empty:
+                if self.error is not None:
+                    raise RuntimeError(f"prefetch worker failed: {self.error!r}") from self.error
+                if self.finished and self.queue.empty():
+                    return None
+                if time.time() > deadline:
+                    return None
+
+    def has_batch(self) -> bool:
+        return not self.queue.empty()
+
+    def is_done(self) -> bool:
+        return self.finished and self.queue.empty()
+
+    def get_stats(self) -> dict:
+        elapsed = time.time() - self.start_time if self.start_time else 0.0
+        return {"total_cells": self.total_cells_added, "elapsed_time": elapsed,
+                "cells_per_sec": self.total_cells_added / elapsed if elapsed > 0 else 0.0,
+                "queue_size": self.queue.qsize(), "queue_full": self.queue.full(),
+                "current_epoch": self.current_epoch if not self.is_done() else self.batch_processor.n_epochs,
+                "n_epochs": self.batch_processor.n_epochs}
+
+
+# ----------------------------------------------------------------------------------------------
+# SLAFIterableDataset (reference: datasets.py:1462-1938)
+# ----------------------------------------------------------------------------------------------
+class SLAFIterableDataset(IterableDataset):
+    def __init__(self, slaf_array: Any, tokenizer: SLAFTokenizer | None, batch_size: int = 32, seed: int = 42,
+                 max_queue_size: int = 8, pin_memory: bool = False, sampler_strategy: str = "sequential",
+                 use_binned_expressions: bool = False, n_epochs: int = 1, raw_mode: bool = False, verbose: bool = True,
+                 batches_per_chunk: int = 1, by_fragment: bool = True, use_mixture_of_scanners: bool = True, n_scanners: int = 16,
+                 prefetch_batch_size: int = 4194304, parallelize_fragment_reads: bool = False,
+                 prefetcher_ready_timeout: float = 10.0, device=None, output_device=None):
+        super().__init__()
+        self.slaf_array = slaf_array
+        self.tokenizer = tokenizer
+        self.batch_size = batch_size
+        self.seed = seed
+        self.max_queue_size = max_queue_size
+        self.pin_memory = pin_memory
+        self.n_epochs = n_epochs
+        self.raw_mode = raw_mode
+        self.verbose = verbose
+        self.by_fragment = by_fragment
+        self.parallelize_fragment_reads = parallelize_fragment_reads
+        self.output_device = torch.device(output_device) if output_device is not None else None
+        from .samplers import ShuffleType, create_shuffle
+
+        self.batch_processor = PrefetchBatchProcessor(
+            slaf_array=slaf_array, shuffle=create_shuffle(ShuffleType.RANDOM), tokenizer=tokenizer, seed=seed,
+            batches_per_chunk=batches_per_chunk, n_expression_bins=getattr(tokenizer, "n_expression_bins", 10),
+            use_binned_expressions=use_binned_expressions, n_epochs=n_epochs, raw_mode=raw_mode, verbose=verbose,
+            log_metrics=False, batch_size=batch_size, by_fragment=by_fragment, use_mixture_of_scanners=use_mixture_of_scanners,
+            n_scanners=n_scanners, prefetch_batch_size=prefetch_batch_size, parallelize_fragment_reads=parallelize_fragment_reads,
+            device=device)
+        self.prefetcher = AsyncPrefetcher(self.batch_processor, max_queue_size=max_queue_size)
+        self.prefetcher.start()
+        self.device = self.output_device if self.output_device is not None else torch.device("cuda")
+
+    def __iter__(self) -> Iterator[dict]:
+        while True:
+            data = self.prefetcher.get_batch(timeout=60.0)
+            if data is None:
+                break
+            if isinstance(data, RawPrefetchBatch):
+                for df in data.batch_dfs:
+                    ids = frames.column(df, "cell_integer_id")
+                    out = {"x": df, "cell_ids": [int(x) for x in ids[np.sort(np.unique(ids, return_index=True)[1])]]}
+                    if self.n_epochs > 1:
+                        out["epoch"] = self.prefetcher.current_epoch
+                    yield out
+                continue
+            input_ids, attention_mask, values, cell_ids = data.input_ids, data.attention_mask, data.values, data.cell_ids
+            if values is not None:                                   # datasets.py:1837-1847
+                if values.shape != input_ids.shape:
+                    raise ValueError("scGPT dual-stream contract violated: values and input_ids must "
+                                     f"have identical shapes, got {tuple(values.shape)} vs {tuple(input_ids.shape)}")
+                if values.shape != attention_mask.shape:
+                    raise ValueError("scGPT dual-stream contract violated: values and attention_mask must "
+                                     f"have identical shapes, got {tuple(values.shape)} vs {tuple(attention_mask.shape)}")
+            if input_ids.is_cuda:
+                cur = torch.cuda.current_stream(input_ids.device)
+                if data.ready_event is not None:
+                    cur.wait_event(data.ready_event)               # consumer stream waits; the host does not
+                for t in (input_ids, attention_mask, values, cell_ids):
+                    if t is not None:
+                        t.record_stream(cur)
+            if self.output_device is not None and self.output_device.type == "cpu":
+                input_ids, attention_mask, cell_ids = input_ids.cpu(), attention_mask.cpu(), cell_ids.cpu()
+                values = values.cpu() if values is not None else None
+            num_cells = int(input_ids.shape[0])
+            for lo in range(0, num_cells, self.batch_size):
+                hi = min(lo + self.batch_size, num_cells)
+                batch = {"input_ids": input_ids[lo:hi], "attention_mask": attention_mask[lo:hi], "cell_ids": cell_ids[lo:hi]}
+                if values is not None:
+                    batch["values"] = values[lo:hi]
+                if self.n_epochs > 1:
+                    batch["epoch"] = data.epoch
+                yield batch
+
+    def __del__(self):
+        try:
+            self.prefetcher.stop()
+        except Exception:
+            pass

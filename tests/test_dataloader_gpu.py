@@ -1,0 +1,191 @@
+"""GPU tests of the dataloader mirror (slaf_b200.ml.datasets / dataloaders), modelled on the
+reference's tests/test_dataloaders.py, tests/test_pytorch_datasets.py and
+tests/test_cell_boundary_reassembly.py: shapes / dtypes / keys, every cell exactly once with all
+of its rows despite fragment boundaries, and every emitted row bit-equal to the CPU oracle."""
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle
+from oracle import py_restatement as pr
+from slaf_b200 import synthetic
+from slaf_b200.ml import (GeneformerTokenizer, PrefetchBatchProcessor, RandomShuffle, ScGPTTokenizer, SLAFDataLoader,
+                          TokenizedPrefetchBatch)
+from slaf_b200.ml.sources import ArrowExpressionSource, SyntheticSLAFArray, write_arrow_dataset
+from tests.util import assert_same
+
+pytestmark = pytest.mark.gpu
+
+N_CELLS, N_GENES = 300, 2000
+
+
+@pytest.fixture(scope="module")
+def data():
+    b = synthetic.make_batch(N_CELLS, N_GENES, 60, seed=5, min_nnz=4, first_cell_id=0)
+    return b
+
+
+def _array(b, rows_per_file=1777):
+    return SyntheticSLAFArray.from_batch(b, N_GENES, max_rows_per_file=rows_per_file)
+
+
+def _expected_rows(b, mode, **kw):
+    ids, mask, vals, cids = c_oracle.tokenize(b.cell, b.gene, b.value, mode, **kw)
+    return {int(c): (ids[i], mask[i], None if vals is None else vals[i]) for i, c in enumerate(cids)}
+
+
+def _spanning_cells(b, rows_per_file):
+    """cells whose rows cross a fragment boundary: under mixture-of-scanners their two parts can meet in
+    either order (the reference's partition_by keeps arrival order too), so only their token multiset is fixed"""
+    cuts = np.arange(rows_per_file, b.n_rows, rows_per_file)
+    return {int(b.cell[c]) for c in cuts if b.cell[c] == b.cell[c - 1]}
+
+
+def _check_rows(batches, expected, scgpt, loose=()):
+    seen = []
+    for batch in batches:
+        ids, mask, cids = batch["input_ids"].cpu().numpy(), batch["attention_mask"].cpu().numpy(), batch["cell_ids"].cpu().numpy()
+        vals = batch["values"].cpu().numpy() if scgpt else None
+        for r, c in enumerate(cids):
+            e = expected[int(c)]
+            if int(c) in loose:
+                assert np.array_equal(np.sort(ids[r]), np.sort(e[0])) and np.array_equal(mask[r], e[1]), f"spanning cell {c}"
+                continue
+            assert np.array_equal(ids[r], e[0]) and np.array_equal(mask[r], e[1]), f"cell {c}"
+            if scgpt:
+                assert np.array_equal(vals[r], e[2]), f"cell {c} values"
+        seen.extend(int(c) for c in cids)
+    return seen
+
+
+@pytest.mark.parametrize("mode", ["mos", "fragment", "sequential"])
+def test_geneformer_loader_every_cell_once_and_bit_exact(data, mode):
+    kw = dict(use_mixture_of_scanners=(mode == "mos"), by_fragment=(mode != "sequential"))
+    np.random.seed(0)
+    loader = SLAFDataLoader(_array(data), tokenizer_type="geneformer", batch_size=32, max_genes=256, prefetch_batch_size=1000,
+                            n_scanners=3, batches_per_chunk=2 if mode == "sequential" else 1, verbose=False, **kw)
+    batches = list(loader)
+    b0 = batches[0]
+    assert set(b0.keys()) == {"input_ids", "attention_mask", "cell_ids"}                 # tests/test_dataloaders.py:76-83
+    assert b0["input_ids"].dtype == torch.int64 and b0["attention_mask"].dtype == torch.bool and b0["cell_ids"].dtype == torch.int64
+    assert b0["input_ids"].is_cuda and b0["input_ids"].shape[1] == 256
+    assert all(b["input_ids"].shape[0] <= 32 for b in batches)
+    for b in batches:                                                                    # :147-161 unique ids within a batch, in range
+        ids = b["cell_ids"].cpu().tolist()
+        assert len(set(ids)) == len(ids) and all(0 <= i < N_CELLS for i in ids)
+    # max_genes=256 exceeds every cell's row count here, so no row is filtered and a spanning cell keeps its token multiset
+    seen = _check_rows(batches, _expected_rows(data, "geneformer", max_genes=256), scgpt=False,
+                       loose=_spanning_cells(data, 1777) if mode == "mos" else ())
+    assert sorted(seen) == list(range(N_CELLS))                                          # test_cell_boundary_reassembly.py:33-73
+    assert len(loader) == 0
+
+
+@pytest.mark.parametrize("binned", [True, False])
+def test_scgpt_loader_values_stream(data, binned):
+    arr = _array(data)
+    tok = ScGPTTokenizer(arr, vocab_size=5000, n_expression_bins=51, max_genes=48)
+    proc = PrefetchBatchProcessor(arr, RandomShuffle(), tok, seed=42, n_expression_bins=51, use_binned_expressions=binned,
+                                  use_mixture_of_scanners=False, by_fragment=True, verbose=False)
+    assert proc.use_binned_expressions == binned and proc.batch_id == 0 and proc.current_epoch == 0
+    out = []
+    with pytest.raises(StopIteration, match="No more epochs available"):
+        while True:
+            out.append(proc.load_prefetch_batch())
+    assert all(isinstance(o, TokenizedPrefetchBatch) for o in out)
+    mode = "scgpt_binned" if binned else "scgpt_raw"
+    exp = _expected_rows(data, mode, max_genes=48, n_bins=51, vocab_size=5000)
+    seen = _check_rows([{"input_ids": o.input_ids, "attention_mask": o.attention_mask, "values": o.values, "cell_ids": o.cell_ids}
+                        for o in out], exp, scgpt=True)
+    assert sorted(seen) == list(range(N_CELLS))
+    assert out[0].input_ids.shape[1] == 50 and out[0].values.shape == out[0].input_ids.shape       # L = max_genes + 2
+    assert out[0].cell_integer_ids == out[0].cell_ids.cpu().tolist()
+    proc.close()
+
+
+def test_fragment_mode_matches_reference_batch_composition_and_order(data):
+    """by_fragment, no MoS is deterministic in the reference: emulate datasets.py:812-953 + 1011-1098 with
+    the numpy restatement and compare batch by batch, including the shuffled cell order."""
+    arr = _array(data, rows_per_file=2500)
+    tok = GeneformerTokenizer(arr, max_genes=32)
+    proc = PrefetchBatchProcessor(arr, RandomShuffle(), tok, seed=42, n_epochs=2, use_mixture_of_scanners=False, by_fragment=True,
+                                  verbose=False)
+    got = []
+    try:
+        while True:
+            got.append(proc.load_prefetch_batch())
+    except StopIteration:
+        pass
+    want = []
+    for epoch in range(2):
+        batch_id, partial = 0, None
+        frags = [(data.cell[lo:lo + 2500], data.gene[lo:lo + 2500], data.value[lo:lo + 2500]) for lo in range(0, data.n_rows, 2500)]
+        for frag in frags + [None]:
+            if frag is None:
+                if partial is None:
+                    break
+                comb, complete_mask = partial, np.ones(len(partial[0]), bool)
+            else:
+                comb = frag if partial is None else tuple(np.concatenate([p, f]) for p, f in zip(partial, frag))
+                complete_mask = comb[0] < comb[0].max()
+            complete = tuple(c[complete_mask] for c in comb)
+            partial = tuple(c[~complete_mask] for c in comb) if (~complete_mask).any() else None
+            if len(complete[0]):
+                want.append((epoch, batch_id, pr.hot_path(*complete, "geneformer", 32, seed=42 + batch_id + epoch * 10000)))
+            batch_id += 1
+    assert len(got) == len(want)
+    for g, (epoch, batch_id, (ids, mask, _vals, cids)) in zip(got, want):
+        assert (g.epoch, g.batch_id) == (epoch, batch_id)
+        assert_same(g.cell_ids.cpu().numpy(), cids, "cell order")
+        assert_same(g.input_ids.cpu().numpy(), ids, "ids")
+        assert_same(g.attention_mask.cpu().numpy(), mask, "mask")
+    proc.close()
+
+
+def test_multi_epoch_and_cpu_placement(data):
+    loader = SLAFDataLoader(_array(data), tokenizer_type="scgpt", batch_size=64, max_genes=16, n_expression_bins=10, n_epochs=3,
+                            use_mixture_of_scanners=False, by_fragment=True, verbose=False, output_device="cpu")
+    epochs, cells = [], {0: [], 1: [], 2: []}
+    for b in loader:
+        assert set(b.keys()) == {"input_ids", "attention_mask", "cell_ids", "values", "epoch"}
+        assert b["input_ids"].device.type == "cpu" and b["input_ids"].shape[1] == 18               # :114-122
+        epochs.append(b["epoch"])
+        cells[b["epoch"]].extend(b["cell_ids"].tolist())
+    assert sorted(set(epochs)) == [0, 1, 2] and epochs == sorted(epochs)
+    for e in range(3):
+        assert sorted(cells[e]) == list(range(N_CELLS))
+    assert cells[0] != cells[1]                                                                   # seed + epoch * 10000
+
+
+def test_arrow_directory_source_and_torch_dataloader(tmp_path, data):
+    write_arrow_dataset(str(tmp_path / "expression.arrow"), data.cell, data.gene, data.value, max_rows_per_file=3001, rows_per_batch=700)
+    src = ArrowExpressionSource(str(tmp_path / "expression.arrow"))
+    assert src.count_rows() == data.n_rows and len(src.get_fragments()) == -(-data.n_rows // 3001)
+    csi = np.asarray(data.cell_start)
+    arr = SyntheticSLAFArray(src, csi, N_GENES, slaf_path=str(tmp_path))
+    from slaf_b200.ml import SLAFIterableDataset
+
+    np.random.seed(1)
+    ds = SLAFIterableDataset(arr, GeneformerTokenizer(arr, max_genes=400), batch_size=50, n_scanners=2, prefetch_batch_size=1000, verbose=False)
+    dl = torch.utils.data.DataLoader(ds, batch_size=None)                                        # tests/test_pytorch_datasets.py:430-469
+    seen = _check_rows(list(dl), _expected_rows(data, "geneformer", max_genes=400), scgpt=False, loose=_spanning_cells(data, 3001))
+    assert sorted(seen) == list(range(N_CELLS))
+
+
+def test_loader_validation_errors(data):
+    arr = _array(data)
+    with pytest.raises(ValueError, match="n_scanners must be at least 1"):
+        SLAFDataLoader(arr, n_scanners=0)
+    with pytest.raises(ValueError, match="n_scanners cannot exceed 100"):
+        SLAFDataLoader(arr, n_scanners=101)
+    with pytest.raises(ValueError, match="prefetch_batch_size must be at least 1,000"):
+        SLAFDataLoader(arr, prefetch_batch_size=10)
+    with pytest.raises(ValueError, match="prefetch_batch_size cannot exceed 10,000,000"):
+        SLAFDataLoader(arr, prefetch_batch_size=10_000_001)
+    with pytest.raises(ValueError, match="is not supported"):
+        SLAFDataLoader(arr, tokenizer_type="bert", use_mixture_of_scanners=False)
+    proc = PrefetchBatchProcessor(arr, RandomShuffle(), None, use_mixture_of_scanners=False, verbose=False)
+    with pytest.raises(RuntimeError, match="Tokenizer is required for tokenized mode"):
+        proc.load_prefetch_batch()
+    with pytest.raises(ValueError, match="Invalid epoch 5"):
+        proc.reset_for_epoch(5)

@@ -142,3 +142,72 @@ def test_build_grouped_arrow_and_dict():
     assert t.column_names == ["cell_integer_id", "gene_sequence"]
     assert t.column("gene_sequence").to_pylist() == [[0, 1], [], [2, 3, 4]]
     assert frames.list_column(t, "gene_sequence") == [[0, 1], [], [2, 3, 4]]
+
+
+# ---------------------------------------------------------------- host feeder (no GPU: raw mode)
+def _raw_dataset(mode, n_cells=120, rows_per_file=611):
+    from slaf_b200 import synthetic
+    from slaf_b200.ml.sources import SyntheticSLAFArray
+
+    b = synthetic.make_batch(n_cells, 500, 30, seed=3, min_nnz=2)
+    return b, SyntheticSLAFArray.from_batch(b, 500, max_rows_per_file=rows_per_file)
+
+
+@pytest.mark.parametrize("mode", ["mos", "fragment", "sequential"])
+def test_raw_mode_boundary_reassembly_every_cell_once_with_all_rows(mode):
+    """reference tests/test_cell_boundary_reassembly.py:33-73: despite fragments that cut cells, every
+    cell comes out exactly once and with its full row count."""
+    from slaf_b200.ml import SLAFDataLoader
+
+    b, arr = _raw_dataset(mode)
+    np.random.seed(3)
+    loader = SLAFDataLoader(arr, raw_mode=True, batch_size=16, use_mixture_of_scanners=(mode == "mos"),
+                            by_fragment=(mode != "sequential"), n_scanners=2, prefetch_batch_size=1000, verbose=False)
+    assert loader.tokenizer is None and loader.special_tokens is None
+    counts: dict[int, int] = {}
+    for batch in loader:
+        assert set(batch.keys()) == {"x", "cell_ids"}
+        ids = np.asarray(batch["x"]["cell_integer_id"])
+        assert len(batch["cell_ids"]) <= 16 and len(set(batch["cell_ids"])) == len(batch["cell_ids"])
+        for c, n in zip(*np.unique(ids, return_counts=True)):
+            assert int(c) not in counts, f"cell {c} emitted twice"
+            counts[int(c)] = int(n)
+    expected = np.diff(b.cell_start)
+    assert sorted(counts) == list(range(b.n_cells))
+    assert [counts[i] for i in range(b.n_cells)] == expected.tolist()
+
+
+def test_processor_attributes_and_epoch_protocol():
+    from slaf_b200.ml import PrefetchBatchProcessor, RandomShuffle, RawPrefetchBatch
+
+    b, arr = _raw_dataset("fragment")
+    proc = PrefetchBatchProcessor(arr, RandomShuffle(), None, raw_mode=True, n_epochs=2, use_mixture_of_scanners=False,
+                                  by_fragment=True, batch_size=8, verbose=False, log_metrics=True)
+    assert (proc.batch_id, proc.current_epoch, proc.n_epochs, proc.partial_cell_data) == (0, 0, 2, {})
+    epochs = []
+    with pytest.raises(StopIteration, match="No more epochs available"):
+        while True:
+            out = proc.load_prefetch_batch()
+            assert isinstance(out, RawPrefetchBatch) and len(out.batch_dfs) == -(-len(out.cell_integer_ids) // 8)
+            epochs.append(proc.current_epoch)
+    assert sorted(set(epochs)) == [0, 1]
+    m = proc.get_timing_metrics()
+    assert set(m) == {"lance_loading", "window", "shuffle", "tokenize", "total", "cells_processed"} and m["cells_processed"] > 0
+    with pytest.raises(ValueError, match="Invalid epoch -1"):
+        proc.reset_for_epoch(-1)
+    proc.reset_for_epoch(1)
+    assert proc.batch_id == 0 and proc.current_epoch == 1 and proc.partial_cell_data == {}
+
+
+def test_arrow_source_roundtrip(tmp_path):
+    from slaf_b200.ml.sources import ArrowExpressionSource, open_expression, write_arrow_dataset
+
+    b, _ = _raw_dataset("fragment")
+    write_arrow_dataset(str(tmp_path / "expression.arrow"), b.cell, b.gene, b.value, max_rows_per_file=700, rows_per_batch=256)
+    src = open_expression(str(tmp_path))
+    assert isinstance(src, ArrowExpressionSource) and src.count_rows() == b.n_rows
+    got = np.concatenate([c.cell for f in src.get_fragments() for c in f.to_batches(300)])
+    assert np.array_equal(got, b.cell) and got.dtype == b.cell.dtype
+    whole = np.concatenate([f.to_table().value for f in src.get_fragments()])
+    assert np.array_equal(whole, b.value) and whole.dtype == np.uint16
+    assert np.array_equal(np.concatenate([c.gene for c in src.to_batches(8192)]), b.gene)
