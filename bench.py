@@ -202,6 +202,49 @@ def run_reference(args, w):
     print(json.dumps(line), flush=True)
 
 
+def loader_rate(w, batches, dev, value_dtype):
+    """cells/s through the drop-in SLAFIterableDataset (what SLAFDataLoader iterates) (host feeder + boundary handling + fused device
+    pass + batch slicing), over an in-memory expression table whose fragments cut cells: the call a user of
+    the reference makes.  Per-rank figure (every rank runs its own loader over its own shard)."""
+    import torch
+
+    from slaf_b200.ml import GeneformerTokenizer, ScGPTTokenizer, SLAFIterableDataset
+    from slaf_b200.ml.sources import ArrayExpressionSource, SyntheticSLAFArray
+
+    cell = np.concatenate([b.cell for b in batches])
+    gene = np.concatenate([b.gene for b in batches])
+    value = np.concatenate([b.value for b in batches])
+    first = int(cell[0])
+    starts = np.concatenate([[0]] + [b.cell_start[1:] + off for b, off in zip(batches, np.cumsum([0] + [b.n_rows for b in batches[:-1]]))])
+    csi = np.zeros(first + len(starts), np.int64)
+    csi[first:] = starts
+    src = ArrayExpressionSource(cell, gene, value, max_rows_per_file=1 << 24)      # 16.8 M-row fragments, not cell aligned
+    pinned = src.pin()
+    arr = SyntheticSLAFArray(src, csi, w["n_genes"])
+    out = {"pinned_source": bool(pinned), "fragments": len(src.get_fragments()), "rows": int(len(cell))}
+    for bs in (32, 1024):
+        rates = []
+        for _rep in range(2):
+            tok = (ScGPTTokenizer(arr, vocab_size=w["vocab"], n_expression_bins=w["n_bins"], max_genes=w["max_genes"], device=dev)
+                   if w["tokenizer"] == "scgpt" else GeneformerTokenizer(arr, vocab_size=w["vocab"], max_genes=w["max_genes"], device=dev))
+            loader = SLAFIterableDataset(arr, tok, batch_size=bs, use_binned_expressions=w["binned"], use_mixture_of_scanners=False,
+                                         by_fragment=True, verbose=False, device=dev, max_queue_size=4)
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            n = 0
+            last = None
+            for batch in loader:
+                n += batch["input_ids"].shape[0]
+                last = batch
+            _ = last["cell_ids"].cpu()                       # D2H read of the last batch's result
+            torch.cuda.synchronize(dev)
+            rates.append(n / (time.perf_counter() - t0))
+            del loader, last, batch
+        out[f"cells_per_s_batch{bs}"] = max(rates)
+    src.unpin()
+    return out
+
+
 # ----------------------------------------------------------------------------- B200 arm
 def main():
     ap = argparse.ArgumentParser()
@@ -214,6 +257,7 @@ def main():
     ap.add_argument("--value-dtype", default="uint16", choices=["uint16", "float32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-loader", action="store_true")
     ap.add_argument("--verify-cells", type=int, default=2048)
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
@@ -346,6 +390,9 @@ def main():
         e2e = {"value": sum_over_ranks(cells_e) / dt, "unit": "cells/s", "h2d_bytes_per_step": h2d_bytes // args.steps,
                "d2h_bytes_per_step": d2h_e // args.steps, "ms_per_step": 1000.0 * dt / args.steps,
                "h2d_gbs_per_gpu": h2d_bytes / dt / 1e9, "h2d_copy_gbs": (h2d_bytes / (tme["h2d_ms"] / 1e3) / 1e9) if tme["h2d_ms"] else None}
+
+        if not args.no_loader:
+            e2e["loader"] = loader_rate(w, batches, dev, args.value_dtype)
 
     clocks = sampler.stop() if rank == 0 else None
     if rank != 0:

@@ -151,6 +151,11 @@ int slafb_tokenize(slafb_ctx *ctx, const slafb_coo *in, const slafb_params *p, c
  * up to three submits may precede the collect of the oldest batch.  Replaces the AsyncPrefetcher hand-off
  * (slaf/ml/datasets.py:1242-1294) for the device-side part of the work. */
 int slafb_submit(slafb_ctx *ctx, const slafb_coo *in, void *stream, int32_t *slot);
+/* submit() for a batch that is the concatenation of n_pieces row blocks (all host or all device, same
+ * dtypes): the partial cells carried over plus the fragment chunks just read (datasets.py:748-760,
+ * 880-888).  Host blocks are copied into the slot's staging columns straight from where they live,
+ * so with pinned / registered source memory the feeder does no host-side assembly at all. */
+int slafb_submit_pieces(slafb_ctx *ctx, const slafb_coo *pieces, int32_t n_pieces, void *stream, int32_t *slot);
 int slafb_collect(slafb_ctx *ctx, int32_t slot, const slafb_params *p, const slafb_out *out,
                   int64_t *n_cells, void *stream);
 
@@ -193,6 +198,10 @@ int slafb_gene_stats(slafb_ctx *ctx, const slafb_coo *in, int64_t n_genes, uint6
 /* Pinned host memory for the feeder's staging buffers (so H2D copies are truly async). */
 int slafb_host_alloc(void **ptr, size_t bytes);
 int slafb_host_free(void *ptr);
+/* Page-lock memory the caller already owns (e.g. the column buffers of an in-memory / memory-mapped
+ * expression table), so slices of it are DMA sources without a staging copy. */
+int slafb_host_register(void *ptr, size_t bytes);
+int slafb_host_unregister(void *ptr);
 
 /* Timing / counters since the previous call (synchronises the context's streams). */
 int slafb_get_timing(slafb_ctx *ctx, slafb_timing *t);

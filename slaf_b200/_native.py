@@ -31,7 +31,7 @@ SHUFFLE_NONE, SHUFFLE_SEED, SHUFFLE_PERM = 0, 1, 2
 FLAG_CHECK_CONTIGUOUS = 1
 
 EXPORTS = [
-    "slafb_version", "slafb_create", "slafb_destroy", "slafb_last_error", "slafb_tokenize", "slafb_submit",
+    "slafb_version", "slafb_create", "slafb_destroy", "slafb_last_error", "slafb_tokenize", "slafb_submit", "slafb_submit_pieces", "slafb_host_register", "slafb_host_unregister",
     "slafb_collect", "slafb_segments", "slafb_window", "slafb_tokenize_lists", "slafb_shuffle_perm", "slafb_gene_stats",
     "slafb_host_alloc", "slafb_host_free", "slafb_get_timing",
 ]
@@ -121,6 +121,9 @@ def lib() -> ctypes.CDLL:
     L.slafb_destroy.argtypes = [c_void_p]
     L.slafb_tokenize.argtypes = [c_void_p, POINTER(Coo), POINTER(Params), POINTER(Out), POINTER(c_int64), c_void_p]
     L.slafb_submit.argtypes = [c_void_p, POINTER(Coo), c_void_p, POINTER(c_int32)]
+    L.slafb_submit_pieces.argtypes = [c_void_p, POINTER(Coo), c_int32, c_void_p, POINTER(c_int32)]
+    L.slafb_host_register.argtypes = [c_void_p, c_size_t]
+    L.slafb_host_unregister.argtypes = [c_void_p]
     L.slafb_collect.argtypes = [c_void_p, c_int32, POINTER(Params), POINTER(Out), POINTER(c_int64), c_void_p]
     L.slafb_segments.argtypes = [c_void_p, c_int32, POINTER(c_int64), c_void_p, c_void_p, c_int64]
     L.slafb_window.argtypes = [c_void_p, POINTER(Coo), POINTER(Params), c_void_p, c_void_p, c_void_p, c_void_p,

@@ -280,34 +280,66 @@ void fill_tok_args(slafb_ctx *ctx, Slot &s, const slafb_params *p, TokArgs &a, u
     a.all_cells = 0;
 }
 
-// front half: (H2D) + K1 + count read-back, on the side stream
-int front(slafb_ctx *ctx, Slot &s, const slafb_coo *in, cudaStream_t caller) {
-    int rc = check_coo(ctx, in);
-    if (rc) return rc;
+// front half: (H2D) + K1 + count read-back, on the side stream.  The batch is the concatenation of
+// `n_pieces` row blocks (the host feeder's partial cells + fragment chunks, datasets.py:880-888):
+// host pieces are copied back to back into the slot's staging columns straight from where they
+// live (pinned / registered memory = true async DMA, no host-side assembly); a single device piece
+// is used in place.
+int front(slafb_ctx *ctx, Slot &s, const slafb_coo *pieces, int n_pieces, cudaStream_t caller) {
+    if (!pieces || n_pieces < 1) return fail(ctx, SLAFB_ERR_INVALID, "no input pieces");
+    int64_t total = 0;
+    for (int i = 0; i < n_pieces; i++) {
+        int rc = check_coo(ctx, &pieces[i]);
+        if (rc) return rc;
+        if (pieces[i].cell_dtype != pieces[0].cell_dtype || pieces[i].gene_dtype != pieces[0].gene_dtype ||
+            pieces[i].value_dtype != pieces[0].value_dtype || pieces[i].location != pieces[0].location)
+            return fail(ctx, SLAFB_ERR_INVALID, "all pieces of a batch must share column dtypes and location");
+        total += pieces[i].n_rows;
+    }
+    if (total > ctx->max_rows) return fail(ctx, SLAFB_ERR_CAPACITY, "n_rows %lld exceeds context max_rows %lld", (long long)total, (long long)ctx->max_rows);
+    const slafb_coo *in = &pieces[0];
     if (s.ev_done) {
         // the slot's scratch may still be read by the previous batch's tokenization
         CU(ctx, cudaEventSynchronize(s.ev_done));
         harvest(ctx, s);
     }
-    s.n_rows = in->n_rows;
+    s.n_rows = total;
     s.cell_dtype = in->cell_dtype;
     s.gene_dtype = in->gene_dtype;
     s.value_dtype = in->value_dtype;
     s.h_counters[0] = 0;
     s.h_counters[1] = 0;
-    if (in->n_rows == 0) {
+    if (total == 0) {
         CU(ctx, cudaEventRecord(s.ev_front, ctx->s_in));
         return SLAFB_OK;
     }
     CU(ctx, cudaEventRecord(s.ev_in, caller));
     CU(ctx, cudaStreamWaitEvent(ctx->s_in, s.ev_in, 0));
-    if (in->location == SLAFB_LOC_HOST) {
-        rc = ensure_staging(ctx, s);
+    if (in->location == SLAFB_LOC_HOST || n_pieces > 1) {
+        int rc = ensure_staging(ctx, s);
         if (rc) return rc;
+        const cudaMemcpyKind kind = in->location == SLAFB_LOC_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+        const size_t gsz = dtype_size(in->gene_dtype), vsz = dtype_size(in->value_dtype);
         CU(ctx, cudaEventRecord(s.t_h2d0, ctx->s_in));
-        CU(ctx, cudaMemcpyAsync(s.in_cell, in->cell, (size_t)in->n_rows * 4, cudaMemcpyHostToDevice, ctx->s_in));
-        CU(ctx, cudaMemcpyAsync(s.in_gene, in->gene, (size_t)in->n_rows * dtype_size(in->gene_dtype), cudaMemcpyHostToDevice, ctx->s_in));
-        CU(ctx, cudaMemcpyAsync(s.in_value, in->value, (size_t)in->n_rows * dtype_size(in->value_dtype), cudaMemcpyHostToDevice, ctx->s_in));
+        // column by column, so each staging column is written front to back
+        size_t off = 0;
+        for (int i = 0; i < n_pieces; i++) {
+            const size_t n = (size_t)pieces[i].n_rows;
+            if (n) CU(ctx, cudaMemcpyAsync(static_cast<char *>(s.in_cell) + off * 4, pieces[i].cell, n * 4, kind, ctx->s_in));
+            off += n;
+        }
+        off = 0;
+        for (int i = 0; i < n_pieces; i++) {
+            const size_t n = (size_t)pieces[i].n_rows;
+            if (n) CU(ctx, cudaMemcpyAsync(static_cast<char *>(s.in_gene) + off * gsz, pieces[i].gene, n * gsz, kind, ctx->s_in));
+            off += n;
+        }
+        off = 0;
+        for (int i = 0; i < n_pieces; i++) {
+            const size_t n = (size_t)pieces[i].n_rows;
+            if (n) CU(ctx, cudaMemcpyAsync(static_cast<char *>(s.in_value) + off * vsz, pieces[i].value, n * vsz, kind, ctx->s_in));
+            off += n;
+        }
         CU(ctx, cudaEventRecord(s.t_h2d1, ctx->s_in));
         s.timed_h2d = true;
         s.cell = s.in_cell; s.gene = s.in_gene; s.value = s.in_value;
@@ -316,7 +348,7 @@ int front(slafb_ctx *ctx, Slot &s, const slafb_coo *in, cudaStream_t caller) {
     }
     CsrArgs k{};
     k.cell = static_cast<const uint32_t *>(s.cell);
-    k.n_rows = (uint32_t)in->n_rows;
+    k.n_rows = (uint32_t)total;
     k.max_cells = (uint32_t)ctx->max_cells;
     k.seg_start = s.seg_start;
     k.seg_cell = s.seg_cell;
@@ -338,10 +370,10 @@ int front(slafb_ctx *ctx, Slot &s, const slafb_coo *in, cudaStream_t caller) {
         if (v >= 1 && v <= 8) per_sm = (uint32_t)v;
     }
     uint32_t grid = (uint32_t)ctx->n_sm * per_sm;
-    const uint64_t tiles = ((uint64_t)in->n_rows + kCsrStageRows - 1) / kCsrStageRows;
+    const uint64_t tiles = ((uint64_t)total + kCsrStageRows - 1) / kCsrStageRows;
     if (tiles < grid) grid = (uint32_t)tiles;
     k.rows_per_cta = (uint32_t)(((tiles + grid - 1) / grid) * kCsrStageRows);
-    grid = (uint32_t)(((uint64_t)in->n_rows + k.rows_per_cta - 1) / k.rows_per_cta);   // no empty spans
+    grid = (uint32_t)(((uint64_t)total + k.rows_per_cta - 1) / k.rows_per_cta);   // no empty spans
     CU(ctx, cudaEventRecord(s.t_k1a, ctx->s_in));
     csr_build_kernel<<<grid, kCsrBlock, 0, ctx->s_in>>>(k);
     CU(ctx, cudaGetLastError());
@@ -476,6 +508,15 @@ int slafb_host_alloc(void **ptr, size_t bytes) {
     CU(nullptr, cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
     return SLAFB_OK;
 }
+int slafb_host_register(void *ptr, size_t bytes) {
+    if (!ptr || !bytes) return fail(nullptr, SLAFB_ERR_INVALID, "nothing to register");
+    CU(nullptr, cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+    return SLAFB_OK;
+}
+int slafb_host_unregister(void *ptr) {
+    if (ptr) CU(nullptr, cudaHostUnregister(ptr));
+    return SLAFB_OK;
+}
 int slafb_host_free(void *ptr) {
     if (ptr) CU(nullptr, cudaFreeHost(ptr));
     return SLAFB_OK;
@@ -569,20 +610,24 @@ int slafb_destroy(slafb_ctx *ctx) {
     return SLAFB_OK;
 }
 
-int slafb_submit(slafb_ctx *ctx, const slafb_coo *in, void *stream, int32_t *slot) {
+int slafb_submit_pieces(slafb_ctx *ctx, const slafb_coo *pieces, int32_t n_pieces, void *stream, int32_t *slot) {
     if (!ctx || !slot) return fail(ctx, SLAFB_ERR_INVALID, "ctx / slot is NULL");
     CU(ctx, cudaSetDevice(ctx->device));
     const int i = ctx->next_slot;
     Slot &s = ctx->slot[i];
     if (s.in_flight) return fail(ctx, SLAFB_ERR_BUSY, "pipeline slot %d not collected yet", i);
     const double t0 = now_ms();
-    int rc = front(ctx, s, in, static_cast<cudaStream_t>(stream));
+    int rc = front(ctx, s, pieces, n_pieces, static_cast<cudaStream_t>(stream));
     ctx->acc.host_submit_ms += now_ms() - t0;
     if (rc) return rc;
     s.in_flight = true;
     ctx->next_slot = (i + 1) % kSlots;
     *slot = i;
     return SLAFB_OK;
+}
+
+int slafb_submit(slafb_ctx *ctx, const slafb_coo *in, void *stream, int32_t *slot) {
+    return slafb_submit_pieces(ctx, in, 1, stream, slot);
 }
 
 int slafb_collect(slafb_ctx *ctx, int32_t slot, const slafb_params *p, const slafb_out *out, int64_t *n_cells, void *stream) {
@@ -637,7 +682,7 @@ int slafb_window(slafb_ctx *ctx, const slafb_coo *in, const slafb_params *p, int
     if (rc) return rc;
     Slot &s = ctx->slot[ctx->next_slot];
     if (s.in_flight) return fail(ctx, SLAFB_ERR_BUSY, "pipeline slot busy");
-    rc = front(ctx, s, in, st);
+    rc = front(ctx, s, in, 1, st);
     if (rc) return rc;
     bool use_perm = false;
     rc = middle(ctx, s, p, n_cells, st, &use_perm);

@@ -167,6 +167,24 @@ class HotPathEngine:
         self._pending[slot.value] = (keep, coo.n_rows)
         return slot.value
 
+    def submit_pieces(self, pieces: list[tuple[Any, Any, Any]]) -> int:
+        """submit() for a batch given as consecutive row blocks [(cell, gene, value), ...] -- no host-side
+        concatenation; with pinned / registered blocks every copy is an async DMA."""
+        if not pieces:
+            raise ValueError("no pieces")
+        coos, keeps, total = [], [], 0
+        for cell, gene, value in pieces:
+            coo, keep = _coo(cell, gene, value)
+            coos.append(coo)
+            keeps.append(keep)
+            total += coo.n_rows
+        arr = (N.Coo * len(coos))(*coos)
+        slot = ctypes.c_int32(-1)
+        with torch.cuda.device(self.device):
+            N.check(self._L.slafb_submit_pieces(self._ctx, arr, len(coos), self._stream(), ctypes.byref(slot)), self._ctx)
+        self._pending[slot.value] = (keeps[0] + tuple(keeps[1:]), total)
+        return slot.value
+
     def collect(self, slot: int, *, mode: str, max_genes: int, max_items: int | None = None, n_bins: int = 10,
                 vocab_size: int = 50000, min_percentile: float | None = None, shuffle_seed: int | None = None,
                 perm=None, capacity_cells: int | None = None, check_contiguous: bool = False,
@@ -332,3 +350,39 @@ def _free_pinned(address: int) -> None:
         N.lib().slafb_host_free(ctypes.c_void_p(address))
     except Exception:
         pass
+
+
+# ---------------------------------------------------------------------------- registered (page-locked) user memory
+_REGISTERED: dict[int, int] = {}     # base address -> bytes
+
+
+def register_host_memory(arr: np.ndarray) -> bool:
+    """Page-lock the memory of `arr` (cudaHostRegister) so slices of it are zero-copy DMA sources.
+    Returns False when the driver refuses (e.g. read-only file mappings); the caller then keeps using
+    the staged path."""
+    if not isinstance(arr, np.ndarray) or arr.nbytes == 0 or not arr.flags.c_contiguous:
+        return False
+    base = arr.ctypes.data
+    if is_page_locked(arr):
+        return True
+    rc = N.lib().slafb_host_register(ctypes.c_void_p(base), arr.nbytes)
+    if rc != N.OK:
+        return False
+    _REGISTERED[base] = arr.nbytes
+    return True
+
+
+def unregister_host_memory(arr: np.ndarray) -> None:
+    base = arr.ctypes.data
+    if _REGISTERED.pop(base, None) is not None:
+        N.lib().slafb_host_unregister(ctypes.c_void_p(base))
+
+
+def is_page_locked(arr: np.ndarray) -> bool:
+    """True when `arr` lies inside memory registered through register_host_memory."""
+    a = arr.ctypes.data
+    b = a + arr.nbytes
+    for base, size in _REGISTERED.items():
+        if a >= base and b <= base + size:
+            return True
+    return False

@@ -33,7 +33,7 @@ import torch
 
 from .. import _native as N
 from ..core.tabular_schema import SLAF_LANCE_COO_SCHEMA
-from ..engine import HotPathEngine, pinned_empty, regroup_contiguous, shuffle_perm
+from ..engine import HotPathEngine, is_page_locked, pinned_empty, regroup_contiguous, shuffle_perm
 from . import frames
 from .samplers import RandomShuffle, StratifiedShuffle
 from .sources import CooChunk, ExpressionSource, concat_chunks, open_expression
@@ -366,11 +366,24 @@ class PrefetchBatchProcessor:
             return np.ones(len(seg_cell), bool)
         return seg_cell < seg_cell.max()
 
-    def _stash_partials(self, rows: CooChunk, seg_start: np.ndarray, seg_cell: np.ndarray, complete: np.ndarray) -> None:
+    def _stash_partials(self, pieces: list[CooChunk], seg_start: np.ndarray, seg_cell: np.ndarray, complete: np.ndarray) -> None:
+        """Keep the rows of the incomplete cells on the host (copies: the pieces may be recycled buffers)."""
         self.partial_cell_data = {}
-        for j in np.flatnonzero(~complete):
+        bad = np.flatnonzero(~complete)
+        if bad.size == 0:
+            return
+        offs = np.concatenate(([0], np.cumsum([len(p) for p in pieces])))
+        for j in bad:
             lo, hi = int(seg_start[j]), int(seg_start[j + 1])
-            part = CooChunk(rows.cell[lo:hi].copy(), rows.gene[lo:hi].copy(), rows.value[lo:hi].copy())
+            parts = []
+            k = int(np.searchsorted(offs, lo, side="right")) - 1
+            while lo < hi:
+                a, b = lo - int(offs[k]), min(hi, int(offs[k + 1])) - int(offs[k])
+                p = pieces[k]
+                parts.append(CooChunk(p.cell[a:b].copy(), p.gene[a:b].copy(), p.value[a:b].copy()))
+                lo = int(offs[k + 1])
+                k += 1
+            part = concat_chunks(parts)
             key = int(seg_cell[j])
             self.partial_cell_data[key] = concat_chunks([self.partial_cell_data[key], part]) if key in self.partial_cell_data else part
 
@@ -421,35 +434,48 @@ class PrefetchBatchProcessor:
             self.batch_id += 1
             return out
 
+    #: pieces smaller than this are handed to the driver as they are (its pageable path copies them synchronously)
+    SMALL_PIECE_ROWS = 1 << 15
+
+    def _submit(self, eng: HotPathEngine, pieces: list[CooChunk]) -> tuple[int, list[CooChunk]]:
+        """H2D + CSR build of the combined rows.  Page-locked pieces (pinned / registered source memory) go
+        straight from where they live; otherwise the rows are assembled in the pinned staging ring first."""
+        direct = all(len(p) <= self.SMALL_PIECE_ROWS or (is_page_locked(p.cell) and is_page_locked(p.gene) and is_page_locked(p.value))
+                     for p in pieces)
+        if direct and len(pieces) <= 256:
+            return eng.submit_pieces([(p.cell, p.gene, p.value) for p in pieces]), pieces
+        rows = self._staging.assemble(pieces)
+        return eng.submit(rows.cell, rows.gene, rows.value), [rows]
+
     def _load_fused(self, pieces: list[CooChunk], seed: int, start_time: float) -> TokenizedPrefetchBatch | None:
         t0 = time.time()
-        rows = self._staging.assemble(pieces)
-        eng = self._engine_for(len(rows))
-        slot = eng.submit(rows.cell, rows.gene, rows.value)
+        n_rows = sum(len(p) for p in pieces)
+        eng = self._engine_for(n_rows)
+        slot, pieces = self._submit(eng, pieces)
         try:
             seg_start, seg_cell = eng.segments(slot)
         except N.SlafB200Error as err:
             if err.code != N.ERR_CAPACITY:
                 raise
             eng.release(slot)                                   # more cells than the segment tables hold: size for the worst case
-            eng = self._engine_for(len(rows), all_cells=True)
-            slot = eng.submit(rows.cell, rows.gene, rows.value)
+            eng = self._engine_for(n_rows, all_cells=True)
+            slot, pieces = self._submit(eng, pieces)
             seg_start, seg_cell = eng.segments(slot)
         if len(np.unique(seg_cell)) != len(seg_cell):
             # a cell re-joined from two separated runs (partial + continuation with other chunks in
             # between): splice on the host like partition_by does, then resubmit (rare)
-            eng.collect(slot, perm=np.zeros(0, np.int32), **self._params())
+            eng.release(slot)
+            rows = concat_chunks(pieces)
             c, g, v = regroup_contiguous(rows.cell, rows.gene, rows.value)
-            rows = self._staging.assemble([CooChunk(c, g, v)])
-            slot = eng.submit(rows.cell, rows.gene, rows.value)
+            slot, pieces = self._submit(eng, [CooChunk(c, g, v)])
             seg_start, seg_cell = eng.segments(slot)
         seg_len = np.diff(seg_start.astype(np.int64))
         complete = self._complete_mask(seg_cell, seg_len)
-        self._stash_partials(rows, seg_start, seg_cell, complete)
+        self._stash_partials(pieces, seg_start, seg_cell, complete)
         sel = np.flatnonzero(complete).astype(np.int32)
         shuffle_time = time.time() - t0
         if sel.size == 0:
-            eng.collect(slot, perm=sel, **self._params())
+            eng.release(slot)
             return None
         t1 = time.time()
         order = sel[shuffle_perm(seed, sel.size)]              # random.seed(seed); random.shuffle(chunks), samplers.py:89-96

@@ -113,10 +113,26 @@ class ArrayExpressionSource(ExpressionSource):
         whole = CooChunk(np.ascontiguousarray(cell), np.ascontiguousarray(gene), np.ascontiguousarray(value))
         self._fragments = [_ArrayFragment(whole.slice(lo, min(lo + max_rows_per_file, len(whole))))
                            for lo in range(0, max(len(whole), 1), max_rows_per_file)]
-        self.default_batch_size = 8192
+        self._whole = whole
+        self.pinned = False
 
     def get_fragments(self) -> list[Fragment]:
         return list(self._fragments)
+
+    def pin(self) -> bool:
+        """Page-lock the column arrays (cudaHostRegister): every chunk then reaches the GPU by DMA
+        straight from these arrays, the feeder copies nothing on the host."""
+        from ..engine import register_host_memory
+
+        self.pinned = all(register_host_memory(a) for a in (self._whole.cell, self._whole.gene, self._whole.value))
+        return self.pinned
+
+    def unpin(self) -> None:
+        from ..engine import unregister_host_memory
+
+        for a in (self._whole.cell, self._whole.gene, self._whole.value):
+            unregister_host_memory(a)
+        self.pinned = False
 
 
 # ------------------------------------------------------------------------------ Arrow IPC directory
