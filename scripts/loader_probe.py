@@ -1,0 +1,69 @@
+"""Where the host feeder's time goes: per-stage wall times of PrefetchBatchProcessor.load_prefetch_batch
+over an in-memory table (run on a GPU box)."""
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from slaf_b200 import synthetic
+from slaf_b200.ml import PrefetchBatchProcessor, RandomShuffle, ScGPTTokenizer
+from slaf_b200.ml import datasets as D
+from slaf_b200.ml.sources import ArrayExpressionSource, SyntheticSLAFArray
+
+cells = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
+frag_rows = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 24
+pin = (sys.argv[3] != "nopin") if len(sys.argv) > 3 else True
+b = synthetic.make_batch(cells, 60000, 2000, seed=3)
+src = ArrayExpressionSource(b.cell, b.gene, b.value, max_rows_per_file=frag_rows)
+print("pinned:", src.pin() if pin else False, "rows", b.n_rows, "fragments", len(src.get_fragments()))
+arr = SyntheticSLAFArray(src, b.cell_start, 60000)
+tok = ScGPTTokenizer(arr, vocab_size=65000, n_expression_bins=51, max_genes=1200)
+
+stages = {}
+
+
+def timed(name, fn):
+    def wrap(*a, **k):
+        t0 = time.perf_counter()
+        r = fn(*a, **k)
+        stages.setdefault(name, []).append(time.perf_counter() - t0)
+        return r
+    return wrap
+
+
+for epoch_mode in ("fragment", "mos"):
+    proc = PrefetchBatchProcessor(arr, RandomShuffle(), tok, n_expression_bins=51, use_binned_expressions=True, n_epochs=3,
+                                  use_mixture_of_scanners=(epoch_mode == "mos"), by_fragment=True, verbose=False, n_scanners=4,
+                                  prefetch_batch_size=4194304)
+    proc._next_pieces = timed("read", proc._next_pieces)
+    proc._submit = timed("submit", proc._submit)
+    proc._stash_partials = timed("stash", proc._stash_partials)
+    proc._complete_mask = timed("complete", proc._complete_mask)
+    stages.clear()
+    n = 0
+    t_first = None
+    t0 = time.perf_counter()
+    try:
+        while True:
+            e = proc._engine
+            if e is not None and not hasattr(e, "_wrapped"):
+                e.segments = timed("segments", e.segments)
+                e.collect = timed("collect", e.collect)
+                e._wrapped = True
+            out = proc.load_prefetch_batch()
+            if t_first is None:
+                torch.cuda.synchronize()
+                t_first = time.perf_counter()
+                n0 = out.n_cells
+            n += out.n_cells
+    except StopIteration:
+        pass
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    print(f"[{epoch_mode}] {n} cells in {t1 - t0:.3f}s ({n / (t1 - t0):,.0f} cells/s incl. start-up; steady {(n - n0) / (t1 - t_first):,.0f} cells/s)")
+    for k, v in stages.items():
+        print(f"   {k:10s} n={len(v):3d} mean={1e3 * np.mean(v):8.3f} ms  first={1e3 * v[0]:8.3f} ms  total={np.sum(v):.3f}s")
+    proc.close()

@@ -108,6 +108,77 @@ def _runs(cell: np.ndarray):
     return starts, ends, cell[starts]
 
 
+def _head_run(cell: np.ndarray, x) -> int:
+    """Number of leading rows equal to x (galloping: touches O(run length) rows)."""
+    n, w = len(cell), 256
+    while True:
+        neq = np.flatnonzero(cell[:w] != x)
+        if neq.size:
+            return int(neq[0])
+        if w >= n:
+            return n
+        w *= 4
+
+
+def _tail_run(cell: np.ndarray, x) -> int:
+    """Number of trailing rows equal to x."""
+    return _head_run(cell[::-1], x)
+
+
+def _splice_partials(partials: dict, body: list[CooChunk]) -> list[CooChunk]:
+    """[partial rows of cell X, the runs of X found at the head / tail of later chunks, ...other partials..., rest].
+    All pieces are views; the order of cells is the order of first appearance in [partials..., body] and the
+    rows of a cell keep their arrival order -- what partition_by(maintain_order) + concat produce."""
+    if not partials:
+        return body
+    body = list(body)
+    out: list[CooChunk] = []
+    for x, part in partials.items():
+        out.append(part)
+        for i, ch in enumerate(body):
+            if len(ch) == 0:
+                continue
+            if ch.cell[0] == x:
+                n = _head_run(ch.cell, x)
+                out.append(ch.slice(0, n))
+                body[i] = ch = ch.slice(n, len(ch))
+            if len(ch) and ch.cell[-1] == x:
+                n = _tail_run(ch.cell, x)
+                out.append(ch.slice(len(ch) - n, len(ch)))
+                body[i] = ch.slice(0, len(ch) - n)
+    return out + [b for b in body if len(b)]
+
+
+def _regroup_segments(pieces: list[CooChunk], seg_start: np.ndarray, seg_cell: np.ndarray) -> list[CooChunk]:
+    """Safety net for cells that still arrive in separated runs: reorder whole SEGMENTS (not rows) so that
+    every cell is one run, cells by first appearance, runs of a cell in arrival order.  Returns views."""
+    _, first, inv = np.unique(seg_cell, return_index=True, return_inverse=True)
+    order = np.argsort(first[inv], kind="stable")
+    offs = np.concatenate(([0], np.cumsum([len(p) for p in pieces])))
+    out: list[CooChunk] = []
+    run_lo = run_hi = None
+    ranges = []
+    for j in order:
+        lo, hi = int(seg_start[j]), int(seg_start[j + 1])
+        if run_hi == lo:
+            run_hi = hi
+        else:
+            if run_lo is not None:
+                ranges.append((run_lo, run_hi))
+            run_lo, run_hi = lo, hi
+    if run_lo is not None:
+        ranges.append((run_lo, run_hi))
+    for lo, hi in ranges:
+        k = int(np.searchsorted(offs, lo, side="right")) - 1
+        while lo < hi:
+            a, b = lo - int(offs[k]), min(hi, int(offs[k + 1])) - int(offs[k])
+            if b > a:
+                out.append(pieces[k].slice(a, b))
+            lo = int(offs[k + 1])
+            k += 1
+    return out
+
+
 class _Staging:
     """Ring of pinned host buffers the combined rows of a batch are assembled in (so the H2D copy
     is a true async DMA).  Copies run on a small thread pool: numpy releases the GIL in memcpy."""
@@ -254,7 +325,7 @@ class PrefetchBatchProcessor:
         if cells_processed > 0:
             self._timing_metrics["cells_processed"].append(cells_processed)
 
-    def _read_from_generator(self, idx: int) -> tuple[CooChunk | None, int, bool]:
+    def _read_from_generator(self, idx: int) -> tuple[list[CooChunk] | None, int, bool]:
         """``batches_per_chunk`` batches of one fragment generator (datasets.py:561-606).  Unlike the
         reference, batches already read are kept when the generator ends inside the chunk (the
         reference drops them, losing rows whenever batches_per_chunk > 1)."""
@@ -270,7 +341,7 @@ class PrefetchBatchProcessor:
             return None, idx, True
         if exhausted:
             self.generator_active[idx] = False
-        return concat_chunks(got), idx, False
+        return [g for g in got if len(g)], idx, False      # consecutive storage rows: kept as separate views, never copied
 
     def _next_pieces(self) -> tuple[list[CooChunk], int] | None:
         """Rows of the next load: (pieces in row order, batch_count); None = epoch transition handled
@@ -293,23 +364,28 @@ class PrefetchBatchProcessor:
                 results = list(self._read_pool.map(self._read_from_generator, [int(i) for i in selected]))
             else:
                 results = [self._read_from_generator(int(i)) for i in selected]
-            chunks: list[CooChunk] = []
-            for chunk, idx, exhausted in results:
+            body: list[CooChunk] = []
+            n_chunks = 0
+            for got, idx, exhausted in results:
                 if exhausted:
                     self.generator_active[idx] = False
                     continue
-                if chunk is None or len(chunk) == 0:
+                if not got:
                     continue
                 last = self.generator_last_cells[idx]
                 if last is not None:
-                    first_cell = int(chunk.cell[0])
+                    first_cell = int(got[0].cell[0])
                     if (first_cell == last or first_cell == last + 1) and last in self.partial_cell_data:
-                        chunk = concat_chunks([self.partial_cell_data.pop(last), chunk])     # datasets.py:748-760
-                self.generator_last_cells[idx] = int(chunk.cell[-1])
-                chunks.append(chunk)
-            if not chunks:
+                        got = [self.partial_cell_data.pop(last)] + got                        # datasets.py:748-760
+                self.generator_last_cells[idx] = int(got[-1].cell[-1])
+                body.extend(got)
+                n_chunks += 1
+            if not body:
                 return None
-            pieces, count = chunks, len(chunks)
+            # the partial cells still pending go in front (datasets.py:880-888); runs of the same cell at the
+            # head / tail of a chunk are moved up behind them, which is where partition_by would gather them
+            pieces = _splice_partials(self.partial_cell_data, body)
+            return pieces, n_chunks
         elif self.by_fragment:
             try:
                 fragment = next(self.fragment_iterator)
@@ -337,7 +413,7 @@ class PrefetchBatchProcessor:
                 return self._advance_epoch()
             pieces, count = got, len(got)
         if self.partial_cell_data:                                                        # datasets.py:880-888
-            pieces = list(self.partial_cell_data.values()) + pieces
+            pieces = list(self.partial_cell_data.values()) + pieces           # the last cell's rows continue at the top of the new rows
         return pieces, count
 
     def _advance_epoch(self) -> None:
@@ -465,9 +541,7 @@ class PrefetchBatchProcessor:
             # a cell re-joined from two separated runs (partial + continuation with other chunks in
             # between): splice on the host like partition_by does, then resubmit (rare)
             eng.release(slot)
-            rows = concat_chunks(pieces)
-            c, g, v = regroup_contiguous(rows.cell, rows.gene, rows.value)
-            slot, pieces = self._submit(eng, [CooChunk(c, g, v)])
+            slot, pieces = self._submit(eng, _regroup_segments(pieces, seg_start, seg_cell))
             seg_start, seg_cell = eng.segments(slot)
         seg_len = np.diff(seg_start.astype(np.int64))
         complete = self._complete_mask(seg_cell, seg_len)

@@ -211,3 +211,32 @@ def test_arrow_source_roundtrip(tmp_path):
     whole = np.concatenate([f.to_table().value for f in src.get_fragments()])
     assert np.array_equal(whole, b.value) and whole.dtype == np.uint16
     assert np.array_equal(np.concatenate([c.gene for c in src.to_batches(8192)]), b.gene)
+
+
+def test_splice_partials_and_segment_regroup_equal_partition_by():
+    """A boundary cell whose parts arrive through different scanners: the feeder's piece splice (views only)
+    and the segment-level safety net both give what partition_by(maintain_order) + concat would."""
+    from slaf_b200.ml.datasets import _regroup_segments, _runs, _splice_partials
+    from slaf_b200.ml.sources import CooChunk, concat_chunks
+
+    def chunk(ids, lens, base):
+        cell = np.repeat(np.asarray(ids, np.uint32), lens)
+        return CooChunk(cell, (np.arange(len(cell)) + base).astype(np.uint16), np.ones(len(cell), np.uint16))
+
+    partials = {7: chunk([7], [3], 0), 40: chunk([40], [2], 100)}
+    body = [chunk([20, 21, 40], [4, 5, 6], 200),        # ends with rows of cell 40 (its first part arrives last)
+            chunk([7, 8, 9], [300, 2, 2], 1000),         # starts with the continuation of cell 7 (longer than the gallop window)
+            chunk([30], [5], 3000)]
+    naive = concat_chunks(list(partials.values()) + body)
+    want = regroup_contiguous(naive.cell, naive.gene, naive.value)
+    got = concat_chunks(_splice_partials(partials, body))
+    for a, b in zip((got.cell, got.gene, got.value), want):
+        assert np.array_equal(a, b)
+    # the safety net on the un-spliced order, driven by the segment table K1 would report
+    starts, ends, ids = _runs(naive.cell)
+    seg_start = np.concatenate((starts, [len(naive)])).astype(np.uint32)
+    pieces = _regroup_segments(list(partials.values()) + body, seg_start, ids)
+    got2 = concat_chunks(pieces)
+    for a, b in zip((got2.cell, got2.gene, got2.value), want):
+        assert np.array_equal(a, b)
+    assert all(p.cell.base is not None for p in pieces)           # views, not copies
