@@ -312,6 +312,7 @@ def main():
     max_rows = max(b.n_rows for b in batches)
     eng = HotPathEngine(dev, max_rows=max_rows + 1024, max_cells=cps + 1024)
     kw = dict(mode=w["mode"], max_genes=w["max_genes"], n_bins=w["n_bins"], vocab_size=w["vocab"])
+    timing_every = int(os.environ.get("SLAFB_BENCH_TIMING_EVERY", "8"))
 
     # ---- parity gate (bit-exact against the CPU oracle) before any number counts
     from oracle import c_oracle
@@ -340,7 +341,7 @@ def main():
     def bytes_over(n_steps):   # (K1, K2, H2D) algorithmic bytes of n_steps steps (batches are cycled)
         return tuple(sum(per_batch[i % NB][j] for i in range(n_steps)) for j in range(3))
 
-    def run_steps(cols, n_steps, read_result, depth=2):
+    def run_steps(cols, n_steps, read_result, depth=int(os.environ.get("SLAFB_BENCH_DEPTH", "2"))):
         """pipelined: up to `depth` submits (H2D + CSR build) run ahead of the collect of the
         oldest batch.  Returns (#cells, #rows, d2h bytes)."""
         from collections import deque
@@ -351,7 +352,7 @@ def main():
         keep = None
         for i in range(n_steps):
             while nxt < n_steps and len(q) <= depth:
-                q.append(eng.submit(*cols[nxt % NB]))
+                q.append(eng.submit(*cols[nxt % NB], shuffle_seed=42 + nxt))   # seed known at submit: the library prepares the shuffle off-thread
                 nxt += 1
             out = eng.collect(q.popleft(), shuffle_seed=42 + i, **kw)
             cells += out.n_cells
@@ -362,6 +363,7 @@ def main():
         return cells, rows, d2h
 
     # ---- value: inputs resident in HBM
+    eng.set_timing_interval(timing_every)
     run_steps(dev_cols, args.warmup, False)
     eng.timing()
     barrier()
@@ -411,8 +413,10 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     k1_b, k2_b, _ = bytes_over(args.steps)
-    k2_gbs = k2_b / (tm["tokenize_ms"] / 1e3) / 1e9 if tm["tokenize_ms"] else None
-    k1_gbs = k1_b / (tm["csr_ms"] / 1e3) / 1e9 if tm["csr_ms"] else None
+    nt = max(1, tm["timed_batches"])          # launches that carried CUDA events (every `timing_every`-th batch, all batches in rotation)
+    k2_ms, k1_ms, gen_ms = tm["tokenize_ms"] / nt, tm["csr_ms"] / nt, tm["slowpath_ms"] / nt
+    k2_gbs = (k2_b / args.steps) / (k2_ms / 1e3) / 1e9 if k2_ms else None
+    k1_gbs = (k1_b / args.steps) / (k1_ms / 1e3) / 1e9 if k1_ms else None
     traffic = None
     try:   # dram__bytes_read.sum + dram__bytes_write.sum of K2 from the committed ncu --set full capture, per cell
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{args.workload}:{args.value_dtype}")
@@ -428,10 +432,10 @@ def main():
         "roofline": {"bound": "hbm", "kernel": "tokenize_cells_kernel", "achieved": k2_gbs, "peak": peak, "unit": "GB/s",
                      "frac": (k2_gbs / peak) if k2_gbs else None, "traffic": traffic,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s",
-                     "algorithmic_bytes_per_launch": int(k2_b / args.steps), "avg_launch_ms": tm["tokenize_ms"] / max(1, tm["batches"]),
+                     "algorithmic_bytes_per_launch": int(k2_b / args.steps), "avg_launch_ms": k2_ms, "timed_launches": int(tm["timed_batches"]),
                      "csr_build_kernel": {"achieved": k1_gbs, "frac": (k1_gbs / peak) if k1_gbs else None,
-                                          "algorithmic_bytes_per_launch": int(k1_b / args.steps), "avg_launch_ms": tm["csr_ms"] / max(1, tm["batches"])},
-                     "general_path": {"cells_per_step": tm["slow_cells"] / max(1, tm["batches"]), "avg_launch_ms": tm["slowpath_ms"] / max(1, tm["batches"])},
+                                          "algorithmic_bytes_per_launch": int(k1_b / args.steps), "avg_launch_ms": k1_ms},
+                     "general_path": {"cells_per_step": tm["slow_cells"] / max(1, tm["batches"]), "avg_launch_ms": gen_ms},
                      "whole_step_hbm_frac": ((k1_b + k2_b) / (ms / 1e3) / 1e9 / peak) if world == 1 else None},
         "gpu_launches": int(tm["kernel_launches"]),
         "host_us_per_step": {k: round(1000.0 * tm[f"host_{k}_ms"] / max(1, tm["batches"]), 1) for k in ("submit", "collect", "wait", "shuffle")},

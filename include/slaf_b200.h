@@ -126,6 +126,7 @@ typedef struct {
     double host_collect_ms;  /* host wall time spent inside slafb_collect (includes the two below) */
     double host_wait_ms;     /* ... of which: waiting for the cell count (H2D + K1 to finish)   */
     double host_shuffle_ms;  /* ... of which: building the CPython-exact permutation            */
+    int64_t timed_batches;   /* batches that carried the per-kernel events (csr_ms .. h2d_ms sum over these) */
 } slafb_timing;
 
 int slafb_version(void);
@@ -156,6 +157,11 @@ int slafb_submit(slafb_ctx *ctx, const slafb_coo *in, void *stream, int32_t *slo
  * 880-888).  Host blocks are copied into the slot's staging columns straight from where they live,
  * so with pinned / registered source memory the feeder does no host-side assembly at all. */
 int slafb_submit_pieces(slafb_ctx *ctx, const slafb_coo *pieces, int32_t n_pieces, void *stream, int32_t *slot);
+/* Optional hint between submit() and collect(): the shuffle seed the batch will be collected with
+ * (seed + batch_id + epoch*10000, datasets.py:1016).  The context's helper thread then builds the
+ * CPython-exact permutation as soon as the CSR build has produced the cell count, off the caller's
+ * critical path; collect() with SLAFB_SHUFFLE_SEED and the same seed picks it up. */
+int slafb_prepare_shuffle(slafb_ctx *ctx, int32_t slot, int64_t seed);
 int slafb_collect(slafb_ctx *ctx, int32_t slot, const slafb_params *p, const slafb_out *out,
                   int64_t *n_cells, void *stream);
 
@@ -202,6 +208,10 @@ int slafb_host_free(void *ptr);
  * expression table), so slices of it are DMA sources without a staging copy. */
 int slafb_host_register(void *ptr, size_t bytes);
 int slafb_host_unregister(void *ptr);
+
+/* Per-kernel CUDA-event timing is taken on every `every`-th batch (default 1 = all).  Each event record
+ * is a stream operation; a throughput-critical caller samples (bench.py uses 4). */
+int slafb_set_timing_interval(slafb_ctx *ctx, int32_t every);
 
 /* Timing / counters since the previous call (synchronises the context's streams). */
 int slafb_get_timing(slafb_ctx *ctx, slafb_timing *t);

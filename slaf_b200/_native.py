@@ -32,8 +32,8 @@ FLAG_CHECK_CONTIGUOUS = 1
 
 EXPORTS = [
     "slafb_version", "slafb_create", "slafb_destroy", "slafb_last_error", "slafb_tokenize", "slafb_submit", "slafb_submit_pieces", "slafb_host_register", "slafb_host_unregister",
-    "slafb_collect", "slafb_segments", "slafb_window", "slafb_tokenize_lists", "slafb_shuffle_perm", "slafb_gene_stats",
-    "slafb_host_alloc", "slafb_host_free", "slafb_get_timing",
+    "slafb_collect", "slafb_prepare_shuffle", "slafb_segments", "slafb_window", "slafb_tokenize_lists", "slafb_shuffle_perm", "slafb_gene_stats",
+    "slafb_host_alloc", "slafb_host_free", "slafb_get_timing", "slafb_set_timing_interval",
 ]
 
 
@@ -66,6 +66,7 @@ class Timing(Structure):
         ("batches", c_int64), ("kernel_launches", c_int64), ("cells", c_int64), ("rows", c_int64),
         ("slow_cells", c_int64),
         ("host_submit_ms", c_double), ("host_collect_ms", c_double), ("host_wait_ms", c_double), ("host_shuffle_ms", c_double),
+        ("timed_batches", c_int64),
     ]
 
 
@@ -124,6 +125,7 @@ def lib() -> ctypes.CDLL:
     L.slafb_submit_pieces.argtypes = [c_void_p, POINTER(Coo), c_int32, c_void_p, POINTER(c_int32)]
     L.slafb_host_register.argtypes = [c_void_p, c_size_t]
     L.slafb_host_unregister.argtypes = [c_void_p]
+    L.slafb_prepare_shuffle.argtypes = [c_void_p, c_int32, c_int64]
     L.slafb_collect.argtypes = [c_void_p, c_int32, POINTER(Params), POINTER(Out), POINTER(c_int64), c_void_p]
     L.slafb_segments.argtypes = [c_void_p, c_int32, POINTER(c_int64), c_void_p, c_void_p, c_int64]
     L.slafb_window.argtypes = [c_void_p, POINTER(Coo), POINTER(Params), c_void_p, c_void_p, c_void_p, c_void_p,
@@ -134,6 +136,7 @@ def lib() -> ctypes.CDLL:
     L.slafb_gene_stats.argtypes = [c_void_p, POINTER(Coo), c_int64, c_void_p, c_void_p, c_void_p]
     L.slafb_host_alloc.argtypes = [POINTER(c_void_p), c_size_t]
     L.slafb_host_free.argtypes = [c_void_p]
+    L.slafb_set_timing_interval.argtypes = [c_void_p, c_int32]
     L.slafb_get_timing.argtypes = [c_void_p, POINTER(Timing)]
     for name in EXPORTS:
         getattr(L, name)  # AttributeError here = header and library out of sync

@@ -215,6 +215,7 @@ struct CsrArgs {
     uint32_t ticket_base;
     uint32_t epoch;         // 30-bit launch id, so tile_state needs no memset
     uint32_t *n_cells_out;  // [0] = number of segments, [1] = error flags
+    uint32_t *host_counts;  // the same two words in mapped pinned host memory (no D2H copy in the stream)
     uint32_t *work_counters;  // [0] general-path count, [1] general-path head, [2] K2 row ticket (reset here)
 };
 
@@ -348,6 +349,8 @@ __global__ void __launch_bounds__(kCsrBlock) csr_build_kernel(const CsrArgs a) {
                 const uint32_t total = excl + count;
                 a.n_cells_out[0] = total;
                 a.n_cells_out[1] = (total > a.max_cells) ? 1u : 0u;
+                a.host_counts[0] = total;
+                a.host_counts[1] = (total > a.max_cells) ? 1u : 0u;
                 if (total <= a.max_cells) a.seg_start[total] = R;
                 a.work_counters[0] = 0u;
                 a.work_counters[1] = 0u;
@@ -426,6 +429,7 @@ struct TokArgs {
     const double *log1p_lut;      // [65536] glibc log1p(double(v)), uploaded once
     uint32_t *work_list;          // output rows deferred to the general kernel
     uint32_t *work_counters;      // [0] count, [1] head
+    uint32_t *host_slow;          // mapped pinned host word: number of cells the general kernel handled
     uint32_t *sort_scratch;       // [n_rows] keys, general path with > kSortSmemKeys float rows
     int all_cells;                // general kernel: iterate every output row (percentile mode)
 };
@@ -1205,6 +1209,7 @@ __global__ void __launch_bounds__(kTokThreads) tokenize_general_kernel(const Tok
     __shared__ uint32_t s_item;
     extern __shared__ __align__(16) uint32_t dyn[];   // bitmap (u16) or sort keys (f32)
     const uint32_t count = a.all_cells ? a.n_cells : a.work_counters[0];
+    if (blockIdx.x == 0 && threadIdx.x == 0 && a.host_slow) *a.host_slow = count;
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) s_item = atomicAdd(a.work_counters + 1, 1u);

@@ -15,8 +15,13 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <new>
+#include <thread>
 
 #include "../../include/slaf_b200.h"
 #include "kernels.cuh"
@@ -38,8 +43,13 @@ struct Slot {
     // staged copies of host input (lazy)
     void *in_cell = nullptr, *in_gene = nullptr, *in_value = nullptr;
     // pinned host
-    uint32_t *h_counters = nullptr; // [0] n_cells, [1] err, [2] cells deferred to the general kernel
+    uint32_t *h_counters = nullptr; // [0] n_cells, [1] err, [2] cells deferred to the general kernel (mapped pinned: kernels write it)
+    uint32_t *h_counters_dev = nullptr;  // device-side address of h_counters
     bool all_general = false;
+    // permutation prepared ahead of collect() by the helper thread (slafb_prepare_shuffle)
+    std::atomic<int> prep_state{0};   // 0 none, 1 queued / running, 2 ready
+    int64_t prep_seed = 0;
+    int64_t prep_cells = -1;
     int32_t *h_perm = nullptr;
     uint32_t *h_draws = nullptr;    // scratch of the host shuffle (plain malloc)
     // batch description (device pointers actually used by the kernels)
@@ -50,6 +60,8 @@ struct Slot {
     // timing events
     cudaEvent_t t_h2d0 = nullptr, t_h2d1 = nullptr, t_k1a = nullptr, t_k1b = nullptr, t_k2a = nullptr, t_k2b = nullptr, t_k2c = nullptr;
     bool timed_front = false, timed_back = false, timed_h2d = false;
+    bool sample = true;               // this batch carries the per-kernel timing events
+    bool ran_back = false;
 };
 
 }  // namespace
@@ -76,6 +88,17 @@ struct slafb_ctx {
     long long *h_total = nullptr;
     slafb_timing acc{};
     char err[512] = {0};
+    // helper thread: builds CPython-exact permutations as soon as a batch's cell count is known
+    std::thread worker;
+    std::mutex wm;
+    std::condition_variable wcv, wdone;
+    std::deque<int> wjobs;
+    bool wstop = false;
+    bool wstarted = false;
+    // per-kernel CUDA-event timing is sampled: every `timing_every`-th batch carries the seven events
+    // (each event record is a stream operation; on every batch they cost a few percent of a step)
+    int timing_every = 1;
+    uint64_t batch_seq = 0;
 };
 
 namespace {
@@ -139,12 +162,13 @@ void harvest(slafb_ctx *ctx, Slot &s) {
     float ms;
     if (s.timed_h2d && cudaEventElapsedTime(&ms, s.t_h2d0, s.t_h2d1) == cudaSuccess) ctx->acc.h2d_ms += ms;
     if (s.timed_front && cudaEventElapsedTime(&ms, s.t_k1a, s.t_k1b) == cudaSuccess) ctx->acc.csr_ms += ms;
+    if (s.timed_front) ctx->acc.timed_batches++;
     if (s.timed_back) {
         if (cudaEventElapsedTime(&ms, s.t_k2a, s.t_k2b) == cudaSuccess) ctx->acc.tokenize_ms += ms;
         if (cudaEventElapsedTime(&ms, s.t_k2b, s.t_k2c) == cudaSuccess) ctx->acc.slowpath_ms += ms;
-        ctx->acc.slow_cells += s.all_general ? (int64_t)s.h_counters[0] : (int64_t)s.h_counters[2];
     }
-    s.timed_front = s.timed_back = s.timed_h2d = false;
+    if (s.ran_back) ctx->acc.slow_cells += s.all_general ? (int64_t)s.h_counters[0] : (int64_t)s.h_counters[2];
+    s.timed_front = s.timed_back = s.timed_h2d = s.ran_back = false;
 }
 
 int ensure_staging(slafb_ctx *ctx, Slot &s) {
@@ -278,6 +302,7 @@ void fill_tok_args(slafb_ctx *ctx, Slot &s, const slafb_params *p, TokArgs &a, u
     a.work_counters = s.counters + 2;
     a.sort_scratch = ctx->sort_scratch;
     a.all_cells = 0;
+    a.host_slow = nullptr;
 }
 
 // front half: (H2D) + K1 + count read-back, on the side stream.  The batch is the concatenation of
@@ -298,11 +323,17 @@ int front(slafb_ctx *ctx, Slot &s, const slafb_coo *pieces, int n_pieces, cudaSt
     }
     if (total > ctx->max_rows) return fail(ctx, SLAFB_ERR_CAPACITY, "n_rows %lld exceeds context max_rows %lld", (long long)total, (long long)ctx->max_rows);
     const slafb_coo *in = &pieces[0];
+    // The side stream exists to overlap H2D copies with tokenization.  A device-resident batch has no
+    // copy to hide; SLAFB_FRONT_ON_CALLER=1 keeps its CSR build on the caller's stream (tuning knob).
+    static const bool front_on_caller = getenv("SLAFB_FRONT_ON_CALLER") && atoi(getenv("SLAFB_FRONT_ON_CALLER")) != 0;
+    cudaStream_t sf = (front_on_caller && in->location == SLAFB_LOC_DEVICE && n_pieces == 1) ? caller : ctx->s_in;
     if (s.ev_done) {
         // the slot's scratch may still be read by the previous batch's tokenization
         CU(ctx, cudaEventSynchronize(s.ev_done));
         harvest(ctx, s);
     }
+    s.sample = (ctx->timing_every <= 1) || (ctx->batch_seq % (uint64_t)ctx->timing_every == 0);
+    ctx->batch_seq++;
     s.n_rows = total;
     s.cell_dtype = in->cell_dtype;
     s.gene_dtype = in->gene_dtype;
@@ -310,38 +341,37 @@ int front(slafb_ctx *ctx, Slot &s, const slafb_coo *pieces, int n_pieces, cudaSt
     s.h_counters[0] = 0;
     s.h_counters[1] = 0;
     if (total == 0) {
-        CU(ctx, cudaEventRecord(s.ev_front, ctx->s_in));
+        CU(ctx, cudaEventRecord(s.ev_front, sf));
         return SLAFB_OK;
     }
     CU(ctx, cudaEventRecord(s.ev_in, caller));
-    CU(ctx, cudaStreamWaitEvent(ctx->s_in, s.ev_in, 0));
+    CU(ctx, cudaStreamWaitEvent(sf, s.ev_in, 0));
     if (in->location == SLAFB_LOC_HOST || n_pieces > 1) {
         int rc = ensure_staging(ctx, s);
         if (rc) return rc;
         const cudaMemcpyKind kind = in->location == SLAFB_LOC_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
         const size_t gsz = dtype_size(in->gene_dtype), vsz = dtype_size(in->value_dtype);
-        CU(ctx, cudaEventRecord(s.t_h2d0, ctx->s_in));
+        if (s.sample) CU(ctx, cudaEventRecord(s.t_h2d0, sf));
         // column by column, so each staging column is written front to back
         size_t off = 0;
         for (int i = 0; i < n_pieces; i++) {
             const size_t n = (size_t)pieces[i].n_rows;
-            if (n) CU(ctx, cudaMemcpyAsync(static_cast<char *>(s.in_cell) + off * 4, pieces[i].cell, n * 4, kind, ctx->s_in));
+            if (n) CU(ctx, cudaMemcpyAsync(static_cast<char *>(s.in_cell) + off * 4, pieces[i].cell, n * 4, kind, sf));
             off += n;
         }
         off = 0;
         for (int i = 0; i < n_pieces; i++) {
             const size_t n = (size_t)pieces[i].n_rows;
-            if (n) CU(ctx, cudaMemcpyAsync(static_cast<char *>(s.in_gene) + off * gsz, pieces[i].gene, n * gsz, kind, ctx->s_in));
+            if (n) CU(ctx, cudaMemcpyAsync(static_cast<char *>(s.in_gene) + off * gsz, pieces[i].gene, n * gsz, kind, sf));
             off += n;
         }
         off = 0;
         for (int i = 0; i < n_pieces; i++) {
             const size_t n = (size_t)pieces[i].n_rows;
-            if (n) CU(ctx, cudaMemcpyAsync(static_cast<char *>(s.in_value) + off * vsz, pieces[i].value, n * vsz, kind, ctx->s_in));
+            if (n) CU(ctx, cudaMemcpyAsync(static_cast<char *>(s.in_value) + off * vsz, pieces[i].value, n * vsz, kind, sf));
             off += n;
         }
-        CU(ctx, cudaEventRecord(s.t_h2d1, ctx->s_in));
-        s.timed_h2d = true;
+        if (s.sample) { CU(ctx, cudaEventRecord(s.t_h2d1, sf)); s.timed_h2d = true; }
         s.cell = s.in_cell; s.gene = s.in_gene; s.value = s.in_value;
     } else {
         s.cell = in->cell; s.gene = in->gene; s.value = in->value;
@@ -357,11 +387,12 @@ int front(slafb_ctx *ctx, Slot &s, const slafb_coo *pieces, int n_pieces, cudaSt
     k.ticket_base = ctx->ticket_base;
     ctx->epoch = (ctx->epoch + 1u) & 0x3fffffffu;
     if (ctx->epoch == 0) {  // 2^30 launches: restart the epoch space
-        CU(ctx, cudaMemsetAsync(ctx->tile_state, 0, (size_t)ctx->n_sm * 8 * sizeof(unsigned long long), ctx->s_in));
+        CU(ctx, cudaMemsetAsync(ctx->tile_state, 0, (size_t)ctx->n_sm * 8 * sizeof(unsigned long long), sf));
         ctx->epoch = 1;
     }
     k.epoch = ctx->epoch;
     k.n_cells_out = s.counters;
+    k.host_counts = s.h_counters_dev;
     k.work_counters = s.counters + 2;
     // one contiguous span of rows per CTA (a whole number of 2048-row stages); ~4 CTAs per SM
     uint32_t per_sm = 4;
@@ -374,16 +405,47 @@ int front(slafb_ctx *ctx, Slot &s, const slafb_coo *pieces, int n_pieces, cudaSt
     if (tiles < grid) grid = (uint32_t)tiles;
     k.rows_per_cta = (uint32_t)(((tiles + grid - 1) / grid) * kCsrStageRows);
     grid = (uint32_t)(((uint64_t)total + k.rows_per_cta - 1) / k.rows_per_cta);   // no empty spans
-    CU(ctx, cudaEventRecord(s.t_k1a, ctx->s_in));
-    csr_build_kernel<<<grid, kCsrBlock, 0, ctx->s_in>>>(k);
+    if (s.sample) CU(ctx, cudaEventRecord(s.t_k1a, sf));
+    csr_build_kernel<<<grid, kCsrBlock, 0, sf>>>(k);
     CU(ctx, cudaGetLastError());
-    CU(ctx, cudaEventRecord(s.t_k1b, ctx->s_in));
-    s.timed_front = true;
+    if (s.sample) { CU(ctx, cudaEventRecord(s.t_k1b, sf)); s.timed_front = true; }
     ctx->ticket_base += grid;
     ctx->acc.kernel_launches++;
-    CU(ctx, cudaMemcpyAsync(s.h_counters, s.counters, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->s_in));
-    CU(ctx, cudaEventRecord(s.ev_front, ctx->s_in));
+    CU(ctx, cudaEventRecord(s.ev_front, sf));
     return SLAFB_OK;
+}
+
+void shuffle_worker(slafb_ctx *ctx) {
+    cudaSetDevice(ctx->device);
+    for (;;) {
+        int i;
+        {
+            std::unique_lock<std::mutex> lk(ctx->wm);
+            ctx->wcv.wait(lk, [&] { return ctx->wstop || !ctx->wjobs.empty(); });
+            if (ctx->wstop) return;
+            i = ctx->wjobs.front();
+            ctx->wjobs.pop_front();
+        }
+        Slot &s = ctx->slot[i];
+        int64_t C = -1;
+        if (cudaEventSynchronize(s.ev_front) == cudaSuccess && !s.h_counters[1]) {
+            C = s.h_counters[0];
+            py_shuffle_perm(s.prep_seed, C, s.h_perm, s.h_draws);
+        }
+        {
+            std::lock_guard<std::mutex> lk(ctx->wm);
+            s.prep_cells = C;
+            s.prep_state.store(2);
+        }
+        ctx->wdone.notify_all();
+    }
+}
+
+// the helper may still be writing the slot's permutation buffers: wait for it (and drop its result)
+void settle_prepared(slafb_ctx *ctx, Slot &s) {
+    if (s.prep_state.load() == 0) return;
+    std::unique_lock<std::mutex> lk(ctx->wm);
+    ctx->wdone.wait(lk, [&] { return s.prep_state.load() == 2; });
 }
 
 // waits for the cell count; builds + uploads the permutation.  Returns n_cells through *n.
@@ -419,10 +481,15 @@ int middle(slafb_ctx *ctx, Slot &s, const slafb_params *p, int64_t *n, cudaStrea
         if (s.h_counters[3])
             return fail(ctx, SLAFB_ERR_NONCONTIGUOUS, "a cell id occurs in two separated row runs; splice partial cells on the host first");
     }
+    settle_prepared(ctx, s);
+    const bool prepared = s.prep_state.load() == 2 && p->shuffle == SLAFB_SHUFFLE_SEED && s.prep_seed == p->seed && s.prep_cells == C;
+    s.prep_state.store(0);
     if (p->shuffle == SLAFB_SHUFFLE_SEED) {
-        const double ts0 = now_ms();
-        py_shuffle_perm(p->seed, C, s.h_perm, s.h_draws);
-        ctx->acc.host_shuffle_ms += now_ms() - ts0;
+        if (!prepared) {
+            const double ts0 = now_ms();
+            py_shuffle_perm(p->seed, C, s.h_perm, s.h_draws);
+            ctx->acc.host_shuffle_ms += now_ms() - ts0;
+        }
         *use_perm = true;
     } else if (p->shuffle == SLAFB_SHUFFLE_PERM) {
         // a permutation of all segments, or a SELECTION: fewer entries than segments emit only those
@@ -466,21 +533,22 @@ int back(slafb_ctx *ctx, Slot &s, const slafb_params *p, const slafb_out *out, i
     a.mask = out->attention_mask;
     a.vals = reinterpret_cast<long long *>(out->values);
     a.cell_ids = reinterpret_cast<long long *>(out->cell_ids);
+    a.host_slow = s.h_counters_dev + 2;
     WindowSink none{};
-    CU(ctx, cudaEventRecord(s.t_k2a, st));
+    if (s.sample) CU(ctx, cudaEventRecord(s.t_k2a, st));
     bool fast_launched = false;
     if (p->mode != SLAFB_GENEFORMER_PCT) {
         DISPATCH_TYPES(s.gene_dtype, s.value_dtype, rc = (dispatch_fast<GeneT, ValT>(ctx, p->mode, a, st, &fast_launched)));
         if (rc) return rc;
     }
     if (!fast_launched) a.all_cells = 1;
-    CU(ctx, cudaEventRecord(s.t_k2b, st));
+    if (s.sample) CU(ctx, cudaEventRecord(s.t_k2b, st));
     DISPATCH_TYPES(s.gene_dtype, s.value_dtype, rc = (dispatch_general<GeneT, ValT, 0>(ctx, p->mode, a, none, st)));
     if (rc) return rc;
-    CU(ctx, cudaEventRecord(s.t_k2c, st));
-    CU(ctx, cudaMemcpyAsync(s.h_counters + 2, s.counters + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    if (s.sample) CU(ctx, cudaEventRecord(s.t_k2c, st));
     s.all_general = !fast_launched;
-    s.timed_back = true;
+    s.timed_back = s.sample;
+    s.ran_back = true;
     CU(ctx, cudaEventRecord(s.ev_done, st));
     ctx->acc.batches++;
     ctx->acc.cells += C;
@@ -572,7 +640,9 @@ int slafb_create(slafb_ctx **out, int device, int64_t max_rows, int64_t max_cell
         CUC(cudaMalloc(&s.work_list, ((size_t)max_cells + 1) * sizeof(uint32_t)));
         CUC(cudaMalloc(&s.counters, 8 * sizeof(uint32_t)));
         CUC(cudaMemset(s.counters, 0, 8 * sizeof(uint32_t)));
-        CUC(cudaHostAlloc(&s.h_counters, 4 * sizeof(uint32_t), cudaHostAllocDefault));
+        CUC(cudaHostAlloc(&s.h_counters, 4 * sizeof(uint32_t), cudaHostAllocMapped | cudaHostAllocPortable));
+        memset(s.h_counters, 0, 4 * sizeof(uint32_t));
+        CUC(cudaHostGetDevicePointer(reinterpret_cast<void **>(&s.h_counters_dev), s.h_counters, 0));
         CUC(cudaHostAlloc(&s.h_perm, ((size_t)max_cells + 1) * sizeof(int32_t), cudaHostAllocDefault));
         s.h_draws = (uint32_t *)malloc(((size_t)max_cells + 1) * sizeof(uint32_t));
         if (!s.h_draws) { slafb_destroy(ctx); return fail(nullptr, SLAFB_ERR_INVALID, "out of host memory"); }
@@ -590,6 +660,14 @@ int slafb_create(slafb_ctx **out, int device, int64_t max_rows, int64_t max_cell
 int slafb_destroy(slafb_ctx *ctx) {
     if (!ctx) return SLAFB_OK;
     cudaSetDevice(ctx->device);
+    if (ctx->wstarted) {
+        {
+            std::lock_guard<std::mutex> lk(ctx->wm);
+            ctx->wstop = true;
+        }
+        ctx->wcv.notify_all();
+        ctx->worker.join();
+    }
     if (ctx->s_in) cudaStreamSynchronize(ctx->s_in);
     for (int i = 0; i < kSlots; i++) {
         Slot &s = ctx->slot[i];
@@ -630,6 +708,26 @@ int slafb_submit(slafb_ctx *ctx, const slafb_coo *in, void *stream, int32_t *slo
     return slafb_submit_pieces(ctx, in, 1, stream, slot);
 }
 
+int slafb_prepare_shuffle(slafb_ctx *ctx, int32_t slot, int64_t seed) {
+    if (!ctx || slot < 0 || slot >= kSlots) return fail(ctx, SLAFB_ERR_INVALID, "bad ctx / slot");
+    Slot &s = ctx->slot[slot];
+    if (!s.in_flight) return fail(ctx, SLAFB_ERR_INVALID, "slot %d has no submitted batch", slot);
+    if (s.prep_state.load() != 0) return fail(ctx, SLAFB_ERR_BUSY, "slot %d already has a prepared shuffle", slot);
+    {
+        std::lock_guard<std::mutex> lk(ctx->wm);
+        if (!ctx->wstarted) {
+            ctx->worker = std::thread(shuffle_worker, ctx);
+            ctx->wstarted = true;
+        }
+        s.prep_seed = seed;
+        s.prep_cells = -1;
+        s.prep_state.store(1);
+        ctx->wjobs.push_back(slot);
+    }
+    ctx->wcv.notify_one();
+    return SLAFB_OK;
+}
+
 int slafb_collect(slafb_ctx *ctx, int32_t slot, const slafb_params *p, const slafb_out *out, int64_t *n_cells, void *stream) {
     if (!ctx || slot < 0 || slot >= kSlots) return fail(ctx, SLAFB_ERR_INVALID, "bad ctx / slot");
     CU(ctx, cudaSetDevice(ctx->device));
@@ -641,7 +739,11 @@ int slafb_collect(slafb_ctx *ctx, int32_t slot, const slafb_params *p, const sla
     // output tensors too small: the CSR of this slot is still valid, so the caller may
     // re-collect with larger tensors; every other outcome releases the slot
     const bool retryable = (rc == SLAFB_ERR_CAPACITY) && n_cells && (*n_cells <= ctx->max_cells);
-    if (!retryable) s.in_flight = false;
+    if (!retryable) {
+        settle_prepared(ctx, s);        // the helper must be done with this slot's buffers before it is reused
+        s.prep_state.store(0);
+        s.in_flight = false;
+    }
     return rc;
 }
 
@@ -773,6 +875,12 @@ int slafb_gene_stats(slafb_ctx *ctx, const slafb_coo *in, int64_t n_genes, uint6
                                                                        (uint32_t)in->n_rows, (uint32_t)n_genes, usum, ucnt)));
     CU(ctx, cudaGetLastError());
     ctx->acc.kernel_launches++;
+    return SLAFB_OK;
+}
+
+int slafb_set_timing_interval(slafb_ctx *ctx, int32_t every) {
+    if (!ctx || every < 1) return fail(ctx, SLAFB_ERR_INVALID, "timing interval must be >= 1");
+    ctx->timing_every = every;
     return SLAFB_OK;
 }
 

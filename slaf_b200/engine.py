@@ -158,12 +158,15 @@ class HotPathEngine:
         return out, (ids, mask, vals, cids)
 
     # ------------------------------------------------------------------ the hot path
-    def submit(self, cell: Any, gene: Any, value: Any) -> int:
-        """Enqueue H2D (host columns) + CSR build on the side stream; returns the slot."""
+    def submit(self, cell: Any, gene: Any, value: Any, shuffle_seed: int | None = None) -> int:
+        """Enqueue H2D (host columns) + CSR build on the side stream; returns the slot.  With
+        ``shuffle_seed`` the library's helper thread prepares that shuffle while the GPU works."""
         coo, keep = _coo(cell, gene, value)
         slot = ctypes.c_int32(-1)
         with torch.cuda.device(self.device):
             N.check(self._L.slafb_submit(self._ctx, ctypes.byref(coo), self._stream(), ctypes.byref(slot)), self._ctx)
+            if shuffle_seed is not None:
+                N.check(self._L.slafb_prepare_shuffle(self._ctx, slot.value, int(shuffle_seed)), self._ctx)
         self._pending[slot.value] = (keep, coo.n_rows)
         return slot.value
 
@@ -302,6 +305,10 @@ class HotPathEngine:
                                              self._stream()), self._ctx)
         del keep
         return sum_out, cnt_out
+
+    def set_timing_interval(self, every: int) -> None:
+        """Take the per-kernel CUDA-event timings on every `every`-th batch only."""
+        N.check(self._L.slafb_set_timing_interval(self._ctx, int(every)), self._ctx)
 
     def timing(self) -> dict[str, float]:
         t = N.Timing()

@@ -36,7 +36,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_native.Coo) == 3 * 8 + 8 + 4 * 4
     assert ctypes.sizeof(_native.Params) == 4 * 4 + 8 + 8 + 4 + 4 + 8 + 8 + 8 + 4 + 4
     assert ctypes.sizeof(_native.Out) == 5 * 8
-    assert ctypes.sizeof(_native.Timing) == 4 * 8 + 5 * 8 + 4 * 8
+    assert ctypes.sizeof(_native.Timing) == 4 * 8 + 5 * 8 + 4 * 8 + 8
 
 
 @pytest.mark.parametrize("seed", [0, 1, 42, 43, 10042, 2**31 + 5, 2**40 + 7, -9])

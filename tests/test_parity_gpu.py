@@ -239,3 +239,17 @@ def test_large_batch_properties_and_full_compare(engine):
     assert sorted(got.cell_ids.cpu().tolist()) == list(range(2000))   # every cell exactly once
     want = c_oracle.tokenize(b.cell, b.gene, b.value, "scgpt_binned", 1200, perm=py_perm(42, 2000), n_bins=51, vocab_size=65000)
     compare(got, want, "scgpt_binned")
+
+
+def test_prepared_shuffle_matches_inline_shuffle(engine):
+    """slafb_prepare_shuffle: the helper thread's permutation is the one collect() would build itself;
+    a mismatching seed at collect time falls back to the inline build."""
+    b = synthetic.make_batch(700, 20000, 300, seed=12)
+    kw = dict(mode="geneformer", max_genes=256)
+    want = c_oracle.tokenize(b.cell, b.gene, b.value, "geneformer", 256, perm=py_perm(77, b.n_cells))
+    slots = [engine.submit(b.cell, b.gene, b.value, shuffle_seed=77) for _ in range(2)]
+    compare(engine.collect(slots[0], shuffle_seed=77, **kw), want, "geneformer")
+    want2 = c_oracle.tokenize(b.cell, b.gene, b.value, "geneformer", 256, perm=py_perm(78, b.n_cells))
+    compare(engine.collect(slots[1], shuffle_seed=78, **kw), want2, "geneformer")       # prepared for 77, collected with 78
+    s = engine.submit(b.cell, b.gene, b.value, shuffle_seed=5)
+    compare(engine.collect(s, **kw), c_oracle.tokenize(b.cell, b.gene, b.value, "geneformer", 256), "geneformer")   # prepared, then no shuffle
