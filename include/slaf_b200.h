@@ -209,9 +209,14 @@ int slafb_host_free(void *ptr);
 int slafb_host_register(void *ptr, size_t bytes);
 int slafb_host_unregister(void *ptr);
 
-/* Per-kernel CUDA-event timing is taken on every `every`-th batch (default 1 = all).  Each event record
- * is a stream operation; a throughput-critical caller samples (bench.py uses 4). */
-int slafb_set_timing_interval(slafb_ctx *ctx, int32_t every);
+/* Context options.
+ *   SLAFB_OPT_TIMING_INTERVAL  n >= 1: the per-kernel CUDA-event timings are taken on every n-th batch
+ *                              (default 1).  Each event record is a stream operation; bench.py samples.
+ *   SLAFB_OPT_FRONT_ON_CALLER  0|1: run the CSR build of DEVICE-resident batches on the caller's stream
+ *                              instead of the side stream (default 0).  Kernels then never overlap, which
+ *                              is how bench.py measures each kernel's own duration. */
+typedef enum { SLAFB_OPT_TIMING_INTERVAL = 1, SLAFB_OPT_FRONT_ON_CALLER = 2 } slafb_option;
+int slafb_set_option(slafb_ctx *ctx, int32_t option, int64_t value);
 
 /* Timing / counters since the previous call (synchronises the context's streams). */
 int slafb_get_timing(slafb_ctx *ctx, slafb_timing *t);

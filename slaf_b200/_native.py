@@ -29,11 +29,12 @@ GENEFORMER, GENEFORMER_PCT, SCGPT_RAW, SCGPT_BINNED = 0, 1, 2, 3
 LOC_DEVICE, LOC_HOST = 0, 1
 SHUFFLE_NONE, SHUFFLE_SEED, SHUFFLE_PERM = 0, 1, 2
 FLAG_CHECK_CONTIGUOUS = 1
+OPT_TIMING_INTERVAL, OPT_FRONT_ON_CALLER = 1, 2
 
 EXPORTS = [
     "slafb_version", "slafb_create", "slafb_destroy", "slafb_last_error", "slafb_tokenize", "slafb_submit", "slafb_submit_pieces", "slafb_host_register", "slafb_host_unregister",
     "slafb_collect", "slafb_prepare_shuffle", "slafb_segments", "slafb_window", "slafb_tokenize_lists", "slafb_shuffle_perm", "slafb_gene_stats",
-    "slafb_host_alloc", "slafb_host_free", "slafb_get_timing", "slafb_set_timing_interval",
+    "slafb_host_alloc", "slafb_host_free", "slafb_get_timing", "slafb_set_option",
 ]
 
 
@@ -136,7 +137,7 @@ def lib() -> ctypes.CDLL:
     L.slafb_gene_stats.argtypes = [c_void_p, POINTER(Coo), c_int64, c_void_p, c_void_p, c_void_p]
     L.slafb_host_alloc.argtypes = [POINTER(c_void_p), c_size_t]
     L.slafb_host_free.argtypes = [c_void_p]
-    L.slafb_set_timing_interval.argtypes = [c_void_p, c_int32]
+    L.slafb_set_option.argtypes = [c_void_p, c_int32, c_int64]
     L.slafb_get_timing.argtypes = [c_void_p, POINTER(Timing)]
     for name in EXPORTS:
         getattr(L, name)  # AttributeError here = header and library out of sync

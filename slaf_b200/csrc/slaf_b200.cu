@@ -99,6 +99,7 @@ struct slafb_ctx {
     // (each event record is a stream operation; on every batch they cost a few percent of a step)
     int timing_every = 1;
     uint64_t batch_seq = 0;
+    bool front_on_caller = false;
 };
 
 namespace {
@@ -324,9 +325,9 @@ int front(slafb_ctx *ctx, Slot &s, const slafb_coo *pieces, int n_pieces, cudaSt
     if (total > ctx->max_rows) return fail(ctx, SLAFB_ERR_CAPACITY, "n_rows %lld exceeds context max_rows %lld", (long long)total, (long long)ctx->max_rows);
     const slafb_coo *in = &pieces[0];
     // The side stream exists to overlap H2D copies with tokenization.  A device-resident batch has no
-    // copy to hide; SLAFB_FRONT_ON_CALLER=1 keeps its CSR build on the caller's stream (tuning knob).
-    static const bool front_on_caller = getenv("SLAFB_FRONT_ON_CALLER") && atoi(getenv("SLAFB_FRONT_ON_CALLER")) != 0;
-    cudaStream_t sf = (front_on_caller && in->location == SLAFB_LOC_DEVICE && n_pieces == 1) ? caller : ctx->s_in;
+    // copy to hide; SLAFB_OPT_FRONT_ON_CALLER keeps its CSR build on the caller's stream, so every kernel
+    // runs alone and its CUDA-event time is that kernel's own (bench.py's isolated-kernel pass).
+    cudaStream_t sf = (ctx->front_on_caller && in->location == SLAFB_LOC_DEVICE && n_pieces == 1) ? caller : ctx->s_in;
     if (s.ev_done) {
         // the slot's scratch may still be read by the previous batch's tokenization
         CU(ctx, cudaEventSynchronize(s.ev_done));
@@ -878,10 +879,19 @@ int slafb_gene_stats(slafb_ctx *ctx, const slafb_coo *in, int64_t n_genes, uint6
     return SLAFB_OK;
 }
 
-int slafb_set_timing_interval(slafb_ctx *ctx, int32_t every) {
-    if (!ctx || every < 1) return fail(ctx, SLAFB_ERR_INVALID, "timing interval must be >= 1");
-    ctx->timing_every = every;
-    return SLAFB_OK;
+int slafb_set_option(slafb_ctx *ctx, int32_t option, int64_t value) {
+    if (!ctx) return fail(ctx, SLAFB_ERR_INVALID, "ctx is NULL");
+    switch (option) {
+    case SLAFB_OPT_TIMING_INTERVAL:
+        if (value < 1 || value > 1000000) return fail(ctx, SLAFB_ERR_INVALID, "timing interval must be in [1, 1e6]");
+        ctx->timing_every = (int)value;
+        return SLAFB_OK;
+    case SLAFB_OPT_FRONT_ON_CALLER:
+        ctx->front_on_caller = value != 0;
+        return SLAFB_OK;
+    default:
+        return fail(ctx, SLAFB_ERR_INVALID, "unknown option %d", option);
+    }
 }
 
 int slafb_get_timing(slafb_ctx *ctx, slafb_timing *t) {

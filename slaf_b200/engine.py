@@ -308,7 +308,11 @@ class HotPathEngine:
 
     def set_timing_interval(self, every: int) -> None:
         """Take the per-kernel CUDA-event timings on every `every`-th batch only."""
-        N.check(self._L.slafb_set_timing_interval(self._ctx, int(every)), self._ctx)
+        N.check(self._L.slafb_set_option(self._ctx, N.OPT_TIMING_INTERVAL, int(every)), self._ctx)
+
+    def set_front_on_caller(self, on: bool) -> None:
+        """Device-resident batches: CSR build on the caller's stream (kernels never overlap)."""
+        N.check(self._L.slafb_set_option(self._ctx, N.OPT_FRONT_ON_CALLER, int(bool(on))), self._ctx)
 
     def timing(self) -> dict[str, float]:
         t = N.Timing()
