@@ -36,6 +36,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+ALL_CPUS = os.sched_getaffinity(0)
 
 WORKLOADS = {
     # BASELINE.json configs[1]: scGPT binned, n_bins=51, max_genes=1200, 60k genes (the metric's 1-GPU config)
@@ -281,6 +282,15 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    try:   # keep this rank's threads (and the pinned buffers they first touch) on the GPU's NUMA node
+        import pynvml
+
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[local_rank]) if vis and vis.split(",")[local_rank].isdigit() else local_rank
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(idx))
+    except Exception:
+        pass
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -467,6 +477,10 @@ def main():
     if e2e:
         line["e2e"] = e2e
     if world == 1 and not args.no_cpu_baseline:
+        try:   # the CPU arm may use every host core (the GPU arm pinned this process to the GPU's NUMA node)
+            os.sched_setaffinity(0, ALL_CPUS)
+        except Exception:
+            pass
         cores = len(os.sched_getaffinity(0))
         rate, n = cpu_port_rate(w, 768 * cores, cores)
         c_rate, c_thr = c_oracle_rate(w, 2048)

@@ -13,9 +13,9 @@ echo "== bench"; timeout 900 python bench.py --workload $W > gpurun_out/bench_$T
 echo "== bench reference arm"; timeout 600 python bench.py --impl reference --workload $W --steps 3 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2> gpurun_out/bench_ref_$TAG.err; echo "ref rc=$?"; tail -c 1500 gpurun_out/bench_ref_$TAG.json
 if [ $rc -eq 0 ]; then
   echo "== ncu launch list (bench.py, short)"
-  timeout 600 python bench.py --workload $W --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/bench_short_$TAG.json 2>&1 &&
+  timeout 600 python bench.py --workload $W --steps 4 --warmup 3 --no-cpu-baseline --no-loader > gpurun_out/bench_short_$TAG.json 2>&1 &&
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv \
-      python bench.py --workload $W --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_list_$TAG.log 2>&1
+      python bench.py --workload $W --steps 4 --warmup 3 --no-cpu-baseline --no-loader > gpurun_out/ncu_list_$TAG.log 2>&1
   echo "list rc=$?"
   echo "== ncu full (prof_driver: one K1 + K2 sequence per step)"
   timeout 300 python scripts/prof_driver.py $W 6 32768 > gpurun_out/prof_plain_$TAG.log 2>&1 &&
