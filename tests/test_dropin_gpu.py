@@ -218,3 +218,52 @@ def test_create_window_factory():
     assert isinstance(create_window("simple"), SimpleWindow)
     with pytest.raises(ValueError):
         create_window("nope")
+
+
+# ---------------------------------------------------------------- generic (Modal-side) pipeline: second caller of the path
+def test_generic_batch_processor_and_format_batch(engine):
+    """slaf/distributed/processor.py:105-301 + dataloader.py:357-475: boundary handling -> shuffle -> window ->
+    tokenize -> per-group samples -> collated batch; fused route and three-call route agree with the oracle."""
+    from oracle import py_restatement as pr
+    from slaf_b200.ml.distributed import BatchProcessor, format_batch, tokenize_grouped
+    from slaf_b200.ml.samplers import GenericShuffle
+
+    rng = np.random.default_rng(4)
+    lens = rng.integers(3, 40, 60)
+    cell = np.repeat(np.arange(100, 160, dtype=np.uint32), lens)
+    gene = np.concatenate([np.sort(rng.choice(5000, n, replace=False)) for n in lens]).astype(np.uint16)
+    value = rng.geometric(0.3, cell.size).astype(np.uint16)
+    cut = int(np.cumsum(lens)[29] + 2)                      # the batch boundary falls inside cell 130
+    raw = [{"cell_integer_id": cell[:cut], "gene_integer_id": gene[:cut], "value": value[:cut]},
+           {"cell_integer_id": cell[cut:], "gene_integer_id": gene[cut:], "value": value[cut:]}]
+
+    class Custom(GenericShuffle):       # a user-supplied strategy object forces the three-call route
+        pass
+
+    for shuffle in (GenericShuffle(), Custom()):
+        tok = ScGPTTokenizer(Mock(), vocab_size=6000, n_expression_bins=10, max_genes=16)
+        proc = BatchProcessor(SLAF_LANCE_COO_SCHEMA, window=ScGPTWindow(), shuffle=shuffle, tokenizer=tokenize_grouped(tok),
+                              max_items=16, seed=42, n_expression_bins=10, use_binned_expressions=False)
+        s1 = proc.process_batch([raw[0]], epoch=0, partition_id=0)
+        s2 = proc.process_batch([raw[1]], epoch=0, partition_id=0, is_partition_exhausted=True)
+        assert [x["group_key"] for x in s1 + s2] != sorted(x["group_key"] for x in s1 + s2)      # shuffled
+        assert sorted(x["group_key"] for x in s1) == list(range(100, 130))                      # cell 130 waits for its tail
+        assert sorted(x["group_key"] for x in s2) == list(range(130, 160))
+        # expected: complete rows of each call through the restated reference path, seed 42 + batch_id
+        first = cell < 130
+        for samples, rows, seed in ((s1, first, 42), (s2, ~first, 43)):
+            ids, mask, vals, cids = pr.hot_path(cell[rows], gene[rows], value[rows], "scgpt", 16, seed=seed, vocab_size=6000,
+                                                n_expression_bins=10, use_binned_expressions=False)
+            batch = next(format_batch(samples))
+            assert set(batch) == {"input_ids", "attention_mask", "cell_ids", "values"}
+            assert_same(batch["cell_ids"].cpu().numpy(), cids, "cell ids")
+            assert_same(batch["input_ids"].cpu().numpy(), ids, "ids")
+            assert_same(batch["values"].cpu().numpy(), vals, "values")
+            assert_same(batch["attention_mask"].cpu().numpy(), mask, "mask")
+    # no tokenizer: grouped samples
+    proc = BatchProcessor(SLAF_LANCE_COO_SCHEMA, window=GeneformerWindow(), shuffle=None, tokenizer=None, max_items=8)
+    out = proc.process_batch(raw, is_partition_exhausted=True)
+    assert len(out) == 60 and out[0]["group_key"] == 100 and set(out[0]["grouped"]) == {"cell_integer_id", "gene_sequence"}
+    g = next(format_batch(out[:3]))
+    assert g["group_keys"] == [100, 101, 102] and len(g["grouped"]) == 3
+    assert list(format_batch([])) == []

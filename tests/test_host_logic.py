@@ -240,3 +240,24 @@ def test_splice_partials_and_segment_regroup_equal_partition_by():
     for a, b in zip((got2.cell, got2.gene, got2.value), want):
         assert np.array_equal(a, b)
     assert all(p.cell.base is not None for p in pieces)           # views, not copies
+
+
+def test_group_boundary_handler_local_merge():
+    """slaf/distributed/boundary.py:66-153,285-357 (local part): the last group of a batch waits for the next
+    batch of the same partition; continuity = same group or the next integer."""
+    from slaf_b200.ml.distributed import GroupBoundaryHandler
+
+    h = GroupBoundaryHandler(SLAF_LANCE_COO_SCHEMA, continuity_check="sequential")
+    assert h.check_continuity(5, 5) and h.check_continuity(5, 6) and not h.check_continuity(5, 7)
+    assert GroupBoundaryHandler(SLAF_LANCE_COO_SCHEMA, "ordered").check_continuity(5, 9)
+    assert not GroupBoundaryHandler(SLAF_LANCE_COO_SCHEMA, "none").check_continuity(5, 6)
+    mk = lambda ids: {"cell_integer_id": np.asarray(ids, np.uint32), "gene_integer_id": np.arange(len(ids), dtype=np.uint16),
+                      "value": np.ones(len(ids), np.uint16)}
+    complete, partial = h.merge_partial_data({}, mk([1, 1, 2, 2, 3]), partition_id=0)
+    assert complete["cell_integer_id"].tolist() == [1, 1, 2, 2] and list(partial) == [3]
+    complete, partial = h.merge_partial_data(partial, mk([3, 3, 4]), partition_id=0)
+    assert complete["cell_integer_id"].tolist() == [3, 3, 3] and complete["gene_integer_id"].tolist() == [4, 0, 1] and list(partial) == [4]
+    complete, partial = h.merge_partial_data(partial, mk([5, 6]), partition_id=0, is_partition_exhausted=True)
+    assert complete["cell_integer_id"].tolist() == [4, 5, 6] and partial == {}
+    with pytest.raises(NotImplementedError):
+        GroupBoundaryHandler(SLAF_LANCE_COO_SCHEMA, partial_groups_kv={})
