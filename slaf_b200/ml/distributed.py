@@ -196,7 +196,8 @@ class BatchProcessor:
                        for i, key in enumerate(keys)]
         else:
             items = frames.list_column(grouped, s.item_list_key)
-            vals = frames.list_column(grouped, s.value_list_key) if s.value_list_key else None
+            cols_out = grouped.column_names if frames.frame_kind(grouped) == "arrow" else list(grouped.columns)
+            vals = frames.list_column(grouped, s.value_list_key) if (s.value_list_key and s.value_list_key in cols_out) else None
             samples = []
             for i, key in enumerate(keys):
                 g = {key_col: [key], s.item_list_key: [items[i]]}
