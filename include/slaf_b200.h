@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SLAFB_ABI_VERSION 1
+#define SLAFB_ABI_VERSION 2
 
 typedef struct slafb_ctx slafb_ctx;
 
@@ -78,6 +78,11 @@ typedef enum {
                                smaller than the number of segments (a selection: the other cells are not emitted)  */
 } slafb_shuffle;
 
+/* Order of the kept genes of a cell.  The reference keeps ROW order (aggregators.py:198-214, pinned by
+ * tests/test_aggregators.py:146-174); SLAFB_ORDER_RANK is the textbook Geneformer rank-value encoding
+ * (descending value, ties in row order) offered as a clearly separate extension. */
+typedef enum { SLAFB_ORDER_ROW = 0, SLAFB_ORDER_RANK = 1 } slafb_order;
+
 /* params.flags */
 #define SLAFB_FLAG_CHECK_CONTIGUOUS 1 /* verify that no cell id occurs in two separated runs (one extra sync) */
 
@@ -95,7 +100,12 @@ typedef struct {
     int64_t n_perm;
     int32_t window_n_bins; /* SLAFB_SCGPT_BINNED: n_expression_bins the WINDOW bins with (PrefetchBatchProcessor's,
                               datasets.py:1025-1028) when it differs from the tokenizer's n_bins; 0 = same as n_bins */
-    int32_t reserved;
+    int32_t order;         /* slafb_order; SLAFB_GENEFORMER only */
+    /* EXTENSION (not in the reference, BASELINE.json config 4): per-gene normaliser, float32 [n_norm] on the
+     * device.  Ranks are taken on float32(value) / norm[gene] (genes >= n_norm: 1.0).  NULL = the
+     * reference's behaviour (rank on the raw value).  SLAFB_GENEFORMER only. */
+    const float *norm;
+    int64_t n_norm;
 } slafb_params;
 
 /* Output tensors (device, row-major, caller-allocated for `capacity_cells` rows):
@@ -200,6 +210,14 @@ int slafb_shuffle_perm(int64_t seed, int64_t n, int32_t *perm);
  * accumulated INTO sum/cnt (uint64, device, length n_genes) so that ranks can all-reduce them. */
 int slafb_gene_stats(slafb_ctx *ctx, const slafb_coo *in, int64_t n_genes, uint64_t *sum,
                      uint64_t *cnt, void *stream);
+
+/* Extension (config 4): per-gene histogram of the uint16 values, accumulated INTO hist (uint32, device,
+ * [n_genes x n_bins], values >= n_bins - 1 in the last bin) so that ranks can all-reduce it; and the exact
+ * nonzero median of every gene from such a table (numpy.median semantics); exact[g] = 0 when a middle
+ * value fell into the overflow bin. */
+int slafb_gene_hist(slafb_ctx *ctx, const slafb_coo *in, int64_t n_genes, int32_t n_bins, uint32_t *hist, void *stream);
+int slafb_gene_median(slafb_ctx *ctx, const uint32_t *hist, int64_t n_genes, int32_t n_bins, float *median,
+                      uint8_t *exact, void *stream);
 
 /* Pinned host memory for the feeder's staging buffers (so H2D copies are truly async). */
 int slafb_host_alloc(void **ptr, size_t bytes);

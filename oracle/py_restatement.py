@@ -256,3 +256,42 @@ def hot_path(
             grouped["gene_sequence"], grouped["expr_sequence"], max_genes, vocab_size, n_expression_bins
         )
     return ids, mask, vals, np.asarray(grouped["cell_integer_id"], np.int64)
+
+
+# --------------------------------------------------------------------------- extension oracle (NOT in the reference)
+def geneformer_rank_value(cell, gene, value, max_genes: int, max_items: int | None = None, norm=None, order: str = "rank",
+                          seed: int | None = None):
+    """Oracle of the library's rank-value EXTENSION (BASELINE.json config 4); the reference has neither per-gene
+    normalisation nor rank order, so this pins the kernels to a written definition, not to
+    the reference ("parity unpinned").  Per cell, rows in arrival order:
+        x    = float32(value) / float32(norm[gene])      (norm None: x = value)
+        keep = rows whose dense rank of x, descending, is <= max_items             (the reference's filter)
+        seq  = kept genes by descending x, ties in row order (order="rank"), or in row order (order="row")
+    then GeneformerTokenizer.tokenize(seq).  Returns (ids, mask, cell_ids)."""
+    k = max_items if max_items is not None else max_genes
+    if seed is not None:
+        cell, gene, value = apply_block_shuffle(cell, gene, value, seed)
+    g, ids = first_appearance_groups(np.asarray(cell))
+    order_rows = np.argsort(g, kind="stable")
+    bounds = np.concatenate(([0], np.cumsum(np.bincount(g, minlength=len(ids)))))
+    seqs = []
+    for c in range(len(ids)):
+        rows = order_rows[bounds[c]:bounds[c + 1]]
+        gg = np.asarray(gene)[rows].astype(np.int64)
+        x = np.asarray(value)[rows].astype(np.float32)
+        if norm is not None:
+            d = np.ones(len(rows), np.float32)
+            inside = gg < len(norm)
+            d[inside] = np.asarray(norm, np.float32)[gg[inside]]
+            x = (x / d).astype(np.float32)
+        distinct = np.unique(x)[::-1]
+        thr = distinct[min(k, len(distinct)) - 1]
+        keep = x >= thr
+        if order == "rank":
+            idx = np.flatnonzero(keep)
+            idx = idx[np.lexsort((idx, -x[idx].astype(np.float64)))]
+        else:
+            idx = np.flatnonzero(keep)
+        seqs.append(gg[idx].tolist())
+    tok, mask, _ = geneformer_tokenize(seqs, max_genes)
+    return tok, mask, ids

@@ -30,10 +30,12 @@ LOC_DEVICE, LOC_HOST = 0, 1
 SHUFFLE_NONE, SHUFFLE_SEED, SHUFFLE_PERM = 0, 1, 2
 FLAG_CHECK_CONTIGUOUS = 1
 OPT_TIMING_INTERVAL, OPT_FRONT_ON_CALLER = 1, 2
+ORDER_ROW, ORDER_RANK = 0, 1
+ABI_VERSION = 2
 
 EXPORTS = [
     "slafb_version", "slafb_create", "slafb_destroy", "slafb_last_error", "slafb_tokenize", "slafb_submit", "slafb_submit_pieces", "slafb_host_register", "slafb_host_unregister",
-    "slafb_collect", "slafb_prepare_shuffle", "slafb_segments", "slafb_window", "slafb_tokenize_lists", "slafb_shuffle_perm", "slafb_gene_stats",
+    "slafb_collect", "slafb_prepare_shuffle", "slafb_segments", "slafb_window", "slafb_tokenize_lists", "slafb_shuffle_perm", "slafb_gene_stats", "slafb_gene_hist", "slafb_gene_median",
     "slafb_host_alloc", "slafb_host_free", "slafb_get_timing", "slafb_set_option",
 ]
 
@@ -50,7 +52,7 @@ class Params(Structure):
         ("mode", c_int32), ("max_items", c_int32), ("max_genes", c_int32), ("n_bins", c_int32),
         ("vocab_size", c_int64), ("min_percentile", c_double), ("shuffle", c_int32), ("flags", c_int32),
         ("seed", c_int64), ("perm", POINTER(c_int32)), ("n_perm", c_int64),
-        ("window_n_bins", c_int32), ("reserved", c_int32),
+        ("window_n_bins", c_int32), ("order", c_int32), ("norm", c_void_p), ("n_norm", c_int64),
     ]
 
 
@@ -135,6 +137,8 @@ def lib() -> ctypes.CDLL:
                                        c_int32, c_int64, POINTER(Out), c_void_p]
     L.slafb_shuffle_perm.argtypes = [c_int64, c_int64, c_void_p]
     L.slafb_gene_stats.argtypes = [c_void_p, POINTER(Coo), c_int64, c_void_p, c_void_p, c_void_p]
+    L.slafb_gene_hist.argtypes = [c_void_p, POINTER(Coo), c_int64, c_int32, c_void_p, c_void_p]
+    L.slafb_gene_median.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p]
     L.slafb_host_alloc.argtypes = [POINTER(c_void_p), c_size_t]
     L.slafb_host_free.argtypes = [c_void_p]
     L.slafb_set_option.argtypes = [c_void_p, c_int32, c_int64]

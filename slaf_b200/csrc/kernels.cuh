@@ -1222,6 +1222,203 @@ __global__ void __launch_bounds__(kTokThreads) tokenize_general_kernel(const Tok
 }
 
 // ------------------------------------------------------------------------------------------
+// K6 (extension, BASELINE.json config 4): Geneformer rank-value encoding with per-gene normalisation
+// ------------------------------------------------------------------------------------------
+// Not in the reference (it has no normalisation and keeps row order).  Per cell:
+//   x_i   = float32(value_i) / norm[gene_i]          (norm == nullptr: x_i = value_i)
+//   keep  = rows whose dense rank of x (descending) is <= max_items        -- the reference's filter
+//   order = rank_order ? descending x, ties in row order (stable)  :  row order
+// then the Geneformer framing (CLS, gene + 4, SEP, truncate to max_genes, PAD, mask).
+// One CTA per cell, persistent over a ticket; the cell's rows are sorted as 64-bit composites
+// (~key << 32 | row) with a bitonic network in shared memory (global scratch beyond 8192 rows).
+struct RankArgs {
+    TokArgs t;
+    const float *norm;               // [n_norm] or nullptr
+    uint32_t n_norm;
+    int rank_order;
+    unsigned long long *scratch64;   // [n_rows] composites of cells larger than kRankSmemKeys
+};
+constexpr int kRankSmemKeys = 8192;
+
+__device__ void bitonic_sort_asc_u64(unsigned long long *keys, uint32_t n) {
+    const int tid = threadIdx.x;
+    uint32_t P = 1;
+    while (P < n) P <<= 1;
+    const uint32_t half = P >> 1;
+    for (uint32_t k = 2; k <= P; k <<= 1) {
+        const uint32_t hk = k >> 1;
+        for (uint32_t t = tid; t < half; t += kTokThreads) {
+            const uint32_t blk = t / hk, i = t - blk * hk;
+            const uint32_t lo = blk * k + i, hi = blk * k + k - 1 - i;
+            if (hi < n) {
+                const unsigned long long x = keys[lo], y = keys[hi];
+                if (x > y) { keys[lo] = y; keys[hi] = x; }
+            }
+        }
+        __syncthreads();
+        for (uint32_t j = hk >> 1; j >= 1; j >>= 1) {
+            for (uint32_t t = tid; t < half; t += kTokThreads) {
+                const uint32_t lo = 2 * j * (t / j) + (t % j), hi = lo + j;
+                if (hi < n) {
+                    const unsigned long long x = keys[lo], y = keys[hi];
+                    if (x > y) { keys[lo] = y; keys[hi] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+template <typename GeneT, typename ValT>
+__device__ __forceinline__ uint32_t rank_key(const RankArgs &ra, GeneT g, ValT v) {
+    if (ra.norm == nullptr) return key_of(v);
+    const uint32_t gi = (uint32_t)g;
+    const float d = gi < ra.n_norm ? __ldg(ra.norm + gi) : 1.0f;
+    return key_of(__fdiv_rn((float)v, d));
+}
+
+template <typename GeneT, typename ValT>
+__global__ void __launch_bounds__(kTokThreads) tokenize_rank_kernel(const RankArgs ra) {
+    extern __shared__ __align__(16) unsigned long long rk_keys[];
+    __shared__ uint32_t s_ws[32], s_bcast[4], s_item;
+    const TokArgs &a = ra.t;
+    const int tid = threadIdx.x;
+    const GeneT *__restrict__ gene = static_cast<const GeneT *>(a.gene);
+    const ValT *__restrict__ value = static_cast<const ValT *>(a.value);
+    const uint32_t k = a.max_items, L = a.L, limit = L - 1u;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_item = atomicAdd(a.work_counters + 1, 1u);
+        __syncthreads();
+        const uint32_t j = s_item;
+        if (j >= a.n_cells) break;
+        const uint32_t c = a.perm ? (uint32_t)a.perm[j] : j;
+        const uint32_t s = __ldg(a.seg_start + c), e = __ldg(a.seg_start + c + 1), n = e - s;
+        unsigned long long *keys = (n <= (uint32_t)kRankSmemKeys) ? rk_keys : (ra.scratch64 + s);
+        for (uint32_t i = tid; i < n; i += kTokThreads) {
+            const uint32_t key = rank_key<GeneT, ValT>(ra, __ldg(gene + s + i), __ldg(value + s + i));
+            keys[i] = ((unsigned long long)(~key) << 32) | (unsigned long long)i;
+        }
+        __syncthreads();
+        bitonic_sort_asc_u64(keys, n);
+        // m = rows with dense rank <= k: the prefix before the (k+1)-th distinct key
+        if (tid == 0) s_bcast[0] = n;
+        __syncthreads();
+        uint32_t run = 0;
+        for (uint32_t ib = 0; ib < n && run <= k; ib += kTokThreads) {
+            const uint32_t i = ib + tid;
+            const uint32_t head = (i < n && (i == 0 || (uint32_t)(keys[i] >> 32) != (uint32_t)(keys[i - 1] >> 32))) ? 1u : 0u;
+            uint32_t tot;
+            const uint32_t ex = run + block_excl_scan(head, s_ws, tot);
+            if (head && ex == k) atomicMin(&s_bcast[0], i);
+            run += tot;
+        }
+        __syncthreads();
+        const uint32_t m = s_bcast[0];
+        const size_t row_base = (size_t)j * L;
+        uint32_t n_emit;
+        if (ra.rank_order) {
+            n_emit = min(m, limit);
+            for (uint32_t r = tid; r < n_emit; r += kTokThreads) {
+                const GeneT g = __ldg(gene + s + (uint32_t)(keys[r] & 0xffffffffull));
+                long long gid;
+                if constexpr (sizeof(GeneT) == 2) gid = (long long)g; else gid = (long long)(int32_t)g;
+                a.ids[row_base + 1 + r] = gid + 4;
+            }
+        } else {
+            // row order: keep rows whose key is >= the smallest kept key
+            const uint32_t thr_inv = m ? (uint32_t)(keys[m - 1] >> 32) : 0u;      // largest ~key kept
+            __syncthreads();
+            uint32_t base = 0;
+            for (uint32_t ib = 0; ib < n && base < limit; ib += kTokThreads) {
+                const uint32_t i = ib + tid;
+                GeneT g{};
+                uint32_t kp = 0;
+                if (i < n) {
+                    g = __ldg(gene + s + i);
+                    kp = (m && (~rank_key<GeneT, ValT>(ra, g, __ldg(value + s + i)) <= thr_inv)) ? 1u : 0u;
+                }
+                uint32_t tot;
+                const uint32_t off = base + block_excl_scan(kp, s_ws, tot);
+                if (kp && off < limit) {
+                    long long gid;
+                    if constexpr (sizeof(GeneT) == 2) gid = (long long)g; else gid = (long long)(int32_t)g;
+                    a.ids[row_base + 1 + off] = gid + 4;
+                }
+                base += tot;
+            }
+            n_emit = min(base, limit);
+        }
+        const uint32_t sep_pos = 1u + n_emit, t_len = min(n_emit + 2u, L);
+        if (tid == 0) {
+            a.ids[row_base] = 1;
+            if (sep_pos < L) a.ids[row_base + sep_pos] = 2;
+            const uint32_t cid = __ldg(a.seg_cell + c);
+            a.cell_ids[j] = a.cell_signed ? (long long)(int32_t)cid : (long long)cid;
+        }
+        fill_zero_i64(a.ids, row_base + t_len, row_base + L);
+        fill_mask(a.mask, row_base, L, t_len);
+    }
+}
+
+// K7 (extension): per-gene histogram of uint16 values (exact nonzero medians), [n_genes x n_bins] uint32;
+// values >= n_bins - 1 land in the last bin.  Integer counts: any reduction order gives the same table.
+template <typename GeneT>
+__global__ void __launch_bounds__(256) gene_hist_kernel(const GeneT *__restrict__ gene, const uint16_t *__restrict__ value,
+                                                        uint32_t n_rows, uint32_t n_genes, uint32_t n_bins, uint32_t *hist) {
+    const uint32_t stride = gridDim.x * blockDim.x * kGroup;
+    for (uint32_t r0 = (blockIdx.x * blockDim.x + threadIdx.x) * kGroup; r0 < n_rows; r0 += stride) {
+        GeneT g[8];
+        uint16_t v[8];
+        load8(gene, r0, n_rows, g);
+        load8(value, r0, n_rows, v);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t gi = (uint32_t)g[i];
+            if (r0 + i < n_rows && gi < n_genes && v[i] != 0)
+                atomicAdd(hist + (size_t)gi * n_bins + min((uint32_t)v[i], n_bins - 1u), 1u);
+        }
+    }
+}
+
+// median of the nonzero values of every gene from its histogram row (numpy.median: mean of the two middle
+// values for an even count); one warp per gene.  exact[g] = 0 when a middle value fell into the overflow bin.
+__global__ void __launch_bounds__(256) gene_median_kernel(const uint32_t *__restrict__ hist, uint32_t n_genes, uint32_t n_bins,
+                                                          float *__restrict__ median, uint8_t *__restrict__ exact) {
+    const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (g >= n_genes) return;
+    const uint32_t *row = hist + (size_t)g * n_bins;
+    unsigned long long total = 0;
+    for (uint32_t b = lane; b < n_bins; b += 32) total += row[b];
+#pragma unroll
+    for (int d = 16; d; d >>= 1) total += __shfl_xor_sync(0xffffffffu, total, d);
+    if (total == 0) { if (lane == 0) { median[g] = 0.0f; exact[g] = 1; } return; }
+    const unsigned long long r_lo = (total - 1) >> 1, r_hi = total >> 1;      // 0-based ranks of the middle values
+    uint32_t v_lo = 0xffffffffu, v_hi = 0xffffffffu;
+    unsigned long long run = 0;
+    for (uint32_t b0 = 0; b0 < n_bins && v_hi == 0xffffffffu; b0 += 32) {
+        const uint32_t b = b0 + lane;
+        const unsigned long long cnt = b < n_bins ? row[b] : 0ull;
+        unsigned long long inc = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, d);
+            if ((int)lane >= d) inc += t;
+        }
+        const unsigned long long ex = run + inc - cnt;
+        const bool has_lo = cnt && r_lo >= ex && r_lo < ex + cnt, has_hi = cnt && r_hi >= ex && r_hi < ex + cnt;
+        const uint32_t m_lo = __ballot_sync(0xffffffffu, has_lo), m_hi = __ballot_sync(0xffffffffu, has_hi);
+        if (m_lo && v_lo == 0xffffffffu) v_lo = b0 + (__ffs(m_lo) - 1);
+        if (m_hi) v_hi = b0 + (__ffs(m_hi) - 1);
+        run += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) {
+        median[g] = 0.5f * ((float)v_lo + (float)v_hi);
+        exact[g] = (v_hi < n_bins - 1u) ? 1 : 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // facade helpers
 // ------------------------------------------------------------------------------------------
 // exclusive scan of kept counts (one CTA; C is at most a few hundred thousand)

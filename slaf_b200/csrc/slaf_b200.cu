@@ -80,6 +80,7 @@ struct slafb_ctx {
     uint32_t *vstar_table = nullptr;  // binned window on uint16 storage: bin>=1 threshold per cell maximum
     int vstar_nbins = -1;
     uint32_t *sort_scratch = nullptr;
+    unsigned long long *rank_scratch = nullptr;   // rank-value extension: composites of very large cells (lazy)
     unsigned long long *dup_table = nullptr;   // contiguity check (lazy, grow-only)
     size_t dup_slots = 0;
     // window facade scratch
@@ -153,6 +154,10 @@ int check_params(slafb_ctx *ctx, const slafb_params *p) {
     if (p->max_items < 1) return fail(ctx, SLAFB_ERR_INVALID, "max_items must be >= 1, got %d", p->max_items);
     if (p->mode >= SLAFB_SCGPT_RAW && p->n_bins < 1) return fail(ctx, SLAFB_ERR_INVALID, "n_bins must be >= 1");
     if (p->window_n_bins < 0) return fail(ctx, SLAFB_ERR_INVALID, "window_n_bins must be >= 0");
+    if (p->order != SLAFB_ORDER_ROW && p->order != SLAFB_ORDER_RANK) return fail(ctx, SLAFB_ERR_INVALID, "unknown order %d", p->order);
+    if ((p->order == SLAFB_ORDER_RANK || p->norm) && p->mode != SLAFB_GENEFORMER)
+        return fail(ctx, SLAFB_ERR_INVALID, "rank order / per-gene normalisation are Geneformer-mode extensions");
+    if (p->norm && p->n_norm < 1) return fail(ctx, SLAFB_ERR_INVALID, "norm given but n_norm < 1");
     if (p->mode == SLAFB_GENEFORMER_PCT && !(p->min_percentile >= 0.0 && p->min_percentile <= 100.0))
         return fail(ctx, SLAFB_ERR_INVALID, "min_percentile must be within [0, 100]");
     return SLAFB_OK;
@@ -245,6 +250,23 @@ int launch_general(slafb_ctx *ctx, const TokArgs &a, const WindowSink &w, cudaSt
     if (a.n_cells < grid) grid = a.n_cells;
     if (grid == 0) grid = 1;
     kern<<<grid, kTokThreads, dyn, st>>>(a, w);
+    CU(ctx, cudaGetLastError());
+    ctx->acc.kernel_launches++;
+    return SLAFB_OK;
+}
+
+template <typename GeneT, typename ValT>
+int launch_rank(slafb_ctx *ctx, const RankArgs &ra, cudaStream_t st) {
+    auto kern = tokenize_rank_kernel<GeneT, ValT>;
+    const size_t dyn = (size_t)kRankSmemKeys * sizeof(unsigned long long);
+    static bool attr_set[64] = {false};
+    if (!attr_set[ctx->device & 63]) {
+        CU(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        attr_set[ctx->device & 63] = true;
+    }
+    uint32_t grid = (uint32_t)ctx->n_sm * 3u;       // 64 KiB of keys per CTA: three CTAs per SM
+    if (ra.t.n_cells < grid) grid = ra.t.n_cells;
+    kern<<<grid, kTokThreads, dyn, st>>>(ra);
     CU(ctx, cudaGetLastError());
     ctx->acc.kernel_launches++;
     return SLAFB_OK;
@@ -536,6 +558,30 @@ int back(slafb_ctx *ctx, Slot &s, const slafb_params *p, const slafb_out *out, i
     a.cell_ids = reinterpret_cast<long long *>(out->cell_ids);
     a.host_slow = s.h_counters_dev + 2;
     WindowSink none{};
+    if (p->mode == SLAFB_GENEFORMER && (p->order == SLAFB_ORDER_RANK || p->norm)) {
+        // extension path: every cell through the rank-value kernel
+        if (!ctx->rank_scratch) CU(ctx, cudaMalloc(&ctx->rank_scratch, ((size_t)ctx->max_rows + 64) * sizeof(unsigned long long)));
+        RankArgs ra;
+        ra.t = a;
+        ra.norm = p->norm;
+        ra.n_norm = (uint32_t)(p->n_norm > 0xffffffffll ? 0xffffffffll : p->n_norm);
+        ra.rank_order = p->order == SLAFB_ORDER_RANK;
+        ra.scratch64 = ctx->rank_scratch;
+        CU(ctx, cudaMemsetAsync(s.counters + 3, 0, sizeof(uint32_t), st));
+        if (s.sample) CU(ctx, cudaEventRecord(s.t_k2a, st));
+        DISPATCH_TYPES(s.gene_dtype, s.value_dtype, rc = (launch_rank<GeneT, ValT>(ctx, ra, st)));
+        if (rc) return rc;
+        if (s.sample) { CU(ctx, cudaEventRecord(s.t_k2b, st)); CU(ctx, cudaEventRecord(s.t_k2c, st)); }
+        s.h_counters[2] = 0;
+        s.all_general = false;
+        s.timed_back = s.sample;
+        s.ran_back = true;
+        CU(ctx, cudaEventRecord(s.ev_done, st));
+        ctx->acc.batches++;
+        ctx->acc.cells += C;
+        ctx->acc.rows += s.n_rows;
+        return SLAFB_OK;
+    }
     if (s.sample) CU(ctx, cudaEventRecord(s.t_k2a, st));
     bool fast_launched = false;
     if (p->mode != SLAFB_GENEFORMER_PCT) {
@@ -681,7 +727,7 @@ int slafb_destroy(slafb_ctx *ctx) {
         cudaEvent_t evs[] = {s.ev_front, s.ev_done, s.ev_in, s.t_h2d0, s.t_h2d1, s.t_k1a, s.t_k1b, s.t_k2a, s.t_k2b, s.t_k2c};
         for (auto e : evs) if (e) cudaEventDestroy(e);
     }
-    cudaFree(ctx->tile_state); cudaFree(ctx->ticket); cudaFree(ctx->log1p_lut); cudaFree(ctx->vstar_table); cudaFree(ctx->sort_scratch); cudaFree(ctx->dup_table);
+    cudaFree(ctx->tile_state); cudaFree(ctx->ticket); cudaFree(ctx->log1p_lut); cudaFree(ctx->vstar_table); cudaFree(ctx->sort_scratch); cudaFree(ctx->rank_scratch); cudaFree(ctx->dup_table);
     cudaFree(ctx->kept_count); cudaFree(ctx->total_dev);
     if (ctx->h_total) cudaFreeHost(ctx->h_total);
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
@@ -874,6 +920,39 @@ int slafb_gene_stats(slafb_ctx *ctx, const slafb_coo *in, int64_t n_genes, uint6
     DISPATCH_TYPES(in->gene_dtype, in->value_dtype,
                    (gene_stats_kernel<GeneT, ValT><<<grid, 256, 0, st>>>(static_cast<const GeneT *>(in->gene), static_cast<const ValT *>(in->value),
                                                                        (uint32_t)in->n_rows, (uint32_t)n_genes, usum, ucnt)));
+    CU(ctx, cudaGetLastError());
+    ctx->acc.kernel_launches++;
+    return SLAFB_OK;
+}
+
+int slafb_gene_hist(slafb_ctx *ctx, const slafb_coo *in, int64_t n_genes, int32_t n_bins, uint32_t *hist, void *stream) {
+    if (!ctx || !hist) return fail(ctx, SLAFB_ERR_INVALID, "NULL argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    int rc = check_coo(ctx, in);
+    if (rc) return rc;
+    if (in->location != SLAFB_LOC_DEVICE) return fail(ctx, SLAFB_ERR_INVALID, "gene_hist takes device-resident columns");
+    if (in->value_dtype != SLAFB_U16) return fail(ctx, SLAFB_ERR_INVALID, "gene_hist needs uint16 values (exact medians are defined on counts)");
+    if (n_genes < 1 || n_genes > 0x7fffffff || n_bins < 2 || n_bins > 65536) return fail(ctx, SLAFB_ERR_INVALID, "bad n_genes / n_bins");
+    if (in->n_rows == 0) return SLAFB_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const unsigned grid = (unsigned)ctx->n_sm * 8u;
+    if (in->gene_dtype == SLAFB_U16)
+        gene_hist_kernel<uint16_t><<<grid, 256, 0, st>>>(static_cast<const uint16_t *>(in->gene), static_cast<const uint16_t *>(in->value),
+                                                         (uint32_t)in->n_rows, (uint32_t)n_genes, (uint32_t)n_bins, hist);
+    else
+        gene_hist_kernel<int32_t><<<grid, 256, 0, st>>>(static_cast<const int32_t *>(in->gene), static_cast<const uint16_t *>(in->value),
+                                                        (uint32_t)in->n_rows, (uint32_t)n_genes, (uint32_t)n_bins, hist);
+    CU(ctx, cudaGetLastError());
+    ctx->acc.kernel_launches++;
+    return SLAFB_OK;
+}
+
+int slafb_gene_median(slafb_ctx *ctx, const uint32_t *hist, int64_t n_genes, int32_t n_bins, float *median, uint8_t *exact, void *stream) {
+    if (!ctx || !hist || !median || !exact) return fail(ctx, SLAFB_ERR_INVALID, "NULL argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (n_genes < 1 || n_genes > 0x3ffffff || n_bins < 2 || n_bins > 65536) return fail(ctx, SLAFB_ERR_INVALID, "bad n_genes / n_bins");
+    const unsigned blocks = (unsigned)((n_genes * 32 + 255) / 256);
+    gene_median_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(hist, (uint32_t)n_genes, (uint32_t)n_bins, median, exact);
     CU(ctx, cudaGetLastError());
     ctx->acc.kernel_launches++;
     return SLAFB_OK;

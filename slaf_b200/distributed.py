@@ -124,6 +124,20 @@ def gene_stats(engine: Any, batches, n_genes: int, group: Any = None) -> tuple[t
     return buf[0], buf[1]
 
 
+def gene_medians(engine: Any, batches, n_genes: int, n_bins: int = 1024, group: Any = None):
+    """Exact per-gene nonzero medians over ALL ranks' rows: per-rank histograms ([G, n_bins] int32, accumulated by
+    the kernel straight into the reduce buffer), one all-reduce, then the median kernel.  Returns
+    (median float32 [G], exact bool [G]); exact is False where a middle value is >= n_bins - 1."""
+    import torch.distributed as dist
+
+    hist = torch.zeros((n_genes, n_bins), dtype=torch.int32, device=engine.device)
+    for cols in batches:
+        engine.gene_hist(cols[-2], cols[-1], n_genes, n_bins, hist_out=hist)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
+    return engine.gene_median(hist)
+
+
 def normalisation_vector(total: torch.Tensor, count: torch.Tensor) -> torch.Tensor:
     """Per-gene mean of the nonzero values as float32 (1.0 for genes never seen); f64 division after
     the integer reduce, so every rank computes the bit-identical vector."""

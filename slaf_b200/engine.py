@@ -121,7 +121,7 @@ class HotPathEngine:
     # ------------------------------------------------------------------ helpers
     def _params(self, mode: str, max_genes: int, max_items: int | None, n_bins: int, vocab_size: int,
                 min_percentile: float | None, shuffle_seed: int | None, perm, check_contiguous: bool = False,
-                window_n_bins: int | None = None) -> tuple[N.Params, Any]:
+                window_n_bins: int | None = None, order: str = "row", norm: torch.Tensor | None = None) -> tuple[N.Params, Any]:
         if mode not in MODES:
             raise ValueError(f"unknown mode {mode!r}")
         if max_genes < 1:
@@ -135,6 +135,14 @@ class HotPathEngine:
         p.min_percentile = float(min_percentile) if min_percentile is not None else 0.0
         p.flags = N.FLAG_CHECK_CONTIGUOUS if check_contiguous else 0
         p.window_n_bins = int(window_n_bins) if window_n_bins else 0
+        if order not in ("row", "rank"):
+            raise ValueError(f"order must be 'row' (the reference's) or 'rank', got {order!r}")
+        p.order = N.ORDER_RANK if order == "rank" else N.ORDER_ROW
+        if norm is not None:
+            if not (isinstance(norm, torch.Tensor) and norm.is_cuda and norm.dtype == torch.float32 and norm.is_contiguous()):
+                raise TypeError("norm must be a contiguous float32 CUDA tensor [n_genes]")
+            p.norm = norm.data_ptr()
+            p.n_norm = norm.numel()
         keep = None
         if perm is not None:
             keep = np.ascontiguousarray(np.asarray(perm, np.int32))
@@ -191,10 +199,10 @@ class HotPathEngine:
     def collect(self, slot: int, *, mode: str, max_genes: int, max_items: int | None = None, n_bins: int = 10,
                 vocab_size: int = 50000, min_percentile: float | None = None, shuffle_seed: int | None = None,
                 perm=None, capacity_cells: int | None = None, check_contiguous: bool = False,
-                window_n_bins: int | None = None) -> TokenizedBatch:
+                window_n_bins: int | None = None, order: str = "row", norm: torch.Tensor | None = None) -> TokenizedBatch:
         keep, n_rows = self._pending.pop(slot)
         p, pkeep = self._params(mode, max_genes, max_items, n_bins, vocab_size, min_percentile, shuffle_seed, perm,
-                                check_contiguous, window_n_bins)
+                                check_contiguous, window_n_bins, order, norm)
         scgpt = p.mode >= N.SCGPT_RAW
         L = max_genes + 2 if scgpt else max_genes
         cap = capacity_cells or self._cap_hint or max(64, min(self.max_cells, n_rows // 256 + 64))
@@ -305,6 +313,27 @@ class HotPathEngine:
                                              self._stream()), self._ctx)
         del keep
         return sum_out, cnt_out
+
+    def gene_hist(self, gene: torch.Tensor, value: torch.Tensor, n_genes: int, n_bins: int = 1024, hist_out: torch.Tensor | None = None):
+        """Accumulate the per-gene histogram of uint16 values into an int32 [n_genes, n_bins] device tensor (extension)."""
+        if hist_out is None:
+            hist_out = torch.zeros((n_genes, n_bins), dtype=torch.int32, device=self.device)
+        cell_dummy = torch.empty(gene.numel(), dtype=torch.int32, device=self.device)
+        coo, keep = _coo(cell_dummy, gene, value)
+        with torch.cuda.device(self.device):
+            N.check(self._L.slafb_gene_hist(self._ctx, ctypes.byref(coo), n_genes, n_bins, hist_out.data_ptr(), self._stream()), self._ctx)
+        del keep
+        return hist_out
+
+    def gene_median(self, hist: torch.Tensor):
+        """(median float32 [G], exact bool [G]) of the nonzero values per gene from a histogram table."""
+        n_genes, n_bins = hist.shape
+        med = torch.empty(n_genes, dtype=torch.float32, device=self.device)
+        exact = torch.empty(n_genes, dtype=torch.bool, device=self.device)
+        with torch.cuda.device(self.device):
+            N.check(self._L.slafb_gene_median(self._ctx, hist.data_ptr(), n_genes, n_bins, med.data_ptr(), exact.data_ptr(),
+                                              self._stream()), self._ctx)
+        return med, exact
 
     def set_timing_interval(self, every: int) -> None:
         """Take the per-kernel CUDA-event timings on every `every`-th batch only."""

@@ -29,12 +29,12 @@ def test_header_symbols_all_exported(lib):
     assert declared == set(_native.EXPORTS), declared ^ set(_native.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
-    assert lib.slafb_version() == 1
+    assert lib.slafb_version() == _native.ABI_VERSION == 2
 
 
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(_native.Coo) == 3 * 8 + 8 + 4 * 4
-    assert ctypes.sizeof(_native.Params) == 4 * 4 + 8 + 8 + 4 + 4 + 8 + 8 + 8 + 4 + 4
+    assert ctypes.sizeof(_native.Params) == 4 * 4 + 8 + 8 + 4 + 4 + 8 + 8 + 8 + 4 + 4 + 8 + 8
     assert ctypes.sizeof(_native.Out) == 5 * 8
     assert ctypes.sizeof(_native.Timing) == 4 * 8 + 5 * 8 + 4 * 8 + 8
 
