@@ -200,9 +200,13 @@ class HotPathEngine:
                 vocab_size: int = 50000, min_percentile: float | None = None, shuffle_seed: int | None = None,
                 perm=None, capacity_cells: int | None = None, check_contiguous: bool = False,
                 window_n_bins: int | None = None, order: str = "row", norm: torch.Tensor | None = None) -> TokenizedBatch:
+        try:
+            p, pkeep = self._params(mode, max_genes, max_items, n_bins, vocab_size, min_percentile, shuffle_seed, perm,
+                                    check_contiguous, window_n_bins, order, norm)
+        except Exception:
+            self._abandon(slot)          # bad arguments must not leave the submitted batch occupying its slot
+            raise
         keep, n_rows = self._pending.pop(slot)
-        p, pkeep = self._params(mode, max_genes, max_items, n_bins, vocab_size, min_percentile, shuffle_seed, perm,
-                                check_contiguous, window_n_bins, order, norm)
         scgpt = p.mode >= N.SCGPT_RAW
         L = max_genes + 2 if scgpt else max_genes
         cap = capacity_cells or self._cap_hint or max(64, min(self.max_cells, n_rows // 256 + 64))
@@ -222,6 +226,16 @@ class HotPathEngine:
         ids, mask, vals, cids = tensors
         del keep, pkeep
         return TokenizedBatch(ids[:C], mask[:C], vals[:C] if scgpt else None, cids[:C], C)
+
+    def _abandon(self, slot: int) -> None:
+        if slot in self._pending:
+            self._pending.pop(slot)
+            p = N.Params()
+            p.mode, p.max_genes, p.max_items, p.n_bins, p.shuffle, p.n_perm = N.GENEFORMER, 1, 1, 1, N.SHUFFLE_PERM, 0
+            out = N.Out(None, None, None, None, 0)
+            n = ctypes.c_int64(0)
+            with torch.cuda.device(self.device):
+                self._L.slafb_collect(self._ctx, slot, ctypes.byref(p), ctypes.byref(out), ctypes.byref(n), self._stream())
 
     def release(self, slot: int) -> None:
         """Give a submitted slot back without tokenizing it (an empty selection emits no rows)."""
@@ -251,9 +265,9 @@ class HotPathEngine:
     def tokenize(self, cell: Any, gene: Any, value: Any, **kw) -> TokenizedBatch:
         """shuffle -> window -> tokenize -> cell ids for one batch of complete cells
         (reference: slaf/ml/datasets.py:1011-1098)."""
-        probe = {k: kw.get(k) for k in ("max_items", "min_percentile", "shuffle_seed", "perm")}
-        self._params(kw["mode"], kw["max_genes"], probe["max_items"], kw.get("n_bins", 10), kw.get("vocab_size", 50000),
-                     probe["min_percentile"], probe["shuffle_seed"], probe["perm"])  # raises before a slot is taken
+        self._params(kw["mode"], kw["max_genes"], kw.get("max_items"), kw.get("n_bins", 10), kw.get("vocab_size", 50000),
+                     kw.get("min_percentile"), kw.get("shuffle_seed"), kw.get("perm"), kw.get("check_contiguous", False),
+                     kw.get("window_n_bins"), kw.get("order", "row"), kw.get("norm"))      # raises before a slot is taken
         return self.collect(self.submit(cell, gene, value), **kw)
 
     # ------------------------------------------------------------------ facades
