@@ -47,6 +47,12 @@ WORKLOADS = {
                  mode="geneformer", tokenizer="geneformer", max_genes=2048, n_bins=10, vocab=50000, n_genes=20000, mean_nnz=2000, binned=False),
     "cfg3": dict(name="cfg3: Geneformer tokenization (max_genes=2048), synthetic 62k-gene Tahoe-scale COO, ~2k nnz/cell, sharded by fragment range",
                  mode="geneformer", tokenizer="geneformer", max_genes=2048, n_bins=10, vocab=50000, n_genes=62000, mean_nnz=2000, binned=False),
+    # configs[3] (EXTENSION, not in the reference): per-gene normalisation vectors computed on device (+ all-reduce over the
+    # ranks), feeding Geneformer rank-value tokenization in descending normalised-value order
+    "cfg4": dict(name="cfg4 (extension): per-gene nonzero means on device + all-reduce, then Geneformer rank-value tokenization "
+                      "(descending value/norm[gene], max_genes=2048), synthetic 62k-gene COO, ~2k nnz/cell",
+                 mode="geneformer", tokenizer="geneformer", max_genes=2048, n_bins=10, vocab=50000, n_genes=62000, mean_nnz=2000, binned=False,
+                 rank_norm=True),
 }
 
 
@@ -63,7 +69,7 @@ def algorithmic_bytes(w, nnz, value_bytes=2, gene_bytes=2):
     L = w["max_genes"] + 2 if scgpt else w["max_genes"]
     limit = w["max_genes"] if scgpt else w["max_genes"] - 1
     out_per_cell = (17 * L + 8) if scgpt else (9 * L + 8)
-    need_values = scgpt | (nnz > w["max_genes"])          # Geneformer cells with n <= k never touch their values
+    need_values = scgpt | (nnz > w["max_genes"]) | bool(w.get("rank_norm"))   # Geneformer cells with n <= k never touch their values
     k1 = 4 * n_rows + 8 * n_cells
     k2 = int(value_bytes * nnz[need_values].sum() + gene_bytes * np.minimum(nnz, limit).sum()) + (12 + out_per_cell) * n_cells
     h2d = (4 + gene_bytes + value_bytes) * n_rows
@@ -132,8 +138,12 @@ def _port_worker(args):
     (cell, gene, value, w, seed) = args
     from oracle import py_restatement as pr
     t0 = time.perf_counter()
-    ids, mask, vals, cids = pr.hot_path(cell, gene, value, w["tokenizer"], w["max_genes"], seed=seed, vocab_size=w["vocab"],
-                                        n_expression_bins=w["n_bins"], use_binned_expressions=w["binned"])
+    if w.get("rank_norm"):
+        norm = np.ones(w["n_genes"], np.float32)       # the CPU arm is given the vector; only the tokenization is timed
+        ids, mask, cids = pr.geneformer_rank_value(cell, gene, value, w["max_genes"], norm=norm, order="rank", seed=seed)
+    else:
+        ids, mask, vals, cids = pr.hot_path(cell, gene, value, w["tokenizer"], w["max_genes"], seed=seed, vocab_size=w["vocab"],
+                                            n_expression_bins=w["n_bins"], use_binned_expressions=w["binned"])
     return len(cids), time.perf_counter() - t0
 
 
@@ -324,6 +334,25 @@ def main():
     kw = dict(mode=w["mode"], max_genes=w["max_genes"], n_bins=w["n_bins"], vocab_size=w["vocab"])
     timing_every = int(os.environ.get("SLAFB_BENCH_TIMING_EVERY", "8"))
 
+    dev_cols = [(torch.from_numpy(b.cell).to(dev), torch.from_numpy(b.gene).to(dev), torch.from_numpy(b.value).to(dev)) for b in batches]
+    stats = None
+    if w.get("rank_norm"):
+        # config 4: per-gene nonzero sum / count over this rank's rows (K5 accumulates straight into the reduce buffer),
+        # ONE all-reduce over NVLink, mean = sum / count in f64 -> the float32 normaliser every rank uses
+        from slaf_b200.distributed import gene_stats, normalisation_vector
+
+        gene_stats(eng, dev_cols[:1], w["n_genes"])        # warm-up (NCCL communicator, kernel load)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        total, count = gene_stats(eng, dev_cols, w["n_genes"])
+        s1.record()
+        barrier()
+        norm_dev = normalisation_vector(total, count).contiguous()
+        stats = {"ms_stats_plus_allreduce": max_over_ranks(s0.elapsed_time(s1)), "rows_per_gpu": int(sum(b.n_rows for b in batches)),
+                 "allreduce_bytes": 2 * 8 * w["n_genes"], "collective": "NCCL all-reduce (sum, int64) of [2, n_genes]" if world > 1 else "none (1 rank)"}
+        kw.update(order="rank", norm=norm_dev)
+
     # ---- parity gate (bit-exact against the CPU oracle) before any number counts
     from oracle import c_oracle
     import random as _random
@@ -333,15 +362,23 @@ def main():
     rows_v = int(vb.cell_start[nv])
     _random.seed(42)
     perm = list(range(nv)); _random.shuffle(perm)
-    want = c_oracle.tokenize(vb.cell[:rows_v], vb.gene[:rows_v], vb.value[:rows_v], w["mode"], w["max_genes"], perm=perm,
-                             n_bins=w["n_bins"], vocab_size=w["vocab"])
+    if w.get("rank_norm"):
+        from oracle import py_restatement as _pr
+
+        nv = min(nv, 512)
+        rows_v = int(vb.cell_start[nv])
+        w_ids, w_mask, w_cids = _pr.geneformer_rank_value(vb.cell[:rows_v], vb.gene[:rows_v], vb.value[:rows_v], w["max_genes"],
+                                                          norm=norm_dev.cpu().numpy(), order="rank", seed=42)
+        want = (w_ids, w_mask, None, w_cids)
+    else:
+        want = c_oracle.tokenize(vb.cell[:rows_v], vb.gene[:rows_v], vb.value[:rows_v], w["mode"], w["max_genes"], perm=perm,
+                                 n_bins=w["n_bins"], vocab_size=w["vocab"])
     got = eng.tokenize(vb.cell[:rows_v], vb.gene[:rows_v], vb.value[:rows_v], shuffle_seed=42, **kw)
     ok = (np.array_equal(got.input_ids.cpu().numpy(), want[0]) and np.array_equal(got.attention_mask.cpu().numpy(), want[1])
           and (want[2] is None or np.array_equal(got.values.cpu().numpy(), want[2])) and np.array_equal(got.cell_ids.cpu().numpy(), want[3]))
     if not ok:
         raise SystemExit("PARITY FAILURE: CUDA path differs from the oracle; refusing to report throughput")
 
-    dev_cols = [(torch.from_numpy(b.cell).to(dev), torch.from_numpy(b.gene).to(dev), torch.from_numpy(b.value).to(dev)) for b in batches]
     host_cols = [tuple(torch.from_numpy(a).pin_memory() for a in (b.cell, b.gene, b.value)) for b in batches]
     tot_rows = [b.n_rows for b in batches]
     vbytes = 2 if args.value_dtype == "uint16" else 4
@@ -421,7 +458,7 @@ def main():
                "h2d_gbs_per_gpu": h2d_bytes / dt / 1e9,
                "h2d_copy_gbs": (h2d_bytes * tme["timed_batches"] / max(1, tme["batches"]) / (tme["h2d_ms"] / 1e3) / 1e9) if tme["h2d_ms"] else None}
 
-        if not args.no_loader:
+        if not args.no_loader and not w.get("rank_norm"):
             e2e["loader"] = loader_rate(w, batches, dev, args.value_dtype)
 
     clocks = sampler.stop() if rank == 0 else None
@@ -460,8 +497,9 @@ def main():
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
         "config": {"workload": w["name"], "cells_per_step_per_gpu": cps, "rows_per_step_per_gpu": int(np.mean(tot_rows)),
                    "value_dtype": args.value_dtype, "l2": f"{NB} distinct resident batches of {int(np.mean(tot_rows)) * 8 >> 20} MiB input each are cycled (each > 126 MB L2)",
-                   "shuffle": "CPython-exact block shuffle, seed 42+step", "parity": f"bit-exact vs oracle on {nv} cells before timing"},
-        "roofline": {"bound": "hbm", "kernel": "tokenize_cells_kernel", "achieved": k2_gbs, "peak": peak, "unit": "GB/s",
+                   "shuffle": "CPython-exact block shuffle, seed 42+step", "parity": f"bit-exact vs oracle on {nv} cells before timing",
+                   **({"gene_stats": stats} if stats else {})},
+        "roofline": {"bound": "hbm", "kernel": "tokenize_rank_kernel (per-cell bitonic sort: not HBM-bound)" if w.get("rank_norm") else "tokenize_cells_kernel", "achieved": k2_gbs, "peak": peak, "unit": "GB/s",
                      "frac": (k2_gbs / peak) if k2_gbs else None, "traffic": traffic,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s",
                      "algorithmic_bytes_per_launch": int(k2_b / args.steps), "avg_launch_ms": k2_ms, "timed_launches": int(tm["timed_batches"]),
