@@ -613,27 +613,30 @@ __device__ uint32_t threshold_bitmap(const ValT *__restrict__ value, uint32_t s,
 // float32 values: bitonic sort of the keys (shared memory, or global scratch when the cell is
 // larger than kSortSmemKeys), then the a*-th distinct key.  All compare-exchanges are ascending
 // (mirrored first step), so the virtual +inf padding above n never moves.
-__device__ void bitonic_sort_asc(uint32_t *keys, uint32_t n) {
+template <typename KeyT>
+__device__ void bitonic_sort_asc_t(KeyT *keys, uint32_t n) {
     const int tid = threadIdx.x;
     uint32_t P = 1;
     while (P < n) P <<= 1;
     const uint32_t half = P >> 1;
-    for (uint32_t k = 2; k <= P; k <<= 1) {
-        const uint32_t hk = k >> 1;
+    // all strides are powers of two: index arithmetic with shifts and masks only
+    for (uint32_t k = 2, lgk = 1; k <= P; k <<= 1, lgk++) {
+        const uint32_t hk = k >> 1, lgh = lgk - 1;
         for (uint32_t t = tid; t < half; t += kTokThreads) {
-            const uint32_t blk = t / hk, i = t - blk * hk;
-            const uint32_t lo = blk * k + i, hi = blk * k + k - 1 - i;
+            const uint32_t i = t & (hk - 1u);
+            const uint32_t base = (t >> lgh) << lgk;
+            const uint32_t lo = base | i, hi = base | ((k - 1u) ^ i);          // mirrored first step: i <-> k-1-i
             if (hi < n) {
-                const uint32_t x = keys[lo], y = keys[hi];
+                const KeyT x = keys[lo], y = keys[hi];
                 if (x > y) { keys[lo] = y; keys[hi] = x; }
             }
         }
         __syncthreads();
-        for (uint32_t j = hk >> 1; j >= 1; j >>= 1) {
+        for (uint32_t j = hk >> 1, lgj = lgh - 1u; j >= 1; j >>= 1, lgj--) {
             for (uint32_t t = tid; t < half; t += kTokThreads) {
-                const uint32_t lo = 2 * j * (t / j) + (t % j), hi = lo + j;
+                const uint32_t lo = ((t >> lgj) << (lgj + 1u)) | (t & (j - 1u)), hi = lo | j;
                 if (hi < n) {
-                    const uint32_t x = keys[lo], y = keys[hi];
+                    const KeyT x = keys[lo], y = keys[hi];
                     if (x > y) { keys[lo] = y; keys[hi] = x; }
                 }
             }
@@ -641,6 +644,7 @@ __device__ void bitonic_sort_asc(uint32_t *keys, uint32_t n) {
         }
     }
 }
+__device__ void bitonic_sort_asc(uint32_t *keys, uint32_t n) { bitonic_sort_asc_t<uint32_t>(keys, n); }
 
 template <typename ValT>
 __device__ uint32_t threshold_sort(const ValT *__restrict__ value, uint32_t s, uint32_t e, uint32_t R,
@@ -1240,34 +1244,7 @@ struct RankArgs {
 };
 constexpr int kRankSmemKeys = 8192;
 
-__device__ void bitonic_sort_asc_u64(unsigned long long *keys, uint32_t n) {
-    const int tid = threadIdx.x;
-    uint32_t P = 1;
-    while (P < n) P <<= 1;
-    const uint32_t half = P >> 1;
-    for (uint32_t k = 2; k <= P; k <<= 1) {
-        const uint32_t hk = k >> 1;
-        for (uint32_t t = tid; t < half; t += kTokThreads) {
-            const uint32_t blk = t / hk, i = t - blk * hk;
-            const uint32_t lo = blk * k + i, hi = blk * k + k - 1 - i;
-            if (hi < n) {
-                const unsigned long long x = keys[lo], y = keys[hi];
-                if (x > y) { keys[lo] = y; keys[hi] = x; }
-            }
-        }
-        __syncthreads();
-        for (uint32_t j = hk >> 1; j >= 1; j >>= 1) {
-            for (uint32_t t = tid; t < half; t += kTokThreads) {
-                const uint32_t lo = 2 * j * (t / j) + (t % j), hi = lo + j;
-                if (hi < n) {
-                    const unsigned long long x = keys[lo], y = keys[hi];
-                    if (x > y) { keys[lo] = y; keys[hi] = x; }
-                }
-            }
-            __syncthreads();
-        }
-    }
-}
+__device__ void bitonic_sort_asc_u64(unsigned long long *keys, uint32_t n) { bitonic_sort_asc_t<unsigned long long>(keys, n); }
 
 template <typename GeneT, typename ValT>
 __device__ __forceinline__ uint32_t rank_key(const RankArgs &ra, GeneT g, ValT v) {
