@@ -175,6 +175,15 @@ int slafb_prepare_shuffle(slafb_ctx *ctx, int32_t slot, int64_t seed);
 int slafb_collect(slafb_ctx *ctx, int32_t slot, const slafb_params *p, const slafb_out *out,
                   int64_t *n_cells, void *stream);
 
+/* Raw mode on the device, replacing RawPrefetchBatch (slaf/ml/datasets.py:288-296, 958-1008: shuffle only, no
+ * window, no tokenizer): the submitted batch as a CSR matrix whose rows are the cells in the requested order
+ * (p->shuffle / seed / perm as in collect(); a perm may be a selection).  Device outputs, caller allocated:
+ * crow int64 [capacity_cells + 1], col int32 [capacity_rows] (gene ids), val [capacity_rows] in the batch's value
+ * dtype, cell_ids int64 [capacity_cells].  Synchronous with respect to *n_cells and *n_rows; always releases the slot. */
+int slafb_collect_csr(slafb_ctx *ctx, int32_t slot, const slafb_params *p, int64_t *crow, int32_t *col, void *val,
+                      int64_t *cell_ids, int64_t capacity_cells, int64_t capacity_rows, int64_t *n_cells, int64_t *n_rows,
+                      void *stream);
+
 /* The segment table K1 built for a submitted batch, copied to the host (blocks until the H2D copy
  * and CSR build of that slot are done): n_cells segments in order of first appearance,
  * seg_start[n_cells + 1] row offsets, seg_cell[n_cells] cell ids (uint32 bits of the cell column).

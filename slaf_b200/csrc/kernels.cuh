@@ -1461,6 +1461,37 @@ __global__ void dup_check_kernel(const uint32_t *seg_cell, uint32_t n, unsigned 
     }
 }
 
+// K8: raw mode on the device (RawPrefetchBatch, reference slaf/ml/datasets.py:288-296,958-1008): the batch as a
+// CSR matrix whose rows are the cells in shuffled order.  Lengths in output order -> scan -> segment copies.
+__global__ void csr_lengths_kernel(const uint32_t *__restrict__ seg_start, const uint32_t *__restrict__ seg_cell,
+                                   const int32_t *__restrict__ perm, uint32_t n, int cell_signed, uint32_t *__restrict__ len,
+                                   long long *__restrict__ cell_ids) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint32_t c = perm ? (uint32_t)perm[j] : j;
+    len[j] = seg_start[c + 1] - seg_start[c];
+    const uint32_t cid = seg_cell[c];
+    cell_ids[j] = cell_signed ? (long long)(int32_t)cid : (long long)cid;
+}
+
+// one warp per output row copies its segment (genes widened to int32 column indices, values kept in their dtype)
+template <typename GeneT, typename ValT>
+__global__ void __launch_bounds__(256) csr_gather_kernel(const GeneT *__restrict__ gene, const ValT *__restrict__ value,
+                                                         const uint32_t *__restrict__ seg_start, const int32_t *__restrict__ perm,
+                                                         uint32_t n, const long long *__restrict__ crow, int32_t *__restrict__ col,
+                                                         ValT *__restrict__ val) {
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5, lane = threadIdx.x & 31;
+    for (uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < n; j += warps) {
+        const uint32_t c = perm ? (uint32_t)perm[j] : j;
+        const uint32_t s = seg_start[c], m = seg_start[c + 1] - s;
+        const long long o = crow[j];
+        for (uint32_t i = lane; i < m; i += 32) {
+            col[o + i] = (int32_t)__ldg(gene + s + i);
+            val[o + i] = __ldg(value + s + i);
+        }
+    }
+}
+
 // K4: SLAFTokenizer.tokenize on flattened pre-windowed lists: one CTA per list
 struct ListArgs {
     const long long *offsets;

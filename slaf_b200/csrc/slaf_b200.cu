@@ -821,6 +821,54 @@ int slafb_tokenize(slafb_ctx *ctx, const slafb_coo *in, const slafb_params *p, c
     return slafb_collect(ctx, slot, p, out, n_cells, stream);
 }
 
+int slafb_collect_csr(slafb_ctx *ctx, int32_t slot, const slafb_params *p, int64_t *crow, int32_t *col, void *val, int64_t *cell_ids,
+                      int64_t capacity_cells, int64_t capacity_rows, int64_t *n_cells, int64_t *n_rows, void *stream) {
+    if (!ctx || slot < 0 || slot >= kSlots || !p || !n_cells || !n_rows) return fail(ctx, SLAFB_ERR_INVALID, "bad ctx / slot / argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    Slot &s = ctx->slot[slot];
+    if (!s.in_flight) return fail(ctx, SLAFB_ERR_INVALID, "slot %d has no submitted batch", slot);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    bool use_perm = false;
+    int rc = middle(ctx, s, p, n_cells, st, &use_perm);
+    const int64_t C = *n_cells;
+    *n_rows = 0;
+    if (rc == SLAFB_OK && C > 0) {
+        if (C > capacity_cells) rc = fail(ctx, SLAFB_ERR_CAPACITY, "batch has %lld cells, output capacity is %lld", (long long)C, (long long)capacity_cells);
+        else if (s.n_rows > capacity_rows) rc = fail(ctx, SLAFB_ERR_CAPACITY, "batch has %lld rows, output capacity is %lld", (long long)s.n_rows, (long long)capacity_rows);
+        else if (!crow || !col || !val || !cell_ids) rc = fail(ctx, SLAFB_ERR_INVALID, "NULL output");
+    }
+    if (rc == SLAFB_OK && C > 0) {
+        const int32_t *perm = use_perm ? s.perm_dev : nullptr;
+        csr_lengths_kernel<<<(unsigned)((C + 255) / 256), 256, 0, st>>>(s.seg_start, s.seg_cell, perm, (uint32_t)C, s.cell_dtype == SLAFB_I32,
+                                                                        ctx->kept_count, reinterpret_cast<long long *>(cell_ids));
+        scan_counts_kernel<<<1, 1024, 0, st>>>(ctx->kept_count, reinterpret_cast<long long *>(crow), (uint32_t)C, ctx->total_dev);
+        const unsigned grid = (unsigned)ctx->n_sm * 8u;
+        DISPATCH_TYPES(s.gene_dtype, s.value_dtype,
+                       (csr_gather_kernel<GeneT, ValT><<<grid, 256, 0, st>>>(static_cast<const GeneT *>(s.gene), static_cast<const ValT *>(s.value),
+                                                                           s.seg_start, perm, (uint32_t)C, reinterpret_cast<const long long *>(crow),
+                                                                           col, static_cast<ValT *>(val))));
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) rc = fail(ctx, SLAFB_ERR_CUDA, "csr kernels failed: %s", cudaGetErrorString(e));
+        ctx->acc.kernel_launches += 3;
+        if (rc == SLAFB_OK) {
+            cudaMemcpyAsync(ctx->h_total, ctx->total_dev, sizeof(long long), cudaMemcpyDeviceToHost, st);
+            cudaEventRecord(s.ev_done, st);
+            e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) rc = fail(ctx, SLAFB_ERR_CUDA, "csr collect failed: %s", cudaGetErrorString(e));
+            *n_rows = *ctx->h_total;
+            ctx->acc.batches++;
+            ctx->acc.cells += C;
+            ctx->acc.rows += s.n_rows;
+        }
+    } else if (rc == SLAFB_OK) {
+        cudaEventRecord(s.ev_done, st);
+    }
+    settle_prepared(ctx, s);
+    s.prep_state.store(0);
+    s.in_flight = false;
+    return rc;
+}
+
 int slafb_window(slafb_ctx *ctx, const slafb_coo *in, const slafb_params *p, int64_t *cell_ids, int64_t *offsets,
                  int64_t *gene_list, double *expr_list, int64_t capacity_cells, int64_t *n_cells, int64_t *n_items,
                  void *stream) {

@@ -33,6 +33,21 @@ class TokenizedBatch:
 
 
 @dataclass
+class CsrBatch:
+    """Device-resident raw batch: CSR over (cells in shuffled order) x genes."""
+
+    crow_indices: torch.Tensor           # int64 [C + 1]
+    col_indices: torch.Tensor            # int32 [nnz]  gene_integer_id
+    values: torch.Tensor                 # uint16 | float32 [nnz]
+    cell_ids: torch.Tensor               # int64 [C]
+    n_cells: int
+
+    def to_sparse_csr(self, n_genes: int, dtype=torch.float32) -> torch.Tensor:
+        return torch.sparse_csr_tensor(self.crow_indices, self.col_indices.to(torch.int64), self.values.to(dtype),
+                                       size=(self.n_cells, n_genes))
+
+
+@dataclass
 class WindowResult:
     cell_ids: torch.Tensor               # int64 [C]
     offsets: torch.Tensor                # int64 [C+1]
@@ -261,6 +276,31 @@ class HotPathEngine:
         if keep[0].code == N.I32:
             ids = ids.view(np.int32)
         return start[: C + 1].copy(), ids
+
+    def collect_csr(self, slot: int, *, shuffle_seed: int | None = None, perm=None) -> "CsrBatch":
+        """Raw mode on the device: the submitted batch as CSR tensors, rows = cells in shuffled order
+        (reference RawPrefetchBatch, slaf/ml/datasets.py:958-1008)."""
+        try:
+            p, pkeep = self._params("geneformer", 1, 1, 1, 0, None, shuffle_seed, perm)
+        except Exception:
+            self._abandon(slot)
+            raise
+        keep, n_rows = self._pending.pop(slot)
+        n_out = len(pkeep) if pkeep is not None else None
+        cap_cells = max(1, min(self.max_cells, n_rows) if n_out is None else n_out)
+        dev = self.device
+        crow = torch.zeros(cap_cells + 1, dtype=torch.int64, device=dev)
+        col = torch.empty(max(n_rows, 1), dtype=torch.int32, device=dev)
+        vdt = torch.uint16 if keep[2].code == N.U16 else torch.float32
+        val = torch.empty(max(n_rows, 1), dtype=vdt, device=dev)
+        cids = torch.empty(cap_cells, dtype=torch.int64, device=dev)
+        n, r = ctypes.c_int64(0), ctypes.c_int64(0)
+        with torch.cuda.device(self.device):
+            N.check(self._L.slafb_collect_csr(self._ctx, slot, ctypes.byref(p), crow.data_ptr(), col.data_ptr(), val.data_ptr(),
+                                              cids.data_ptr(), cap_cells, max(n_rows, 1), ctypes.byref(n), ctypes.byref(r), self._stream()), self._ctx)
+        del keep, pkeep
+        C, R = int(n.value), int(r.value)
+        return CsrBatch(crow[: C + 1], col[:R], val[:R], cids[:C], C)
 
     def tokenize(self, cell: Any, gene: Any, value: Any, **kw) -> TokenizedBatch:
         """shuffle -> window -> tokenize -> cell ids for one batch of complete cells

@@ -241,8 +241,9 @@ class PrefetchBatchProcessor:
                  n_epochs: int = 1, raw_mode: bool = False, verbose: bool = True, log_metrics: bool = False,
                  batch_size: int = 32, by_fragment: bool = True, use_mixture_of_scanners: bool = True, n_scanners: int = 16,
                  prefetch_batch_size: int = 4194304, parallelize_fragment_reads: bool = False, device=None,
-                 copy_threads: int = 4):
+                 copy_threads: int = 4, device_raw: bool = False):
         self.slaf_array = slaf_array
+        self.device_raw = device_raw
         self.shuffle = shuffle
         self.tokenizer = tokenizer
         self.seed = seed
@@ -498,7 +499,9 @@ class PrefetchBatchProcessor:
                 self.batch_id += 1
                 continue
             seed = self.seed + self.batch_id + self.current_epoch * 10000               # datasets.py:1016
-            if self.raw_mode or not self._fused_ok():
+            if self.raw_mode and self.device_raw and type(self.shuffle) in (RandomShuffle, StratifiedShuffle):
+                out = self._load_raw_device(pieces, seed, start_time)
+            elif self.raw_mode or not self._fused_ok():
                 out = self._load_on_host_frames(pieces, seed, start_time)
             else:
                 if self.tokenizer is None:
@@ -523,8 +526,9 @@ class PrefetchBatchProcessor:
         rows = self._staging.assemble(pieces)
         return eng.submit(rows.cell, rows.gene, rows.value), [rows]
 
-    def _load_fused(self, pieces: list[CooChunk], seed: int, start_time: float) -> TokenizedPrefetchBatch | None:
-        t0 = time.time()
+    def _front(self, pieces: list[CooChunk]):
+        """submit -> segment table -> (splice safety net) -> completeness -> partial stash.
+        Returns (engine, slot, indices of the complete cells in first-appearance order, their row counts)."""
         n_rows = sum(len(p) for p in pieces)
         eng = self._engine_for(n_rows)
         slot, pieces = self._submit(eng, pieces)
@@ -547,6 +551,36 @@ class PrefetchBatchProcessor:
         complete = self._complete_mask(seg_cell, seg_len)
         self._stash_partials(pieces, seg_start, seg_cell, complete)
         sel = np.flatnonzero(complete).astype(np.int32)
+        return eng, slot, sel, seg_len
+
+    def _load_raw_device(self, pieces: list[CooChunk], seed: int, start_time: float) -> RawPrefetchBatch | None:
+        """Raw mode on the device: the complete cells of the batch as CSR tensors in shuffled
+        order, cut into ``batch_size``-cell chunks (views; the row pointers are rebased per chunk)."""
+        t0 = time.time()
+        eng, slot, sel, seg_len = self._front(pieces)
+        if sel.size == 0:
+            eng.release(slot)
+            return None
+        order = sel[shuffle_perm(seed, sel.size)]
+        csr = eng.collect_csr(slot, perm=order)
+        ends = np.concatenate(([0], np.cumsum(seg_len[order])))            # row offsets per output cell, known on the host
+        chunks = []
+        for lo in range(0, csr.n_cells, self.batch_size):
+            hi = min(lo + self.batch_size, csr.n_cells)
+            a, b = int(ends[lo]), int(ends[hi])
+            chunks.append({"crow_indices": csr.crow_indices[lo:hi + 1] - a, "col_indices": csr.col_indices[a:b], "values": csr.values[a:b],
+                           "cell_ids": csr.cell_ids[lo:hi]})
+        process_time = time.time() - t0
+        self._record_timing("shuffle", process_time)
+        self._record_timing("total", time.time() - start_time)
+        self._record_timing("cells_processed", 0, csr.n_cells)
+        self.total_prefetch_cells += csr.n_cells
+        return RawPrefetchBatch(batch_id=self.batch_id, batch_dfs=chunks, cell_integer_ids=csr.cell_ids.cpu().tolist(),
+                                process_time=process_time, memory_mb=0.0)
+
+    def _load_fused(self, pieces: list[CooChunk], seed: int, start_time: float) -> TokenizedPrefetchBatch | None:
+        t0 = time.time()
+        eng, slot, sel, _seg_len = self._front(pieces)
         shuffle_time = time.time() - t0
         if sel.size == 0:
             eng.release(slot)
@@ -755,7 +789,7 @@ class SLAFIterableDataset(IterableDataset):
                  use_binned_expressions: bool = False, n_epochs: int = 1, raw_mode: bool = False, verbose: bool = True,
                  batches_per_chunk: int = 1, by_fragment: bool = True, use_mixture_of_scanners: bool = True, n_scanners: int = 16,
                  prefetch_batch_size: int = 4194304, parallelize_fragment_reads: bool = False,
-                 prefetcher_ready_timeout: float = 10.0, device=None, output_device=None):
+                 prefetcher_ready_timeout: float = 10.0, device=None, output_device=None, device_raw: bool = False):
         super().__init__()
         self.slaf_array = slaf_array
         self.tokenizer = tokenizer
@@ -777,7 +811,7 @@ class SLAFIterableDataset(IterableDataset):
             use_binned_expressions=use_binned_expressions, n_epochs=n_epochs, raw_mode=raw_mode, verbose=verbose,
             log_metrics=False, batch_size=batch_size, by_fragment=by_fragment, use_mixture_of_scanners=use_mixture_of_scanners,
             n_scanners=n_scanners, prefetch_batch_size=prefetch_batch_size, parallelize_fragment_reads=parallelize_fragment_reads,
-            device=device)
+            device=device, device_raw=device_raw)
         self.prefetcher = AsyncPrefetcher(self.batch_processor, max_queue_size=max_queue_size)
         self.prefetcher.start()
         self.device = self.output_device if self.output_device is not None else torch.device("cuda")
@@ -789,6 +823,12 @@ class SLAFIterableDataset(IterableDataset):
                 break
             if isinstance(data, RawPrefetchBatch):
                 for df in data.batch_dfs:
+                    if isinstance(df, dict) and "crow_indices" in df:          # device raw mode: CSR tensors of the batch's cells
+                        out = {"x": df, "cell_ids": df["cell_ids"]}
+                        if self.n_epochs > 1:
+                            out["epoch"] = self.prefetcher.current_epoch
+                        yield out
+                        continue
                     ids = frames.column(df, "cell_integer_id")
                     out = {"x": df, "cell_ids": [int(x) for x in ids[np.sort(np.unique(ids, return_index=True)[1])]]}
                     if self.n_epochs > 1:

@@ -189,3 +189,52 @@ def test_loader_validation_errors(data):
         proc.load_prefetch_batch()
     with pytest.raises(ValueError, match="Invalid epoch 5"):
         proc.reset_for_epoch(5)
+
+
+def test_collect_csr_raw_mode_on_device(engine, data):
+    """slafb_collect_csr: the batch as CSR in shuffled cell order (reference RawPrefetchBatch semantics: shuffle only)."""
+    import random
+
+    b = data
+    slot = engine.submit(b.cell, b.gene, b.value)
+    csr = engine.collect_csr(slot, shuffle_seed=91)
+    random.seed(91)
+    order = list(range(b.n_cells))
+    random.shuffle(order)
+    assert csr.cell_ids.cpu().tolist() == order and csr.n_cells == b.n_cells
+    crow = csr.crow_indices.cpu().numpy()
+    assert crow[0] == 0 and crow[-1] == b.n_rows and csr.col_indices.dtype == torch.int32 and csr.values.dtype == torch.uint16
+    col, val = csr.col_indices.cpu().numpy(), csr.values.cpu().numpy()
+    for j in (0, 1, 57, b.n_cells - 1):
+        c = order[j]
+        lo, hi = b.cell_start[c], b.cell_start[c + 1]
+        assert np.array_equal(col[crow[j]:crow[j + 1]], b.gene[lo:hi].astype(np.int32))
+        assert np.array_equal(val[crow[j]:crow[j + 1]], b.value[lo:hi])
+    dense = csr.to_sparse_csr(N_GENES).to_dense()
+    assert dense.shape == (b.n_cells, N_GENES) and float(dense.sum()) == float(b.value.sum())
+    # a selection emits only those cells
+    slot = engine.submit(b.cell, b.gene, b.value)
+    sub = engine.collect_csr(slot, perm=np.array([5, 0, 7], np.int32))
+    assert sub.cell_ids.cpu().tolist() == [5, 0, 7] and int(sub.crow_indices[-1]) == sum(int(b.cell_start[c + 1] - b.cell_start[c]) for c in (5, 0, 7))
+
+
+@pytest.mark.parametrize("mode", ["mos", "fragment"])
+def test_raw_mode_on_device_loader(data, mode):
+    np.random.seed(2)
+    loader = SLAFDataLoader(_array(data), raw_mode=True, device_raw=True, batch_size=24, use_mixture_of_scanners=(mode == "mos"),
+                            by_fragment=True, n_scanners=3, prefetch_batch_size=1000, verbose=False)
+    seen = {}
+    for batch in loader:
+        x = batch["x"]
+        crow = x["crow_indices"].cpu().numpy()
+        ids = batch["cell_ids"].cpu().tolist()
+        assert x["col_indices"].is_cuda and crow[0] == 0 and len(crow) == len(ids) + 1 and len(ids) <= 24
+        assert crow[-1] == x["col_indices"].numel() == x["values"].numel()
+        col, val = x["col_indices"].cpu().numpy(), x["values"].cpu().numpy()
+        for r, c in enumerate(ids):
+            assert c not in seen
+            seen[c] = (np.sort(col[crow[r]:crow[r + 1]]), int(val[crow[r]:crow[r + 1]].sum()))
+    assert sorted(seen) == list(range(N_CELLS))
+    for c in (0, 33, N_CELLS - 1):
+        lo, hi = data.cell_start[c], data.cell_start[c + 1]
+        assert np.array_equal(seen[c][0], np.sort(data.gene[lo:hi]).astype(np.int32)) and seen[c][1] == int(data.value[lo:hi].sum())
