@@ -16,7 +16,7 @@ from ctypes import POINTER, Structure, byref, c_char_p, c_double, c_int, c_int32
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "_lib", "libslaf_b200.so")
+LIB_PATH = os.environ.get("SLAFB_LIB") or os.path.join(_HERE, "_lib", "libslaf_b200.so")   # SLAFB_LIB: A/B builds
 SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("slaf_b200.cu", "kernels.cuh", "py_shuffle.h")]
 HEADER = os.path.join(_ROOT, "include", "slaf_b200.h")
 
@@ -93,6 +93,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     ]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
+    for extra in os.environ.get("SLAFB_NVCC_FLAGS", "").split():
+        cmd.insert(1, extra)
     env = dict(os.environ)
     env.pop("CC", None)   # the image exports a CC without libgomp specs; nvcc should pick the system g++
     env.pop("CXX", None)

@@ -35,7 +35,10 @@ constexpr int kTokThreads = 256;
 constexpr int kGroup = 8;                           // rows per thread per chunk (one 128-bit load of u16)
 constexpr int kChunkRows = kTokThreads * kGroup;    // 2048 rows staged per iteration
 constexpr int kCsrListCap = 1024;                   // segment heads a CTA keeps in shared memory (else: replay)
-constexpr int kFastThreads = 256;                   // K2: threads per persistent CTA
+#ifndef SLAFB_FAST_THREADS
+#define SLAFB_FAST_THREADS 256
+#endif
+constexpr int kFastThreads = SLAFB_FAST_THREADS;    // K2: threads per persistent CTA (build-time tuning knob)
 constexpr int kFastWarps = kFastThreads / 32;
 constexpr int kBitmapWords = 65536 / 32;
 constexpr int kSortSmemKeys = 12288;                // general path: float keys sorted in shared memory up to here

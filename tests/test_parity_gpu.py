@@ -253,3 +253,62 @@ def test_prepared_shuffle_matches_inline_shuffle(engine):
     compare(engine.collect(slots[1], shuffle_seed=78, **kw), want2, "geneformer")       # prepared for 77, collected with 78
     s = engine.submit(b.cell, b.gene, b.value, shuffle_seed=5)
     compare(engine.collect(s, **kw), c_oracle.tokenize(b.cell, b.gene, b.value, "geneformer", 256), "geneformer")   # prepared, then no shuffle
+
+
+@pytest.mark.parametrize("cfg", ["cfg2_scgpt_binned", "cfg3_geneformer"])
+def test_full_size_prefetch_batch_checksums(cfg):
+    """BASELINE.json's bench shape at full prefetch-batch size (32,768 cells, ~70 M rows): properties of EVERY output
+    row against numpy reductions of the input (a checksum per cell, no per-cell Python), plus the full oracle on a
+    random sample of cells.  Count data has far fewer distinct values per cell than max_items, so the reference's
+    dense-rank filter keeps every row and each cell's tokens are its first min(n, limit) genes in row order."""
+    from slaf_b200.engine import HotPathEngine
+
+    C = 32768
+    if cfg == "cfg2_scgpt_binned":
+        b = synthetic.make_batch(C, 60000, 2000, seed=2)
+        kw = dict(mode="scgpt_binned", max_genes=1200, n_bins=51, vocab_size=65000)
+        L, limit = 1202, 1200
+    else:
+        b = synthetic.make_batch(C, 62000, 2000, seed=3)
+        kw = dict(mode="geneformer", max_genes=2048)
+        L, limit = 2048, 2047
+    eng = HotPathEngine(0, max_rows=b.n_rows + 1024, max_cells=C + 1024)
+    got = eng.tokenize(to_dev(b.cell), to_dev(b.gene), to_dev(b.value), shuffle_seed=42, **kw)
+    ids, mask, cids = got.input_ids, got.attention_mask, got.cell_ids
+    assert tuple(ids.shape) == (C, L) and got.n_cells == C
+    order = np.asarray(py_perm(42, C))
+    assert_same(cids.cpu().numpy(), order, "cell order = CPython shuffle of first-appearance order")
+    nnz = np.diff(b.cell_start)
+    n_emit = np.minimum(nnz, limit)
+    # per-cell checksum of the gene tokens: sum over the first n_emit rows of (gene + 4), via one cumulative sum
+    csum = np.concatenate(([0], np.cumsum(b.gene.astype(np.int64) + 4)))
+    want_sum = csum[b.cell_start[:-1] + n_emit] - csum[b.cell_start[:-1]] + 1 + np.where(n_emit + 1 < L, 2, 0)
+    assert_same(ids.sum(1).cpu().numpy(), want_sum[order], "row checksums")
+    assert_same(mask.sum(1).cpu().numpy(), np.minimum(n_emit + 2, L)[order], "attention lengths")
+    assert bool(((ids != 0) == mask).all()) and bool((ids[:, 0] == 1).all())
+    assert bool(((ids == 2).sum(1) == torch.from_numpy((n_emit + 1 < L)[order]).cuda()).all())          # SEP present iff it fits
+    if got.values is not None:
+        vals = got.values
+        assert bool((vals[:, 0] == 0).all()) and bool((vals[~mask] == 0).all())
+        assert bool(((vals == 0) | (vals == 65000 + 50)).all())
+        # bin >= 1  <=>  floor(log1p(v) * 51 / log1p(vmax)) >= 1, evaluated with numpy on every kept row
+        vmax = np.maximum.reduceat(b.value, b.cell_start[:-1])
+        lv = np.log1p(b.value.astype(np.float64))
+        top = (np.floor(lv * 51 / np.repeat(np.log1p(vmax.astype(np.float64)), nnz)) >= 1)
+        tsum = np.concatenate(([0], np.cumsum(top.astype(np.int64))))
+        want_top = tsum[b.cell_start[:-1] + n_emit] - tsum[b.cell_start[:-1]]
+        assert_same((vals != 0).sum(1).cpu().numpy(), want_top[order], "top-bin counts")
+    # the full oracle on a random sample of cells
+    rng = np.random.default_rng(0)
+    pick = np.sort(rng.choice(C, 384, replace=False))
+    rows = np.concatenate([np.arange(b.cell_start[c], b.cell_start[c + 1]) for c in pick])
+    okw = {k: v for k, v in kw.items() if k != "mode"}
+    want = c_oracle.tokenize(b.cell[rows], b.gene[rows], b.value[rows], kw["mode"], **okw)
+    pos = np.empty(C, np.int64)
+    pos[order] = np.arange(C)
+    sel = torch.from_numpy(pos[pick]).cuda()
+    assert_same(ids[sel].cpu().numpy(), want[0], "sampled ids")
+    assert_same(mask[sel].cpu().numpy(), want[1], "sampled mask")
+    if got.values is not None:
+        assert_same(got.values[sel].cpu().numpy(), want[2], "sampled values")
+    eng.close()
