@@ -42,6 +42,9 @@ constexpr int kFastThreads = SLAFB_FAST_THREADS;    // K2: threads per persisten
 constexpr int kFastWarps = kFastThreads / 32;
 constexpr int kBitmapWords = 65536 / 32;
 constexpr int kSortSmemKeys = 12288;                // general path: float keys sorted in shared memory up to here
+constexpr int kHashBits = 11;                       // K2, float32 values: distinct-value set of 2048 slots in shared memory,
+constexpr int kHashSlots = 1 << kHashBits;          // trusted up to kHashMaxDistinct entries (every thread may add one more
+constexpr int kHashMaxDistinct = 1536;              // before it sees the limit: 1536 + 256 < 2048, so probing always ends)
 
 enum : int { MODE_GF = 0, MODE_GF_PCT = 1, MODE_SCGPT_RAW = 2, MODE_SCGPT_BINNED = 3 };
 
@@ -710,7 +713,6 @@ __device__ bool process_cell(const TokArgs &a, const WindowSink &wsnk, uint32_t 
     float m_f32 = 0.0f;
     if (BINNED || !keep_all) {
         uint32_t lo = 0xffffffffu, hi = 0u;
-        float lvmax = -INFINITY;
         for (uint32_t g0 = s & ~7u; g0 < e; g0 += kChunkRows) {
             const uint32_t r0 = g0 + tid * kGroup;
             if (r0 < e) {
@@ -723,18 +725,14 @@ __device__ bool process_cell(const TokArgs &a, const WindowSink &wsnk, uint32_t 
                         const uint32_t key = key_of(v[i]);
                         lo = min(lo, key);
                         hi = max(hi, key);
-                        if constexpr (BINNED && !U16) lvmax = fmaxf(lvmax, log1pf_window((float)v[i]));
                     }
                 }
             }
         }
         block_minmax(lo, hi, sm.ws);
         kmax = hi;
-        if constexpr (BINNED && !U16) {
-            uint32_t lk = key_of(lvmax), dummy = 0xffffffffu;
-            block_minmax(dummy, lk, sm.ws);
-            m_f32 = float_of_key(lk);
-        }
+        // log1p is monotone: max(log1pf(x)) over the cell = log1pf(max x)
+        if constexpr (BINNED && !U16) m_f32 = log1pf_window(float_of_key(hi));
         if (!keep_all) {
             if (!PCT && U16 && (hi - lo + 1u <= k)) {
                 keep_all = true;  // at most k distinct values can exist in [lo, hi]
@@ -911,6 +909,8 @@ __device__ __forceinline__ void fast_issue(const FastArgs &fa, uint32_t j, uint3
     }
 }
 
+static_assert(kHashMaxDistinct + kFastThreads < kHashSlots, "the distinct-value set must never fill up");
+
 template <typename GeneT, typename ValT, int MODE>
 __global__ void __launch_bounds__(kFastThreads, 2048 / kFastThreads) tokenize_cells_kernel(const FastArgs fa) {
     constexpr bool SCGPT = (MODE == MODE_SCGPT_RAW || MODE == MODE_SCGPT_BINNED);
@@ -1007,7 +1007,6 @@ __global__ void __launch_bounds__(kFastThreads, 2048 / kFastThreads) tokenize_ce
         float m_f32 = 0.0f;
         if (BINNED || !keep_all) {
             uint32_t lo = 0xffffffffu, hi = 0u;
-            float lvmax = -INFINITY;
             const uint32_t ngroups = (sh + d.n_v + 7u) >> 3;
             for (uint32_t gi = tid; gi < ngroups; gi += kFastThreads) {
                 const uint32_t r0 = a0 + gi * 8u;
@@ -1039,7 +1038,6 @@ __global__ void __launch_bounds__(kFastThreads, 2048 / kFastThreads) tokenize_ce
                             const uint32_t key = key_of(x);
                             lo = min(lo, key);
                             hi = max(hi, key);
-                            if constexpr (BINNED) lvmax = fmaxf(lvmax, log1pf_window(x));
                         }
                     }
                 }
@@ -1050,21 +1048,18 @@ __global__ void __launch_bounds__(kFastThreads, 2048 / kFastThreads) tokenize_ce
                 const uint32_t key = key_of(x);
                 lo = min(lo, key);
                 hi = max(hi, key);
-                if constexpr (BINNED && !U16) lvmax = fmaxf(lvmax, log1pf_window((float)x));
             }
             lo = __reduce_min_sync(0xffffffffu, lo);
             hi = __reduce_max_sync(0xffffffffu, hi);
-            uint32_t lk = 0;
-            if constexpr (BINNED && !U16) lk = __reduce_max_sync(0xffffffffu, key_of(lvmax));
-            if (lane == 0) { s_ws[warp] = lo; s_ws[kFastWarps + warp] = hi; s_ws[2 * kFastWarps + warp] = lk; }
+            if (lane == 0) { s_ws[warp] = lo; s_ws[kFastWarps + warp] = hi; }
             __syncthreads();
 #pragma unroll
             for (int w = 0; w < kFastWarps; w++) {
                 lo = min(lo, s_ws[w]);
                 hi = max(hi, s_ws[kFastWarps + w]);
-                lk = max(lk, s_ws[2 * kFastWarps + w]);
             }
-            if constexpr (BINNED && !U16) m_f32 = float_of_key(lk);   // max(log1pf) over the cell
+            // log1p is monotone, so max(log1pf(x)) over the cell is log1pf of the largest value: one evaluation per cell
+            if constexpr (BINNED && !U16) m_f32 = log1pf_window(float_of_key(hi));
             kmax = hi;
             if (!keep_all) {
                 if (U16 && (hi - lo + 1u <= k)) {
@@ -1085,6 +1080,33 @@ __global__ void __launch_bounds__(kFastThreads, 2048 / kFastThreads) tokenize_ce
 #pragma unroll
                     for (int w2 = 0; w2 < kFastWarps; w2++) above += s_ws[w2];
                     if (above <= M) keep_all = true; else defer = true;
+                } else if (!U16) {
+                    // float32 values: exact distinct count with an open-addressing set in shared memory.  Normalised
+                    // expression values take as many distinct values per cell as the counts they came from (tens),
+                    // so "at most k distinct" holds almost always and the cell stays on this path.
+                    uint32_t *tab = reinterpret_cast<uint32_t *>(smem_raw + 2u * stage_bytes);
+                    const uint32_t cap = min(k, (uint32_t)kHashMaxDistinct);
+                    __syncthreads();                                // s_ws is read above by every thread
+                    for (uint32_t i = tid; i < (uint32_t)kHashSlots; i += kFastThreads) tab[i] = 0xffffffffu;
+                    if (tid == 0) s_ws[0] = 0u;
+                    __syncthreads();
+                    volatile uint32_t *distinct = s_ws;
+                    for (uint32_t r = s + tid; r < e && *distinct <= cap; r += kFastThreads) {
+                        const float x = (r < s + d.n_v) ? (float)sv[r - a0] : (float)__ldg(value_g + r);
+                        const uint32_t key = key_of(x);
+                        uint32_t h = (key * 2654435761u) >> (32 - kHashBits);
+                        for (;;) {
+                            const uint32_t old = atomicCAS(tab + h, 0xffffffffu, key);
+                            if (old == 0xffffffffu) { atomicAdd(s_ws, 1u); break; }
+                            if (old == key) break;
+                            h = (h + 1u) & (uint32_t)(kHashSlots - 1);
+                            if (*distinct > cap) break;             // the set will not decide any more: stop probing
+                        }
+                    }
+                    __syncthreads();
+                    const uint32_t D = s_ws[0];
+                    __syncthreads();
+                    if (D <= cap) keep_all = true; else defer = true;   // D <= cap <= k distinct values: every row has rank <= k
                 } else {
                     defer = true;                                   // exact k-th distinct value: general kernel
                 }

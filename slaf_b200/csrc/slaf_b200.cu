@@ -206,7 +206,7 @@ int launch_fast(slafb_ctx *ctx, const TokArgs &a, cudaStream_t st, bool *launche
     fa.vcap = fa.gcap > 4104u ? fa.gcap : 4104u;
     fa.vstar_table = ctx->vstar_table;
     fa.ticket = a.work_counters + 2;   // slot counters[4], zeroed by K1 together with the work-list counters
-    const size_t smem = 2 * ((size_t)fa.gcap * sizeof(GeneT) + (size_t)fa.vcap * sizeof(ValT));
+    const size_t smem = 2 * ((size_t)fa.gcap * sizeof(GeneT) + (size_t)fa.vcap * sizeof(ValT)) + (sizeof(ValT) == 4 ? (size_t)kHashSlots * 4 : 0);
     if (smem > 200 * 1024) return SLAFB_OK;   // very wide rows: general kernel only
     auto kern = tokenize_cells_kernel<GeneT, ValT, MODE>;
     static bool attr_set[64] = {false};

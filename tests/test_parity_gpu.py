@@ -312,3 +312,25 @@ def test_full_size_prefetch_batch_checksums(cfg):
     if got.values is not None:
         assert_same(got.values[sel].cpu().numpy(), want[2], "sampled values")
     eng.close()
+
+
+@pytest.mark.parametrize("mode", ["geneformer", "scgpt_raw", "scgpt_binned"])
+def test_float32_distinct_count_boundaries(engine, mode):
+    """float32 storage: the fast kernel decides "at most k distinct values" with an exact hash set (trusted up to
+    1536 entries); cells just below / at / above k and around the set's limit must all match the oracle."""
+    rng = np.random.default_rng(9)
+    cases = []
+    for k, distincts in ((100, (1, 99, 100, 101, 150)), (1536, (1535, 1536, 1537)), (2048, (1530, 1536, 1537, 2047, 2048, 2049, 2600))):
+        for d in distincts:
+            n = max(d, k) + 37
+            vals = np.concatenate([np.arange(1, d + 1), rng.integers(1, d + 1, n - d)]).astype(np.float64)
+            rng.shuffle(vals)
+            cases.append((k, (vals * 0.37 + 0.01).astype(np.float32)))
+    for k in (100, 1536, 2048):
+        cols = [(i, v) for i, (kk, v) in enumerate(cases) if kk == k]
+        cell = np.concatenate([np.full(len(v), 1000 + i, np.uint32) for i, v in cols])
+        gene = np.concatenate([np.sort(rng.choice(60000, len(v), replace=False)) for _, v in cols]).astype(np.uint16)
+        value = np.concatenate([v for _, v in cols])
+        want = c_oracle.tokenize(cell, gene, value, mode, k, n_bins=51, vocab_size=65000)
+        got = engine.tokenize(to_dev(cell), to_dev(gene), to_dev(value), mode=mode, max_genes=k, n_bins=51, vocab_size=65000)
+        compare(got, want, mode)
