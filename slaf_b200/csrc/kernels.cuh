@@ -867,6 +867,28 @@ __device__ __noinline__ uint32_t count_above_u16(const uint16_t *sv, const uint1
     return above;
 }
 
+// smallest key c in [klo, khi] with pred(c) true, for a monotone pred with pred(khi) true; one full warp, 32-ary search
+// (each round every lane tests one candidate: seven rounds cover 32 bits)
+template <typename Pred>
+__device__ __forceinline__ uint32_t warp_lower_bound(uint32_t klo, uint32_t khi, Pred pred) {
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t L = klo, H = khi;
+    while (L < H) {
+        const uint32_t w = H - L;
+        const uint32_t c = L + (uint32_t)(((unsigned long long)w * (lane + 1u)) / 33ull);      // in [L, H)
+        const uint32_t m = __ballot_sync(0xffffffffu, pred(c));
+        if (m) {
+            const int f = __ffs(m) - 1;
+            H = __shfl_sync(0xffffffffu, c, f);
+            const uint32_t below = __shfl_sync(0xffffffffu, c, f > 0 ? f - 1 : 0);
+            if (f > 0) L = below + 1u;
+        } else {
+            L = __shfl_sync(0xffffffffu, c, 31) + 1u;
+        }
+    }
+    return H;
+}
+
 struct FastArgs {
     TokArgs t;
     uint32_t gcap;                // gene stage capacity (rows, multiple of 8)
@@ -920,6 +942,7 @@ __global__ void __launch_bounds__(kFastThreads, 2048 / kFastThreads) tokenize_ce
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ CellDesc s_desc[2];
     __shared__ uint32_t s_ws[3 * kFastWarps];
+    __shared__ uint32_t s_xstar;      // float32 binned window: key of the smallest value whose bin is >= 1
     const TokArgs &a = fa.t;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t gbytes = fa.gcap * (uint32_t)sizeof(GeneT), vbytes = fa.vcap * (uint32_t)sizeof(ValT);
@@ -1095,10 +1118,14 @@ __global__ void __launch_bounds__(kFastThreads, 2048 / kFastThreads) tokenize_ce
                         const float x = (r < s + d.n_v) ? (float)sv[r - a0] : (float)__ldg(value_g + r);
                         const uint32_t key = key_of(x);
                         uint32_t h = (key * 2654435761u) >> (32 - kHashBits);
+                        volatile uint32_t *vt = tab;
                         for (;;) {
-                            const uint32_t old = atomicCAS(tab + h, 0xffffffffu, key);
-                            if (old == 0xffffffffu) { atomicAdd(s_ws, 1u); break; }
-                            if (old == key) break;
+                            uint32_t cur = vt[h];                   // plain read first: the common case is "already present"
+                            if (cur == 0xffffffffu) {
+                                cur = atomicCAS(tab + h, 0xffffffffu, key);
+                                if (cur == 0xffffffffu) { atomicAdd(s_ws, 1u); break; }
+                            }
+                            if (cur == key) break;
                             h = (h + 1u) & (uint32_t)(kHashSlots - 1);
                             if (*distinct > cap) break;             // the set will not decide any more: stop probing
                         }
@@ -1123,6 +1150,23 @@ __global__ void __launch_bounds__(kFastThreads, 2048 / kFastThreads) tokenize_ce
             uint32_t vstar = 0xffffffffu;
             const long long top = a.vocab + (long long)(a.n_bins - 1);
             if constexpr (BINNED && U16) vstar = __ldg(fa.vstar_table + kmax);
+            if constexpr (BINNED && !U16) {
+                // The binned window followed by the tokenizer's float branch gives  token = (bin >= 1) ? top : PAD, and
+                // bin(x) = floor(log1pf(x) * n / m) is monotone in x: instead of one log1p per row, warp 0 finds the
+                // smallest float whose bin is >= 1 (32-ary search over the ordered key space, ~7 rounds) while the
+                // other warps already emit the gene stream; rows then need one compare each.
+                if (warp == 0) {
+                    const float wb = (float)a.w_bins;
+                    auto pred = [&](uint32_t c) -> bool {
+                        const float lv = log1pf_window(float_of_key(c));
+                        return lv > 0.0f && __fdiv_rn(__fmul_rn(lv, wb), m_f32) >= 1.0f;
+                    };
+                    const uint32_t kzero = key_of(0.0f);
+                    uint32_t xs = 0xffffffffu;                       // no value reaches bin 1
+                    if (a.w_bins >= 2 && kmax >= kzero && pred(kmax)) xs = warp_lower_bound(kzero, kmax, pred);
+                    if (lane == 0) s_xstar = xs;
+                }
+            }
             (void)m_f64; (void)top; (void)vstar;
             auto id_tok = [&](long long t) -> long long {
                 if (t == 0) return 1ll;                                        // CLS
@@ -1136,6 +1180,7 @@ __global__ void __launch_bounds__(kFastThreads, 2048 / kFastThreads) tokenize_ce
                 if (t < 1 || t > (long long)n_emit) return 0ll;
                 const ValT x = sv[sh + (uint32_t)t - 1u];
                 if constexpr (BINNED && U16) return ((uint32_t)x >= vstar) ? top : 0ll;
+                else if constexpr (BINNED) return (key_of(x) >= vstar) ? top : 0ll;      // vstar = s_xstar, loaded after the barrier below
                 else return value_token<ValT, MODE>(raw_bits(x), a, m_f64, m_f32);
             };
             // Token t of the row lives at flat index A + t.  Pairs are 16-byte aligned in the flat
@@ -1155,6 +1200,10 @@ __global__ void __launch_bounds__(kFastThreads, 2048 / kFastThreads) tokenize_ce
                 else { x0 = (long long)(int32_t)sg[gi] + 4ll; x1 = (long long)(int32_t)sg[gi + 1] + 4ll; }
                 *reinterpret_cast<longlong2 *>(ids_al + 2u * p) = make_longlong2(x0, x1);
             }
+            if constexpr (BINNED && !U16) {
+                __syncthreads();                                 // warp 0 has published the bin threshold
+                vstar = s_xstar;
+            }
             if constexpr (SCGPT) {
                 // the value stream second: the bin-threshold load above has landed by now
 #pragma unroll 2
@@ -1164,6 +1213,9 @@ __global__ void __launch_bounds__(kFastThreads, 2048 / kFastThreads) tokenize_ce
                     if constexpr (BINNED && U16) {
                         y0 = ((uint32_t)sv[gi] >= vstar) ? top : 0ll;
                         y1 = ((uint32_t)sv[gi + 1] >= vstar) ? top : 0ll;
+                    } else if constexpr (BINNED) {
+                        y0 = (key_of(sv[gi]) >= vstar) ? top : 0ll;
+                        y1 = (key_of(sv[gi + 1]) >= vstar) ? top : 0ll;
                     } else {
                         y0 = value_token<ValT, MODE>(raw_bits(sv[gi]), a, m_f64, m_f32);
                         y1 = value_token<ValT, MODE>(raw_bits(sv[gi + 1]), a, m_f64, m_f32);
