@@ -1028,7 +1028,56 @@ __global__ void __launch_bounds__(kFastThreads, 2048 / kFastThreads) tokenize_ce
         bool defer = false;
         uint32_t kmax = 0;
         float m_f32 = 0.0f;
-        if (BINNED || !keep_all) {
+        if constexpr (!U16) {
+            // float32 values: ONE pass over the cell's values gives the maximum (for the bins) and, when the cell has more
+            // rows than max_items, the exact number of distinct values through an open-addressing set in shared memory.
+            // Normalised expression values take as many distinct values per cell as the counts they came from (tens), so
+            // "at most k distinct" holds almost always and the cell stays on this path.
+            if (BINNED || !keep_all) {
+                const bool do_hash = !keep_all;
+                uint32_t *tab = reinterpret_cast<uint32_t *>(smem_raw + 2u * stage_bytes);
+                const uint32_t cap = min(k, (uint32_t)kHashMaxDistinct);
+                if (do_hash) {
+                    for (uint32_t i = tid; i < (uint32_t)kHashSlots; i += kFastThreads) tab[i] = 0xffffffffu;
+                    if (tid == 0) s_ws[0] = 0u;
+                    __syncthreads();
+                }
+                volatile uint32_t *distinct = s_ws;
+                volatile uint32_t *vt = tab;
+                float xmax = -INFINITY;
+                for (uint32_t r = s + tid; r < e; r += kFastThreads) {
+                    const float x = (r < s + d.n_v) ? (float)sv[r - a0] : (float)__ldg(value_g + r);
+                    xmax = fmaxf(xmax, x);
+                    if (do_hash && *distinct <= cap) {
+                        const uint32_t key = key_of(x);
+                        uint32_t h = (key * 2654435761u) >> (32 - kHashBits);
+                        for (;;) {
+                            uint32_t cur = vt[h];                   // plain read first: the common case is "already present"
+                            if (cur == 0xffffffffu) {
+                                cur = atomicCAS(tab + h, 0xffffffffu, key);
+                                if (cur == 0xffffffffu) { atomicAdd(s_ws, 1u); break; }
+                            }
+                            if (cur == key) break;
+                            h = (h + 1u) & (uint32_t)(kHashSlots - 1);
+                            if (*distinct > cap) break;             // the set will not decide any more: stop probing
+                        }
+                    }
+                }
+                uint32_t hi = __reduce_max_sync(0xffffffffu, key_of(xmax));
+                if (lane == 0) s_ws[kFastWarps + warp] = hi;
+                __syncthreads();
+#pragma unroll
+                for (int w = 0; w < kFastWarps; w++) hi = max(hi, s_ws[kFastWarps + w]);
+                kmax = hi;
+                if constexpr (BINNED) m_f32 = log1pf_window(float_of_key(hi));   // log1p is monotone: max(log1pf(x)) = log1pf(max x)
+                if (do_hash) {
+                    const uint32_t D = s_ws[0];
+                    if (D <= cap) keep_all = true; else defer = true;            // D <= cap <= k distinct values: every row has rank <= k
+                }
+                __syncthreads();                                                  // s_ws is reused by the next cell
+            }
+        }
+        if (U16 && (BINNED || !keep_all)) {
             uint32_t lo = 0xffffffffu, hi = 0u;
             const uint32_t ngroups = (sh + d.n_v + 7u) >> 3;
             for (uint32_t gi = tid; gi < ngroups; gi += kFastThreads) {
