@@ -1082,7 +1082,7 @@ __global__ void __launch_bounds__(kFastThreads, 2048 / kFastThreads) tokenize_ce
             const uint32_t ngroups = (sh + d.n_v + 7u) >> 3;
             for (uint32_t gi = tid; gi < ngroups; gi += kFastThreads) {
                 const uint32_t r0 = a0 + gi * 8u;
-                if constexpr (U16) {
+                {
                     const uint4 q = *reinterpret_cast<const uint4 *>(sv + gi * 8u);
                     if (r0 >= s && r0 + 8u <= s + d.n_v) {
                         uint32_t mn = __vminu2(__vminu2(q.x, q.y), __vminu2(q.z, q.w));
@@ -1099,17 +1099,6 @@ __global__ void __launch_bounds__(kFastThreads, 2048 / kFastThreads) tokenize_ce
                                 lo = min(lo, key);
                                 hi = max(hi, key);
                             }
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        const uint32_t r = r0 + i;
-                        if (r >= s && r < s + d.n_v) {
-                            const float x = sv[gi * 8u + i];
-                            const uint32_t key = key_of(x);
-                            lo = min(lo, key);
-                            hi = max(hi, key);
                         }
                     }
                 }
@@ -1130,8 +1119,6 @@ __global__ void __launch_bounds__(kFastThreads, 2048 / kFastThreads) tokenize_ce
                 lo = min(lo, s_ws[w]);
                 hi = max(hi, s_ws[kFastWarps + w]);
             }
-            // log1p is monotone, so max(log1pf(x)) over the cell is log1pf of the largest value: one evaluation per cell
-            if constexpr (BINNED && !U16) m_f32 = log1pf_window(float_of_key(hi));
             kmax = hi;
             if (!keep_all) {
                 if (U16 && (hi - lo + 1u <= k)) {
@@ -1152,37 +1139,6 @@ __global__ void __launch_bounds__(kFastThreads, 2048 / kFastThreads) tokenize_ce
 #pragma unroll
                     for (int w2 = 0; w2 < kFastWarps; w2++) above += s_ws[w2];
                     if (above <= M) keep_all = true; else defer = true;
-                } else if (!U16) {
-                    // float32 values: exact distinct count with an open-addressing set in shared memory.  Normalised
-                    // expression values take as many distinct values per cell as the counts they came from (tens),
-                    // so "at most k distinct" holds almost always and the cell stays on this path.
-                    uint32_t *tab = reinterpret_cast<uint32_t *>(smem_raw + 2u * stage_bytes);
-                    const uint32_t cap = min(k, (uint32_t)kHashMaxDistinct);
-                    __syncthreads();                                // s_ws is read above by every thread
-                    for (uint32_t i = tid; i < (uint32_t)kHashSlots; i += kFastThreads) tab[i] = 0xffffffffu;
-                    if (tid == 0) s_ws[0] = 0u;
-                    __syncthreads();
-                    volatile uint32_t *distinct = s_ws;
-                    for (uint32_t r = s + tid; r < e && *distinct <= cap; r += kFastThreads) {
-                        const float x = (r < s + d.n_v) ? (float)sv[r - a0] : (float)__ldg(value_g + r);
-                        const uint32_t key = key_of(x);
-                        uint32_t h = (key * 2654435761u) >> (32 - kHashBits);
-                        volatile uint32_t *vt = tab;
-                        for (;;) {
-                            uint32_t cur = vt[h];                   // plain read first: the common case is "already present"
-                            if (cur == 0xffffffffu) {
-                                cur = atomicCAS(tab + h, 0xffffffffu, key);
-                                if (cur == 0xffffffffu) { atomicAdd(s_ws, 1u); break; }
-                            }
-                            if (cur == key) break;
-                            h = (h + 1u) & (uint32_t)(kHashSlots - 1);
-                            if (*distinct > cap) break;             // the set will not decide any more: stop probing
-                        }
-                    }
-                    __syncthreads();
-                    const uint32_t D = s_ws[0];
-                    __syncthreads();
-                    if (D <= cap) keep_all = true; else defer = true;   // D <= cap <= k distinct values: every row has rank <= k
                 } else {
                     defer = true;                                   // exact k-th distinct value: general kernel
                 }
