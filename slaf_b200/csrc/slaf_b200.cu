@@ -249,7 +249,11 @@ int launch_general(slafb_ctx *ctx, const TokArgs &a, const WindowSink &w, cudaSt
         CU(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
         attr_set[ctx->device & 63] = true;
     }
-    uint32_t grid = (uint32_t)ctx->n_sm * 2u;
+    // persistent CTAs over a ticket: as many per SM as shared memory allows (static TokSmem ~17 KB + bitmap / sort keys)
+    size_t per_sm = (220 * 1024) / (dyn + 18 * 1024);
+    if (per_sm > 2048 / kTokThreads) per_sm = 2048 / kTokThreads;
+    if (per_sm < 1) per_sm = 1;
+    uint32_t grid = (uint32_t)(ctx->n_sm * per_sm);
     if (a.n_cells < grid) grid = a.n_cells;
     if (grid == 0) grid = 1;
     kern<<<grid, kTokThreads, dyn, st>>>(a, w);
