@@ -22,6 +22,10 @@
 //   K3  window_*                Window.apply facade: kept-count, offsets, flat list columns.
 //   K4  tokenize_lists_kernel   SLAFTokenizer.tokenize facade on pre-windowed lists.
 //   K5  gene_stats_kernel       per-gene nonzero sum / count (extension, BASELINE.json config 4).
+//   K6  tokenize_rank_kernel    Geneformer rank-value encoding with per-gene normalisation / rank order (extension).
+//   K7  gene_hist / gene_median per-gene value histogram and exact nonzero medians (extension).
+//   K8  csr_lengths / csr_gather raw mode on the device: the batch as CSR in shuffled cell order
+//                               (RawPrefetchBatch, reference slaf/ml/datasets.py:958-1008).
 //
 // All of it is HBM-bound integer/byte work: no tensor cores.  Loads are 128-bit, aligned to
 // 8-row groups of the column arrays; stores are coalesced 8/16-byte vectors.

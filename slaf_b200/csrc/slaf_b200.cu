@@ -1,13 +1,15 @@
 // slaf_b200.cu -- C-ABI implementation (see include/slaf_b200.h for the contract and the
 // reference interfaces each entry point replaces).
 //
-// Stream model.  Each context owns a side stream `s_in` and two pipeline slots.
-//   submit : [s_in]    wait(caller stream) -> H2D of the COO columns (host input) -> K1 CSR build
-//                      -> D2H of {n_cells, error flags} into pinned memory -> event `front`
-//   collect: [host]    wait `front`; build the shuffle permutation (CPython-exact, host C)
-//            [stream]  wait(front) -> H2D permutation -> K2 tokenize -> K2g general path -> event `done`
-// so the H2D copy and CSR build of batch i+1 overlap the tokenization of batch i, and the only
-// host<->device round trip per batch is the 8-byte cell count.
+// Stream model.  Each context owns a side stream `s_in`, a helper thread and four pipeline slots.
+//   submit : [s_in]    wait(caller stream) -> H2D of the COO columns (host input, piece by piece, straight from
+//                      the caller's pinned / registered memory) -> K1 CSR build, which also writes {n_cells, error
+//                      flag} into mapped pinned memory -> event `front`
+//            [helper]  (slafb_prepare_shuffle) waits `front`, builds the CPython-exact permutation
+//   collect: [host]    waits `front` (and the helper); uploads the permutation
+//            [stream]  wait(front) -> K2 tokenize -> K2g general path (or K6 rank-value) -> event `done`
+// so the H2D copy and CSR build of the next batches overlap the tokenization of the current one, there is no
+// device-to-host copy in either stream, and the only host<->device round trip per batch is the wait on `front`.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdarg.h>
