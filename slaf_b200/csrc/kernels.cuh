@@ -586,7 +586,9 @@ __device__ uint32_t threshold_bitmap(const ValT *__restrict__ value, uint32_t s,
                 const uint32_t r = r0 + i;
                 if (r >= s && r < e) {
                     const uint32_t key = key_of(v[i]);
-                    atomicOr(&bitmap[key >> 5], 1u << (key & 31));
+                    const uint32_t bit = 1u << (key & 31);
+                    // counts repeat: after the first rows nearly every bit is already set, so look before the atomic
+                    if (!(reinterpret_cast<volatile uint32_t *>(bitmap)[key >> 5] & bit)) atomicOr(&bitmap[key >> 5], bit);
                 }
             }
         }
