@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdint>
+#include <cstdlib>
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *b, uint32_t c) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(c) : "memory"); }
 __device__ __forceinline__ void mbar_expect(uint64_t *b, uint32_t n) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(n) : "memory"); }
@@ -56,8 +57,8 @@ __global__ void p_tma(const uint4 *a, size_t n, unsigned *sink) {
     }
     if (acc == 0x12345678u) *sink = acc;
 }
-int main() {
-    const size_t N = (size_t)35000000 * 4 / 16;   // 140 MB like the cfg2 cell column
+int main(int argc, char **argv) {
+    const size_t N = (size_t)(argc > 1 ? atol(argv[1]) : 69600000) * 4 / 16;   // the cell column of one prefetch batch (278 MB by default)
     uint4 *a; unsigned *sink; cudaMalloc(&a, N * 16 + (1 << 20)); cudaMalloc(&sink, 4); cudaMemset(a, 1, N * 16);
     uint4 *flush; cudaMalloc(&flush, (size_t)256 << 20);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
