@@ -430,7 +430,13 @@ def main():
     cells, rows, _ = run_steps(dev_cols, args.steps, False)
     e1.record()
     barrier()
-    ms = max_over_ranks(e0.elapsed_time(e1))
+    ms_local = e0.elapsed_time(e1)
+    ms = max_over_ranks(ms_local)
+    per_rank_ms = [ms_local / args.steps]
+    if world > 1:
+        allms = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(allms, torch.tensor([ms_local / args.steps], dtype=torch.float64, device=dev))
+        per_rank_ms = [float(t.item()) for t in allms]
     tm = eng.timing()
     total_cells = sum_over_ranks(cells)
     value = total_cells / (ms / 1000.0)
@@ -505,7 +511,7 @@ def main():
         pass
     line = {
         "metric": "tokenized cells/sec", "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "ms_per_step": ms / args.steps, "ms_per_step_per_rank": [round(x, 5) for x in per_rank_ms], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
         "config": {"workload": w["name"], "cells_per_step_per_gpu": cps, "rows_per_step_per_gpu": int(np.mean(tot_rows)),
                    "value_dtype": args.value_dtype, "l2": f"{NB} distinct resident batches of {int(np.mean(tot_rows)) * 8 >> 20} MiB input each are cycled (each > 126 MB L2)",
                    "shuffle": "CPython-exact block shuffle, seed 42+step", "parity": f"bit-exact vs oracle on {nv} cells before timing",
