@@ -88,7 +88,7 @@ class ClockSampler:
 
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, gpu_index: int, period_s: float = 0.02):
+    def __init__(self, gpu_index: int, period_s: float = 0.05):
         self.gpu, self.period = gpu_index, period_s
         self.sm, self.power, self.bits = [], [], 0
         self.sm_max = None
