@@ -103,6 +103,7 @@ struct slafb_ctx {
     int timing_every = 1;
     uint64_t batch_seq = 0;
     bool front_on_caller = false;
+    int64_t recent_slow = 1 << 20;    // decayed maximum of the cells recently deferred to the general kernel (starts pessimistic)
 };
 
 namespace {
@@ -175,7 +176,12 @@ void harvest(slafb_ctx *ctx, Slot &s) {
         if (cudaEventElapsedTime(&ms, s.t_k2a, s.t_k2b) == cudaSuccess) ctx->acc.tokenize_ms += ms;
         if (cudaEventElapsedTime(&ms, s.t_k2b, s.t_k2c) == cudaSuccess) ctx->acc.slowpath_ms += ms;
     }
-    if (s.ran_back) ctx->acc.slow_cells += s.all_general ? (int64_t)s.h_counters[0] : (int64_t)s.h_counters[2];
+    if (s.ran_back) {
+        const int64_t slow = s.all_general ? (int64_t)s.h_counters[0] : (int64_t)s.h_counters[2];
+        ctx->acc.slow_cells += slow;
+        // how much work the general kernel found lately (it is launched after every fast kernel, usually for nothing)
+        ctx->recent_slow = slow > ctx->recent_slow ? slow : (ctx->recent_slow * 7) / 8;
+    }
     s.timed_front = s.timed_back = s.timed_h2d = s.ran_back = false;
 }
 
@@ -255,6 +261,9 @@ int launch_general(slafb_ctx *ctx, const TokArgs &a, const WindowSink &w, cudaSt
     size_t per_sm = (220 * 1024) / (dyn + 18 * 1024);
     if (per_sm > 2048 / kTokThreads) per_sm = 2048 / kTokThreads;
     if (per_sm < 1) per_sm = 1;
+    // behind a fast kernel the work list is normally empty: when the recent batches deferred (almost) nothing, one CTA
+    // per SM is plenty and the launch itself is cheaper; any count is still processed correctly, only by fewer CTAs
+    if (!a.all_cells && SINK == 0 && ctx->recent_slow < (int64_t)ctx->n_sm) per_sm = 1;
     uint32_t grid = (uint32_t)(ctx->n_sm * per_sm);
     if (a.n_cells < grid) grid = a.n_cells;
     if (grid == 0) grid = 1;
