@@ -334,3 +334,56 @@ def test_float32_distinct_count_boundaries(engine, mode):
         want = c_oracle.tokenize(cell, gene, value, mode, k, n_bins=51, vocab_size=65000)
         got = engine.tokenize(to_dev(cell), to_dev(gene), to_dev(value), mode=mode, max_genes=k, n_bins=51, vocab_size=65000)
         compare(got, want, mode)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_fuzz_random_shapes_and_parameters(engine, seed):
+    """Randomised parity: random cell sizes (including 1-row and multi-thousand-row cells), value distributions
+    (ties, heavy tails, all-equal, all-distinct), dtypes, modes, k / max_genes / n_bins, shuffles and perm selections."""
+    rng = np.random.default_rng(1000 + seed)
+    value_dtype = rng.choice(["uint16", "float32"])
+    gene_dtype, cell_dtype = [("uint16", "uint32"), ("int32", "int32")][int(rng.integers(2))]
+    G = 60000 if gene_dtype == "uint16" else 90000
+    n_cells = int(rng.integers(1, 60))
+    cells = []
+    for _ in range(n_cells):
+        n = int(rng.choice([1, 2, int(rng.integers(3, 200)), int(rng.integers(200, 3000)), int(rng.integers(3000, 9000))],
+                           p=[0.1, 0.1, 0.4, 0.3, 0.1]))
+        kind = rng.integers(5)
+        if kind == 0:
+            v = rng.geometric(0.3, n)
+        elif kind == 1:
+            v = np.full(n, int(rng.integers(1, 100)))
+        elif kind == 2:
+            v = rng.permutation(n) + 1
+        elif kind == 3:
+            v = rng.integers(1, max(2, n // 3), n)
+        else:
+            v = np.r_[rng.geometric(0.4, max(n - 2, 0)), rng.integers(1000, 60000, min(n, 2))][:n]
+        cells.append((np.sort(rng.choice(G, n, replace=False)), v))
+    ids = rng.choice(10_000_000, n_cells, replace=False)
+    cell = np.concatenate([np.full(len(g), ids[i]) for i, (g, _) in enumerate(cells)]).astype(cell_dtype)
+    gene = np.concatenate([g for g, _ in cells]).astype(gene_dtype)
+    raw = np.concatenate([v for _, v in cells])
+    value = np.minimum(raw, 65535).astype(np.uint16) if value_dtype == "uint16" else (np.sqrt(raw.astype(np.float64)) * 0.731).astype(np.float32)
+    mode = str(rng.choice(["geneformer", "geneformer_pct", "scgpt_raw", "scgpt_binned"]))
+    pct = float(rng.choice([0.0, 12.5, 50.0, 99.0, 100.0])) if mode == "geneformer_pct" else None
+    max_genes = int(rng.choice([1, 2, 3, 17, 64, 255, 1200, 2048, 4097]))
+    max_items = int(rng.choice([max_genes, 1, 5, 100, 3000]))
+    n_bins = int(rng.choice([1, 2, 10, 51, 300]))
+    kw = dict(max_items=max_items, n_bins=n_bins, vocab_size=int(rng.choice([1000, 65000])), min_percentile=pct)
+    choice = int(rng.integers(3))
+    if choice == 0:
+        perm, okw = None, {}
+    elif choice == 1:
+        s = int(rng.integers(0, 100000))
+        perm, okw = py_perm(s, n_cells), dict(shuffle_seed=s)
+    else:
+        perm = rng.permutation(n_cells)[: int(rng.integers(0, n_cells + 1))]
+        okw = dict(perm=perm)
+    want = c_oracle.tokenize(cell, gene, value, mode, max_genes, perm=None if choice == 2 else perm, **kw)
+    if choice == 2:
+        want = tuple(None if w is None else w[perm] for w in want)
+    cols = (cell, gene, value) if rng.integers(2) else (to_dev(cell), to_dev(gene), to_dev(value))
+    got = engine.tokenize(*cols, mode=mode, max_genes=max_genes, **kw, **okw)
+    compare(got, want, mode)
