@@ -59,6 +59,7 @@ struct Slot {
     int64_t n_rows = 0;
     int32_t cell_dtype = 0, gene_dtype = 0, value_dtype = 0;
     cudaEvent_t ev_front = nullptr, ev_done = nullptr, ev_in = nullptr;
+    cudaEvent_t ev_loaded = nullptr;   // all three columns are on the device (ev_front: cell column + CSR build only)
     // timing events
     cudaEvent_t t_h2d0 = nullptr, t_h2d1 = nullptr, t_k1a = nullptr, t_k1b = nullptr, t_k2a = nullptr, t_k2b = nullptr, t_k2c = nullptr;
     bool timed_front = false, timed_back = false, timed_h2d = false;
@@ -73,6 +74,7 @@ struct slafb_ctx {
     int n_sm = 148;
     int64_t max_rows = 0, max_cells = 0;
     cudaStream_t s_in = nullptr;
+    cudaStream_t s_aux = nullptr;      // small device-to-host reads that must not queue behind the big H2D copies
     Slot slot[kSlots];
     int next_slot = 0;
     unsigned long long *tile_state = nullptr;
@@ -169,7 +171,11 @@ int check_params(slafb_ctx *ctx, const slafb_params *p) {
 // accumulate the event timings of a slot's previous use (events are complete: ev_done was waited on)
 void harvest(slafb_ctx *ctx, Slot &s) {
     float ms;
-    if (s.timed_h2d && cudaEventElapsedTime(&ms, s.t_h2d0, s.t_h2d1) == cudaSuccess) ctx->acc.h2d_ms += ms;
+    if (s.timed_h2d && cudaEventElapsedTime(&ms, s.t_h2d0, s.t_h2d1) == cudaSuccess) {
+        float k1 = 0.f;                       // the CSR build sits between the cell column and the other two
+        if (s.timed_front) cudaEventElapsedTime(&k1, s.t_k1a, s.t_k1b);
+        ctx->acc.h2d_ms += ms - k1;
+    }
     if (s.timed_front && cudaEventElapsedTime(&ms, s.t_k1a, s.t_k1b) == cudaSuccess) ctx->acc.csr_ms += ms;
     if (s.timed_front) ctx->acc.timed_batches++;
     if (s.timed_back) {
@@ -383,36 +389,27 @@ int front(slafb_ctx *ctx, Slot &s, const slafb_coo *pieces, int n_pieces, cudaSt
     s.h_counters[1] = 0;
     if (total == 0) {
         CU(ctx, cudaEventRecord(s.ev_front, sf));
+        CU(ctx, cudaEventRecord(s.ev_loaded, sf));
         return SLAFB_OK;
     }
     CU(ctx, cudaEventRecord(s.ev_in, caller));
     CU(ctx, cudaStreamWaitEvent(sf, s.ev_in, 0));
+    bool staged = false;
     if (in->location == SLAFB_LOC_HOST || n_pieces > 1) {
         int rc = ensure_staging(ctx, s);
         if (rc) return rc;
         const cudaMemcpyKind kind = in->location == SLAFB_LOC_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
-        const size_t gsz = dtype_size(in->gene_dtype), vsz = dtype_size(in->value_dtype);
         if (s.sample) CU(ctx, cudaEventRecord(s.t_h2d0, sf));
-        // column by column, so each staging column is written front to back
+        // The cell column goes first and the CSR build runs right behind it: the segment table (all the host
+        // needs to decide what the NEXT batch looks like) is ready after half of the bytes, while the gene and
+        // value columns are still in flight.  Column by column, so each staging column is written front to back.
         size_t off = 0;
         for (int i = 0; i < n_pieces; i++) {
             const size_t n = (size_t)pieces[i].n_rows;
             if (n) CU(ctx, cudaMemcpyAsync(static_cast<char *>(s.in_cell) + off * 4, pieces[i].cell, n * 4, kind, sf));
             off += n;
         }
-        off = 0;
-        for (int i = 0; i < n_pieces; i++) {
-            const size_t n = (size_t)pieces[i].n_rows;
-            if (n) CU(ctx, cudaMemcpyAsync(static_cast<char *>(s.in_gene) + off * gsz, pieces[i].gene, n * gsz, kind, sf));
-            off += n;
-        }
-        off = 0;
-        for (int i = 0; i < n_pieces; i++) {
-            const size_t n = (size_t)pieces[i].n_rows;
-            if (n) CU(ctx, cudaMemcpyAsync(static_cast<char *>(s.in_value) + off * vsz, pieces[i].value, n * vsz, kind, sf));
-            off += n;
-        }
-        if (s.sample) { CU(ctx, cudaEventRecord(s.t_h2d1, sf)); s.timed_h2d = true; }
+        staged = true;
         s.cell = s.in_cell; s.gene = s.in_gene; s.value = s.in_value;
     } else {
         s.cell = in->cell; s.gene = in->gene; s.value = in->value;
@@ -453,6 +450,24 @@ int front(slafb_ctx *ctx, Slot &s, const slafb_coo *pieces, int n_pieces, cudaSt
     ctx->ticket_base += grid;
     ctx->acc.kernel_launches++;
     CU(ctx, cudaEventRecord(s.ev_front, sf));
+    if (staged) {
+        const cudaMemcpyKind kind = in->location == SLAFB_LOC_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+        const size_t gsz = dtype_size(in->gene_dtype), vsz = dtype_size(in->value_dtype);
+        size_t off = 0;
+        for (int i = 0; i < n_pieces; i++) {
+            const size_t n = (size_t)pieces[i].n_rows;
+            if (n) CU(ctx, cudaMemcpyAsync(static_cast<char *>(s.in_gene) + off * gsz, pieces[i].gene, n * gsz, kind, sf));
+            off += n;
+        }
+        off = 0;
+        for (int i = 0; i < n_pieces; i++) {
+            const size_t n = (size_t)pieces[i].n_rows;
+            if (n) CU(ctx, cudaMemcpyAsync(static_cast<char *>(s.in_value) + off * vsz, pieces[i].value, n * vsz, kind, sf));
+            off += n;
+        }
+        if (s.sample) { CU(ctx, cudaEventRecord(s.t_h2d1, sf)); s.timed_h2d = true; }
+    }
+    CU(ctx, cudaEventRecord(s.ev_loaded, sf));
     return SLAFB_OK;
 }
 
@@ -544,7 +559,7 @@ int middle(slafb_ctx *ctx, Slot &s, const slafb_params *p, int64_t *n, cudaStrea
         *use_perm = true;
         *n = p->n_perm;
     }
-    CU(ctx, cudaStreamWaitEvent(st, s.ev_front, 0));
+    CU(ctx, cudaStreamWaitEvent(st, s.ev_loaded, 0));      // gene / value columns (ev_front covered the cell column only)
     if (*use_perm && *n > 0) CU(ctx, cudaMemcpyAsync(s.perm_dev, s.h_perm, (size_t)(*n) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     return SLAFB_OK;
 }
@@ -677,6 +692,7 @@ int slafb_create(slafb_ctx **out, int device, int64_t max_rows, int64_t max_cell
     ctx->max_cells = max_cells;
 #define CUC(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { int rc__ = fail(nullptr, SLAFB_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__)); slafb_destroy(ctx); return rc__; } } while (0)
     CUC(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+    CUC(cudaStreamCreateWithFlags(&ctx->s_aux, cudaStreamNonBlocking));
     const size_t n_tiles_max = (size_t)ctx->n_sm * 8;
     CUC(cudaMalloc(&ctx->tile_state, n_tiles_max * sizeof(unsigned long long)));
     CUC(cudaMemset(ctx->tile_state, 0, n_tiles_max * sizeof(unsigned long long)));
@@ -711,7 +727,7 @@ int slafb_create(slafb_ctx **out, int device, int64_t max_rows, int64_t max_cell
         CUC(cudaHostAlloc(&s.h_perm, ((size_t)max_cells + 1) * sizeof(int32_t), cudaHostAllocDefault));
         s.h_draws = (uint32_t *)malloc(((size_t)max_cells + 1) * sizeof(uint32_t));
         if (!s.h_draws) { slafb_destroy(ctx); return fail(nullptr, SLAFB_ERR_INVALID, "out of host memory"); }
-        cudaEvent_t *plain[] = {&s.ev_front, &s.ev_done, &s.ev_in};
+        cudaEvent_t *plain[] = {&s.ev_front, &s.ev_done, &s.ev_in, &s.ev_loaded};
         for (auto e : plain) CUC(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
         cudaEvent_t *timed[] = {&s.t_h2d0, &s.t_h2d1, &s.t_k1a, &s.t_k1b, &s.t_k2a, &s.t_k2b, &s.t_k2c};
         for (auto e : timed) CUC(cudaEventCreate(e));
@@ -742,13 +758,14 @@ int slafb_destroy(slafb_ctx *ctx) {
         if (s.h_counters) cudaFreeHost(s.h_counters);
         if (s.h_perm) cudaFreeHost(s.h_perm);
         free(s.h_draws);
-        cudaEvent_t evs[] = {s.ev_front, s.ev_done, s.ev_in, s.t_h2d0, s.t_h2d1, s.t_k1a, s.t_k1b, s.t_k2a, s.t_k2b, s.t_k2c};
+        cudaEvent_t evs[] = {s.ev_front, s.ev_done, s.ev_in, s.ev_loaded, s.t_h2d0, s.t_h2d1, s.t_k1a, s.t_k1b, s.t_k2a, s.t_k2b, s.t_k2c};
         for (auto e : evs) if (e) cudaEventDestroy(e);
     }
     cudaFree(ctx->tile_state); cudaFree(ctx->ticket); cudaFree(ctx->log1p_lut); cudaFree(ctx->vstar_table); cudaFree(ctx->sort_scratch); cudaFree(ctx->rank_scratch); cudaFree(ctx->dup_table);
     cudaFree(ctx->kept_count); cudaFree(ctx->total_dev);
     if (ctx->h_total) cudaFreeHost(ctx->h_total);
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+    if (ctx->s_aux) cudaStreamDestroy(ctx->s_aux);
     delete ctx;
     return SLAFB_OK;
 }
@@ -826,9 +843,9 @@ int slafb_segments(slafb_ctx *ctx, int32_t slot, int64_t *n_cells, uint32_t *seg
     if (C > capacity_cells) return fail(ctx, SLAFB_ERR_CAPACITY, "batch has %lld cells, host table capacity is %lld", (long long)C, (long long)capacity_cells);
     if (C == 0) { if (seg_start) seg_start[0] = 0; return SLAFB_OK; }
     if (!seg_start || !seg_cell) return fail(ctx, SLAFB_ERR_INVALID, "NULL table pointer");
-    CU(ctx, cudaMemcpyAsync(seg_start, s.seg_start, (size_t)(C + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->s_in));
-    CU(ctx, cudaMemcpyAsync(seg_cell, s.seg_cell, (size_t)C * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->s_in));
-    CU(ctx, cudaStreamSynchronize(ctx->s_in));
+    CU(ctx, cudaMemcpyAsync(seg_start, s.seg_start, (size_t)(C + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->s_aux));
+    CU(ctx, cudaMemcpyAsync(seg_cell, s.seg_cell, (size_t)C * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->s_aux));
+    CU(ctx, cudaStreamSynchronize(ctx->s_aux));
     return SLAFB_OK;
 }
 
