@@ -57,6 +57,51 @@ __global__ void p_tma(const uint4 *a, size_t n, unsigned *sink) {
     }
     if (acc == 0x12345678u) *sink = acc;
 }
+// hybrid: even tiles through the TMA ring, odd tiles loaded directly by the consumer warps (LDG.128), so the SM is not
+// limited to the bulk-copy engine's 16 B/clk
+template <int STAGES, int TILE_U4, int LDG_PER_TMA>
+__global__ void p_hybrid(const uint4 *a, size_t n, unsigned *sink) {
+    __shared__ __align__(128) uint4 buf[STAGES][TILE_U4];
+    __shared__ __align__(8) uint64_t full[STAGES], empty[STAGES];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NC = blockDim.x - 32;
+    if (tid == 0) { for (int i = 0; i < STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], NC / 32); } asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncthreads();
+    const size_t n_tiles_all = n / TILE_U4;
+    const size_t per = (n_tiles_all + gridDim.x - 1) / gridDim.x;
+    const size_t t_beg = blockIdx.x * per, my_tiles = t_beg < n_tiles_all ? min(per, n_tiles_all - t_beg) : 0;
+    constexpr int GROUP = 1 + LDG_PER_TMA;                 // one TMA tile followed by LDG_PER_TMA direct tiles
+    const size_t n_groups = (my_tiles + GROUP - 1) / GROUP;
+    unsigned acc = 0;
+    if (warp == NC / 32) {
+        if (lane == 0) for (size_t g = 0; g < n_groups; g++) {
+            int st = g % STAGES;
+            if (g >= STAGES) mbar_wait(&empty[st], ((g / STAGES) - 1) & 1);
+            mbar_expect(&full[st], TILE_U4 * 16);
+            bulk(buf[st], a + (t_beg + g * GROUP) * TILE_U4, TILE_U4 * 16, &full[st]);
+        }
+    } else {
+        for (size_t g = 0; g < n_groups; g++) {
+            int st = g % STAGES;
+            uint4 r[LDG_PER_TMA][TILE_U4 / 256];
+#pragma unroll
+            for (int k = 0; k < LDG_PER_TMA; k++) {
+                const size_t t = g * GROUP + 1 + k;
+#pragma unroll
+                for (int i = 0; i < TILE_U4 / 256; i++)
+                    r[k][i] = (t < my_tiles) ? __ldcs(a + (t_beg + t) * TILE_U4 + tid + i * NC) : make_uint4(0, 0, 0, 0);
+            }
+            mbar_wait(&full[st], (g / STAGES) & 1);
+            for (int i = tid; i < TILE_U4; i += NC) { uint4 v = buf[st][i]; acc |= v.x ^ v.y ^ v.z ^ v.w; }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[st]);
+#pragma unroll
+            for (int k = 0; k < LDG_PER_TMA; k++)
+#pragma unroll
+                for (int i = 0; i < TILE_U4 / 256; i++) acc |= r[k][i].x ^ r[k][i].y ^ r[k][i].z ^ r[k][i].w;
+        }
+    }
+    if (acc == 0x12345678u) *sink = acc;
+}
 int main(int argc, char **argv) {
     const size_t N = (size_t)(argc > 1 ? atol(argv[1]) : 69600000) * 4 / 16;   // the cell column of one prefetch batch (278 MB by default)
     uint4 *a; unsigned *sink; cudaMalloc(&a, N * 16 + (1 << 20)); cudaMalloc(&sink, 4); cudaMemset(a, 1, N * 16);
@@ -82,5 +127,9 @@ int main(int argc, char **argv) {
     run("TMA 4x8K strided, 740x288", [&] { p_tma<4, 512, true><<<740, 288>>>(a, N, sink); });
     run("TMA 4x4K strided, 1184x288", [&] { p_tma<4, 256, true><<<1184, 288>>>(a, N, sink); });
     run("TMA 4x4K span, 1184x288", [&] { p_tma<4, 256, false><<<1184, 288>>>(a, N, sink); });
+    run("hybrid TMA 4x8K + 1 LDG tile, 592x288", [&] { p_hybrid<4, 512, 1><<<592, 288>>>(a, N, sink); });
+    run("hybrid TMA 4x8K + 2 LDG tiles, 592x288", [&] { p_hybrid<4, 512, 2><<<592, 288>>>(a, N, sink); });
+    run("hybrid TMA 4x8K + 1 LDG tile, 740x288", [&] { p_hybrid<4, 512, 1><<<740, 288>>>(a, N, sink); });
+    run("hybrid TMA 3x8K + 3 LDG tiles, 740x288", [&] { p_hybrid<3, 512, 3><<<740, 288>>>(a, N, sink); });
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
 }
