@@ -238,3 +238,55 @@ def test_raw_mode_on_device_loader(data, mode):
     for c in (0, 33, N_CELLS - 1):
         lo, hi = data.cell_start[c], data.cell_start[c + 1]
         assert np.array_equal(seen[c][0], np.sort(data.gene[lo:hi]).astype(np.int32)) and seen[c][1] == int(data.value[lo:hi].sum())
+
+
+def test_reference_cross_fragment_fixture_tokenized():
+    """The reference's own boundary fixture (tests/conftest.py:478-481: cell 1 split across two fragments, all values 1.0)
+    through the tokenized loader in both loading modes: every cell once, tokens = all of the cell's genes in row order."""
+    from tests.test_host_logic import _reference_boundary_fixture
+
+    want = {0: [0, 1], 1: [0, 1, 2, 3, 4, 5], 2: [0, 1], 3: [0, 1, 2], 4: [0, 1], 5: [0]}
+    for mos in (True, False):
+        arr, _ = _reference_boundary_fixture()
+        np.random.seed(1)
+        loader = SLAFDataLoader(arr, tokenizer_type="scgpt", batch_size=4, max_genes=8, n_expression_bins=10, vocab_size=100,
+                                use_mixture_of_scanners=mos, by_fragment=True, n_scanners=2, prefetch_batch_size=1000, verbose=False)
+        seen = {}
+        for batch in loader:
+            for row, c in zip(batch["input_ids"].cpu().tolist(), batch["cell_ids"].cpu().tolist()):
+                assert c not in seen
+                seen[c] = row
+        assert sorted(seen) == list(range(6))
+        for c, genes in want.items():
+            assert seen[c] == [1] + [g + 4 for g in genes] + [2] + [0] * (10 - len(genes) - 2), (mos, c)
+
+
+def test_reference_tiny_adata_matrix_all_tokenizers(engine):
+    """The reference's `tiny_adata` fixture matrix (tests/conftest.py:298-324: seed 42, 100 x 50, density 0.3, uniform(1, 5)
+    float32, every row and column non-empty), in converter row order, through every mode against the oracle."""
+    from scipy.sparse import csr_matrix
+
+    np.random.seed(42)
+    n_cells, n_genes = 100, 50
+    n_nonzero = int(n_cells * n_genes * 0.3)
+    data = np.random.uniform(1.0, 5.0, n_nonzero).astype(np.float32)
+    rows = np.random.randint(0, n_cells, n_nonzero)
+    cols = np.random.randint(0, n_genes, n_nonzero)
+    X = csr_matrix((data, (rows, cols)), shape=(n_cells, n_genes)).tolil()
+    for i in range(n_cells):
+        if X[i, :].nnz == 0:
+            X[i, np.random.randint(0, n_genes)] = np.random.uniform(1.0, 5.0)
+    for j in range(n_genes):
+        if X[:, j].nnz == 0:
+            X[np.random.randint(0, n_cells), j] = np.random.uniform(1.0, 5.0)
+    coo = X.tocsr().tocoo()                                        # cell-major, gene-ascending: the converter's row order
+    cell, gene, value = coo.row.astype(np.int32), coo.col.astype(np.int32), coo.data.astype(np.float32)
+    assert len(np.unique(cell)) == 100
+    for mode, pct in (("geneformer", None), ("geneformer_pct", 25.0), ("scgpt_raw", None), ("scgpt_binned", None)):
+        for k in (3, 10, 64):
+            w = c_oracle.tokenize(cell, gene, value, mode, k, n_bins=10, vocab_size=50000, min_percentile=pct)
+            g = engine.tokenize(cell, gene, value, mode=mode, max_genes=k, n_bins=10, vocab_size=50000, min_percentile=pct)
+            assert_same(g.input_ids.cpu().numpy(), w[0], f"{mode} k={k} ids")
+            assert_same(g.attention_mask.cpu().numpy(), w[1], f"{mode} k={k} mask")
+            if w[2] is not None:
+                assert_same(g.values.cpu().numpy(), w[2], f"{mode} k={k} values")

@@ -261,3 +261,53 @@ def test_group_boundary_handler_local_merge():
     assert complete["cell_integer_id"].tolist() == [4, 5, 6] and partial == {}
     with pytest.raises(NotImplementedError):
         GroupBoundaryHandler(SLAF_LANCE_COO_SCHEMA, partial_groups_kv={})
+
+
+# ---------------------------------------------------------------- the reference's own boundary fixture
+def _reference_boundary_fixture():
+    """tests/conftest.py:478-481 of the reference: two fragments, cell 1 split across them, all values 1.0 (int32/int32/float32)."""
+    from slaf_b200.ml.sources import CooChunk, ExpressionSource, Fragment, SyntheticSLAFArray
+
+    frag1_cell, frag1_gene = [0, 0, 1, 1, 1], [0, 1, 0, 1, 2]
+    frag2_cell, frag2_gene = [1, 1, 1, 2, 2, 3, 3, 3, 4, 4, 5], [3, 4, 5, 0, 1, 0, 1, 2, 0, 1, 0]
+
+    class _Frag(Fragment):
+        def __init__(self, c, g):
+            self._t = CooChunk(np.asarray(c, np.int32), np.asarray(g, np.int32), np.ones(len(c), np.float32))
+
+        def count_rows(self):
+            return len(self._t)
+
+        def to_table(self):
+            return self._t
+
+    class _Src(ExpressionSource):
+        def get_fragments(self):
+            return [_Frag(frag1_cell, frag1_gene), _Frag(frag2_cell, frag2_gene)]
+
+    csi = np.array([0, 2, 8, 10, 13, 15, 16], np.int64)
+    return SyntheticSLAFArray(_Src(), csi, 10), csi
+
+
+@pytest.mark.parametrize("mos", [True, False])
+def test_reference_cross_fragment_fixture_raw_epoch(mos):
+    """tests/test_cell_boundary_reassembly.py:33-73 on the reference's fixture: every cell exactly once, observed rows per
+    cell == _cell_start_index, no duplicate (cell, gene) pair."""
+    from slaf_b200.ml import PrefetchBatchProcessor, RandomShuffle, RawPrefetchBatch
+
+    arr, csi = _reference_boundary_fixture()
+    np.random.seed(0)
+    proc = PrefetchBatchProcessor(arr, RandomShuffle(), None, raw_mode=True, use_mixture_of_scanners=mos, by_fragment=True,
+                                  n_scanners=2, prefetch_batch_size=1000, batch_size=4, verbose=False)
+    batches = []
+    with pytest.raises(StopIteration):
+        while True:
+            batches.append(proc.load_prefetch_batch())
+    assert all(isinstance(b, RawPrefetchBatch) for b in batches)
+    cells = np.concatenate([np.asarray(df["cell_integer_id"]) for b in batches for df in b.batch_dfs])
+    genes = np.concatenate([np.asarray(df["gene_integer_id"]) for b in batches for df in b.batch_dfs])
+    ids, counts = np.unique(cells, return_counts=True)
+    assert ids.tolist() == list(range(6)) and counts.tolist() == np.diff(csi).tolist()
+    assert len({(int(c), int(g)) for c, g in zip(cells, genes)}) == len(cells) == 16
+    emitted = [c for b in batches for c in b.cell_integer_ids]
+    assert sorted(emitted) == list(range(6))
