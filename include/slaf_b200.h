@@ -167,6 +167,15 @@ int slafb_submit(slafb_ctx *ctx, const slafb_coo *in, void *stream, int32_t *slo
  * 880-888).  Host blocks are copied into the slot's staging columns straight from where they live,
  * so with pinned / registered source memory the feeder does no host-side assembly at all. */
 int slafb_submit_pieces(slafb_ctx *ctx, const slafb_coo *pieces, int32_t n_pieces, void *stream, int32_t *slot);
+/* submit() for a feeder that already KNOWS the cell boundaries of the rows it hands over -- SLAF keeps the row offset of
+ * every cell in SLAFArray._cell_start_index (slaf/core/slaf.py:645-702; the reference uses it for its completeness
+ * check, slaf/ml/datasets.py:891-928) -- so the cell column neither crosses PCIe (half of the bytes) nor needs a CSR
+ * build.  pieces[i].cell is ignored (may be NULL; cell_dtype still says how to widen the ids); seg_start[n_cells + 1]
+ * (row offsets into the concatenated pieces, seg_start[0] = 0, seg_start[n_cells] = total rows) and seg_cell[n_cells]
+ * are HOST arrays.  Everything downstream (collect, collect_csr, segments) is unchanged. */
+int slafb_submit_segments(slafb_ctx *ctx, const slafb_coo *pieces, int32_t n_pieces, const uint32_t *seg_start,
+                          const uint32_t *seg_cell, int64_t n_cells, void *stream, int32_t *slot);
+
 /* Optional hint between submit() and collect(): the shuffle seed the batch will be collected with
  * (seed + batch_id + epoch*10000, datasets.py:1016).  The context's helper thread then builds the
  * CPython-exact permutation as soon as the CSR build has produced the cell count, off the caller's

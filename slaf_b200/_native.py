@@ -34,7 +34,7 @@ ORDER_ROW, ORDER_RANK = 0, 1
 ABI_VERSION = 2
 
 EXPORTS = [
-    "slafb_version", "slafb_create", "slafb_destroy", "slafb_last_error", "slafb_tokenize", "slafb_submit", "slafb_submit_pieces", "slafb_host_register", "slafb_host_unregister",
+    "slafb_version", "slafb_create", "slafb_destroy", "slafb_last_error", "slafb_tokenize", "slafb_submit", "slafb_submit_pieces", "slafb_submit_segments", "slafb_host_register", "slafb_host_unregister",
     "slafb_collect", "slafb_collect_csr", "slafb_prepare_shuffle", "slafb_segments", "slafb_window", "slafb_tokenize_lists", "slafb_shuffle_perm", "slafb_gene_stats", "slafb_gene_hist", "slafb_gene_median",
     "slafb_host_alloc", "slafb_host_free", "slafb_get_timing", "slafb_set_option",
 ]
@@ -128,6 +128,7 @@ def lib() -> ctypes.CDLL:
     L.slafb_tokenize.argtypes = [c_void_p, POINTER(Coo), POINTER(Params), POINTER(Out), POINTER(c_int64), c_void_p]
     L.slafb_submit.argtypes = [c_void_p, POINTER(Coo), c_void_p, POINTER(c_int32)]
     L.slafb_submit_pieces.argtypes = [c_void_p, POINTER(Coo), c_int32, c_void_p, POINTER(c_int32)]
+    L.slafb_submit_segments.argtypes = [c_void_p, POINTER(Coo), c_int32, c_void_p, c_void_p, c_int64, c_void_p, POINTER(c_int32)]
     L.slafb_host_register.argtypes = [c_void_p, c_size_t]
     L.slafb_host_unregister.argtypes = [c_void_p]
     L.slafb_collect_csr.argtypes = [c_void_p, c_int32, POINTER(Params), c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,

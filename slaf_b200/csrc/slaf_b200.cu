@@ -786,6 +786,85 @@ int slafb_submit_pieces(slafb_ctx *ctx, const slafb_coo *pieces, int32_t n_piece
     return SLAFB_OK;
 }
 
+int slafb_submit_segments(slafb_ctx *ctx, const slafb_coo *pieces, int32_t n_pieces, const uint32_t *seg_start, const uint32_t *seg_cell,
+                          int64_t n_cells, void *stream, int32_t *slot) {
+    if (!ctx || !slot || !pieces || n_pieces < 1) return fail(ctx, SLAFB_ERR_INVALID, "bad ctx / slot / pieces");
+    CU(ctx, cudaSetDevice(ctx->device));
+    const int si = ctx->next_slot;
+    Slot &s = ctx->slot[si];
+    if (s.in_flight) return fail(ctx, SLAFB_ERR_BUSY, "pipeline slot %d not collected yet", si);
+    const double t0 = now_ms();
+    int64_t total = 0;
+    for (int i = 0; i < n_pieces; i++) {
+        const slafb_coo &p = pieces[i];
+        if (p.n_rows < 0 || (p.n_rows > 0 && (!p.gene || !p.value))) return fail(ctx, SLAFB_ERR_INVALID, "NULL gene / value column");
+        if (p.gene_dtype != pieces[0].gene_dtype || p.value_dtype != pieces[0].value_dtype || p.location != pieces[0].location)
+            return fail(ctx, SLAFB_ERR_INVALID, "all pieces of a batch must share column dtypes and location");
+        total += p.n_rows;
+    }
+    const slafb_coo *in = &pieces[0];
+    if (in->gene_dtype != SLAFB_U16 && in->gene_dtype != SLAFB_I32 && in->gene_dtype != SLAFB_U32) return fail(ctx, SLAFB_ERR_INVALID, "gene dtype must be uint16, int32 or uint32");
+    if (in->value_dtype != SLAFB_U16 && in->value_dtype != SLAFB_F32) return fail(ctx, SLAFB_ERR_INVALID, "value dtype must be uint16 or float32");
+    if (in->cell_dtype != SLAFB_U32 && in->cell_dtype != SLAFB_I32) return fail(ctx, SLAFB_ERR_INVALID, "cell dtype must be uint32 or int32");
+    if (total > ctx->max_rows) return fail(ctx, SLAFB_ERR_CAPACITY, "n_rows %lld exceeds context max_rows %lld", (long long)total, (long long)ctx->max_rows);
+    if (n_cells < 0 || n_cells > ctx->max_cells) return fail(ctx, SLAFB_ERR_CAPACITY, "n_cells %lld exceeds context max_cells %lld", (long long)n_cells, (long long)ctx->max_cells);
+    if (n_cells > 0 && (!seg_start || !seg_cell)) return fail(ctx, SLAFB_ERR_INVALID, "NULL segment table");
+    if (n_cells > 0 && (seg_start[0] != 0 || (int64_t)seg_start[n_cells] != total)) return fail(ctx, SLAFB_ERR_INVALID, "segment table does not cover the rows");
+    if (s.ev_done) {
+        CU(ctx, cudaEventSynchronize(s.ev_done));
+        harvest(ctx, s);
+    }
+    cudaStream_t sf = ctx->s_in;
+    s.sample = (ctx->timing_every <= 1) || (ctx->batch_seq % (uint64_t)ctx->timing_every == 0);
+    ctx->batch_seq++;
+    s.n_rows = total;
+    s.cell_dtype = in->cell_dtype;
+    s.gene_dtype = in->gene_dtype;
+    s.value_dtype = in->value_dtype;
+    s.h_counters[0] = (uint32_t)n_cells;
+    s.h_counters[1] = 0;
+    CU(ctx, cudaEventRecord(s.ev_in, static_cast<cudaStream_t>(stream)));
+    CU(ctx, cudaStreamWaitEvent(sf, s.ev_in, 0));
+    // the segment table comes from the host (8 bytes per cell): no cell column crosses the bus and no CSR build runs
+    CU(ctx, cudaMemsetAsync(s.counters, 0, 8 * sizeof(uint32_t), sf));
+    if (n_cells > 0) {
+        CU(ctx, cudaMemcpyAsync(s.seg_start, seg_start, (size_t)(n_cells + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, sf));
+        CU(ctx, cudaMemcpyAsync(s.seg_cell, seg_cell, (size_t)n_cells * sizeof(uint32_t), cudaMemcpyHostToDevice, sf));
+    }
+    CU(ctx, cudaEventRecord(s.ev_front, sf));
+    if (total > 0) {
+        if (in->location == SLAFB_LOC_HOST || n_pieces > 1) {
+            int rc = ensure_staging(ctx, s);
+            if (rc) return rc;
+            const cudaMemcpyKind kind = in->location == SLAFB_LOC_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+            const size_t gsz = dtype_size(in->gene_dtype), vsz = dtype_size(in->value_dtype);
+            if (s.sample) CU(ctx, cudaEventRecord(s.t_h2d0, sf));
+            size_t off = 0;
+            for (int i = 0; i < n_pieces; i++) {
+                const size_t n = (size_t)pieces[i].n_rows;
+                if (n) CU(ctx, cudaMemcpyAsync(static_cast<char *>(s.in_gene) + off * gsz, pieces[i].gene, n * gsz, kind, sf));
+                off += n;
+            }
+            off = 0;
+            for (int i = 0; i < n_pieces; i++) {
+                const size_t n = (size_t)pieces[i].n_rows;
+                if (n) CU(ctx, cudaMemcpyAsync(static_cast<char *>(s.in_value) + off * vsz, pieces[i].value, n * vsz, kind, sf));
+                off += n;
+            }
+            if (s.sample) { CU(ctx, cudaEventRecord(s.t_h2d1, sf)); s.timed_h2d = true; }
+            s.cell = nullptr; s.gene = s.in_gene; s.value = s.in_value;
+        } else {
+            s.cell = nullptr; s.gene = in->gene; s.value = in->value;
+        }
+    }
+    CU(ctx, cudaEventRecord(s.ev_loaded, sf));
+    ctx->acc.host_submit_ms += now_ms() - t0;
+    s.in_flight = true;
+    ctx->next_slot = (si + 1) % kSlots;
+    *slot = si;
+    return SLAFB_OK;
+}
+
 int slafb_submit(slafb_ctx *ctx, const slafb_coo *in, void *stream, int32_t *slot) {
     return slafb_submit_pieces(ctx, in, 1, stream, slot);
 }

@@ -211,6 +211,38 @@ class HotPathEngine:
         self._pending[slot.value] = (keeps[0] + tuple(keeps[1:]), total)
         return slot.value
 
+    def submit_segments(self, pieces: list[tuple[Any, Any]], seg_start: np.ndarray, seg_cell: np.ndarray, cell_signed: bool = False,
+                        shuffle_seed: int | None = None) -> int:
+        """submit() when the cell boundaries are already known on the host (from SLAFArray._cell_start_index): `pieces` are
+        consecutive (gene, value) row blocks, `seg_start` uint32 [C + 1] row offsets into their concatenation, `seg_cell`
+        the cell ids.  The cell column never crosses PCIe and no CSR build runs."""
+        if not pieces:
+            raise ValueError("no pieces")
+        coos, keeps, total = [], [], 0
+        for gene, value in pieces:
+            g = _Column(gene, (N.U16, N.I32, N.U32), "gene_integer_id")
+            v = _Column(value, (N.U16, N.F32), "value")
+            if g.n != v.n or g.location != v.location:
+                raise ValueError("gene / value blocks must have equal length and location")
+            coos.append(N.Coo(None, g.ptr or None, v.ptr or None, g.n, N.I32 if cell_signed else N.U32, g.code, v.code, g.location))
+            keeps.append((g, v))
+            total += g.n
+        seg_start = np.ascontiguousarray(seg_start, np.uint32)
+        seg_cell = np.ascontiguousarray(seg_cell).view(np.uint32) if np.asarray(seg_cell).dtype.itemsize == 4 else np.ascontiguousarray(seg_cell, np.uint32)
+        C = seg_cell.size
+        if seg_start.size != C + 1:
+            raise ValueError("seg_start must have one more entry than seg_cell")
+        arr = (N.Coo * len(coos))(*coos)
+        slot = ctypes.c_int32(-1)
+        with torch.cuda.device(self.device):
+            N.check(self._L.slafb_submit_segments(self._ctx, arr, len(coos), seg_start.ctypes.data, seg_cell.ctypes.data, C, self._stream(),
+                                                  ctypes.byref(slot)), self._ctx)
+            if shuffle_seed is not None:
+                N.check(self._L.slafb_prepare_shuffle(self._ctx, slot.value, int(shuffle_seed)), self._ctx)
+        cell_col = _Column(np.zeros(1, np.int32 if cell_signed else np.uint32), (N.U32, N.I32), "cell_integer_id")
+        self._pending[slot.value] = ((cell_col, keeps[0][0], keeps[0][1]) + tuple(keeps[1:]) + (seg_start, seg_cell), total)
+        return slot.value
+
     def collect(self, slot: int, *, mode: str, max_genes: int, max_items: int | None = None, n_bins: int = 10,
                 vocab_size: int = 50000, min_percentile: float | None = None, shuffle_seed: int | None = None,
                 perm=None, capacity_cells: int | None = None, check_contiguous: bool = False,

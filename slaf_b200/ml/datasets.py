@@ -179,6 +179,38 @@ def _regroup_segments(pieces: list[CooChunk], seg_start: np.ndarray, seg_cell: n
     return out
 
 
+def _segments_from_csi(pieces: list[CooChunk], csi: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+    """Segment table of the concatenated pieces from SLAFArray._cell_start_index alone (no look at the cell column):
+    piece p covers table rows [row_lo, row_lo + len); cell c owns rows [csi[c], csi[c + 1]).  Consecutive pieces that
+    continue the same cell give ONE segment (their rows are adjacent in the staging columns); a cell that shows up in
+    two separated places gives two segments with the same id, which the caller's splice safety net handles.
+    Returns (seg_start uint32 [C + 1], seg_cell int64 [C]).  O(cells), vectorised."""
+    starts, ids = [], []
+    pos = 0
+    for p in pieces:
+        n = len(p)
+        if n == 0:
+            continue
+        lo, hi = int(p.row_lo), int(p.row_lo) + n
+        c0 = int(np.searchsorted(csi, lo, side="right")) - 1
+        c1 = int(np.searchsorted(csi, hi - 1, side="right")) - 1
+        cells = np.arange(c0, c1 + 1, dtype=np.int64)
+        first_row = np.maximum(csi[cells], lo)
+        nonempty = csi[cells + 1] > first_row                      # cells without rows (or not reaching into this piece) have no segment
+        cells, first_row = cells[nonempty], first_row[nonempty]
+        st = first_row - lo + pos
+        if ids and len(cells) and ids[-1][-1] == cells[0] and st[0] == pos:
+            cells, st = cells[1:], st[1:]                            # the previous piece's last cell continues here: one segment
+        starts.append(st)
+        ids.append(cells if len(cells) else np.zeros(0, np.int64))
+        pos += n
+    ids = [i for i in ids if len(i)]
+    starts = [s_ for s_ in starts if len(s_)]
+    seg_cell = np.concatenate(ids) if ids else np.zeros(0, np.int64)
+    seg_start = np.concatenate(starts + [np.array([pos], np.int64)]) if starts else np.array([0], np.int64)
+    return seg_start.astype(np.uint32), seg_cell
+
+
 class _Staging:
     """Ring of pinned host buffers the combined rows of a batch are assembled in (so the H2D copy
     is a true async DMA).  Copies run on a small thread pool: numpy releases the GIL in memcpy."""
@@ -241,9 +273,12 @@ class PrefetchBatchProcessor:
                  n_epochs: int = 1, raw_mode: bool = False, verbose: bool = True, log_metrics: bool = False,
                  batch_size: int = 32, by_fragment: bool = True, use_mixture_of_scanners: bool = True, n_scanners: int = 16,
                  prefetch_batch_size: int = 4194304, parallelize_fragment_reads: bool = False, device=None,
-                 copy_threads: int = 4, device_raw: bool = False):
+                 copy_threads: int = 4, device_raw: bool = False, use_cell_start_index: bool = False):
         self.slaf_array = slaf_array
         self.device_raw = device_raw
+        # EXTENSION: take the cell boundaries from slaf_array._cell_start_index instead of the cell column, so that
+        # column neither crosses PCIe nor is scanned (needs a source that knows the table position of its chunks)
+        self.use_cell_start_index = use_cell_start_index
         self.shuffle = shuffle
         self.tokenizer = tokenizer
         self.seed = seed
@@ -457,7 +492,7 @@ class PrefetchBatchProcessor:
             while lo < hi:
                 a, b = lo - int(offs[k]), min(hi, int(offs[k + 1])) - int(offs[k])
                 p = pieces[k]
-                parts.append(CooChunk(p.cell[a:b].copy(), p.gene[a:b].copy(), p.value[a:b].copy()))
+                parts.append(p.slice(a, b).copy())
                 lo = int(offs[k + 1])
                 k += 1
             part = concat_chunks(parts)
@@ -526,27 +561,51 @@ class PrefetchBatchProcessor:
         rows = self._staging.assemble(pieces)
         return eng.submit(rows.cell, rows.gene, rows.value), [rows]
 
+    def _submit_with_csi(self, eng: HotPathEngine, pieces: list[CooChunk]):
+        csi = np.asarray(self.slaf_array._cell_start_index, np.int64)
+        seg_start, seg_cell = _segments_from_csi(pieces, csi)
+        if len(np.unique(seg_cell)) != len(seg_cell):                      # a cell in two separated places: splice (views) first
+            pieces = _regroup_segments(pieces, seg_start, seg_cell)
+            seg_start, seg_cell = _segments_from_csi(pieces, csi)
+        for p in pieces:                                                     # O(1) consistency probes against the rows themselves
+            lo = int(p.row_lo)
+            if int(p.cell[0]) != int(np.searchsorted(csi, lo, side="right")) - 1 or \
+                    int(p.cell[-1]) != int(np.searchsorted(csi, lo + len(p) - 1, side="right")) - 1:
+                raise ValueError("_cell_start_index does not describe the expression rows (cell ids at a chunk boundary differ)")
+        signed = pieces[0].cell.dtype == np.int32
+        direct = all(len(p) <= self.SMALL_PIECE_ROWS or (is_page_locked(p.gene) and is_page_locked(p.value)) for p in pieces)
+        if direct and len(pieces) <= 256:
+            slot = eng.submit_segments([(p.gene, p.value) for p in pieces], seg_start, seg_cell.astype(np.uint32), cell_signed=signed)
+        else:
+            rows = self._staging.assemble(pieces)
+            slot = eng.submit_segments([(rows.gene, rows.value)], seg_start, seg_cell.astype(np.uint32), cell_signed=signed)
+        ids = seg_cell.astype(np.int32) if signed else seg_cell.astype(np.uint32)
+        return slot, pieces, seg_start, ids
+
     def _front(self, pieces: list[CooChunk]):
         """submit -> segment table -> (splice safety net) -> completeness -> partial stash.
         Returns (engine, slot, indices of the complete cells in first-appearance order, their row counts)."""
         n_rows = sum(len(p) for p in pieces)
         eng = self._engine_for(n_rows)
-        slot, pieces = self._submit(eng, pieces)
-        try:
-            seg_start, seg_cell = eng.segments(slot)
-        except N.SlafB200Error as err:
-            if err.code != N.ERR_CAPACITY:
-                raise
-            eng.release(slot)                                   # more cells than the segment tables hold: size for the worst case
-            eng = self._engine_for(n_rows, all_cells=True)
+        if self.use_cell_start_index and all(p.row_lo is not None for p in pieces):
+            slot, pieces, seg_start, seg_cell = self._submit_with_csi(eng, pieces)
+        else:
             slot, pieces = self._submit(eng, pieces)
-            seg_start, seg_cell = eng.segments(slot)
-        if len(np.unique(seg_cell)) != len(seg_cell):
-            # a cell re-joined from two separated runs (partial + continuation with other chunks in
-            # between): splice on the host like partition_by does, then resubmit (rare)
-            eng.release(slot)
-            slot, pieces = self._submit(eng, _regroup_segments(pieces, seg_start, seg_cell))
-            seg_start, seg_cell = eng.segments(slot)
+            try:
+                seg_start, seg_cell = eng.segments(slot)
+            except N.SlafB200Error as err:
+                if err.code != N.ERR_CAPACITY:
+                    raise
+                eng.release(slot)                                   # more cells than the segment tables hold: size for the worst case
+                eng = self._engine_for(n_rows, all_cells=True)
+                slot, pieces = self._submit(eng, pieces)
+                seg_start, seg_cell = eng.segments(slot)
+            if len(np.unique(seg_cell)) != len(seg_cell):
+                # a cell re-joined from two separated runs (partial + continuation with other chunks in
+                # between): splice on the host like partition_by does, then resubmit (rare)
+                eng.release(slot)
+                slot, pieces = self._submit(eng, _regroup_segments(pieces, seg_start, seg_cell))
+                seg_start, seg_cell = eng.segments(slot)
         seg_len = np.diff(seg_start.astype(np.int64))
         complete = self._complete_mask(seg_cell, seg_len)
         self._stash_partials(pieces, seg_start, seg_cell, complete)
@@ -789,7 +848,8 @@ class SLAFIterableDataset(IterableDataset):
                  use_binned_expressions: bool = False, n_epochs: int = 1, raw_mode: bool = False, verbose: bool = True,
                  batches_per_chunk: int = 1, by_fragment: bool = True, use_mixture_of_scanners: bool = True, n_scanners: int = 16,
                  prefetch_batch_size: int = 4194304, parallelize_fragment_reads: bool = False,
-                 prefetcher_ready_timeout: float = 10.0, device=None, output_device=None, device_raw: bool = False):
+                 prefetcher_ready_timeout: float = 10.0, device=None, output_device=None, device_raw: bool = False,
+                 use_cell_start_index: bool = False):
         super().__init__()
         self.slaf_array = slaf_array
         self.tokenizer = tokenizer
@@ -811,7 +871,7 @@ class SLAFIterableDataset(IterableDataset):
             use_binned_expressions=use_binned_expressions, n_epochs=n_epochs, raw_mode=raw_mode, verbose=verbose,
             log_metrics=False, batch_size=batch_size, by_fragment=by_fragment, use_mixture_of_scanners=use_mixture_of_scanners,
             n_scanners=n_scanners, prefetch_batch_size=prefetch_batch_size, parallelize_fragment_reads=parallelize_fragment_reads,
-            device=device, device_raw=device_raw)
+            device=device, device_raw=device_raw, use_cell_start_index=use_cell_start_index)
         self.prefetcher = AsyncPrefetcher(self.batch_processor, max_queue_size=max_queue_size)
         self.prefetcher.start()
         self.device = self.output_device if self.output_device is not None else torch.device("cuda")

@@ -33,12 +33,16 @@ class CooChunk:
     cell: np.ndarray
     gene: np.ndarray
     value: np.ndarray
+    row_lo: int | None = None     # absolute row of the first row in the expression table (when the source knows it)
 
     def __len__(self) -> int:
         return int(self.cell.shape[0])
 
     def slice(self, lo: int, hi: int) -> "CooChunk":
-        return CooChunk(self.cell[lo:hi], self.gene[lo:hi], self.value[lo:hi])
+        return CooChunk(self.cell[lo:hi], self.gene[lo:hi], self.value[lo:hi], None if self.row_lo is None else self.row_lo + lo)
+
+    def copy(self) -> "CooChunk":
+        return CooChunk(self.cell.copy(), self.gene.copy(), self.value.copy(), self.row_lo)
 
     def as_dict(self) -> dict[str, np.ndarray]:
         return {"cell_integer_id": self.cell, "gene_integer_id": self.gene, "value": self.value}
@@ -47,8 +51,14 @@ class CooChunk:
 def concat_chunks(chunks: list[CooChunk]) -> CooChunk:
     if len(chunks) == 1:
         return chunks[0]
+    row_lo, pos = chunks[0].row_lo, chunks[0].row_lo
+    for c in chunks:                                     # the result keeps its table position only if the parts are consecutive rows
+        if pos is None or c.row_lo != pos:
+            row_lo = None
+            break
+        pos += len(c)
     return CooChunk(np.concatenate([c.cell for c in chunks]), np.concatenate([c.gene for c in chunks]),
-                    np.concatenate([c.value for c in chunks]))
+                    np.concatenate([c.value for c in chunks]), row_lo)
 
 
 def chunk_from_frame(frame: Any) -> CooChunk:
@@ -110,7 +120,7 @@ class ArrayExpressionSource(ExpressionSource):
             raise ValueError("column lengths differ")
         if max_rows_per_file < 1:
             raise ValueError("max_rows_per_file must be >= 1")
-        whole = CooChunk(np.ascontiguousarray(cell), np.ascontiguousarray(gene), np.ascontiguousarray(value))
+        whole = CooChunk(np.ascontiguousarray(cell), np.ascontiguousarray(gene), np.ascontiguousarray(value), 0)
         self._fragments = [_ArrayFragment(whole.slice(lo, min(lo + max_rows_per_file, len(whole))))
                            for lo in range(0, max(len(whole), 1), max_rows_per_file)]
         self._whole = whole
@@ -140,6 +150,7 @@ class _ArrowFileFragment(Fragment):
     def __init__(self, path: str):
         self.path = path
         self._rows = None
+        self.row_lo: int | None = None      # set by the source: rows of the preceding fragments
 
     def _open(self):
         import pyarrow as pa
@@ -153,14 +164,20 @@ class _ArrowFileFragment(Fragment):
         return self._rows
 
     def to_table(self) -> CooChunk:
-        return chunk_from_frame(self._open().read_all().combine_chunks())
+        out = chunk_from_frame(self._open().read_all().combine_chunks())
+        out.row_lo = self.row_lo
+        return out
 
     def to_batches(self, batch_size: int = 8192) -> Iterator[CooChunk]:
         rd = self._open()
+        pos = 0
         for i in range(rd.num_record_batches):
             rb = rd.get_batch(i)
             for lo in range(0, rb.num_rows, batch_size):
-                yield chunk_from_frame(rb.slice(lo, min(batch_size, rb.num_rows - lo)))
+                out = chunk_from_frame(rb.slice(lo, min(batch_size, rb.num_rows - lo)))
+                out.row_lo = None if self.row_lo is None else self.row_lo + pos + lo
+                yield out
+            pos += rb.num_rows
 
 
 class ArrowExpressionSource(ExpressionSource):
@@ -172,6 +189,10 @@ class ArrowExpressionSource(ExpressionSource):
         if not files:
             raise FileNotFoundError(f"no fragment-*.arrow files under {path}")
         self._fragments = [_ArrowFileFragment(f) for f in files]
+        pos = 0
+        for f in self._fragments:            # fragments are consecutive row ranges of the table, in file order
+            f.row_lo = pos
+            pos += f.count_rows()
 
     def get_fragments(self) -> list[Fragment]:
         return list(self._fragments)
@@ -197,18 +218,25 @@ def write_arrow_dataset(path: str, cell: np.ndarray, gene: np.ndarray, value: np
 
 # ------------------------------------------------------------------------------ Lance (optional)
 class _LanceFragment(Fragment):
-    def __init__(self, frag: Any):
+    def __init__(self, frag: Any, row_lo: int | None = None):
         self._frag = frag
+        self.row_lo = row_lo
 
     def count_rows(self) -> int:
         return int(self._frag.count_rows())
 
     def to_table(self) -> CooChunk:
-        return chunk_from_frame(self._frag.to_table(columns=list(COLUMNS)).combine_chunks())
+        out = chunk_from_frame(self._frag.to_table(columns=list(COLUMNS)).combine_chunks())
+        out.row_lo = self.row_lo
+        return out
 
     def to_batches(self, batch_size: int = 8192) -> Iterator[CooChunk]:
+        pos = 0
         for rb in self._frag.to_batches(batch_size=batch_size, columns=list(COLUMNS)):
-            yield chunk_from_frame(rb)
+            out = chunk_from_frame(rb)
+            out.row_lo = None if self.row_lo is None else self.row_lo + pos
+            pos += len(out)
+            yield out
 
 
 class LanceExpressionSource(ExpressionSource):
@@ -223,7 +251,11 @@ class LanceExpressionSource(ExpressionSource):
             self._ds = path_or_dataset
 
     def get_fragments(self) -> list[Fragment]:
-        return [_LanceFragment(f) for f in self._ds.get_fragments()]
+        out, pos = [], 0
+        for f in self._ds.get_fragments():       # dataset order = row order (the converter appends cell-major)
+            out.append(_LanceFragment(f, pos))
+            pos += int(f.count_rows())
+        return out
 
     def count_rows(self) -> int:
         return int(self._ds.count_rows())

@@ -290,3 +290,36 @@ def test_reference_tiny_adata_matrix_all_tokenizers(engine):
             assert_same(g.attention_mask.cpu().numpy(), w[1], f"{mode} k={k} mask")
             if w[2] is not None:
                 assert_same(g.values.cpu().numpy(), w[2], f"{mode} k={k} values")
+
+
+@pytest.mark.parametrize("mode", ["mos", "fragment", "sequential"])
+def test_loader_with_cell_start_index_gives_identical_batches(data, mode):
+    """use_cell_start_index=True: cell boundaries from _cell_start_index, the cell column never reaches the GPU;
+    batch composition, order and every token are the same as on the default path."""
+    kw = dict(use_mixture_of_scanners=(mode == "mos"), by_fragment=(mode != "sequential"), tokenizer_type="scgpt", batch_size=40,
+              max_genes=48, n_expression_bins=51, vocab_size=5000, prefetch_batch_size=1000, n_scanners=3, verbose=False)
+    runs = []
+    for flag in (False, True):
+        np.random.seed(11)                              # same mixture-of-scanners draws
+        loader = SLAFDataLoader(_array(data), use_cell_start_index=flag, **kw)
+        runs.append([{k: v.cpu().numpy() for k, v in b.items()} for b in loader])
+        if flag:
+            t = loader._dataset.batch_processor._engine.timing()
+            assert t["csr_ms"] == 0.0                     # no CSR build ran
+    assert len(runs[0]) == len(runs[1])
+    for a, b in zip(*runs):
+        for k in ("cell_ids", "input_ids", "values", "attention_mask"):
+            assert np.array_equal(a[k], b[k]), k
+    assert sorted(int(c) for b in runs[1] for c in b["cell_ids"]) == list(range(N_CELLS))
+
+
+def test_cell_start_index_mismatch_is_detected(data):
+    arr = _array(data)
+    arr._cell_start_index = arr._cell_start_index.copy()
+    arr._cell_start_index[1:] += 3                         # wrong offsets: the boundary probes must notice
+    tok = GeneformerTokenizer(arr, max_genes=32)
+    proc = PrefetchBatchProcessor(arr, RandomShuffle(), tok, use_mixture_of_scanners=False, by_fragment=True, verbose=False,
+                                  use_cell_start_index=True)
+    with pytest.raises(ValueError, match="_cell_start_index does not describe"):
+        proc.load_prefetch_batch()
+    proc.close()

@@ -311,3 +311,33 @@ def test_reference_cross_fragment_fixture_raw_epoch(mos):
     assert len({(int(c), int(g)) for c, g in zip(cells, genes)}) == len(cells) == 16
     emitted = [c for b in batches for c in b.cell_integer_ids]
     assert sorted(emitted) == list(range(6))
+
+
+def test_segments_from_cell_start_index_match_the_column():
+    """The CSI-driven segment table (no look at the cell column) equals the runs of the column itself: whole fragments,
+    consecutive pieces that continue a cell, unrelated pieces, cells without any row."""
+    from slaf_b200 import synthetic
+    from slaf_b200.ml.datasets import _runs, _segments_from_csi
+    from slaf_b200.ml.sources import ArrayExpressionSource
+
+    b = synthetic.make_batch(200, 500, 30, seed=3, min_nnz=2)
+    # insert cells without rows: ids shift, CSI gets repeated offsets
+    empty_after = {17, 18, 90}
+    new_id, csi = [], [0]
+    nid = 0
+    for c in range(b.n_cells):
+        new_id.append(nid)
+        csi.append(int(b.cell_start[c + 1]))
+        nid += 1
+        if c in empty_after:
+            csi.append(int(b.cell_start[c + 1]))
+            nid += 1
+    cell = np.asarray(new_id, np.uint32)[b.cell]
+    csi = np.asarray(csi, np.int64)
+    src = ArrayExpressionSource(cell, b.gene, b.value, 611)
+    frs = [f.to_table() for f in src.get_fragments()]
+    for pieces in ([frs[0]], [frs[2], frs[3]], [frs[4].slice(5, 300), frs[1]], frs, [frs[0].slice(0, 1)], list(frs[5].slice(0, 40).slice(i, i + 8) for i in range(0, 40, 8))):
+        st, ids = _segments_from_csi(pieces, csi)
+        cat = np.concatenate([p.cell for p in pieces])
+        s0, _e0, i0 = _runs(cat)
+        assert np.array_equal(st[:-1], s0) and st[-1] == len(cat) and np.array_equal(ids, i0)
