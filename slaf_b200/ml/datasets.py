@@ -187,6 +187,7 @@ def _segments_from_csi(pieces: list[CooChunk], csi: np.ndarray) -> tuple[np.ndar
     Returns (seg_start uint32 [C + 1], seg_cell int64 [C]).  O(cells), vectorised."""
     starts, ids = [], []
     pos = 0
+    last_cell = None
     for p in pieces:
         n = len(p)
         if n == 0:
@@ -199,10 +200,13 @@ def _segments_from_csi(pieces: list[CooChunk], csi: np.ndarray) -> tuple[np.ndar
         nonempty = csi[cells + 1] > first_row                      # cells without rows (or not reaching into this piece) have no segment
         cells, first_row = cells[nonempty], first_row[nonempty]
         st = first_row - lo + pos
-        if ids and len(cells) and ids[-1][-1] == cells[0] and st[0] == pos:
-            cells, st = cells[1:], st[1:]                            # the previous piece's last cell continues here: one segment
+        if len(cells):
+            new_last = int(cells[-1])
+            if last_cell is not None and last_cell == int(cells[0]) and st[0] == pos:
+                cells, st = cells[1:], st[1:]                        # the previous piece's last cell continues here: one segment
+            last_cell = new_last
         starts.append(st)
-        ids.append(cells if len(cells) else np.zeros(0, np.int64))
+        ids.append(cells)
         pos += n
     ids = [i for i in ids if len(i)]
     starts = [s_ for s_ in starts if len(s_)]
