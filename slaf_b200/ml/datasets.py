@@ -571,11 +571,19 @@ class PrefetchBatchProcessor:
         if len(np.unique(seg_cell)) != len(seg_cell):                      # a cell in two separated places: splice (views) first
             pieces = _regroup_segments(pieces, seg_start, seg_cell)
             seg_start, seg_cell = _segments_from_csi(pieces, csi)
-        for p in pieces:                                                     # O(1) consistency probes against the rows themselves
-            lo = int(p.row_lo)
-            if int(p.cell[0]) != int(np.searchsorted(csi, lo, side="right")) - 1 or \
-                    int(p.cell[-1]) != int(np.searchsorted(csi, lo + len(p) - 1, side="right")) - 1:
-                raise ValueError("_cell_start_index does not describe the expression rows (cell ids at a chunk boundary differ)")
+        # cheap consistency probes against the rows themselves: at up to 64 evenly spaced segment heads (and the last row) the
+        # cell column must show exactly that id starting exactly there -- a shifted or stale index is caught, O(1) per batch
+        offs = np.concatenate(([0], np.cumsum([len(p) for p in pieces])))
+        C = len(seg_cell)
+        for j in np.unique(np.linspace(0, max(C - 1, 0), num=min(C, 64)).astype(np.int64)) if C else []:
+            row = int(seg_start[j])
+            k = int(np.searchsorted(offs, row, side="right")) - 1
+            a = row - int(offs[k])
+            ok = int(pieces[k].cell[a]) == int(seg_cell[j]) and (a == 0 or int(pieces[k].cell[a - 1]) != int(seg_cell[j]))
+            if not ok:
+                raise ValueError("_cell_start_index does not describe the expression rows (a cell does not start where the index says)")
+        if C and int(pieces[-1].cell[-1]) != int(seg_cell[-1]):
+            raise ValueError("_cell_start_index does not describe the expression rows (last cell id differs)")
         signed = pieces[0].cell.dtype == np.int32
         direct = all(len(p) <= self.SMALL_PIECE_ROWS or (is_page_locked(p.gene) and is_page_locked(p.value)) for p in pieces)
         if direct and len(pieces) <= 256:
