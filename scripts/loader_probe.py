@@ -34,10 +34,10 @@ def timed(name, fn):
     return wrap
 
 
-for epoch_mode in ("fragment", "mos"):
+for epoch_mode in ("fragment", "mos", "fragment+csi", "mos+csi"):
     proc = PrefetchBatchProcessor(arr, RandomShuffle(), tok, n_expression_bins=51, use_binned_expressions=True, n_epochs=3,
-                                  use_mixture_of_scanners=(epoch_mode == "mos"), by_fragment=True, verbose=False, n_scanners=4,
-                                  prefetch_batch_size=4194304)
+                                  use_mixture_of_scanners=epoch_mode.startswith("mos"), by_fragment=True, verbose=False, n_scanners=4,
+                                  prefetch_batch_size=4194304, use_cell_start_index=epoch_mode.endswith("csi"))
     proc._next_pieces = timed("read", proc._next_pieces)
     proc._submit = timed("submit", proc._submit)
     proc._stash_partials = timed("stash", proc._stash_partials)
