@@ -195,7 +195,9 @@ def run_reference(args, w):
     if rank != 0:
         return
     cores = len(os.sched_getaffinity(0))
-    sample = 1024 * cores
+    # a bounded sample per step, shrunk for long runs so that the whole arm stays within a few minutes
+    per_core = max(64, int(1024 * min(1.0, 40.0 / max(1, args.steps))))
+    sample = per_core * cores
     rates = []
     for _ in range(args.warmup):
         cpu_port_rate(w, max(cores * 16, 64), cores)
@@ -211,7 +213,7 @@ def run_reference(args, w):
         "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
         "config": {"workload": w["name"], "cells_per_step": sample},
         "cpu_baseline": {"value": rate, "unit": "cells/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} steps x {sample} cells ({cores} processes x 1024 cells), numpy window + per-cell Python tokenizer loop (reference structure; polars not installable)",
+                         "sample": f"{args.steps} steps x {sample} cells ({cores} processes x {per_core} cells), numpy window + per-cell Python tokenizer loop (reference structure; polars not installable)",
                          "c_oracle_cells_per_s": c_rate, "c_oracle_threads": c_thr},
         "e2e": {"value": rate, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t_all,
