@@ -219,7 +219,11 @@ int launch_fast(slafb_ctx *ctx, const TokArgs &a, cudaStream_t st, bool *launche
     fa.gcap = (limit + 15u + 7u) & ~7u;
     // value stage: whole cells up to ~4k rows for uint16; float32 rows are twice as wide, so the stage holds 2,560 and the
     // (rarer) longer cells read their tail from global memory -- more CTAs per SM matter more than staging every row
-    const uint32_t vmin = sizeof(ValT) == 2 ? 4104u : 2568u;
+    uint32_t vmin = sizeof(ValT) == 2 ? 4104u : 2568u;
+    if (const char *env = getenv("SLAFB_VCAP")) {   // tuning knob: rows of values staged per cell
+        const long v = atol(env);
+        if (v >= 256 && v <= 16384) vmin = (uint32_t)(v + 7) & ~7u;
+    }
     fa.vcap = fa.gcap > vmin ? fa.gcap : vmin;
     fa.vstar_table = ctx->vstar_table;
     fa.ticket = a.work_counters + 2;   // slot counters[4], zeroed by K1 together with the work-list counters

@@ -42,16 +42,16 @@ class Window(ABC):
         if cols.n_rows == 0:
             return frames.build_grouped(cols, schema, np.zeros(0, np.int64), np.zeros(1, np.int64), np.zeros(0, np.int64),
                                         np.zeros(0, np.float64) if with_values else None, mode == "scgpt_binned")
-        eng = runtime.engine_for(cols.n_rows, device=self.device)
         cell, gene, value = cols.cell, cols.gene, cols.value
         kw = dict(mode=mode, max_items=int(max_items), n_bins=int(n_bins), min_percentile=min_percentile, check_contiguous=True)
-        try:
-            res = eng.window(cell, gene, value, **kw)
-        except N.SlafB200Error as err:
-            if err.code != N.ERR_NONCONTIGUOUS:
-                raise
-            cell, gene, value = regroup_contiguous(cell, gene, value)   # partition_by semantics for split cells
-            res = eng.window(cell, gene, value, **kw)
+        with runtime.session(cols.n_rows, device=self.device) as eng:
+            try:
+                res = eng.window(cell, gene, value, **kw)
+            except N.SlafB200Error as err:
+                if err.code != N.ERR_NONCONTIGUOUS:
+                    raise
+                cell, gene, value = regroup_contiguous(cell, gene, value)   # partition_by semantics for split cells
+                res = eng.window(cell, gene, value, **kw)
         exprs = res.exprs.cpu().numpy() if (with_values and res.exprs is not None) else None
         return frames.build_grouped(cols, schema, res.cell_ids.cpu().numpy(), res.offsets.cpu().numpy(),
                                     res.genes.cpu().numpy(), exprs, mode == "scgpt_binned")

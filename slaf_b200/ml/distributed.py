@@ -157,14 +157,14 @@ class BatchProcessor:
         if fused is not None:
             cols = frames.extract(complete, s)
             cell, gene, value = cols.cell, cols.gene, cols.value
-            eng = runtime.engine_for(len(cell), device=self.tokenizer.tokenizer.device)
             kw = dict(shuffle_seed=seed if self.shuffle is not None else None, check_contiguous=True, **fused)
-            try:
-                out = eng.tokenize(cell, gene, value, **kw)
-            except N.SlafB200Error as err:
-                if err.code != N.ERR_NONCONTIGUOUS:
-                    raise
-                out = eng.tokenize(*regroup_contiguous(cell, gene, value), **kw)      # partition_by semantics for split groups
+            with runtime.session(len(cell), device=self.tokenizer.tokenizer.device) as eng:
+                try:
+                    out = eng.tokenize(cell, gene, value, **kw)
+                except N.SlafB200Error as err:
+                    if err.code != N.ERR_NONCONTIGUOUS:
+                        raise
+                    out = eng.tokenize(*regroup_contiguous(cell, gene, value), **kw)      # partition_by semantics for split groups
             keys = out.cell_ids.cpu().tolist()
             samples = []
             for i, key in enumerate(keys):

@@ -223,14 +223,14 @@ class ScGPTTokenizer(SLAFTokenizer):
         x = np.asarray(expression_values)
         if x.size == 0:
             return np.array([], dtype=int)
-        eng = runtime.engine_for(x.size, 1, device=self.device)
-        dev = eng.device
-        offs = torch.tensor([0, x.size], dtype=torch.int64, device=dev)
-        genes = torch.zeros(x.size, dtype=torch.int64, device=dev)
-        exprs = torch.from_numpy(x.astype(np.float32).astype(np.float64)).to(dev)
-        _, _, vals = eng.tokenize_lists(offs, genes, exprs, scgpt=True, exprs_are_int=False, max_genes=int(x.size),
-                                        n_bins=self.n_expression_bins, vocab_size=self.expr_bin_start)
-        return vals[0, 1:1 + x.size].cpu().numpy().astype(int)
+        with runtime.session(x.size, 1, device=self.device) as eng:
+            dev = eng.device
+            offs = torch.tensor([0, x.size], dtype=torch.int64, device=dev)
+            genes = torch.zeros(x.size, dtype=torch.int64, device=dev)
+            exprs = torch.from_numpy(x.astype(np.float32).astype(np.float64)).to(dev)
+            _, _, vals = eng.tokenize_lists(offs, genes, exprs, scgpt=True, exprs_are_int=False, max_genes=int(x.size),
+                                            n_bins=self.n_expression_bins, vocab_size=self.expr_bin_start)
+            return vals[0, 1:1 + x.size].cpu().numpy().astype(int)
 
     def tokenize(self, gene_sequences, expr_sequences=None):
         if gene_sequences is None or len(gene_sequences) == 0:
@@ -251,21 +251,21 @@ class ScGPTTokenizer(SLAFTokenizer):
         _, xflat = _flatten(exprs_t, np.float64)
         if not is_int[nonempty].any():
             xflat = xflat.astype(np.float32).astype(np.float64)   # np.array(exprs, dtype=np.float32), tokenizers.py:446
-        eng = runtime.engine_for(max(int(offs[-1]), 1), B, device=self.device)
-        dev = eng.device
-        d_offs, d_genes, d_exprs = (torch.from_numpy(a).to(dev) for a in (offs, gflat, xflat))
         kw = dict(scgpt=True, max_genes=self.max_genes, n_bins=self.n_expression_bins, vocab_size=self.expr_bin_start)
         all_int = bool(is_int[nonempty].all()) if nonempty.any() else False
         all_float = not is_int[nonempty].any()
-        if all_int or all_float:
-            ids, mask, vals = eng.tokenize_lists(d_offs, d_genes, d_exprs, exprs_are_int=all_int, **kw)
-        else:
-            # mixed Python int / float cells in one call: run both branches, select per cell
-            x32 = torch.from_numpy(xflat.astype(np.float32).astype(np.float64)).to(dev)
-            ids, mask, vals_i = eng.tokenize_lists(d_offs, d_genes, d_exprs, exprs_are_int=True, **kw)
-            _, _, vals_f = eng.tokenize_lists(d_offs, d_genes, x32, exprs_are_int=False, **kw)
-            sel = torch.from_numpy(is_int).to(dev)[:, None]
-            vals = torch.where(sel, vals_i, vals_f)
+        with runtime.session(max(int(offs[-1]), 1), B, device=self.device) as eng:
+            dev = eng.device
+            d_offs, d_genes, d_exprs = (torch.from_numpy(a).to(dev) for a in (offs, gflat, xflat))
+            if all_int or all_float:
+                ids, mask, vals = eng.tokenize_lists(d_offs, d_genes, d_exprs, exprs_are_int=all_int, **kw)
+            else:
+                # mixed Python int / float cells in one call: run both branches, select per cell
+                x32 = torch.from_numpy(xflat.astype(np.float32).astype(np.float64)).to(dev)
+                ids, mask, vals_i = eng.tokenize_lists(d_offs, d_genes, d_exprs, exprs_are_int=True, **kw)
+                _, _, vals_f = eng.tokenize_lists(d_offs, d_genes, x32, exprs_are_int=False, **kw)
+                sel = torch.from_numpy(is_int).to(dev)[:, None]
+                vals = torch.where(sel, vals_i, vals_f)
         return self._place(ids, mask, vals)
 
     def decode_tokens(self, tokens: list[int]) -> dict[str, Any]:
@@ -296,10 +296,10 @@ class GeneformerTokenizer(SLAFTokenizer):
         if gene_sequences is None or len(gene_sequences) == 0:
             raise ValueError("Gene sequences cannot be empty")
         offs, gflat = _flatten(gene_sequences, np.int64)
-        eng = runtime.engine_for(max(int(offs[-1]), 1), len(gene_sequences), device=self.device)
-        dev = eng.device
-        ids, mask, _ = eng.tokenize_lists(torch.from_numpy(offs).to(dev), torch.from_numpy(gflat).to(dev), None,
-                                          scgpt=False, exprs_are_int=True, max_genes=self.max_genes)
+        with runtime.session(max(int(offs[-1]), 1), len(gene_sequences), device=self.device) as eng:
+            dev = eng.device
+            ids, mask, _ = eng.tokenize_lists(torch.from_numpy(offs).to(dev), torch.from_numpy(gflat).to(dev), None,
+                                              scgpt=False, exprs_are_int=True, max_genes=self.max_genes)
         ids, mask = self._place(ids, mask)
         return ids, mask, None
 

@@ -3,12 +3,13 @@
 from __future__ import annotations
 
 import threading
+from contextlib import contextmanager
 
 import torch
 
 from .engine import HotPathEngine
 
-_lock = threading.Lock()
+_lock = threading.RLock()
 _engines: dict[int, HotPathEngine] = {}
 
 
@@ -40,8 +41,21 @@ def engine_for(n_rows: int, n_cells: int | None = None, device=None) -> HotPathE
         return eng
 
 
+@contextmanager
+def session(n_rows: int, n_cells: int | None = None, device=None):
+    """The shared engine of `device`, held exclusively for the duration of one facade call: a context is single-threaded
+    by contract and may be replaced by a larger one between calls, so facade calls from different threads take turns."""
+    with _lock:
+        yield engine_for(n_rows, n_cells, device)
+
+
 def shutdown() -> None:
     with _lock:
         for eng in _engines.values():
             eng.close()
         _engines.clear()
+
+
+import atexit  # noqa: E402
+
+atexit.register(shutdown)
