@@ -35,6 +35,20 @@
 
 namespace slafb {
 
+// output stores of K2: SLAFB_STORE_MODE 0 = default (write-back), 1 = st.global.cs (streaming), 2 = st.global.wt
+#ifndef SLAFB_STORE_MODE
+#define SLAFB_STORE_MODE 0
+#endif
+__device__ __forceinline__ void store_pair(long long *p, long long x0, long long x1) {
+#if SLAFB_STORE_MODE == 1
+    __stcs(reinterpret_cast<longlong2 *>(p), make_longlong2(x0, x1));
+#elif SLAFB_STORE_MODE == 2
+    __stwt(reinterpret_cast<longlong2 *>(p), make_longlong2(x0, x1));
+#else
+    *reinterpret_cast<longlong2 *>(p) = make_longlong2(x0, x1);
+#endif
+}
+
 constexpr int kTokThreads = 256;
 constexpr int kGroup = 8;                           // rows per thread per chunk (one 128-bit load of u16)
 constexpr int kChunkRows = kTokThreads * kGroup;    // 2048 rows staged per iteration
@@ -1209,7 +1223,7 @@ __global__ void __launch_bounds__(kFastThreads, 2048 / kFastThreads) tokenize_ce
                 long long x0, x1;
                 if constexpr (sizeof(GeneT) == 2) { x0 = (long long)sg[gi] + 4ll; x1 = (long long)sg[gi + 1] + 4ll; }
                 else { x0 = (long long)(int32_t)sg[gi] + 4ll; x1 = (long long)(int32_t)sg[gi + 1] + 4ll; }
-                *reinterpret_cast<longlong2 *>(ids_al + 2u * p) = make_longlong2(x0, x1);
+                store_pair(ids_al + 2u * p, x0, x1);
             }
             if constexpr (BINNED && !U16) {
                 __syncthreads();                                 // warp 0 has published the bin threshold
@@ -1231,15 +1245,15 @@ __global__ void __launch_bounds__(kFastThreads, 2048 / kFastThreads) tokenize_ce
                         y0 = value_token<ValT, MODE>(raw_bits(sv[gi]), a, m_f64, m_f32);
                         y1 = value_token<ValT, MODE>(raw_bits(sv[gi + 1]), a, m_f64, m_f32);
                     }
-                    *reinterpret_cast<longlong2 *>(vals_al + 2u * p) = make_longlong2(y0, y1);
+                    store_pair(vals_al + 2u * p, y0, y1);
                 }
             }
             // PAD pairs: both tokens beyond SEP
             const uint32_t p_pad = (n_emit + 2u + off + 1u) >> 1;         // smallest p with t0 >= n_emit + 2
             const uint32_t p_full_end = (L + off) >> 1;                   // pairs whose second token is < L
             for (uint32_t p = p_pad + tid; p < p_full_end; p += kFastThreads) {
-                *reinterpret_cast<longlong2 *>(ids_al + 2u * p) = make_longlong2(0ll, 0ll);
-                if constexpr (SCGPT) *reinterpret_cast<longlong2 *>(vals_al + 2u * p) = make_longlong2(0ll, 0ll);
+                store_pair(ids_al + 2u * p, 0ll, 0ll);
+                if constexpr (SCGPT) store_pair(vals_al + 2u * p, 0ll, 0ll);
             }
             // boundary pairs (CLS, the last gene / SEP / first PAD, row ends): generic, a handful per row
             {

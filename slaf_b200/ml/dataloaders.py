@@ -24,8 +24,26 @@ from __future__ import annotations
 
 from typing import Any
 
+import torch
+
 from .datasets import SLAFIterableDataset
 from .tokenizers import GeneformerTokenizer, ScGPTTokenizer
+
+
+def get_optimal_device():
+    """reference: slaf/ml/dataloaders.py:31-78.  Here the answer can only be a CUDA device: the path has no CPU form."""
+    return torch.device("cuda") if torch.cuda.is_available() else None
+
+
+def get_device_info() -> dict:
+    """reference: slaf/ml/dataloaders.py:81-154 (same keys)."""
+    info = {"torch_available": True, "cuda_available": torch.cuda.is_available(), "mps_available": False,
+            "optimal_device": str(get_optimal_device())}
+    if torch.cuda.is_available():
+        info["cuda_device_count"] = torch.cuda.device_count()
+        info["cuda_device_name"] = torch.cuda.get_device_name(0)
+        info["cuda_device_capability"] = torch.cuda.get_device_capability(0)
+    return info
 
 
 class SLAFDataLoader:
