@@ -143,3 +143,49 @@ def normalisation_vector(total: torch.Tensor, count: torch.Tensor) -> torch.Tens
     the integer reduce, so every rank computes the bit-identical vector."""
     mean = total.to(torch.float64) / count.clamp(min=1).to(torch.float64)
     return torch.where(count > 0, mean, torch.ones_like(mean)).to(torch.float32)
+
+
+# ------------------------------------------------------------------------------ names of the reference's slaf.distributed
+class PartitionAssignment:
+    """reference: slaf/distributed/coordinator.py:14-19."""
+
+    def __init__(self, worker_id: str, partition_indices: list[int]):
+        self.worker_id = worker_id
+        self.partition_indices = partition_indices
+
+
+class Coordinator:
+    """reference: slaf/distributed/coordinator.py:22-80 -- seeded shuffle of the partition (fragment) indices, contiguous
+    split, remainder to the first workers.  ``data_source`` needs ``get_partition_count()`` (or is an ExpressionSource)."""
+
+    def __init__(self, data_source: Any, n_workers: int):
+        self.data_source = data_source
+        self.n_workers = n_workers
+        self.total_partitions = (data_source.get_partition_count() if hasattr(data_source, "get_partition_count")
+                                 else len(data_source.get_fragments()))
+
+    def assign_partitions(self, seed: int = 42) -> dict[str, PartitionAssignment]:
+        parts = assign_fragments(self.total_partitions, self.n_workers, seed=seed, shuffle=True)
+        return {f"worker_{i}": PartitionAssignment(f"worker_{i}", p) for i, p in enumerate(parts)}
+
+
+def __getattr__(name: str):
+    # BatchProcessor / GroupBoundaryHandler / Window / Shuffle / DataSchema under the reference's package name, resolved
+    # lazily (slaf_b200.ml imports this module for the sharding helpers)
+    if name in ("BatchProcessor", "GroupBoundaryHandler"):
+        from .ml import distributed as _d
+
+        return getattr(_d, name)
+    if name == "Window":
+        from .ml.aggregators import GenericWindow
+
+        return GenericWindow
+    if name == "Shuffle":
+        from .ml.samplers import GenericShuffle
+
+        return GenericShuffle
+    if name == "DataSchema":
+        from .core.tabular_schema import DataSchema
+
+        return DataSchema
+    raise AttributeError(name)

@@ -125,3 +125,16 @@ def test_allreduce_argument_checks_and_single_process_identity():
         allreduce_gene_stats(torch.zeros(4, dtype=torch.int64))
     with pytest.raises(ValueError):
         allreduce_gene_stats(torch.zeros((2, 4), dtype=torch.float32))
+
+
+def test_coordinator_mirror_matches_reference_assignment():
+    """slaf/distributed/coordinator.py:40-80: seeded shuffle of the partition indices, contiguous split, remainder first."""
+    from slaf_b200 import distributed as D
+
+    src = ArrayExpressionSource(np.zeros(100, np.uint32), np.zeros(100, np.uint16), np.zeros(100, np.uint16), 10)
+    got = D.Coordinator(src, 3).assign_partitions(seed=42)
+    random.seed(42)
+    idx = list(range(10))
+    random.shuffle(idx)
+    assert [got[f"worker_{i}"].partition_indices for i in range(3)] == [idx[:4], idx[4:7], idx[7:]]
+    assert D.Window is not None and D.Shuffle is not None and D.BatchProcessor is not None and D.DataSchema is not None
