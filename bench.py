@@ -344,7 +344,9 @@ def main():
     kw = dict(mode=w["mode"], max_genes=w["max_genes"], n_bins=w["n_bins"], vocab_size=w["vocab"])
     if w.get("min_percentile") is not None:
         kw["min_percentile"] = w["min_percentile"]
-    timing_every = int(os.environ.get("SLAFB_BENCH_TIMING_EVERY", "8"))
+    # per-kernel CUDA events on every 8th batch (each record is a stream operation); short runs time every batch so
+    # that the roofline still has launches to average
+    timing_every = int(os.environ.get("SLAFB_BENCH_TIMING_EVERY", "8" if args.steps >= 24 else "1"))
 
     dev_cols = [(torch.from_numpy(b.cell).to(dev), torch.from_numpy(b.gene).to(dev), torch.from_numpy(b.value).to(dev)) for b in batches]
     stats = None
