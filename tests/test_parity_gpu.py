@@ -387,3 +387,22 @@ def test_fuzz_random_shapes_and_parameters(engine, seed):
     cols = (cell, gene, value) if rng.integers(2) else (to_dev(cell), to_dev(gene), to_dev(value))
     got = engine.tokenize(*cols, mode=mode, max_genes=max_genes, **kw, **okw)
     compare(got, want, mode)
+
+
+def test_many_tiny_cells_take_the_dense_head_path(engine):
+    """Hundreds of thousands of 1-3 row cells: every CSR-build span holds far more segment heads than its shared-memory
+    list (the replay path with a block scan per tile), the fast kernel sees tiny segments, the permutation is large."""
+    rng = np.random.default_rng(77)
+    C = 120_000
+    lens = rng.integers(1, 4, C)
+    cell = np.repeat(np.arange(C, dtype=np.uint32) * 3 + 5, lens)
+    gene = rng.integers(0, 60000, cell.size).astype(np.uint16)
+    value = rng.integers(1, 9, cell.size).astype(np.uint16)
+    for mode in ("geneformer", "scgpt_binned"):
+        want = c_oracle.tokenize(cell, gene, value, mode, 6, perm=py_perm(3, C), n_bins=10, vocab_size=70000)
+        got = engine.tokenize(to_dev(cell), to_dev(gene), to_dev(value), mode=mode, max_genes=6, n_bins=10, vocab_size=70000, shuffle_seed=3)
+        compare(got, want, mode)
+    # float32 values and int32 ids through the same shapes
+    want = c_oracle.tokenize(cell.astype(np.int32), gene.astype(np.int32), value.astype(np.float32), "scgpt_raw", 2, n_bins=10, vocab_size=70000)
+    got = engine.tokenize(cell.astype(np.int32), gene.astype(np.int32), value.astype(np.float32), mode="scgpt_raw", max_genes=2, n_bins=10, vocab_size=70000)
+    compare(got, want, "scgpt_raw")
