@@ -253,89 +253,15 @@ constexpr int kCsrBlock = kCsrConsumers + 32;      // + 1 producer warp
 constexpr int kCsrStageRows = kCsrConsumers * 8;   // 2048 rows = 8 KiB per stage
 constexpr int kCsrStages = 4;
 
-__global__ void __launch_bounds__(kCsrBlock) csr_build_kernel(const CsrArgs a) {
-    __shared__ __align__(128) uint32_t s_stage[kCsrStages][kCsrStageRows + 4];   // [0..3] = the 4 rows before the tile
-    __shared__ __align__(8) uint64_t s_full[kCsrStages], s_empty[kCsrStages];
-    __shared__ uint32_t s_list[kCsrListCap], s_sorted[kCsrListCap];
-    __shared__ uint32_t s_count, s_span, s_base, s_ws[16], s_part[kCsrBlock / 32];
+// The part of K1 after the scan: order the span's heads, publish the count, gather the counts of all preceding spans,
+// write the span's rows of the segment table.  Shared by the TMA-fed and the direct-load variant of the kernel.
+template <int BLOCK>
+__device__ __forceinline__ void csr_finish(const CsrArgs &a, uint32_t span, uint32_t r_beg, uint32_t r_end, uint32_t *s_list,
+                                           uint32_t *s_sorted, uint32_t &s_count, uint32_t &s_base, uint32_t *s_ws, uint32_t *s_part) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) {
-        s_span = atomicAdd(a.ticket, 1u) - a.ticket_base;
-        s_count = 0u;
-        for (int i = 0; i < kCsrStages; i++) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], kCsrConsumers / 32); }
-        mbar_fence_init();
-    }
-    __syncthreads();
-    const uint32_t span = s_span, R = a.n_rows;
-    const unsigned long long sb = (unsigned long long)span * a.rows_per_cta;
-    const uint32_t r_beg = sb < R ? (uint32_t)sb : R;
-    const uint32_t r_end = (sb + a.rows_per_cta < R) ? (uint32_t)(sb + a.rows_per_cta) : R;
-    const uint32_t n_tiles = (r_end - r_beg + kCsrStageRows - 1) / kCsrStageRows;
-
-    if (warp == kCsrConsumers / 32) {
-        // ---------------- producer warp: keep kCsrStages bulk copies in flight
-        if (lane == 0) {
-            for (uint32_t t = 0; t < n_tiles; t++) {
-                const uint32_t st = t % kCsrStages;
-                if (t >= (uint32_t)kCsrStages) mbar_wait(&s_empty[st], ((t / kCsrStages) - 1u) & 1u);
-                const uint32_t t0 = r_beg + t * kCsrStageRows;
-                const uint32_t rows = min((uint32_t)kCsrStageRows, r_end - t0) & ~3u;   // 16-byte granules; a ragged tail is read directly
-                const uint32_t lead = t0 >= 4u ? 4u : 0u;                               // the row before the tile, for the first compare
-                const uint32_t bytes = (rows + lead) * 4u;
-                if (bytes) {
-                    mbar_arrive_expect_tx(&s_full[st], bytes);
-                    bulk_g2s(&s_stage[st][4u - lead], a.cell + t0 - lead, bytes, &s_full[st]);
-                } else {
-                    mbar_arrive(&s_full[st]);
-                }
-            }
-        }
-    } else {
-        // ---------------- consumer warps
-        for (uint32_t t = 0; t < n_tiles; t++) {
-            const uint32_t st = t % kCsrStages;
-            mbar_wait(&s_full[st], (t / kCsrStages) & 1u);
-            const uint32_t t0 = r_beg + t * kCsrStageRows;
-            const uint32_t rows = min((uint32_t)kCsrStageRows, r_end - t0);
-            const uint32_t rows4 = rows & ~3u;
-            const uint32_t i0 = (uint32_t)tid * 8u;          // first of my 8 rows inside the tile
-            if (i0 < rows) {
-                uint32_t c[8], prev;
-                const uint32_t *sp = &s_stage[st][4u + i0];
-                if (i0 + 8u <= rows4) {
-                    const uint4 q0 = *reinterpret_cast<const uint4 *>(sp), q1 = *reinterpret_cast<const uint4 *>(sp + 4);
-                    c[0] = q0.x; c[1] = q0.y; c[2] = q0.z; c[3] = q0.w; c[4] = q1.x; c[5] = q1.y; c[6] = q1.z; c[7] = q1.w;
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 8; e++) {
-                        const uint32_t i = i0 + e;
-                        c[e] = (i < rows4) ? sp[e] : ((i < rows) ? __ldg(a.cell + t0 + i) : 0u);
-                    }
-                }
-                const uint32_t r0 = t0 + i0;
-                if (r0 == 0u) prev = ~c[0];                                  // row 0 always opens a segment
-                else prev = sp[-1];                                          // previous row (lead rows for i0 == 0)
-                uint32_t diff = c[0] ^ prev;
-#pragma unroll
-                for (int e = 1; e < 8; e++) diff |= c[e] ^ c[e - 1];
-                if (diff) {                                                   // rare: ~1 segment head per 2000 rows
-                    uint32_t p = prev;
-#pragma unroll
-                    for (int e = 0; e < 8; e++) {
-                        if (i0 + e < rows && c[e] != p) {
-                            const uint32_t k = atomicAdd(&s_count, 1u);
-                            if (k < (uint32_t)kCsrListCap) s_list[k] = r0 + e;
-                        }
-                        p = c[e];
-                    }
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_empty[st]);
-        }
-    }
-    __syncthreads();
-
+    const uint32_t R = a.n_rows;
+    constexpr int kCsrBlock = BLOCK;          // (shadows the namespace constant inside this function)
+    constexpr int kCsrConsumers = 256;
     // ---------------- order the heads of this span
     const uint32_t count = s_count;
     const bool listed = count <= (uint32_t)kCsrListCap;
@@ -424,6 +350,162 @@ __global__ void __launch_bounds__(kCsrBlock) csr_build_kernel(const CsrArgs a) {
             run += tot;
         }
     }
+}
+
+__global__ void __launch_bounds__(kCsrBlock) csr_build_kernel(const CsrArgs a) {
+    __shared__ __align__(128) uint32_t s_stage[kCsrStages][kCsrStageRows + 4];   // [0..3] = the 4 rows before the tile
+    __shared__ __align__(8) uint64_t s_full[kCsrStages], s_empty[kCsrStages];
+    __shared__ uint32_t s_list[kCsrListCap], s_sorted[kCsrListCap];
+    __shared__ uint32_t s_count, s_span, s_base, s_ws[16], s_part[kCsrBlock / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        s_span = atomicAdd(a.ticket, 1u) - a.ticket_base;
+        s_count = 0u;
+        for (int i = 0; i < kCsrStages; i++) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], kCsrConsumers / 32); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const uint32_t span = s_span, R = a.n_rows;
+    const unsigned long long sb = (unsigned long long)span * a.rows_per_cta;
+    const uint32_t r_beg = sb < R ? (uint32_t)sb : R;
+    const uint32_t r_end = (sb + a.rows_per_cta < R) ? (uint32_t)(sb + a.rows_per_cta) : R;
+    const uint32_t n_tiles = (r_end - r_beg + kCsrStageRows - 1) / kCsrStageRows;
+
+    if (warp == kCsrConsumers / 32) {
+        // ---------------- producer warp: keep kCsrStages bulk copies in flight
+        if (lane == 0) {
+            for (uint32_t t = 0; t < n_tiles; t++) {
+                const uint32_t st = t % kCsrStages;
+                if (t >= (uint32_t)kCsrStages) mbar_wait(&s_empty[st], ((t / kCsrStages) - 1u) & 1u);
+                const uint32_t t0 = r_beg + t * kCsrStageRows;
+                const uint32_t rows = min((uint32_t)kCsrStageRows, r_end - t0) & ~3u;   // 16-byte granules; a ragged tail is read directly
+                const uint32_t lead = t0 >= 4u ? 4u : 0u;                               // the row before the tile, for the first compare
+                const uint32_t bytes = (rows + lead) * 4u;
+                if (bytes) {
+                    mbar_arrive_expect_tx(&s_full[st], bytes);
+                    bulk_g2s(&s_stage[st][4u - lead], a.cell + t0 - lead, bytes, &s_full[st]);
+                } else {
+                    mbar_arrive(&s_full[st]);
+                }
+            }
+        }
+    } else {
+        // ---------------- consumer warps
+        for (uint32_t t = 0; t < n_tiles; t++) {
+            const uint32_t st = t % kCsrStages;
+            mbar_wait(&s_full[st], (t / kCsrStages) & 1u);
+            const uint32_t t0 = r_beg + t * kCsrStageRows;
+            const uint32_t rows = min((uint32_t)kCsrStageRows, r_end - t0);
+            const uint32_t rows4 = rows & ~3u;
+            const uint32_t i0 = (uint32_t)tid * 8u;          // first of my 8 rows inside the tile
+            if (i0 < rows) {
+                uint32_t c[8], prev;
+                const uint32_t *sp = &s_stage[st][4u + i0];
+                if (i0 + 8u <= rows4) {
+                    const uint4 q0 = *reinterpret_cast<const uint4 *>(sp), q1 = *reinterpret_cast<const uint4 *>(sp + 4);
+                    c[0] = q0.x; c[1] = q0.y; c[2] = q0.z; c[3] = q0.w; c[4] = q1.x; c[5] = q1.y; c[6] = q1.z; c[7] = q1.w;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; e++) {
+                        const uint32_t i = i0 + e;
+                        c[e] = (i < rows4) ? sp[e] : ((i < rows) ? __ldg(a.cell + t0 + i) : 0u);
+                    }
+                }
+                const uint32_t r0 = t0 + i0;
+                if (r0 == 0u) prev = ~c[0];                                  // row 0 always opens a segment
+                else prev = sp[-1];                                          // previous row (lead rows for i0 == 0)
+                uint32_t diff = c[0] ^ prev;
+#pragma unroll
+                for (int e = 1; e < 8; e++) diff |= c[e] ^ c[e - 1];
+                if (diff) {                                                   // rare: ~1 segment head per 2000 rows
+                    uint32_t p = prev;
+#pragma unroll
+                    for (int e = 0; e < 8; e++) {
+                        if (i0 + e < rows && c[e] != p) {
+                            const uint32_t k = atomicAdd(&s_count, 1u);
+                            if (k < (uint32_t)kCsrListCap) s_list[k] = r0 + e;
+                        }
+                        p = c[e];
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[st]);
+        }
+    }
+    __syncthreads();
+
+    csr_finish<kCsrBlock>(a, span, r_beg, r_end, s_list, s_sorted, s_count, s_base, s_ws, s_part);
+}
+
+// K1, direct-load variant: the same spans, heads and ordering, but the rows come through LDG.128 instead of the bulk-copy
+// engine (cp.async.bulk moves 16 B per clock per SM = 4.65 TB/s over the chip; plain coalesced loads reach ~5.1 TB/s for
+// this span pattern, profiles/r1i_read_probe.txt).  256 threads, a tile of 2048 rows per iteration: warp w, lane l holds rows
+// [w*256 + l*4, +4) and [w*256 + 128 + l*4, +4) -- every load instruction of a warp covers 512 contiguous bytes -- and the
+// next tile is already in flight while the current one is tested.
+constexpr int kCsrLdgBlock = 256;
+
+__global__ void __launch_bounds__(kCsrLdgBlock, 8) csr_build_ldg_kernel(const CsrArgs a) {
+    __shared__ uint32_t s_list[kCsrListCap], s_sorted[kCsrListCap];
+    __shared__ uint32_t s_count, s_span, s_base, s_ws[16], s_part[kCsrLdgBlock / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        s_span = atomicAdd(a.ticket, 1u) - a.ticket_base;
+        s_count = 0u;
+    }
+    __syncthreads();
+    const uint32_t span = s_span, R = a.n_rows;
+    const unsigned long long sb = (unsigned long long)span * a.rows_per_cta;
+    const uint32_t r_beg = sb < R ? (uint32_t)sb : R;
+    const uint32_t r_end = (sb + a.rows_per_cta < R) ? (uint32_t)(sb + a.rows_per_cta) : R;
+    const uint32_t n_tiles = (r_end - r_beg + kCsrStageRows - 1) / kCsrStageRows;
+    const uint32_t in_tile = (uint32_t)warp * 256u + (uint32_t)lane * 4u;          // first row of my first group inside a tile
+
+    auto load_tile = [&](uint32_t t, uint4 &q0, uint4 &q1, uint32_t &before) {
+        const uint32_t t0 = r_beg + t * kCsrStageRows, g0 = t0 + in_tile, g1 = g0 + 128u;
+        if (g1 + 4u <= r_end) {                                       // both groups inside the span: two aligned 16-byte loads
+            q0 = __ldg(reinterpret_cast<const uint4 *>(a.cell + g0));
+            q1 = __ldg(reinterpret_cast<const uint4 *>(a.cell + g1));
+        } else {                                                      // ragged end of the table: element-wise, zero beyond
+            uint32_t c[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const uint32_t r = (e < 4 ? g0 : g1) + (uint32_t)(e & 3);
+                c[e] = r < r_end ? __ldg(a.cell + r) : 0u;
+            }
+            q0 = make_uint4(c[0], c[1], c[2], c[3]);
+            q1 = make_uint4(c[4], c[5], c[6], c[7]);
+        }
+        before = (lane == 0 && g0 > 0u && g0 < r_end) ? __ldg(a.cell + g0 - 1) : 0u;   // the row before the warp's 256 rows
+    };
+    uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0, n0 = q0, n1 = q0;
+    uint32_t before = 0, nbefore = 0;
+    if (n_tiles) load_tile(0, q0, q1, before);
+    for (uint32_t t = 0; t < n_tiles; t++) {
+        if (t + 1 < n_tiles) load_tile(t + 1, n0, n1, nbefore);
+        const uint32_t t0 = r_beg + t * kCsrStageRows, g0 = t0 + in_tile, g1 = g0 + 128u;
+        // predecessor of each group's first row: the previous lane's last element (lane 0: the row before / lane 31's group 0)
+        uint32_t p0 = __shfl_up_sync(0xffffffffu, q0.w, 1), p1 = __shfl_up_sync(0xffffffffu, q1.w, 1);
+        const uint32_t last0 = __shfl_sync(0xffffffffu, q0.w, 31);
+        if (lane == 0) { p0 = (g0 == 0u) ? ~q0.x : before; p1 = last0; }
+        const uint32_t d0 = (q0.x ^ p0) | (q0.y ^ q0.x) | (q0.z ^ q0.y) | (q0.w ^ q0.z);
+        const uint32_t d1 = (q1.x ^ p1) | (q1.y ^ q1.x) | (q1.z ^ q1.y) | (q1.w ^ q1.z);
+        if ((d0 && g0 < r_end) || (d1 && g1 < r_end)) {                // rare: ~1 segment head per 2000 rows
+            const uint32_t c[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const uint32_t r = (e < 4 ? g0 : g1) + (uint32_t)(e & 3);
+                const uint32_t prev = (e == 0) ? p0 : (e == 4 ? p1 : c[e - 1]);
+                if (r < r_end && c[e] != prev) {
+                    const uint32_t k = atomicAdd(&s_count, 1u);
+                    if (k < (uint32_t)kCsrListCap) s_list[k] = r;
+                }
+            }
+        }
+        q0 = n0; q1 = n1; before = nbefore;
+    }
+    __syncthreads();
+    csr_finish<kCsrLdgBlock>(a, span, r_beg, r_end, s_list, s_sorted, s_count, s_base, s_ws, s_part);
 }
 
 // ------------------------------------------------------------------------------------------

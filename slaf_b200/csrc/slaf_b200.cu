@@ -31,6 +31,10 @@
 
 using namespace slafb;
 
+#ifndef SLAFB_K1_LDG_DEFAULT
+#define SLAFB_K1_LDG_DEFAULT false
+#endif
+
 namespace {
 
 constexpr int kSlots = 4;
@@ -436,8 +440,10 @@ int front(slafb_ctx *ctx, Slot &s, const slafb_coo *pieces, int n_pieces, cudaSt
     k.n_cells_out = s.counters;
     k.host_counts = s.h_counters_dev;
     k.work_counters = s.counters + 2;
-    // one contiguous span of rows per CTA (a whole number of 2048-row stages); ~4 CTAs per SM
-    uint32_t per_sm = 4;
+    // one contiguous span of rows per CTA (a whole number of 2048-row stages).  Two variants of the scan: rows through the
+    // bulk-copy engine (4 CTAs of 288 threads per SM) or through direct 128-bit loads (8 CTAs of 256 threads per SM)
+    static const bool use_ldg = [] { const char *e = getenv("SLAFB_K1_LDG"); return e ? atoi(e) != 0 : SLAFB_K1_LDG_DEFAULT; }();
+    uint32_t per_sm = use_ldg ? 8 : 4;
     if (const char *env = getenv("SLAFB_CSR_CTAS_PER_SM")) {   // tuning knob
         const long v = atol(env);
         if (v >= 1 && v <= 8) per_sm = (uint32_t)v;
@@ -448,7 +454,8 @@ int front(slafb_ctx *ctx, Slot &s, const slafb_coo *pieces, int n_pieces, cudaSt
     k.rows_per_cta = (uint32_t)(((tiles + grid - 1) / grid) * kCsrStageRows);
     grid = (uint32_t)(((uint64_t)total + k.rows_per_cta - 1) / k.rows_per_cta);   // no empty spans
     if (s.sample) CU(ctx, cudaEventRecord(s.t_k1a, sf));
-    csr_build_kernel<<<grid, kCsrBlock, 0, sf>>>(k);
+    if (use_ldg) csr_build_ldg_kernel<<<grid, kCsrLdgBlock, 0, sf>>>(k);
+    else csr_build_kernel<<<grid, kCsrBlock, 0, sf>>>(k);
     CU(ctx, cudaGetLastError());
     if (s.sample) { CU(ctx, cudaEventRecord(s.t_k1b, sf)); s.timed_front = true; }
     ctx->ticket_base += grid;
