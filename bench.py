@@ -393,17 +393,7 @@ def main():
     if not ok:
         raise SystemExit("PARITY FAILURE: CUDA path differs from the oracle; refusing to report throughput")
 
-    if os.environ.get("SLAFB_BENCH_WC", "0") != "0":      # write-combined staging buffers (A/B knob)
-        from slaf_b200.engine import pinned_empty
-
-        def _wc(a):
-            buf = pinned_empty(a.size, a.dtype, write_combined=True)
-            buf[:] = a
-            return buf
-
-        host_cols = [tuple(_wc(a) for a in (b.cell, b.gene, b.value)) for b in batches]
-    else:
-        host_cols = [tuple(torch.from_numpy(a).pin_memory() for a in (b.cell, b.gene, b.value)) for b in batches]
+    host_cols = [tuple(torch.from_numpy(a).pin_memory() for a in (b.cell, b.gene, b.value)) for b in batches]
     tot_rows = [b.n_rows for b in batches]
     vbytes = 2 if args.value_dtype == "uint16" else 4
     gbytes = batches[0].gene.dtype.itemsize

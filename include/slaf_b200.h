@@ -239,9 +239,6 @@ int slafb_gene_median(slafb_ctx *ctx, const uint32_t *hist, int64_t n_genes, int
 
 /* Pinned host memory for the feeder's staging buffers (so H2D copies are truly async). */
 int slafb_host_alloc(void **ptr, size_t bytes);
-/* Write-combined variant: not snooped while the GPU reads it over PCIe (faster H2D when many GPUs pull from one host),
- * slow for the CPU to READ -- for staging buffers that the feeder only writes. */
-int slafb_host_alloc_wc(void **ptr, size_t bytes);
 int slafb_host_free(void *ptr);
 /* Page-lock memory the caller already owns (e.g. the column buffers of an in-memory / memory-mapped
  * expression table), so slices of it are DMA sources without a staging copy. */

@@ -36,7 +36,7 @@ ABI_VERSION = 2
 EXPORTS = [
     "slafb_version", "slafb_create", "slafb_destroy", "slafb_last_error", "slafb_tokenize", "slafb_submit", "slafb_submit_pieces", "slafb_submit_segments", "slafb_host_register", "slafb_host_unregister",
     "slafb_collect", "slafb_collect_csr", "slafb_prepare_shuffle", "slafb_segments", "slafb_window", "slafb_tokenize_lists", "slafb_shuffle_perm", "slafb_gene_stats", "slafb_gene_hist", "slafb_gene_median",
-    "slafb_host_alloc", "slafb_host_alloc_wc", "slafb_host_free", "slafb_get_timing", "slafb_set_option",
+    "slafb_host_alloc", "slafb_host_free", "slafb_get_timing", "slafb_set_option",
 ]
 
 
@@ -145,7 +145,6 @@ def lib() -> ctypes.CDLL:
     L.slafb_gene_hist.argtypes = [c_void_p, POINTER(Coo), c_int64, c_int32, c_void_p, c_void_p]
     L.slafb_gene_median.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p]
     L.slafb_host_alloc.argtypes = [POINTER(c_void_p), c_size_t]
-    L.slafb_host_alloc_wc.argtypes = [POINTER(c_void_p), c_size_t]
     L.slafb_host_free.argtypes = [c_void_p]
     L.slafb_set_option.argtypes = [c_void_p, c_int32, c_int64]
     L.slafb_get_timing.argtypes = [c_void_p, POINTER(Timing)]

@@ -667,11 +667,6 @@ int slafb_host_alloc(void **ptr, size_t bytes) {
     CU(nullptr, cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
     return SLAFB_OK;
 }
-int slafb_host_alloc_wc(void **ptr, size_t bytes) {
-    if (!ptr) return fail(nullptr, SLAFB_ERR_INVALID, "ptr is NULL");
-    CU(nullptr, cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocWriteCombined | cudaHostAllocPortable));
-    return SLAFB_OK;
-}
 int slafb_host_register(void *ptr, size_t bytes) {
     if (!ptr || !bytes) return fail(nullptr, SLAFB_ERR_INVALID, "nothing to register");
     CU(nullptr, cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));

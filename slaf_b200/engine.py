@@ -458,16 +458,14 @@ def shuffle_perm(seed: int, n: int) -> np.ndarray:
     return perm
 
 
-def pinned_empty(n: int, dtype, write_combined: bool = False) -> np.ndarray:
-    """numpy array over cudaHostAlloc'ed memory; freed when the last view of it is garbage collected.
-    write_combined=True: not snooped during PCIe reads (good for write-once staging buffers), slow to read on the CPU."""
+def pinned_empty(n: int, dtype) -> np.ndarray:
+    """numpy array over cudaHostAlloc'ed memory; freed when the last view of it is garbage collected."""
     import weakref
 
     dtype = np.dtype(dtype)
     ptr = ctypes.c_void_p()
     nbytes = max(1, n * dtype.itemsize)
-    alloc = N.lib().slafb_host_alloc_wc if write_combined else N.lib().slafb_host_alloc
-    N.check(alloc(ctypes.byref(ptr), nbytes))
+    N.check(N.lib().slafb_host_alloc(ctypes.byref(ptr), nbytes))
     buf = (ctypes.c_char * nbytes).from_address(ptr.value)
     weakref.finalize(buf, _free_pinned, ptr.value)
     return np.frombuffer(buf, dtype=dtype, count=n)
