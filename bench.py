@@ -402,7 +402,7 @@ def main():
     def bytes_over(n_steps):   # (K1, K2, H2D) algorithmic bytes of n_steps steps (batches are cycled)
         return tuple(sum(per_batch[i % NB][j] for i in range(n_steps)) for j in range(3))
 
-    def run_steps(cols, n_steps, read_result, depth=int(os.environ.get("SLAFB_BENCH_DEPTH", "2"))):
+    def run_steps(cols, n_steps, read_result, depth=int(os.environ.get("SLAFB_BENCH_DEPTH", "4"))):
         """pipelined: up to `depth` submits (H2D + CSR build) run ahead of the collect of the
         oldest batch.  Returns (#cells, #rows, d2h bytes)."""
         from collections import deque

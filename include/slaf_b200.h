@@ -158,8 +158,8 @@ int slafb_tokenize(slafb_ctx *ctx, const slafb_coo *in, const slafb_params *p, c
 
 /* Same path, pipelined (double buffered): submit() enqueues the H2D copy (host input) and the
  * CSR build on the context's side stream and returns a slot; collect() waits for the cell
- * count, applies the shuffle and launches the tokenizing kernels on `stream`.  Four slots:
- * up to three submits may precede the collect of the oldest batch.  Replaces the AsyncPrefetcher hand-off
+ * count, applies the shuffle and launches the tokenizing kernels on `stream`.  Eight slots:
+ * up to seven submits may precede the collect of the oldest batch (a deep queue absorbs host scheduling hiccups).  Replaces the AsyncPrefetcher hand-off
  * (slaf/ml/datasets.py:1242-1294) for the device-side part of the work. */
 int slafb_submit(slafb_ctx *ctx, const slafb_coo *in, void *stream, int32_t *slot);
 /* submit() for a batch that is the concatenation of n_pieces row blocks (all host or all device, same

@@ -1,7 +1,7 @@
 // slaf_b200.cu -- C-ABI implementation (see include/slaf_b200.h for the contract and the
 // reference interfaces each entry point replaces).
 //
-// Stream model.  Each context owns a side stream `s_in`, a helper thread and four pipeline slots.
+// Stream model.  Each context owns a side stream `s_in`, a helper thread and eight pipeline slots.
 //   submit : [s_in]    wait(caller stream) -> H2D of the COO columns (host input, piece by piece, straight from
 //                      the caller's pinned / registered memory) -> K1 CSR build, which also writes {n_cells, error
 //                      flag} into mapped pinned memory -> event `front`
@@ -37,7 +37,7 @@ using namespace slafb;
 
 namespace {
 
-constexpr int kSlots = 4;
+constexpr int kSlots = 8;
 
 struct Slot {
     bool in_flight = false;
