@@ -341,3 +341,48 @@ def test_segments_from_cell_start_index_match_the_column():
         cat = np.concatenate([p.cell for p in pieces])
         s0, _e0, i0 = _runs(cat)
         assert np.array_equal(st[:-1], s0) and st[-1] == len(cat) and np.array_equal(ids, i0)
+
+
+# ---------------------------------------------------------------- property tests (hypothesis)
+from hypothesis import given, settings  # noqa: E402
+from hypothesis import strategies as st  # noqa: E402
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.lists(st.integers(0, 7), min_size=1, max_size=40), st.integers(1, 30), st.data())
+def test_property_csi_segments_equal_column_runs(lens, rows_per_file, data):
+    """For any table (cells of 0..7 rows), any fragment size and any selection of consecutive fragment slices, the segment
+    table computed from _cell_start_index alone equals the runs of the cell column."""
+    from slaf_b200.ml.datasets import _runs, _segments_from_csi
+    from slaf_b200.ml.sources import ArrayExpressionSource
+
+    lens = np.asarray(lens, np.int64)
+    if lens.sum() == 0:
+        lens[0] = 1
+    csi = np.concatenate(([0], np.cumsum(lens)))
+    cell = np.repeat(np.arange(len(lens), dtype=np.uint32), lens)
+    src = ArrayExpressionSource(cell, np.zeros(len(cell), np.uint16), np.ones(len(cell), np.uint16), rows_per_file)
+    frs = [f.to_table() for f in src.get_fragments()]
+    k0 = data.draw(st.integers(0, len(frs) - 1))
+    k1 = data.draw(st.integers(k0, len(frs) - 1))
+    pieces = frs[k0:k1 + 1]
+    cut = data.draw(st.integers(0, len(pieces[0]) - 1))
+    pieces = [pieces[0].slice(cut, len(pieces[0]))] + pieces[1:]
+    stt, ids = _segments_from_csi(pieces, csi)
+    cat = np.concatenate([p.cell for p in pieces])
+    s0, _e0, i0 = _runs(cat)
+    assert np.array_equal(stt[:-1], s0) and stt[-1] == len(cat) and np.array_equal(ids, i0)
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.lists(st.tuples(st.integers(0, 5), st.integers(1, 6)), min_size=1, max_size=25), st.integers(0, 2**31 - 1))
+def test_property_block_shuffle_keeps_cells_whole_and_matches_cpython(runs, seed):
+    """RandomShuffle.apply on arbitrary (even non-contiguous) cell runs: every cell's rows stay together in arrival order,
+    and the cell order is CPython's shuffle of the first-appearance order."""
+    cell = np.concatenate([np.full(n, c, np.uint32) for c, n in runs])
+    gene = np.arange(len(cell), dtype=np.uint16)
+    out = RandomShuffle().apply({"cell_integer_id": cell, "gene_integer_id": gene, "value": gene}, seed)
+    want = pr.apply_block_shuffle(cell, gene, gene, seed)
+    assert np.array_equal(out["cell_integer_id"], want[0]) and np.array_equal(out["gene_integer_id"], want[1])
+    oc = np.asarray(out["cell_integer_id"])
+    assert len(np.flatnonzero(oc[1:] != oc[:-1])) + 1 == len(np.unique(cell))        # one run per cell
