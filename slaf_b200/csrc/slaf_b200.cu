@@ -43,6 +43,7 @@ struct Slot {
     bool in_flight = false;
     // device scratch
     uint32_t *seg_start = nullptr, *seg_cell = nullptr;
+    int32_t *perm_dev = nullptr;
     uint32_t *work_list = nullptr;
     uint32_t *counters = nullptr;   // [0] n_cells, [1] err, [2] work count, [3] work head, [4] fast-kernel row ticket
     // staged copies of host input (lazy)
@@ -63,7 +64,8 @@ struct Slot {
     int32_t cell_dtype = 0, gene_dtype = 0, value_dtype = 0;
     cudaEvent_t ev_front = nullptr, ev_done = nullptr, ev_in = nullptr;
     cudaEvent_t ev_loaded = nullptr;   // all three columns are on the device (ev_front: cell column + CSR build only)
-    int32_t *h_perm_dev = nullptr;     // device-side address of h_perm (mapped pinned memory)
+    cudaEvent_t ev_perm = nullptr;     // the helper thread's upload of the prepared permutation
+    bool perm_uploaded = false;
     // timing events
     cudaEvent_t t_h2d0 = nullptr, t_h2d1 = nullptr, t_k1a = nullptr, t_k1b = nullptr, t_k2a = nullptr, t_k2b = nullptr, t_k2c = nullptr;
     bool timed_front = false, timed_back = false, timed_h2d = false;
@@ -79,6 +81,7 @@ struct slafb_ctx {
     int64_t max_rows = 0, max_cells = 0;
     cudaStream_t s_in = nullptr;
     cudaStream_t s_aux = nullptr;      // small device-to-host reads that must not queue behind the big H2D copies
+    cudaStream_t s_perm = nullptr;     // the helper thread's permutation uploads
     Slot slot[kSlots];
     int next_slot = 0;
     unsigned long long *tile_state = nullptr;
@@ -341,7 +344,7 @@ void fill_tok_args(slafb_ctx *ctx, Slot &s, const slafb_params *p, TokArgs &a, u
     a.n_rows = (uint32_t)s.n_rows;
     a.seg_start = s.seg_start;
     a.seg_cell = s.seg_cell;
-    a.perm = use_perm ? s.h_perm_dev : nullptr;      // read in place from mapped pinned host memory
+    a.perm = use_perm ? s.perm_dev : nullptr;
     a.n_cells = n_cells;
     a.cell_signed = (s.cell_dtype == SLAFB_I32);
     a.max_items = (uint32_t)p->max_items;
@@ -495,9 +498,15 @@ void shuffle_worker(slafb_ctx *ctx) {
         }
         Slot &s = ctx->slot[i];
         int64_t C = -1;
+        s.perm_uploaded = false;
         if (cudaEventSynchronize(s.ev_front) == cudaSuccess && !s.h_counters[1]) {
             C = s.h_counters[0];
             py_shuffle_perm(s.prep_seed, C, s.h_perm, s.h_draws);
+            // upload it right away on the auxiliary stream: collect() then only waits for an event that is long complete,
+            // instead of putting a copy in front of the tokenizing kernel on the caller's stream
+            if (C > 0 && cudaMemcpyAsync(s.perm_dev, s.h_perm, (size_t)C * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_perm) == cudaSuccess &&
+                cudaEventRecord(s.ev_perm, ctx->s_perm) == cudaSuccess)
+                s.perm_uploaded = true;
         }
         {
             std::lock_guard<std::mutex> lk(ctx->wm);
@@ -551,6 +560,12 @@ int middle(slafb_ctx *ctx, Slot &s, const slafb_params *p, int64_t *n, cudaStrea
     settle_prepared(ctx, s);
     const bool prepared = s.prep_state.load() == 2 && p->shuffle == SLAFB_SHUFFLE_SEED && s.prep_seed == p->seed && s.prep_cells == C;
     s.prep_state.store(0);
+    if (s.perm_uploaded && !prepared) {
+        // a permutation was prepared (and is being uploaded) for another seed / order: let that copy finish before the
+        // permutation buffers are rewritten
+        CU(ctx, cudaEventSynchronize(s.ev_perm));
+        s.perm_uploaded = false;
+    }
     if (p->shuffle == SLAFB_SHUFFLE_SEED) {
         if (!prepared) {
             const double ts0 = now_ms();
@@ -571,9 +586,12 @@ int middle(slafb_ctx *ctx, Slot &s, const slafb_params *p, int64_t *n, cudaStrea
         *n = p->n_perm;
     }
     CU(ctx, cudaStreamWaitEvent(st, s.ev_loaded, 0));      // gene / value columns (ev_front covered the cell column only)
-    // The permutation is NOT copied: the kernels read it in place from mapped pinned host memory (128 KB per 32 k cells
-    // over PCIe, fetched rows ahead by the thread that also prefetches the segment bounds).  A copy in front of the
-    // tokenizing kernel was a bubble on the caller's stream, and on a busy H2D engine it queued behind whole batches.
+    if (prepared && s.perm_uploaded) {
+        CU(ctx, cudaStreamWaitEvent(st, s.ev_perm, 0));    // the helper already uploaded this permutation
+        s.perm_uploaded = false;
+        return SLAFB_OK;
+    }
+    if (*use_perm && *n > 0) CU(ctx, cudaMemcpyAsync(s.perm_dev, s.h_perm, (size_t)(*n) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     return SLAFB_OK;
 }
 
@@ -706,6 +724,7 @@ int slafb_create(slafb_ctx **out, int device, int64_t max_rows, int64_t max_cell
 #define CUC(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { int rc__ = fail(nullptr, SLAFB_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__)); slafb_destroy(ctx); return rc__; } } while (0)
     CUC(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
     CUC(cudaStreamCreateWithFlags(&ctx->s_aux, cudaStreamNonBlocking));
+    CUC(cudaStreamCreateWithFlags(&ctx->s_perm, cudaStreamNonBlocking));
     const size_t n_tiles_max = (size_t)ctx->n_sm * 8;
     CUC(cudaMalloc(&ctx->tile_state, n_tiles_max * sizeof(unsigned long long)));
     CUC(cudaMemset(ctx->tile_state, 0, n_tiles_max * sizeof(unsigned long long)));
@@ -730,17 +749,17 @@ int slafb_create(slafb_ctx **out, int device, int64_t max_rows, int64_t max_cell
         Slot &s = ctx->slot[i];
         CUC(cudaMalloc(&s.seg_start, ((size_t)max_cells + 2) * sizeof(uint32_t)));
         CUC(cudaMalloc(&s.seg_cell, ((size_t)max_cells + 1) * sizeof(uint32_t)));
+        CUC(cudaMalloc(&s.perm_dev, ((size_t)max_cells + 1) * sizeof(int32_t)));
         CUC(cudaMalloc(&s.work_list, ((size_t)max_cells + 1) * sizeof(uint32_t)));
         CUC(cudaMalloc(&s.counters, 8 * sizeof(uint32_t)));
         CUC(cudaMemset(s.counters, 0, 8 * sizeof(uint32_t)));
         CUC(cudaHostAlloc(&s.h_counters, 4 * sizeof(uint32_t), cudaHostAllocMapped | cudaHostAllocPortable));
         memset(s.h_counters, 0, 4 * sizeof(uint32_t));
         CUC(cudaHostGetDevicePointer(reinterpret_cast<void **>(&s.h_counters_dev), s.h_counters, 0));
-        CUC(cudaHostAlloc(&s.h_perm, ((size_t)max_cells + 1) * sizeof(int32_t), cudaHostAllocMapped | cudaHostAllocPortable));
-        CUC(cudaHostGetDevicePointer(reinterpret_cast<void **>(&s.h_perm_dev), s.h_perm, 0));
+        CUC(cudaHostAlloc(&s.h_perm, ((size_t)max_cells + 1) * sizeof(int32_t), cudaHostAllocDefault));
         s.h_draws = (uint32_t *)malloc(((size_t)max_cells + 1) * sizeof(uint32_t));
         if (!s.h_draws) { slafb_destroy(ctx); return fail(nullptr, SLAFB_ERR_INVALID, "out of host memory"); }
-        cudaEvent_t *plain[] = {&s.ev_front, &s.ev_done, &s.ev_in, &s.ev_loaded};
+        cudaEvent_t *plain[] = {&s.ev_front, &s.ev_done, &s.ev_in, &s.ev_loaded, &s.ev_perm};
         for (auto e : plain) CUC(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
         cudaEvent_t *timed[] = {&s.t_h2d0, &s.t_h2d1, &s.t_k1a, &s.t_k1b, &s.t_k2a, &s.t_k2b, &s.t_k2c};
         for (auto e : timed) CUC(cudaEventCreate(e));
@@ -766,12 +785,12 @@ int slafb_destroy(slafb_ctx *ctx) {
     for (int i = 0; i < kSlots; i++) {
         Slot &s = ctx->slot[i];
         if (s.ev_done) cudaEventSynchronize(s.ev_done);
-        cudaFree(s.seg_start); cudaFree(s.seg_cell); cudaFree(s.work_list); cudaFree(s.counters);
+        cudaFree(s.seg_start); cudaFree(s.seg_cell); cudaFree(s.perm_dev); cudaFree(s.work_list); cudaFree(s.counters);
         cudaFree(s.in_cell); cudaFree(s.in_gene); cudaFree(s.in_value);
         if (s.h_counters) cudaFreeHost(s.h_counters);
         if (s.h_perm) cudaFreeHost(s.h_perm);
         free(s.h_draws);
-        cudaEvent_t evs[] = {s.ev_front, s.ev_done, s.ev_in, s.ev_loaded, s.t_h2d0, s.t_h2d1, s.t_k1a, s.t_k1b, s.t_k2a, s.t_k2b, s.t_k2c};
+        cudaEvent_t evs[] = {s.ev_front, s.ev_done, s.ev_in, s.ev_loaded, s.ev_perm, s.t_h2d0, s.t_h2d1, s.t_k1a, s.t_k1b, s.t_k2a, s.t_k2b, s.t_k2c};
         for (auto e : evs) if (e) cudaEventDestroy(e);
     }
     cudaFree(ctx->tile_state); cudaFree(ctx->ticket); cudaFree(ctx->log1p_lut); cudaFree(ctx->vstar_table); cudaFree(ctx->sort_scratch); cudaFree(ctx->rank_scratch); cudaFree(ctx->dup_table);
@@ -779,6 +798,7 @@ int slafb_destroy(slafb_ctx *ctx) {
     if (ctx->h_total) cudaFreeHost(ctx->h_total);
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
     if (ctx->s_aux) cudaStreamDestroy(ctx->s_aux);
+    if (ctx->s_perm) cudaStreamDestroy(ctx->s_perm);
     delete ctx;
     return SLAFB_OK;
 }
@@ -965,7 +985,7 @@ int slafb_collect_csr(slafb_ctx *ctx, int32_t slot, const slafb_params *p, int64
         else if (!crow || !col || !val || !cell_ids) rc = fail(ctx, SLAFB_ERR_INVALID, "NULL output");
     }
     if (rc == SLAFB_OK && C > 0) {
-        const int32_t *perm = use_perm ? s.h_perm_dev : nullptr;
+        const int32_t *perm = use_perm ? s.perm_dev : nullptr;
         csr_lengths_kernel<<<(unsigned)((C + 255) / 256), 256, 0, st>>>(s.seg_start, s.seg_cell, perm, (uint32_t)C, s.cell_dtype == SLAFB_I32,
                                                                         ctx->kept_count, reinterpret_cast<long long *>(cell_ids));
         scan_counts_kernel<<<1, 1024, 0, st>>>(ctx->kept_count, reinterpret_cast<long long *>(crow), (uint32_t)C, ctx->total_dev);
@@ -1037,7 +1057,7 @@ int slafb_window(slafb_ctx *ctx, const slafb_coo *in, const slafb_params *p, int
     CU(ctx, cudaMemsetAsync(s.counters + 3, 0, sizeof(uint32_t), st));
     DISPATCH_TYPES(s.gene_dtype, s.value_dtype, rc = (dispatch_general<GeneT, ValT, 2>(ctx, p->mode, a, w, st)));
     if (rc) return rc;
-    cell_ids_kernel<<<(unsigned)((C + 255) / 256), 256, 0, st>>>(s.seg_cell, use_perm ? s.h_perm_dev : nullptr, (uint32_t)C,
+    cell_ids_kernel<<<(unsigned)((C + 255) / 256), 256, 0, st>>>(s.seg_cell, use_perm ? s.perm_dev : nullptr, (uint32_t)C,
                                                                  s.cell_dtype == SLAFB_I32, reinterpret_cast<long long *>(cell_ids));
     CU(ctx, cudaGetLastError());
     ctx->acc.kernel_launches += 2;
