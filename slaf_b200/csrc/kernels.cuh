@@ -1629,6 +1629,13 @@ __global__ void cell_ids_kernel(const uint32_t *seg_cell, const int32_t *perm, u
     cell_ids[j] = cell_signed ? (long long)(int32_t)cid : (long long)cid;
 }
 
+// The permutation reaches the device through the SMs, not the copy engine: 4 bytes per cell read from mapped pinned host
+// memory and written to HBM.  (A cudaMemcpyAsync would queue behind whole batches of column copies on the H2D engine.)
+__global__ void perm_upload_kernel(const int32_t *__restrict__ host_perm, int32_t *__restrict__ perm, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) perm[i] = host_perm[i];
+}
+
 // duplicate detection over the segment table's cell ids (a cell split into two separated row runs
 // would silently become two output rows): open-addressing hash set, 64-bit slots (1<<32 | id)
 __global__ void dup_check_kernel(const uint32_t *seg_cell, uint32_t n, unsigned long long *table, uint32_t mask, uint32_t *flag) {

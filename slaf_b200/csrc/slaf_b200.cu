@@ -66,6 +66,7 @@ struct Slot {
     cudaEvent_t ev_loaded = nullptr;   // all three columns are on the device (ev_front: cell column + CSR build only)
     cudaEvent_t ev_perm = nullptr;     // the helper thread's upload of the prepared permutation
     bool perm_uploaded = false;
+    int32_t *h_perm_dev = nullptr;     // device-side address of h_perm (mapped pinned memory)
     // timing events
     cudaEvent_t t_h2d0 = nullptr, t_h2d1 = nullptr, t_k1a = nullptr, t_k1b = nullptr, t_k2a = nullptr, t_k2b = nullptr, t_k2c = nullptr;
     bool timed_front = false, timed_back = false, timed_h2d = false;
@@ -502,11 +503,12 @@ void shuffle_worker(slafb_ctx *ctx) {
         if (cudaEventSynchronize(s.ev_front) == cudaSuccess && !s.h_counters[1]) {
             C = s.h_counters[0];
             py_shuffle_perm(s.prep_seed, C, s.h_perm, s.h_draws);
-            // upload it right away on the auxiliary stream: collect() then only waits for an event that is long complete,
-            // instead of putting a copy in front of the tokenizing kernel on the caller's stream
-            if (C > 0 && cudaMemcpyAsync(s.perm_dev, s.h_perm, (size_t)C * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_perm) == cudaSuccess &&
-                cudaEventRecord(s.ev_perm, ctx->s_perm) == cudaSuccess)
-                s.perm_uploaded = true;
+            // upload it right away on its own stream with a tiny kernel (not the copy engine, which is busy with whole
+            // batches of columns): collect() then only waits for an event that is long complete
+            if (C > 0) {
+                perm_upload_kernel<<<(unsigned)((C + 255) / 256), 256, 0, ctx->s_perm>>>(s.h_perm_dev, s.perm_dev, (uint32_t)C);
+                if (cudaGetLastError() == cudaSuccess && cudaEventRecord(s.ev_perm, ctx->s_perm) == cudaSuccess) s.perm_uploaded = true;
+            }
         }
         {
             std::lock_guard<std::mutex> lk(ctx->wm);
@@ -591,7 +593,11 @@ int middle(slafb_ctx *ctx, Slot &s, const slafb_params *p, int64_t *n, cudaStrea
         s.perm_uploaded = false;
         return SLAFB_OK;
     }
-    if (*use_perm && *n > 0) CU(ctx, cudaMemcpyAsync(s.perm_dev, s.h_perm, (size_t)(*n) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    if (*use_perm && *n > 0) {
+        perm_upload_kernel<<<(unsigned)((*n + 255) / 256), 256, 0, st>>>(s.h_perm_dev, s.perm_dev, (uint32_t)*n);
+        CU(ctx, cudaGetLastError());
+        ctx->acc.kernel_launches++;
+    }
     return SLAFB_OK;
 }
 
@@ -756,7 +762,8 @@ int slafb_create(slafb_ctx **out, int device, int64_t max_rows, int64_t max_cell
         CUC(cudaHostAlloc(&s.h_counters, 4 * sizeof(uint32_t), cudaHostAllocMapped | cudaHostAllocPortable));
         memset(s.h_counters, 0, 4 * sizeof(uint32_t));
         CUC(cudaHostGetDevicePointer(reinterpret_cast<void **>(&s.h_counters_dev), s.h_counters, 0));
-        CUC(cudaHostAlloc(&s.h_perm, ((size_t)max_cells + 1) * sizeof(int32_t), cudaHostAllocDefault));
+        CUC(cudaHostAlloc(&s.h_perm, ((size_t)max_cells + 1) * sizeof(int32_t), cudaHostAllocMapped | cudaHostAllocPortable));
+        CUC(cudaHostGetDevicePointer(reinterpret_cast<void **>(&s.h_perm_dev), s.h_perm, 0));
         s.h_draws = (uint32_t *)malloc(((size_t)max_cells + 1) * sizeof(uint32_t));
         if (!s.h_draws) { slafb_destroy(ctx); return fail(nullptr, SLAFB_ERR_INVALID, "out of host memory"); }
         cudaEvent_t *plain[] = {&s.ev_front, &s.ev_done, &s.ev_in, &s.ev_loaded, &s.ev_perm};
