@@ -922,6 +922,7 @@ int slafb_prepare_shuffle(slafb_ctx *ctx, int32_t slot, int64_t seed) {
         }
         s.prep_seed = seed;
         s.prep_cells = -1;
+        ctx->acc.kernel_launches++;      // the helper launches perm_upload_kernel for this batch
         s.prep_state.store(1);
         ctx->wjobs.push_back(slot);
     }
