@@ -402,7 +402,7 @@ def main():
     def bytes_over(n_steps):   # (K1, K2, H2D) algorithmic bytes of n_steps steps (batches are cycled)
         return tuple(sum(per_batch[i % NB][j] for i in range(n_steps)) for j in range(3))
 
-    def run_steps(cols, n_steps, read_result, depth=int(os.environ.get("SLAFB_BENCH_DEPTH", "4"))):
+    def run_steps(cols, n_steps, read_result, depth=int(os.environ.get("SLAFB_BENCH_DEPTH", "4")), segs=None):
         """pipelined: up to `depth` submits (H2D + CSR build) run ahead of the collect of the
         oldest batch.  Returns (#cells, #rows, d2h bytes)."""
         from collections import deque
@@ -413,7 +413,10 @@ def main():
         keep = None
         for i in range(n_steps):
             while nxt < n_steps and len(q) <= depth:
-                q.append(eng.submit(*cols[nxt % NB], shuffle_seed=42 + nxt))   # seed known at submit: the library prepares the shuffle off-thread
+                if segs is None:
+                    q.append(eng.submit(*cols[nxt % NB], shuffle_seed=42 + nxt))   # seed known at submit: the library prepares the shuffle off-thread
+                else:     # the cell boundaries come from the dataset's cell_start_index: gene / value columns only
+                    q.append(eng.submit_segments([cols[nxt % NB][1:]], *segs[nxt % NB], shuffle_seed=42 + nxt))
                 nxt += 1
             out = eng.collect(q.popleft(), shuffle_seed=42 + i, **kw)
             cells += out.n_cells
@@ -477,6 +480,30 @@ def main():
                "d2h_bytes_per_step": d2h_e // args.steps, "ms_per_step": 1000.0 * dt / args.steps,
                "h2d_gbs_per_gpu": h2d_bytes / dt / 1e9,
                "h2d_copy_gbs": (h2d_bytes * tme["timed_batches"] / max(1, tme["batches"]) / (tme["h2d_ms"] / 1e3) / 1e9) if tme["h2d_ms"] else None}
+
+        # the same call when the caller passes the dataset's cell_start_index instead of the cell column (SLAFArray always has
+        # one): the segment table (8 B per cell) replaces 4 B per row on the bus.  Checked against the COO route first.
+        segs = [(b.cell_start.astype(np.uint32), b.cell[b.cell_start[:-1]].astype(np.uint32)) for b in batches]
+        a = eng.collect(eng.submit(*host_cols[0], shuffle_seed=7), shuffle_seed=7, **kw)
+        a_t = [t.clone() for t in (a.input_ids, a.attention_mask, a.cell_ids)] + ([a.values.clone()] if a.values is not None else [])
+        b_ = eng.collect(eng.submit_segments([host_cols[0][1:]], *segs[0], shuffle_seed=7), shuffle_seed=7, **kw)
+        b_t = [b_.input_ids, b_.attention_mask, b_.cell_ids] + ([b_.values] if b_.values is not None else [])
+        if not all(torch.equal(x, y) for x, y in zip(a_t, b_t)):
+            raise SystemExit("PARITY FAILURE: cell_start_index route differs from the COO route")
+        del a, a_t, b_, b_t
+        run_steps(host_cols, args.warmup, True, segs=segs)
+        barrier()
+        t0 = time.perf_counter()
+        cells_s, _, _ = run_steps(host_cols, args.steps, True, segs=segs)
+        torch.cuda.synchronize(dev)
+        barrier()
+        dts = max_over_ranks(time.perf_counter() - t0)
+        eng.timing()
+        seg_bytes = sum((per_batch[i % NB][2] - 4 * tot_rows[i % NB] + 8 * cps + 4) for i in range(args.steps))
+        e2e["with_cell_start_index"] = {"value": sum_over_ranks(cells_s) / dts, "unit": "cells/s", "ms_per_step": 1000.0 * dts / args.steps,
+                                        "h2d_bytes_per_step": seg_bytes // args.steps, "h2d_gbs_per_gpu": seg_bytes / dts / 1e9,
+                                        "note": "slafb_submit_segments: gene + value columns and the segment table (8 B per cell) cross the bus, "
+                                                "the cell column does not and no CSR build runs; same outputs (checked)"}
 
         if not args.no_loader and not w.get("rank_norm"):
             e2e["loader"] = loader_rate(w, batches, dev, args.value_dtype)

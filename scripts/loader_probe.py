@@ -34,14 +34,25 @@ def timed(name, fn):
     return wrap
 
 
-for epoch_mode in ("fragment", "mos", "fragment+csi", "mos+csi"):
+profile = os.environ.get("SLAFB_PROBE_PROFILE") == "1"       # cProfile of the feeder thread's work instead of the stage timers
+modes = tuple(os.environ.get("SLAFB_PROBE_MODES", "fragment,mos,fragment+csi,mos+csi").split(","))
+for epoch_mode in modes:
     proc = PrefetchBatchProcessor(arr, RandomShuffle(), tok, n_expression_bins=51, use_binned_expressions=True, n_epochs=3,
                                   use_mixture_of_scanners=epoch_mode.startswith("mos"), by_fragment=True, verbose=False, n_scanners=4,
                                   prefetch_batch_size=4194304, use_cell_start_index=epoch_mode.endswith("csi"))
-    proc._next_pieces = timed("read", proc._next_pieces)
-    proc._submit = timed("submit", proc._submit)
-    proc._stash_partials = timed("stash", proc._stash_partials)
-    proc._complete_mask = timed("complete", proc._complete_mask)
+    if not profile:
+        proc._next_pieces = timed("read", proc._next_pieces)
+        proc._submit = timed("submit", proc._submit)
+        proc._stash_partials = timed("stash", proc._stash_partials)
+        proc._complete_mask = timed("complete", proc._complete_mask)
+    else:
+        import cProfile
+        import pstats
+
+        proc.load_prefetch_batch()         # context creation outside the profile
+        torch.cuda.synchronize()
+        prof = cProfile.Profile()
+        prof.enable()
     stages.clear()
     n = 0
     t_first = None
@@ -49,7 +60,7 @@ for epoch_mode in ("fragment", "mos", "fragment+csi", "mos+csi"):
     try:
         while True:
             e = proc._engine
-            if e is not None and not hasattr(e, "_wrapped"):
+            if e is not None and not hasattr(e, "_wrapped") and not profile:
                 e.segments = timed("segments", e.segments)
                 e.collect = timed("collect", e.collect)
                 e._wrapped = True
@@ -61,8 +72,12 @@ for epoch_mode in ("fragment", "mos", "fragment+csi", "mos+csi"):
             n += out.n_cells
     except StopIteration:
         pass
+    if profile:
+        prof.disable()
     torch.cuda.synchronize()
     t1 = time.perf_counter()
+    if profile:
+        pstats.Stats(prof).sort_stats("tottime").print_stats(22)
     print(f"[{epoch_mode}] {n} cells in {t1 - t0:.3f}s ({n / (t1 - t0):,.0f} cells/s incl. start-up; steady {(n - n0) / (t1 - t_first):,.0f} cells/s)")
     for k, v in stages.items():
         print(f"   {k:10s} n={len(v):3d} mean={1e3 * np.mean(v):8.3f} ms  first={1e3 * v[0]:8.3f} ms  total={np.sum(v):.3f}s")

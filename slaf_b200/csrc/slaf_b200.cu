@@ -38,6 +38,7 @@ using namespace slafb;
 namespace {
 
 constexpr int kSlots = 8;
+constexpr int kHelpers = 2;   // host threads preparing CPython-exact shuffles (a 32k-cell shuffle costs about as much host time as the GPU needs for the batch)
 
 struct Slot {
     bool in_flight = false;
@@ -57,6 +58,7 @@ struct Slot {
     int64_t prep_seed = 0;
     int64_t prep_cells = -1;
     int32_t *h_perm = nullptr;
+    uint32_t *h_seg = nullptr;         // pinned copy of a caller-supplied segment table (submit_segments): [C + 1] starts, then [C] cell ids
     uint32_t *h_draws = nullptr;    // scratch of the host shuffle (plain malloc)
     // batch description (device pointers actually used by the kernels)
     const void *cell = nullptr, *gene = nullptr, *value = nullptr;
@@ -102,7 +104,7 @@ struct slafb_ctx {
     slafb_timing acc{};
     char err[512] = {0};
     // helper thread: builds CPython-exact permutations as soon as a batch's cell count is known
-    std::thread worker;
+    std::thread worker[kHelpers];      // shuffle helpers: the batches' permutations are independent, each job is one slot
     std::mutex wm;
     std::condition_variable wcv, wdone;
     std::deque<int> wjobs;
@@ -764,6 +766,7 @@ int slafb_create(slafb_ctx **out, int device, int64_t max_rows, int64_t max_cell
         CUC(cudaHostGetDevicePointer(reinterpret_cast<void **>(&s.h_counters_dev), s.h_counters, 0));
         CUC(cudaHostAlloc(&s.h_perm, ((size_t)max_cells + 1) * sizeof(int32_t), cudaHostAllocMapped | cudaHostAllocPortable));
         CUC(cudaHostGetDevicePointer(reinterpret_cast<void **>(&s.h_perm_dev), s.h_perm, 0));
+        CUC(cudaHostAlloc(&s.h_seg, (2 * (size_t)max_cells + 2) * sizeof(uint32_t), cudaHostAllocPortable));
         s.h_draws = (uint32_t *)malloc(((size_t)max_cells + 1) * sizeof(uint32_t));
         if (!s.h_draws) { slafb_destroy(ctx); return fail(nullptr, SLAFB_ERR_INVALID, "out of host memory"); }
         cudaEvent_t *plain[] = {&s.ev_front, &s.ev_done, &s.ev_in, &s.ev_loaded, &s.ev_perm};
@@ -786,7 +789,7 @@ int slafb_destroy(slafb_ctx *ctx) {
             ctx->wstop = true;
         }
         ctx->wcv.notify_all();
-        ctx->worker.join();
+        for (auto &w : ctx->worker) if (w.joinable()) w.join();
     }
     if (ctx->s_in) cudaStreamSynchronize(ctx->s_in);
     for (int i = 0; i < kSlots; i++) {
@@ -796,6 +799,7 @@ int slafb_destroy(slafb_ctx *ctx) {
         cudaFree(s.in_cell); cudaFree(s.in_gene); cudaFree(s.in_value);
         if (s.h_counters) cudaFreeHost(s.h_counters);
         if (s.h_perm) cudaFreeHost(s.h_perm);
+        if (s.h_seg) cudaFreeHost(s.h_seg);
         free(s.h_draws);
         cudaEvent_t evs[] = {s.ev_front, s.ev_done, s.ev_in, s.ev_loaded, s.ev_perm, s.t_h2d0, s.t_h2d1, s.t_k1a, s.t_k1b, s.t_k2a, s.t_k2b, s.t_k2c};
         for (auto e : evs) if (e) cudaEventDestroy(e);
@@ -868,8 +872,12 @@ int slafb_submit_segments(slafb_ctx *ctx, const slafb_coo *pieces, int32_t n_pie
     // the segment table comes from the host (8 bytes per cell): no cell column crosses the bus and no CSR build runs
     CU(ctx, cudaMemsetAsync(s.counters, 0, 8 * sizeof(uint32_t), sf));
     if (n_cells > 0) {
-        CU(ctx, cudaMemcpyAsync(s.seg_start, seg_start, (size_t)(n_cells + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, sf));
-        CU(ctx, cudaMemcpyAsync(s.seg_cell, seg_cell, (size_t)n_cells * sizeof(uint32_t), cudaMemcpyHostToDevice, sf));
+        // through the slot's own pinned block: the caller's arrays may be pageable (a pageable async copy stalls the
+        // copy stream behind the driver's staging) and need not outlive this call
+        memcpy(s.h_seg, seg_start, (size_t)(n_cells + 1) * sizeof(uint32_t));
+        memcpy(s.h_seg + n_cells + 1, seg_cell, (size_t)n_cells * sizeof(uint32_t));
+        CU(ctx, cudaMemcpyAsync(s.seg_start, s.h_seg, (size_t)(n_cells + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, sf));
+        CU(ctx, cudaMemcpyAsync(s.seg_cell, s.h_seg + n_cells + 1, (size_t)n_cells * sizeof(uint32_t), cudaMemcpyHostToDevice, sf));
     }
     CU(ctx, cudaEventRecord(s.ev_front, sf));
     if (total > 0) {
@@ -917,7 +925,7 @@ int slafb_prepare_shuffle(slafb_ctx *ctx, int32_t slot, int64_t seed) {
     {
         std::lock_guard<std::mutex> lk(ctx->wm);
         if (!ctx->wstarted) {
-            ctx->worker = std::thread(shuffle_worker, ctx);
+            for (auto &w : ctx->worker) w = std::thread(shuffle_worker, ctx);
             ctx->wstarted = true;
         }
         s.prep_seed = seed;
