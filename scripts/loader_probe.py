@@ -81,4 +81,8 @@ for epoch_mode in modes:
     print(f"[{epoch_mode}] {n} cells in {t1 - t0:.3f}s ({n / (t1 - t0):,.0f} cells/s incl. start-up; steady {(n - n0) / (t1 - t_first):,.0f} cells/s)")
     for k, v in stages.items():
         print(f"   {k:10s} n={len(v):3d} mean={1e3 * np.mean(v):8.3f} ms  first={1e3 * v[0]:8.3f} ms  total={np.sum(v):.3f}s")
+    if proc._engine is not None:
+        t = proc._engine.timing()
+        print("   library: host_submit %.3f ms/batch, host_collect %.3f ms/batch, wait %.3f ms/batch over %d batches" % (
+            t["host_submit_ms"] / max(1, t["batches"]), t["host_collect_ms"] / max(1, t["batches"]), t["host_wait_ms"] / max(1, t["batches"]), t["batches"]))
     proc.close()

@@ -24,6 +24,7 @@
 #include <mutex>
 #include <new>
 #include <thread>
+#include <vector>
 
 #include "../../include/slaf_b200.h"
 #include "kernels.cuh"
@@ -42,6 +43,7 @@ constexpr int kHelpers = 2;   // host threads preparing CPython-exact shuffles (
 
 struct Slot {
     bool in_flight = false;
+    uint64_t freed_at = 0;             // release order (pick_slot)
     // device scratch
     uint32_t *seg_start = nullptr, *seg_cell = nullptr;
     int32_t *perm_dev = nullptr;
@@ -58,6 +60,8 @@ struct Slot {
     int64_t prep_seed = 0;
     int64_t prep_cells = -1;
     int32_t *h_perm = nullptr;
+    char *h_small = nullptr;           // pinned scratch small pageable host pieces are staged through (three column regions)
+    size_t small_rows = 0;             // rows per column region of h_small
     uint32_t *h_seg = nullptr;         // pinned copy of a caller-supplied segment table (submit_segments): [C + 1] starts, then [C] cell ids
     uint32_t *h_draws = nullptr;    // scratch of the host shuffle (plain malloc)
     // batch description (device pointers actually used by the kernels)
@@ -86,7 +90,7 @@ struct slafb_ctx {
     cudaStream_t s_aux = nullptr;      // small device-to-host reads that must not queue behind the big H2D copies
     cudaStream_t s_perm = nullptr;     // the helper thread's permutation uploads
     Slot slot[kSlots];
-    int next_slot = 0;
+    uint64_t free_seq = 0;
     unsigned long long *tile_state = nullptr;
     uint32_t *ticket = nullptr;
     uint32_t ticket_base = 0, epoch = 0;
@@ -366,6 +370,76 @@ void fill_tok_args(slafb_ctx *ctx, Slot &s, const slafb_params *p, TokArgs &a, u
     a.host_slow = nullptr;
 }
 
+// The slot for the next batch: a free one whose previous tokenization has already finished (reusing it costs no wait) and,
+// among those, one that already owns staging columns (no allocation); otherwise the free slot released longest ago, which
+// submit then waits for.  A feeder that keeps one or two batches in flight therefore touches two or three slots (and their
+// 12 B/row of staging), a deep pipeline all eight.
+int pick_slot(slafb_ctx *ctx) {
+    int ready_alloc = -1, ready = -1, oldest = -1;
+    for (int i = 0; i < kSlots; i++) {
+        Slot &s = ctx->slot[i];
+        if (s.in_flight) continue;
+        if (oldest < 0 || s.freed_at < ctx->slot[oldest].freed_at) oldest = i;
+        bool done = true;
+        if (s.ev_done && cudaEventQuery(s.ev_done) != cudaSuccess) { done = false; cudaGetLastError(); }
+        if (!done) continue;
+        if (s.in_cell) { if (ready_alloc < 0 || s.freed_at < ctx->slot[ready_alloc].freed_at) ready_alloc = i; }
+        else if (ready < 0 || s.freed_at < ctx->slot[ready].freed_at) ready = i;
+    }
+    return ready_alloc >= 0 ? ready_alloc : ready >= 0 ? ready : oldest;
+}
+
+// Small host pieces in pageable memory (the host feeder's partial cells: a few thousand rows) are copied into the slot's
+// pinned scratch first.  A pageable cudaMemcpyAsync makes the calling thread wait until the copy stream has drained, which
+// would tie the feeder to the copy engine exactly when it tries to run ahead of it; big pageable pieces are left to the
+// driver.  `src` receives the pointers to copy from, per piece: {cell, gene, value}.
+struct PieceSrc { const void *col[3]; };
+constexpr size_t kSmallPieceRows = 1u << 16;      // per piece
+constexpr size_t kSmallTotalRows = 1u << 21;      // per batch (8 MiB per column region at most)
+
+bool is_pageable_host(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+int stage_small_pieces(slafb_ctx *ctx, Slot &s, const slafb_coo *pieces, int n_pieces, bool with_cell, std::vector<PieceSrc> &src) {
+    src.resize((size_t)n_pieces);
+    std::vector<char> take((size_t)n_pieces, 0);
+    size_t rows = 0;
+    for (int i = 0; i < n_pieces; i++) {
+        const slafb_coo &p = pieces[i];
+        src[i] = PieceSrc{{p.cell, p.gene, p.value}};
+        const size_t n = (size_t)p.n_rows;
+        if (p.location != SLAFB_LOC_HOST || n == 0 || n > kSmallPieceRows || rows + n > kSmallTotalRows) continue;
+        if (!(is_pageable_host(p.gene) || is_pageable_host(p.value) || (with_cell && is_pageable_host(p.cell)))) continue;
+        take[i] = 1;
+        rows += n;
+    }
+    if (!rows) return SLAFB_OK;
+    if (rows > s.small_rows) {
+        if (s.h_small) CU(ctx, cudaFreeHost(s.h_small));
+        s.h_small = nullptr; s.small_rows = 0;
+        size_t cap = 1u << 14;
+        while (cap < rows) cap <<= 1;
+        CU(ctx, cudaHostAlloc(&s.h_small, cap * 12, cudaHostAllocPortable));
+        s.small_rows = cap;
+    }
+    const size_t width[3] = {4, dtype_size(pieces[0].gene_dtype), dtype_size(pieces[0].value_dtype)};
+    size_t off = 0;
+    for (int i = 0; i < n_pieces; i++) {
+        if (!take[i]) continue;
+        const size_t n = (size_t)pieces[i].n_rows;
+        for (int c = with_cell ? 0 : 1; c < 3; c++) {
+            char *dst = s.h_small + (size_t)c * s.small_rows * 4 + off * width[c];
+            memcpy(dst, src[i].col[c], n * width[c]);
+            src[i].col[c] = dst;
+        }
+        off += n;
+    }
+    return SLAFB_OK;
+}
+
 // front half: (H2D) + K1 + count read-back, on the side stream.  The batch is the concatenation of
 // `n_pieces` row blocks (the host feeder's partial cells + fragment chunks, datasets.py:880-888):
 // host pieces are copied back to back into the slot's staging columns straight from where they
@@ -409,8 +483,11 @@ int front(slafb_ctx *ctx, Slot &s, const slafb_coo *pieces, int n_pieces, cudaSt
     CU(ctx, cudaEventRecord(s.ev_in, caller));
     CU(ctx, cudaStreamWaitEvent(sf, s.ev_in, 0));
     bool staged = false;
+    std::vector<PieceSrc> src;
     if (in->location == SLAFB_LOC_HOST || n_pieces > 1) {
         int rc = ensure_staging(ctx, s);
+        if (rc) return rc;
+        rc = stage_small_pieces(ctx, s, pieces, n_pieces, true, src);
         if (rc) return rc;
         const cudaMemcpyKind kind = in->location == SLAFB_LOC_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
         if (s.sample) CU(ctx, cudaEventRecord(s.t_h2d0, sf));
@@ -420,7 +497,7 @@ int front(slafb_ctx *ctx, Slot &s, const slafb_coo *pieces, int n_pieces, cudaSt
         size_t off = 0;
         for (int i = 0; i < n_pieces; i++) {
             const size_t n = (size_t)pieces[i].n_rows;
-            if (n) CU(ctx, cudaMemcpyAsync(static_cast<char *>(s.in_cell) + off * 4, pieces[i].cell, n * 4, kind, sf));
+            if (n) CU(ctx, cudaMemcpyAsync(static_cast<char *>(s.in_cell) + off * 4, src[i].col[0], n * 4, kind, sf));
             off += n;
         }
         staged = true;
@@ -473,13 +550,13 @@ int front(slafb_ctx *ctx, Slot &s, const slafb_coo *pieces, int n_pieces, cudaSt
         size_t off = 0;
         for (int i = 0; i < n_pieces; i++) {
             const size_t n = (size_t)pieces[i].n_rows;
-            if (n) CU(ctx, cudaMemcpyAsync(static_cast<char *>(s.in_gene) + off * gsz, pieces[i].gene, n * gsz, kind, sf));
+            if (n) CU(ctx, cudaMemcpyAsync(static_cast<char *>(s.in_gene) + off * gsz, src[i].col[1], n * gsz, kind, sf));
             off += n;
         }
         off = 0;
         for (int i = 0; i < n_pieces; i++) {
             const size_t n = (size_t)pieces[i].n_rows;
-            if (n) CU(ctx, cudaMemcpyAsync(static_cast<char *>(s.in_value) + off * vsz, pieces[i].value, n * vsz, kind, sf));
+            if (n) CU(ctx, cudaMemcpyAsync(static_cast<char *>(s.in_value) + off * vsz, src[i].col[2], n * vsz, kind, sf));
             off += n;
         }
         if (s.sample) { CU(ctx, cudaEventRecord(s.t_h2d1, sf)); s.timed_h2d = true; }
@@ -800,6 +877,7 @@ int slafb_destroy(slafb_ctx *ctx) {
         if (s.h_counters) cudaFreeHost(s.h_counters);
         if (s.h_perm) cudaFreeHost(s.h_perm);
         if (s.h_seg) cudaFreeHost(s.h_seg);
+        if (s.h_small) cudaFreeHost(s.h_small);
         free(s.h_draws);
         cudaEvent_t evs[] = {s.ev_front, s.ev_done, s.ev_in, s.ev_loaded, s.ev_perm, s.t_h2d0, s.t_h2d1, s.t_k1a, s.t_k1b, s.t_k2a, s.t_k2b, s.t_k2c};
         for (auto e : evs) if (e) cudaEventDestroy(e);
@@ -817,15 +895,14 @@ int slafb_destroy(slafb_ctx *ctx) {
 int slafb_submit_pieces(slafb_ctx *ctx, const slafb_coo *pieces, int32_t n_pieces, void *stream, int32_t *slot) {
     if (!ctx || !slot) return fail(ctx, SLAFB_ERR_INVALID, "ctx / slot is NULL");
     CU(ctx, cudaSetDevice(ctx->device));
-    const int i = ctx->next_slot;
+    const int i = pick_slot(ctx);
+    if (i < 0) return fail(ctx, SLAFB_ERR_BUSY, "all %d pipeline slots hold batches that were not collected yet", kSlots);
     Slot &s = ctx->slot[i];
-    if (s.in_flight) return fail(ctx, SLAFB_ERR_BUSY, "pipeline slot %d not collected yet", i);
     const double t0 = now_ms();
     int rc = front(ctx, s, pieces, n_pieces, static_cast<cudaStream_t>(stream));
     ctx->acc.host_submit_ms += now_ms() - t0;
     if (rc) return rc;
     s.in_flight = true;
-    ctx->next_slot = (i + 1) % kSlots;
     *slot = i;
     return SLAFB_OK;
 }
@@ -834,9 +911,9 @@ int slafb_submit_segments(slafb_ctx *ctx, const slafb_coo *pieces, int32_t n_pie
                           int64_t n_cells, void *stream, int32_t *slot) {
     if (!ctx || !slot || !pieces || n_pieces < 1) return fail(ctx, SLAFB_ERR_INVALID, "bad ctx / slot / pieces");
     CU(ctx, cudaSetDevice(ctx->device));
-    const int si = ctx->next_slot;
+    const int si = pick_slot(ctx);
+    if (si < 0) return fail(ctx, SLAFB_ERR_BUSY, "all %d pipeline slots hold batches that were not collected yet", kSlots);
     Slot &s = ctx->slot[si];
-    if (s.in_flight) return fail(ctx, SLAFB_ERR_BUSY, "pipeline slot %d not collected yet", si);
     const double t0 = now_ms();
     int64_t total = 0;
     for (int i = 0; i < n_pieces; i++) {
@@ -884,19 +961,22 @@ int slafb_submit_segments(slafb_ctx *ctx, const slafb_coo *pieces, int32_t n_pie
         if (in->location == SLAFB_LOC_HOST || n_pieces > 1) {
             int rc = ensure_staging(ctx, s);
             if (rc) return rc;
+            std::vector<PieceSrc> src;
+            rc = stage_small_pieces(ctx, s, pieces, n_pieces, false, src);
+            if (rc) return rc;
             const cudaMemcpyKind kind = in->location == SLAFB_LOC_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
             const size_t gsz = dtype_size(in->gene_dtype), vsz = dtype_size(in->value_dtype);
             if (s.sample) CU(ctx, cudaEventRecord(s.t_h2d0, sf));
             size_t off = 0;
             for (int i = 0; i < n_pieces; i++) {
                 const size_t n = (size_t)pieces[i].n_rows;
-                if (n) CU(ctx, cudaMemcpyAsync(static_cast<char *>(s.in_gene) + off * gsz, pieces[i].gene, n * gsz, kind, sf));
+                if (n) CU(ctx, cudaMemcpyAsync(static_cast<char *>(s.in_gene) + off * gsz, src[i].col[1], n * gsz, kind, sf));
                 off += n;
             }
             off = 0;
             for (int i = 0; i < n_pieces; i++) {
                 const size_t n = (size_t)pieces[i].n_rows;
-                if (n) CU(ctx, cudaMemcpyAsync(static_cast<char *>(s.in_value) + off * vsz, pieces[i].value, n * vsz, kind, sf));
+                if (n) CU(ctx, cudaMemcpyAsync(static_cast<char *>(s.in_value) + off * vsz, src[i].col[2], n * vsz, kind, sf));
                 off += n;
             }
             if (s.sample) { CU(ctx, cudaEventRecord(s.t_h2d1, sf)); s.timed_h2d = true; }
@@ -908,7 +988,6 @@ int slafb_submit_segments(slafb_ctx *ctx, const slafb_coo *pieces, int32_t n_pie
     CU(ctx, cudaEventRecord(s.ev_loaded, sf));
     ctx->acc.host_submit_ms += now_ms() - t0;
     s.in_flight = true;
-    ctx->next_slot = (si + 1) % kSlots;
     *slot = si;
     return SLAFB_OK;
 }
@@ -953,6 +1032,7 @@ int slafb_collect(slafb_ctx *ctx, int32_t slot, const slafb_params *p, const sla
         settle_prepared(ctx, s);        // the helper must be done with this slot's buffers before it is reused
         s.prep_state.store(0);
         s.in_flight = false;
+        s.freed_at = ++ctx->free_seq;
     }
     return rc;
 }
@@ -1029,6 +1109,7 @@ int slafb_collect_csr(slafb_ctx *ctx, int32_t slot, const slafb_params *p, int64
     settle_prepared(ctx, s);
     s.prep_state.store(0);
     s.in_flight = false;
+    s.freed_at = ++ctx->free_seq;
     return rc;
 }
 
@@ -1040,8 +1121,9 @@ int slafb_window(slafb_ctx *ctx, const slafb_coo *in, const slafb_params *p, int
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int rc = check_params(ctx, p);
     if (rc) return rc;
-    Slot &s = ctx->slot[ctx->next_slot];
-    if (s.in_flight) return fail(ctx, SLAFB_ERR_BUSY, "pipeline slot busy");
+    const int wi = pick_slot(ctx);
+    if (wi < 0) return fail(ctx, SLAFB_ERR_BUSY, "all %d pipeline slots hold batches that were not collected yet", kSlots);
+    Slot &s = ctx->slot[wi];
     rc = front(ctx, s, in, 1, st);
     if (rc) return rc;
     bool use_perm = false;

@@ -96,6 +96,23 @@ class RawPrefetchBatch:
 PrefetchBatch = TokenizedPrefetchBatch | RawPrefetchBatch
 
 
+@dataclass
+class _Staged:
+    """One load of the fused route between reading its rows and tokenizing them (see ``load_prefetch_batch``)."""
+
+    body: list                       # rows read from the source, without the partial cells put in front
+    pieces: list                     # partial cells + body: what is (or will be) submitted
+    flush: bool                      # end-of-data flush of the pending partial cells: every cell counts as complete
+    batch_id: int
+    epoch: int
+    seed: int
+    start_time: float
+    eng: Any = None
+    slot: int | None = None          # None: not submitted (yet)
+    pred: tuple | None = None        # (cell id, rows) of the one cell predicted to stay incomplete; () = none; None = no prediction
+    stash: dict | None = None        # the predicted partial_cell_data after this load
+
+
 def _runs(cell: np.ndarray):
     """(starts, ends, ids) of the maximal runs of equal ids, in row order (host, O(R))."""
     n = len(cell)
@@ -324,7 +341,8 @@ class PrefetchBatchProcessor:
             {"lance_loading": [], "window": [], "shuffle": [], "tokenize": [], "total": [], "cells_processed": []}
             if log_metrics else None)
         self._engine: HotPathEngine | None = None
-        self._staging = _Staging(depth=2, threads=copy_threads)
+        self._staging = _Staging(depth=3, threads=copy_threads)     # three: with the look-ahead two loads can be in flight while a third is assembled
+        self._ahead: _Staged | StopIteration | None = None
         self._read_pool: ThreadPoolExecutor | None = None
 
     # ------------------------------------------------------------------ readers / epochs
@@ -345,6 +363,7 @@ class PrefetchBatchProcessor:
     def reset_for_epoch(self, epoch: int) -> None:
         if epoch < 0 or epoch >= self.n_epochs:
             raise ValueError(f"Invalid epoch {epoch}. Must be 0 <= epoch < {self.n_epochs}")
+        self._drop_ahead()
         self.current_epoch = epoch
         self.batch_id = 0
         self.partial_cell_data = {}
@@ -463,8 +482,9 @@ class PrefetchBatchProcessor:
         raise StopIteration("No more epochs available") from None
 
     # ------------------------------------------------------------------ completeness (host, C entries)
-    def _complete_mask(self, seg_cell: np.ndarray, seg_len: np.ndarray) -> np.ndarray:
-        """Which cells of the combined rows are complete (datasets.py:891-953)."""
+    def _complete_mask(self, seg_cell: np.ndarray, seg_len: np.ndarray, flush: bool | None = None) -> np.ndarray:
+        """Which cells of the combined rows are complete (datasets.py:891-953).  ``flush``: the load is the end-of-data flush
+        of the non-MoS modes (taken from the processor's flag when not given)."""
         if self.use_mixture_of_scanners:
             csi = np.asarray(self.slaf_array._cell_start_index)
             ids = seg_cell.astype(np.int64)
@@ -477,8 +497,9 @@ class PrefetchBatchProcessor:
                 if not done.any():
                     return np.ones(len(seg_cell), bool)
             return done
-        if self._non_mos_pending_tail_flush:
-            self._non_mos_pending_tail_flush = False
+        if flush is None:
+            flush, self._non_mos_pending_tail_flush = self._non_mos_pending_tail_flush, False
+        if flush:
             return np.ones(len(seg_cell), bool)
         return seg_cell < seg_cell.max()
 
@@ -523,7 +544,21 @@ class PrefetchBatchProcessor:
                 and type(self.tokenizer.window).__module__ == "slaf_b200.ml.aggregators")
 
     # ------------------------------------------------------------------ the hot path
+    def _lookahead_ok(self) -> bool:
+        """The fused routes without mixture-of-scanners read ahead: the rows of load i+1 are submitted (H2D + CSR build) before
+        the host waits for the segment table of load i.  What load i+1 needs from load i are its incomplete boundary cells;
+        there (datasets.py:931-953) that is always the cell with the largest id, which for SLAF's cell-sorted tables is the last
+        run of the last piece -- predicted on the host from the rows themselves, checked against the segment table afterwards
+        (``_finish``), and redone from the table if the prediction was wrong (tables that are not sorted by cell)."""
+        if self.use_mixture_of_scanners or self.use_cell_start_index:
+            return False
+        if self.raw_mode:
+            return self.device_raw and type(self.shuffle) in (RandomShuffle, StratifiedShuffle)
+        return self._fused_ok()
+
     def load_prefetch_batch(self) -> PrefetchBatch:
+        if self._lookahead_ok():
+            return self._load_with_lookahead()
         while True:
             start_time = time.time()
             nxt = self._next_pieces()
@@ -539,18 +574,116 @@ class PrefetchBatchProcessor:
                 continue
             seed = self.seed + self.batch_id + self.current_epoch * 10000               # datasets.py:1016
             if self.raw_mode and self.device_raw and type(self.shuffle) in (RandomShuffle, StratifiedShuffle):
-                out = self._load_raw_device(pieces, seed, start_time)
+                out = self._load_raw_device(self._sync_record(pieces, seed, start_time))
             elif self.raw_mode or not self._fused_ok():
                 out = self._load_on_host_frames(pieces, seed, start_time)
             else:
                 if self.tokenizer is None:
                     raise RuntimeError("Tokenizer is required for tokenized mode")
-                out = self._load_fused(pieces, seed, start_time)
+                out = self._load_fused(self._sync_record(pieces, seed, start_time))
             if out is None:                    # no complete cell in this chunk (datasets.py:1099-1102)
                 self.batch_id += 1
                 continue
             self.batch_id += 1
             return out
+
+    def _sync_record(self, pieces: list[CooChunk], seed: int, start_time: float) -> _Staged:
+        flush, self._non_mos_pending_tail_flush = self._non_mos_pending_tail_flush, False
+        return _Staged(body=pieces, pieces=pieces, flush=flush, batch_id=self.batch_id, epoch=self.current_epoch, seed=seed,
+                       start_time=start_time)
+
+    # -- look-ahead ------------------------------------------------------------------------------
+    def _load_with_lookahead(self) -> PrefetchBatch:
+        if self.tokenizer is None and not self.raw_mode:
+            raise RuntimeError("Tokenizer is required for tokenized mode")
+        while True:
+            cur, self._ahead = self._ahead, None
+            if cur is None:
+                cur = self._stage()
+            if isinstance(cur, StopIteration):
+                raise cur
+            if cur.slot is None:
+                self._submit_staged(cur)                       # deferred: the engine had to grow, nothing else is in flight now
+            if cur.pred is not None:
+                try:
+                    self._ahead = self._stage()                # the next load's rows go out before this one's table is awaited
+                except StopIteration as end:
+                    self._ahead = end
+            out = self._load_raw_device(cur) if self.raw_mode else self._load_fused(cur)
+            if out is not None:
+                return out
+
+    def _stage(self) -> _Staged:
+        """Read the next load, predict its incomplete cell, submit its rows.  Raises StopIteration at the end of the last epoch."""
+        while True:
+            start_time = time.time()
+            n_partials = len(self.partial_cell_data)
+            nxt = self._next_pieces()
+            if nxt is None:
+                continue
+            pieces, _count = nxt
+            flush, self._non_mos_pending_tail_flush = self._non_mos_pending_tail_flush, False
+            body = [] if flush else [p for p in pieces[n_partials:] if len(p)]
+            pieces = [p for p in pieces if len(p)]
+            self._record_timing("lance_loading", time.time() - start_time)
+            if sum(len(p) for p in pieces) == 0:
+                self.batch_id += 1
+                continue
+            rec = _Staged(body=body, pieces=pieces, flush=flush, batch_id=self.batch_id, epoch=self.current_epoch,
+                          seed=self.seed + self.batch_id + self.current_epoch * 10000, start_time=start_time)     # datasets.py:1016
+            self.batch_id += 1
+            self._predict(rec)
+            eng = self._engine
+            n_rows = sum(len(p) for p in pieces)
+            if eng is not None and eng.max_rows >= n_rows:
+                self._submit_staged(rec)                       # otherwise deferred until nothing is in flight (the engine is re-created)
+            return rec
+
+    def _predict(self, rec: _Staged) -> None:
+        """partial_cell_data as it will be after ``rec`` (non-MoS rule: the cell with the largest id waits for the next load;
+        the end-of-data flush leaves nothing).  The rows are copied: the pieces may be recycled buffers."""
+        if rec.flush:
+            rec.pred, rec.stash = (), {}
+        else:
+            x = rec.pieces[-1].cell[-1]
+            parts, total = [], 0
+            for p in reversed(rec.pieces):
+                n = _tail_run(p.cell, x)
+                if n == 0:
+                    break
+                parts.append(p.slice(len(p) - n, len(p)).copy())
+                total += n
+                if n < len(p):
+                    break
+            parts.reverse()
+            rec.pred, rec.stash = (int(x), total), {int(x): concat_chunks(parts)}
+        self.partial_cell_data = dict(rec.stash)
+
+    def _submit_staged(self, rec: _Staged) -> None:
+        rec.eng = self._engine_for(sum(len(p) for p in rec.pieces))
+        rec.slot, rec.pieces = self._submit(rec.eng, rec.pieces)
+
+    def _unsubmit_ahead(self) -> None:
+        """Take the look-ahead's rows back off the device (its slot is released; it is submitted again when its turn comes)."""
+        a = self._ahead
+        if isinstance(a, _Staged) and a.slot is not None:
+            a.eng.release(a.slot)
+            a.slot = a.eng = None
+
+    def _drop_ahead(self) -> None:
+        self._unsubmit_ahead()
+        self._ahead = None
+
+    def _restage_ahead(self, stash: dict) -> None:
+        """The prediction for the current load was wrong: rebuild the look-ahead from the true partial cells."""
+        a = self._ahead
+        if not isinstance(a, _Staged):
+            self._ahead = None                                  # (an end-of-data marker is re-derived: pending cells get their flush load)
+            self.partial_cell_data = stash
+            return
+        a.pieces = [p for p in list(stash.values()) + a.body if len(p)]
+        self.partial_cell_data = {}
+        self._predict(a)                                        # sets partial_cell_data to what follows the look-ahead
 
     #: pieces smaller than this are handed to the driver as they are (its pageable path copies them synchronously)
     SMALL_PIECE_ROWS = 1 << 15
@@ -594,45 +727,64 @@ class PrefetchBatchProcessor:
         ids = seg_cell.astype(np.int32) if signed else seg_cell.astype(np.uint32)
         return slot, pieces, seg_start, ids
 
-    def _front(self, pieces: list[CooChunk]):
+    def _front(self, rec: _Staged):
         """submit -> segment table -> (splice safety net) -> completeness -> partial stash.
         Returns (engine, slot, indices of the complete cells in first-appearance order, their row counts)."""
+        pieces = rec.pieces
         n_rows = sum(len(p) for p in pieces)
-        eng = self._engine_for(n_rows)
-        if self.use_cell_start_index and all(p.row_lo is not None for p in pieces):
+        if rec.slot is None and self.use_cell_start_index and all(p.row_lo is not None for p in pieces):
+            eng = self._engine_for(n_rows)
             slot, pieces, seg_start, seg_cell = self._submit_with_csi(eng, pieces)
         else:
-            slot, pieces = self._submit(eng, pieces)
+            if rec.slot is None:
+                self._submit_staged(rec)
+            eng, slot, pieces = rec.eng, rec.slot, rec.pieces
             try:
                 seg_start, seg_cell = eng.segments(slot)
             except N.SlafB200Error as err:
                 if err.code != N.ERR_CAPACITY:
                     raise
                 eng.release(slot)                                   # more cells than the segment tables hold: size for the worst case
+                self._unsubmit_ahead()
                 eng = self._engine_for(n_rows, all_cells=True)
                 slot, pieces = self._submit(eng, pieces)
                 seg_start, seg_cell = eng.segments(slot)
-            if len(np.unique(seg_cell)) != len(seg_cell):
+            if not (seg_cell.size < 2 or bool(np.all(seg_cell[1:] > seg_cell[:-1]))) and len(np.unique(seg_cell)) != len(seg_cell):
                 # a cell re-joined from two separated runs (partial + continuation with other chunks in
                 # between): splice on the host like partition_by does, then resubmit (rare)
                 eng.release(slot)
+                self._unsubmit_ahead()
                 slot, pieces = self._submit(eng, _regroup_segments(pieces, seg_start, seg_cell))
                 seg_start, seg_cell = eng.segments(slot)
         seg_len = np.diff(seg_start.astype(np.int64))
-        complete = self._complete_mask(seg_cell, seg_len)
-        self._stash_partials(pieces, seg_start, seg_cell, complete)
+        complete = self._complete_mask(seg_cell, seg_len, rec.flush)
+        if rec.pred is not None:
+            bad = np.flatnonzero(~complete)
+            C = len(seg_cell)
+            as_predicted = (bad.size == 0) if rec.pred == () else \
+                (bad.size == 1 and int(bad[0]) == C - 1 and (int(seg_cell[-1]), int(seg_len[-1])) == rec.pred)
+            if not as_predicted:
+                self._unsubmit_ahead()
+                keep = self.partial_cell_data
+                self._stash_partials(pieces, seg_start, seg_cell, complete)
+                rec.stash, true_stash = dict(self.partial_cell_data), self.partial_cell_data
+                self.partial_cell_data = keep
+                self._restage_ahead(true_stash)
+        else:
+            self._stash_partials(pieces, seg_start, seg_cell, complete)
+            rec.stash = dict(self.partial_cell_data)
         sel = np.flatnonzero(complete).astype(np.int32)
         return eng, slot, sel, seg_len
 
-    def _load_raw_device(self, pieces: list[CooChunk], seed: int, start_time: float) -> RawPrefetchBatch | None:
+    def _load_raw_device(self, rec: _Staged) -> RawPrefetchBatch | None:
         """Raw mode on the device: the complete cells of the batch as CSR tensors in shuffled
         order, cut into ``batch_size``-cell chunks (views; the row pointers are rebased per chunk)."""
         t0 = time.time()
-        eng, slot, sel, seg_len = self._front(pieces)
+        eng, slot, sel, seg_len = self._front(rec)
         if sel.size == 0:
             eng.release(slot)
             return None
-        order = sel[shuffle_perm(seed, sel.size)]
+        order = sel[shuffle_perm(rec.seed, sel.size)]
         csr = eng.collect_csr(slot, perm=order)
         ends = np.concatenate(([0], np.cumsum(seg_len[order])))            # row offsets per output cell, known on the host
         chunks = []
@@ -643,35 +795,35 @@ class PrefetchBatchProcessor:
                            "cell_ids": csr.cell_ids[lo:hi]})
         process_time = time.time() - t0
         self._record_timing("shuffle", process_time)
-        self._record_timing("total", time.time() - start_time)
+        self._record_timing("total", time.time() - rec.start_time)
         self._record_timing("cells_processed", 0, csr.n_cells)
         self.total_prefetch_cells += csr.n_cells
-        return RawPrefetchBatch(batch_id=self.batch_id, batch_dfs=chunks, cell_integer_ids=csr.cell_ids.cpu().tolist(),
+        return RawPrefetchBatch(batch_id=rec.batch_id, batch_dfs=chunks, cell_integer_ids=csr.cell_ids.cpu().tolist(),
                                 process_time=process_time, memory_mb=0.0)
 
-    def _load_fused(self, pieces: list[CooChunk], seed: int, start_time: float) -> TokenizedPrefetchBatch | None:
+    def _load_fused(self, rec: _Staged) -> TokenizedPrefetchBatch | None:
         t0 = time.time()
-        eng, slot, sel, _seg_len = self._front(pieces)
+        eng, slot, sel, _seg_len = self._front(rec)
         shuffle_time = time.time() - t0
         if sel.size == 0:
             eng.release(slot)
             return None
         t1 = time.time()
-        order = sel[shuffle_perm(seed, sel.size)]              # random.seed(seed); random.shuffle(chunks), samplers.py:89-96
+        order = sel[shuffle_perm(rec.seed, sel.size)]              # random.seed(seed); random.shuffle(chunks), samplers.py:89-96
         out = eng.collect(slot, perm=order, capacity_cells=int(order.size), **self._params())
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(eng.device))
         tokenize_time = time.time() - t1
-        total = time.time() - start_time
+        total = time.time() - rec.start_time
         self._record_timing("shuffle", shuffle_time)
         self._record_timing("window", 0.0)
         self._record_timing("tokenize", tokenize_time)
         self._record_timing("total", total)
         self._record_timing("cells_processed", 0, out.n_cells)
         self.total_prefetch_cells += out.n_cells
-        return TokenizedPrefetchBatch(batch_id=self.batch_id, input_ids=out.input_ids, attention_mask=out.attention_mask,
-                                      values=out.values, cell_ids=out.cell_ids, partial_cell_data=dict(self.partial_cell_data),
-                                      tokenize_time=tokenize_time, epoch=self.current_epoch, ready_event=ev)
+        return TokenizedPrefetchBatch(batch_id=rec.batch_id, input_ids=out.input_ids, attention_mask=out.attention_mask,
+                                      values=out.values, cell_ids=out.cell_ids, partial_cell_data=dict(rec.stash or {}),
+                                      tokenize_time=tokenize_time, epoch=rec.epoch, ready_event=ev)
 
     def _params(self) -> dict:
         return self.tokenizer.hot_path_params(use_binned_expressions=self.use_binned_expressions,
@@ -742,6 +894,10 @@ class PrefetchBatchProcessor:
                                       tokenize_time=tokenize_time, epoch=self.current_epoch)
 
     def close(self) -> None:
+        try:
+            self._drop_ahead()
+        except Exception:
+            pass
         if self._engine is not None:
             self._engine.close()
             self._engine = None
@@ -925,14 +1081,20 @@ class SLAFIterableDataset(IterableDataset):
             if self.output_device is not None and self.output_device.type == "cpu":
                 input_ids, attention_mask, cell_ids = input_ids.cpu(), attention_mask.cpu(), cell_ids.cpu()
                 values = values.cpu() if values is not None else None
-            num_cells = int(input_ids.shape[0])
-            for lo in range(0, num_cells, self.batch_size):
-                hi = min(lo + self.batch_size, num_cells)
-                batch = {"input_ids": input_ids[lo:hi], "attention_mask": attention_mask[lo:hi], "cell_ids": cell_ids[lo:hi]}
+            # batch_size-cell views of the prefetch batch (datasets.py:1885-1912); split() makes all views of a tensor in one call
+            if input_ids.shape[0] == 0:
+                continue
+            bs = self.batch_size
+            epoch = data.epoch if self.n_epochs > 1 else None
+            parts = [input_ids.split(bs), attention_mask.split(bs), cell_ids.split(bs)]
+            if values is not None:
+                parts.append(values.split(bs))
+            for views in zip(*parts):
+                batch = {"input_ids": views[0], "attention_mask": views[1], "cell_ids": views[2]}
                 if values is not None:
-                    batch["values"] = values[lo:hi]
-                if self.n_epochs > 1:
-                    batch["epoch"] = data.epoch
+                    batch["values"] = views[3]
+                if epoch is not None:
+                    batch["epoch"] = epoch
                 yield batch
 
     def __del__(self):

@@ -323,3 +323,99 @@ def test_cell_start_index_mismatch_is_detected(data):
     with pytest.raises(ValueError, match="_cell_start_index does not describe"):
         proc.load_prefetch_batch()
     proc.close()
+
+
+def _emulate_fragment_mode(cell, gene, value, rows_per_file, n_epochs, max_genes, seed=42):
+    """datasets.py:812-953 + 1011-1098 for by_fragment without mixture-of-scanners, with the numpy restatement: the rows with the
+    largest cell id of [partial + fragment] wait for the next load, the rest is tokenized in first-appearance order, shuffled."""
+    want = []
+    for epoch in range(n_epochs):
+        batch_id, partial = 0, None
+        frags = [(cell[lo:lo + rows_per_file], gene[lo:lo + rows_per_file], value[lo:lo + rows_per_file]) for lo in range(0, len(cell), rows_per_file)]
+        for frag in frags + [None]:
+            if frag is None:
+                if partial is None:
+                    break
+                comb, complete_mask = partial, np.ones(len(partial[0]), bool)
+            else:
+                comb = frag if partial is None else tuple(np.concatenate([p, f]) for p, f in zip(partial, frag))
+                complete_mask = comb[0] < comb[0].max()
+            complete = tuple(c[complete_mask] for c in comb)
+            partial = tuple(c[~complete_mask] for c in comb) if (~complete_mask).any() else None
+            if len(complete[0]):
+                want.append((epoch, batch_id, pr.hot_path(*complete, "geneformer", max_genes, seed=seed + batch_id + epoch * 10000)))
+            batch_id += 1
+    return want
+
+
+def _drain(proc):
+    got = []
+    try:
+        while True:
+            got.append(proc.load_prefetch_batch())
+    except StopIteration:
+        pass
+    return got
+
+
+def test_look_ahead_falls_back_when_the_table_is_not_sorted_by_cell(data):
+    """The look-ahead predicts the waiting cell as the last run of the load; with cell ids that are NOT ascending the cell with
+    the largest id sits somewhere else, the segment table contradicts the prediction and the next load is rebuilt from the
+    table -- batch composition, order, ids and epochs stay those of the reference's rule."""
+    rng = np.random.default_rng(3)
+    relabel = rng.permutation(N_CELLS).astype(data.cell.dtype)
+    cell = relabel[data.cell]                                   # runs stay contiguous, ids are shuffled
+    from slaf_b200.ml.sources import ArrayExpressionSource
+
+    arr = SyntheticSLAFArray(ArrayExpressionSource(cell, data.gene, data.value, 2500), np.zeros(N_CELLS + 1, np.int64), N_GENES)
+    tok = GeneformerTokenizer(arr, max_genes=32)
+    proc = PrefetchBatchProcessor(arr, RandomShuffle(), tok, seed=42, n_epochs=2, use_mixture_of_scanners=False, by_fragment=True, verbose=False)
+    assert proc._lookahead_ok()
+    got = _drain(proc)
+    want = _emulate_fragment_mode(cell, data.gene, data.value, 2500, 2, 32)
+    assert len(got) == len(want) and len(got) > 4
+    for g, (epoch, batch_id, (ids, mask, _vals, cids)) in zip(got, want):
+        assert (g.epoch, g.batch_id) == (epoch, batch_id)
+        assert_same(g.cell_ids.cpu().numpy(), cids, "cell order")
+        assert_same(g.input_ids.cpu().numpy(), ids, "ids")
+        assert_same(g.attention_mask.cpu().numpy(), mask, "mask")
+    proc.close()
+
+
+def test_look_ahead_defers_the_submit_when_the_engine_has_to_grow(data):
+    from slaf_b200.engine import HotPathEngine
+
+    arr = _array(data, rows_per_file=2500)
+    tok = GeneformerTokenizer(arr, max_genes=32)
+    proc = PrefetchBatchProcessor(arr, RandomShuffle(), tok, seed=42, use_mixture_of_scanners=False, by_fragment=True, verbose=False)
+    proc._engine = small = HotPathEngine(0, max_rows=2510, max_cells=2510)     # the first load fits, partial + second fragment does not
+    got = _drain(proc)
+    assert proc._engine is not small and proc._engine.max_rows > 2510
+    want = _emulate_fragment_mode(data.cell, data.gene, data.value, 2500, 1, 32)
+    assert len(got) == len(want)
+    for g, (_epoch, batch_id, (ids, _mask, _vals, cids)) in zip(got, want):
+        assert g.batch_id == batch_id
+        assert_same(g.cell_ids.cpu().numpy(), cids, "cell order")
+        assert_same(g.input_ids.cpu().numpy(), ids, "ids")
+    assert [sorted(g.partial_cell_data) for g in got[:-1]] == [[int(g.cell_ids.max().item()) + 1] for g in got[:-1]]   # the waiting cell
+    assert got[-1].partial_cell_data == {}
+    proc.close()
+
+
+def test_look_ahead_reset_for_epoch_drops_the_submitted_load(data):
+    arr = _array(data, rows_per_file=2500)
+    tok = GeneformerTokenizer(arr, max_genes=32)
+    proc = PrefetchBatchProcessor(arr, RandomShuffle(), tok, seed=42, n_epochs=2, use_mixture_of_scanners=False, by_fragment=True, verbose=False)
+    first = proc.load_prefetch_batch()
+    second = proc.load_prefetch_batch()
+    assert proc._ahead is not None and (first.batch_id, second.batch_id) == (0, 1)
+    proc.reset_for_epoch(1)
+    assert proc._ahead is None and proc.batch_id == 0
+    again = _drain(proc)
+    want = [w for w in _emulate_fragment_mode(data.cell, data.gene, data.value, 2500, 2, 32) if w[0] == 1]
+    assert len(again) == len(want)
+    for g, (epoch, batch_id, (ids, _mask, _vals, cids)) in zip(again, want):
+        assert (g.epoch, g.batch_id) == (epoch, batch_id)
+        assert_same(g.cell_ids.cpu().numpy(), cids, "cell order")
+        assert_same(g.input_ids.cpu().numpy(), ids, "ids")
+    proc.close()

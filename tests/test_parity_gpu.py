@@ -136,6 +136,26 @@ def test_pipelined_submit_collect_two_in_flight(engine):
         compare(got, want, "scgpt_binned")
 
 
+def test_slots_out_of_order_collect_and_exhaustion(engine):
+    """Eight batches may be in flight; they can be collected in any order; a ninth submit is refused (SLAFB_ERR_BUSY) and
+    leaves the pipeline intact; a released slot is reused."""
+    batches = [synthetic.make_batch(120 + 10 * i, 20000, 300, seed=300 + i) for i in range(9)]
+    kw = dict(mode="geneformer", max_genes=256)
+    slots = [engine.submit(b.cell, b.gene, b.value, shuffle_seed=7 + i) for i, b in enumerate(batches[:8])]
+    assert sorted(slots) == list(range(8))
+    with pytest.raises(_native.SlafB200Error) as ei:
+        engine.submit(batches[8].cell, batches[8].gene, batches[8].value)
+    assert ei.value.code == _native.ERR_BUSY
+    order = [5, 0, 7, 2, 1, 6, 3, 4]
+    outs = {i: engine.collect(slots[i], shuffle_seed=7 + i, **kw) for i in order}
+    again = engine.submit(batches[8].cell, batches[8].gene, batches[8].value)
+    assert again in slots
+    outs[8] = engine.collect(again, shuffle_seed=15, **kw)
+    for i, b in enumerate(batches):
+        want = c_oracle.tokenize(b.cell, b.gene, b.value, "geneformer", 256, perm=py_perm(7 + i, b.n_cells))
+        compare(outs[i], want, "geneformer")
+
+
 def test_output_capacity_retry_and_errors(engine):
     b = synthetic.make_batch(200, 5000, 100, seed=9)
     got = engine.collect(engine.submit(b.cell, b.gene, b.value), mode="geneformer", max_genes=64, capacity_cells=3)
