@@ -420,7 +420,7 @@ int stage_small_pieces(slafb_ctx *ctx, Slot &s, const slafb_coo *pieces, int n_p
     if (rows > s.small_rows) {
         if (s.h_small) CU(ctx, cudaFreeHost(s.h_small));
         s.h_small = nullptr; s.small_rows = 0;
-        size_t cap = 1u << 14;
+        size_t cap = 1u << 18;       // 3 MiB: the pending cells of a 16-scanner feeder fit without ever growing
         while (cap < rows) cap <<= 1;
         CU(ctx, cudaHostAlloc(&s.h_small, cap * 12, cudaHostAllocPortable));
         s.small_rows = cap;

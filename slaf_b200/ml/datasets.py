@@ -109,8 +109,9 @@ class _Staged:
     start_time: float
     eng: Any = None
     slot: int | None = None          # None: not submitted (yet)
-    pred: tuple | None = None        # (cell id, rows) of the one cell predicted to stay incomplete; () = none; None = no prediction
+    pred: list | None = None         # [(cell id, rows), ...] of the cells predicted to stay incomplete, in row order; None = no prediction
     stash: dict | None = None        # the predicted partial_cell_data after this load
+    reads: list | None = None        # mixture-of-scanners: the draw (generator, chunks, last cell before) the pieces were built from
 
 
 def _runs(cell: np.ndarray):
@@ -402,49 +403,65 @@ class PrefetchBatchProcessor:
             self.generator_active[idx] = False
         return [g for g in got if len(g)], idx, False      # consecutive storage rows: kept as separate views, never copied
 
+    def _mos_read(self) -> tuple[str, list | None, int]:
+        """One mixture-of-scanners draw (datasets.py:672-760): ("rows", [(generator, chunks, its last cell before), ...], n) |
+        ("none", ...) nothing came back | ("flush", ...) every generator is exhausted and partial cells are pending |
+        ("epoch", ...) every generator is exhausted.  Advances the generators, does not touch partial_cell_data."""
+        active = [i for i, a in enumerate(self.generator_active) if a]
+        if not active:
+            return ("flush" if self.partial_cell_data else "epoch"), None, 0
+        n_to_sample = min(self.n_scanners, len(active))
+        selected = np.random.choice(active, size=n_to_sample, replace=False)      # datasets.py:689 (unseeded there too)
+        if self.parallelize_fragment_reads and len(selected) > 1:
+            if self._read_pool is None:
+                self._read_pool = ThreadPoolExecutor(max_workers=min(32, self.n_scanners))
+            results = list(self._read_pool.map(self._read_from_generator, [int(i) for i in selected]))
+        else:
+            results = [self._read_from_generator(int(i)) for i in selected]
+        reads = []
+        for got, idx, exhausted in results:
+            if exhausted:
+                self.generator_active[idx] = False
+                continue
+            if not got:
+                continue
+            reads.append((idx, got, self.generator_last_cells[idx]))
+            self.generator_last_cells[idx] = int(got[-1].cell[-1])
+        if not reads:
+            return "none", None, 0
+        return "rows", reads, len(reads)
+
+    @staticmethod
+    def _mos_build(reads: list, partials: dict) -> list[CooChunk]:
+        """Rows of one load in the order the reference concatenates them: a generator's own pending cell goes right in front of
+        its chunk (datasets.py:748-760), the other pending cells in front of everything (datasets.py:880-888), and runs of a
+        pending cell at the head / tail of a chunk are moved up behind it -- where partition_by would gather them.
+        ``partials`` is consumed (entries put in front of a chunk are popped)."""
+        body: list[CooChunk] = []
+        for _idx, got, last in reads:
+            if last is not None:
+                first_cell = int(got[0].cell[0])
+                if (first_cell == last or first_cell == last + 1) and last in partials:
+                    got = [partials.pop(last)] + got
+            body.extend(got)
+        return _splice_partials(partials, body)
+
     def _next_pieces(self) -> tuple[list[CooChunk], int] | None:
         """Rows of the next load: (pieces in row order, batch_count); None = epoch transition handled
         (caller loops).  Raises StopIteration at the end of the last epoch."""
         pieces: list[CooChunk] = []
         if self.use_mixture_of_scanners:
-            active = [i for i, a in enumerate(self.generator_active) if a]
-            if not active:
-                if self.partial_cell_data:
-                    pieces = list(self.partial_cell_data.values())
-                    self.partial_cell_data = {}
-                    self._mos_final_flush = True
-                    return pieces, 0
+            kind, reads, n_chunks = self._mos_read()
+            if kind == "flush":
+                pieces = list(self.partial_cell_data.values())
+                self.partial_cell_data = {}
+                self._mos_final_flush = True
+                return pieces, 0
+            if kind == "epoch":
                 return self._advance_epoch()
-            n_to_sample = min(self.n_scanners, len(active))
-            selected = np.random.choice(active, size=n_to_sample, replace=False)      # datasets.py:689 (unseeded there too)
-            if self.parallelize_fragment_reads and len(selected) > 1:
-                if self._read_pool is None:
-                    self._read_pool = ThreadPoolExecutor(max_workers=min(32, self.n_scanners))
-                results = list(self._read_pool.map(self._read_from_generator, [int(i) for i in selected]))
-            else:
-                results = [self._read_from_generator(int(i)) for i in selected]
-            body: list[CooChunk] = []
-            n_chunks = 0
-            for got, idx, exhausted in results:
-                if exhausted:
-                    self.generator_active[idx] = False
-                    continue
-                if not got:
-                    continue
-                last = self.generator_last_cells[idx]
-                if last is not None:
-                    first_cell = int(got[0].cell[0])
-                    if (first_cell == last or first_cell == last + 1) and last in self.partial_cell_data:
-                        got = [self.partial_cell_data.pop(last)] + got                        # datasets.py:748-760
-                self.generator_last_cells[idx] = int(got[-1].cell[-1])
-                body.extend(got)
-                n_chunks += 1
-            if not body:
+            if kind == "none":
                 return None
-            # the partial cells still pending go in front (datasets.py:880-888); runs of the same cell at the
-            # head / tail of a chunk are moved up behind them, which is where partition_by would gather them
-            pieces = _splice_partials(self.partial_cell_data, body)
-            return pieces, n_chunks
+            return self._mos_build(reads, self.partial_cell_data), n_chunks
         elif self.by_fragment:
             try:
                 fragment = next(self.fragment_iterator)
@@ -484,21 +501,19 @@ class PrefetchBatchProcessor:
     # ------------------------------------------------------------------ completeness (host, C entries)
     def _complete_mask(self, seg_cell: np.ndarray, seg_len: np.ndarray, flush: bool | None = None) -> np.ndarray:
         """Which cells of the combined rows are complete (datasets.py:891-953).  ``flush``: the load is the end-of-data flush
-        of the non-MoS modes (taken from the processor's flag when not given)."""
+        of the pending partial cells (taken from the processor's flag when not given)."""
+        if flush is None:
+            flush = self._take_flush_flag()
         if self.use_mixture_of_scanners:
             csi = np.asarray(self.slaf_array._cell_start_index)
             ids = seg_cell.astype(np.int64)
             expected = csi[ids + 1] - csi[ids]
             done = seg_len >= expected
-            if self._mos_final_flush:
+            if flush and not done.any():
                 # every generator is exhausted: nothing can complete these cells any more.  The reference
                 # would spin forever on such rows (datasets.py:660-668 + 1099-1102); emit them instead.
-                self._mos_final_flush = False
-                if not done.any():
-                    return np.ones(len(seg_cell), bool)
+                return np.ones(len(seg_cell), bool)
             return done
-        if flush is None:
-            flush, self._non_mos_pending_tail_flush = self._non_mos_pending_tail_flush, False
         if flush:
             return np.ones(len(seg_cell), bool)
         return seg_cell < seg_cell.max()
@@ -545,12 +560,12 @@ class PrefetchBatchProcessor:
 
     # ------------------------------------------------------------------ the hot path
     def _lookahead_ok(self) -> bool:
-        """The fused routes without mixture-of-scanners read ahead: the rows of load i+1 are submitted (H2D + CSR build) before
-        the host waits for the segment table of load i.  What load i+1 needs from load i are its incomplete boundary cells;
-        there (datasets.py:931-953) that is always the cell with the largest id, which for SLAF's cell-sorted tables is the last
-        run of the last piece -- predicted on the host from the rows themselves, checked against the segment table afterwards
-        (``_finish``), and redone from the table if the prediction was wrong (tables that are not sorted by cell)."""
-        if self.use_mixture_of_scanners or self.use_cell_start_index:
+        """The fused routes read ahead: the rows of load i+1 are submitted (H2D + CSR build) before the host waits for the
+        segment table of load i.  What load i+1 needs from load i are its incomplete cells (datasets.py:891-953).  In a table
+        sorted by cell only the cells at the head or tail of a piece can be cut, so the host predicts them from those runs
+        alone (``_predict``), checks the prediction against the segment table when it arrives (``_front``) and, if it was wrong
+        (rows not sorted by cell, an index that does not match), rebuilds the next load from the table."""
+        if self.use_cell_start_index:
             return False
         if self.raw_mode:
             return self.device_raw and type(self.shuffle) in (RandomShuffle, StratifiedShuffle)
@@ -588,9 +603,16 @@ class PrefetchBatchProcessor:
             return out
 
     def _sync_record(self, pieces: list[CooChunk], seed: int, start_time: float) -> _Staged:
-        flush, self._non_mos_pending_tail_flush = self._non_mos_pending_tail_flush, False
-        return _Staged(body=pieces, pieces=pieces, flush=flush, batch_id=self.batch_id, epoch=self.current_epoch, seed=seed,
-                       start_time=start_time)
+        return _Staged(body=pieces, pieces=pieces, flush=self._take_flush_flag(), batch_id=self.batch_id, epoch=self.current_epoch,
+                       seed=seed, start_time=start_time)
+
+    def _take_flush_flag(self) -> bool:
+        """Was the load just read the end-of-data flush of the pending partial cells?  (read and cleared)"""
+        if self.use_mixture_of_scanners:
+            flush, self._mos_final_flush = self._mos_final_flush, False
+        else:
+            flush, self._non_mos_pending_tail_flush = self._non_mos_pending_tail_flush, False
+        return flush
 
     # -- look-ahead ------------------------------------------------------------------------------
     def _load_with_lookahead(self) -> PrefetchBatch:
@@ -602,6 +624,8 @@ class PrefetchBatchProcessor:
                 cur = self._stage()
             if isinstance(cur, StopIteration):
                 raise cur
+            if not cur.pieces:                                  # a rebuilt flush load that turned out to have nothing left to flush
+                continue
             if cur.slot is None:
                 self._submit_staged(cur)                       # deferred: the engine had to grow, nothing else is in flight now
             if cur.pred is not None:
@@ -614,23 +638,37 @@ class PrefetchBatchProcessor:
                 return out
 
     def _stage(self) -> _Staged:
-        """Read the next load, predict its incomplete cell, submit its rows.  Raises StopIteration at the end of the last epoch."""
+        """Read the next load, predict its incomplete cells, submit its rows.  Raises StopIteration at the end of the last epoch."""
         while True:
             start_time = time.time()
-            n_partials = len(self.partial_cell_data)
-            nxt = self._next_pieces()
-            if nxt is None:
-                continue
-            pieces, _count = nxt
-            flush, self._non_mos_pending_tail_flush = self._non_mos_pending_tail_flush, False
-            body = [] if flush else [p for p in pieces[n_partials:] if len(p)]
+            reads = None
+            if self.use_mixture_of_scanners:
+                kind, reads, _n = self._mos_read()
+                if kind == "epoch":
+                    self._advance_epoch()
+                    continue
+                if kind == "none":
+                    continue
+                if kind == "flush":
+                    pieces, self.partial_cell_data, self._mos_final_flush = list(self.partial_cell_data.values()), {}, True
+                else:
+                    pieces = self._mos_build(reads, self.partial_cell_data)
+                body: list[CooChunk] = []
+            else:
+                n_partials = len(self.partial_cell_data)
+                nxt = self._next_pieces()
+                if nxt is None:
+                    continue
+                pieces, _count = nxt
+                body = [] if self._non_mos_pending_tail_flush else [p for p in pieces[n_partials:] if len(p)]
+            flush = self._take_flush_flag()
             pieces = [p for p in pieces if len(p)]
             self._record_timing("lance_loading", time.time() - start_time)
             if sum(len(p) for p in pieces) == 0:
                 self.batch_id += 1
                 continue
             rec = _Staged(body=body, pieces=pieces, flush=flush, batch_id=self.batch_id, epoch=self.current_epoch,
-                          seed=self.seed + self.batch_id + self.current_epoch * 10000, start_time=start_time)     # datasets.py:1016
+                          seed=self.seed + self.batch_id + self.current_epoch * 10000, start_time=start_time, reads=reads)     # datasets.py:1016
             self.batch_id += 1
             self._predict(rec)
             eng = self._engine
@@ -639,24 +677,58 @@ class PrefetchBatchProcessor:
                 self._submit_staged(rec)                       # otherwise deferred until nothing is in flight (the engine is re-created)
             return rec
 
+    @staticmethod
+    def _boundary_runs(pieces: list[CooChunk]) -> list[tuple[int, int, list[CooChunk]]]:
+        """(cell id, rows, [views]) of the runs that touch a piece boundary, in row order; a run that continues across adjacent
+        pieces is one entry.  Touches O(run length) rows per piece."""
+        out: list[tuple[int, int, list[CooChunk]]] = []
+        open_run = None                                            # the run reaching the end of the previous piece
+        for p in pieces:
+            n = len(p)
+            if n == 0:
+                continue
+            first = p.cell[0]
+            h = _head_run(p.cell, first)
+            if open_run is not None and open_run[0] == int(first):
+                open_run = (open_run[0], open_run[1] + h, open_run[2] + [p.slice(0, h)])
+            else:
+                if open_run is not None:
+                    out.append(open_run)
+                open_run = (int(first), h, [p.slice(0, h)])
+            if h < n:
+                out.append(open_run)
+                last = p.cell[-1]
+                t = _tail_run(p.cell, last)
+                open_run = (int(last), t, [p.slice(n - t, n)])
+        if open_run is not None:
+            out.append(open_run)
+        return out
+
     def _predict(self, rec: _Staged) -> None:
-        """partial_cell_data as it will be after ``rec`` (non-MoS rule: the cell with the largest id waits for the next load;
-        the end-of-data flush leaves nothing).  The rows are copied: the pieces may be recycled buffers."""
-        if rec.flush:
-            rec.pred, rec.stash = (), {}
+        """partial_cell_data as it will be after ``rec``, from the runs at the piece boundaries (the rows are copied: the
+        pieces may be recycled buffers).  Mixture of scanners: the runs shorter than the cell's row count in
+        ``_cell_start_index``; otherwise the reference's rule for one stream, the cell with the largest id waits; the
+        end-of-data flush leaves nothing.  No prediction (``pred`` None: this load is finished before the next is read) when a
+        cell shows up in two separated runs -- that load goes through the splice safety net."""
+        runs = self._boundary_runs(rec.pieces)
+        ids = [r[0] for r in runs]
+        if len(set(ids)) != len(ids):
+            rec.pred = rec.stash = None
+            return
+        if self.use_mixture_of_scanners:
+            csi = np.asarray(self.slaf_array._cell_start_index)
+            a = np.asarray(ids, np.int64)
+            done = np.asarray([r[1] for r in runs], np.int64) >= csi[a + 1] - csi[a]
+            # the final flush holds nothing but pending cells (every run is a whole piece); if none of them can be completed
+            # any more they are all emitted (see _complete_mask)
+            bad = [] if (rec.flush and not done.any()) else [r for r, d in zip(runs, done) if not d]
+        elif rec.flush:
+            bad = []
         else:
-            x = rec.pieces[-1].cell[-1]
-            parts, total = [], 0
-            for p in reversed(rec.pieces):
-                n = _tail_run(p.cell, x)
-                if n == 0:
-                    break
-                parts.append(p.slice(len(p) - n, len(p)).copy())
-                total += n
-                if n < len(p):
-                    break
-            parts.reverse()
-            rec.pred, rec.stash = (int(x), total), {int(x): concat_chunks(parts)}
+            x = max(ids)
+            bad = [r for r in runs if r[0] == x]
+        rec.pred = [(r[0], r[1]) for r in bad]
+        rec.stash = {r[0]: concat_chunks([v.copy() for v in r[2]]) for r in bad}
         self.partial_cell_data = dict(rec.stash)
 
     def _submit_staged(self, rec: _Staged) -> None:
@@ -681,9 +753,17 @@ class PrefetchBatchProcessor:
             self._ahead = None                                  # (an end-of-data marker is re-derived: pending cells get their flush load)
             self.partial_cell_data = stash
             return
-        a.pieces = [p for p in list(stash.values()) + a.body if len(p)]
+        if a.flush:
+            pieces = list(stash.values())
+        elif a.reads is not None:
+            pieces = self._mos_build(a.reads, dict(stash))
+        else:
+            pieces = list(stash.values()) + a.body
+        a.pieces = [p for p in pieces if len(p)]
         self.partial_cell_data = {}
         self._predict(a)                                        # sets partial_cell_data to what follows the look-ahead
+        if a.pred is None:
+            self.partial_cell_data = {}                         # decided by the table when its turn comes (nothing is read ahead of it)
 
     #: pieces smaller than this are handed to the driver as they are (its pageable path copies them synchronously)
     SMALL_PIECE_ROWS = 1 << 15
@@ -760,9 +840,7 @@ class PrefetchBatchProcessor:
         complete = self._complete_mask(seg_cell, seg_len, rec.flush)
         if rec.pred is not None:
             bad = np.flatnonzero(~complete)
-            C = len(seg_cell)
-            as_predicted = (bad.size == 0) if rec.pred == () else \
-                (bad.size == 1 and int(bad[0]) == C - 1 and (int(seg_cell[-1]), int(seg_len[-1])) == rec.pred)
+            as_predicted = bad.size == len(rec.pred) and [(int(seg_cell[j]), int(seg_len[j])) for j in bad] == rec.pred
             if not as_predicted:
                 self._unsubmit_ahead()
                 keep = self.partial_cell_data

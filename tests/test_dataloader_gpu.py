@@ -419,3 +419,44 @@ def test_look_ahead_reset_for_epoch_drops_the_submitted_load(data):
         assert_same(g.cell_ids.cpu().numpy(), cids, "cell order")
         assert_same(g.input_ids.cpu().numpy(), ids, "ids")
     proc.close()
+
+
+def _stream(proc):
+    return [(g.epoch, g.batch_id, g.cell_ids.cpu().numpy(), g.input_ids.cpu().numpy(), sorted(g.partial_cell_data)) for g in _drain(proc)]
+
+
+@pytest.mark.parametrize("case", ["consistent", "index_overstates_one_cell"])
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_mixture_of_scanners_look_ahead_equals_the_synchronous_feeder(data, seed, case, monkeypatch):
+    """Under mixture-of-scanners the look-ahead predicts the incomplete cells from the runs at the piece boundaries and
+    _cell_start_index.  With the same scanner draws the stream of prefetch batches (ids, order, tokens, pending cells) must
+    be the one the synchronous feeder produces -- also when the prediction is wrong because the index claims more rows for
+    a cell in the middle of a chunk than the table has (that cell then waits until the final flush in both)."""
+    def run(lookahead):
+        arr = _array(data, rows_per_file=1777)
+        if case == "index_overstates_one_cell":
+            # cell 150 lies inside a chunk: claim 5 more rows for it without moving any other cell's count
+            csi = arr._cell_start_index.copy()
+            counts = np.diff(csi)
+            counts[150] += 5
+            arr._cell_start_index = np.concatenate(([0], np.cumsum(counts)))
+        tok = GeneformerTokenizer(arr, max_genes=32)
+        proc = PrefetchBatchProcessor(arr, RandomShuffle(), tok, seed=42, n_epochs=2, use_mixture_of_scanners=True, n_scanners=3,
+                                      prefetch_batch_size=1000, verbose=False)
+        if not lookahead:
+            monkeypatch.setattr(proc, "_lookahead_ok", lambda: False)
+        else:
+            assert proc._lookahead_ok()
+        np.random.seed(seed)
+        out = _stream(proc)
+        proc.close()
+        return out
+
+    a, b = run(True), run(False)
+    assert len(a) == len(b) and len(a) > 6
+    for x, y in zip(a, b):
+        assert x[:2] == y[:2] and x[4] == y[4]
+        assert np.array_equal(x[2], y[2]) and np.array_equal(x[3], y[3])
+    for epoch in (0, 1):
+        seen = np.concatenate([x[2] for x in a if x[0] == epoch])
+        assert sorted(seen.tolist()) == list(range(N_CELLS))
