@@ -165,7 +165,9 @@ def cpu_port_rate(w, n_cells_total: int, n_proc: int, seed: int = 1234, repeats:
         b = synthetic.make_batch(per, w["n_genes"], w["mean_nnz"], seed=seed + i)
         jobs.append((b.cell, b.gene, b.value, w, 42 + i))
     best = None
-    ctx = mp.get_context("fork")
+    # spawn, not fork: the GPU arm's process holds CUDA state and helper / feeder threads, and a forked child can inherit a
+    # lock one of them held (a default run of this file once sat in exactly that until its time limit)
+    ctx = mp.get_context("spawn")
     with ctx.Pool(n_proc) as pool:
         pool.map(_port_worker, [(j[0][:1000], j[1][:1000], j[2][:1000], w, 1) for j in jobs])  # warm imports
         for _ in range(repeats):
@@ -244,14 +246,16 @@ def loader_rate(w, batches, dev, value_dtype):
     out = {"pinned_source": bool(pinned), "fragments": len(src.get_fragments()), "rows": int(len(cell)), "epochs": n_epochs,
            "mode": "by_fragment (one 16.8 M-row fragment per prefetch batch), boundary cells carried on the host; epoch 0 is warm-up, epochs 1.. are timed",
            "cell_start_index": "extension: cell boundaries from SLAFArray._cell_start_index, the cell column stays on the host (4 B/row over PCIe instead of 8)"}
-    for bs, csi_mode in ((32, False), (1024, False), (1024, True)):
+    for bs, csi_mode, mos in ((32, False, False), (1024, False, False), (1024, True, False), (1024, False, True)):
         rates = []
         for _rep in range(2):                         # best of two: several loaders in one process disturb each other's first seconds
             tok = (ScGPTTokenizer(arr, vocab_size=w["vocab"], n_expression_bins=w["n_bins"], max_genes=w["max_genes"], device=dev)
                    if w["tokenizer"] == "scgpt" else GeneformerTokenizer(arr, vocab_size=w["vocab"], max_genes=w["max_genes"], device=dev))
-            loader = SLAFIterableDataset(arr, tok, batch_size=bs, use_binned_expressions=w["binned"], use_mixture_of_scanners=False,
+            stage(f"  loader batch_size={bs} cell_start_index={csi_mode} mixture_of_scanners={mos} rep={_rep}")
+            np.random.seed(17)                           # the scanner draws of the mixture-of-scanners variant
+            loader = SLAFIterableDataset(arr, tok, batch_size=bs, use_binned_expressions=w["binned"], use_mixture_of_scanners=mos,
                                          by_fragment=True, verbose=False, device=dev, max_queue_size=4, n_epochs=n_epochs,
-                                         use_cell_start_index=csi_mode)
+                                         use_cell_start_index=csi_mode)              # mos: the reference's defaults (16 scanners x 4,194,304 rows)
             n = 0
             t0 = t1 = None
             last = None
@@ -274,12 +278,21 @@ def loader_rate(w, batches, dev, value_dtype):
             torch.cuda.synchronize(dev)
             rates.append(n / (t1 - t0))
             del loader, last, batch
-        out[f"cells_per_s_batch{bs}" + ("_cell_start_index" if csi_mode else "")] = max(rates)
+        out[f"cells_per_s_batch{bs}" + ("_cell_start_index" if csi_mode else "") + ("_mixture_of_scanners" if mos else "")] = max(rates)
     src.unpin()
     return out
 
 
 # ----------------------------------------------------------------------------- B200 arm
+_T0 = time.perf_counter()
+
+
+def stage(msg: str) -> None:
+    """progress line on stderr (rank 0): where a run was when it stopped"""
+    if os.environ.get("RANK", "0") == "0":
+        print(f"[bench {time.perf_counter() - _T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -293,12 +306,30 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-loader", action="store_true")
     ap.add_argument("--verify-cells", type=int, default=2048)
+    ap.add_argument("--watchdog", type=int, default=780, help="seconds after which every thread's stack is dumped to stderr and the run aborts")
     args = ap.parse_args()
+    import faulthandler
+
+    faulthandler.enable()
+    if args.watchdog > 0:       # a hang must cost a bounded amount of box time and leave a trace of where it sat
+        faulthandler.dump_traceback_later(args.watchdog, exit=True)
     w = WORKLOADS[args.workload]
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
     if args.impl == "reference":
         return run_reference(args, w)
+
+    cpu_baseline = None
+    if int(os.environ.get("WORLD_SIZE", "1")) == 1 and not args.no_cpu_baseline:
+        # first, while this process is still single-threaded and has no CUDA context, on every host core
+        cores = len(os.sched_getaffinity(0))
+        stage(f"cpu baseline on {cores} cores")
+        rate, n = cpu_port_rate(w, 768 * cores, cores)
+        c_rate, c_thr = c_oracle_rate(w, 2048)
+        cpu_baseline = {"value": rate, "unit": "cells/s", "cores": cores, "kind": "port",
+                        "sample": f"{n} cells ({cores} processes x {n // cores}), numpy window + per-cell Python tokenizer loop (reference structure; polars not installable)",
+                        "c_oracle_cells_per_s": c_rate, "c_oracle_threads": c_thr,
+                        "published_reference": "5,350 cells/s scGPT / 6,494 cells/s Geneformer on M1 Max (docs/benchmarks/ml_benchmarks.md:49-52)"}
 
     import torch
     import torch.distributed as dist
@@ -377,6 +408,7 @@ def main():
         kw.update(order="rank", norm=norm_dev)
 
     # ---- parity gate (bit-exact against the CPU oracle) before any number counts
+    stage("parity gate")
     from oracle import c_oracle
     import random as _random
 
@@ -436,6 +468,7 @@ def main():
         return cells, rows, d2h
 
     # ---- value: inputs resident in HBM
+    stage("value: warm-up + timed steps, inputs in HBM")
     eng.set_timing_interval(timing_every)
     run_steps(dev_cols, args.warmup, False)
     eng.timing()
@@ -459,6 +492,7 @@ def main():
     total_cells = sum_over_ranks(cells)
     value = total_cells / (ms / 1000.0)
 
+    stage("isolated-kernel pass")
     # ---- isolated-kernel pass: same steps, CSR build on the launch stream so no two kernels overlap and every
     #      kernel's CUDA-event time is its own (in the pipelined run above K1 of a later batch shares HBM with K2)
     eng.set_front_on_caller(True)
@@ -475,6 +509,7 @@ def main():
     # ---- e2e: host (pinned) columns, H2D + result read inside the timed region
     e2e = None
     if not args.no_e2e:
+        stage("e2e: host columns")
         run_steps(host_cols, args.warmup, True)
         eng.timing()
         barrier()
@@ -492,6 +527,7 @@ def main():
 
         # the same call when the caller passes the dataset's cell_start_index instead of the cell column (SLAFArray always has
         # one): the segment table (8 B per cell) replaces 4 B per row on the bus.  Checked against the COO route first.
+        stage("e2e: host columns with cell_start_index")
         segs = [(b.cell_start.astype(np.uint32), b.cell[b.cell_start[:-1]].astype(np.uint32)) for b in batches]
         a = eng.collect(eng.submit(*host_cols[0], shuffle_seed=7), shuffle_seed=7, **kw)
         a_t = [t.clone() for t in (a.input_ids, a.attention_mask, a.cell_ids)] + ([a.values.clone()] if a.values is not None else [])
@@ -515,7 +551,9 @@ def main():
                                                 "the cell column does not and no CSR build runs; same outputs (checked)"}
 
         if not args.no_loader and not w.get("rank_norm"):
+            stage("loader")
             e2e["loader"] = loader_rate(w, batches, dev, args.value_dtype)
+            stage("loader done")
 
     clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
@@ -580,18 +618,8 @@ def main():
     }
     if e2e:
         line["e2e"] = e2e
-    if world == 1 and not args.no_cpu_baseline:
-        try:   # the CPU arm may use every host core (the GPU arm pinned this process to the GPU's NUMA node)
-            os.sched_setaffinity(0, ALL_CPUS)
-        except Exception:
-            pass
-        cores = len(os.sched_getaffinity(0))
-        rate, n = cpu_port_rate(w, 768 * cores, cores)
-        c_rate, c_thr = c_oracle_rate(w, 2048)
-        line["cpu_baseline"] = {"value": rate, "unit": "cells/s", "cores": cores, "kind": "port",
-                                "sample": f"{n} cells ({cores} processes x {n // cores}), numpy window + per-cell Python tokenizer loop (reference structure; polars not installable here)",
-                                "c_oracle_cells_per_s": c_rate, "c_oracle_threads": c_thr,
-                                "published_reference": "5,350 cells/s scGPT / 6,494 cells/s Geneformer on M1 Max (docs/benchmarks/ml_benchmarks.md:49-52)"}
+    if cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

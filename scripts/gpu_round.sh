@@ -7,9 +7,11 @@ TAG=${1:-r1}
 W=${2:-cfg2}
 nvidia-smi --query-gpu=name,memory.total,clocks.max.sm,clocks.max.mem --format=csv > gpurun_out/gpu.txt 2>&1
 nproc >> gpurun_out/gpu.txt; free -g | head -2 >> gpurun_out/gpu.txt
+if [ -z "$SKIP_TESTS" ]; then
 echo "== smoke"; timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/smoke.log
 echo "== pytest gpu"; timeout 1200 python -m pytest tests -q -m gpu -x --timeout 600 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/pytest_gpu.log
-echo "== bench"; timeout 900 python bench.py --workload $W > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; rc=$?; echo "bench rc=$rc"; tail -c 3000 gpurun_out/bench_$TAG.json; tail -5 gpurun_out/bench_$TAG.err
+fi
+echo "== bench"; timeout 600 python bench.py --workload $W --watchdog 540 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; rc=$?; echo "bench rc=$rc"; tail -c 3000 gpurun_out/bench_$TAG.json; tail -5 gpurun_out/bench_$TAG.err
 echo "== bench reference arm"; timeout 600 python bench.py --impl reference --workload $W --steps 3 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2> gpurun_out/bench_ref_$TAG.err; echo "ref rc=$?"; tail -c 1500 gpurun_out/bench_ref_$TAG.json
 if [ $rc -eq 0 ]; then
   echo "== ncu launch list (bench.py, short)"
