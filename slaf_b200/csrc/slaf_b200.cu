@@ -579,7 +579,14 @@ void shuffle_worker(slafb_ctx *ctx) {
         Slot &s = ctx->slot[i];
         int64_t C = -1;
         s.perm_uploaded = false;
-        if (cudaEventSynchronize(s.ev_front) == cudaSuccess && !s.h_counters[1]) {
+        // wait for the cell count without occupying a core: the helpers have most of a pipeline depth of slack, and on an
+        // 8-GPU host (4 vCPUs per rank on this pool) a spinning cudaEventSynchronize per helper competes with the feeder threads
+        cudaError_t ready;
+        while ((ready = cudaEventQuery(s.ev_front)) == cudaErrorNotReady) {
+            cudaGetLastError();
+            std::this_thread::sleep_for(std::chrono::microseconds(20));
+        }
+        if (ready == cudaSuccess && !s.h_counters[1]) {
             C = s.h_counters[0];
             py_shuffle_perm(s.prep_seed, C, s.h_perm, s.h_draws);
             // upload it right away on its own stream with a tiny kernel (not the copy engine, which is busy with whole
