@@ -1,0 +1,249 @@
+"""CPU tests of the host feeder's control flow (slaf_b200/ml/datasets.py) with a stand-in engine: which rows are submitted when,
+which cells are emitted in which load, what waits in partial_cell_data -- the look-ahead must produce exactly the stream of the
+synchronous feeder, which in turn is the reference's loop (slaf/ml/datasets.py:812-953, 1011-1098).  The stand-in keeps the
+submitted cell columns, answers ``segments`` with their runs and ``collect`` with the selected cell ids; the tokens themselves are
+the GPU tests' business (tests/test_dataloader_gpu.py runs the same comparisons through the real library)."""
+
+import numpy as np
+import pytest
+import torch
+
+from slaf_b200 import synthetic
+from slaf_b200.ml import GeneformerTokenizer, PrefetchBatchProcessor, RandomShuffle, SLAFIterableDataset
+from slaf_b200.ml import datasets as D
+from slaf_b200.ml.sources import ArrayExpressionSource, SyntheticSLAFArray
+
+N_CELLS, N_GENES = 400, 3000
+
+
+class _Out:
+    def __init__(self, cids, width):
+        n = len(cids)
+        self.input_ids = torch.zeros((n, width), dtype=torch.int64)
+        self.attention_mask = torch.zeros((n, width), dtype=torch.bool)
+        self.values = None
+        self.cell_ids = torch.from_numpy(np.asarray(cids, np.int64))
+        self.n_cells = n
+
+
+class StandInEngine:
+    """submit / segments / collect / release of HotPathEngine on numpy; eight slots like the library, and a log of the calls."""
+
+    device = torch.device("cpu")
+
+    def __init__(self, max_rows, max_cells):
+        self.max_rows, self.max_cells, self.slots, self.next, self.log = max_rows, max_cells, {}, 0, []
+
+    def _put(self, cell):
+        assert len(cell) <= self.max_rows, "submitted more rows than the engine was sized for"
+        assert len(self.slots) < 8, "more than eight batches in flight"
+        slot, self.next = self.next, self.next + 1
+        self.slots[slot] = np.array(cell)            # a copy: the feeder may recycle its buffers once submit has returned
+        self.log.append(("submit", slot))
+        return slot
+
+    def submit_pieces(self, pieces):
+        return self._put(np.concatenate([np.asarray(p[0]) for p in pieces]))
+
+    def submit(self, cell, gene, value, shuffle_seed=None):
+        return self._put(np.asarray(cell))
+
+    def segments(self, slot):
+        cell = self.slots[slot]
+        starts, _ends, ids = D._runs(cell)
+        self.log.append(("segments", slot))
+        return np.concatenate((starts, [len(cell)])).astype(np.uint32), ids.copy()
+
+    def collect(self, slot, perm=None, capacity_cells=None, **kw):
+        ids = D._runs(self.slots.pop(slot))[2]
+        self.log.append(("collect", slot))
+        return _Out(ids[np.asarray(perm)], kw["max_genes"])
+
+    def release(self, slot):
+        self.slots.pop(slot, None)
+        self.log.append(("release", slot))
+
+    def close(self):
+        pass
+
+
+@pytest.fixture()
+def stand_in(monkeypatch):
+    engines = []
+
+    def engine_for(self, rows, all_cells=False):
+        if self._engine is None or self._engine.max_rows < rows:
+            assert self._engine is None or not self._engine.slots, "engine re-created with batches in flight"
+            self._engine = StandInEngine(rows + rows // 4, rows)
+            engines.append(self._engine)
+        return self._engine
+
+    class _Event:
+        def record(self, *a):
+            pass
+
+        def synchronize(self):
+            pass
+
+    monkeypatch.setattr(D.PrefetchBatchProcessor, "_engine_for", engine_for)
+    monkeypatch.setattr(D, "pinned_empty", lambda n, dt=np.uint8: np.empty(n, dt))
+    monkeypatch.setattr(torch.cuda, "Event", _Event)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: None)
+    return engines
+
+
+def _data(seed=5):
+    return synthetic.make_batch(N_CELLS, N_GENES, 50, seed=seed, min_nnz=3, first_cell_id=0)
+
+
+def _proc(b, cell=None, csi=None, rows_per_file=1777, **kw):
+    cell = b.cell if cell is None else cell
+    arr = SyntheticSLAFArray(ArrayExpressionSource(cell, b.gene, b.value, rows_per_file),
+                             b.cell_start if csi is None else csi, N_GENES)
+    tok = GeneformerTokenizer(arr, max_genes=16)
+    return PrefetchBatchProcessor(arr, RandomShuffle(), tok, seed=42, verbose=False, **kw)
+
+
+def _drain(proc):
+    out = []
+    try:
+        while True:
+            g = proc.load_prefetch_batch()
+            out.append((g.epoch, g.batch_id, g.cell_ids.numpy().copy(), sorted(g.partial_cell_data)))
+    except StopIteration:
+        pass
+    return out
+
+
+def _same(a, b):
+    assert len(a) == len(b)
+    for x, y in zip(a, b):
+        assert x[:2] == y[:2] and x[3] == y[3] and np.array_equal(x[2], y[2])
+
+
+@pytest.mark.parametrize("mode", ["fragment", "sequential", "mos"])
+@pytest.mark.parametrize("seed", [0, 1])
+def test_look_ahead_stream_equals_synchronous_stream(stand_in, monkeypatch, mode, seed):
+    b = _data()
+    kw = dict(use_mixture_of_scanners=(mode == "mos"), by_fragment=(mode != "sequential"), n_scanners=3, prefetch_batch_size=1000,
+              batches_per_chunk=2 if mode == "sequential" else 1, n_epochs=2)
+    runs = []
+    for lookahead in (True, False):
+        proc = _proc(b, **kw)
+        if lookahead:
+            assert proc._lookahead_ok()
+        else:
+            monkeypatch.setattr(proc, "_lookahead_ok", lambda: False)
+        np.random.seed(seed)
+        runs.append(_drain(proc))
+        log = proc._engine.log
+        if lookahead:
+            # the point of it: a later load's rows are submitted before the current load's table is asked for
+            first_seg = next(i for i, e in enumerate(log) if e[0] == "segments")
+            assert sum(1 for e in log[:first_seg] if e[0] == "submit") == 2
+        assert not proc._engine.slots                                  # nothing left in flight at the end
+    _same(*runs)
+    for epoch in (0, 1):
+        seen = np.concatenate([x[2] for x in runs[0] if x[0] == epoch])
+        assert sorted(seen.tolist()) == list(range(N_CELLS))
+
+
+def test_fragment_stream_is_the_reference_rule(stand_in):
+    """by_fragment without mixture-of-scanners: the cell with the largest id of [pending + fragment] waits (datasets.py:931-953)."""
+    b = _data()
+    got = _drain(_proc(b, rows_per_file=2500, use_mixture_of_scanners=False, by_fragment=True))
+    import random
+
+    pending = np.zeros(0, b.cell.dtype)
+    want, batch_id = [], 0
+    for lo in list(range(0, b.n_rows, 2500)) + [None]:
+        comb = pending if lo is None else np.concatenate([pending, b.cell[lo:lo + 2500]])
+        if lo is None and not len(pending):
+            break
+        keep = np.ones(len(comb), bool) if lo is None else comb < comb.max()
+        ids = comb[keep][np.sort(np.unique(comb[keep], return_index=True)[1])]
+        pending = comb[~keep]
+        if len(ids):
+            random.seed(42 + batch_id)
+            order = list(range(len(ids)))
+            random.shuffle(order)
+            want.append((batch_id, ids[order], sorted(set(pending.tolist()))))
+        batch_id += 1
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert g[1] == w[0] and np.array_equal(g[2], w[1]) and g[3] == w[2]
+
+
+def test_wrong_prediction_is_rebuilt_from_the_table(stand_in, monkeypatch):
+    """Cell ids that do not ascend: the waiting cell is not the last run, the look-ahead is released and rebuilt."""
+    b = _data()
+    relabel = np.random.default_rng(3).permutation(N_CELLS).astype(b.cell.dtype)
+    cell = relabel[b.cell]
+    kw = dict(rows_per_file=2500, use_mixture_of_scanners=False, by_fragment=True, n_epochs=2)
+    ahead = _proc(b, cell=cell, **kw)
+    a = _drain(ahead)
+    assert any(e[0] == "release" for e in ahead._engine.log)          # the fallback really ran
+    sync = _proc(b, cell=cell, **kw)
+    monkeypatch.setattr(sync, "_lookahead_ok", lambda: False)
+    _same(a, _drain(sync))
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_mos_index_that_overstates_a_cell(stand_in, monkeypatch, seed):
+    """_cell_start_index claims five rows more for a cell in the middle of a chunk: the boundary-run prediction misses it, the
+    table shows it incomplete; both feeders carry it to the final flush and emit it there."""
+    b = _data()
+    counts = np.diff(b.cell_start)
+    counts[150] += 5
+    csi = np.concatenate(([0], np.cumsum(counts)))
+    kw = dict(csi=csi, use_mixture_of_scanners=True, n_scanners=3, prefetch_batch_size=1000, n_epochs=1)
+    runs = []
+    for lookahead in (True, False):
+        proc = _proc(b, **kw)
+        if not lookahead:
+            monkeypatch.setattr(proc, "_lookahead_ok", lambda: False)
+        np.random.seed(seed)
+        runs.append(_drain(proc))
+    _same(*runs)
+    assert 150 in runs[0][-1][2].tolist() and all(150 not in x[2].tolist() for x in runs[0][:-1])
+    assert sorted(np.concatenate([x[2] for x in runs[0]]).tolist()) == list(range(N_CELLS))
+
+
+def test_engine_growth_is_deferred_until_nothing_is_in_flight(stand_in):
+    b = _data()
+    proc = _proc(b, rows_per_file=2500, use_mixture_of_scanners=False, by_fragment=True)
+    proc._engine = small = StandInEngine(2510, 2510)                   # the first fragment fits, pending cell + second does not
+    got = _drain(proc)
+    assert proc._engine is not small and len(stand_in) == 1            # re-created once, by the fixture's engine_for (which asserts idleness)
+    assert sorted(np.concatenate([x[2] for x in got]).tolist()) == list(range(N_CELLS))
+
+
+def test_reset_for_epoch_releases_the_look_ahead(stand_in):
+    b = _data()
+    proc = _proc(b, rows_per_file=2500, use_mixture_of_scanners=False, by_fragment=True, n_epochs=2)
+    proc.load_prefetch_batch()
+    assert proc._ahead is not None and len(proc._engine.slots) == 1
+    proc.reset_for_epoch(1)
+    assert proc._ahead is None and not proc._engine.slots and proc.batch_id == 0
+    rest = _drain(proc)
+    assert {x[0] for x in rest} == {1} and sorted(np.concatenate([x[2] for x in rest]).tolist()) == list(range(N_CELLS))
+
+
+@pytest.mark.parametrize("mos", [False, True])
+@pytest.mark.parametrize("batch_size", [7, 64])
+def test_iterable_dataset_batches_over_the_stand_in(stand_in, mos, batch_size):
+    """Producer thread + consumer: batch_size-cell views, every cell once per epoch, the epoch key, a clean end."""
+    b = _data()
+    arr = SyntheticSLAFArray(ArrayExpressionSource(b.cell, b.gene, b.value, 1777), b.cell_start, N_GENES)
+    tok = GeneformerTokenizer(arr, max_genes=16)
+    np.random.seed(4)
+    ds = SLAFIterableDataset(arr, tok, batch_size=batch_size, use_mixture_of_scanners=mos, by_fragment=True, verbose=False,
+                             n_epochs=3, n_scanners=3, prefetch_batch_size=1000, max_queue_size=3)
+    per_epoch: dict = {}
+    for batch in ds:
+        assert set(batch) == {"input_ids", "attention_mask", "cell_ids", "epoch"}
+        assert 0 < batch["input_ids"].shape[0] <= batch_size and batch["input_ids"].shape[0] == batch["cell_ids"].shape[0]
+        per_epoch.setdefault(batch["epoch"], []).extend(batch["cell_ids"].tolist())
+    assert sorted(per_epoch) == [0, 1, 2]
+    for ids in per_epoch.values():
+        assert sorted(ids) == list(range(N_CELLS))
