@@ -11,6 +11,10 @@ What changes against the reference:
   ``_cell_start_index``, and K2 emits the token tensors of the complete cells in the CPython-exact
   shuffled order.  The rows of incomplete boundary cells are kept on the host exactly like the
   reference's ``partial_cell_data`` (datasets.py:891-953);
+* the fused routes read ahead: the rows of load i+1 are submitted before the host waits for the segment table of load i; the
+  incomplete cells load i+1 needs are predicted from the runs at the piece boundaries and checked against the table when it
+  arrives (``_predict`` / ``_front``; a wrong prediction rebuilds the look-ahead, so the stream never differs from the
+  synchronous feeder's);
 * batches are device tensors (views of the prefetch batch); the queue hands over a CUDA event, the
   consumer stream waits on it -- no host synchronisation per batch;
 * a full queue blocks the producer instead of silently dropping the batch (datasets.py:1277-1281).
