@@ -153,10 +153,18 @@ def _port_worker(args):
     return len(cids), time.perf_counter() - t0
 
 
-def cpu_port_rate(w, n_cells_total: int, n_proc: int, seed: int = 1234, repeats: int = 1):
+def port_pool(n_proc: int):
+    """Worker processes of the CPU arm.  Spawned, not forked: the GPU arm's process holds CUDA state and helper / feeder threads,
+    and a forked child can inherit a lock one of them held (a default run of this file once sat in exactly that until its time
+    limit)."""
+    import multiprocessing as mp
+
+    return mp.get_context("spawn").Pool(n_proc)
+
+
+def cpu_port_rate(w, n_cells_total: int, n_proc: int, seed: int = 1234, repeats: int = 1, pool=None):
     """cells/s of the CPU port over `n_proc` processes, each on its own range of cells
     (stands in for polars' thread pool; the reference's tokenizer loop is single-threaded Python)."""
-    import multiprocessing as mp
     from slaf_b200 import synthetic
 
     per = max(1, n_cells_total // n_proc)
@@ -165,10 +173,10 @@ def cpu_port_rate(w, n_cells_total: int, n_proc: int, seed: int = 1234, repeats:
         b = synthetic.make_batch(per, w["n_genes"], w["mean_nnz"], seed=seed + i)
         jobs.append((b.cell, b.gene, b.value, w, 42 + i))
     best = None
-    # spawn, not fork: the GPU arm's process holds CUDA state and helper / feeder threads, and a forked child can inherit a
-    # lock one of them held (a default run of this file once sat in exactly that until its time limit)
-    ctx = mp.get_context("spawn")
-    with ctx.Pool(n_proc) as pool:
+    own = pool is None
+    if own:
+        pool = port_pool(n_proc)
+    try:
         pool.map(_port_worker, [(j[0][:1000], j[1][:1000], j[2][:1000], w, 1) for j in jobs])  # warm imports
         for _ in range(repeats):
             t0 = time.perf_counter()
@@ -177,6 +185,10 @@ def cpu_port_rate(w, n_cells_total: int, n_proc: int, seed: int = 1234, repeats:
             cells = sum(r[0] for r in res)
             rate = cells / dt
             best = rate if best is None or rate > best else best
+    finally:
+        if own:
+            pool.close()
+            pool.join()
     return best, per * n_proc
 
 
@@ -201,12 +213,17 @@ def run_reference(args, w):
     per_core = max(64, int(1024 * min(1.0, 40.0 / max(1, args.steps))))
     sample = per_core * cores
     rates = []
-    for _ in range(args.warmup):
-        cpu_port_rate(w, max(cores * 16, 64), cores)
-    t_all = time.perf_counter()
-    for _ in range(args.steps):
-        r, n = cpu_port_rate(w, sample, cores)
-        rates.append(r)
+    pool = port_pool(cores)
+    try:
+        for _ in range(args.warmup):
+            cpu_port_rate(w, max(cores * 16, 64), cores, pool=pool)
+        t_all = time.perf_counter()
+        for _ in range(args.steps):
+            r, n = cpu_port_rate(w, sample, cores, pool=pool)
+            rates.append(r)
+    finally:
+        pool.close()
+        pool.join()
     rate = statistics.median(rates)
     c_rate, c_thr = c_oracle_rate(w, 2048)
     line = {
