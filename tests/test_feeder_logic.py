@@ -247,3 +247,38 @@ def test_iterable_dataset_batches_over_the_stand_in(stand_in, mos, batch_size):
     assert sorted(per_epoch) == [0, 1, 2]
     for ids in per_epoch.values():
         assert sorted(ids) == list(range(N_CELLS))
+
+
+# ---------------------------------------------------------------------------------------------- properties
+from hypothesis import HealthCheck, given, settings  # noqa: E402
+from hypothesis import strategies as st  # noqa: E402
+
+
+@settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(lens=st.lists(st.integers(0, 40), min_size=2, max_size=60), rows_per_file=st.integers(5, 300), mos=st.booleans(),
+       n_scanners=st.integers(1, 5), chunk=st.integers(1000, 1400), draw_seed=st.integers(0, 1000), n_epochs=st.integers(1, 2))
+def test_property_look_ahead_equals_synchronous_feeder(stand_in, lens, rows_per_file, mos, n_scanners, chunk, draw_seed, n_epochs):
+    """Any table sorted by cell (cells without rows included), any fragment size, either loading mode: same stream of loads."""
+    lens = np.asarray(lens, np.int64)
+    if lens.sum() == 0:
+        lens[0] = 3
+    cell = np.repeat(np.arange(len(lens), dtype=np.uint32), lens)
+    rng = np.random.default_rng(draw_seed)
+    gene = rng.integers(0, 100, len(cell)).astype(np.uint16)
+    value = rng.integers(1, 50, len(cell)).astype(np.uint16)
+    csi = np.concatenate(([0], np.cumsum(lens)))
+    runs = []
+    for lookahead in (True, False):
+        arr = SyntheticSLAFArray(ArrayExpressionSource(cell, gene, value, rows_per_file), csi, 100)
+        proc = PrefetchBatchProcessor(arr, RandomShuffle(), GeneformerTokenizer(arr, max_genes=8), seed=7, verbose=False, n_epochs=n_epochs,
+                                      use_mixture_of_scanners=mos, by_fragment=True, n_scanners=n_scanners, prefetch_batch_size=chunk)
+        if not lookahead:
+            proc._lookahead_ok = lambda: False
+        np.random.seed(draw_seed)
+        runs.append(_drain(proc))
+        assert not proc._engine.slots
+    _same(*runs)
+    present = np.flatnonzero(lens > 0).tolist()
+    for epoch in range(n_epochs):
+        seen = [int(c) for x in runs[0] if x[0] == epoch for c in x[2]]
+        assert sorted(seen) == present
