@@ -785,7 +785,8 @@ class PrefetchBatchProcessor:
     def _submit_with_csi(self, eng: HotPathEngine, pieces: list[CooChunk]):
         csi = np.asarray(self.slaf_array._cell_start_index, np.int64)
         seg_start, seg_cell = _segments_from_csi(pieces, csi)
-        if len(np.unique(seg_cell)) != len(seg_cell):                      # a cell in two separated places: splice (views) first
+        ascending = seg_cell.size < 2 or bool(np.all(seg_cell[1:] > seg_cell[:-1]))        # the usual case, and it implies distinct ids
+        if not ascending and len(np.unique(seg_cell)) != len(seg_cell):    # a cell in two separated places: splice (views) first
             pieces = _regroup_segments(pieces, seg_start, seg_cell)
             seg_start, seg_cell = _segments_from_csi(pieces, csi)
         # cheap consistency probes against the rows themselves: at up to 64 evenly spaced segment heads (and the last row) the
