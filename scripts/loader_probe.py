@@ -10,7 +10,6 @@ import torch
 
 from slaf_b200 import synthetic
 from slaf_b200.ml import PrefetchBatchProcessor, RandomShuffle, ScGPTTokenizer
-from slaf_b200.ml import datasets as D
 from slaf_b200.ml.sources import ArrayExpressionSource, SyntheticSLAFArray
 
 cells = int(sys.argv[1]) if len(sys.argv) > 1 else 65536

@@ -37,7 +37,7 @@ import torch
 
 from .. import _native as N
 from ..core.tabular_schema import SLAF_LANCE_COO_SCHEMA
-from ..engine import HotPathEngine, is_page_locked, pinned_empty, regroup_contiguous, shuffle_perm
+from ..engine import HotPathEngine, is_page_locked, pinned_empty, shuffle_perm
 from . import frames
 from .samplers import RandomShuffle, StratifiedShuffle
 from .sources import CooChunk, ExpressionSource, concat_chunks, open_expression
