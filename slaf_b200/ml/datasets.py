@@ -347,7 +347,7 @@ class PrefetchBatchProcessor:
             if log_metrics else None)
         self._engine: HotPathEngine | None = None
         self._staging = _Staging(depth=3, threads=copy_threads)     # three: with the look-ahead two loads can be in flight while a third is assembled
-        self._ahead: _Staged | StopIteration | None = None
+        self._ahead: _Staged | BaseException | None = None
         self._read_pool: ThreadPoolExecutor | None = None
 
     # ------------------------------------------------------------------ readers / epochs
@@ -626,8 +626,8 @@ class PrefetchBatchProcessor:
             cur, self._ahead = self._ahead, None
             if cur is None:
                 cur = self._stage()
-            if isinstance(cur, StopIteration):
-                raise cur
+            if isinstance(cur, BaseException):                 # the end of the data, or an error met while reading ahead:
+                raise cur                                       # delivered after the load before it
             if not cur.pieces:                                  # a rebuilt flush load that turned out to have nothing left to flush
                 continue
             if cur.slot is None:
@@ -635,7 +635,7 @@ class PrefetchBatchProcessor:
             if cur.pred is not None:
                 try:
                     self._ahead = self._stage()                # the next load's rows go out before this one's table is awaited
-                except StopIteration as end:
+                except Exception as end:                       # StopIteration (last epoch done) or a reader error
                     self._ahead = end
             out = self._load_raw_device(cur) if self.raw_mode else self._load_fused(cur)
             if out is not None:

@@ -282,3 +282,24 @@ def test_property_look_ahead_equals_synchronous_feeder(stand_in, lens, rows_per_
     for epoch in range(n_epochs):
         seen = [int(c) for x in runs[0] if x[0] == epoch for c in x[2]]
         assert sorted(seen) == present
+
+
+def test_error_while_reading_ahead_surfaces_after_the_current_load(stand_in):
+    """A reader error met while staging load i+1 must not lose load i (already on the device): it is raised by the next call."""
+    b = _data()
+    proc = _proc(b, rows_per_file=2500, use_mixture_of_scanners=False, by_fragment=True)
+    real = proc._next_pieces
+    calls = {"n": 0}
+
+    def flaky():
+        calls["n"] += 1
+        if calls["n"] == 3:
+            raise OSError("fragment unreadable")
+        return real()
+
+    proc._next_pieces = flaky
+    first = proc.load_prefetch_batch()            # stages loads 0 and 1
+    second = proc.load_prefetch_batch()           # staging load 2 fails; load 1 is still delivered
+    assert (first.batch_id, second.batch_id) == (0, 1) and not proc._engine.slots
+    with pytest.raises(OSError, match="fragment unreadable"):
+        proc.load_prefetch_batch()
