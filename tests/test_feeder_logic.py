@@ -303,3 +303,30 @@ def test_error_while_reading_ahead_surfaces_after_the_current_load(stand_in):
     assert (first.batch_id, second.batch_id) == (0, 1) and not proc._engine.slots
     with pytest.raises(OSError, match="fragment unreadable"):
         proc.load_prefetch_batch()
+
+
+def _chunk(ids):
+    ids = np.asarray(ids, np.uint32)
+    from slaf_b200.ml.sources import CooChunk
+
+    return CooChunk(ids, np.arange(len(ids), dtype=np.uint16), np.ones(len(ids), np.uint16))
+
+
+def test_boundary_runs_merge_across_adjacent_pieces():
+    runs = PrefetchBatchProcessor._boundary_runs([_chunk([4, 4]), _chunk([4, 5, 5, 6]), _chunk([6, 6]), _chunk([6, 7, 8, 8]), _chunk([]), _chunk([9])])
+    assert [(r[0], r[1]) for r in runs] == [(4, 3), (6, 4), (8, 2), (9, 1)]          # 5 and 7 are interior: never candidates
+    assert [sum(len(v) for v in r[2]) for r in runs] == [3, 4, 2, 1]
+    assert [int(v.gene[0]) for v in runs[1][2]] == [3, 0, 0]                        # views in row order: tail of piece 2, piece 3, head of piece 4
+    assert PrefetchBatchProcessor._boundary_runs([]) == []
+    one = PrefetchBatchProcessor._boundary_runs([_chunk([3, 3, 3])])
+    assert [(r[0], r[1]) for r in one] == [(3, 3)]
+
+
+def test_mos_build_puts_a_generators_pending_cell_in_front_of_its_chunk():
+    """datasets.py:748-760 and 880-888: generator 1 last delivered cell 6 and continues with 6 -> its pending rows go right in
+    front of its chunk; the other pending cell (2) goes in front of everything; runs of it at a chunk head are moved up."""
+    partials = {2: _chunk([2, 2]), 6: _chunk([6])}
+    reads = [(0, [_chunk([2, 3, 3])], 1), (1, [_chunk([6, 6, 7])], 6)]
+    pieces = PrefetchBatchProcessor._mos_build(reads, partials)
+    assert np.concatenate([p.cell for p in pieces]).tolist() == [2, 2, 2, 3, 3, 6, 6, 6, 7]
+    assert list(partials) == [2]                                                   # 6 was consumed by its generator
