@@ -67,6 +67,15 @@ class _SlicedFragment(Fragment):
     def to_table(self) -> CooChunk:
         return self._frag.to_table().slice(self._lo, self._hi)
 
+    def to_pieces(self) -> list[CooChunk]:
+        out, pos = [], 0
+        for piece in self._frag.to_pieces():
+            lo, hi = max(self._lo - pos, 0), min(self._hi - pos, len(piece))
+            if hi > lo:
+                out.append(piece.slice(lo, hi))
+            pos += len(piece)
+        return out
+
     def to_batches(self, batch_size: int = 8192) -> Iterator[CooChunk]:
         pos = 0
         for chunk in self._frag.to_batches(batch_size):

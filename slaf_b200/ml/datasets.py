@@ -469,7 +469,7 @@ class PrefetchBatchProcessor:
         elif self.by_fragment:
             try:
                 fragment = next(self.fragment_iterator)
-                pieces, count = [fragment.to_table()], 1
+                pieces, count = fragment.to_pieces(), 1          # storage chunks as they lie (views), never concatenated on the host
             except StopIteration:
                 if self.partial_cell_data:
                     pieces, count = list(self.partial_cell_data.values()), 0

@@ -83,6 +83,12 @@ class Fragment:
     def to_table(self) -> CooChunk:
         raise NotImplementedError
 
+    def to_pieces(self) -> list[CooChunk]:
+        """The fragment's rows as consecutive blocks in storage order, WITHOUT gathering them into one array: what the feeder
+        hands to the library (which copies the blocks back to back into its staging columns).  Sources whose storage is
+        chunked (Arrow record batches, Lance pages) return views of the chunks here; ``to_table`` has to concatenate them."""
+        return [self.to_table()]
+
     def to_batches(self, batch_size: int = 8192) -> Iterator[CooChunk]:
         table = self.to_table()
         for lo in range(0, len(table), batch_size):
@@ -168,6 +174,17 @@ class _ArrowFileFragment(Fragment):
         out.row_lo = self.row_lo
         return out
 
+    def to_pieces(self) -> list[CooChunk]:
+        rd = self._open()
+        out, pos = [], 0
+        for i in range(rd.num_record_batches):       # zero-copy views of the memory map, one per record batch
+            ch = chunk_from_frame(rd.get_batch(i))
+            ch.row_lo = None if self.row_lo is None else self.row_lo + pos
+            pos += len(ch)
+            if len(ch):
+                out.append(ch)
+        return out
+
     def to_batches(self, batch_size: int = 8192) -> Iterator[CooChunk]:
         rd = self._open()
         pos = 0
@@ -228,6 +245,16 @@ class _LanceFragment(Fragment):
     def to_table(self) -> CooChunk:
         out = chunk_from_frame(self._frag.to_table(columns=list(COLUMNS)).combine_chunks())
         out.row_lo = self.row_lo
+        return out
+
+    def to_pieces(self) -> list[CooChunk]:
+        out, pos = [], 0
+        for rb in self._frag.to_table(columns=list(COLUMNS)).to_batches():      # the decoded chunks as they are, no concatenation
+            ch = chunk_from_frame(rb)
+            ch.row_lo = None if self.row_lo is None else self.row_lo + pos
+            pos += len(ch)
+            if len(ch):
+                out.append(ch)
         return out
 
     def to_batches(self, batch_size: int = 8192) -> Iterator[CooChunk]:

@@ -330,3 +330,35 @@ def test_mos_build_puts_a_generators_pending_cell_in_front_of_its_chunk():
     pieces = PrefetchBatchProcessor._mos_build(reads, partials)
     assert np.concatenate([p.cell for p in pieces]).tolist() == [2, 2, 2, 3, 3, 6, 6, 6, 7]
     assert list(partials) == [2]                                                   # 6 was consumed by its generator
+
+
+@pytest.mark.parametrize("mos", [False, True])
+def test_arrow_fragments_are_fed_as_record_batch_views(stand_in, tmp_path, mos):
+    """An Arrow fragment with several record batches reaches the engine as views of those batches (``to_pieces``), never gathered
+    into one array on the host; the stream of loads is the one of the same table held in one numpy array per column."""
+    from slaf_b200.distributed import RowRangeSource
+    from slaf_b200.ml.sources import ArrowExpressionSource, write_arrow_dataset
+
+    b = _data()
+    write_arrow_dataset(str(tmp_path / "expr"), b.cell, b.gene, b.value, max_rows_per_file=2500, rows_per_batch=700)
+    arrow = ArrowExpressionSource(str(tmp_path / "expr"))
+    frag = arrow.get_fragments()[1]
+    pieces = frag.to_pieces()
+    assert [len(p) for p in pieces] == [700, 700, 700, 400] and [p.row_lo for p in pieces] == [2500, 3200, 3900, 4600]
+    assert all(not p.cell.flags.owndata for p in pieces)                       # views of the memory map
+    whole = frag.to_table()
+    assert np.array_equal(np.concatenate([p.cell for p in pieces]), whole.cell) and np.array_equal(np.concatenate([p.value for p in pieces]), whole.value)
+    sliced = RowRangeSource(arrow, 3000, 4700).get_fragments()[0].to_pieces()  # a rank's cell-aligned row range keeps the views
+    assert [len(p) for p in sliced] == [200, 700, 700, 100] and sliced[0].row_lo == 3000
+    runs = []
+    for source in (arrow, ArrayExpressionSource(b.cell, b.gene, b.value, 2500)):
+        arr = SyntheticSLAFArray(source, b.cell_start, N_GENES)
+        proc = PrefetchBatchProcessor(arr, RandomShuffle(), GeneformerTokenizer(arr, max_genes=16), seed=42, verbose=False, n_epochs=2,
+                                      use_mixture_of_scanners=mos, by_fragment=True, n_scanners=2, prefetch_batch_size=1000)
+        np.random.seed(9)
+        runs.append(_drain(proc))
+    if not mos:      # under mixture-of-scanners the chunking differs (record batches vs array slices), so only coverage is fixed
+        _same(*runs)
+    for run in runs:
+        for epoch in (0, 1):
+            assert sorted(int(c) for x in run if x[0] == epoch for c in x[2]) == list(range(N_CELLS))
