@@ -781,7 +781,13 @@ int slafb_host_alloc(void **ptr, size_t bytes) {
 }
 int slafb_host_register(void *ptr, size_t bytes) {
     if (!ptr || !bytes) return fail(nullptr, SLAFB_ERR_INVALID, "nothing to register");
-    CU(nullptr, cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterDefault);
+    if (e != cudaSuccess) {
+        // read-only mappings (a memory-mapped Arrow file) cannot be registered for writing; the copy engine only reads them
+        cudaGetLastError();
+        e = cudaHostRegister(ptr, bytes, cudaHostRegisterReadOnly);
+    }
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(nullptr, SLAFB_ERR_CUDA, "cudaHostRegister failed: %s", cudaGetErrorString(e)); }
     return SLAFB_OK;
 }
 int slafb_host_unregister(void *ptr) {

@@ -504,6 +504,24 @@ def unregister_host_memory(arr: np.ndarray) -> None:
         N.lib().slafb_host_unregister(ctypes.c_void_p(base))
 
 
+def register_host_range(address: int, nbytes: int) -> bool:
+    """register_host_memory for a raw address range (e.g. a whole memory-mapped file: arrays that are views of it are then
+    page-locked DMA sources).  False when the driver refuses."""
+    if nbytes <= 0:
+        return False
+    if address in _REGISTERED and _REGISTERED[address] >= nbytes:
+        return True
+    if N.lib().slafb_host_register(ctypes.c_void_p(address), nbytes) != N.OK:
+        return False
+    _REGISTERED[address] = nbytes
+    return True
+
+
+def unregister_host_range(address: int) -> None:
+    if _REGISTERED.pop(address, None) is not None:
+        N.lib().slafb_host_unregister(ctypes.c_void_p(address))
+
+
 def is_page_locked(arr: np.ndarray) -> bool:
     """True when `arr` lies inside memory registered through register_host_memory."""
     a = arr.ctypes.data

@@ -156,12 +156,34 @@ class _ArrowFileFragment(Fragment):
     def __init__(self, path: str):
         self.path = path
         self._rows = None
+        self._map = None
+        self._pinned: tuple[int, int] | None = None
         self.row_lo: int | None = None      # set by the source: rows of the preceding fragments
 
     def _open(self):
         import pyarrow as pa
 
-        return pa.ipc.open_file(pa.memory_map(self.path, "r"))
+        if self._map is None:                   # one mapping per fragment for its lifetime: the views handed out keep pointing
+            self._map = pa.memory_map(self.path, "r")      # into it, and pin() page-locks exactly this address range
+        return pa.ipc.open_file(self._map)
+
+    def pin(self) -> bool:
+        """Page-lock the file's mapping (cudaHostRegister, read-only), so the record-batch views are DMA sources and the feeder
+        copies nothing on the host.  Needs the file to fit in RAM; False when the driver refuses, the staged path then remains."""
+        from ..engine import register_host_range
+
+        self._open()
+        buf = self._map.read_buffer()           # zero-copy view of the whole mapping
+        self._map.seek(0)
+        self._pinned = (buf.address, buf.size) if register_host_range(buf.address, buf.size) else None
+        return self._pinned is not None
+
+    def unpin(self) -> None:
+        from ..engine import unregister_host_range
+
+        if self._pinned is not None:
+            unregister_host_range(self._pinned[0])
+            self._pinned = None
 
     def count_rows(self) -> int:
         if self._rows is None:
@@ -213,6 +235,17 @@ class ArrowExpressionSource(ExpressionSource):
 
     def get_fragments(self) -> list[Fragment]:
         return list(self._fragments)
+
+    def pin(self) -> bool:
+        """Page-lock every fragment's mapping (see ``_ArrowFileFragment.pin``); True when all of them were accepted."""
+        ok = [f.pin() for f in self._fragments]
+        self.pinned = all(ok)
+        return self.pinned
+
+    def unpin(self) -> None:
+        for f in self._fragments:
+            f.unpin()
+        self.pinned = False
 
 
 def write_arrow_dataset(path: str, cell: np.ndarray, gene: np.ndarray, value: np.ndarray, max_rows_per_file: int,

@@ -460,3 +460,29 @@ def test_mixture_of_scanners_look_ahead_equals_the_synchronous_feeder(data, seed
     for epoch in (0, 1):
         seen = np.concatenate([x[2] for x in a if x[0] == epoch])
         assert sorted(seen.tolist()) == list(range(N_CELLS))
+
+
+def test_arrow_source_page_locked_maps_feed_the_copy_engine_directly(tmp_path, data):
+    """ArrowExpressionSource.pin(): the files' read-only mappings are registered with the driver, the record-batch views are
+    DMA sources and the feeder's pinned staging ring is never allocated; tokens are the same either way.  (A driver that refuses
+    to register file mappings leaves the staged path in place: pin() then returns False and only the equality is checked.)"""
+    write_arrow_dataset(str(tmp_path / "expression.arrow"), data.cell, data.gene, data.value, max_rows_per_file=3001, rows_per_batch=700)
+    expected = _expected_rows(data, "geneformer", max_genes=400)
+    for pin in (False, True):
+        src = ArrowExpressionSource(str(tmp_path / "expression.arrow"))
+        pinned = src.pin() if pin else False
+        arr = SyntheticSLAFArray(src, np.asarray(data.cell_start), N_GENES)
+        proc = PrefetchBatchProcessor(arr, RandomShuffle(), GeneformerTokenizer(arr, max_genes=400), seed=42, use_mixture_of_scanners=False,
+                                      by_fragment=True, verbose=False)
+        proc.SMALL_PIECE_ROWS = 650                    # the 700-row record batches of this small table must be page-locked or staged; pending cells stay small
+        out = _drain(proc)
+        seen = _check_rows([{"input_ids": o.input_ids, "attention_mask": o.attention_mask, "cell_ids": o.cell_ids} for o in out], expected, scgpt=False)
+        assert sorted(seen) == list(range(N_CELLS))
+        if pinned:
+            assert proc._staging.capacity == 0, "page-locked views must not go through the staging ring"
+        elif not pin:
+            assert proc._staging.capacity > 0
+        torch.cuda.synchronize()
+        proc.close()
+        src.unpin()
+        print("arrow mappings page-locked:", pinned)
