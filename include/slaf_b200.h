@@ -159,8 +159,12 @@ int slafb_tokenize(slafb_ctx *ctx, const slafb_coo *in, const slafb_params *p, c
 /* Same path, pipelined (double buffered): submit() enqueues the H2D copy (host input) and the
  * CSR build on the context's side stream and returns a slot; collect() waits for the cell
  * count, applies the shuffle and launches the tokenizing kernels on `stream`.  Eight slots:
- * up to seven submits may precede the collect of the oldest batch (a deep queue absorbs host scheduling hiccups).  Replaces the AsyncPrefetcher hand-off
- * (slaf/ml/datasets.py:1242-1294) for the device-side part of the work. */
+ * up to eight batches may be in flight and they may be collected in any order (a ninth submit returns SLAFB_ERR_BUSY and
+ * changes nothing).  A submit takes a free slot whose previous tokenization has finished and that already owns staging
+ * columns, so a caller with one or two batches in flight touches two or three slots' worth of staging (12 B/row each),
+ * a deep pipeline all eight.  Small host pieces in pageable memory are copied through a pinned scratch of the slot first:
+ * a pageable async copy would make the calling thread wait for the copy stream to drain.  Replaces the AsyncPrefetcher
+ * hand-off (slaf/ml/datasets.py:1242-1294) for the device-side part of the work. */
 int slafb_submit(slafb_ctx *ctx, const slafb_coo *in, void *stream, int32_t *slot);
 /* submit() for a batch that is the concatenation of n_pieces row blocks (all host or all device, same
  * dtypes): the partial cells carried over plus the fragment chunks just read (datasets.py:748-760,
@@ -241,7 +245,8 @@ int slafb_gene_median(slafb_ctx *ctx, const uint32_t *hist, int64_t n_genes, int
 int slafb_host_alloc(void **ptr, size_t bytes);
 int slafb_host_free(void *ptr);
 /* Page-lock memory the caller already owns (e.g. the column buffers of an in-memory / memory-mapped
- * expression table), so slices of it are DMA sources without a staging copy. */
+ * expression table), so slices of it are DMA sources without a staging copy.  Read-only mappings are
+ * retried with cudaHostRegisterReadOnly; SLAFB_ERR_CUDA when the driver refuses both. */
 int slafb_host_register(void *ptr, size_t bytes);
 int slafb_host_unregister(void *ptr);
 
