@@ -322,11 +322,14 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-loader", action="store_true")
     ap.add_argument("--verify-cells", type=int, default=2048)
-    ap.add_argument("--watchdog", type=int, default=780, help="seconds after which every thread's stack is dumped to stderr and the run aborts")
+    ap.add_argument("--watchdog", type=int, default=None,
+                    help="seconds after which every thread's stack is dumped to stderr and the run aborts (default: 780 s, more for very long runs; 0 = off)")
     args = ap.parse_args()
     import faulthandler
 
     faulthandler.enable()
+    if args.watchdog is None:
+        args.watchdog = int(max(780, 300 + 0.15 * (args.steps + args.warmup)))
     if args.watchdog > 0:       # a hang must cost a bounded amount of box time and leave a trace of where it sat
         faulthandler.dump_traceback_later(args.watchdog, exit=True)
     w = WORKLOADS[args.workload]
