@@ -348,6 +348,10 @@ class PrefetchBatchProcessor:
         self._engine: HotPathEngine | None = None
         self._staging = _Staging(depth=3, threads=copy_threads)     # three: with the look-ahead two loads can be in flight while a third is assembled
         self._ahead: _Staged | BaseException | None = None
+        # the reference's tests (and users) call reset_for_epoch from the consumer thread while the prefetcher thread is inside
+        # load_prefetch_batch (tests/test_pytorch_datasets.py:1064-1067); with batches in flight on the device those two must
+        # not interleave
+        self._lock = threading.RLock()
         self._read_pool: ThreadPoolExecutor | None = None
 
     # ------------------------------------------------------------------ readers / epochs
@@ -368,13 +372,14 @@ class PrefetchBatchProcessor:
     def reset_for_epoch(self, epoch: int) -> None:
         if epoch < 0 or epoch >= self.n_epochs:
             raise ValueError(f"Invalid epoch {epoch}. Must be 0 <= epoch < {self.n_epochs}")
-        self._drop_ahead()
-        self.current_epoch = epoch
-        self.batch_id = 0
-        self.partial_cell_data = {}
-        self._non_mos_pending_tail_flush = False
-        self._mos_final_flush = False
-        self._open_readers()
+        with self._lock:
+            self._drop_ahead()
+            self.current_epoch = epoch
+            self.batch_id = 0
+            self.partial_cell_data = {}
+            self._non_mos_pending_tail_flush = False
+            self._mos_final_flush = False
+            self._open_readers()
 
     def get_timing_metrics(self) -> dict | None:
         if not self.log_metrics or self._timing_metrics is None:
@@ -576,6 +581,10 @@ class PrefetchBatchProcessor:
         return self._fused_ok()
 
     def load_prefetch_batch(self) -> PrefetchBatch:
+        with self._lock:
+            return self._load_prefetch_batch()
+
+    def _load_prefetch_batch(self) -> PrefetchBatch:
         if self._lookahead_ok():
             return self._load_with_lookahead()
         while True:
@@ -977,6 +986,10 @@ class PrefetchBatchProcessor:
                                       tokenize_time=tokenize_time, epoch=self.current_epoch)
 
     def close(self) -> None:
+        with self._lock:
+            self._close()
+
+    def _close(self) -> None:
         try:
             self._drop_ahead()
         except Exception:

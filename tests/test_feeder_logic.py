@@ -362,3 +362,24 @@ def test_arrow_fragments_are_fed_as_record_batch_views(stand_in, tmp_path, mos):
     for run in runs:
         for epoch in (0, 1):
             assert sorted(int(c) for x in run if x[0] == epoch for c in x[2]) == list(range(N_CELLS))
+
+
+def test_reset_for_epoch_from_the_consumer_thread_while_the_prefetcher_runs(stand_in):
+    """reference tests/test_pytorch_datasets.py:1064-1067 resets the processor of a running dataset from the main thread; with
+    loads in flight that must not interleave with the prefetcher's load (the processor serialises the two)."""
+    b = _data()
+    arr = SyntheticSLAFArray(ArrayExpressionSource(b.cell, b.gene, b.value, 900), b.cell_start, N_GENES)
+    ds = SLAFIterableDataset(arr, GeneformerTokenizer(arr, max_genes=16), batch_size=16, use_mixture_of_scanners=False, by_fragment=True,
+                             verbose=False, n_epochs=3, max_queue_size=2)
+    it = iter(ds)
+    first = [next(it) for _ in range(5)]
+    assert all(x["epoch"] == 0 for x in first)
+    ds.batch_processor.reset_for_epoch(2)
+    assert ds.batch_processor.current_epoch == 2
+    rest = list(it)
+    assert ds.prefetcher.error is None
+    tail = [x for x in rest if x["epoch"] == 2]
+    assert tail and rest[-1]["epoch"] == 2
+    ids = [int(c) for x in tail for c in x["cell_ids"]]
+    assert sorted(ids) == list(range(N_CELLS))                      # the epoch after the reset is complete and clean
+    assert not any(eng.slots for eng in stand_in)                   # nothing left on the device
