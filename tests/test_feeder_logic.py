@@ -87,6 +87,7 @@ def stand_in(monkeypatch):
 
     monkeypatch.setattr(D.PrefetchBatchProcessor, "_engine_for", engine_for)
     monkeypatch.setattr(D, "pinned_empty", lambda n, dt=np.uint8: np.empty(n, dt))
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: False)      # also on a GPU box these tests stay on the stand-in
     monkeypatch.setattr(torch.cuda, "Event", _Event)
     monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: None)
     return engines
