@@ -802,15 +802,23 @@ class PrefetchBatchProcessor:
         # cell column must show exactly that id starting exactly there -- a shifted or stale index is caught, O(1) per batch
         offs = np.concatenate(([0], np.cumsum([len(p) for p in pieces])))
         C = len(seg_cell)
-        for j in np.unique(np.linspace(0, max(C - 1, 0), num=min(C, 64)).astype(np.int64)) if C else []:
-            row = int(seg_start[j])
-            k = int(np.searchsorted(offs, row, side="right")) - 1
-            a = row - int(offs[k])
-            ok = int(pieces[k].cell[a]) == int(seg_cell[j]) and (a == 0 or int(pieces[k].cell[a - 1]) != int(seg_cell[j]))
+        if C:
+            probe = np.unique(np.linspace(0, C - 1, num=min(C, 64)).astype(np.int64))
+            rows = seg_start[probe].astype(np.int64)
+            which = np.searchsorted(offs, rows, side="right") - 1
+            want = np.asarray(seg_cell)[probe].astype(np.int64)
+            ok = True
+            for k in np.unique(which):
+                sel_k = which == k
+                a = rows[sel_k] - int(offs[k])
+                col = pieces[int(k)].cell
+                here = col[a].astype(np.int64)
+                before = col[np.maximum(a - 1, 0)].astype(np.int64)
+                ok = ok and bool(np.all(here == want[sel_k])) and bool(np.all((a == 0) | (before != want[sel_k])))
             if not ok:
                 raise ValueError("_cell_start_index does not describe the expression rows (a cell does not start where the index says)")
-        if C and int(pieces[-1].cell[-1]) != int(seg_cell[-1]):
-            raise ValueError("_cell_start_index does not describe the expression rows (last cell id differs)")
+            if int(pieces[-1].cell[-1]) != int(seg_cell[-1]):
+                raise ValueError("_cell_start_index does not describe the expression rows (last cell id differs)")
         signed = pieces[0].cell.dtype == np.int32
         direct = all(len(p) <= self.SMALL_PIECE_ROWS or (is_page_locked(p.gene) and is_page_locked(p.value)) for p in pieces)
         if direct and len(pieces) <= 256:

@@ -48,6 +48,14 @@ class StandInEngine:
     def submit(self, cell, gene, value, shuffle_seed=None):
         return self._put(np.asarray(cell))
 
+    def submit_segments(self, pieces, seg_start, seg_cell, cell_signed=False, shuffle_seed=None):
+        # the cell-start-index route: no cell column; the table comes from the host and must cover the rows handed over
+        n_rows = sum(len(np.asarray(g)) for g, _v in pieces)
+        seg_start, seg_cell = np.asarray(seg_start), np.asarray(seg_cell)
+        assert all(len(np.asarray(g)) == len(np.asarray(v)) for g, v in pieces)
+        assert seg_start[0] == 0 and seg_start[-1] == n_rows and len(seg_start) == len(seg_cell) + 1 and np.all(np.diff(seg_start.astype(np.int64)) > 0)
+        return self._put(np.repeat(seg_cell, np.diff(seg_start.astype(np.int64))))
+
     def segments(self, slot):
         cell = self.slots[slot]
         starts, _ends, ids = D._runs(cell)
@@ -87,6 +95,7 @@ def stand_in(monkeypatch):
 
     monkeypatch.setattr(D.PrefetchBatchProcessor, "_engine_for", engine_for)
     monkeypatch.setattr(D, "pinned_empty", lambda n, dt=np.uint8: np.empty(n, dt))
+    monkeypatch.setattr(D, "is_page_locked", lambda a: True)           # "direct" route: pieces are handed over as they are
     monkeypatch.setattr(torch.cuda, "is_available", lambda: False)      # also on a GPU box these tests stay on the stand-in
     monkeypatch.setattr(torch.cuda, "Event", _Event)
     monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: None)
@@ -384,3 +393,32 @@ def test_reset_for_epoch_from_the_consumer_thread_while_the_prefetcher_runs(stan
     ids = [int(c) for x in tail for c in x["cell_ids"]]
     assert sorted(ids) == list(range(N_CELLS))                      # the epoch after the reset is complete and clean
     assert not any(eng.slots for eng in stand_in)                   # nothing left on the device
+
+
+@pytest.mark.parametrize("mode", ["fragment", "sequential", "mos"])
+def test_cell_start_index_route_gives_the_same_stream(stand_in, mode):
+    """use_cell_start_index=True: the segment table handed to the engine is derived from _cell_start_index and the chunk
+    positions alone; loads, order and pending cells are those of the default route (which reads the table off the cell column)."""
+    b = _data()
+    kw = dict(use_mixture_of_scanners=(mode == "mos"), by_fragment=(mode != "sequential"), n_scanners=3, prefetch_batch_size=1000,
+              batches_per_chunk=2 if mode == "sequential" else 1, n_epochs=2)
+    runs = []
+    for csi_route in (False, True):
+        proc = _proc(b, use_cell_start_index=csi_route, **kw)
+        np.random.seed(6)
+        runs.append(_drain(proc))
+        assert not proc._engine.slots
+    _same(*runs)
+
+
+def test_cell_start_index_that_does_not_match_the_rows_is_refused(stand_in):
+    b = _data()
+    for shift in (3, -2):
+        csi = b.cell_start.copy()
+        csi[1:-1] += shift                                             # every cell starts somewhere else than the index says
+        proc = _proc(b, csi=csi, use_mixture_of_scanners=False, by_fragment=True, use_cell_start_index=True)
+        with pytest.raises(ValueError, match="_cell_start_index does not describe"):
+            _drain(proc)
+    relabel = _proc(b, cell=(b.cell + 1).astype(b.cell.dtype), csi=np.concatenate(([0], b.cell_start)), use_mixture_of_scanners=False,
+                    by_fragment=True, use_cell_start_index=True)
+    _drain(relabel)                                                    # ids shifted together with the index: consistent again
