@@ -17,8 +17,10 @@ tokenizer loop) so that timing it says something about the reference's CPU path:
     tokenize  slaf/ml/tokenizers.py:375-479, 635-722 (per-cell Python loop, numpy rows)
 
 Parity status: the tokenizer functions are pinned against the reference's own
-tokenizers.py (tests/golden/tokenizer_golden.npz); the window functions are pinned only by
-the reference tests' known-answer vectors (tests/golden/window_kats.json).
+tokenizers.py (tests/golden/tokenizer_golden.npz); the window functions are pinned by the
+reference tests' known-answer vectors plus hand-worked vectors for the percentile and
+integer-storage binned branches (tests/golden/window_kats.json) and cross-checked against a
+pandas transcription of the reference's expressions (tests/test_oracle_crosscheck.py).
 """
 
 from __future__ import annotations

@@ -6,7 +6,7 @@
 // The algorithm is CPython's published one (Modules/_randommodule.c: MT19937 seeded with
 // init_by_array over the 32-bit limbs of abs(seed); Lib/random.py: Fisher-Yates from the top
 // with _randbelow_with_getrandbits = rejection sampling on getrandbits(bit_length(n))).
-// tests/test_shuffle.py checks it against the interpreter's own `random` for many (seed, n).
+// tests/test_abi.py::test_shuffle_matches_cpython_random checks it against the interpreter's own `random` for many (seed, n).
 // O(n), ~3 ns per cell: this is control-plane work that stays on the host by design
 // (the permutation depends only on (seed, n_cells)); the device applies it as an indirection.
 #pragma once

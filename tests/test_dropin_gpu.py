@@ -40,6 +40,8 @@ def _frame(case, kind):
 def _window_for(case):
     if case["mode"] == "geneformer":
         return GeneformerWindow(), {}
+    if case["mode"] == "geneformer_pct":
+        return GeneformerWindow(), {"min_percentile": case["min_percentile"]}
     if case["mode"] == "scgpt_binned":
         return ScGPTWindow(), {"n_expression_bins": case["n_bins"], "use_binned_expressions": True}
     return ScGPTWindow(), {"n_expression_bins": case["n_bins"], "use_binned_expressions": False}

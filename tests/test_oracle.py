@@ -27,7 +27,8 @@ def test_window_kats_c_and_py(case):
     cell = np.asarray(case["cell"], np.int32)
     gene = np.asarray(case["gene"], np.int32)
     value = np.asarray(case["value"], case["value_dtype"])
-    cids, offs, genes, exprs = c_oracle.window(cell, gene, value, case["mode"], case["max_items"], n_bins=case["n_bins"])
+    cids, offs, genes, exprs = c_oracle.window(cell, gene, value, case["mode"], case["max_items"], n_bins=case["n_bins"],
+                                               min_percentile=case.get("min_percentile"))
     assert cids.tolist() == case["expect_cells"]
     got_genes = _lists(offs, genes)
     assert got_genes == case["expect_genes"]
@@ -40,9 +41,10 @@ def test_window_kats_c_and_py(case):
     if "expect_len" in case:
         assert [len(g) for g in got_genes] == case["expect_len"]
     # the independent numpy restatement gives the same frame
-    kind = {"geneformer": "geneformer", "scgpt_raw": "scgpt", "scgpt_binned": "scgpt"}[case["mode"]]
+    kind = {"geneformer": "geneformer", "geneformer_pct": "geneformer", "scgpt_raw": "scgpt", "scgpt_binned": "scgpt"}[case["mode"]]
+    extra = {"min_percentile": case["min_percentile"]} if "min_percentile" in case else {}
     w = pr.window_apply(cell, gene, value, kind, case["max_items"], n_expression_bins=case["n_bins"],
-                        use_binned_expressions=case["mode"] == "scgpt_binned")
+                        use_binned_expressions=case["mode"] == "scgpt_binned", **extra)
     assert w["cell_integer_id"] == case["expect_cells"]
     assert w["gene_sequence"] == case["expect_genes"]
     if kind == "scgpt" and len(cell):

@@ -183,7 +183,8 @@ def test_window_facade_reference_kats(engine, case):
     cell = np.asarray(case["cell"], np.int32)
     gene = np.asarray(case["gene"], np.int32)
     value = np.asarray(case["value"], case["value_dtype"])
-    w = engine.window(cell, gene, value, mode=case["mode"], max_items=case["max_items"], n_bins=case["n_bins"])
+    w = engine.window(cell, gene, value, mode=case["mode"], max_items=case["max_items"], n_bins=case["n_bins"],
+                      min_percentile=case.get("min_percentile"))
     offs = w.offsets.cpu().numpy()
     assert w.cell_ids.cpu().tolist() == case["expect_cells"]
     assert _lists(offs, w.genes.cpu().numpy()) == case["expect_genes"]
