@@ -7,13 +7,20 @@ A "step" is one pass of the hot path (shuffle order -> CSR build -> window -> to
 collate into the batch tensors) over one prefetch batch of `--cells-per-step` complete cells.
 
   value  : whole-job cells/s with the COO columns already resident in HBM (3 distinct batches
-           cycled, each larger than the 126 MB L2), pipelined submit/collect, CUDA events on the
-           launch stream, max over ranks.
-  e2e    : same steps through the public API with HOST (pinned) columns: the H2D copy of every
-           step's input and the D2H read of its result (cell count + cell ids) are inside the
-           timed region.
-  roofline: dominant kernel (K2 tokenize_cells_kernel), algorithmic bytes / CUDA-event time,
-           against MEASURED_PEAKS.json's HBM copy bandwidth.
+           cycled, each larger than the 126 MB L2), through the library's pipe (slafb_pipe_push:
+           one C call per step, outputs into a pre-allocated ring), NO timing events in any
+           stream, CUDA events around the K steps on the launch stream, max over ranks.  The
+           pipeline is in steady state: warm-up leaves `depth` batches in flight, every timed
+           step submits one batch and completes one (K CSR builds + K tokenizations inside
+           the window), the tail is drained after the clock stops.
+  e2e    : same steps with HOST (pinned) columns: the H2D copy of every step's input and the
+           D2H read of its result (cell ids) are inside the timed region.  Headline route =
+           the dataset's cell_start_index (gene + value columns + 8 B/cell cross the bus, the
+           loader's default); `e2e.coo_route` = the cell column shipped and scanned too.
+  roofline: dominant kernel (K2 tokenize_cells_kernel), algorithmic bytes / CUDA-event time
+           (a second pipelined pass that carries per-kernel events, and an isolated pass
+           where no two kernels overlap), against MEASURED_PEAKS.json's HBM copy bandwidth
+           and the nominal 8 TB/s.
   cpu_baseline: the oracle "port" (numpy window + per-cell Python tokenizer loop = the
            reference's structure, polars replaced by numpy) on a bounded sample, all host cores.
 
@@ -202,6 +209,45 @@ def c_oracle_rate(w, n_cells: int, seed: int = 99):
     return n_cells / dt, c_oracle.num_threads()
 
 
+def bench_config(args, w) -> dict:
+    """`config` of the JSON line -- identical in both arms (the reference arm's bounded per-step sample is described in its
+    cpu_baseline.sample, not here)."""
+    return {"workload": w["name"], "cells_per_step_per_gpu": args.cells_per_step, "value_dtype": args.value_dtype,
+            "dataset": "every step is one prefetch batch of the synthetic dataset (cells generated from (seed, rank, batch index) with "
+                       "the SURVEY section-8d generator); 3 distinct batches per GPU are cycled",
+            "l2": "3 distinct batches of ~530 MiB input each are cycled (each > 126 MB L2)",
+            "shuffle": "CPython-exact block shuffle, seed 42+step",
+            "timing": "steady-state pipeline: every timed step submits one batch and completes one; barrier + synchronize on both sides"}
+
+
+def pin_rank_cores(local_rank: int, world: int):
+    """Give every rank of a multi-GPU run its own disjoint set of whole physical cores (main thread, the library's shuffle
+    helpers, NCCL's threads and the feeder all inherit it), so that eight ranks on one 32-vCPU host do not migrate onto each
+    other's hyperthread siblings.  Returns the CPU list, or None when there are fewer cores than ranks."""
+    cpus = sorted(os.sched_getaffinity(0))
+    groups, seen = [], set()
+    for c in cpus:
+        if c in seen:
+            continue
+        sib = {c}
+        try:
+            txt = open(f"/sys/devices/system/cpu/cpu{c}/topology/thread_siblings_list").read().strip()
+            for part in txt.split(","):
+                lo, _, hi = part.partition("-")
+                sib |= set(range(int(lo), int(hi or lo) + 1))
+        except Exception:
+            pass
+        sib &= set(cpus)
+        groups.append(sorted(sib))
+        seen |= sib
+    per = len(groups) // world
+    if per < 1:
+        return None
+    mine = sorted(c for g in groups[local_rank * per:(local_rank + 1) * per] for c in g)
+    os.sched_setaffinity(0, mine)
+    return mine
+
+
 def run_reference(args, w):
     """`--impl reference`: the reference's CPU path (restated; polars/lance are not installable)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -229,7 +275,7 @@ def run_reference(args, w):
         "impl": "reference", "metric": "tokenized cells/sec", "value": rate, "unit": "cells/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * sample / rate, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-        "config": {"workload": w["name"], "cells_per_step": sample},
+        "config": bench_config(args, w),
         "cpu_baseline": {"value": rate, "unit": "cells/s", "cores": cores, "kind": "port",
                          "sample": f"{args.steps} steps x {sample} cells ({cores} processes x {per_core} cells), numpy window + per-cell Python tokenizer loop (reference structure; polars not installable)",
                          "c_oracle_cells_per_s": c_rate, "c_oracle_threads": c_thr},
@@ -261,8 +307,10 @@ def loader_rate(w, batches, dev, value_dtype):
     n_epochs = 12
     out = {"pinned_source": bool(pinned), "fragments": len(src.get_fragments()), "rows": int(len(cell)), "epochs": n_epochs,
            "mode": "by_fragment (one 16.8 M-row fragment per prefetch batch), boundary cells carried on the host; epoch 0 is warm-up, epochs 1.. are timed",
-           "cell_start_index": "extension: cell boundaries from SLAFArray._cell_start_index, the cell column stays on the host (4 B/row over PCIe instead of 8)"}
-    for bs, csi_mode, mos in ((32, False, False), (1024, False, False), (1024, True, False), (1024, False, True)):
+           "routes": "default: cell boundaries from SLAFArray._cell_start_index, the cell column stays on the host (4 B/row over PCIe); "
+                     "*_coo_route: use_cell_start_index=False, the cell column is shipped and scanned (8 B/row)"}
+    # csi_mode None = the loader's default (the index is used while it validates), False = the cell column is shipped and scanned
+    for bs, csi_mode, mos in ((32, None, False), (1024, None, False), (1024, False, False), (1024, None, True)):
         rates = []
         for _rep in range(2):                         # best of two: several loaders in one process disturb each other's first seconds
             tok = (ScGPTTokenizer(arr, vocab_size=w["vocab"], n_expression_bins=w["n_bins"], max_genes=w["max_genes"], device=dev)
@@ -294,7 +342,7 @@ def loader_rate(w, batches, dev, value_dtype):
             torch.cuda.synchronize(dev)
             rates.append(n / (t1 - t0))
             del loader, last, batch
-        out[f"cells_per_s_batch{bs}" + ("_cell_start_index" if csi_mode else "") + ("_mixture_of_scanners" if mos else "")] = max(rates)
+        out[f"cells_per_s_batch{bs}" + ("_coo_route" if csi_mode is False else "") + ("_mixture_of_scanners" if mos else "")] = max(rates)
     src.unpin()
     return out
 
@@ -350,26 +398,23 @@ def main():
                         "c_oracle_cells_per_s": c_rate, "c_oracle_threads": c_thr,
                         "published_reference": "5,350 cells/s scGPT / 6,494 cells/s Geneformer on M1 Max (docs/benchmarks/ml_benchmarks.md:49-52)"}
 
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    # one disjoint set of whole cores per rank, taken BEFORE any thread exists (torch, NCCL, the library's helpers inherit it)
+    my_cpus = pin_rank_cores(local_rank, world) if world > 1 and not os.environ.get("SLAFB_BENCH_NO_PIN") else None
+    for var in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+        os.environ.setdefault(var, "1")
+
     import torch
     import torch.distributed as dist
 
     from slaf_b200 import synthetic
-    from slaf_b200.engine import HotPathEngine
+    from slaf_b200.engine import HotPathEngine, PreparedInput
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.set_num_threads(1)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    try:   # keep this rank's threads (and the pinned buffers they first touch) on the GPU's NUMA node
-        import pynvml
-
-        pynvml.nvmlInit()
-        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-        idx = int(vis.split(",")[local_rank]) if vis and vis.split(",")[local_rank].isdigit() else local_rank
-        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(idx))
-    except Exception:
-        pass
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -393,6 +438,14 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    def gather_ranks(xs: list[float]) -> list[list[float]]:
+        if world == 1:
+            return [xs]
+        mine = torch.tensor(xs, dtype=torch.float64, device=dev)
+        out = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(out, mine)
+        return [[round(float(v), 5) for v in t.tolist()] for t in out]
+
     # ---- synthetic shard of this rank: NB distinct prefetch batches, cycled (weak scaling: fixed work per GPU)
     NB = 3
     cps = args.cells_per_step
@@ -403,9 +456,6 @@ def main():
     kw = dict(mode=w["mode"], max_genes=w["max_genes"], n_bins=w["n_bins"], vocab_size=w["vocab"])
     if w.get("min_percentile") is not None:
         kw["min_percentile"] = w["min_percentile"]
-    # per-kernel CUDA events on every 8th batch (each record is a stream operation); short runs time every batch so
-    # that the roofline still has launches to average
-    timing_every = int(os.environ.get("SLAFB_BENCH_TIMING_EVERY", "8" if args.steps >= 24 else "1"))
 
     dev_cols = [(torch.from_numpy(b.cell).to(dev), torch.from_numpy(b.gene).to(dev), torch.from_numpy(b.value).to(dev)) for b in batches]
     stats = None
@@ -416,13 +466,14 @@ def main():
 
         gene_stats(eng, dev_cols[:1], w["n_genes"])        # warm-up (NCCL communicator, kernel load)
         barrier()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0, s1, s2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         s0.record()
-        total, count = gene_stats(eng, dev_cols, w["n_genes"])
-        s1.record()
+        total, count = gene_stats(eng, dev_cols, w["n_genes"], mark=s1)
+        s2.record()
         barrier()
         norm_dev = normalisation_vector(total, count).contiguous()
-        stats = {"ms_stats_plus_allreduce": max_over_ranks(s0.elapsed_time(s1)), "rows_per_gpu": int(sum(b.n_rows for b in batches)),
+        stats = {"ms_stats_plus_allreduce": max_over_ranks(s0.elapsed_time(s2)), "ms_stats_kernels": max_over_ranks(s0.elapsed_time(s1)),
+                 "ms_allreduce": max_over_ranks(s1.elapsed_time(s2)), "rows_per_gpu": int(sum(b.n_rows for b in batches)),
                  "allreduce_bytes": 2 * 8 * w["n_genes"], "collective": "NCCL all-reduce (sum, int64) of [2, n_genes]" if world > 1 else "none (1 rank)"}
         kw.update(order="rank", norm=norm_dev)
 
@@ -431,29 +482,32 @@ def main():
     from oracle import c_oracle
     import random as _random
 
-    nv = min(args.verify_cells, cps)
-    vb = batches[0]
-    rows_v = int(vb.cell_start[nv])
-    _random.seed(42)
-    perm = list(range(nv)); _random.shuffle(perm)
-    if w.get("rank_norm"):
-        from oracle import py_restatement as _pr
+    def oracle_for(vb, n_cells, seed):
+        rows_v = int(vb.cell_start[n_cells])
+        _random.seed(seed)
+        perm = list(range(n_cells)); _random.shuffle(perm)
+        if w.get("rank_norm"):
+            from oracle import py_restatement as _pr
 
-        nv = min(nv, 512)
-        rows_v = int(vb.cell_start[nv])
-        w_ids, w_mask, w_cids = _pr.geneformer_rank_value(vb.cell[:rows_v], vb.gene[:rows_v], vb.value[:rows_v], w["max_genes"],
-                                                          norm=norm_dev.cpu().numpy(), order="rank", seed=42)
-        want = (w_ids, w_mask, None, w_cids)
-    else:
-        want = c_oracle.tokenize(vb.cell[:rows_v], vb.gene[:rows_v], vb.value[:rows_v], w["mode"], w["max_genes"], perm=perm,
-                                 n_bins=w["n_bins"], vocab_size=w["vocab"], min_percentile=w.get("min_percentile"))
-    got = eng.tokenize(vb.cell[:rows_v], vb.gene[:rows_v], vb.value[:rows_v], shuffle_seed=42, **kw)
-    ok = (np.array_equal(got.input_ids.cpu().numpy(), want[0]) and np.array_equal(got.attention_mask.cpu().numpy(), want[1])
-          and (want[2] is None or np.array_equal(got.values.cpu().numpy(), want[2])) and np.array_equal(got.cell_ids.cpu().numpy(), want[3]))
-    if not ok:
+            w_ids, w_mask, w_cids = _pr.geneformer_rank_value(vb.cell[:rows_v], vb.gene[:rows_v], vb.value[:rows_v], w["max_genes"],
+                                                              norm=norm_dev.cpu().numpy(), order="rank", seed=seed)
+            return rows_v, (w_ids, w_mask, None, w_cids)
+        return rows_v, c_oracle.tokenize(vb.cell[:rows_v], vb.gene[:rows_v], vb.value[:rows_v], w["mode"], w["max_genes"], perm=perm,
+                                         n_bins=w["n_bins"], vocab_size=w["vocab"], min_percentile=w.get("min_percentile"))
+
+    def same(got, want) -> bool:
+        return (np.array_equal(got.input_ids.cpu().numpy(), want[0]) and np.array_equal(got.attention_mask.cpu().numpy(), want[1])
+                and (want[2] is None or np.array_equal(got.values.cpu().numpy(), want[2])) and np.array_equal(got.cell_ids.cpu().numpy(), want[3]))
+
+    nv = min(args.verify_cells, cps, 512 if w.get("rank_norm") else cps)
+    rows_v, want = oracle_for(batches[0], nv, 42)
+    got = eng.tokenize(batches[0].cell[:rows_v], batches[0].gene[:rows_v], batches[0].value[:rows_v], shuffle_seed=42, **kw)
+    if not same(got, want):
         raise SystemExit("PARITY FAILURE: CUDA path differs from the oracle; refusing to report throughput")
+    del got
 
     host_cols = [tuple(torch.from_numpy(a).pin_memory() for a in (b.cell, b.gene, b.value)) for b in batches]
+    segs = [(b.cell_start.astype(np.uint32), b.cell[b.cell_start[:-1]].astype(np.uint32)) for b in batches]
     tot_rows = [b.n_rows for b in batches]
     vbytes = 2 if args.value_dtype == "uint16" else 4
     gbytes = batches[0].gene.dtype.itemsize
@@ -462,92 +516,106 @@ def main():
     def bytes_over(n_steps):   # (K1, K2, H2D) algorithmic bytes of n_steps steps (batches are cycled)
         return tuple(sum(per_batch[i % NB][j] for i in range(n_steps)) for j in range(3))
 
-    def run_steps(cols, n_steps, read_result, depth=int(os.environ.get("SLAFB_BENCH_DEPTH", "4")), segs=None):
-        """pipelined: up to `depth` submits (H2D + CSR build) run ahead of the collect of the
-        oldest batch.  Returns (#cells, #rows, d2h bytes)."""
-        from collections import deque
+    DEPTH = int(os.environ.get("SLAFB_BENCH_DEPTH", "4"))
+    pipe = eng.pipe(ring=3, capacity_cells=cps + 1024, depth=DEPTH, **kw)
+    in_dev = [PreparedInput([c]) for c in dev_cols]
+    in_host = [PreparedInput([c]) for c in host_cols]
+    in_host_csi = [PreparedInput([c], seg_start=sg[0], seg_cell=sg[1]) for c, sg in zip(host_cols, segs)]
+    host_ids = torch.empty(cps + 1024, dtype=torch.int64).pin_memory()
 
-        cells = rows = d2h = 0
-        q = deque()
-        nxt = 0
-        keep = None
-        for i in range(n_steps):
-            while nxt < n_steps and len(q) <= depth:
-                if segs is None:
-                    q.append(eng.submit(*cols[nxt % NB], shuffle_seed=42 + nxt))   # seed known at submit: the library prepares the shuffle off-thread
-                else:     # the cell boundaries come from the dataset's cell_start_index: gene / value columns only
-                    q.append(eng.submit_segments([cols[nxt % NB][1:]], *segs[nxt % NB], shuffle_seed=42 + nxt))
-                nxt += 1
-            out = eng.collect(q.popleft(), shuffle_seed=42 + i, **kw)
-            cells += out.n_cells
-            rows += tot_rows[i % NB]
-            if read_result:
-                keep = out.cell_ids.to("cpu", non_blocking=False)   # D2H read of the step's result
-                d2h += 8 + 8 * out.n_cells
-        return cells, rows, d2h
+    class Stream:
+        """The steady pipeline over cycled inputs: `prime` leaves DEPTH batches in flight, every `step` submits one batch and
+        completes the oldest (one slafb_pipe_push), `drain` completes the tail."""
 
-    # ---- value: inputs resident in HBM
+        def __init__(self, inputs):
+            self.inputs, self.i, self.cells, self.last = inputs, 0, 0, None
+
+        def prime(self):
+            for _ in range(DEPTH):
+                assert pipe.push(self.inputs[self.i % NB], 42 + self.i)[0] < 0
+                self.i += 1
+
+        def steps(self, n, read_result=False):
+            cells = d2h = 0
+            push, inputs = pipe.push, self.inputs
+            for _ in range(n):
+                ri, nc, seq = push(inputs[self.i % NB], 42 + self.i)
+                self.i += 1
+                cells += nc
+                if read_result:                    # D2H read of the step's result: the cell ids, in shuffled order
+                    host_ids[:nc].copy_(pipe.tensors[ri][3][:nc])
+                    d2h += 8 + 8 * nc
+            self.last = (ri, nc, seq)
+            return cells, d2h
+
+        def drain(self):
+            while pipe.pop()[0] >= 0:
+                pass
+
+    def timed(inputs, n_warm, n_steps, read_result, wall):
+        """(cells, seconds [max over ranks], this rank's seconds, d2h bytes, last completed (ring, n, seq))"""
+        st = Stream(inputs)
+        st.prime()
+        st.steps(n_warm, read_result)
+        eng.timing()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        cells, d2h = st.steps(n_steps, read_result)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        dt_wall = time.perf_counter() - t0
+        tm_ = eng.timing()                  # counters of exactly the timed steps (the drain below is not part of them)
+        barrier()
+        local = dt_wall if wall else e0.elapsed_time(e1) / 1e3
+        last = st.last
+        st.drain()
+        return cells, max_over_ranks(local), local, d2h, last, tm_
+
+    # ---- value: inputs resident in HBM, no timing events in any stream
     stage("value: warm-up + timed steps, inputs in HBM")
-    eng.set_timing_interval(timing_every)
-    run_steps(dev_cols, args.warmup, False)
-    eng.timing()
-    barrier()
+    eng.set_timing_interval(0)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    cells, rows, _ = run_steps(dev_cols, args.steps, False)
-    e1.record()
-    barrier()
-    ms_local = e0.elapsed_time(e1)
-    ms = max_over_ranks(ms_local)
-    per_rank_ms = [ms_local / args.steps]
-    if world > 1:
-        allms = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
-        dist.all_gather(allms, torch.tensor([ms_local / args.steps], dtype=torch.float64, device=dev))
-        per_rank_ms = [float(t.item()) for t in allms]
-    tm = eng.timing()
+    cells, sec, sec_local, _, last, tm = timed(in_dev, args.warmup, args.steps, False, wall=False)
+    ms = sec * 1e3
     total_cells = sum_over_ranks(cells)
-    value = total_cells / (ms / 1000.0)
+    value = total_cells / sec
+    per_rank = gather_ranks([1e3 * sec_local / args.steps] + [1000.0 * tm[f"host_{k}_ms"] / max(1, tm["batches"]) for k in ("submit", "collect", "wait")])
+    # the batch the last timed step completed, checked in full against the oracle (rank 0; the ring still holds it)
+    if rank == 0 and not w.get("rank_norm"):
+        ri, nc, seq = last
+        _, want_full = oracle_for(batches[seq % NB], nc, 42 + seq)
+        if not same(pipe.batch(ri, nc), want_full):
+            raise SystemExit("PARITY FAILURE: a batch of the timed pass differs from the oracle")
+
+    # ---- the same pipelined steps carrying per-kernel CUDA events (what roofline.frac is computed from)
+    stage("pipelined pass with per-kernel events")
+    eng.set_timing_interval(1)
+    n_ev = max(12, min(args.steps, 48))
+    tev = timed(in_dev, 3, n_ev, False, wall=False)[5]
 
     stage("isolated-kernel pass")
     # ---- isolated-kernel pass: same steps, CSR build on the launch stream so no two kernels overlap and every
     #      kernel's CUDA-event time is its own (in the pipelined run above K1 of a later batch shares HBM with K2)
     eng.set_front_on_caller(True)
-    eng.set_timing_interval(1)
-    run_steps(dev_cols, 3, False)
-    eng.timing()
     n_iso = 12
-    run_steps(dev_cols, n_iso, False)
+    for i in range(3 + n_iso):
+        if i == 3:
+            torch.cuda.synchronize(dev)
+            eng.timing()
+        eng.collect(eng.submit(*dev_cols[i % NB], shuffle_seed=42 + i), shuffle_seed=42 + i, **kw)
     torch.cuda.synchronize(dev)
     tiso = eng.timing()
     eng.set_front_on_caller(False)
-    eng.set_timing_interval(timing_every)
+    eng.set_timing_interval(0)
 
     # ---- e2e: host (pinned) columns, H2D + result read inside the timed region
     e2e = None
     if not args.no_e2e:
-        stage("e2e: host columns")
-        run_steps(host_cols, args.warmup, True)
-        eng.timing()
-        barrier()
-        t0 = time.perf_counter()
-        cells_e, rows_e, d2h_e = run_steps(host_cols, args.steps, True)
-        torch.cuda.synchronize(dev)
-        barrier()
-        dt = max_over_ranks(time.perf_counter() - t0)
-        tme = eng.timing()
-        h2d_bytes = bytes_over(args.steps)[2]
-        e2e = {"value": sum_over_ranks(cells_e) / dt, "unit": "cells/s", "h2d_bytes_per_step": h2d_bytes // args.steps,
-               "d2h_bytes_per_step": d2h_e // args.steps, "ms_per_step": 1000.0 * dt / args.steps,
-               "h2d_gbs_per_gpu": h2d_bytes / dt / 1e9,
-               "h2d_copy_gbs": (h2d_bytes * tme["timed_batches"] / max(1, tme["batches"]) / (tme["h2d_ms"] / 1e3) / 1e9) if tme["h2d_ms"] else None}
-
-        # the same call when the caller passes the dataset's cell_start_index instead of the cell column (SLAFArray always has
-        # one): the segment table (8 B per cell) replaces 4 B per row on the bus.  Checked against the COO route first.
-        stage("e2e: host columns with cell_start_index")
-        segs = [(b.cell_start.astype(np.uint32), b.cell[b.cell_start[:-1]].astype(np.uint32)) for b in batches]
+        # the two routes give identical tensors: checked once before either is timed
         a = eng.collect(eng.submit(*host_cols[0], shuffle_seed=7), shuffle_seed=7, **kw)
         a_t = [t.clone() for t in (a.input_ids, a.attention_mask, a.cell_ids)] + ([a.values.clone()] if a.values is not None else [])
         b_ = eng.collect(eng.submit_segments([host_cols[0][1:]], *segs[0], shuffle_seed=7), shuffle_seed=7, **kw)
@@ -555,19 +623,27 @@ def main():
         if not all(torch.equal(x, y) for x, y in zip(a_t, b_t)):
             raise SystemExit("PARITY FAILURE: cell_start_index route differs from the COO route")
         del a, a_t, b_, b_t
-        run_steps(host_cols, args.warmup, True, segs=segs)
-        barrier()
-        t0 = time.perf_counter()
-        cells_s, _, _ = run_steps(host_cols, args.steps, True, segs=segs)
-        torch.cuda.synchronize(dev)
-        barrier()
-        dts = max_over_ranks(time.perf_counter() - t0)
-        eng.timing()
-        seg_bytes = sum((per_batch[i % NB][2] - 4 * tot_rows[i % NB] + 8 * cps + 4) for i in range(args.steps))
-        e2e["with_cell_start_index"] = {"value": sum_over_ranks(cells_s) / dts, "unit": "cells/s", "ms_per_step": 1000.0 * dts / args.steps,
-                                        "h2d_bytes_per_step": seg_bytes // args.steps, "h2d_gbs_per_gpu": seg_bytes / dts / 1e9,
-                                        "note": "slafb_submit_segments: gene + value columns and the segment table (8 B per cell) cross the bus, "
-                                                "the cell column does not and no CSR build runs; same outputs (checked)"}
+        e2e_steps, e2e_warm = args.steps, max(3, args.warmup)
+
+        stage("e2e: host columns, cell_start_index route (headline)")
+        eng.set_timing_interval(8)
+        cells_s, dts, _, d2h_s, _, tms = timed(in_host_csi, e2e_warm, e2e_steps, True, wall=True)
+        seg_bytes = sum((per_batch[i % NB][2] - 4 * tot_rows[i % NB] + 8 * cps + 4) for i in range(e2e_steps))
+        e2e = {"value": sum_over_ranks(cells_s) / dts, "unit": "cells/s", "h2d_bytes_per_step": seg_bytes // e2e_steps,
+               "d2h_bytes_per_step": d2h_s // e2e_steps, "ms_per_step": 1000.0 * dts / e2e_steps, "h2d_gbs_per_gpu": seg_bytes / dts / 1e9,
+               "h2d_copy_gbs": (seg_bytes * tms["timed_batches"] / max(1, tms["batches"]) / (tms["h2d_ms"] / 1e3) / 1e9) if tms["h2d_ms"] else None,
+               "route": "cell_start_index (the loader's default when SLAFArray._cell_start_index validates): gene + value columns and an "
+                        "8 B/cell segment table cross the bus, the cell column does not and no CSR build runs; outputs identical to the "
+                        "COO route (checked in this run)"}
+
+        stage("e2e: host columns, COO route")
+        cells_e, dt, _, d2h_e, _, tme = timed(in_host, e2e_warm, e2e_steps, True, wall=True)
+        h2d_bytes = bytes_over(e2e_steps)[2]
+        e2e["coo_route"] = {"value": sum_over_ranks(cells_e) / dt, "unit": "cells/s", "h2d_bytes_per_step": h2d_bytes // e2e_steps,
+                            "d2h_bytes_per_step": d2h_e // e2e_steps, "ms_per_step": 1000.0 * dt / e2e_steps, "h2d_gbs_per_gpu": h2d_bytes / dt / 1e9,
+                            "h2d_copy_gbs": (h2d_bytes * tme["timed_batches"] / max(1, tme["batches"]) / (tme["h2d_ms"] / 1e3) / 1e9) if tme["h2d_ms"] else None,
+                            "route": "the reference's COO contract: all three columns cross the bus (8 B/row), K1 builds the segment table on the device"}
+        eng.set_timing_interval(0)
 
         if not args.no_loader and not w.get("rank_norm"):
             stage("loader")
@@ -575,6 +651,7 @@ def main():
             stage("loader done")
 
     clocks = sampler.stop() if rank == 0 else None
+    pipe.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -586,53 +663,59 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+    NOMINAL = 8000.0
     k1_b, k2_b, _ = bytes_over(args.steps)
-    nt = max(1, tm["timed_batches"])          # launches that carried CUDA events (every `timing_every`-th batch, all batches in rotation)
-    k2_ms, k1_ms, gen_ms = tm["tokenize_ms"] / nt, tm["csr_ms"] / nt, tm["slowpath_ms"] / nt
-    if w.get("min_percentile") is not None:       # percentile mode has no fast kernel: the general kernel IS the tokenizer
+    k1_e, k2_e, _ = bytes_over(n_ev)
+    nt = max(1, tev["timed_batches"])
+    k2_ms, k1_ms, gen_ms = tev["tokenize_ms"] / nt, tev["csr_ms"] / nt, tev["slowpath_ms"] / nt
+    slow_all = w.get("min_percentile") is not None and args.value_dtype == "float32"     # percentile on float32: the general kernel IS the tokenizer
+    if slow_all:
         k2_ms, gen_ms = gen_ms, 0.0
         tiso["tokenize_ms"] = tiso["slowpath_ms"]
-    k2_gbs = (k2_b / args.steps) / (k2_ms / 1e3) / 1e9 if k2_ms else None
-    k1_gbs = (k1_b / args.steps) / (k1_ms / 1e3) / 1e9 if k1_ms else None
+    k2_gbs = (k2_e / n_ev) / (k2_ms / 1e3) / 1e9 if k2_ms else None
     k1_i, k2_i, _ = bytes_over(n_iso)
     nti = max(1, tiso["timed_batches"])
+    iso_k2 = k2_i / n_iso / (tiso["tokenize_ms"] / nti / 1e3) / 1e9
+    iso_k1 = k1_i / n_iso / (tiso["csr_ms"] / nti / 1e3) / 1e9
     iso = {"note": "same steps with the CSR build on the launch stream: no two kernels overlap, each CUDA-event time is that kernel alone",
            "launches": int(tiso["timed_batches"]),
-           "tokenize_cells_kernel": {"avg_launch_ms": tiso["tokenize_ms"] / nti, "achieved": k2_i / n_iso / (tiso["tokenize_ms"] / nti / 1e3) / 1e9,
-                                     "frac": k2_i / n_iso / (tiso["tokenize_ms"] / nti / 1e3) / 1e9 / peak},
-           "csr_build_kernel": {"avg_launch_ms": tiso["csr_ms"] / nti, "achieved": k1_i / n_iso / (tiso["csr_ms"] / nti / 1e3) / 1e9,
-                                "frac": k1_i / n_iso / (tiso["csr_ms"] / nti / 1e3) / 1e9 / peak}}
+           "tokenize_cells_kernel": {"avg_launch_ms": tiso["tokenize_ms"] / nti, "achieved": iso_k2, "frac": iso_k2 / peak, "frac_of_nominal_8tbs": iso_k2 / NOMINAL},
+           "csr_build_kernel": {"avg_launch_ms": tiso["csr_ms"] / nti, "achieved": iso_k1, "frac": iso_k1 / peak, "frac_of_nominal_8tbs": iso_k1 / NOMINAL}}
     traffic = None
     try:   # dram__bytes_read.sum + dram__bytes_write.sum of K2 from the committed ncu --set full capture, per cell
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{args.workload}:{args.value_dtype}")
         traffic = int(tj["k2_dram_bytes_per_cell"] * cps) if tj else None
     except Exception:
         pass
+    cfg = bench_config(args, w)
+    cfg.update({"rows_per_step_per_gpu": int(np.mean(tot_rows)), "pipeline_depth": DEPTH,
+                "parity": f"bit-exact vs oracle on {nv} cells before timing and on the last batch of the timed pass ({cps} cells)",
+                "cpus_of_rank0": my_cpus, **({"gene_stats": stats} if stats else {})})
+    whole = (k1_b + k2_b) / (ms / 1e3) / 1e9 if world == 1 else None
     line = {
         "metric": "tokenized cells/sec", "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "ms_per_step_per_rank": [round(x, 5) for x in per_rank_ms], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-        "config": {"workload": w["name"], "cells_per_step_per_gpu": cps,
-                   "dataset": "every step is one prefetch batch of the synthetic dataset (cells generated from (seed, rank, batch index) with the "
-                              "SURVEY section-8d generator); 3 distinct batches per GPU are resident and cycled", "rows_per_step_per_gpu": int(np.mean(tot_rows)),
-                   "value_dtype": args.value_dtype, "l2": f"{NB} distinct resident batches of {int(np.mean(tot_rows)) * 8 >> 20} MiB input each are cycled (each > 126 MB L2)",
-                   "shuffle": "CPython-exact block shuffle, seed 42+step", "parity": f"bit-exact vs oracle on {nv} cells before timing",
-                   **({"gene_stats": stats} if stats else {})},
-        "roofline": {"bound": "hbm", "kernel": ("tokenize_rank_kernel (per-cell bitonic sort: not HBM-bound)" if w.get("rank_norm") else
-                                             "tokenize_general_kernel (exact k-th distinct value for every cell)" if w.get("min_percentile") is not None else "tokenize_cells_kernel"), "achieved": k2_gbs, "peak": peak, "unit": "GB/s",
-                     "frac": (k2_gbs / peak) if k2_gbs else None, "frac_isolated": iso["tokenize_cells_kernel"]["frac"], "traffic": traffic,
-                     "note": "frac: pipelined run, the CSR build of a later batch executes inside this kernel's CUDA-event window on the side stream "
-                             "and shares HBM with it; frac_isolated: same steps with no two kernels overlapping",
-                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s",
-                     "algorithmic_bytes_per_launch": int(k2_b / args.steps), "avg_launch_ms": k2_ms, "timed_launches": int(tm["timed_batches"]),
+        "ms_per_step": ms / args.steps, "ms_per_step_per_rank": [r[0] for r in per_rank], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "config": cfg,
+        "roofline": {"bound": "hbm", "kernel": ("tokenize_rank_kernel (per-cell sort)" if w.get("rank_norm") else
+                                             "tokenize_general_kernel (exact k-th distinct value for every cell)" if slow_all else "tokenize_cells_kernel"), "achieved": k2_gbs, "peak": peak, "unit": "GB/s",
+                     "frac": (k2_gbs / peak) if k2_gbs else None, "frac_isolated": iso["tokenize_cells_kernel"]["frac"],
+                     "frac_of_nominal_8tbs": (k2_gbs / NOMINAL) if k2_gbs else None, "traffic": traffic,
+                     "traffic_source": "static: profiles/traffic.json (dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture, per cell x cells per launch), not measured in this run",
+                     "note": "frac: a pipelined pass of the same steps that carries per-kernel CUDA events (the throughput pass above carries none); the CSR "
+                             "build of a later batch executes inside this kernel's event window on the side stream and shares HBM with it; "
+                             "frac_isolated: same steps with no two kernels overlapping",
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s", "nominal_peak": NOMINAL,
+                     "algorithmic_bytes_per_launch": int(k2_e / n_ev), "avg_launch_ms": k2_ms, "timed_launches": int(tev["timed_batches"]),
                      "csr_build_kernel": {"achieved": iso["csr_build_kernel"]["achieved"], "frac": iso["csr_build_kernel"]["frac"],
                                           "algorithmic_bytes_per_launch": int(k1_b / args.steps), "avg_launch_ms": iso["csr_build_kernel"]["avg_launch_ms"],
                                           "in_pipeline": {"event_window_ms": k1_ms, "note": "on the side stream the kernel queues behind the persistent tokenizing "
                                                           "kernel: this CUDA-event window includes waiting for free SMs, it is not a kernel duration"}},
-                     "general_path": {"cells_per_step": tm["slow_cells"] / max(1, tm["batches"]), "avg_launch_ms": gen_ms},
-                     "whole_step_hbm_frac": ((k1_b + k2_b) / (ms / 1e3) / 1e9 / peak) if world == 1 else None,
+                     "general_path": {"cells_per_step": tev["slow_cells"] / max(1, tev["batches"]), "avg_launch_ms": gen_ms},
+                     "whole_step_hbm_frac": (whole / peak) if whole else None, "whole_step_frac_of_nominal_8tbs": (whole / NOMINAL) if whole else None,
                      "isolated": iso},
         "gpu_launches": int(tm["kernel_launches"]),
         "host_us_per_step": {k: round(1000.0 * tm[f"host_{k}_ms"] / max(1, tm["batches"]), 1) for k in ("submit", "collect", "wait", "shuffle")},
+        "per_rank": {"columns": ["ms_per_step", "host_submit_us", "host_collect_us", "host_wait_us"], "rows": per_rank},
         "clocks": clocks,
     }
     if e2e:

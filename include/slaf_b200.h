@@ -17,6 +17,10 @@
  *   - `stream` is a cudaStream_t (NULL = legacy default stream); results are valid in
  *     stream order after the call that produced them returns.
  *   - there is NO CPU fallback: with no usable sm_100 device slafb_create fails.
+ *   - HOST input columns (location = SLAFB_LOC_HOST) are read by the copy engine AFTER submit returns: they must stay valid and
+ *     unmodified until the batch's H2D copy has finished -- i.e. until slafb_wait_loaded(slot) returns, or until anything
+ *     ordered after the batch's outputs on `stream` has completed (collect returning is NOT enough: it only enqueues work
+ *     behind the copy).  Small pageable pieces and the segment tables of submit_segments are copied before submit returns.
  */
 #ifndef SLAF_B200_H
 #define SLAF_B200_H
@@ -28,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SLAFB_ABI_VERSION 2
+#define SLAFB_ABI_VERSION 3
 
 typedef struct slafb_ctx slafb_ctx;
 
@@ -46,6 +50,8 @@ typedef enum {
  * (slaf/data/converter.py:2748-2799): cell_integer_id uint32|int32, gene_integer_id
  * uint16|int32|uint32, value uint16|float32.  No nulls, no NaN. */
 typedef enum { SLAFB_U16 = 0, SLAFB_I32 = 1, SLAFB_U32 = 2, SLAFB_F32 = 3 } slafb_dtype;
+/* Gene ids given as SLAFB_U32 are read as int32: they must be below 2^31 (SLAF's gene_integer_id is a dense index,
+ * converter.py:2432-2434; a table with more than 2^31 genes does not exist). */
 
 /* Which window + tokenizer pair runs (slaf/ml/aggregators.py, slaf/ml/tokenizers.py). */
 typedef enum {
@@ -180,6 +186,26 @@ int slafb_submit_pieces(slafb_ctx *ctx, const slafb_coo *pieces, int32_t n_piece
 int slafb_submit_segments(slafb_ctx *ctx, const slafb_coo *pieces, int32_t n_pieces, const uint32_t *seg_start,
                           const uint32_t *seg_cell, int64_t n_cells, void *stream, int32_t *slot);
 
+/* submit() for a feeder that has the index itself: the segment table is derived INSIDE the library from
+ * SLAFArray._cell_start_index (slaf/core/slaf.py:645-702) and the table position of each piece, replacing the host side of the
+ * reference's completeness bookkeeping (slaf/ml/datasets.py:891-928) for the rows handed over.  Piece i holds the table rows
+ * [row_lo[i], row_lo[i] + pieces[i].n_rows); csi[c] is the first table row of cell c, csi[n_csi - 1] the total row count (int64,
+ * host).  Pieces that continue one cell back to back give ONE segment; a cell that occurs in two separated places gives two
+ * segments with the same id (the caller splices, as after slafb_segments).  check: 0 = trust the index, 1 = compare every 16th
+ * segment head (and each piece's last row) with pieces[i].cell, 2 = every head; a mismatch is SLAFB_ERR_INVALID and nothing is
+ * submitted.  pieces[i].cell may be NULL (nothing to compare with); it never crosses the bus.  *n_cells = segments found; the table
+ * itself is available through slafb_segments() without waiting for the GPU. */
+int slafb_submit_csi(slafb_ctx *ctx, const slafb_coo *pieces, int32_t n_pieces, const int64_t *row_lo, const int64_t *csi,
+                     int64_t n_csi, int32_t check, void *stream, int32_t *slot, int64_t *n_cells);
+
+/* The host half of slafb_submit_csi on its own (no GPU involved, no context needed): the segment table the index implies for
+ * the pieces, written to seg_start[capacity_cells + 1] / seg_cell[capacity_cells]. */
+int slafb_csi_segments(const slafb_coo *pieces, int32_t n_pieces, const int64_t *row_lo, const int64_t *csi, int64_t n_csi,
+                       int32_t check, uint32_t *seg_start, uint32_t *seg_cell, int64_t capacity_cells, int64_t *n_cells);
+
+/* Blocks until the H2D copy of the batch last submitted into `slot` has finished: its host columns may be reused. */
+int slafb_wait_loaded(slafb_ctx *ctx, int32_t slot);
+
 /* Optional hint between submit() and collect(): the shuffle seed the batch will be collected with
  * (seed + batch_id + epoch*10000, datasets.py:1016).  The context's helper thread then builds the
  * CPython-exact permutation as soon as the CSR build has produced the cell count, off the caller's
@@ -187,6 +213,27 @@ int slafb_submit_segments(slafb_ctx *ctx, const slafb_coo *pieces, int32_t n_pie
 int slafb_prepare_shuffle(slafb_ctx *ctx, int32_t slot, int64_t seed);
 int slafb_collect(slafb_ctx *ctx, int32_t slot, const slafb_params *p, const slafb_out *out,
                   int64_t *n_cells, void *stream);
+
+/* A steady pipeline over one context, for callers that tokenize batch after batch with fixed parameters (the AsyncPrefetcher loop,
+ * slaf/ml/datasets.py:1242-1294): ONE call per step and no allocation per step.  `ring` holds n_ring sets of caller-owned output
+ * tensors (each with capacity_cells rows); push() submits a batch (COO pieces, or gene / value pieces plus a host segment table when
+ * seg_start != NULL) with its shuffle seed and, once more than `depth` batches are in flight, collects the OLDEST one into the next
+ * ring entry (round robin) on `stream`; pop() collects the oldest without submitting.  done->ring_index is -1 when the call completed
+ * no batch.  Ring entry i is rewritten n_ring completions later in `stream` order, so consumers on that stream need no further
+ * synchronisation; consumers elsewhere order themselves with an event.  p->shuffle is SLAFB_SHUFFLE_SEED (seed per push) or
+ * SLAFB_SHUFFLE_NONE.  A batch that does not fit a ring entry is dropped with SLAFB_ERR_CAPACITY. */
+typedef struct slafb_pipe slafb_pipe;
+typedef struct {
+    int32_t ring_index; /* ring entry holding the completed batch, or -1 */
+    int32_t reserved;
+    int64_t n_cells;
+    int64_t seq;        /* push order of the completed batch (0, 1, 2, ...) */
+} slafb_pipe_result;
+int slafb_pipe_create(slafb_ctx *ctx, const slafb_params *p, const slafb_out *ring, int32_t n_ring, int32_t depth, slafb_pipe **pipe);
+int slafb_pipe_push(slafb_pipe *pipe, const slafb_coo *pieces, int32_t n_pieces, const uint32_t *seg_start, const uint32_t *seg_cell,
+                    int64_t n_seg_cells, int64_t seed, void *stream, slafb_pipe_result *done);
+int slafb_pipe_pop(slafb_pipe *pipe, void *stream, slafb_pipe_result *done);
+int slafb_pipe_destroy(slafb_pipe *pipe);
 
 /* Raw mode on the device, replacing RawPrefetchBatch (slaf/ml/datasets.py:288-296, 958-1008: shuffle only, no
  * window, no tokenizer): the submitted batch as a CSR matrix whose rows are the cells in the requested order
@@ -252,7 +299,7 @@ int slafb_host_unregister(void *ptr);
 
 /* Context options.
  *   SLAFB_OPT_TIMING_INTERVAL  n >= 1: the per-kernel CUDA-event timings are taken on every n-th batch
- *                              (default 1).  Each event record is a stream operation; bench.py samples.
+ *                              (default 1); 0: never (no timing events in any stream: bench.py's throughput passes).
  *   SLAFB_OPT_FRONT_ON_CALLER  0|1: run the CSR build of DEVICE-resident batches on the caller's stream
  *                              instead of the side stream (default 0).  Kernels then never overlap, which
  *                              is how bench.py measures each kernel's own duration. */

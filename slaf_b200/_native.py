@@ -31,12 +31,13 @@ SHUFFLE_NONE, SHUFFLE_SEED, SHUFFLE_PERM = 0, 1, 2
 FLAG_CHECK_CONTIGUOUS = 1
 OPT_TIMING_INTERVAL, OPT_FRONT_ON_CALLER = 1, 2
 ORDER_ROW, ORDER_RANK = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 EXPORTS = [
     "slafb_version", "slafb_create", "slafb_destroy", "slafb_last_error", "slafb_tokenize", "slafb_submit", "slafb_submit_pieces", "slafb_submit_segments", "slafb_host_register", "slafb_host_unregister",
     "slafb_collect", "slafb_collect_csr", "slafb_prepare_shuffle", "slafb_segments", "slafb_window", "slafb_tokenize_lists", "slafb_shuffle_perm", "slafb_gene_stats", "slafb_gene_hist", "slafb_gene_median",
     "slafb_host_alloc", "slafb_host_free", "slafb_get_timing", "slafb_set_option",
+    "slafb_submit_csi", "slafb_csi_segments", "slafb_wait_loaded", "slafb_pipe_create", "slafb_pipe_push", "slafb_pipe_pop", "slafb_pipe_destroy",
 ]
 
 
@@ -61,6 +62,10 @@ class Out(Structure):
         ("input_ids", c_void_p), ("attention_mask", c_void_p), ("values", c_void_p), ("cell_ids", c_void_p),
         ("capacity_cells", c_int64),
     ]
+
+
+class PipeResult(Structure):
+    _fields_ = [("ring_index", c_int32), ("reserved", c_int32), ("n_cells", c_int64), ("seq", c_int64)]
 
 
 class Timing(Structure):
@@ -148,6 +153,14 @@ def lib() -> ctypes.CDLL:
     L.slafb_host_free.argtypes = [c_void_p]
     L.slafb_set_option.argtypes = [c_void_p, c_int32, c_int64]
     L.slafb_get_timing.argtypes = [c_void_p, POINTER(Timing)]
+    L.slafb_submit_csi.argtypes = [c_void_p, POINTER(Coo), c_int32, c_void_p, c_void_p, c_int64, c_int32, c_void_p, POINTER(c_int32),
+                                   POINTER(c_int64)]
+    L.slafb_csi_segments.argtypes = [POINTER(Coo), c_int32, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_int64, POINTER(c_int64)]
+    L.slafb_wait_loaded.argtypes = [c_void_p, c_int32]
+    L.slafb_pipe_create.argtypes = [c_void_p, POINTER(Params), POINTER(Out), c_int32, c_int32, POINTER(c_void_p)]
+    L.slafb_pipe_push.argtypes = [c_void_p, POINTER(Coo), c_int32, c_void_p, c_void_p, c_int64, c_int64, c_void_p, POINTER(PipeResult)]
+    L.slafb_pipe_pop.argtypes = [c_void_p, c_void_p, POINTER(PipeResult)]
+    L.slafb_pipe_destroy.argtypes = [c_void_p]
     for name in EXPORTS:
         getattr(L, name)  # AttributeError here = header and library out of sync
     _lib = L

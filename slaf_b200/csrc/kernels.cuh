@@ -63,6 +63,8 @@ constexpr int kSortSmemKeys = 12288;                // general path: float keys 
 constexpr int kHashBits = 11;                       // K2, float32 values: distinct-value set of 2048 slots in shared memory,
 constexpr int kHashSlots = 1 << kHashBits;          // trusted up to kHashMaxDistinct entries (every thread may add one more
 constexpr int kHashMaxDistinct = 1536;              // before it sees the limit: 1536 + 256 < 2048, so probing always ends)
+constexpr int kPctBits = 8192;                      // K2, percentile mode on uint16 values: presence bitmap over [lo, hi] of the cell
+constexpr int kPctWords = kPctBits / 32;            // (1 KiB of shared memory); a wider value range goes to the general kernel
 
 enum : int { MODE_GF = 0, MODE_GF_PCT = 1, MODE_SCGPT_RAW = 2, MODE_SCGPT_BINNED = 3 };
 
@@ -1015,8 +1017,10 @@ __device__ __forceinline__ void fast_issue(const FastArgs &fa, uint32_t j, uint3
     if (j >= a.n_cells) { mbar_arrive(bar); return; }     // end marker for the consumers
     const uint32_t n = e - s, a0 = s & ~7u, R8 = a.n_rows & ~7u;
     const uint32_t limit = SCGPT ? a.max_genes : (a.L - 1u);
-    const bool need_val = SCGPT || (n > a.max_items);
-    const uint32_t n_g = min(n, limit);
+    constexpr bool PCT = (MODE == MODE_GF_PCT);
+    const bool need_val = SCGPT || PCT || (n > a.max_items);
+    // percentile mode: any row may survive the filter, so the genes of all rows are staged (the gene stage is as long as the value stage)
+    const uint32_t n_g = PCT ? min(n, fa.gcap - 8u) : min(n, limit);
     const uint32_t n_v = need_val ? min(n, fa.vcap - 8u) : 0u;
     const uint32_t g_end = min((s + n_g + 7u) & ~7u, R8), v_end = min((s + n_v + 7u) & ~7u, R8);
     const uint32_t g_bulk = (n_g && g_end > a0) ? g_end - a0 : 0u;
@@ -1039,12 +1043,17 @@ template <typename GeneT, typename ValT, int MODE>
 __global__ void __launch_bounds__(kFastThreads, 2048 / kFastThreads) tokenize_cells_kernel(const FastArgs fa) {
     constexpr bool SCGPT = (MODE == MODE_SCGPT_RAW || MODE == MODE_SCGPT_BINNED);
     constexpr bool BINNED = (MODE == MODE_SCGPT_BINNED);
+    constexpr bool PCT = (MODE == MODE_GF_PCT);
     constexpr bool U16 = (sizeof(ValT) == 2);
+    static_assert(!PCT || U16, "percentile mode runs in this kernel for uint16 values only (float32: general kernel)");
+    static_assert(kPctWords % kFastThreads == 0, "every thread owns a whole number of bitmap words");
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ CellDesc s_desc[2];
     __shared__ uint32_t s_ws[3 * kFastWarps];
     __shared__ uint32_t s_xstar;      // float32 binned window: key of the smallest value whose bin is >= 1
+    __shared__ uint32_t s_bitmap[PCT ? kPctWords : 1];   // percentile mode: which values of [lo, lo + 8192) occur in the cell
+    __shared__ uint32_t s_thr;        // percentile mode: the smallest value that is kept
     const TokArgs &a = fa.t;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t gbytes = fa.gcap * (uint32_t)sizeof(GeneT), vbytes = fa.vcap * (uint32_t)sizeof(ValT);
@@ -1126,10 +1135,11 @@ __global__ void __launch_bounds__(kFastThreads, 2048 / kFastThreads) tokenize_ce
         }
 
         // ---- statistics of the cell's values (range test for the dense-rank filter, max for the bins)
-        bool keep_all = (n <= k);
+        bool keep_all = PCT ? false : (n <= k);    // the percentile rule also filters cells with few rows
         bool defer = false;
-        uint32_t kmax = 0;
+        uint32_t kmax = 0, thr = 0;
         float m_f32 = 0.0f;
+        (void)thr;
         if constexpr (!U16) {
             // float32 values: ONE pass over the cell's values gives the maximum (for the bins) and, when the cell has more
             // rows than max_items, the exact number of distinct values through an open-addressing set in shared memory.
@@ -1171,7 +1181,8 @@ __global__ void __launch_bounds__(kFastThreads, 2048 / kFastThreads) tokenize_ce
 #pragma unroll
                 for (int w = 0; w < kFastWarps; w++) hi = max(hi, s_ws[kFastWarps + w]);
                 kmax = hi;
-                if constexpr (BINNED) m_f32 = log1pf_window(float_of_key(hi));   // log1p is monotone: max(log1pf(x)) = log1pf(max x)
+                // log1p is monotone: max(log1pf(x)) = log1pf(max x).  Only warp 0 (the threshold search below) needs it.
+                if constexpr (BINNED) { if (warp == 0) m_f32 = log1pf_window(float_of_key(hi)); }
                 if (do_hash) {
                     const uint32_t D = s_ws[0];
                     if (D <= cap) keep_all = true; else defer = true;            // D <= cap <= k distinct values: every row has rank <= k
@@ -1222,7 +1233,74 @@ __global__ void __launch_bounds__(kFastThreads, 2048 / kFastThreads) tokenize_ce
                 hi = max(hi, s_ws[kFastWarps + w]);
             }
             kmax = hi;
-            if (!keep_all) {
+            if constexpr (PCT) {
+                // Percentile branch (aggregators.py:167-196): the filter needs the exact number of distinct values D and the
+                // a*-th smallest of them.  Counts live in a narrow range, so a presence bitmap over [lo, hi] in shared memory
+                // answers both from the staged values in one pass; a cell whose range exceeds the bitmap goes to the general kernel.
+                const uint32_t range = hi - lo + 1u;
+                if (range > (uint32_t)kPctBits) {
+                    defer = true;
+                } else {
+                    const uint32_t words = (range + 31u) >> 5;
+                    for (uint32_t w = tid; w < words; w += kFastThreads) s_bitmap[w] = 0u;
+                    __syncthreads();
+                    volatile uint32_t *vb = s_bitmap;
+                    for (uint32_t gi = tid; gi < ngroups; gi += kFastThreads) {
+                        const uint32_t r0 = a0 + gi * 8u;
+                        const uint4 q = *reinterpret_cast<const uint4 *>(sv + gi * 8u);
+                        const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            const uint32_t r = r0 + i;
+                            if (r >= s && r < s + d.n_v) {
+                                const uint32_t b = ((w4[i >> 1] >> ((i & 1) * 16)) & 0xffffu) - lo;
+                                const uint32_t bit = 1u << (b & 31u);
+                                if (!(vb[b >> 5] & bit)) atomicOr(&s_bitmap[b >> 5], bit);   // counts repeat: look before the atomic
+                            }
+                        }
+                    }
+                    for (uint32_t r = s + d.n_v + tid; r < e; r += kFastThreads) {
+                        const uint32_t b = (uint32_t)__ldg(value_g + r) - lo;
+                        atomicOr(&s_bitmap[b >> 5], 1u << (b & 31u));
+                    }
+                    __syncthreads();
+                    constexpr int WPT = kPctWords / kFastThreads;
+                    uint32_t wv[WPT], pc = 0;
+#pragma unroll
+                    for (int q2 = 0; q2 < WPT; q2++) {
+                        const uint32_t w = (uint32_t)tid * WPT + q2;
+                        wv[q2] = w < words ? s_bitmap[w] : 0u;
+                        pc += __popc(wv[q2]);
+                    }
+                    const uint32_t inc = warp_incl_scan(pc);
+                    if (lane == 31) s_ws[warp] = inc;
+                    __syncthreads();
+                    uint32_t wbase = 0, D = 0;
+#pragma unroll
+                    for (int w2 = 0; w2 < kFastWarps; w2++) {
+                        const uint32_t t = s_ws[w2];
+                        if (w2 < warp) wbase += t;
+                        D += t;
+                    }
+                    const uint32_t astar = target_asc_rank(D, k, true, a.min_pct);
+                    uint32_t ex = wbase + inc - pc;
+                    if (astar > ex && astar <= ex + pc) {             // the a*-th distinct value lies in my words
+#pragma unroll
+                        for (int q2 = 0; q2 < WPT; q2++) {
+                            const uint32_t c = __popc(wv[q2]);
+                            if (astar > ex && astar <= ex + c) {
+                                uint32_t x = wv[q2];
+                                for (uint32_t i = ex + 1u; i < astar; i++) x &= x - 1u;   // drop the lower set bits
+                                s_thr = lo + (((uint32_t)tid * WPT + q2) << 5) + (uint32_t)(__ffs(x) - 1);
+                            }
+                            ex += c;
+                        }
+                    }
+                    __syncthreads();
+                    thr = s_thr;
+                    if (astar == 1u) keep_all = true;                 // every distinct value passes both rules
+                }
+            } else if (!keep_all) {
                 if (U16 && (hi - lo + 1u <= k)) {
                     keep_all = true;                                // at most k distinct values fit in [lo, hi]
                 } else if (U16 && k >= 8u) {
@@ -1247,11 +1325,81 @@ __global__ void __launch_bounds__(kFastThreads, 2048 / kFastThreads) tokenize_ce
             }
         }
 
+        uint32_t n_keep = n;
+        if constexpr (PCT) {
+            if (!defer && !keep_all) {
+                // Row-order compaction of the genes whose value passes the threshold, IN PLACE in the gene stage: a chunk of
+                // 8 rows per thread is read into registers, one block scan gives the offsets, the kept genes are written back
+                // at or before the positions they were read from (later chunks are untouched).  The emission below then reads
+                // a dense gene list exactly as in the keep-everything case.
+                const uint32_t staged = min(d.n_g, d.n_v);            // rows [s, s + staged) lie in both stages
+                const uint32_t ng_all = (sh + n + 7u) >> 3;
+                uint32_t base = 0;
+                for (uint32_t g0 = 0; g0 < ng_all && base < limit; g0 += kFastThreads) {
+                    const uint32_t gi = g0 + tid, r0 = a0 + gi * 8u;
+                    uint32_t flags = 0;
+                    GeneT g[8];
+                    if (gi < ng_all) {
+                        if (r0 >= s && r0 + 8u <= s + staged) {       // whole group staged: vector loads
+                            const uint4 qv = *reinterpret_cast<const uint4 *>(sv + gi * 8u);
+                            const uint32_t w4[4] = {qv.x, qv.y, qv.z, qv.w};
+                            if constexpr (sizeof(GeneT) == 2) {
+                                const uint4 qg = *reinterpret_cast<const uint4 *>(sg + gi * 8u);
+                                const uint32_t g4[4] = {qg.x, qg.y, qg.z, qg.w};
+#pragma unroll
+                                for (int i = 0; i < 8; i++) g[i] = (GeneT)((g4[i >> 1] >> ((i & 1) * 16)) & 0xffffu);
+                            } else {
+                                const uint4 qa = *reinterpret_cast<const uint4 *>(sg + gi * 8u), qb = *(reinterpret_cast<const uint4 *>(sg + gi * 8u) + 1);
+                                g[0] = (GeneT)qa.x; g[1] = (GeneT)qa.y; g[2] = (GeneT)qa.z; g[3] = (GeneT)qa.w;
+                                g[4] = (GeneT)qb.x; g[5] = (GeneT)qb.y; g[6] = (GeneT)qb.z; g[7] = (GeneT)qb.w;
+                            }
+#pragma unroll
+                            for (int i = 0; i < 8; i++)
+                                flags |= ((((w4[i >> 1] >> ((i & 1) * 16)) & 0xffffu) >= thr) ? 1u : 0u) << i;
+                        } else {                                       // ragged ends, rows beyond the stages
+#pragma unroll
+                            for (int i = 0; i < 8; i++) {
+                                const uint32_t r = r0 + i;
+                                g[i] = GeneT{};
+                                if (r >= s && r < e) {
+                                    const bool in = r < s + staged;
+                                    const uint32_t v = in ? (uint32_t)sv[r - a0] : (uint32_t)__ldg(value_g + r);
+                                    g[i] = in ? sg[r - a0] : __ldg(gene_g + r);
+                                    flags |= (v >= thr ? 1u : 0u) << i;
+                                }
+                            }
+                        }
+                    }
+                    const uint32_t pc = __popc(flags), inc = warp_incl_scan(pc);
+                    if (lane == 31) s_ws[warp] = inc;
+                    __syncthreads();                                   // all reads of this chunk are done as well
+                    uint32_t wbase = 0, tot = 0;
+#pragma unroll
+                    for (int w2 = 0; w2 < kFastWarps; w2++) {
+                        const uint32_t t = s_ws[w2];
+                        if (w2 < warp) wbase += t;
+                        tot += t;
+                    }
+                    uint32_t off = base + wbase + inc - pc;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        if (flags & (1u << i)) {
+                            if (off < limit) sg[sh + off] = g[i];
+                            off++;
+                        }
+                    }
+                    base += tot;
+                    __syncthreads();                                   // scratch and stage are consistent for the next chunk / the emission
+                }
+                n_keep = base;
+            }
+        }
+
         if (defer) {
             if (tid == 0) a.work_list[atomicAdd(a.work_counters, 1u)] = j;   // exact k-th distinct value: general kernel
         } else {
             // ---- emission: token pairs (128-bit stores), value stream, PAD fill, mask, cell id
-            const uint32_t n_emit = min(n, limit);
+            const uint32_t n_emit = min(n_keep, limit);
             const size_t A = (size_t)j * L;
             double m_f64 = 0.0;
             uint32_t vstar = 0xffffffffu;
@@ -1270,7 +1418,20 @@ __global__ void __launch_bounds__(kFastThreads, 2048 / kFastThreads) tokenize_ce
                     };
                     const uint32_t kzero = key_of(0.0f);
                     uint32_t xs = 0xffffffffu;                       // no value reaches bin 1
-                    if (a.w_bins >= 2 && kmax >= kzero && pred(kmax)) xs = warp_lower_bound(kzero, kmax, pred);
+                    if (a.w_bins >= 2 && kmax > kzero && pred(kmax)) {
+                        // bin(x) >= 1  <=>  log1pf(x) * n / m >= 1, so the threshold sits within a few ulps of expm1(m / n):
+                        // the 32 lanes test the 32 floats around that guess in ONE round; the exact predicate decides, the
+                        // full 32-ary search only runs when the boundary is not inside the window.
+                        const float x0 = (float)expm1((double)m_f32 / (double)wb);
+                        uint32_t k0 = key_of(x0);
+                        k0 = min(max(k0, kzero + 1u), kmax);
+                        const uint32_t wlo = (k0 - kzero > 16u) ? k0 - 16u : kzero + 1u;
+                        const uint32_t c = min(wlo + (uint32_t)lane, kmax);
+                        const uint32_t hit = __ballot_sync(0xffffffffu, pred(c));
+                        if (hit == 0u) xs = warp_lower_bound(wlo + 32u, kmax, pred);             // boundary above the window
+                        else if ((hit & 1u) && wlo > kzero + 1u) xs = warp_lower_bound(kzero + 1u, wlo, pred);   // at or below its first float
+                        else xs = min(wlo + (uint32_t)(__ffs(hit) - 1), kmax);
+                    }
                     if (lane == 0) s_xstar = xs;
                 }
             }

@@ -55,6 +55,7 @@ struct Slot {
     uint32_t *h_counters = nullptr; // [0] n_cells, [1] err, [2] cells deferred to the general kernel (mapped pinned: kernels write it)
     uint32_t *h_counters_dev = nullptr;  // device-side address of h_counters
     bool all_general = false;
+    bool host_segs = false;            // the segment table came from the host (submit_segments / submit_csi): the cell count is known without the GPU
     // permutation prepared ahead of collect() by the helper thread (slafb_prepare_shuffle)
     std::atomic<int> prep_state{0};   // 0 none, 1 queued / running, 2 ready
     int64_t prep_seed = 0;
@@ -119,7 +120,23 @@ struct slafb_ctx {
     int timing_every = 1;
     uint64_t batch_seq = 0;
     bool front_on_caller = false;
+    cudaEvent_t ev_k1 = nullptr;       // end of the latest CSR build: K1 launches share the context's span ticket / tile states, so a K1
+    cudaStream_t k1_stream = nullptr;  // on another stream than the previous one (SLAFB_OPT_FRONT_ON_CALLER) waits for it first
+    bool k1_any = false;
     int64_t recent_slow = 1 << 20;    // decayed maximum of the cells recently deferred to the general kernel (starts pessimistic)
+};
+
+// A steady pipeline over one context: batches go in (submit + shuffle preparation), the oldest batch in flight comes out into
+// the next entry of a ring of caller-owned output tensors.  One call per step; nothing is allocated per step.
+struct slafb_pipe {
+    slafb_ctx *ctx = nullptr;
+    slafb_params p{};
+    std::vector<slafb_out> ring;
+    int depth = 1;
+    struct Item { int32_t slot; int64_t seed; int64_t seq; };
+    std::deque<Item> q;
+    int64_t next_seq = 0;
+    int32_t next_ring = 0;
 };
 
 namespace {
@@ -239,15 +256,16 @@ int launch_fast(slafb_ctx *ctx, const TokArgs &a, cudaStream_t st, bool *launche
         if (v >= 256 && v <= 16384) vmin = (uint32_t)(v + 7) & ~7u;
     }
     fa.vcap = fa.gcap > vmin ? fa.gcap : vmin;
+    if (MODE == MODE_GF_PCT) fa.gcap = fa.vcap;          // percentile mode: any row may survive the filter, so every row's gene is staged too
     fa.vstar_table = ctx->vstar_table;
     fa.ticket = a.work_counters + 2;   // slot counters[4], zeroed by K1 together with the work-list counters
     const size_t smem = 2 * ((size_t)fa.gcap * sizeof(GeneT) + (size_t)fa.vcap * sizeof(ValT)) + (sizeof(ValT) == 4 ? (size_t)kHashSlots * 4 : 0);
     if (smem > 200 * 1024) return SLAFB_OK;   // very wide rows: general kernel only
     auto kern = tokenize_cells_kernel<GeneT, ValT, MODE>;
-    static bool attr_set[64] = {false};
-    if (!attr_set[ctx->device & 63]) {
+    static std::atomic<bool> attr_set[64];   // zero-initialised; setting the attribute twice is harmless
+    if (!attr_set[ctx->device & 63].load(std::memory_order_acquire)) {
         CU(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set[ctx->device & 63] = true;
+        attr_set[ctx->device & 63].store(true, std::memory_order_release);
     }
     if (MODE == MODE_SCGPT_BINNED && sizeof(ValT) == 2 && ctx->vstar_nbins != a.w_bins) {
         vstar_table_kernel<<<256, 256, 0, st>>>(ctx->log1p_lut, a.w_bins, ctx->vstar_table);
@@ -276,10 +294,10 @@ template <typename GeneT, typename ValT, int MODE, int SINK>
 int launch_general(slafb_ctx *ctx, const TokArgs &a, const WindowSink &w, cudaStream_t st) {
     auto kern = tokenize_general_kernel<GeneT, ValT, MODE, SINK>;
     const size_t dyn = (sizeof(ValT) == 2) ? (size_t)kBitmapWords * 4 : (size_t)kSortSmemKeys * 4;
-    static bool attr_set[64] = {false};  // per instantiation, per device
-    if (!attr_set[ctx->device & 63]) {
+    static std::atomic<bool> attr_set[64];  // per instantiation, per device (zero-initialised; setting the attribute twice is harmless)
+    if (!attr_set[ctx->device & 63].load(std::memory_order_acquire)) {
         CU(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-        attr_set[ctx->device & 63] = true;
+        attr_set[ctx->device & 63].store(true, std::memory_order_release);
     }
     // persistent CTAs over a ticket: as many per SM as shared memory allows (static TokSmem ~17 KB + bitmap / sort keys)
     size_t per_sm = (220 * 1024) / (dyn + 18 * 1024);
@@ -301,10 +319,10 @@ template <typename GeneT, typename ValT>
 int launch_rank(slafb_ctx *ctx, const RankArgs &ra, cudaStream_t st) {
     auto kern = tokenize_rank_kernel<GeneT, ValT>;
     const size_t dyn = (size_t)kRankSmemKeys * sizeof(unsigned long long);
-    static bool attr_set[64] = {false};
-    if (!attr_set[ctx->device & 63]) {
+    static std::atomic<bool> attr_set[64];   // zero-initialised; setting the attribute twice is harmless
+    if (!attr_set[ctx->device & 63].load(std::memory_order_acquire)) {
         CU(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-        attr_set[ctx->device & 63] = true;
+        attr_set[ctx->device & 63].store(true, std::memory_order_release);
     }
     uint32_t grid = (uint32_t)ctx->n_sm * 3u;       // 64 KiB of keys per CTA: three CTAs per SM
     if (ra.t.n_cells < grid) grid = ra.t.n_cells;
@@ -320,7 +338,11 @@ int dispatch_fast(slafb_ctx *ctx, int mode, const TokArgs &a, cudaStream_t st, b
     case MODE_GF: return launch_fast<GeneT, ValT, MODE_GF>(ctx, a, st, launched);
     case MODE_SCGPT_RAW: return launch_fast<GeneT, ValT, MODE_SCGPT_RAW>(ctx, a, st, launched);
     case MODE_SCGPT_BINNED: return launch_fast<GeneT, ValT, MODE_SCGPT_BINNED>(ctx, a, st, launched);
-    default: *launched = false; return SLAFB_OK;  // percentile mode has no fast kernel
+    case MODE_GF_PCT:
+        // uint16 values: presence bitmap in shared memory; float32 values need a sort per cell (general kernel)
+        if constexpr (sizeof(ValT) == 2) return launch_fast<GeneT, ValT, MODE_GF_PCT>(ctx, a, st, launched);
+        else { *launched = false; return SLAFB_OK; }
+    default: *launched = false; return SLAFB_OK;
     }
 }
 template <typename GeneT, typename ValT, int SINK>
@@ -467,8 +489,9 @@ int front(slafb_ctx *ctx, Slot &s, const slafb_coo *pieces, int n_pieces, cudaSt
         CU(ctx, cudaEventSynchronize(s.ev_done));
         harvest(ctx, s);
     }
-    s.sample = (ctx->timing_every <= 1) || (ctx->batch_seq % (uint64_t)ctx->timing_every == 0);
+    s.sample = ctx->timing_every > 0 && ((ctx->timing_every == 1) || (ctx->batch_seq % (uint64_t)ctx->timing_every == 0));
     ctx->batch_seq++;
+    s.host_segs = false;
     s.n_rows = total;
     s.cell_dtype = in->cell_dtype;
     s.gene_dtype = in->gene_dtype;
@@ -536,11 +559,19 @@ int front(slafb_ctx *ctx, Slot &s, const slafb_coo *pieces, int n_pieces, cudaSt
     if (tiles < grid) grid = (uint32_t)tiles;
     k.rows_per_cta = (uint32_t)(((tiles + grid - 1) / grid) * kCsrStageRows);
     grid = (uint32_t)(((uint64_t)total + k.rows_per_cta - 1) / k.rows_per_cta);   // no empty spans
+    // every CSR build of this context draws spans from one ticket and publishes into one tile-state array: two of them must
+    // never run at once.  On one stream they are ordered anyway; when the stream changes, wait for the previous build.
+    if (ctx->k1_any && ctx->k1_stream != sf) CU(ctx, cudaStreamWaitEvent(sf, ctx->ev_k1, 0));
     if (s.sample) CU(ctx, cudaEventRecord(s.t_k1a, sf));
     if (use_ldg) csr_build_ldg_kernel<<<grid, kCsrLdgBlock, 0, sf>>>(k);
     else csr_build_kernel<<<grid, kCsrBlock, 0, sf>>>(k);
     CU(ctx, cudaGetLastError());
     if (s.sample) { CU(ctx, cudaEventRecord(s.t_k1b, sf)); s.timed_front = true; }
+    if (ctx->front_on_caller || ctx->k1_stream != sf) {          // (the default configuration keeps every build on s_in: no event needed)
+        CU(ctx, cudaEventRecord(ctx->ev_k1, sf));
+        ctx->k1_stream = sf;
+        ctx->k1_any = true;
+    }
     ctx->ticket_base += grid;
     ctx->acc.kernel_launches++;
     CU(ctx, cudaEventRecord(s.ev_front, sf));
@@ -581,8 +612,8 @@ void shuffle_worker(slafb_ctx *ctx) {
         s.perm_uploaded = false;
         // wait for the cell count without occupying a core: the helpers have most of a pipeline depth of slack, and on an
         // 8-GPU host (4 vCPUs per rank on this pool) a spinning cudaEventSynchronize per helper competes with the feeder threads
-        cudaError_t ready;
-        while ((ready = cudaEventQuery(s.ev_front)) == cudaErrorNotReady) {
+        cudaError_t ready = cudaSuccess;
+        while (!s.host_segs && (ready = cudaEventQuery(s.ev_front)) == cudaErrorNotReady) {   // host-supplied segments: the count is already there
             cudaGetLastError();
             std::this_thread::sleep_for(std::chrono::microseconds(20));
         }
@@ -614,9 +645,11 @@ void settle_prepared(slafb_ctx *ctx, Slot &s) {
 
 // waits for the cell count; builds + uploads the permutation.  Returns n_cells through *n.
 int middle(slafb_ctx *ctx, Slot &s, const slafb_params *p, int64_t *n, cudaStream_t st, bool *use_perm) {
-    const double tw0 = now_ms();
-    CU(ctx, cudaEventSynchronize(s.ev_front));
-    ctx->acc.host_wait_ms += now_ms() - tw0;
+    if (!s.host_segs) {               // (a host-supplied segment table: the count is known, nothing to wait for)
+        const double tw0 = now_ms();
+        CU(ctx, cudaEventSynchronize(s.ev_front));
+        ctx->acc.host_wait_ms += now_ms() - tw0;
+    }
     if (s.h_counters[1]) {
         *n = s.h_counters[0];
         return fail(ctx, SLAFB_ERR_CAPACITY, "batch has %u cells, context max_cells is %lld", s.h_counters[0], (long long)ctx->max_cells);
@@ -740,10 +773,8 @@ int back(slafb_ctx *ctx, Slot &s, const slafb_params *p, const slafb_out *out, i
     }
     if (s.sample) CU(ctx, cudaEventRecord(s.t_k2a, st));
     bool fast_launched = false;
-    if (p->mode != SLAFB_GENEFORMER_PCT) {
-        DISPATCH_TYPES(s.gene_dtype, s.value_dtype, rc = (dispatch_fast<GeneT, ValT>(ctx, p->mode, a, st, &fast_launched)));
-        if (rc) return rc;
-    }
+    DISPATCH_TYPES(s.gene_dtype, s.value_dtype, rc = (dispatch_fast<GeneT, ValT>(ctx, p->mode, a, st, &fast_launched)));
+    if (rc) return rc;
     if (!fast_launched) a.all_cells = 1;
     if (s.sample) CU(ctx, cudaEventRecord(s.t_k2b, st));
     DISPATCH_TYPES(s.gene_dtype, s.value_dtype, rc = (dispatch_general<GeneT, ValT, 0>(ctx, p->mode, a, none, st)));
@@ -756,6 +787,106 @@ int back(slafb_ctx *ctx, Slot &s, const slafb_params *p, const slafb_out *out, i
     ctx->acc.batches++;
     ctx->acc.cells += C;
     ctx->acc.rows += s.n_rows;
+    return SLAFB_OK;
+}
+
+// submit() when the segment table is known on the host: validates the pieces, takes a slot and leaves the table's pinned
+// block (s.h_seg: [C + 1] starts, then [C] ids) to be filled by `fill`, then enqueues table + gene / value columns.
+template <typename Fill>
+int submit_host_segments(slafb_ctx *ctx, const slafb_coo *pieces, int32_t n_pieces, int64_t n_cells_max, void *stream, int32_t *slot,
+                         int64_t *n_cells_out, Fill fill) {
+    if (!ctx || !slot || !pieces || n_pieces < 1) return fail(ctx, SLAFB_ERR_INVALID, "bad ctx / slot / pieces");
+    CU(ctx, cudaSetDevice(ctx->device));
+    const int si = pick_slot(ctx);
+    if (si < 0) return fail(ctx, SLAFB_ERR_BUSY, "all %d pipeline slots hold batches that were not collected yet", kSlots);
+    Slot &s = ctx->slot[si];
+    const double t0 = now_ms();
+    int64_t total = 0;
+    for (int i = 0; i < n_pieces; i++) {
+        const slafb_coo &p = pieces[i];
+        if (p.n_rows < 0 || (p.n_rows > 0 && (!p.gene || !p.value))) return fail(ctx, SLAFB_ERR_INVALID, "NULL gene / value column");
+        if (p.gene_dtype != pieces[0].gene_dtype || p.value_dtype != pieces[0].value_dtype || p.location != pieces[0].location ||
+            p.cell_dtype != pieces[0].cell_dtype)
+            return fail(ctx, SLAFB_ERR_INVALID, "all pieces of a batch must share column dtypes and location");
+        total += p.n_rows;
+    }
+    const slafb_coo *in = &pieces[0];
+    if (in->gene_dtype != SLAFB_U16 && in->gene_dtype != SLAFB_I32 && in->gene_dtype != SLAFB_U32) return fail(ctx, SLAFB_ERR_INVALID, "gene dtype must be uint16, int32 or uint32");
+    if (in->value_dtype != SLAFB_U16 && in->value_dtype != SLAFB_F32) return fail(ctx, SLAFB_ERR_INVALID, "value dtype must be uint16 or float32");
+    if (in->cell_dtype != SLAFB_U32 && in->cell_dtype != SLAFB_I32) return fail(ctx, SLAFB_ERR_INVALID, "cell dtype must be uint32 or int32");
+    if (total > ctx->max_rows) return fail(ctx, SLAFB_ERR_CAPACITY, "n_rows %lld exceeds context max_rows %lld", (long long)total, (long long)ctx->max_rows);
+    if (n_cells_max < 0 || n_cells_max > ctx->max_cells) return fail(ctx, SLAFB_ERR_CAPACITY, "n_cells %lld exceeds context max_cells %lld", (long long)n_cells_max, (long long)ctx->max_cells);
+    if (s.ev_done) {
+        CU(ctx, cudaEventSynchronize(s.ev_done));      // the slot's tables (and h_seg) may still be in use by its previous batch
+        harvest(ctx, s);
+    }
+    int64_t n_cells = 0;
+    int rc = fill(s.h_seg, s.h_seg + (size_t)ctx->max_cells + 1, total, &n_cells);    // starts, ids
+    if (rc) return rc;
+    // the table must describe the rows: non-decreasing offsets from 0 to the row count (an out-of-range entry would send the
+    // tokenizing kernel's bulk copies out of bounds)
+    if (n_cells > 0) {
+        const uint32_t *st = s.h_seg;
+        if (st[0] != 0 || (int64_t)st[n_cells] != total) return fail(ctx, SLAFB_ERR_INVALID, "segment table does not cover the rows");
+        uint32_t bad = 0;
+        for (int64_t i = 0; i < n_cells; i++) bad |= (st[i] > st[i + 1]) ? 1u : 0u;
+        if (bad) return fail(ctx, SLAFB_ERR_INVALID, "segment table offsets are not monotone");
+    } else if (total != 0) {
+        return fail(ctx, SLAFB_ERR_INVALID, "rows without a segment table");
+    }
+    cudaStream_t sf = ctx->s_in;
+    s.sample = ctx->timing_every > 0 && ((ctx->timing_every == 1) || (ctx->batch_seq % (uint64_t)ctx->timing_every == 0));
+    ctx->batch_seq++;
+    s.host_segs = true;
+    s.n_rows = total;
+    s.cell_dtype = in->cell_dtype;
+    s.gene_dtype = in->gene_dtype;
+    s.value_dtype = in->value_dtype;
+    s.h_counters[0] = (uint32_t)n_cells;
+    s.h_counters[1] = 0;
+    CU(ctx, cudaEventRecord(s.ev_in, static_cast<cudaStream_t>(stream)));
+    CU(ctx, cudaStreamWaitEvent(sf, s.ev_in, 0));
+    // the segment table comes from the host (8 bytes per cell): no cell column crosses the bus and no CSR build runs
+    CU(ctx, cudaMemsetAsync(s.counters, 0, 8 * sizeof(uint32_t), sf));
+    if (n_cells > 0) {
+        CU(ctx, cudaMemcpyAsync(s.seg_start, s.h_seg, (size_t)(n_cells + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, sf));
+        CU(ctx, cudaMemcpyAsync(s.seg_cell, s.h_seg + (size_t)ctx->max_cells + 1, (size_t)n_cells * sizeof(uint32_t), cudaMemcpyHostToDevice, sf));
+    }
+    CU(ctx, cudaEventRecord(s.ev_front, sf));
+    if (total > 0) {
+        if (in->location == SLAFB_LOC_HOST || n_pieces > 1) {
+            rc = ensure_staging(ctx, s);
+            if (rc) return rc;
+            std::vector<PieceSrc> src;
+            rc = stage_small_pieces(ctx, s, pieces, n_pieces, false, src);
+            if (rc) return rc;
+            const cudaMemcpyKind kind = in->location == SLAFB_LOC_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+            const size_t gsz = dtype_size(in->gene_dtype), vsz = dtype_size(in->value_dtype);
+            if (s.sample) CU(ctx, cudaEventRecord(s.t_h2d0, sf));
+            size_t off = 0;
+            for (int i = 0; i < n_pieces; i++) {
+                const size_t n = (size_t)pieces[i].n_rows;
+                if (n) CU(ctx, cudaMemcpyAsync(static_cast<char *>(s.in_gene) + off * gsz, src[i].col[1], n * gsz, kind, sf));
+                off += n;
+            }
+            off = 0;
+            for (int i = 0; i < n_pieces; i++) {
+                const size_t n = (size_t)pieces[i].n_rows;
+                if (n) CU(ctx, cudaMemcpyAsync(static_cast<char *>(s.in_value) + off * vsz, src[i].col[2], n * vsz, kind, sf));
+                off += n;
+            }
+            if (s.sample) { CU(ctx, cudaEventRecord(s.t_h2d1, sf)); s.timed_h2d = true; }
+            s.cell = nullptr; s.gene = s.in_gene; s.value = s.in_value;
+        } else {
+            if (((uintptr_t)in->gene | (uintptr_t)in->value) & 15u) return fail(ctx, SLAFB_ERR_INVALID, "device column pointers must be 16-byte aligned");
+            s.cell = nullptr; s.gene = in->gene; s.value = in->value;
+        }
+    }
+    CU(ctx, cudaEventRecord(s.ev_loaded, sf));
+    ctx->acc.host_submit_ms += now_ms() - t0;
+    s.in_flight = true;
+    *slot = si;
+    if (n_cells_out) *n_cells_out = n_cells;
     return SLAFB_OK;
 }
 
@@ -823,6 +954,7 @@ int slafb_create(slafb_ctx **out, int device, int64_t max_rows, int64_t max_cell
     CUC(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
     CUC(cudaStreamCreateWithFlags(&ctx->s_aux, cudaStreamNonBlocking));
     CUC(cudaStreamCreateWithFlags(&ctx->s_perm, cudaStreamNonBlocking));
+    CUC(cudaEventCreateWithFlags(&ctx->ev_k1, cudaEventDisableTiming));
     const size_t n_tiles_max = (size_t)ctx->n_sm * 8;
     CUC(cudaMalloc(&ctx->tile_state, n_tiles_max * sizeof(unsigned long long)));
     CUC(cudaMemset(ctx->tile_state, 0, n_tiles_max * sizeof(unsigned long long)));
@@ -898,6 +1030,7 @@ int slafb_destroy(slafb_ctx *ctx) {
     cudaFree(ctx->tile_state); cudaFree(ctx->ticket); cudaFree(ctx->log1p_lut); cudaFree(ctx->vstar_table); cudaFree(ctx->sort_scratch); cudaFree(ctx->rank_scratch); cudaFree(ctx->dup_table);
     cudaFree(ctx->kept_count); cudaFree(ctx->total_dev);
     if (ctx->h_total) cudaFreeHost(ctx->h_total);
+    if (ctx->ev_k1) cudaEventDestroy(ctx->ev_k1);
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
     if (ctx->s_aux) cudaStreamDestroy(ctx->s_aux);
     if (ctx->s_perm) cudaStreamDestroy(ctx->s_perm);
@@ -922,86 +1055,82 @@ int slafb_submit_pieces(slafb_ctx *ctx, const slafb_coo *pieces, int32_t n_piece
 
 int slafb_submit_segments(slafb_ctx *ctx, const slafb_coo *pieces, int32_t n_pieces, const uint32_t *seg_start, const uint32_t *seg_cell,
                           int64_t n_cells, void *stream, int32_t *slot) {
-    if (!ctx || !slot || !pieces || n_pieces < 1) return fail(ctx, SLAFB_ERR_INVALID, "bad ctx / slot / pieces");
-    CU(ctx, cudaSetDevice(ctx->device));
-    const int si = pick_slot(ctx);
-    if (si < 0) return fail(ctx, SLAFB_ERR_BUSY, "all %d pipeline slots hold batches that were not collected yet", kSlots);
-    Slot &s = ctx->slot[si];
-    const double t0 = now_ms();
-    int64_t total = 0;
-    for (int i = 0; i < n_pieces; i++) {
-        const slafb_coo &p = pieces[i];
-        if (p.n_rows < 0 || (p.n_rows > 0 && (!p.gene || !p.value))) return fail(ctx, SLAFB_ERR_INVALID, "NULL gene / value column");
-        if (p.gene_dtype != pieces[0].gene_dtype || p.value_dtype != pieces[0].value_dtype || p.location != pieces[0].location)
-            return fail(ctx, SLAFB_ERR_INVALID, "all pieces of a batch must share column dtypes and location");
-        total += p.n_rows;
-    }
-    const slafb_coo *in = &pieces[0];
-    if (in->gene_dtype != SLAFB_U16 && in->gene_dtype != SLAFB_I32 && in->gene_dtype != SLAFB_U32) return fail(ctx, SLAFB_ERR_INVALID, "gene dtype must be uint16, int32 or uint32");
-    if (in->value_dtype != SLAFB_U16 && in->value_dtype != SLAFB_F32) return fail(ctx, SLAFB_ERR_INVALID, "value dtype must be uint16 or float32");
-    if (in->cell_dtype != SLAFB_U32 && in->cell_dtype != SLAFB_I32) return fail(ctx, SLAFB_ERR_INVALID, "cell dtype must be uint32 or int32");
-    if (total > ctx->max_rows) return fail(ctx, SLAFB_ERR_CAPACITY, "n_rows %lld exceeds context max_rows %lld", (long long)total, (long long)ctx->max_rows);
-    if (n_cells < 0 || n_cells > ctx->max_cells) return fail(ctx, SLAFB_ERR_CAPACITY, "n_cells %lld exceeds context max_cells %lld", (long long)n_cells, (long long)ctx->max_cells);
     if (n_cells > 0 && (!seg_start || !seg_cell)) return fail(ctx, SLAFB_ERR_INVALID, "NULL segment table");
-    if (n_cells > 0 && (seg_start[0] != 0 || (int64_t)seg_start[n_cells] != total)) return fail(ctx, SLAFB_ERR_INVALID, "segment table does not cover the rows");
-    if (s.ev_done) {
-        CU(ctx, cudaEventSynchronize(s.ev_done));
-        harvest(ctx, s);
-    }
-    cudaStream_t sf = ctx->s_in;
-    s.sample = (ctx->timing_every <= 1) || (ctx->batch_seq % (uint64_t)ctx->timing_every == 0);
-    ctx->batch_seq++;
-    s.n_rows = total;
-    s.cell_dtype = in->cell_dtype;
-    s.gene_dtype = in->gene_dtype;
-    s.value_dtype = in->value_dtype;
-    s.h_counters[0] = (uint32_t)n_cells;
-    s.h_counters[1] = 0;
-    CU(ctx, cudaEventRecord(s.ev_in, static_cast<cudaStream_t>(stream)));
-    CU(ctx, cudaStreamWaitEvent(sf, s.ev_in, 0));
-    // the segment table comes from the host (8 bytes per cell): no cell column crosses the bus and no CSR build runs
-    CU(ctx, cudaMemsetAsync(s.counters, 0, 8 * sizeof(uint32_t), sf));
-    if (n_cells > 0) {
-        // through the slot's own pinned block: the caller's arrays may be pageable (a pageable async copy stalls the
-        // copy stream behind the driver's staging) and need not outlive this call
-        memcpy(s.h_seg, seg_start, (size_t)(n_cells + 1) * sizeof(uint32_t));
-        memcpy(s.h_seg + n_cells + 1, seg_cell, (size_t)n_cells * sizeof(uint32_t));
-        CU(ctx, cudaMemcpyAsync(s.seg_start, s.h_seg, (size_t)(n_cells + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, sf));
-        CU(ctx, cudaMemcpyAsync(s.seg_cell, s.h_seg + n_cells + 1, (size_t)n_cells * sizeof(uint32_t), cudaMemcpyHostToDevice, sf));
-    }
-    CU(ctx, cudaEventRecord(s.ev_front, sf));
-    if (total > 0) {
-        if (in->location == SLAFB_LOC_HOST || n_pieces > 1) {
-            int rc = ensure_staging(ctx, s);
-            if (rc) return rc;
-            std::vector<PieceSrc> src;
-            rc = stage_small_pieces(ctx, s, pieces, n_pieces, false, src);
-            if (rc) return rc;
-            const cudaMemcpyKind kind = in->location == SLAFB_LOC_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
-            const size_t gsz = dtype_size(in->gene_dtype), vsz = dtype_size(in->value_dtype);
-            if (s.sample) CU(ctx, cudaEventRecord(s.t_h2d0, sf));
-            size_t off = 0;
-            for (int i = 0; i < n_pieces; i++) {
-                const size_t n = (size_t)pieces[i].n_rows;
-                if (n) CU(ctx, cudaMemcpyAsync(static_cast<char *>(s.in_gene) + off * gsz, src[i].col[1], n * gsz, kind, sf));
-                off += n;
+    // through the slot's own pinned block: the caller's arrays may be pageable (a pageable async copy stalls the copy stream
+    // behind the driver's staging) and need not outlive this call
+    return submit_host_segments(ctx, pieces, n_pieces, n_cells, stream, slot, nullptr,
+                                [&](uint32_t *st, uint32_t *id, int64_t, int64_t *n_out) -> int {
+                                    if (n_cells > 0) {
+                                        memcpy(st, seg_start, (size_t)(n_cells + 1) * sizeof(uint32_t));
+                                        memcpy(id, seg_cell, (size_t)n_cells * sizeof(uint32_t));
+                                    }
+                                    *n_out = n_cells;
+                                    return SLAFB_OK;
+                                });
+}
+
+int slafb_csi_segments(const slafb_coo *pieces, int32_t n_pieces, const int64_t *row_lo, const int64_t *csi, int64_t n_csi, int32_t check,
+                       uint32_t *seg_start, uint32_t *seg_cell, int64_t capacity_cells, int64_t *n_cells) {
+    // Host only (no CUDA call).  Segment table of the concatenated pieces from the index alone: piece i covers table rows
+    // [row_lo[i], row_lo[i] + n_i); cell c owns rows [csi[c], csi[c + 1]).  Adjacent pieces that continue one cell give one
+    // segment; cells without rows give none.
+    if (!pieces || n_pieces < 1 || !row_lo || !csi || n_csi < 1 || !seg_start || !seg_cell || !n_cells)
+        return fail(nullptr, SLAFB_ERR_INVALID, "bad pieces / index / table pointers");
+    const int64_t n_total = n_csi - 1;                 // cells in the table
+    uint32_t *st = seg_start, *id = seg_cell;
+    int64_t C = 0, pos = 0;
+    for (int i = 0; i < n_pieces; i++) {
+        const int64_t n = pieces[i].n_rows;
+        if (n < 0) return fail(nullptr, SLAFB_ERR_INVALID, "n_rows < 0");
+        if (n == 0) continue;
+        const int64_t lo = row_lo[i], hi = lo + n;
+        if (lo < csi[0] || hi > csi[n_total]) return fail(nullptr, SLAFB_ERR_INVALID, "piece %d covers table rows [%lld, %lld) outside the cell start index", i, (long long)lo, (long long)hi);
+        if (pos + n > 0xffffffffll) return fail(nullptr, SLAFB_ERR_CAPACITY, "more than 2^32 rows in one batch");
+        int64_t a = 0, b = n_total;                    // largest c with csi[c] <= lo
+        while (b - a > 1) { const int64_t m = (a + b) >> 1; if (csi[m] <= lo) a = m; else b = m; }
+        const uint32_t *cells = (check && pieces[i].location == SLAFB_LOC_HOST) ? static_cast<const uint32_t *>(pieces[i].cell) : nullptr;
+        for (int64_t c = a; c < n_total && csi[c] < hi; c++) {
+            const int64_t first = csi[c] > lo ? csi[c] : lo;
+            if (csi[c + 1] <= first) continue;         // no rows (here)
+            const int64_t start = first - lo + pos;
+            if (C > 0 && (int64_t)id[C - 1] == c && start == pos) continue;      // the previous piece's last cell continues: one segment
+            if (C >= capacity_cells) return fail(nullptr, SLAFB_ERR_CAPACITY, "batch has more than %lld cells (table capacity)", (long long)capacity_cells);
+            if (c > 0xffffffffll) return fail(nullptr, SLAFB_ERR_INVALID, "cell id does not fit 32 bits");
+            st[C] = (uint32_t)start;
+            id[C] = (uint32_t)c;
+            // consistency probe against the rows themselves (every segment with check = 2, every 16th with check = 1):
+            // the cell column must show exactly that id starting exactly there, or the index is stale / shifted
+            if (cells && (check >= 2 || (C & 15) == 0)) {
+                const int64_t r = first - lo;
+                if (cells[r] != (uint32_t)c || (r > 0 && cells[r - 1] == (uint32_t)c))
+                    return fail(nullptr, SLAFB_ERR_INVALID, "cell_start_index does not describe the expression rows (cell %lld does not start at table row %lld)", (long long)c, (long long)first);
             }
-            off = 0;
-            for (int i = 0; i < n_pieces; i++) {
-                const size_t n = (size_t)pieces[i].n_rows;
-                if (n) CU(ctx, cudaMemcpyAsync(static_cast<char *>(s.in_value) + off * vsz, src[i].col[2], n * vsz, kind, sf));
-                off += n;
-            }
-            if (s.sample) { CU(ctx, cudaEventRecord(s.t_h2d1, sf)); s.timed_h2d = true; }
-            s.cell = nullptr; s.gene = s.in_gene; s.value = s.in_value;
-        } else {
-            s.cell = nullptr; s.gene = in->gene; s.value = in->value;
+            C++;
         }
+        if (cells && (C == 0 || cells[n - 1] != id[C - 1]))
+            return fail(nullptr, SLAFB_ERR_INVALID, "cell_start_index does not describe the expression rows (last cell of piece %d differs)", i);
+        pos += n;
     }
-    CU(ctx, cudaEventRecord(s.ev_loaded, sf));
-    ctx->acc.host_submit_ms += now_ms() - t0;
-    s.in_flight = true;
-    *slot = si;
+    st[C] = (uint32_t)pos;
+    *n_cells = C;
+    return SLAFB_OK;
+}
+
+int slafb_submit_csi(slafb_ctx *ctx, const slafb_coo *pieces, int32_t n_pieces, const int64_t *row_lo, const int64_t *csi, int64_t n_csi,
+                     int32_t check, void *stream, int32_t *slot, int64_t *n_cells) {
+    if (!ctx) return fail(ctx, SLAFB_ERR_INVALID, "ctx is NULL");
+    return submit_host_segments(ctx, pieces, n_pieces, 0, stream, slot, n_cells,
+                                [&](uint32_t *st, uint32_t *id, int64_t, int64_t *n_out) -> int {
+                                    const int rc = slafb_csi_segments(pieces, n_pieces, row_lo, csi, n_csi, check, st, id, ctx->max_cells, n_out);
+                                    if (rc) snprintf(ctx->err, sizeof ctx->err, "%s", g_err);
+                                    return rc;
+                                });
+}
+
+int slafb_wait_loaded(slafb_ctx *ctx, int32_t slot) {
+    if (!ctx || slot < 0 || slot >= kSlots) return fail(ctx, SLAFB_ERR_INVALID, "bad ctx / slot");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaEventSynchronize(ctx->slot[slot].ev_loaded));
     return SLAFB_OK;
 }
 
@@ -1050,20 +1179,111 @@ int slafb_collect(slafb_ctx *ctx, int32_t slot, const slafb_params *p, const sla
     return rc;
 }
 
+int slafb_pipe_create(slafb_ctx *ctx, const slafb_params *p, const slafb_out *ring, int32_t n_ring, int32_t depth, slafb_pipe **pipe) {
+    if (!ctx || !p || !ring || !pipe) return fail(ctx, SLAFB_ERR_INVALID, "NULL argument");
+    *pipe = nullptr;
+    if (n_ring < 1 || n_ring > 1024) return fail(ctx, SLAFB_ERR_INVALID, "the output ring needs 1..1024 entries");
+    if (depth < 0 || depth > kSlots - 1) return fail(ctx, SLAFB_ERR_INVALID, "depth must be in [0, %d]", kSlots - 1);
+    if (p->shuffle == SLAFB_SHUFFLE_PERM) return fail(ctx, SLAFB_ERR_INVALID, "a pipe shuffles by seed (or not at all)");
+    int rc = check_params(ctx, p);
+    if (rc) return rc;
+    slafb_pipe *pp = new (std::nothrow) slafb_pipe();
+    if (!pp) return fail(ctx, SLAFB_ERR_INVALID, "out of host memory");
+    pp->ctx = ctx;
+    pp->p = *p;
+    pp->ring.assign(ring, ring + n_ring);
+    pp->depth = depth;
+    *pipe = pp;
+    return SLAFB_OK;
+}
+
+static int pipe_pop(slafb_pipe *pipe, void *stream, slafb_pipe_result *done) {
+    slafb_ctx *ctx = pipe->ctx;
+    const slafb_pipe::Item it = pipe->q.front();
+    pipe->q.pop_front();
+    slafb_params p = pipe->p;
+    p.seed = it.seed;
+    const int32_t ri = pipe->next_ring;
+    int64_t n = 0;
+    int rc = slafb_collect(ctx, it.slot, &p, &pipe->ring[ri], &n, stream);
+    if (rc == SLAFB_ERR_CAPACITY && ctx->slot[it.slot].in_flight) {
+        // the ring's tensors are too small for this batch; the pipe cannot grow them: drop the batch so the slot is not leaked
+        char keep[sizeof ctx->err];
+        memcpy(keep, ctx->err, sizeof keep);
+        slafb_params e = pipe->p;
+        e.shuffle = SLAFB_SHUFFLE_PERM; e.perm = nullptr; e.n_perm = 0;
+        slafb_out none{};
+        int64_t z = 0;
+        slafb_collect(ctx, it.slot, &e, &none, &z, stream);
+        memcpy(ctx->err, keep, sizeof keep);
+    }
+    if (rc) return rc;
+    pipe->next_ring = (ri + 1) % (int32_t)pipe->ring.size();
+    if (done) { done->ring_index = ri; done->n_cells = n; done->seq = it.seq; }
+    return SLAFB_OK;
+}
+
+int slafb_pipe_push(slafb_pipe *pipe, const slafb_coo *pieces, int32_t n_pieces, const uint32_t *seg_start, const uint32_t *seg_cell,
+                    int64_t n_seg_cells, int64_t seed, void *stream, slafb_pipe_result *done) {
+    if (!pipe) return fail(nullptr, SLAFB_ERR_INVALID, "pipe is NULL");
+    slafb_ctx *ctx = pipe->ctx;
+    if (done) { done->ring_index = -1; done->n_cells = 0; done->seq = -1; }
+    int32_t slot = -1;
+    int rc = seg_start ? slafb_submit_segments(ctx, pieces, n_pieces, seg_start, seg_cell, n_seg_cells, stream, &slot)
+                       : slafb_submit_pieces(ctx, pieces, n_pieces, stream, &slot);
+    if (rc) return rc;
+    if (pipe->p.shuffle == SLAFB_SHUFFLE_SEED) {
+        rc = slafb_prepare_shuffle(ctx, slot, seed);       // the helper thread builds the CPython-exact permutation off this thread
+        if (rc) return rc;
+    }
+    pipe->q.push_back({slot, seed, pipe->next_seq++});
+    if ((int)pipe->q.size() > pipe->depth) return pipe_pop(pipe, stream, done);
+    return SLAFB_OK;
+}
+
+int slafb_pipe_pop(slafb_pipe *pipe, void *stream, slafb_pipe_result *done) {
+    if (!pipe) return fail(nullptr, SLAFB_ERR_INVALID, "pipe is NULL");
+    if (done) { done->ring_index = -1; done->n_cells = 0; done->seq = -1; }
+    if (pipe->q.empty()) return SLAFB_OK;
+    return pipe_pop(pipe, stream, done);
+}
+
+int slafb_pipe_destroy(slafb_pipe *pipe) {
+    if (!pipe) return SLAFB_OK;
+    while (!pipe->q.empty()) {                            // give the slots of batches still in flight back
+        const int32_t slot = pipe->q.front().slot;
+        pipe->q.pop_front();
+        slafb_params e = pipe->p;
+        e.shuffle = SLAFB_SHUFFLE_PERM; e.perm = nullptr; e.n_perm = 0;
+        slafb_out none{};
+        int64_t z = 0;
+        slafb_collect(pipe->ctx, slot, &e, &none, &z, nullptr);
+    }
+    delete pipe;
+    return SLAFB_OK;
+}
+
 int slafb_segments(slafb_ctx *ctx, int32_t slot, int64_t *n_cells, uint32_t *seg_start, uint32_t *seg_cell, int64_t capacity_cells) {
     if (!ctx || slot < 0 || slot >= kSlots || !n_cells) return fail(ctx, SLAFB_ERR_INVALID, "bad ctx / slot / n_cells");
     CU(ctx, cudaSetDevice(ctx->device));
     Slot &s = ctx->slot[slot];
     if (!s.in_flight) return fail(ctx, SLAFB_ERR_INVALID, "slot %d has no submitted batch", slot);
-    const double tw0 = now_ms();
-    CU(ctx, cudaEventSynchronize(s.ev_front));
-    ctx->acc.host_wait_ms += now_ms() - tw0;
+    if (!s.host_segs) {
+        const double tw0 = now_ms();
+        CU(ctx, cudaEventSynchronize(s.ev_front));
+        ctx->acc.host_wait_ms += now_ms() - tw0;
+    }
     *n_cells = s.h_counters[0];
     if (s.h_counters[1]) return fail(ctx, SLAFB_ERR_CAPACITY, "batch has %u cells, context max_cells is %lld", s.h_counters[0], (long long)ctx->max_cells);
     const int64_t C = *n_cells;
     if (C > capacity_cells) return fail(ctx, SLAFB_ERR_CAPACITY, "batch has %lld cells, host table capacity is %lld", (long long)C, (long long)capacity_cells);
     if (C == 0) { if (seg_start) seg_start[0] = 0; return SLAFB_OK; }
     if (!seg_start || !seg_cell) return fail(ctx, SLAFB_ERR_INVALID, "NULL table pointer");
+    if (s.host_segs) {                       // the table was built on the host: it is still in the slot's pinned block
+        memcpy(seg_start, s.h_seg, (size_t)(C + 1) * sizeof(uint32_t));
+        memcpy(seg_cell, s.h_seg + (size_t)ctx->max_cells + 1, (size_t)C * sizeof(uint32_t));
+        return SLAFB_OK;
+    }
     CU(ctx, cudaMemcpyAsync(seg_start, s.seg_start, (size_t)(C + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->s_aux));
     CU(ctx, cudaMemcpyAsync(seg_cell, s.seg_cell, (size_t)C * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->s_aux));
     CU(ctx, cudaStreamSynchronize(ctx->s_aux));
@@ -1268,7 +1488,7 @@ int slafb_set_option(slafb_ctx *ctx, int32_t option, int64_t value) {
     if (!ctx) return fail(ctx, SLAFB_ERR_INVALID, "ctx is NULL");
     switch (option) {
     case SLAFB_OPT_TIMING_INTERVAL:
-        if (value < 1 || value > 1000000) return fail(ctx, SLAFB_ERR_INVALID, "timing interval must be in [1, 1e6]");
+        if (value < 0 || value > 1000000) return fail(ctx, SLAFB_ERR_INVALID, "timing interval must be in [0, 1e6]");
         ctx->timing_every = (int)value;
         return SLAFB_OK;
     case SLAFB_OPT_FRONT_ON_CALLER:

@@ -122,13 +122,16 @@ def allreduce_gene_stats(sum_cnt: torch.Tensor, group: Any = None) -> torch.Tens
     return sum_cnt
 
 
-def gene_stats(engine: Any, batches, n_genes: int, group: Any = None) -> tuple[torch.Tensor, torch.Tensor]:
+def gene_stats(engine: Any, batches, n_genes: int, group: Any = None, mark: Any = None) -> tuple[torch.Tensor, torch.Tensor]:
     """Per-gene nonzero sum and count over this rank's batches (device column triples or pairs
-    ``(gene, value)``), all-reduced over ``group``.  Returns int64 tensors ``(sum, count)`` of length G."""
+    ``(gene, value)``), all-reduced over ``group``.  Returns int64 tensors ``(sum, count)`` of length G.
+    ``mark``: a CUDA event recorded between the kernels and the all-reduce (bench.py times the two halves)."""
     buf = torch.zeros((2, n_genes), dtype=torch.int64, device=engine.device)
     for cols in batches:
         gene, value = cols[-2], cols[-1]
         engine.gene_stats(gene, value, n_genes, sum_out=buf[0], cnt_out=buf[1])     # the kernel accumulates into the reduce buffer
+    if mark is not None:
+        mark.record()
     allreduce_gene_stats(buf, group)
     return buf[0], buf[1]
 

@@ -116,11 +116,19 @@ class HotPathEngine:
         self._ctx = ctx
         self._cap_hint = 0
         self._pending: dict[int, tuple] = {}
+        # host columns of a collected batch stay referenced until the slot is submitted again: collect() only ENQUEUES the
+        # tokenization behind the batch's H2D copy, so the copy engine may still be reading them when collect() returns
+        # (include/slaf_b200.h, conventions); the next submit into that slot waits for the slot's previous batch first
+        self._parked: dict[int, Any] = {}
         self._seg_buf = None
 
     # ------------------------------------------------------------------ lifecycle
     def close(self) -> None:
         if getattr(self, "_ctx", None):
+            for ref in getattr(self, "_pipes", []):
+                pipe = ref()
+                if pipe is not None:
+                    pipe.close()
             self._L.slafb_destroy(self._ctx)
             self._ctx = None
 
@@ -190,8 +198,12 @@ class HotPathEngine:
             N.check(self._L.slafb_submit(self._ctx, ctypes.byref(coo), self._stream(), ctypes.byref(slot)), self._ctx)
             if shuffle_seed is not None:
                 N.check(self._L.slafb_prepare_shuffle(self._ctx, slot.value, int(shuffle_seed)), self._ctx)
-        self._pending[slot.value] = (keep, coo.n_rows)
+        self._took(slot.value, keep, coo.n_rows)
         return slot.value
+
+    def _took(self, slot: int, keep: Any, n_rows: int) -> None:
+        self._parked.pop(slot, None)          # the library waited for the slot's previous batch before reusing it
+        self._pending[slot] = (keep, n_rows)
 
     def submit_pieces(self, pieces: list[tuple[Any, Any, Any]]) -> int:
         """submit() for a batch given as consecutive row blocks [(cell, gene, value), ...] -- no host-side
@@ -208,7 +220,7 @@ class HotPathEngine:
         slot = ctypes.c_int32(-1)
         with torch.cuda.device(self.device):
             N.check(self._L.slafb_submit_pieces(self._ctx, arr, len(coos), self._stream(), ctypes.byref(slot)), self._ctx)
-        self._pending[slot.value] = (keeps[0] + tuple(keeps[1:]), total)
+        self._took(slot.value, keeps[0] + tuple(keeps[1:]), total)
         return slot.value
 
     def submit_segments(self, pieces: list[tuple[Any, Any]], seg_start: np.ndarray, seg_cell: np.ndarray, cell_signed: bool = False,
@@ -240,8 +252,37 @@ class HotPathEngine:
             if shuffle_seed is not None:
                 N.check(self._L.slafb_prepare_shuffle(self._ctx, slot.value, int(shuffle_seed)), self._ctx)
         cell_col = _Column(np.zeros(1, np.int32 if cell_signed else np.uint32), (N.U32, N.I32), "cell_integer_id")
-        self._pending[slot.value] = ((cell_col, keeps[0][0], keeps[0][1]) + tuple(keeps[1:]) + (seg_start, seg_cell), total)
+        self._took(slot.value, (cell_col, keeps[0][0], keeps[0][1]) + tuple(keeps[1:]) + (seg_start, seg_cell), total)
         return slot.value
+
+    def submit_csi(self, pieces: list[tuple[Any, Any, Any]], row_lo: list[int], csi: np.ndarray, check: int = 1,
+                   shuffle_seed: int | None = None) -> tuple[int, int]:
+        """submit() when the dataset's ``_cell_start_index`` describes the rows: `pieces` are consecutive (cell | None, gene, value)
+        HOST row blocks, `row_lo[i]` the table row of piece i's first row, `csi` the int64 index.  The library derives the segment
+        table itself (C, O(cells)), probes it against the cell column (`check`: 0 none, 1 sampled, 2 every head) and ships gene +
+        value columns plus 8 B per cell; the cell column never crosses PCIe and no CSR build runs.  Returns (slot, n_segments)."""
+        if not pieces:
+            raise ValueError("no pieces")
+        if csi.dtype != np.int64 or not csi.flags.c_contiguous:
+            raise TypeError("cell start index must be a contiguous int64 array")
+        coos, keeps, signed = _csi_pieces(pieces)
+        total = sum(c.n_rows for c in coos)
+        arr = (N.Coo * len(coos))(*coos)
+        lo = (ctypes.c_int64 * len(coos))(*[int(x) for x in row_lo])
+        slot, n = ctypes.c_int32(-1), ctypes.c_int64(0)
+        with torch.cuda.device(self.device):
+            N.check(self._L.slafb_submit_csi(self._ctx, arr, len(coos), lo, csi.ctypes.data, csi.size, int(check), self._stream(),
+                                             ctypes.byref(slot), ctypes.byref(n)), self._ctx)
+            if shuffle_seed is not None:
+                N.check(self._L.slafb_prepare_shuffle(self._ctx, slot.value, int(shuffle_seed)), self._ctx)
+        cell_col = _Column(np.zeros(1, np.int32 if signed else np.uint32), (N.U32, N.I32), "cell_integer_id")
+        self._took(slot.value, (cell_col, keeps[0][1], keeps[0][2]) + tuple(keeps[1:]) + (csi,), total)
+        return slot.value, int(n.value)
+
+    def wait_loaded(self, slot: int) -> None:
+        """Block until the H2D copy of the batch last submitted into `slot` has finished (its host columns may be reused)."""
+        with torch.cuda.device(self.device):
+            N.check(self._L.slafb_wait_loaded(self._ctx, int(slot)), self._ctx)
 
     def collect(self, slot: int, *, mode: str, max_genes: int, max_items: int | None = None, n_bins: int = 10,
                 vocab_size: int = 50000, min_percentile: float | None = None, shuffle_seed: int | None = None,
@@ -271,7 +312,8 @@ class HotPathEngine:
         C = int(n.value)
         self._cap_hint = max(self._cap_hint, min(self.max_cells, C + C // 8 + 16))
         ids, mask, vals, cids = tensors
-        del keep, pkeep
+        self._parked[slot] = keep            # see __init__: the H2D copy of these columns may still be in flight
+        del pkeep
         return TokenizedBatch(ids[:C], mask[:C], vals[:C] if scgpt else None, cids[:C], C)
 
     def _abandon(self, slot: int) -> None:
@@ -330,7 +372,7 @@ class HotPathEngine:
         with torch.cuda.device(self.device):
             N.check(self._L.slafb_collect_csr(self._ctx, slot, ctypes.byref(p), crow.data_ptr(), col.data_ptr(), val.data_ptr(),
                                               cids.data_ptr(), cap_cells, max(n_rows, 1), ctypes.byref(n), ctypes.byref(r), self._stream()), self._ctx)
-        del keep, pkeep
+        del keep, pkeep                      # (slafb_collect_csr synchronises the stream: the copy has finished)
         C, R = int(n.value), int(r.value)
         return CsrBatch(crow[: C + 1], col[:R], val[:R], cids[:C], C)
 
@@ -421,8 +463,22 @@ class HotPathEngine:
                                               self._stream()), self._ctx)
         return med, exact
 
+    def pipe(self, *, ring: int, capacity_cells: int, depth: int = 4, mode: str, max_genes: int, max_items: int | None = None,
+             n_bins: int = 10, vocab_size: int = 50000, min_percentile: float | None = None, shuffle: bool = True,
+             window_n_bins: int | None = None, order: str = "row", norm: torch.Tensor | None = None) -> "Pipe":
+        """A steady pipeline with fixed parameters: one C call per step, outputs into a pre-allocated ring (slafb_pipe_*)."""
+        p, _ = self._params(mode, max_genes, max_items, n_bins, vocab_size, min_percentile, 0 if shuffle else None, None, False,
+                            window_n_bins, order, norm)
+        import weakref
+
+        pipe = Pipe(self, p, ring, capacity_cells, depth, norm)
+        if not hasattr(self, "_pipes"):
+            self._pipes = []
+        self._pipes.append(weakref.ref(pipe))
+        return pipe
+
     def set_timing_interval(self, every: int) -> None:
-        """Take the per-kernel CUDA-event timings on every `every`-th batch only."""
+        """Take the per-kernel CUDA-event timings on every `every`-th batch only (0: never)."""
         N.check(self._L.slafb_set_option(self._ctx, N.OPT_TIMING_INTERVAL, int(every)), self._ctx)
 
     def set_front_on_caller(self, on: bool) -> None:
@@ -434,6 +490,101 @@ class HotPathEngine:
         with torch.cuda.device(self.device):
             N.check(self._L.slafb_get_timing(self._ctx, ctypes.byref(t)), self._ctx)
         return {f: getattr(t, f) for f, _ in N.Timing._fields_}
+
+
+class PreparedInput:
+    """The ctypes description of one batch's input (COO pieces, or gene / value pieces + a host segment table), built once for
+    buffers that are submitted again and again (a feeder's staging ring, bench.py's resident batches)."""
+
+    def __init__(self, pieces: list[tuple[Any, Any, Any]], seg_start: np.ndarray | None = None, seg_cell: np.ndarray | None = None,
+                 cell_signed: bool = False):
+        coos, self.keep, self.n_rows = [], [], 0
+        for cell, gene, value in pieces:
+            if seg_start is None:
+                coo, keep = _coo(cell, gene, value)
+            else:
+                g = _Column(gene, (N.U16, N.I32, N.U32), "gene_integer_id")
+                v = _Column(value, (N.U16, N.F32), "value")
+                if g.n != v.n or g.location != v.location:
+                    raise ValueError("gene / value blocks must have equal length and location")
+                coo, keep = N.Coo(None, g.ptr or None, v.ptr or None, g.n, N.I32 if cell_signed else N.U32, g.code, v.code, g.location), (g, v)
+            coos.append(coo)
+            self.keep.append(keep)
+            self.n_rows += coo.n_rows
+        self.arr = (N.Coo * len(coos))(*coos)
+        self.n_pieces = len(coos)
+        self.seg_start = self.seg_cell = None
+        self.n_seg = 0
+        if seg_start is not None:
+            self.seg_start = np.ascontiguousarray(seg_start, np.uint32)
+            self.seg_cell = np.ascontiguousarray(np.asarray(seg_cell)).view(np.uint32) if np.asarray(seg_cell).dtype.itemsize == 4 \
+                else np.ascontiguousarray(seg_cell, np.uint32)
+            self.n_seg = int(self.seg_cell.size)
+            if self.seg_start.size != self.n_seg + 1:
+                raise ValueError("seg_start must have one more entry than seg_cell")
+        self._ss = self.seg_start.ctypes.data if self.seg_start is not None else None
+        self._sc = self.seg_cell.ctypes.data if self.seg_cell is not None else None
+
+
+class Pipe:
+    """slafb_pipe_* behind torch-allocated ring tensors.  ``push`` returns ``(ring_index, n_cells, seq)`` of the batch the call
+    completed (ring_index -1: none yet); ``batch`` gives that ring entry as tensor views.  Ring entry i is rewritten ``ring``
+    completions later in stream order."""
+
+    def __init__(self, eng: HotPathEngine, params: N.Params, ring: int, capacity_cells: int, depth: int, norm=None):
+        self.eng, self._p, self._norm = eng, params, norm
+        scgpt = params.mode >= N.SCGPT_RAW
+        self.L = params.max_genes + 2 if scgpt else params.max_genes
+        self.capacity_cells = int(capacity_cells)
+        self.tensors, outs = [], []
+        for _ in range(ring):
+            out, t = eng._alloc_out(self.capacity_cells, self.L, scgpt)
+            self.tensors.append(t)
+            outs.append(out)
+        self._ring = (N.Out * ring)(*outs)
+        self._res = N.PipeResult()
+        self._res_ref = ctypes.byref(self._res)
+        self._pipe = ctypes.c_void_p()
+        self._push, self._pop = eng._L.slafb_pipe_push, eng._L.slafb_pipe_pop
+        N.check(eng._L.slafb_pipe_create(eng._ctx, ctypes.byref(params), self._ring, ring, depth, ctypes.byref(self._pipe)), eng._ctx)
+        self._stream = eng._stream()
+        self._inputs: list[PreparedInput] = []        # referenced while their copies may be in flight (bounded by the slot count)
+
+    def set_stream(self) -> None:
+        """Re-read torch's current stream (the pipe launches on the stream that was current at creation / the last call of this)."""
+        self._stream = self.eng._stream()
+
+    def push(self, inp: PreparedInput, seed: int = 0) -> tuple[int, int, int]:
+        rc = self._push(self._pipe, inp.arr, inp.n_pieces, inp._ss, inp._sc, inp.n_seg, seed, self._stream, self._res_ref)
+        if rc:
+            N.check(rc, self.eng._ctx)
+        self._inputs.append(inp)
+        if len(self._inputs) > 16:
+            del self._inputs[0]
+        r = self._res
+        return r.ring_index, r.n_cells, r.seq
+
+    def pop(self) -> tuple[int, int, int]:
+        rc = self._pop(self._pipe, self._stream, self._res_ref)
+        if rc:
+            N.check(rc, self.eng._ctx)
+        r = self._res
+        return r.ring_index, r.n_cells, r.seq
+
+    def batch(self, ring_index: int, n_cells: int) -> TokenizedBatch:
+        ids, mask, vals, cids = self.tensors[ring_index]
+        return TokenizedBatch(ids[:n_cells], mask[:n_cells], vals[:n_cells] if vals is not None else None, cids[:n_cells], n_cells)
+
+    def close(self) -> None:
+        if self._pipe:
+            self.eng._L.slafb_pipe_destroy(self._pipe)
+            self._pipe = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def regroup_contiguous(cell: np.ndarray, gene: np.ndarray, value: np.ndarray):
@@ -449,6 +600,43 @@ def regroup_contiguous(cell: np.ndarray, gene: np.ndarray, value: np.ndarray):
     _, first, inv = np.unique(cell, return_index=True, return_inverse=True)
     order = np.argsort(first[inv], kind="stable")
     return cell[order], np.asarray(gene)[order], np.asarray(value)[order]
+
+
+def _csi_pieces(pieces):
+    coos, keeps, signed = [], [], False
+    for cell, gene, value in pieces:
+        g = _Column(gene, (N.U16, N.I32, N.U32), "gene_integer_id")
+        v = _Column(value, (N.U16, N.F32), "value")
+        c = _Column(cell, (N.U32, N.I32), "cell_integer_id") if cell is not None else None
+        if g.n != v.n or g.location != v.location or (c is not None and (c.n != g.n or c.location != N.LOC_HOST)):
+            raise ValueError("blocks must have equal length; the cell column (if given) must be on the host")
+        signed = signed or (c is not None and c.code == N.I32)
+        coos.append(N.Coo(c.ptr if c is not None and c.n else None, g.ptr or None, v.ptr or None, g.n,
+                          c.code if c is not None else N.U32, g.code, v.code, g.location))
+        keeps.append((c, g, v))
+    if signed:
+        for coo in coos:
+            coo.cell_dtype = N.I32
+    return coos, keeps, signed
+
+
+def csi_segments(pieces: list[tuple[Any, Any, Any]], row_lo: list[int], csi: np.ndarray, check: int = 1) -> tuple[np.ndarray, np.ndarray]:
+    """The segment table ``SLAFArray._cell_start_index`` implies for consecutive row blocks (the host half of ``submit_csi``;
+    runs in the library's C code, no GPU involved): (seg_start uint32 [C + 1], seg_cell uint32 [C])."""
+    if csi.dtype != np.int64 or not csi.flags.c_contiguous:
+        raise TypeError("cell start index must be a contiguous int64 array")
+    coos, keeps, _signed = _csi_pieces(pieces)
+    rows = sum(c.n_rows for c in coos)
+    cap = int(min(rows, max(csi.size - 1, 0) + len(coos))) + 1      # every piece can cut at most one more cell in two
+    start, ids = np.empty(cap + 1, np.uint32), np.empty(cap, np.uint32)
+    arr = (N.Coo * len(coos))(*coos)
+    lo = (ctypes.c_int64 * len(coos))(*[int(x) for x in row_lo])
+    n = ctypes.c_int64(0)
+    N.check(N.lib().slafb_csi_segments(arr, len(coos), lo, csi.ctypes.data, csi.size, int(check), start.ctypes.data, ids.ctypes.data,
+                                       cap, ctypes.byref(n)))
+    del keeps
+    C = int(n.value)
+    return start[: C + 1].copy(), ids[:C].copy()
 
 
 def shuffle_perm(seed: int, n: int) -> np.ndarray:

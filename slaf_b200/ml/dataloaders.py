@@ -11,8 +11,10 @@ dictionaries as the reference's ``slaf.ml.dataloaders.SLAFDataLoader`` (slaf/ml/
 ``device_raw=True`` (with ``raw_mode=True``) keeps raw mode on the GPU: ``batch["x"]`` is a dict of CSR device tensors
 (``crow_indices``, ``col_indices``, ``values``, ``cell_ids``) over the batch's cells in shuffled order instead of a host frame.
 
-``use_cell_start_index=True`` takes the cell boundaries of every chunk from ``slaf_array._cell_start_index`` instead of the
+``use_cell_start_index``: the cell boundaries of every chunk come from ``slaf_array._cell_start_index`` instead of the
 ``cell_integer_id`` column (which then neither crosses PCIe -- half of the bytes -- nor is scanned); the token tensors are identical.
+Default ``None``: used whenever the array carries the index and it keeps validating against the rows (probed per load; the first
+mismatch falls back to the cell column with a warning); ``True`` insists (a mismatch raises); ``False`` never uses it.
 
 Two additions: ``device`` (CUDA device the path runs on; default current) and ``output_device``
 ("cpu" adds an explicit D2H copy of the finished batch for code that asserts the reference's CPU
@@ -52,7 +54,7 @@ class SLAFDataLoader:
                  verbose: bool = True, batches_per_chunk: int = 1, by_fragment: bool = True,
                  use_mixture_of_scanners: bool = True, n_scanners: int = 16, prefetch_batch_size: int = 4194304,
                  max_queue_size: int = 8, parallelize_fragment_reads: bool = False, prefetcher_ready_timeout: float = 10.0,
-                 device=None, output_device=None, device_raw: bool = False, use_cell_start_index: bool = False):
+                 device=None, output_device=None, device_raw: bool = False, use_cell_start_index: bool | None = None):
         self.slaf_array = slaf_array
         self.batch_size = batch_size
         self.max_genes = max_genes

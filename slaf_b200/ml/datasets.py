@@ -201,42 +201,6 @@ def _regroup_segments(pieces: list[CooChunk], seg_start: np.ndarray, seg_cell: n
     return out
 
 
-def _segments_from_csi(pieces: list[CooChunk], csi: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
-    """Segment table of the concatenated pieces from SLAFArray._cell_start_index alone (no look at the cell column):
-    piece p covers table rows [row_lo, row_lo + len); cell c owns rows [csi[c], csi[c + 1]).  Consecutive pieces that
-    continue the same cell give ONE segment (their rows are adjacent in the staging columns); a cell that shows up in
-    two separated places gives two segments with the same id, which the caller's splice safety net handles.
-    Returns (seg_start uint32 [C + 1], seg_cell int64 [C]).  O(cells), vectorised."""
-    starts, ids = [], []
-    pos = 0
-    last_cell = None
-    for p in pieces:
-        n = len(p)
-        if n == 0:
-            continue
-        lo, hi = int(p.row_lo), int(p.row_lo) + n
-        c0 = int(np.searchsorted(csi, lo, side="right")) - 1
-        c1 = int(np.searchsorted(csi, hi - 1, side="right")) - 1
-        cells = np.arange(c0, c1 + 1, dtype=np.int64)
-        first_row = np.maximum(csi[cells], lo)
-        nonempty = csi[cells + 1] > first_row                      # cells without rows (or not reaching into this piece) have no segment
-        cells, first_row = cells[nonempty], first_row[nonempty]
-        st = first_row - lo + pos
-        if len(cells):
-            new_last = int(cells[-1])
-            if last_cell is not None and last_cell == int(cells[0]) and st[0] == pos:
-                cells, st = cells[1:], st[1:]                        # the previous piece's last cell continues here: one segment
-            last_cell = new_last
-        starts.append(st)
-        ids.append(cells)
-        pos += n
-    ids = [i for i in ids if len(i)]
-    starts = [s_ for s_ in starts if len(s_)]
-    seg_cell = np.concatenate(ids) if ids else np.zeros(0, np.int64)
-    seg_start = np.concatenate(starts + [np.array([pos], np.int64)]) if starts else np.array([0], np.int64)
-    return seg_start.astype(np.uint32), seg_cell
-
-
 class _Staging:
     """Ring of pinned host buffers the combined rows of a batch are assembled in (so the H2D copy
     is a true async DMA).  Copies run on a small thread pool: numpy releases the GIL in memcpy."""
@@ -247,21 +211,44 @@ class _Staging:
         self.bufs: list[tuple[np.ndarray, np.ndarray, np.ndarray]] = []
         self.turn = 0
         self.pool = ThreadPoolExecutor(max_workers=max(1, threads)) if threads > 1 else None
+        self.users: list[tuple[Any, int] | None] = [None] * depth     # (engine, slot) whose H2D copy last read each buffer
+        self.last = 0
+
+    def used_by(self, eng: Any, slot: int) -> None:
+        """The buffer handed out last is the DMA source of `slot`: it is not refilled before that copy has finished."""
+        self.users[self.last] = (eng, slot)
 
     def ensure(self, rows: int) -> None:
         if rows <= self.capacity:
             return
         cap = max(rows + rows // 4, 1 << 16)
+        self._wait_all()
         self.bufs = [tuple(pinned_empty(cap * 4, np.uint8) for _ in range(3)) for _ in range(self.depth)]
         self.capacity = cap
 
-    def assemble(self, pieces: list[CooChunk]) -> CooChunk:
+    def _wait(self, i: int) -> None:
+        user, self.users[i] = self.users[i], None
+        if user is not None:
+            eng, slot = user
+            if getattr(eng, "_ctx", True) and hasattr(eng, "wait_loaded"):
+                eng.wait_loaded(slot)            # (a later batch in that slot sits behind ours on the same copy stream: waiting for it covers ours)
+
+    def _wait_all(self) -> None:
+        for i in range(len(self.users)):
+            self._wait(i)
+
+    def assemble(self, pieces: list[CooChunk], with_cell: bool = True) -> CooChunk:
+        """The pieces back to back in the next pinned buffer of the ring.  ``with_cell=False`` leaves the cell column out
+        (cell-start-index route: it does not travel); the returned chunk's ``cell`` is then an empty view."""
         n = sum(len(p) for p in pieces)
         self.ensure(n)
+        self._wait(self.turn)                    # the copy engine may still be reading what this buffer held three loads ago
         raw = self.bufs[self.turn]
+        self.last = self.turn
         self.turn = (self.turn + 1) % self.depth
         first = pieces[0]
-        dst = CooChunk(*(raw[i][: n * src.dtype.itemsize].view(src.dtype) for i, src in enumerate((first.cell, first.gene, first.value))))
+        dst = CooChunk(*(raw[i][: (n if (i or with_cell) else 0) * src.dtype.itemsize].view(src.dtype)
+                         for i, src in enumerate((first.cell, first.gene, first.value))))
         tasks = []
         off = 0
         step = 1 << 21   # rows per copy task
@@ -270,7 +257,7 @@ class _Staging:
                 raise TypeError("fragments of one expression table must share column dtypes")
             for lo in range(0, len(p), step):
                 hi = min(lo + step, len(p))
-                for d, s_ in ((dst.cell, p.cell), (dst.gene, p.gene), (dst.value, p.value)):
+                for d, s_ in (((dst.cell, p.cell),) if with_cell else ()) + ((dst.gene, p.gene), (dst.value, p.value)):
                     tasks.append((d, off + lo, s_, lo, hi))
             off += len(p)
         if self.pool is not None and len(tasks) > 3:
@@ -283,6 +270,10 @@ class _Staging:
     def close(self) -> None:
         if self.pool is not None:
             self.pool.shutdown(wait=False)
+        try:
+            self._wait_all()
+        except Exception:
+            pass
         self.bufs = []
         self.capacity = 0
 
@@ -299,12 +290,23 @@ class PrefetchBatchProcessor:
                  n_epochs: int = 1, raw_mode: bool = False, verbose: bool = True, log_metrics: bool = False,
                  batch_size: int = 32, by_fragment: bool = True, use_mixture_of_scanners: bool = True, n_scanners: int = 16,
                  prefetch_batch_size: int = 4194304, parallelize_fragment_reads: bool = False, device=None,
-                 copy_threads: int = 4, device_raw: bool = False, use_cell_start_index: bool = False):
+                 copy_threads: int = 4, device_raw: bool = False, use_cell_start_index: bool | None = None, csi_check: int = 1):
         self.slaf_array = slaf_array
         self.device_raw = device_raw
-        # EXTENSION: take the cell boundaries from slaf_array._cell_start_index instead of the cell column, so that
-        # column neither crosses PCIe nor is scanned (needs a source that knows the table position of its chunks)
+        # EXTENSION: take the cell boundaries from slaf_array._cell_start_index (slaf/core/slaf.py:645-702) instead of the cell
+        # column, so that column neither crosses PCIe nor is scanned (needs a source that knows the table position of its
+        # chunks).  None (default) = use the index whenever the array has one and it keeps validating against the rows
+        # (probes, csi_check: 1 sampled / 2 every cell); the first mismatch switches this processor to the cell-column route for
+        # good.  True = insist (a mismatch is a ValueError).  False = always ship and scan the cell column (the reference's contract).
         self.use_cell_start_index = use_cell_start_index
+        self.csi_check = int(csi_check)
+        self._csi_arr: np.ndarray | None = None
+        if use_cell_start_index is not False:
+            idx = getattr(slaf_array, "_cell_start_index", None)
+            if idx is not None:
+                self._csi_arr = np.ascontiguousarray(np.asarray(idx), np.int64)
+            elif use_cell_start_index:
+                raise ValueError("use_cell_start_index=True needs slaf_array._cell_start_index")
         self.shuffle = shuffle
         self.tokenizer = tokenizer
         self.seed = seed
@@ -574,8 +576,8 @@ class PrefetchBatchProcessor:
         sorted by cell only the cells at the head or tail of a piece can be cut, so the host predicts them from those runs
         alone (``_predict``), checks the prediction against the segment table when it arrives (``_front``) and, if it was wrong
         (rows not sorted by cell, an index that does not match), rebuilds the next load from the table."""
-        if self.use_cell_start_index:
-            return False
+        if self._csi_arr is not None:
+            return False                      # the table comes from the host: no load ever waits for the GPU, nothing to look ahead for
         if self.raw_mode:
             return self.device_raw and type(self.shuffle) in (RandomShuffle, StratifiedShuffle)
         return self._fused_ok()
@@ -789,55 +791,58 @@ class PrefetchBatchProcessor:
         if direct and len(pieces) <= 256:
             return eng.submit_pieces([(p.cell, p.gene, p.value) for p in pieces]), pieces
         rows = self._staging.assemble(pieces)
-        return eng.submit(rows.cell, rows.gene, rows.value), [rows]
+        slot = eng.submit(rows.cell, rows.gene, rows.value)
+        self._staging.used_by(eng, slot)
+        return slot, [rows]
 
-    def _submit_with_csi(self, eng: HotPathEngine, pieces: list[CooChunk]):
-        csi = np.asarray(self.slaf_array._cell_start_index, np.int64)
-        seg_start, seg_cell = _segments_from_csi(pieces, csi)
-        ascending = seg_cell.size < 2 or bool(np.all(seg_cell[1:] > seg_cell[:-1]))        # the usual case, and it implies distinct ids
-        if not ascending and len(np.unique(seg_cell)) != len(seg_cell):    # a cell in two separated places: splice (views) first
-            pieces = _regroup_segments(pieces, seg_start, seg_cell)
-            seg_start, seg_cell = _segments_from_csi(pieces, csi)
-        # cheap consistency probes against the rows themselves: at up to 64 evenly spaced segment heads (and the last row) the
-        # cell column must show exactly that id starting exactly there -- a shifted or stale index is caught, O(1) per batch
-        offs = np.concatenate(([0], np.cumsum([len(p) for p in pieces])))
-        C = len(seg_cell)
-        if C:
-            probe = np.unique(np.linspace(0, C - 1, num=min(C, 64)).astype(np.int64))
-            rows = seg_start[probe].astype(np.int64)
-            which = np.searchsorted(offs, rows, side="right") - 1
-            want = np.asarray(seg_cell)[probe].astype(np.int64)
-            ok = True
-            for k in np.unique(which):
-                sel_k = which == k
-                a = rows[sel_k] - int(offs[k])
-                col = pieces[int(k)].cell
-                here = col[a].astype(np.int64)
-                before = col[np.maximum(a - 1, 0)].astype(np.int64)
-                ok = ok and bool(np.all(here == want[sel_k])) and bool(np.all((a == 0) | (before != want[sel_k])))
-            if not ok:
-                raise ValueError("_cell_start_index does not describe the expression rows (a cell does not start where the index says)")
-            if int(pieces[-1].cell[-1]) != int(seg_cell[-1]):
-                raise ValueError("_cell_start_index does not describe the expression rows (last cell id differs)")
-        signed = pieces[0].cell.dtype == np.int32
+    def _submit_with_csi(self, eng: HotPathEngine, pieces: list[CooChunk], regrouped: bool = False):
+        """Gene / value columns + the segment table the index implies (built and probed against the cell column inside the library,
+        ``slafb_submit_csi``).  Returns (engine, slot, pieces, seg_start, seg_cell)."""
         direct = all(len(p) <= self.SMALL_PIECE_ROWS or (is_page_locked(p.gene) and is_page_locked(p.value)) for p in pieces)
-        if direct and len(pieces) <= 256:
-            slot = eng.submit_segments([(p.gene, p.value) for p in pieces], seg_start, seg_cell.astype(np.uint32), cell_signed=signed)
-        else:
-            rows = self._staging.assemble(pieces)
-            slot = eng.submit_segments([(rows.gene, rows.value)], seg_start, seg_cell.astype(np.uint32), cell_signed=signed)
-        ids = seg_cell.astype(np.int32) if signed else seg_cell.astype(np.uint32)
-        return slot, pieces, seg_start, ids
+        src = pieces
+        if not (direct and len(pieces) <= 256):
+            rows = self._staging.assemble(pieces, with_cell=False)      # one pinned block; the piece structure (table positions) is kept
+            src, off = [], 0
+            for p in pieces:
+                src.append(CooChunk(p.cell, rows.gene[off:off + len(p)], rows.value[off:off + len(p)], p.row_lo))
+                off += len(p)
+        try:
+            slot, _n = eng.submit_csi([(p.cell, p.gene, p.value) for p in src], [p.row_lo for p in src], self._csi_arr, check=self.csi_check)
+        except N.SlafB200Error as err:
+            if err.code == N.ERR_CAPACITY:                              # more cells than the segment tables hold: size for the worst case
+                eng = self._engine_for(sum(len(p) for p in pieces), all_cells=True)
+                return self._submit_with_csi(eng, pieces, regrouped)
+            if err.code == N.ERR_INVALID and "cell_start_index" in err.message:
+                raise ValueError(f"_cell_start_index does not describe the expression rows ({err.message})") from err
+            raise
+        if src is not pieces:
+            self._staging.used_by(eng, slot)
+        seg_start, seg_cell = eng.segments(slot)                       # (host-built table: no wait for the GPU)
+        ascending = seg_cell.size < 2 or bool(np.all(seg_cell[1:] > seg_cell[:-1]))        # the usual case, and it implies distinct ids
+        if not ascending and not regrouped and len(np.unique(seg_cell)) != len(seg_cell):  # a cell in two separated places: splice (views) first
+            eng.release(slot)
+            return self._submit_with_csi(eng, _regroup_segments(pieces, seg_start, seg_cell), True)
+        return eng, slot, pieces, seg_start, seg_cell
 
     def _front(self, rec: _Staged):
         """submit -> segment table -> (splice safety net) -> completeness -> partial stash.
         Returns (engine, slot, indices of the complete cells in first-appearance order, their row counts)."""
         pieces = rec.pieces
         n_rows = sum(len(p) for p in pieces)
-        if rec.slot is None and self.use_cell_start_index and all(p.row_lo is not None for p in pieces):
-            eng = self._engine_for(n_rows)
-            slot, pieces, seg_start, seg_cell = self._submit_with_csi(eng, pieces)
-        else:
+        done = False
+        if rec.slot is None and self._csi_arr is not None and all(p.row_lo is not None for p in pieces):
+            try:
+                eng, slot, pieces, seg_start, seg_cell = self._submit_with_csi(self._engine_for(n_rows), pieces)
+                done = True
+            except ValueError:
+                if self.use_cell_start_index:
+                    raise
+                import warnings
+
+                warnings.warn("slaf_array._cell_start_index does not describe the expression rows; falling back to the cell column "
+                              "(8 B/row over PCIe instead of 4)", RuntimeWarning, stacklevel=2)
+                self._csi_arr = None
+        if not done:
             if rec.slot is None:
                 self._submit_staged(rec)
             eng, slot, pieces = rec.eng, rec.slot, rec.pieces
@@ -1121,7 +1126,7 @@ class SLAFIterableDataset(IterableDataset):
                  batches_per_chunk: int = 1, by_fragment: bool = True, use_mixture_of_scanners: bool = True, n_scanners: int = 16,
                  prefetch_batch_size: int = 4194304, parallelize_fragment_reads: bool = False,
                  prefetcher_ready_timeout: float = 10.0, device=None, output_device=None, device_raw: bool = False,
-                 use_cell_start_index: bool = False):
+                 use_cell_start_index: bool | None = None):
         super().__init__()
         self.slaf_array = slaf_array
         self.tokenizer = tokenizer

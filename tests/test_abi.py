@@ -29,7 +29,7 @@ def test_header_symbols_all_exported(lib):
     assert declared == set(_native.EXPORTS), declared ^ set(_native.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
-    assert lib.slafb_version() == _native.ABI_VERSION == 2
+    assert lib.slafb_version() == _native.ABI_VERSION == 3
 
 
 def test_struct_layouts_match_header():
@@ -37,6 +37,34 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_native.Params) == 4 * 4 + 8 + 8 + 4 + 4 + 8 + 8 + 8 + 4 + 4 + 8 + 8
     assert ctypes.sizeof(_native.Out) == 5 * 8
     assert ctypes.sizeof(_native.Timing) == 4 * 8 + 5 * 8 + 4 * 8 + 8
+    assert ctypes.sizeof(_native.PipeResult) == 4 + 4 + 8 + 8
+
+
+def test_csi_segments_host_routine_matches_the_index(lib):
+    """slafb_csi_segments (host only): the table SLAFArray._cell_start_index implies for row blocks cut anywhere, including
+    blocks that continue a cell, skip rows, or arrive out of order; a shifted index is refused by the probes."""
+    from slaf_b200 import synthetic
+    from slaf_b200.engine import csi_segments
+
+    b = synthetic.make_batch(200, 3000, 40, seed=3, min_nnz=2)
+    csi = np.ascontiguousarray(b.cell_start, np.int64)
+    rng = np.random.default_rng(1)
+    for trial in range(60):
+        cuts = np.sort(rng.choice(b.n_rows, size=int(rng.integers(0, 6)), replace=False)).tolist()
+        bounds = [0] + cuts + [b.n_rows]
+        blocks = [(bounds[i], bounds[i + 1]) for i in range(len(bounds) - 1)]
+        if trial % 3 == 1 and len(blocks) > 2:
+            blocks.pop(1)                                          # a gap: rows skipped
+        if trial % 3 == 2 and len(blocks) > 2:
+            blocks[0], blocks[1] = blocks[1], blocks[0]            # out of table order
+        start, ids = csi_segments([(b.cell[lo:hi], b.gene[lo:hi], b.value[lo:hi]) for lo, hi in blocks], [lo for lo, _ in blocks], csi, check=2)
+        cat = np.concatenate([b.cell[lo:hi] for lo, hi in blocks])
+        heads = np.flatnonzero(np.r_[True, cat[1:] != cat[:-1]])
+        assert start.tolist() == heads.tolist() + [len(cat)] and ids.tolist() == cat[heads].tolist()
+    shifted = csi.copy()
+    shifted[1:-1] += 2
+    with pytest.raises(_native.SlafB200Error, match="cell_start_index does not describe"):
+        csi_segments([(b.cell, b.gene, b.value)], [0], shifted, check=1)
 
 
 @pytest.mark.parametrize("seed", [0, 1, 42, 43, 10042, 2**31 + 5, 2**40 + 7, -9])

@@ -369,7 +369,7 @@ def test_look_ahead_falls_back_when_the_table_is_not_sorted_by_cell(data):
 
     arr = SyntheticSLAFArray(ArrayExpressionSource(cell, data.gene, data.value, 2500), np.zeros(N_CELLS + 1, np.int64), N_GENES)
     tok = GeneformerTokenizer(arr, max_genes=32)
-    proc = PrefetchBatchProcessor(arr, RandomShuffle(), tok, seed=42, n_epochs=2, use_mixture_of_scanners=False, by_fragment=True, verbose=False)
+    proc = PrefetchBatchProcessor(arr, RandomShuffle(), tok, seed=42, n_epochs=2, use_mixture_of_scanners=False, by_fragment=True, verbose=False, use_cell_start_index=False)
     assert proc._lookahead_ok()
     got = _drain(proc)
     want = _emulate_fragment_mode(cell, data.gene, data.value, 2500, 2, 32)
@@ -387,7 +387,7 @@ def test_look_ahead_defers_the_submit_when_the_engine_has_to_grow(data):
 
     arr = _array(data, rows_per_file=2500)
     tok = GeneformerTokenizer(arr, max_genes=32)
-    proc = PrefetchBatchProcessor(arr, RandomShuffle(), tok, seed=42, use_mixture_of_scanners=False, by_fragment=True, verbose=False)
+    proc = PrefetchBatchProcessor(arr, RandomShuffle(), tok, seed=42, use_mixture_of_scanners=False, by_fragment=True, verbose=False, use_cell_start_index=False)
     proc._engine = small = HotPathEngine(0, max_rows=2510, max_cells=2510)     # the first load fits, partial + second fragment does not
     got = _drain(proc)
     assert proc._engine is not small and proc._engine.max_rows > 2510
@@ -405,7 +405,7 @@ def test_look_ahead_defers_the_submit_when_the_engine_has_to_grow(data):
 def test_look_ahead_reset_for_epoch_drops_the_submitted_load(data):
     arr = _array(data, rows_per_file=2500)
     tok = GeneformerTokenizer(arr, max_genes=32)
-    proc = PrefetchBatchProcessor(arr, RandomShuffle(), tok, seed=42, n_epochs=2, use_mixture_of_scanners=False, by_fragment=True, verbose=False)
+    proc = PrefetchBatchProcessor(arr, RandomShuffle(), tok, seed=42, n_epochs=2, use_mixture_of_scanners=False, by_fragment=True, verbose=False, use_cell_start_index=False)
     first = proc.load_prefetch_batch()
     second = proc.load_prefetch_batch()
     assert proc._ahead is not None and (first.batch_id, second.batch_id) == (0, 1)
@@ -442,7 +442,7 @@ def test_mixture_of_scanners_look_ahead_equals_the_synchronous_feeder(data, seed
             arr._cell_start_index = np.concatenate(([0], np.cumsum(counts)))
         tok = GeneformerTokenizer(arr, max_genes=32)
         proc = PrefetchBatchProcessor(arr, RandomShuffle(), tok, seed=42, n_epochs=2, use_mixture_of_scanners=True, n_scanners=3,
-                                      prefetch_batch_size=1000, verbose=False)
+                                      prefetch_batch_size=1000, verbose=False, use_cell_start_index=False)
         if not lookahead:
             monkeypatch.setattr(proc, "_lookahead_ok", lambda: False)
         else:
@@ -462,7 +462,8 @@ def test_mixture_of_scanners_look_ahead_equals_the_synchronous_feeder(data, seed
         assert sorted(seen.tolist()) == list(range(N_CELLS))
 
 
-def test_arrow_source_page_locked_maps_feed_the_copy_engine_directly(tmp_path, data):
+@pytest.mark.parametrize("csi_route", [None, False], ids=["cell_start_index", "cell_column"])
+def test_arrow_source_page_locked_maps_feed_the_copy_engine_directly(tmp_path, data, csi_route):
     """ArrowExpressionSource.pin(): the files' read-only mappings are registered with the driver, the record-batch views are
     DMA sources and the feeder's pinned staging ring is never allocated; tokens are the same either way.  (A driver that refuses
     to register file mappings leaves the staged path in place: pin() then returns False and only the equality is checked.)"""
@@ -473,7 +474,7 @@ def test_arrow_source_page_locked_maps_feed_the_copy_engine_directly(tmp_path, d
         pinned = src.pin() if pin else False
         arr = SyntheticSLAFArray(src, np.asarray(data.cell_start), N_GENES)
         proc = PrefetchBatchProcessor(arr, RandomShuffle(), GeneformerTokenizer(arr, max_genes=400), seed=42, use_mixture_of_scanners=False,
-                                      by_fragment=True, verbose=False)
+                                      by_fragment=True, verbose=False, use_cell_start_index=csi_route)
         proc.SMALL_PIECE_ROWS = 650                    # the 700-row record batches of this small table must be page-locked or staged; pending cells stay small
         out = _drain(proc)
         seen = _check_rows([{"input_ids": o.input_ids, "attention_mask": o.attention_mask, "cell_ids": o.cell_ids} for o in out], expected, scgpt=False)

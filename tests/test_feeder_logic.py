@@ -16,6 +16,42 @@ from slaf_b200.ml.sources import ArrayExpressionSource, SyntheticSLAFArray
 N_CELLS, N_GENES = 400, 3000
 
 
+def _segments_from_csi(pieces: list, csi: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+    """Segment table of the concatenated pieces from SLAFArray._cell_start_index alone (no look at the cell column):
+    piece p covers table rows [row_lo, row_lo + len); cell c owns rows [csi[c], csi[c + 1]).  Consecutive pieces that
+    continue the same cell give ONE segment (their rows are adjacent in the staging columns); a cell that shows up in
+    two separated places gives two segments with the same id, which the caller's splice safety net handles.
+    Returns (seg_start uint32 [C + 1], seg_cell int64 [C]).  O(cells), vectorised."""
+    starts, ids = [], []
+    pos = 0
+    last_cell = None
+    for p in pieces:
+        n = len(p)
+        if n == 0:
+            continue
+        lo, hi = int(p.row_lo), int(p.row_lo) + n
+        c0 = int(np.searchsorted(csi, lo, side="right")) - 1
+        c1 = int(np.searchsorted(csi, hi - 1, side="right")) - 1
+        cells = np.arange(c0, c1 + 1, dtype=np.int64)
+        first_row = np.maximum(csi[cells], lo)
+        nonempty = csi[cells + 1] > first_row                      # cells without rows (or not reaching into this piece) have no segment
+        cells, first_row = cells[nonempty], first_row[nonempty]
+        st = first_row - lo + pos
+        if len(cells):
+            new_last = int(cells[-1])
+            if last_cell is not None and last_cell == int(cells[0]) and st[0] == pos:
+                cells, st = cells[1:], st[1:]                        # the previous piece's last cell continues here: one segment
+            last_cell = new_last
+        starts.append(st)
+        ids.append(cells)
+        pos += n
+    ids = [i for i in ids if len(i)]
+    starts = [s_ for s_ in starts if len(s_)]
+    seg_cell = np.concatenate(ids) if ids else np.zeros(0, np.int64)
+    seg_start = np.concatenate(starts + [np.array([pos], np.int64)]) if starts else np.array([0], np.int64)
+    return seg_start.astype(np.uint32), seg_cell
+
+
 class _Out:
     def __init__(self, cids, width):
         n = len(cids)
@@ -55,6 +91,20 @@ class StandInEngine:
         assert all(len(np.asarray(g)) == len(np.asarray(v)) for g, v in pieces)
         assert seg_start[0] == 0 and seg_start[-1] == n_rows and len(seg_start) == len(seg_cell) + 1 and np.all(np.diff(seg_start.astype(np.int64)) > 0)
         return self._put(np.repeat(seg_cell, np.diff(seg_start.astype(np.int64))))
+
+    def submit_csi(self, pieces, row_lo, csi, check=1, shuffle_seed=None):
+        # the cell-start-index route: the library's host-only C routine derives (and probes) the table; checked here against the
+        # numpy restatement below
+        from slaf_b200.engine import csi_segments
+        from slaf_b200.ml.sources import CooChunk
+
+        seg_start, seg_cell = csi_segments(pieces, row_lo, csi, check=check)
+        want = _segments_from_csi([CooChunk(c, g, v, lo) for (c, g, v), lo in zip(pieces, row_lo)], csi)
+        assert np.array_equal(seg_start, want[0]) and np.array_equal(seg_cell, want[1].astype(np.uint32))
+        return self.submit_segments([(g, v) for _c, g, v in pieces], seg_start, seg_cell), len(seg_cell)
+
+    def wait_loaded(self, slot):
+        pass
 
     def segments(self, slot):
         cell = self.slots[slot]
@@ -111,6 +161,7 @@ def _proc(b, cell=None, csi=None, rows_per_file=1777, **kw):
     arr = SyntheticSLAFArray(ArrayExpressionSource(cell, b.gene, b.value, rows_per_file),
                              b.cell_start if csi is None else csi, N_GENES)
     tok = GeneformerTokenizer(arr, max_genes=16)
+    kw.setdefault("use_cell_start_index", False)      # most tests here are about the cell-column route and its look-ahead
     return PrefetchBatchProcessor(arr, RandomShuffle(), tok, seed=42, verbose=False, **kw)
 
 
@@ -422,3 +473,22 @@ def test_cell_start_index_that_does_not_match_the_rows_is_refused(stand_in):
     relabel = _proc(b, cell=(b.cell + 1).astype(b.cell.dtype), csi=np.concatenate(([0], b.cell_start)), use_mixture_of_scanners=False,
                     by_fragment=True, use_cell_start_index=True)
     _drain(relabel)                                                    # ids shifted together with the index: consistent again
+
+
+def test_cell_start_index_is_the_default_route_and_falls_back_when_stale(stand_in):
+    """use_cell_start_index=None (the default): the index is used while it validates; a stale one is noticed by the probes, warned
+    about once, and the processor continues on the cell column -- same stream either way."""
+    b = _data()
+    ref = _drain(_proc(b, use_mixture_of_scanners=False, by_fragment=True))
+    auto = _proc(b, use_mixture_of_scanners=False, by_fragment=True, use_cell_start_index=None)
+    assert auto._csi_arr is not None and not auto._lookahead_ok()
+    got = _drain(auto)
+    _same(ref, got)
+    assert not any(kind == "segments" and False for kind, _ in auto._engine.log)
+    csi = b.cell_start.copy()
+    csi[1:-1] += 3
+    stale = _proc(b, csi=csi, use_mixture_of_scanners=False, by_fragment=True, use_cell_start_index=None)
+    with pytest.warns(RuntimeWarning, match="_cell_start_index does not describe"):
+        got = _drain(stale)
+    assert stale._csi_arr is None
+    _same(ref, got)

@@ -317,8 +317,12 @@ def test_segments_from_cell_start_index_match_the_column():
     """The CSI-driven segment table (no look at the cell column) equals the runs of the column itself: whole fragments,
     consecutive pieces that continue a cell, unrelated pieces, cells without any row."""
     from slaf_b200 import synthetic
-    from slaf_b200.ml.datasets import _runs, _segments_from_csi
+    from slaf_b200.engine import csi_segments
+    from slaf_b200.ml.datasets import _runs
     from slaf_b200.ml.sources import ArrayExpressionSource
+
+    def _segments_from_csi(pieces, csi):     # the library's host-only C routine (slafb_csi_segments), every head probed
+        return csi_segments([(p.cell, p.gene, p.value) for p in pieces], [p.row_lo for p in pieces], csi, check=2)
 
     b = synthetic.make_batch(200, 500, 30, seed=3, min_nnz=2)
     # insert cells without rows: ids shift, CSI gets repeated offsets
@@ -353,8 +357,12 @@ from hypothesis import strategies as st  # noqa: E402
 def test_property_csi_segments_equal_column_runs(lens, rows_per_file, data):
     """For any table (cells of 0..7 rows), any fragment size and any selection of consecutive fragment slices, the segment
     table computed from _cell_start_index alone equals the runs of the cell column."""
-    from slaf_b200.ml.datasets import _runs, _segments_from_csi
+    from slaf_b200.engine import csi_segments
+    from slaf_b200.ml.datasets import _runs
     from slaf_b200.ml.sources import ArrayExpressionSource
+
+    def _segments_from_csi(pieces, csi):
+        return csi_segments([(p.cell, p.gene, p.value) for p in pieces], [p.row_lo for p in pieces], np.ascontiguousarray(csi, np.int64), check=2)
 
     lens = np.asarray(lens, np.int64)
     if lens.sum() == 0:

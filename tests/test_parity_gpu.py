@@ -427,3 +427,134 @@ def test_many_tiny_cells_take_the_dense_head_path(engine):
     want = c_oracle.tokenize(cell.astype(np.int32), gene.astype(np.int32), value.astype(np.float32), "scgpt_raw", 2, n_bins=10, vocab_size=70000)
     got = engine.tokenize(cell.astype(np.int32), gene.astype(np.int32), value.astype(np.float32), mode="scgpt_raw", max_genes=2, n_bins=10, vocab_size=70000)
     compare(got, want, "scgpt_raw")
+
+
+# ------------------------------------------------------------------------ round 2: percentile mode in the fast kernel
+@pytest.mark.parametrize("gene_dtype", ["uint16", "int32"])
+@pytest.mark.parametrize("pct", [0.0, 10.0, 37.5, 50.0, 99.9, 100.0])
+def test_percentile_fast_kernel_shapes(engine, pct, gene_dtype):
+    """MODE_GF_PCT on uint16 values runs in tokenize_cells_kernel (presence bitmap in shared memory + in-place compaction):
+    cells with n <= k (the percentile rule still filters them), value ranges wider than the 8,192-bit bitmap (deferred to the
+    general kernel), cells longer than the stages (rows read from global memory), every value equal, one row, ties at the
+    threshold, k below and above the number of distinct values."""
+    rng = np.random.default_rng(int(pct * 10) + 5)
+    G = 60000 if gene_dtype == "uint16" else 70000
+    cells = []
+
+    def add(vals):
+        n = len(vals)
+        cells.append((np.sort(rng.choice(G, size=n, replace=False)), np.asarray(vals)))
+
+    add([7])                                                      # one row
+    add(np.full(300, 3))                                          # one distinct value
+    add(rng.geometric(0.35, 900))                                 # count-like, n <= k
+    add(rng.geometric(0.2, 2500))                                 # count-like, n > k
+    add(np.r_[rng.geometric(0.35, 1500), 9000])                   # range > 8192: general kernel
+    add(np.r_[rng.geometric(0.35, 1500), 8191 + 1])               # range exactly 8192: bitmap
+    add(rng.integers(1, 4000, 3000))                              # ~2100 distinct values: real top-k cut
+    add(rng.integers(1, 50, 4090))                                # just below the stage capacity
+    add(rng.integers(1, 50, 4097))                                # just above: tail rows from global memory
+    add(rng.integers(1, 3000, 9000))                              # far above, many distinct
+    add(np.repeat(np.arange(1, 41), 25))                          # 40 distinct x 25: percentile lands on a tie group
+    for _ in range(12):
+        n = int(rng.integers(1, 3000))
+        add(np.minimum(rng.geometric(float(rng.uniform(0.05, 0.6)), n), 65535))
+    order = rng.permutation(len(cells))
+    ids = rng.choice(500000, size=len(cells), replace=False)
+    cell = np.concatenate([np.full(len(cells[j][0]), ids[j]) for j in order]).astype(np.uint32)
+    gene = np.concatenate([cells[j][0] for j in order]).astype(gene_dtype)
+    value = np.concatenate([cells[j][1] for j in order]).astype(np.uint16)
+    C = len(cells)
+    for k, max_genes in ((2048, 2048), (64, 64), (20, 300), (2048, 100)):
+        want = c_oracle.tokenize(cell, gene, value, "geneformer_pct", max_genes, max_items=k, perm=py_perm(3, C), min_percentile=pct)
+        got = engine.tokenize(cell, gene, value, mode="geneformer_pct", max_genes=max_genes, max_items=k, min_percentile=pct, shuffle_seed=3)
+        compare(got, want, "geneformer_pct")
+    t = engine.timing()
+    assert t["tokenize_ms"] > 0.0                                  # the fast kernel ran
+
+
+def test_percentile_synthetic_config_full_compare(engine):
+    b = synthetic.make_batch(3000, 62000, 2000, seed=77)
+    want = c_oracle.tokenize(b.cell, b.gene, b.value, "geneformer_pct", 2048, perm=py_perm(5, b.n_cells), min_percentile=10.0)
+    got = engine.tokenize(b.cell, b.gene, b.value, mode="geneformer_pct", max_genes=2048, min_percentile=10.0, shuffle_seed=5)
+    compare(got, want, "geneformer_pct")
+    assert engine.timing()["slow_cells"] <= 0.05 * b.n_cells        # only the heavy-tail cells (range > 8192) take the general kernel
+
+
+# ------------------------------------------------------------------------ round 2: pipe, host segment tables
+def test_pipe_matches_submit_collect(engine):
+    """slafb_pipe_*: one call per step, outputs into a ring; every completed batch equals the oracle, in push order."""
+    from slaf_b200.engine import PreparedInput
+
+    batches = [synthetic.make_batch(250 + 40 * i, 30000, 500, seed=400 + i) for i in range(7)]
+    kw = dict(mode="scgpt_binned", max_genes=300, n_bins=51, vocab_size=65000)
+    pipe = engine.pipe(ring=2, capacity_cells=600, depth=3, **kw)
+    dev = [tuple(to_dev(a) for a in (b.cell, b.gene, b.value)) for b in batches]
+    done = []
+    for i, cols in enumerate(dev):
+        ri, n, seq = pipe.push(PreparedInput([cols]), 90 + i)
+        assert (ri < 0) == (i < 3)
+        if ri >= 0:
+            out = pipe.batch(ri, n)
+            done.append((seq, [t.clone() if t is not None else None for t in (out.input_ids, out.attention_mask, out.values, out.cell_ids)]))
+    while True:
+        ri, n, seq = pipe.pop()
+        if ri < 0:
+            break
+        out = pipe.batch(ri, n)
+        done.append((seq, [t.clone() if t is not None else None for t in (out.input_ids, out.attention_mask, out.values, out.cell_ids)]))
+    assert [s for s, _ in done] == list(range(7))
+    for (seq, (ids, mask, vals, cids)), b in zip(done, batches):
+        want = c_oracle.tokenize(b.cell, b.gene, b.value, "scgpt_binned", 300, perm=py_perm(90 + seq, b.n_cells), n_bins=51, vocab_size=65000)
+        assert_same(ids.cpu().numpy(), want[0], "ids")
+        assert_same(mask.cpu().numpy(), want[1], "mask")
+        assert_same(vals.cpu().numpy(), want[2], "vals")
+        assert_same(cids.cpu().numpy(), want[3], "cell ids")
+    # a batch larger than the ring entries is dropped with an error and does not leak its slot
+    big = synthetic.make_batch(700, 30000, 100, seed=1)
+    with pytest.raises(_native.SlafB200Error) as ei:
+        for _ in range(4):
+            pipe.push(PreparedInput([(big.cell, big.gene, big.value)]), 1)
+    assert ei.value.code == _native.ERR_CAPACITY
+    pipe.close()
+    got = engine.tokenize(batches[0].cell, batches[0].gene, batches[0].value, shuffle_seed=90, **kw)     # the context is still usable
+    assert got.n_cells == batches[0].n_cells
+
+
+def test_pipe_host_segments_route_and_csi_submit(engine):
+    """The cell-start-index routes: slafb_submit_segments (table from the caller), slafb_submit_csi (table derived in the
+    library from the index and the piece positions) and the pipe with a prepared table all give the COO route's tensors."""
+    from slaf_b200.engine import PreparedInput
+
+    b = synthetic.make_batch(900, 30000, 400, seed=21, first_cell_id=100)
+    csi = np.concatenate((np.zeros(100, np.int64), b.cell_start)).astype(np.int64)       # cells 0..99 have no rows
+    kw = dict(mode="geneformer", max_genes=512)
+    ref = engine.tokenize(b.cell, b.gene, b.value, shuffle_seed=5, **kw)
+    cuts = [0, 1234, 1235, 200000, b.n_rows]
+    pieces = [(b.cell[lo:hi], b.gene[lo:hi], b.value[lo:hi]) for lo, hi in zip(cuts[:-1], cuts[1:])]
+    slot, n = engine.submit_csi(pieces, cuts[:-1], csi, check=2, shuffle_seed=5)
+    assert n == b.n_cells
+    st, ids = engine.segments(slot)                                   # host-built table: served without waiting for the GPU
+    assert np.array_equal(st, b.cell_start.astype(np.uint32)) and np.array_equal(ids, np.arange(100, 1000, dtype=np.uint32))
+    got = engine.collect(slot, shuffle_seed=5, **kw)
+    for x, y in ((got.input_ids, ref.input_ids), (got.attention_mask, ref.attention_mask), (got.cell_ids, ref.cell_ids)):
+        assert torch.equal(x, y)
+    assert engine.timing()["csr_ms"] >= 0.0
+    pipe = engine.pipe(ring=2, capacity_cells=1000, depth=0, **kw)
+    ri, n, _ = pipe.push(PreparedInput([(None, b.gene, b.value)], seg_start=b.cell_start.astype(np.uint32), seg_cell=np.arange(100, 1000, dtype=np.uint32)), 5)
+    out = pipe.batch(ri, n)
+    assert torch.equal(out.input_ids, ref.input_ids) and torch.equal(out.cell_ids, ref.cell_ids)
+    pipe.close()
+    # a stale index is refused before anything is submitted
+    bad = csi.copy()
+    bad[101:-1] += 1
+    with pytest.raises(_native.SlafB200Error, match="cell_start_index does not describe"):
+        engine.submit_csi(pieces, cuts[:-1], bad, check=1)
+    # so is a caller-supplied table that is not monotone or does not cover the rows (it would send bulk copies out of bounds)
+    st_bad = b.cell_start.astype(np.uint32).copy()
+    st_bad[10], st_bad[11] = st_bad[11], st_bad[10]
+    for table in (st_bad, b.cell_start.astype(np.uint32)[:-1]):
+        with pytest.raises((_native.SlafB200Error, ValueError)):
+            engine.submit_segments([(b.gene, b.value)], table, np.arange(100, 1000, dtype=np.uint32))
+    got = engine.tokenize(b.cell, b.gene, b.value, shuffle_seed=5, **kw)
+    assert torch.equal(got.input_ids, ref.input_ids)
