@@ -347,6 +347,204 @@ def loader_rate(w, batches, dev, value_dtype):
     return out
 
 
+# ----------------------------------------------------------------------------- sharded loader (BASELINE.json config 3)
+def table_layout(w, table_cells: int, chunk_cells: int):
+    """Row offsets of the synthetic table: (cells per chunk, rows per chunk, cell start index of the whole table)."""
+    from slaf_b200 import synthetic
+
+    sizes = [min(chunk_cells, table_cells - lo) for lo in range(0, table_cells, chunk_cells)]
+    nnz = [synthetic.batch_nnz(n, w["n_genes"], w["mean_nnz"], seed=5000 + c) for c, n in enumerate(sizes)]
+    csi = np.zeros(table_cells + 1, np.int64)
+    np.cumsum(np.concatenate(nnz), out=csi[1:])
+    return sizes, [int(x.sum()) for x in nnz], csi
+
+
+def write_table_files(path: str, w, sizes, chunk_rows, files: range, rows_per_file: int, value_dtype: str, rows_per_batch: int = 1 << 20):
+    """Write the Arrow IPC fragments `files` of the table: fragment f holds the table rows [f * rows_per_file, (f + 1) * rows_per_file),
+    cut without regard to cells or generator chunks (a file that straddles two chunks is assembled from both: the generator is
+    deterministic per chunk, so any rank can produce any file)."""
+    import pyarrow as pa
+
+    from slaf_b200 import synthetic
+
+    chunk_row0 = np.concatenate(([0], np.cumsum(chunk_rows)))
+    total = int(chunk_row0[-1])
+    cell0 = np.concatenate(([0], np.cumsum(sizes)))
+    cache: dict[int, object] = {}
+
+    def chunk(c):
+        if c not in cache:
+            if len(cache) > 1:
+                cache.pop(min(cache))
+            cache[c] = synthetic.make_batch(sizes[c], w["n_genes"], w["mean_nnz"], seed=5000 + c, value_dtype=value_dtype, first_cell_id=int(cell0[c]))
+        return cache[c]
+
+    for f in files:
+        lo, hi = f * rows_per_file, min((f + 1) * rows_per_file, total)
+        parts = []
+        c = int(np.searchsorted(chunk_row0, lo, side="right")) - 1
+        while lo < hi:
+            b = chunk(c)
+            a, e = lo - int(chunk_row0[c]), min(hi, int(chunk_row0[c + 1])) - int(chunk_row0[c])
+            parts.append((b.cell[a:e], b.gene[a:e], b.value[a:e]))
+            lo = int(chunk_row0[c + 1])
+            c += 1
+        cols = [np.concatenate([p[i] for p in parts]) if len(parts) > 1 else parts[0][i] for i in range(3)]
+        table = pa.table({"cell_integer_id": cols[0], "gene_integer_id": cols[1], "value": cols[2]})
+        name = os.path.join(path, f"fragment-{f:06d}.arrow")
+        with pa.OSFile(name + ".tmp", "wb") as sink, pa.ipc.new_file(sink, table.schema) as writer:
+            for rb in table.to_batches(max_chunksize=rows_per_batch):
+                writer.write_batch(rb)
+        os.replace(name + ".tmp", name)
+
+
+def run_sharded(args, w):
+    """`--sharded`: BASELINE.json config 3 as the reference shards it (slaf/distributed/coordinator.py:40-80): ONE expression table
+    (Arrow IPC fragments in /dev/shm, not cell aligned), every rank opens the whole table and reads its contiguous fragment range
+    through shard_source + SLAFIterableDataset (boundary cells owned by the rank that holds their first row); no collective on
+    the batch path.  Every-cell-exactly-once is proven with (count, sum, xor, sum of squares mod 2^61) of the emitted cell ids over
+    all ranks.  One JSON line: aggregate loader cells/s (host-resident input: an end-to-end number), per-rank rates and H2D GB/s."""
+    import shutil
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    my_cpus = pin_rank_cores(local_rank, world) if world > 1 and not os.environ.get("SLAFB_BENCH_NO_PIN") else None
+    import torch
+    import torch.distributed as dist
+
+    from slaf_b200.distributed import shard_rows, shard_source
+    from slaf_b200.ml import GeneformerTokenizer, ScGPTTokenizer, SLAFIterableDataset
+    from slaf_b200.ml.sources import ArrowExpressionSource, SyntheticSLAFArray
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def allreduce(x, op):
+        t = torch.tensor(x, dtype=torch.float64 if isinstance(x[0], float) else torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=op)
+        return t.tolist()
+
+    stage(f"sharded: table layout ({args.table_cells} cells)")
+    sizes, chunk_rows, csi = table_layout(w, args.table_cells, 32768)
+    total_rows = int(csi[-1])
+    n_files = -(-total_rows // args.rows_per_file)
+    path = os.path.join(args.table_dir, f"slafb_table_{os.environ.get('MASTER_PORT', 'single')}")
+    if rank == 0:
+        shutil.rmtree(path, ignore_errors=True)
+        os.makedirs(path)
+    barrier()
+    base, rem = divmod(n_files, world)
+    f0 = rank * base + min(rank, rem)
+    t_w = time.perf_counter()
+    write_table_files(path, w, sizes, chunk_rows, range(f0, f0 + base + (1 if rank < rem else 0)), args.rows_per_file, args.value_dtype)
+    barrier()
+    stage(f"sharded: {n_files} fragments written in {time.perf_counter() - t_w:.1f} s (every rank wrote its share)")
+
+    src = ArrowExpressionSource(path)
+    rows = [f.count_rows() for f in src.get_fragments()]
+    lo, hi = shard_rows(rows, csi, world, rank)
+    shard = shard_source(src, csi, world, rank)
+    pinned = bool(src.pin()) if not os.environ.get("SLAFB_BENCH_NO_PIN_SOURCE") else False
+    arr = SyntheticSLAFArray(shard, csi, w["n_genes"])
+    c_lo, c_hi = int(np.searchsorted(csi, lo, side="left")), int(np.searchsorted(csi, hi, side="left"))
+    shard_cells = c_hi - c_lo
+    n_epochs = max(3, 2 + -(-args.sharded_cells // max(1, shard_cells)))
+    tok = (ScGPTTokenizer(arr, vocab_size=w["vocab"], n_expression_bins=w["n_bins"], max_genes=w["max_genes"], device=dev)
+           if w["tokenizer"] == "scgpt" else GeneformerTokenizer(arr, vocab_size=w["vocab"], max_genes=w["max_genes"], device=dev))
+    loader = SLAFIterableDataset(arr, tok, batch_size=1024, use_binned_expressions=w["binned"], use_mixture_of_scanners=False, by_fragment=True,
+                                 verbose=False, device=dev, max_queue_size=4, n_epochs=n_epochs)
+    route = "cell_start_index" if loader.batch_processor._csi_arr is not None else "cell column"
+    # epoch 0: warm-up + the every-cell-once proof; epochs 1 .. n-2: timed between the first batch of epoch 1 and the first of the last epoch
+    M61 = (1 << 61) - 1
+    cnt = torch.zeros((), dtype=torch.int64, device=dev)
+    ssum = torch.zeros((), dtype=torch.int64, device=dev)
+    sxor = torch.zeros((), dtype=torch.int64, device=dev)
+    ssq = torch.zeros((), dtype=torch.int64, device=dev)
+    lo_seen = torch.full((), 1 << 62, dtype=torch.int64, device=dev)
+    hi_seen = torch.full((), -1, dtype=torch.int64, device=dev)
+    n_timed, t0, t1, started = 0, None, None, False
+    stage(f"sharded: rank {rank} reads rows [{lo}, {hi}) = cells [{c_lo}, {c_hi}), {n_epochs} epochs, route {route}, source page-locked: {pinned}")
+    for batch in loader:
+        ep = batch["epoch"]
+        ids = batch["cell_ids"]
+        if ep == 0:
+            cnt += ids.numel()
+            ssum += ids.sum()
+            ssq += ((ids % M61) * (ids % M61) % M61).sum()
+            for part in ids.split(65536):
+                sxor ^= torch.bitwise_xor(part, torch.zeros_like(part)).cpu().numpy().view(np.int64).__class__.bitwise_xor.reduce(part.cpu().numpy()) if False else int(np.bitwise_xor.reduce(part.cpu().numpy()))
+            lo_seen = torch.minimum(lo_seen, ids.min())
+            hi_seen = torch.maximum(hi_seen, ids.max())
+            continue
+        if t1 is not None:
+            continue
+        if not started:
+            barrier()                                   # all ranks start their timed epochs together
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            started = True
+        if ep == n_epochs - 1:
+            _ = ids.cpu()                               # D2H read: everything up to this batch has been computed
+            t1 = time.perf_counter()
+            continue
+        n_timed += ids.numel()
+    torch.cuda.synchronize(dev)
+    dt = t1 - t0
+    got = allreduce([int(cnt), int(ssum), int(ssq) % M61], dist.ReduceOp.SUM)
+    xors = [torch.zeros((), dtype=torch.int64, device=dev) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(xors, sxor)
+    else:
+        xors = [sxor]
+    gx = 0
+    for x in xors:
+        gx ^= int(x)
+    n = args.table_cells
+    allc = np.arange(n, dtype=np.int64)
+    want = [n, n * (n - 1) // 2, int(((allc % M61) * (allc % M61) % M61).sum()), int(np.bitwise_xor.reduce(allc))]
+    once = (got[0] == want[0] and got[1] == want[1] and got[2] % M61 == want[2] % M61 and gx == want[3]
+            and int(lo_seen) == c_lo and int(hi_seen) == c_hi - 1 and int(cnt) == shard_cells)
+    ok_all = allreduce([1 if once else 0], dist.ReduceOp.MIN)[0]
+    rows_timed = int(csi[c_hi] - csi[c_lo]) * (n_timed // max(1, shard_cells)) if shard_cells else 0
+    b_row = (batch_gene_bytes := 2 if w["n_genes"] <= 65535 else 4) + (2 if args.value_dtype == "uint16" else 4) + (0 if route == "cell_start_index" else 4)
+    rates = allreduce([0.0] * rank + [n_timed / dt] + [0.0] * (world - rank - 1), dist.ReduceOp.SUM)
+    h2d = allreduce([0.0] * rank + [rows_timed * b_row / dt / 1e9] + [0.0] * (world - rank - 1), dist.ReduceOp.SUM)
+    tot = allreduce([float(n_timed)], dist.ReduceOp.SUM)[0]
+    tmax = allreduce([float(dt)], dist.ReduceOp.MAX)[0]
+    del loader
+    barrier()
+    src.unpin()
+    if rank == 0:
+        shutil.rmtree(path, ignore_errors=True)
+        if not ok_all:
+            raise SystemExit(f"SHARDING FAILURE: the ranks did not emit every cell exactly once (got {got}, xor {gx}; want {want})")
+        line = {"metric": "tokenized cells/sec", "value": tot / tmax, "unit": "cells/s", "n_gpus": world, "steps": n_epochs - 2, "warmup": 1,
+                "ms_per_step": 1e3 * tmax / max(1, n_epochs - 2), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int64",
+                "data": "synthetic",
+                "config": {"workload": w["name"] + " -- ONE table sharded by contiguous fragment range over the ranks (shard_source + SLAFIterableDataset)",
+                           "table_cells": n, "table_rows": total_rows, "fragments": n_files, "rows_per_file": args.rows_per_file,
+                           "fragments_cell_aligned": False, "value_dtype": args.value_dtype, "route": route, "source": "Arrow IPC files in " + args.table_dir,
+                           "source_page_locked": pinned, "epochs_timed": n_epochs - 2, "cpus_of_rank0": my_cpus,
+                           "note": "a step is one epoch of a rank's shard; host-resident input, so `value` is an end-to-end loader number (H2D inside)"},
+                "every_cell_exactly_once": {"checked": "count, sum, sum of squares mod 2^61-1 and xor of the emitted cell ids over all ranks; min / max / count per rank against its shard",
+                                            "ok": bool(ok_all), "cells": got[0]},
+                "per_rank": {"cells_per_s": [round(x, 1) for x in rates], "h2d_gbs": [round(x, 2) for x in h2d], "seconds": tmax},
+                "e2e": {"value": tot / tmax, "unit": "cells/s", "h2d_bytes_per_step": int(rows_timed * b_row // max(1, n_epochs - 2)), "d2h_bytes_per_step": 8 * 1024}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ----------------------------------------------------------------------------- B200 arm
 _T0 = time.perf_counter()
 
@@ -370,6 +568,11 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-loader", action="store_true")
     ap.add_argument("--verify-cells", type=int, default=2048)
+    ap.add_argument("--sharded", action="store_true", help="config 3 as the reference shards it: one table in /dev/shm, every rank reads its fragment range through the loader")
+    ap.add_argument("--table-cells", type=int, default=1 << 20, help="--sharded: cells of the table")
+    ap.add_argument("--rows-per-file", type=int, default=1 << 24, help="--sharded: rows per fragment file (not cell aligned)")
+    ap.add_argument("--sharded-cells", type=int, default=4_000_000, help="--sharded: cells each rank tokenizes in its timed epochs (at least)")
+    ap.add_argument("--table-dir", default="/dev/shm", help="--sharded: where the Arrow fragments are written")
     ap.add_argument("--watchdog", type=int, default=None,
                     help="seconds after which every thread's stack is dumped to stderr and the run aborts (default: 780 s, more for very long runs; 0 = off)")
     args = ap.parse_args()
@@ -385,6 +588,8 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         return run_reference(args, w)
+    if args.sharded:
+        return run_sharded(args, w)
 
     cpu_baseline = None
     if int(os.environ.get("WORLD_SIZE", "1")) == 1 and not args.no_cpu_baseline:
@@ -552,7 +757,7 @@ def main():
             while pipe.pop()[0] >= 0:
                 pass
 
-    def timed(inputs, n_warm, n_steps, read_result, wall):
+    def timed(inputs, n_warm, n_steps, read_result, wall, keep_last=False):
         """(cells, seconds [max over ranks], this rank's seconds, d2h bytes, last completed (ring, n, seq))"""
         st = Stream(inputs)
         st.prime()
@@ -569,7 +774,11 @@ def main():
         tm_ = eng.timing()                  # counters of exactly the timed steps (the drain below is not part of them)
         barrier()
         local = dt_wall if wall else e0.elapsed_time(e1) / 1e3
-        last = st.last
+        ri, nc, seq = st.last
+        last = None
+        if keep_last:                       # the batch the last timed step completed (the drain below reuses its ring entry)
+            out = pipe.batch(ri, nc)
+            last = (seq, type(out)(*(t.clone() if t is not None else None for t in (out.input_ids, out.attention_mask, out.values, out.cell_ids)), nc))
         st.drain()
         return cells, max_over_ranks(local), local, d2h, last, tm_
 
@@ -579,17 +788,19 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    cells, sec, sec_local, _, last, tm = timed(in_dev, args.warmup, args.steps, False, wall=False)
+    cells, sec, sec_local, _, last, tm = timed(in_dev, args.warmup, args.steps, False, wall=False, keep_last=(rank == 0))
     ms = sec * 1e3
     total_cells = sum_over_ranks(cells)
     value = total_cells / sec
     per_rank = gather_ranks([1e3 * sec_local / args.steps] + [1000.0 * tm[f"host_{k}_ms"] / max(1, tm["batches"]) for k in ("submit", "collect", "wait")])
     # the batch the last timed step completed, checked in full against the oracle (rank 0; the ring still holds it)
     if rank == 0 and not w.get("rank_norm"):
-        ri, nc, seq = last
-        _, want_full = oracle_for(batches[seq % NB], nc, 42 + seq)
-        if not same(pipe.batch(ri, nc), want_full):
+        seq, got_last = last
+        _, want_full = oracle_for(batches[seq % NB], got_last.n_cells, 42 + seq)
+        if not same(got_last, want_full):
             raise SystemExit("PARITY FAILURE: a batch of the timed pass differs from the oracle")
+        del got_last, want_full
+    last = None
 
     # ---- the same pipelined steps carrying per-kernel CUDA events (what roofline.frac is computed from)
     stage("pipelined pass with per-kernel events")

@@ -1587,9 +1587,67 @@ struct RankArgs {
     int rank_order;
     unsigned long long *scratch64;   // [n_rows] composites of cells larger than kRankSmemKeys
 };
-constexpr int kRankSmemKeys = 8192;
+constexpr int kRankSmemKeys = 4096;       // composites sorted in registers + shared memory up to here (32 KiB per CTA: six CTAs per SM)
 
 __device__ void bitonic_sort_asc_u64(unsigned long long *keys, uint32_t n) { bitonic_sort_asc_t<unsigned long long>(keys, n); }
+
+// Bitonic sort of E * kTokThreads 64-bit keys in shared memory (callers pad with ~0), ascending, with the network tiled over the
+// memory hierarchy: thread t owns the E contiguous elements [t * E, t * E + E) in REGISTERS.  Strides below E are compare-
+// exchanges between a thread's own registers, strides below 32 * E are exchanged with another lane by warp shuffles, and only
+// the strides that cross warps go through shared memory (two barriers each).  For 4,096 keys that is 6 shared-memory steps
+// instead of 78 barrier-separated passes over shared memory.
+template <int E>
+__device__ __forceinline__ void bitonic_sort_tiled(unsigned long long *sm) {
+    constexpr uint32_t N = (uint32_t)E * kTokThreads;
+    const uint32_t base = threadIdx.x * (uint32_t)E;
+    unsigned long long v[E];
+#pragma unroll
+    for (int r = 0; r < E; r++) v[r] = sm[base + r];
+    for (uint32_t k = 2; k <= N; k <<= 1) {
+        uint32_t j = k >> 1;
+        for (; j >= (uint32_t)E * 32u; j >>= 1) {                       // partner in another warp
+            __syncthreads();                                            // everyone has read what the previous step left in sm
+#pragma unroll
+            for (int r = 0; r < E; r++) sm[base + r] = v[r];
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < E; r++) {
+                const uint32_t i = base + r;
+                const unsigned long long pv = sm[i ^ j];
+                const bool keep_min = (((i & j) == 0u) == ((i & k) == 0u));
+                v[r] = keep_min ? (pv < v[r] ? pv : v[r]) : (pv > v[r] ? pv : v[r]);
+            }
+        }
+        for (; j >= (uint32_t)E; j >>= 1) {                             // partner in another lane of this warp
+            const uint32_t lm = j / (uint32_t)E;
+            const bool keep_min = (((base & j) == 0u) == ((base & k) == 0u));   // (k > j >= E: neither bit depends on r)
+#pragma unroll
+            for (int r = 0; r < E; r++) {
+                const unsigned long long pv = __shfl_xor_sync(0xffffffffu, v[r], lm);
+                v[r] = keep_min ? (pv < v[r] ? pv : v[r]) : (pv > v[r] ? pv : v[r]);
+            }
+        }
+#pragma unroll
+        for (int jj = E / 2; jj >= 1; jj >>= 1) {                       // partner in my own registers
+            if ((uint32_t)jj <= (k >> 1)) {
+#pragma unroll
+                for (int r = 0; r < E; r++) {
+                    if ((r & jj) == 0) {
+                        const bool asc = (((base + (uint32_t)r) & k) == 0u);
+                        const unsigned long long x = v[r], y = v[r | jj];
+                        const bool sw = (x > y) == asc;
+                        v[r] = sw ? y : x;
+                        v[r | jj] = sw ? x : y;
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < E; r++) sm[base + r] = v[r];
+    __syncthreads();
+}
 
 template <typename GeneT, typename ValT>
 __device__ __forceinline__ uint32_t rank_key(const RankArgs &ra, GeneT g, ValT v) {
@@ -1617,12 +1675,34 @@ __global__ void __launch_bounds__(kTokThreads) tokenize_rank_kernel(const RankAr
         const uint32_t c = a.perm ? (uint32_t)a.perm[j] : j;
         const uint32_t s = __ldg(a.seg_start + c), e = __ldg(a.seg_start + c + 1), n = e - s;
         unsigned long long *keys = (n <= (uint32_t)kRankSmemKeys) ? rk_keys : (ra.scratch64 + s);
-        for (uint32_t i = tid; i < n; i += kTokThreads) {
-            const uint32_t key = rank_key<GeneT, ValT>(ra, __ldg(gene + s + i), __ldg(value + s + i));
-            keys[i] = ((unsigned long long)(~key) << 32) | (unsigned long long)i;
+        if (n <= (uint32_t)kRankSmemKeys) {
+            // composites into shared memory, padded with ~0 (sorts last) up to the next power of two >= 256 per the tiling
+            uint32_t P = kTokThreads;
+            while (P < n) P <<= 1;
+            for (uint32_t i = tid; i < P; i += kTokThreads) {
+                unsigned long long c = ~0ull;
+                if (i < n) {
+                    const uint32_t key = rank_key<GeneT, ValT>(ra, __ldg(gene + s + i), __ldg(value + s + i));
+                    c = ((unsigned long long)(~key) << 32) | (unsigned long long)i;
+                }
+                keys[i] = c;
+            }
+            __syncthreads();
+            switch (P / kTokThreads) {
+            case 1: bitonic_sort_tiled<1>(keys); break;
+            case 2: bitonic_sort_tiled<2>(keys); break;
+            case 4: bitonic_sort_tiled<4>(keys); break;
+            case 8: bitonic_sort_tiled<8>(keys); break;
+            default: bitonic_sort_tiled<16>(keys); break;
+            }
+        } else {
+            for (uint32_t i = tid; i < n; i += kTokThreads) {
+                const uint32_t key = rank_key<GeneT, ValT>(ra, __ldg(gene + s + i), __ldg(value + s + i));
+                keys[i] = ((unsigned long long)(~key) << 32) | (unsigned long long)i;
+            }
+            __syncthreads();
+            bitonic_sort_asc_u64(keys, n);
         }
-        __syncthreads();
-        bitonic_sort_asc_u64(keys, n);
         // m = rows with dense rank <= k: the prefix before the (k+1)-th distinct key
         if (tid == 0) s_bcast[0] = n;
         __syncthreads();

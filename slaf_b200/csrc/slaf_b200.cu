@@ -324,7 +324,14 @@ int launch_rank(slafb_ctx *ctx, const RankArgs &ra, cudaStream_t st) {
         CU(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
         attr_set[ctx->device & 63].store(true, std::memory_order_release);
     }
-    uint32_t grid = (uint32_t)ctx->n_sm * 3u;       // 64 KiB of keys per CTA: three CTAs per SM
+    static std::atomic<int> per_sm_cached[64];       // persistent CTAs over a ticket: as many as are resident (registers: the sort keeps 16 keys per thread)
+    int per_sm = per_sm_cached[ctx->device & 63].load(std::memory_order_acquire);
+    if (per_sm == 0) {
+        CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTokThreads, dyn));
+        if (per_sm < 1) per_sm = 1;
+        per_sm_cached[ctx->device & 63].store(per_sm, std::memory_order_release);
+    }
+    uint32_t grid = (uint32_t)(ctx->n_sm * per_sm);
     if (ra.t.n_cells < grid) grid = ra.t.n_cells;
     kern<<<grid, kTokThreads, dyn, st>>>(ra);
     CU(ctx, cudaGetLastError());

@@ -83,6 +83,13 @@ def make_batch(
     return CooBatch(cell, gene, value, n_cells, start)
 
 
+def batch_nnz(n_cells: int, n_genes: int, mean_nnz: float, seed: int, sigma: float = 0.35, min_nnz: int = 16) -> np.ndarray:
+    """Rows per cell of ``make_batch(n_cells, n_genes, mean_nnz, seed, ...)`` without generating the rows (the generator's first
+    draw replayed): lets every rank of a sharded run know the row offsets of the whole table."""
+    rng = np.random.default_rng(seed)
+    return np.clip(np.rint(rng.lognormal(np.log(mean_nnz), sigma, n_cells)), min(min_nnz, n_genes), n_genes).astype(np.int64)
+
+
 def split_fragments(batch: CooBatch, max_rows_per_file: int) -> list[tuple[np.ndarray, np.ndarray, np.ndarray]]:
     """Contiguous row ranges NOT aligned to cells (cells straddle fragments, converter.py:121)."""
     out = []
