@@ -306,6 +306,11 @@ int slafb_host_unregister(void *ptr);
 typedef enum { SLAFB_OPT_TIMING_INTERVAL = 1, SLAFB_OPT_FRONT_ON_CALLER = 2 } slafb_option;
 int slafb_set_option(slafb_ctx *ctx, int32_t option, int64_t value);
 
+/* Checked builds only (nvcc -DSLAFB_CHECKED: every stage / table / output index is compared with its bound on the device): the
+ * number of violated checks on the current device since the library was loaded, info[8] = {count, code, value, CTA, thread, ...} of
+ * the first.  -1 = the library was not built with checks. */
+int slafb_debug_check_failures(uint32_t *info);
+
 /* Timing / counters since the previous call (synchronises the context's streams). */
 int slafb_get_timing(slafb_ctx *ctx, slafb_timing *t);
 

@@ -37,7 +37,7 @@ EXPORTS = [
     "slafb_version", "slafb_create", "slafb_destroy", "slafb_last_error", "slafb_tokenize", "slafb_submit", "slafb_submit_pieces", "slafb_submit_segments", "slafb_host_register", "slafb_host_unregister",
     "slafb_collect", "slafb_collect_csr", "slafb_prepare_shuffle", "slafb_segments", "slafb_window", "slafb_tokenize_lists", "slafb_shuffle_perm", "slafb_gene_stats", "slafb_gene_hist", "slafb_gene_median",
     "slafb_host_alloc", "slafb_host_free", "slafb_get_timing", "slafb_set_option",
-    "slafb_submit_csi", "slafb_csi_segments", "slafb_wait_loaded", "slafb_pipe_create", "slafb_pipe_push", "slafb_pipe_pop", "slafb_pipe_destroy",
+    "slafb_submit_csi", "slafb_csi_segments", "slafb_wait_loaded", "slafb_pipe_create", "slafb_pipe_push", "slafb_pipe_pop", "slafb_pipe_destroy", "slafb_debug_check_failures",
 ]
 
 
@@ -161,6 +161,7 @@ def lib() -> ctypes.CDLL:
     L.slafb_pipe_push.argtypes = [c_void_p, POINTER(Coo), c_int32, c_void_p, c_void_p, c_int64, c_int64, c_void_p, POINTER(PipeResult)]
     L.slafb_pipe_pop.argtypes = [c_void_p, c_void_p, POINTER(PipeResult)]
     L.slafb_pipe_destroy.argtypes = [c_void_p]
+    L.slafb_debug_check_failures.argtypes = [c_void_p]
     for name in EXPORTS:
         getattr(L, name)  # AttributeError here = header and library out of sync
     _lib = L

@@ -49,6 +49,25 @@ __device__ __forceinline__ void store_pair(long long *p, long long x0, long long
 #endif
 }
 
+// Checked build (-DSLAFB_CHECKED): every index the kernels compute for a shared-memory stage, a scratch table or an output
+// tensor is compared with its bound before use; the first violation is recorded (code, value, CTA, thread) in a device word the
+// host reads with slafb_debug_check_failures().  compute-sanitizer is closed on the pool these kernels are developed on
+// (profiles/r2a_sanitizer_refused.txt), so the GPU test-suite is run once against this build instead (scripts/checked_build.sh).
+#ifdef SLAFB_CHECKED
+__device__ unsigned int g_check_fail[8];
+#define SLAFB_CHECK(cond, code, val)                                                                              \
+    do {                                                                                                          \
+        if (!(cond)) {                                                                                            \
+            if (atomicAdd(&g_check_fail[0], 1u) == 0u) {                                                          \
+                g_check_fail[1] = (unsigned)(code); g_check_fail[2] = (unsigned)(val);                            \
+                g_check_fail[3] = blockIdx.x; g_check_fail[4] = threadIdx.x;                                      \
+            }                                                                                                     \
+        }                                                                                                         \
+    } while (0)
+#else
+#define SLAFB_CHECK(cond, code, val) do { } while (0)
+#endif
+
 constexpr int kTokThreads = 256;
 constexpr int kGroup = 8;                           // rows per thread per chunk (one 128-bit load of u16)
 constexpr int kChunkRows = kTokThreads * kGroup;    // 2048 rows staged per iteration
@@ -319,6 +338,7 @@ __device__ __forceinline__ void csr_finish(const CsrArgs &a, uint32_t span, uint
             const uint32_t o = base + i;
             if (o < a.max_cells) {
                 const uint32_t r = s_sorted[i];
+                SLAFB_CHECK(r < R, 101, r);
                 a.seg_start[o] = r;
                 a.seg_cell[o] = __ldg(a.cell + r);
             }
@@ -888,6 +908,7 @@ __device__ bool process_cell(const TokArgs &a, const WindowSink &wsnk, uint32_t 
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 if (flags & (1u << i)) {
+                    SLAFB_CHECK(off < (uint32_t)kChunkRows, 301, off);
                     sm.stage_gene[off] = (uint32_t)g[i];
                     if constexpr (SCGPT) sm.stage_val[off] = raw_bits(v[i]);
                     off++;
@@ -897,6 +918,7 @@ __device__ bool process_cell(const TokArgs &a, const WindowSink &wsnk, uint32_t 
             const uint32_t m = min(chunk_total, limit - base);
             if constexpr (SINK == 0) {
                 long long *ids = a.ids + row_base + 1 + base;
+                SLAFB_CHECK(out_row < a.n_cells && 1u + base + m <= L, 302, base + m);
                 for (uint32_t i = tid; i < m; i += kTokThreads) {
                     long long gid;
                     if constexpr (sizeof(GeneT) == 2) gid = (long long)sm.stage_gene[i];
@@ -1027,6 +1049,9 @@ __device__ __forceinline__ void fast_issue(const FastArgs &fa, uint32_t j, uint3
     const uint32_t v_bulk = (n_v && v_end > a0) ? v_end - a0 : 0u;
     d->s = s; d->e = e; d->c = c; d->a0 = a0;
     d->g_bulk = g_bulk; d->v_bulk = v_bulk; d->n_g = n_g; d->n_v = n_v;
+    SLAFB_CHECK(g_bulk <= fa.gcap && v_bulk <= fa.vcap, 201, g_bulk > fa.gcap ? g_bulk : v_bulk);
+    SLAFB_CHECK(a0 + max(g_bulk, v_bulk) <= a.n_rows && e <= a.n_rows && s <= e, 202, a0 + max(g_bulk, v_bulk));
+    SLAFB_CHECK(c < 0x7fffffffu && j < a.n_cells, 203, j);
     const uint32_t bytes = g_bulk * (uint32_t)sizeof(GeneT) + v_bulk * (uint32_t)sizeof(ValT);
     if (bytes == 0) {
         mbar_arrive(bar);
@@ -1164,6 +1189,7 @@ __global__ void __launch_bounds__(kFastThreads, 2048 / kFastThreads) tokenize_ce
                         const uint32_t key = key_of(x);
                         uint32_t h = (key * 2654435761u) >> (32 - kHashBits);
                         for (;;) {
+                            SLAFB_CHECK(h < (uint32_t)kHashSlots, 204, h);
                             uint32_t cur = vt[h];                   // plain read first: the common case is "already present"
                             if (cur == 0xffffffffu) {
                                 cur = atomicCAS(tab + h, 0xffffffffu, key);
@@ -1182,7 +1208,7 @@ __global__ void __launch_bounds__(kFastThreads, 2048 / kFastThreads) tokenize_ce
                 for (int w = 0; w < kFastWarps; w++) hi = max(hi, s_ws[kFastWarps + w]);
                 kmax = hi;
                 // log1p is monotone: max(log1pf(x)) = log1pf(max x).  Only warp 0 (the threshold search below) needs it.
-                if constexpr (BINNED) { if (warp == 0) m_f32 = log1pf_window(float_of_key(hi)); }
+                if constexpr (BINNED) { if (warp == (int)(it % (uint32_t)kFastWarps)) m_f32 = log1pf_window(float_of_key(hi)); }
                 if (do_hash) {
                     const uint32_t D = s_ws[0];
                     if (D <= cap) keep_all = true; else defer = true;            // D <= cap <= k distinct values: every row has rank <= k
@@ -1244,7 +1270,12 @@ __global__ void __launch_bounds__(kFastThreads, 2048 / kFastThreads) tokenize_ce
                     const uint32_t words = (range + 31u) >> 5;
                     for (uint32_t w = tid; w < words; w += kFastThreads) s_bitmap[w] = 0u;
                     __syncthreads();
+                    // Counts crowd into the few smallest values, so nearly every row of the cell wants one of the same handful of bits:
+                    // issued as shared-memory atomics they serialise on one address (thousands per cell).  The bits of the two lowest
+                    // words (values lo .. lo + 63) are therefore collected in registers and reduced over the warp -- two atomics per
+                    // warp -- and only the rare larger values go to the bitmap one by one.
                     volatile uint32_t *vb = s_bitmap;
+                    uint32_t m0 = 0u, m1 = 0u;
                     for (uint32_t gi = tid; gi < ngroups; gi += kFastThreads) {
                         const uint32_t r0 = a0 + gi * 8u;
                         const uint4 q = *reinterpret_cast<const uint4 *>(sv + gi * 8u);
@@ -1255,13 +1286,26 @@ __global__ void __launch_bounds__(kFastThreads, 2048 / kFastThreads) tokenize_ce
                             if (r >= s && r < s + d.n_v) {
                                 const uint32_t b = ((w4[i >> 1] >> ((i & 1) * 16)) & 0xffffu) - lo;
                                 const uint32_t bit = 1u << (b & 31u);
-                                if (!(vb[b >> 5] & bit)) atomicOr(&s_bitmap[b >> 5], bit);   // counts repeat: look before the atomic
+                                SLAFB_CHECK((b >> 5) < (uint32_t)kPctWords, 205, b);
+                                if (b < 32u) m0 |= bit;
+                                else if (b < 64u) m1 |= bit;
+                                else if (!(vb[b >> 5] & bit)) atomicOr(&s_bitmap[b >> 5], bit);   // look before the atomic
                             }
                         }
                     }
                     for (uint32_t r = s + d.n_v + tid; r < e; r += kFastThreads) {
                         const uint32_t b = (uint32_t)__ldg(value_g + r) - lo;
-                        atomicOr(&s_bitmap[b >> 5], 1u << (b & 31u));
+                        const uint32_t bit = 1u << (b & 31u);
+                        SLAFB_CHECK((b >> 5) < (uint32_t)kPctWords, 206, b);
+                        if (b < 32u) m0 |= bit;
+                        else if (b < 64u) m1 |= bit;
+                        else if (!(vb[b >> 5] & bit)) atomicOr(&s_bitmap[b >> 5], bit);
+                    }
+                    m0 = __reduce_or_sync(0xffffffffu, m0);
+                    m1 = __reduce_or_sync(0xffffffffu, m1);
+                    if (lane == 0) {
+                        if (m0) atomicOr(&s_bitmap[0], m0);
+                        if (m1) atomicOr(&s_bitmap[1], m1);      // (words >= `words` are never read: range <= 32 leaves m1 empty)
                     }
                     __syncthreads();
                     constexpr int WPT = kPctWords / kFastThreads;
@@ -1384,6 +1428,7 @@ __global__ void __launch_bounds__(kFastThreads, 2048 / kFastThreads) tokenize_ce
 #pragma unroll
                     for (int i = 0; i < 8; i++) {
                         if (flags & (1u << i)) {
+                            SLAFB_CHECK(off >= limit || sh + off < fa.gcap, 207, sh + off);
                             if (off < limit) sg[sh + off] = g[i];
                             off++;
                         }
@@ -1396,7 +1441,11 @@ __global__ void __launch_bounds__(kFastThreads, 2048 / kFastThreads) tokenize_ce
         }
 
         if (defer) {
-            if (tid == 0) a.work_list[atomicAdd(a.work_counters, 1u)] = j;   // exact k-th distinct value: general kernel
+            if (tid == 0) {                                                   // exact k-th distinct value: general kernel
+                const uint32_t wi = atomicAdd(a.work_counters, 1u);
+                SLAFB_CHECK(wi < a.n_cells, 208, wi);
+                a.work_list[wi] = j;
+            }
         } else {
             // ---- emission: token pairs (128-bit stores), value stream, PAD fill, mask, cell id
             const uint32_t n_emit = min(n_keep, limit);
@@ -1407,10 +1456,12 @@ __global__ void __launch_bounds__(kFastThreads, 2048 / kFastThreads) tokenize_ce
             if constexpr (BINNED && U16) vstar = __ldg(fa.vstar_table + kmax);
             if constexpr (BINNED && !U16) {
                 // The binned window followed by the tokenizer's float branch gives  token = (bin >= 1) ? top : PAD, and
-                // bin(x) = floor(log1pf(x) * n / m) is monotone in x: instead of one log1p per row, warp 0 finds the
-                // smallest float whose bin is >= 1 (32-ary search over the ordered key space, ~7 rounds) while the
-                // other warps already emit the gene stream; rows then need one compare each.
-                if (warp == 0) {
+                // bin(x) = floor(log1pf(x) * n / m) is monotone in x: instead of one log1p per row, ONE warp finds the
+                // smallest float whose bin is >= 1 (one round of 32 candidates around a closed-form guess, a 32-ary search
+                // only if that misses) while the other warps already emit the gene stream; rows then need one compare each.
+                // (the searching warp rotates with the cell: the double-precision log1p evaluations of the CTAs sharing an SM then
+                // spread over its four sub-partitions instead of all landing on warp 0's)
+                if (warp == (int)(it % (uint32_t)kFastWarps)) {
                     const float wb = (float)a.w_bins;
                     auto pred = [&](uint32_t c) -> bool {
                         const float lv = log1pf_window(float_of_key(c));
@@ -1461,15 +1512,18 @@ __global__ void __launch_bounds__(kFastThreads, 2048 / kFastThreads) tokenize_ce
             const uint32_t p_lo = (off + 2u) >> 1;                       // smallest p with t0 >= 1
             const uint32_t p_hi = n_emit >= 1u ? (n_emit - 1u + off) / 2u + 1u : 0u;   // one past the largest p with t0 + 1 <= n_emit
 #pragma unroll 2
+            SLAFB_CHECK(sh + n_emit <= fa.gcap && (!SCGPT || sh + n_emit <= fa.vcap), 209, sh + n_emit);
+            SLAFB_CHECK(j < a.n_cells && 2u * n_pairs <= L + 2u, 210, n_pairs);
             for (uint32_t p = p_lo + tid; p < p_hi; p += kFastThreads) {
                 const uint32_t gi = sh + 2u * p - off - 1u;              // stage index of token t0
+                SLAFB_CHECK(gi + 1u < fa.gcap && 2u * p + 1u - off < L, 211, gi);
                 long long x0, x1;
                 if constexpr (sizeof(GeneT) == 2) { x0 = (long long)sg[gi] + 4ll; x1 = (long long)sg[gi + 1] + 4ll; }
                 else { x0 = (long long)(int32_t)sg[gi] + 4ll; x1 = (long long)(int32_t)sg[gi + 1] + 4ll; }
                 store_pair(ids_al + 2u * p, x0, x1);
             }
             if constexpr (BINNED && !U16) {
-                __syncthreads();                                 // warp 0 has published the bin threshold
+                __syncthreads();                                 // the searching warp has published the bin threshold
                 vstar = s_xstar;
             }
             if constexpr (SCGPT) {
@@ -1495,6 +1549,7 @@ __global__ void __launch_bounds__(kFastThreads, 2048 / kFastThreads) tokenize_ce
             const uint32_t p_pad = (n_emit + 2u + off + 1u) >> 1;         // smallest p with t0 >= n_emit + 2
             const uint32_t p_full_end = (L + off) >> 1;                   // pairs whose second token is < L
             for (uint32_t p = p_pad + tid; p < p_full_end; p += kFastThreads) {
+                SLAFB_CHECK(2u * p + 1u - off < L && 2u * p >= off, 212, p);
                 store_pair(ids_al + 2u * p, 0ll, 0ll);
                 if constexpr (SCGPT) store_pair(vals_al + 2u * p, 0ll, 0ll);
             }
@@ -1596,24 +1651,29 @@ __device__ void bitonic_sort_asc_u64(unsigned long long *keys, uint32_t n) { bit
 // exchanges between a thread's own registers, strides below 32 * E are exchanged with another lane by warp shuffles, and only
 // the strides that cross warps go through shared memory (two barriers each).  For 4,096 keys that is 6 shared-memory steps
 // instead of 78 barrier-separated passes over shared memory.
+// Physical position of logical element i: one slot of padding after every 16 elements, so that a warp's accesses to
+// "element r of every thread" (stride E elements = up to 128 bytes) spread over all banks instead of hitting one.
+__device__ __forceinline__ uint32_t rk_phys(uint32_t i) { return i + (i >> 4); }
+constexpr int kRankSmemSlots = kRankSmemKeys + kRankSmemKeys / 16;
+
 template <int E>
 __device__ __forceinline__ void bitonic_sort_tiled(unsigned long long *sm) {
     constexpr uint32_t N = (uint32_t)E * kTokThreads;
     const uint32_t base = threadIdx.x * (uint32_t)E;
     unsigned long long v[E];
 #pragma unroll
-    for (int r = 0; r < E; r++) v[r] = sm[base + r];
+    for (int r = 0; r < E; r++) v[r] = sm[rk_phys(base + r)];
     for (uint32_t k = 2; k <= N; k <<= 1) {
         uint32_t j = k >> 1;
         for (; j >= (uint32_t)E * 32u; j >>= 1) {                       // partner in another warp
             __syncthreads();                                            // everyone has read what the previous step left in sm
 #pragma unroll
-            for (int r = 0; r < E; r++) sm[base + r] = v[r];
+            for (int r = 0; r < E; r++) sm[rk_phys(base + r)] = v[r];
             __syncthreads();
 #pragma unroll
             for (int r = 0; r < E; r++) {
                 const uint32_t i = base + r;
-                const unsigned long long pv = sm[i ^ j];
+                const unsigned long long pv = sm[rk_phys(i ^ j)];
                 const bool keep_min = (((i & j) == 0u) == ((i & k) == 0u));
                 v[r] = keep_min ? (pv < v[r] ? pv : v[r]) : (pv > v[r] ? pv : v[r]);
             }
@@ -1643,9 +1703,17 @@ __device__ __forceinline__ void bitonic_sort_tiled(unsigned long long *sm) {
             }
         }
     }
+    // back to the plain (unpadded) order the callers index: through the padded layout once more, then every thread moves the
+    // elements tid, tid + 256, ... (consecutive addresses on both sides)
     __syncthreads();
 #pragma unroll
-    for (int r = 0; r < E; r++) sm[base + r] = v[r];
+    for (int r = 0; r < E; r++) sm[rk_phys(base + r)] = v[r];
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < E; r++) v[r] = sm[rk_phys(threadIdx.x + (uint32_t)r * kTokThreads)];
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < E; r++) sm[threadIdx.x + (uint32_t)r * kTokThreads] = v[r];
     __syncthreads();
 }
 
@@ -1685,7 +1753,7 @@ __global__ void __launch_bounds__(kTokThreads) tokenize_rank_kernel(const RankAr
                     const uint32_t key = rank_key<GeneT, ValT>(ra, __ldg(gene + s + i), __ldg(value + s + i));
                     c = ((unsigned long long)(~key) << 32) | (unsigned long long)i;
                 }
-                keys[i] = c;
+                keys[rk_phys(i)] = c;
             }
             __syncthreads();
             switch (P / kTokThreads) {
@@ -1997,6 +2065,37 @@ __global__ void __launch_bounds__(256) gene_stats_kernel(const GeneT *__restrict
                 }
             }
         }
+    }
+}
+
+// K5, uint16 values: ONE 64-bit reduction per nonzero row instead of two -- the row's value in the upper 40 bits, a count of one in
+// the lower 24 -- into a per-context scratch vector, unpacked into the caller's sum / count vectors by a second, tiny kernel.
+// The host keeps a launch below 2^24 rows, so neither field can overflow (sum <= 65535 * (2^24 - 1) < 2^40).
+constexpr uint32_t kStatsRowsPerLaunch = (1u << 24) - 8u;       // multiple of 8: chunks keep the 16-byte alignment of the columns
+template <typename GeneT>
+__global__ void __launch_bounds__(256) gene_stats_packed_kernel(const GeneT *__restrict__ gene, const uint16_t *__restrict__ value,
+                                                                uint32_t n_rows, uint32_t n_genes, unsigned long long *packed) {
+    const uint32_t stride = gridDim.x * blockDim.x * kGroup;
+    for (uint32_t r0 = (blockIdx.x * blockDim.x + threadIdx.x) * kGroup; r0 < n_rows; r0 += stride) {
+        GeneT g[8];
+        uint16_t v[8];
+        load8(gene, r0, n_rows, g);
+        load8(value, r0, n_rows, v);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t gi = (uint32_t)g[i];
+            if (r0 + i < n_rows && gi < n_genes && v[i] != 0) atomicAdd(packed + gi, ((unsigned long long)v[i] << 24) | 1ull);
+        }
+    }
+}
+__global__ void gene_stats_unpack_kernel(unsigned long long *packed, uint32_t n_genes, unsigned long long *sum, unsigned long long *cnt) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_genes) return;
+    const unsigned long long p = packed[g];
+    if (p) {
+        sum[g] += p >> 24;
+        cnt[g] += p & 0xffffffull;
+        packed[g] = 0ull;
     }
 }
 

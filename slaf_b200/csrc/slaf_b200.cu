@@ -100,6 +100,8 @@ struct slafb_ctx {
     int vstar_nbins = -1;
     uint32_t *sort_scratch = nullptr;
     unsigned long long *rank_scratch = nullptr;   // rank-value extension: composites of very large cells (lazy)
+    unsigned long long *stats_packed = nullptr;   // gene statistics: packed (sum << 24 | count) reductions of one launch (lazy, grow-only)
+    size_t stats_genes = 0;
     unsigned long long *dup_table = nullptr;   // contiguity check (lazy, grow-only)
     size_t dup_slots = 0;
     // window facade scratch
@@ -318,7 +320,7 @@ int launch_general(slafb_ctx *ctx, const TokArgs &a, const WindowSink &w, cudaSt
 template <typename GeneT, typename ValT>
 int launch_rank(slafb_ctx *ctx, const RankArgs &ra, cudaStream_t st) {
     auto kern = tokenize_rank_kernel<GeneT, ValT>;
-    const size_t dyn = (size_t)kRankSmemKeys * sizeof(unsigned long long);
+    const size_t dyn = (size_t)kRankSmemSlots * sizeof(unsigned long long);
     static std::atomic<bool> attr_set[64];   // zero-initialised; setting the attribute twice is harmless
     if (!attr_set[ctx->device & 63].load(std::memory_order_acquire)) {
         CU(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
@@ -1034,7 +1036,7 @@ int slafb_destroy(slafb_ctx *ctx) {
         cudaEvent_t evs[] = {s.ev_front, s.ev_done, s.ev_in, s.ev_loaded, s.ev_perm, s.t_h2d0, s.t_h2d1, s.t_k1a, s.t_k1b, s.t_k2a, s.t_k2b, s.t_k2c};
         for (auto e : evs) if (e) cudaEventDestroy(e);
     }
-    cudaFree(ctx->tile_state); cudaFree(ctx->ticket); cudaFree(ctx->log1p_lut); cudaFree(ctx->vstar_table); cudaFree(ctx->sort_scratch); cudaFree(ctx->rank_scratch); cudaFree(ctx->dup_table);
+    cudaFree(ctx->tile_state); cudaFree(ctx->ticket); cudaFree(ctx->log1p_lut); cudaFree(ctx->vstar_table); cudaFree(ctx->sort_scratch); cudaFree(ctx->rank_scratch); cudaFree(ctx->dup_table); cudaFree(ctx->stats_packed);
     cudaFree(ctx->kept_count); cudaFree(ctx->total_dev);
     if (ctx->h_total) cudaFreeHost(ctx->h_total);
     if (ctx->ev_k1) cudaEventDestroy(ctx->ev_k1);
@@ -1450,6 +1452,29 @@ int slafb_gene_stats(slafb_ctx *ctx, const slafb_coo *in, int64_t n_genes, uint6
     const unsigned grid = (unsigned)ctx->n_sm * 8u;
     auto *usum = reinterpret_cast<unsigned long long *>(sum);
     auto *ucnt = reinterpret_cast<unsigned long long *>(cnt);
+    if (in->value_dtype == SLAFB_U16) {
+        // counts: one packed 64-bit reduction per nonzero row (kernels.cuh, K5), in launches of < 2^24 rows
+        if ((size_t)n_genes > ctx->stats_genes) {
+            if (ctx->stats_packed) CU(ctx, cudaFree(ctx->stats_packed));
+            ctx->stats_packed = nullptr; ctx->stats_genes = 0;
+            CU(ctx, cudaMalloc(&ctx->stats_packed, (size_t)n_genes * sizeof(unsigned long long)));
+            CU(ctx, cudaMemsetAsync(ctx->stats_packed, 0, (size_t)n_genes * sizeof(unsigned long long), st));
+            ctx->stats_genes = (size_t)n_genes;
+        }
+        const unsigned ublocks = (unsigned)((n_genes + 255) / 256);
+        for (int64_t lo = 0; lo < in->n_rows; lo += kStatsRowsPerLaunch) {
+            const uint32_t n = (uint32_t)(in->n_rows - lo < (int64_t)kStatsRowsPerLaunch ? in->n_rows - lo : (int64_t)kStatsRowsPerLaunch);
+            const uint16_t *val = static_cast<const uint16_t *>(in->value) + lo;
+            if (in->gene_dtype == SLAFB_U16)
+                gene_stats_packed_kernel<uint16_t><<<grid, 256, 0, st>>>(static_cast<const uint16_t *>(in->gene) + lo, val, n, (uint32_t)n_genes, ctx->stats_packed);
+            else
+                gene_stats_packed_kernel<int32_t><<<grid, 256, 0, st>>>(static_cast<const int32_t *>(in->gene) + lo, val, n, (uint32_t)n_genes, ctx->stats_packed);
+            gene_stats_unpack_kernel<<<ublocks, 256, 0, st>>>(ctx->stats_packed, (uint32_t)n_genes, usum, ucnt);
+            CU(ctx, cudaGetLastError());
+            ctx->acc.kernel_launches += 2;
+        }
+        return SLAFB_OK;
+    }
     DISPATCH_TYPES(in->gene_dtype, in->value_dtype,
                    (gene_stats_kernel<GeneT, ValT><<<grid, 256, 0, st>>>(static_cast<const GeneT *>(in->gene), static_cast<const ValT *>(in->value),
                                                                        (uint32_t)in->n_rows, (uint32_t)n_genes, usum, ucnt)));
@@ -1489,6 +1514,21 @@ int slafb_gene_median(slafb_ctx *ctx, const uint32_t *hist, int64_t n_genes, int
     CU(ctx, cudaGetLastError());
     ctx->acc.kernel_launches++;
     return SLAFB_OK;
+}
+
+int slafb_debug_check_failures(uint32_t *info) {
+#ifdef SLAFB_CHECKED
+    unsigned int h[8] = {0};
+    if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpyFromSymbol(h, slafb::g_check_fail, sizeof h) != cudaSuccess) {
+        cudaGetLastError();
+        return -2;
+    }
+    if (info) memcpy(info, h, sizeof h);
+    return (int)(h[0] > 0x7fffffffu ? 0x7fffffffu : h[0]);
+#else
+    (void)info;
+    return -1;      // not a checked build
+#endif
 }
 
 int slafb_set_option(slafb_ctx *ctx, int32_t option, int64_t value) {

@@ -116,6 +116,7 @@ class _Staged:
     pred: list | None = None         # [(cell id, rows), ...] of the cells predicted to stay incomplete, in row order; None = no prediction
     stash: dict | None = None        # the predicted partial_cell_data after this load
     reads: list | None = None        # mixture-of-scanners: the draw (generator, chunks, last cell before) the pieces were built from
+    mispredicted: bool = False       # the segment table contradicted ``pred`` (the look-ahead was repaired from the table)
 
 
 def _runs(cell: np.ndarray):
@@ -350,6 +351,7 @@ class PrefetchBatchProcessor:
         self._engine: HotPathEngine | None = None
         self._staging = _Staging(depth=3, threads=copy_threads)     # three: with the look-ahead two loads can be in flight while a third is assembled
         self._ahead: _Staged | BaseException | None = None
+        self._inject: list[_Staged] = []       # loads that have to run before ``_ahead`` (an epoch's late flush, see _restage_ahead)
         # the reference's tests (and users) call reset_for_epoch from the consumer thread while the prefetcher thread is inside
         # load_prefetch_batch (tests/test_pytorch_datasets.py:1064-1067); with batches in flight on the device those two must
         # not interleave
@@ -634,7 +636,11 @@ class PrefetchBatchProcessor:
         if self.tokenizer is None and not self.raw_mode:
             raise RuntimeError("Tokenizer is required for tokenized mode")
         while True:
-            cur, self._ahead = self._ahead, None
+            injected = bool(self._inject)
+            if injected:
+                cur = self._inject.pop(0)                      # the look-ahead (already staged, next epoch) keeps waiting behind it
+            else:
+                cur, self._ahead = self._ahead, None
             if cur is None:
                 cur = self._stage()
             if isinstance(cur, BaseException):                 # the end of the data, or an error met while reading ahead:
@@ -643,12 +649,14 @@ class PrefetchBatchProcessor:
                 continue
             if cur.slot is None:
                 self._submit_staged(cur)                       # deferred: the engine had to grow, nothing else is in flight now
-            if cur.pred is not None:
+            if cur.pred is not None and not injected:
                 try:
                     self._ahead = self._stage()                # the next load's rows go out before this one's table is awaited
                 except Exception as end:                       # StopIteration (last epoch done) or a reader error
                     self._ahead = end
             out = self._load_raw_device(cur) if self.raw_mode else self._load_fused(cur)
+            if injected and cur.stash and not cur.mispredicted:
+                self._inject.insert(0, self._flush_record(cur.stash, cur))     # cells this flush could not complete: the epoch's next flush
             if out is not None:
                 return out
 
@@ -760,13 +768,31 @@ class PrefetchBatchProcessor:
     def _drop_ahead(self) -> None:
         self._unsubmit_ahead()
         self._ahead = None
+        self._inject = []
 
-    def _restage_ahead(self, stash: dict) -> None:
-        """The prediction for the current load was wrong: rebuild the look-ahead from the true partial cells."""
+    def _flush_record(self, stash: dict, after: _Staged) -> _Staged:
+        """The end-of-data flush of ``stash`` as the load that follows ``after`` in ITS epoch (batch id, seed and epoch tag of the
+        synchronous feeder, datasets.py:660-668 + 1016).  The processor's reader state is left as it is."""
+        rec = _Staged(body=[], pieces=[p for p in stash.values() if len(p)], flush=True, batch_id=after.batch_id + 1, epoch=after.epoch,
+                      seed=self.seed + after.batch_id + 1 + after.epoch * 10000, start_time=time.time())
+        keep = self.partial_cell_data
+        self._predict(rec)                                      # (mixture of scanners: cells that still cannot complete wait for the next flush)
+        self.partial_cell_data = keep
+        return rec
+
+    def _restage_ahead(self, stash: dict, rec: _Staged) -> None:
+        """The prediction for the current load ``rec`` was wrong: rebuild the look-ahead from the true partial cells."""
         a = self._ahead
         if not isinstance(a, _Staged):
             self._ahead = None                                  # (an end-of-data marker is re-derived: pending cells get their flush load)
             self.partial_cell_data = stash
+            return
+        if a.epoch != rec.epoch:
+            # ``rec`` was predicted to close its epoch with nothing pending, so the look-ahead already opened the next epoch.  The
+            # cells that are pending after all get their own flush load in the OLD epoch -- what the synchronous feeder does --
+            # ahead of the look-ahead, which was built on "nothing pending" and stays as it is.
+            if stash:
+                self._inject.insert(0, self._flush_record(stash, rec))
             return
         if a.flush:
             pieces = list(stash.values())
@@ -869,12 +895,13 @@ class PrefetchBatchProcessor:
             bad = np.flatnonzero(~complete)
             as_predicted = bad.size == len(rec.pred) and [(int(seg_cell[j]), int(seg_len[j])) for j in bad] == rec.pred
             if not as_predicted:
+                rec.mispredicted = True
                 self._unsubmit_ahead()
                 keep = self.partial_cell_data
                 self._stash_partials(pieces, seg_start, seg_cell, complete)
                 rec.stash, true_stash = dict(self.partial_cell_data), self.partial_cell_data
                 self.partial_cell_data = keep
-                self._restage_ahead(true_stash)
+                self._restage_ahead(true_stash, rec)
         else:
             self._stash_partials(pieces, seg_start, seg_cell, complete)
             rec.stash = dict(self.partial_cell_data)

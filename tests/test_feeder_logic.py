@@ -492,3 +492,31 @@ def test_cell_start_index_is_the_default_route_and_falls_back_when_stale(stand_i
         got = _drain(stale)
     assert stale._csi_arr is None
     _same(ref, got)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+@pytest.mark.parametrize("which", [150, 68, 129, 165, N_CELLS - 1, "one_inside_every_batch"])     # (68, seeds 1 and 3) hit the epoch edge
+def test_misprediction_on_the_last_load_of_an_epoch_keeps_the_epoch(stand_in, monkeypatch, seed, which):
+    """The index overstates a cell, so the look-ahead predicts "nothing pending" where the table later shows a leftover.  When that
+    happens on the last load of an epoch the look-ahead has already opened the next epoch; the leftover must still be flushed as
+    its own load of the OLD epoch (epoch tag, batch id, seed and order of the synchronous feeder), not spliced into the new one."""
+    b = _data()
+    counts = np.diff(b.cell_start)
+    if which == "one_inside_every_batch":     # whatever the last load of the epoch is, it holds a cell the prediction cannot see
+        inner = {int(b.cell[r]) for r in range(400, b.n_rows, 1000) if b.cell[r - 30] != b.cell[r + 30]}
+        counts[sorted(inner)] += 5
+    else:
+        counts[which] += 5
+    csi = np.concatenate(([0], np.cumsum(counts)))
+    kw = dict(csi=csi, use_mixture_of_scanners=True, n_scanners=3, prefetch_batch_size=1000, n_epochs=3)
+    runs = []
+    for lookahead in (True, False):
+        proc = _proc(b, **kw)
+        if not lookahead:
+            monkeypatch.setattr(proc, "_lookahead_ok", lambda: False)
+        np.random.seed(seed)
+        runs.append(_drain(proc))
+    _same(*runs)
+    for ep in range(3):
+        ids = np.concatenate([x[2] for x in runs[0] if x[0] == ep]).tolist()
+        assert sorted(ids) == list(range(N_CELLS)), f"epoch {ep} is complete and clean"
