@@ -143,6 +143,13 @@ __device__ __forceinline__ void block_minmax(uint32_t &lo, uint32_t &hi, uint32_
     __syncthreads();
 }
 
+// x << n with PTX semantics: shift amounts >= 32 give 0 (the C operator leaves them undefined)
+__device__ __forceinline__ uint32_t shl_clamp(uint32_t x, uint32_t n) {
+    uint32_t r;
+    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(n));
+    return r;
+}
+
 // order-preserving 32-bit key of a value (dense rank compares keys)
 __device__ __forceinline__ uint32_t key_of(uint16_t v) { return (uint32_t)v; }
 __device__ __forceinline__ uint32_t key_of(float x) {
@@ -1064,8 +1071,13 @@ __device__ __forceinline__ void fast_issue(const FastArgs &fa, uint32_t j, uint3
 
 static_assert(kHashMaxDistinct + kFastThreads < kHashSlots, "the distinct-value set must never fill up");
 
+// CTAs per SM the register allocation is sized for: the uint16 count modes stage ~21-25 KB per CTA and run 8 per SM (32
+// registers per thread); float32 values and the percentile mode stage more (6 per SM fit), which leaves them 40 registers.
+template <typename ValT, int MODE>
+constexpr int fast_ctas_per_sm() { return (sizeof(ValT) == 4 || MODE == MODE_GF_PCT) ? (1536 / kFastThreads) : (2048 / kFastThreads); }
+
 template <typename GeneT, typename ValT, int MODE>
-__global__ void __launch_bounds__(kFastThreads, 2048 / kFastThreads) tokenize_cells_kernel(const FastArgs fa) {
+__global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm<ValT, MODE>()) tokenize_cells_kernel(const FastArgs fa) {
     constexpr bool SCGPT = (MODE == MODE_SCGPT_RAW || MODE == MODE_SCGPT_BINNED);
     constexpr bool BINNED = (MODE == MODE_SCGPT_BINNED);
     constexpr bool PCT = (MODE == MODE_GF_PCT);
@@ -1077,8 +1089,9 @@ __global__ void __launch_bounds__(kFastThreads, 2048 / kFastThreads) tokenize_ce
     __shared__ CellDesc s_desc[2];
     __shared__ uint32_t s_ws[3 * kFastWarps];
     __shared__ uint32_t s_xstar;      // float32 binned window: key of the smallest value whose bin is >= 1
-    __shared__ uint32_t s_bitmap[PCT ? kPctWords : 1];   // percentile mode: which values of [lo, lo + 8192) occur in the cell
+    __shared__ uint32_t s_bitmap[PCT ? kPctWords : 1];   // percentile mode: which values of [32, 8192) occur in the cell (bit = value)
     __shared__ uint32_t s_thr;        // percentile mode: the smallest value that is kept
+    __shared__ uint32_t s_dirty;      // percentile mode: the bitmap holds bits of the current cell (wiped when the cell is done)
     const TokArgs &a = fa.t;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t gbytes = fa.gcap * (uint32_t)sizeof(GeneT), vbytes = fa.vcap * (uint32_t)sizeof(ValT);
@@ -1092,7 +1105,9 @@ __global__ void __launch_bounds__(kFastThreads, 2048 / kFastThreads) tokenize_ce
         mbar_init(&s_bar[0], 1);
         mbar_init(&s_bar[1], 1);
         mbar_fence_init();
+        s_dirty = 0u;
     }
+    if constexpr (PCT) for (uint32_t w = tid; w < (uint32_t)kPctWords; w += kFastThreads) s_bitmap[w] = 0u;
     __syncthreads();
     // Rows are handed out IN ORDER by an atomic ticket (first row = blockIdx.x), so the rows being
     // written at any moment form one compact window of the output tensors -- measured 6.0 TB/s
@@ -1162,9 +1177,9 @@ __global__ void __launch_bounds__(kFastThreads, 2048 / kFastThreads) tokenize_ce
         // ---- statistics of the cell's values (range test for the dense-rank filter, max for the bins)
         bool keep_all = PCT ? false : (n <= k);    // the percentile rule also filters cells with few rows
         bool defer = false;
-        uint32_t kmax = 0, thr = 0;
+        uint32_t kmax = 0, thr = 0, dirty = 0;
         float m_f32 = 0.0f;
-        (void)thr;
+        (void)thr; (void)dirty;
         if constexpr (!U16) {
             // float32 values: ONE pass over the cell's values gives the maximum (for the bins) and, when the cell has more
             // rows than max_items, the exact number of distinct values through an open-addressing set in shared memory.
@@ -1182,24 +1197,52 @@ __global__ void __launch_bounds__(kFastThreads, 2048 / kFastThreads) tokenize_ce
                 volatile uint32_t *distinct = s_ws;
                 volatile uint32_t *vt = tab;
                 float xmax = -INFINITY;
-                for (uint32_t r = s + tid; r < e; r += kFastThreads) {
-                    const float x = (r < s + d.n_v) ? (float)sv[r - a0] : (float)__ldg(value_g + r);
-                    xmax = fmaxf(xmax, x);
-                    if (do_hash && *distinct <= cap) {
-                        const uint32_t key = key_of(x);
-                        uint32_t h = (key * 2654435761u) >> (32 - kHashBits);
-                        for (;;) {
-                            SLAFB_CHECK(h < (uint32_t)kHashSlots, 204, h);
-                            uint32_t cur = vt[h];                   // plain read first: the common case is "already present"
-                            if (cur == 0xffffffffu) {
-                                cur = atomicCAS(tab + h, 0xffffffffu, key);
-                                if (cur == 0xffffffffu) { atomicAdd(s_ws, 1u); break; }
+                uint32_t last = 0xffffffffu;                        // the key this thread probed last (the table's "empty" pattern, never a key)
+                bool hashing = do_hash;
+                // set membership is about equality only: the raw bits of x + 0.0f (which folds -0.0 into +0.0) serve as the key
+                auto probe = [&](float x) {
+                    const uint32_t key = __float_as_uint(x + 0.0f);
+                    if (key == last) return;                        // counts repeat: the same value again costs nothing
+                    last = key;
+                    uint32_t h = (key * 2654435761u) >> (32 - kHashBits);
+                    for (;;) {
+                        SLAFB_CHECK(h < (uint32_t)kHashSlots, 204, h);
+                        uint32_t cur = vt[h];                       // plain read first: the common case is "already present"
+                        if (cur == 0xffffffffu) {
+                            cur = atomicCAS(tab + h, 0xffffffffu, key);
+                            if (cur == 0xffffffffu) { atomicAdd(s_ws, 1u); break; }
+                        }
+                        if (cur == key) break;
+                        h = (h + 1u) & (uint32_t)(kHashSlots - 1);
+                        if (*distinct > cap) break;                 // the set will not decide any more: stop probing
+                    }
+                };
+                // staged rows: aligned groups of four (one 128-bit shared-memory load), ragged ends element by element
+                const uint32_t nst = d.n_v, nq = (sh + nst + 3u) >> 2;
+                const float4 *sv4 = reinterpret_cast<const float4 *>(sv);
+                for (uint32_t c = tid; c < nq; c += kFastThreads) {
+                    const float4 q = sv4[c];
+                    const uint32_t p0 = c << 2;
+                    if (hashing && *distinct > cap) hashing = false;        // decided (deferred): only the maximum is still needed
+                    if (p0 >= sh && p0 + 4u <= sh + nst) {
+                        xmax = fmaxf(fmaxf(xmax, fmaxf(q.x, q.y)), fmaxf(q.z, q.w));
+                        if (hashing) { probe(q.x); probe(q.y); probe(q.z); probe(q.w); }
+                    } else {
+                        const float x4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            const uint32_t pp = p0 + (uint32_t)i;
+                            if (pp >= sh && pp < sh + nst) {
+                                xmax = fmaxf(xmax, x4[i]);
+                                if (hashing) probe(x4[i]);
                             }
-                            if (cur == key) break;
-                            h = (h + 1u) & (uint32_t)(kHashSlots - 1);
-                            if (*distinct > cap) break;             // the set will not decide any more: stop probing
                         }
                     }
+                }
+                for (uint32_t r = s + nst + tid; r < e; r += kFastThreads) {    // rows beyond the stage: from global memory
+                    const float x = __ldg(value_g + r);
+                    xmax = fmaxf(xmax, x);
+                    if (hashing && *distinct <= cap) probe(x);
                 }
                 uint32_t hi = __reduce_max_sync(0xffffffffu, key_of(xmax));
                 if (lane == 0) s_ws[kFastWarps + warp] = hi;
@@ -1216,7 +1259,7 @@ __global__ void __launch_bounds__(kFastThreads, 2048 / kFastThreads) tokenize_ce
                 __syncthreads();                                                  // s_ws is reused by the next cell
             }
         }
-        if (U16 && (BINNED || !keep_all)) {
+        if (U16 && !PCT && (BINNED || !keep_all)) {
             uint32_t lo = 0xffffffffu, hi = 0u;
             const uint32_t ngroups = (sh + d.n_v + 7u) >> 3;
             for (uint32_t gi = tid; gi < ngroups; gi += kFastThreads) {
@@ -1259,92 +1302,7 @@ __global__ void __launch_bounds__(kFastThreads, 2048 / kFastThreads) tokenize_ce
                 hi = max(hi, s_ws[kFastWarps + w]);
             }
             kmax = hi;
-            if constexpr (PCT) {
-                // Percentile branch (aggregators.py:167-196): the filter needs the exact number of distinct values D and the
-                // a*-th smallest of them.  Counts live in a narrow range, so a presence bitmap over [lo, hi] in shared memory
-                // answers both from the staged values in one pass; a cell whose range exceeds the bitmap goes to the general kernel.
-                const uint32_t range = hi - lo + 1u;
-                if (range > (uint32_t)kPctBits) {
-                    defer = true;
-                } else {
-                    const uint32_t words = (range + 31u) >> 5;
-                    for (uint32_t w = tid; w < words; w += kFastThreads) s_bitmap[w] = 0u;
-                    __syncthreads();
-                    // Counts crowd into the few smallest values, so nearly every row of the cell wants one of the same handful of bits:
-                    // issued as shared-memory atomics they serialise on one address (thousands per cell).  The bits of the two lowest
-                    // words (values lo .. lo + 63) are therefore collected in registers and reduced over the warp -- two atomics per
-                    // warp -- and only the rare larger values go to the bitmap one by one.
-                    volatile uint32_t *vb = s_bitmap;
-                    uint32_t m0 = 0u, m1 = 0u;
-                    for (uint32_t gi = tid; gi < ngroups; gi += kFastThreads) {
-                        const uint32_t r0 = a0 + gi * 8u;
-                        const uint4 q = *reinterpret_cast<const uint4 *>(sv + gi * 8u);
-                        const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                        for (int i = 0; i < 8; i++) {
-                            const uint32_t r = r0 + i;
-                            if (r >= s && r < s + d.n_v) {
-                                const uint32_t b = ((w4[i >> 1] >> ((i & 1) * 16)) & 0xffffu) - lo;
-                                const uint32_t bit = 1u << (b & 31u);
-                                SLAFB_CHECK((b >> 5) < (uint32_t)kPctWords, 205, b);
-                                if (b < 32u) m0 |= bit;
-                                else if (b < 64u) m1 |= bit;
-                                else if (!(vb[b >> 5] & bit)) atomicOr(&s_bitmap[b >> 5], bit);   // look before the atomic
-                            }
-                        }
-                    }
-                    for (uint32_t r = s + d.n_v + tid; r < e; r += kFastThreads) {
-                        const uint32_t b = (uint32_t)__ldg(value_g + r) - lo;
-                        const uint32_t bit = 1u << (b & 31u);
-                        SLAFB_CHECK((b >> 5) < (uint32_t)kPctWords, 206, b);
-                        if (b < 32u) m0 |= bit;
-                        else if (b < 64u) m1 |= bit;
-                        else if (!(vb[b >> 5] & bit)) atomicOr(&s_bitmap[b >> 5], bit);
-                    }
-                    m0 = __reduce_or_sync(0xffffffffu, m0);
-                    m1 = __reduce_or_sync(0xffffffffu, m1);
-                    if (lane == 0) {
-                        if (m0) atomicOr(&s_bitmap[0], m0);
-                        if (m1) atomicOr(&s_bitmap[1], m1);      // (words >= `words` are never read: range <= 32 leaves m1 empty)
-                    }
-                    __syncthreads();
-                    constexpr int WPT = kPctWords / kFastThreads;
-                    uint32_t wv[WPT], pc = 0;
-#pragma unroll
-                    for (int q2 = 0; q2 < WPT; q2++) {
-                        const uint32_t w = (uint32_t)tid * WPT + q2;
-                        wv[q2] = w < words ? s_bitmap[w] : 0u;
-                        pc += __popc(wv[q2]);
-                    }
-                    const uint32_t inc = warp_incl_scan(pc);
-                    if (lane == 31) s_ws[warp] = inc;
-                    __syncthreads();
-                    uint32_t wbase = 0, D = 0;
-#pragma unroll
-                    for (int w2 = 0; w2 < kFastWarps; w2++) {
-                        const uint32_t t = s_ws[w2];
-                        if (w2 < warp) wbase += t;
-                        D += t;
-                    }
-                    const uint32_t astar = target_asc_rank(D, k, true, a.min_pct);
-                    uint32_t ex = wbase + inc - pc;
-                    if (astar > ex && astar <= ex + pc) {             // the a*-th distinct value lies in my words
-#pragma unroll
-                        for (int q2 = 0; q2 < WPT; q2++) {
-                            const uint32_t c = __popc(wv[q2]);
-                            if (astar > ex && astar <= ex + c) {
-                                uint32_t x = wv[q2];
-                                for (uint32_t i = ex + 1u; i < astar; i++) x &= x - 1u;   // drop the lower set bits
-                                s_thr = lo + (((uint32_t)tid * WPT + q2) << 5) + (uint32_t)(__ffs(x) - 1);
-                            }
-                            ex += c;
-                        }
-                    }
-                    __syncthreads();
-                    thr = s_thr;
-                    if (astar == 1u) keep_all = true;                 // every distinct value passes both rules
-                }
-            } else if (!keep_all) {
+            if (!keep_all) {
                 if (U16 && (hi - lo + 1u <= k)) {
                     keep_all = true;                                // at most k distinct values fit in [lo, hi]
                 } else if (U16 && k >= 8u) {
@@ -1370,12 +1328,178 @@ __global__ void __launch_bounds__(kFastThreads, 2048 / kFastThreads) tokenize_ce
         }
 
         uint32_t n_keep = n;
+        bool compacted = false;          // percentile mode: the kept genes were gathered into the value stage's memory
         if constexpr (PCT) {
-            if (!defer && !keep_all) {
-                // Row-order compaction of the genes whose value passes the threshold, IN PLACE in the gene stage: a chunk of
-                // 8 rows per thread is read into registers, one block scan gives the offsets, the kept genes are written back
-                // at or before the positions they were read from (later chunks are untouched).  The emission below then reads
-                // a dense gene list exactly as in the keep-everything case.
+            // Percentile branch (aggregators.py:167-196): the filter needs the exact number of distinct values D and the a*-th
+            // smallest of them.  ONE pass over the staged values gives the range and a presence mask: the values below 32 --
+            // nearly every row of count data -- are collected in a register and reduced over the warps, the rare larger ones
+            // set their bit in a shared-memory bitmap indexed by the value itself (a handful of atomics per cell); a value
+            // beyond the bitmap sends the cell to the general kernel.  Thread t owns the contiguous 4-row chunks
+            // [t * Q, (t + 1) * Q), so the compaction below needs a single block scan per cell.
+            const uint32_t nst = d.n_v;                                 // staged rows (== n unless the cell is longer than the stage)
+            const uint32_t nch = (sh + nst + 3u) >> 2;
+            const uint32_t Q = (nch + (uint32_t)kFastThreads - 1u) / (uint32_t)kFastThreads;
+            const uint2 *sv2 = reinterpret_cast<const uint2 *>(sv);
+            volatile uint32_t *vb = s_bitmap;
+            uint32_t mn2 = 0xffffffffu, mx2 = 0u, m0 = 0u, big = 0u;
+            auto one = [&](uint32_t v) {                                // a valid value
+                m0 |= shl_clamp(1u, v);
+                if (v >= 32u) {
+                    big = 1u;
+                    if (v < (uint32_t)kPctBits) {
+                        const uint32_t bit = 1u << (v & 31u);
+                        SLAFB_CHECK((v >> 5) < (uint32_t)kPctWords, 205, v);
+                        if (!(vb[v >> 5] & bit)) atomicOr(&s_bitmap[v >> 5], bit);      // look before the atomic
+                    }
+                }
+            };
+            for (uint32_t q = 0; q < Q; q++) {
+                const uint32_t c = (uint32_t)tid * Q + q;
+                if (c >= nch) break;
+                const uint2 w = sv2[c];
+                const uint32_t p0 = c << 2;
+                if (p0 >= sh && p0 + 4u <= sh + nst) {                  // whole chunk inside the cell
+                    mn2 = __vminu2(__vminu2(mn2, w.x), w.y);
+                    mx2 = __vmaxu2(__vmaxu2(mx2, w.x), w.y);
+                    m0 |= shl_clamp(1u, w.x & 0xffffu) | shl_clamp(1u, w.x >> 16) | shl_clamp(1u, w.y & 0xffffu) | shl_clamp(1u, w.y >> 16);
+                    if ((w.x | w.y) & 0xffe0ffe0u) {                    // rare: a value >= 32
+                        const uint32_t v4[4] = {w.x & 0xffffu, w.x >> 16, w.y & 0xffffu, w.y >> 16};
+#pragma unroll
+                        for (int i = 0; i < 4; i++) if (v4[i] >= 32u) one(v4[i]);
+                    }
+                } else {
+                    const uint32_t v4[4] = {w.x & 0xffffu, w.x >> 16, w.y & 0xffffu, w.y >> 16};
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const uint32_t pp = p0 + (uint32_t)i;
+                        if (pp >= sh && pp < sh + nst) {
+                            mn2 = __vminu2(mn2, v4[i] | (v4[i] << 16));
+                            mx2 = __vmaxu2(mx2, v4[i] | (v4[i] << 16));
+                            one(v4[i]);
+                        }
+                    }
+                }
+            }
+            for (uint32_t r = s + nst + tid; r < e; r += kFastThreads) {        // rows beyond the stage: from global memory
+                const uint32_t v = (uint32_t)__ldg(value_g + r);
+                mn2 = __vminu2(mn2, v | (v << 16));
+                mx2 = __vmaxu2(mx2, v | (v << 16));
+                one(v);
+            }
+            uint32_t lo = __reduce_min_sync(0xffffffffu, min(mn2 & 0xffffu, mn2 >> 16));
+            uint32_t hi = __reduce_max_sync(0xffffffffu, max(mx2 & 0xffffu, mx2 >> 16));
+            m0 = __reduce_or_sync(0xffffffffu, m0);
+            big = __reduce_or_sync(0xffffffffu, big);
+            if (lane == 0) { s_ws[warp] = lo; s_ws[kFastWarps + warp] = hi; s_ws[2 * kFastWarps + warp] = m0; if (big) s_dirty = 1u; }
+            __syncthreads();
+            m0 = 0u;
+#pragma unroll
+            for (int w = 0; w < kFastWarps; w++) {
+                lo = min(lo, s_ws[w]);
+                hi = max(hi, s_ws[kFastWarps + w]);
+                m0 |= s_ws[2 * kFastWarps + w];
+            }
+            kmax = hi;
+            dirty = s_dirty;                                            // uniform; the bitmap is wiped at the end of the iteration
+            (void)lo;
+            if (hi >= (uint32_t)kPctBits) {
+                defer = true;
+            } else {
+                const uint32_t d0 = __popc(m0);                         // distinct values below 32
+                uint32_t D = d0, pc = 0, wv = 0, inc = 0, wbase = 0;
+                if (dirty) {                                            // some value >= 32: count the bitmap's words 1 .. hi / 32
+                    static_assert(kPctWords <= kFastThreads, "one bitmap word per thread");
+                    wv = ((uint32_t)tid >= 1u && (uint32_t)tid <= (hi >> 5)) ? s_bitmap[tid] : 0u;
+                    pc = __popc(wv);
+                    inc = warp_incl_scan(pc);
+                    __syncthreads();                                    // (everyone has read lo / hi / m0 from the scratch)
+                    if (lane == 31) s_ws[warp] = inc;
+                    __syncthreads();
+#pragma unroll
+                    for (int w2 = 0; w2 < kFastWarps; w2++) {
+                        const uint32_t t = s_ws[w2];
+                        if (w2 < warp) wbase += t;
+                        D += t;
+                    }
+                }
+                const uint32_t astar = target_asc_rank(D, k, true, a.min_pct);
+                if (astar <= d0) {                                      // the usual case: the threshold is one of the small values
+                    uint32_t x = m0;
+                    for (uint32_t i = 1u; i < astar; i++) x &= x - 1u;  // drop the lower set bits (astar is small: a percentile of D)
+                    thr = (uint32_t)(__ffs(x) - 1);
+                } else {                                                // it lies in the bitmap: the (astar - d0)-th set bit of words >= 1
+                    const uint32_t want = astar - d0, ex = wbase + inc - pc;
+                    if (want > ex && want <= ex + pc) {
+                        uint32_t x = wv;
+                        for (uint32_t i = ex + 1u; i < want; i++) x &= x - 1u;
+                        s_thr = ((uint32_t)tid << 5) + (uint32_t)(__ffs(x) - 1);
+                    }
+                    __syncthreads();
+                    thr = s_thr;
+                }
+                if (astar == 1u) keep_all = true;                       // every distinct value passes both rules
+            }
+            if (!defer && !keep_all && nst == n && limit * (uint32_t)sizeof(GeneT) <= vbytes) {
+                // Row-order compaction, whole cell staged: flags from the values (phase A), ONE block scan, then every thread gathers
+                // the kept genes of its own rows into the value stage's memory (phase B; the values are not needed any more and
+                // everybody finished reading them before the scan's barrier).  The emission then reads a dense gene list from there.
+                const uint32_t thr2 = thr | (thr << 16);
+                uint32_t fl = 0u;                                       // 4 bits per chunk, Q <= 4 chunks
+                for (uint32_t q = 0; q < Q; q++) {
+                    const uint32_t c = (uint32_t)tid * Q + q;
+                    if (c >= nch) break;
+                    const uint2 w = sv2[c];
+                    const uint32_t p0 = c << 2;
+                    const uint32_t cx = __vcmpgeu2(w.x, thr2), cy = __vcmpgeu2(w.y, thr2);     // 0xffff per half that passes
+                    uint32_t f4 = (cx & 1u) | ((cx >> 15) & 2u) | ((cy & 1u) << 2) | ((cy >> 13) & 8u);
+                    if (!(p0 >= sh && p0 + 4u <= sh + n)) {             // ragged ends: rows outside the cell do not count
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            const uint32_t pp = p0 + (uint32_t)i;
+                            if (!(pp >= sh && pp < sh + n)) f4 &= ~(1u << i);
+                        }
+                    }
+                    fl |= f4 << (4u * q);
+                }
+                const uint32_t pc = __popc(fl), inc = warp_incl_scan(pc);
+                __syncthreads();                                        // the scratch is free, and every thread has read its values
+                if (lane == 31) s_ws[warp] = inc;
+                __syncthreads();
+                uint32_t wbase = 0, tot = 0;
+#pragma unroll
+                for (int w2 = 0; w2 < kFastWarps; w2++) {
+                    const uint32_t t = s_ws[w2];
+                    if (w2 < warp) wbase += t;
+                    tot += t;
+                }
+                uint32_t off = wbase + inc - pc;
+                GeneT *dst = reinterpret_cast<GeneT *>(sv);
+                for (uint32_t q = 0; q < Q && fl; q++) {
+                    const uint32_t c = (uint32_t)tid * Q + q, f4 = (fl >> (4u * q)) & 15u;
+                    if (!f4) continue;
+                    GeneT g4[4];
+                    if constexpr (sizeof(GeneT) == 2) {
+                        const uint2 gq = reinterpret_cast<const uint2 *>(sg)[c];
+                        g4[0] = (GeneT)(gq.x & 0xffffu); g4[1] = (GeneT)(gq.x >> 16); g4[2] = (GeneT)(gq.y & 0xffffu); g4[3] = (GeneT)(gq.y >> 16);
+                    } else {
+                        const uint4 gq = reinterpret_cast<const uint4 *>(sg)[c];
+                        g4[0] = (GeneT)gq.x; g4[1] = (GeneT)gq.y; g4[2] = (GeneT)gq.z; g4[3] = (GeneT)gq.w;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        if (f4 & (1u << i)) {
+                            SLAFB_CHECK(off >= limit || (off + 1u) * sizeof(GeneT) <= vbytes, 207, off);
+                            if (off < limit) dst[off] = g4[i];
+                            off++;
+                        }
+                    }
+                }
+                n_keep = tot;
+                compacted = true;
+                __syncthreads();                                        // the gathered list is complete
+            } else if (!defer && !keep_all) {
+                // a cell longer than the stages: chunks of 8 rows per thread, rows beyond the stages from global memory, kept
+                // genes written back IN PLACE in the gene stage at or before the positions they were read from
                 const uint32_t staged = min(d.n_g, d.n_v);            // rows [s, s + staged) lie in both stages
                 const uint32_t ng_all = (sh + n + 7u) >> 3;
                 uint32_t base = 0;
@@ -1449,6 +1573,8 @@ __global__ void __launch_bounds__(kFastThreads, 2048 / kFastThreads) tokenize_ce
         } else {
             // ---- emission: token pairs (128-bit stores), value stream, PAD fill, mask, cell id
             const uint32_t n_emit = min(n_keep, limit);
+            const GeneT *sge = compacted ? reinterpret_cast<const GeneT *>(sv) : sg;      // where the genes to emit start
+            const uint32_t she = compacted ? 0u : sh;
             const size_t A = (size_t)j * L;
             double m_f64 = 0.0;
             uint32_t vstar = 0xffffffffu;
@@ -1486,12 +1612,13 @@ __global__ void __launch_bounds__(kFastThreads, 2048 / kFastThreads) tokenize_ce
                     if (lane == 0) s_xstar = xs;
                 }
             }
-            (void)m_f64; (void)top; (void)vstar;
+            float xstar_f = 0.0f;
+            (void)m_f64; (void)top; (void)vstar; (void)xstar_f;
             auto id_tok = [&](long long t) -> long long {
                 if (t == 0) return 1ll;                                        // CLS
                 if (t <= (long long)n_emit) {
-                    if constexpr (sizeof(GeneT) == 2) return (long long)sg[sh + (uint32_t)t - 1u] + 4ll;
-                    else return (long long)(int32_t)sg[sh + (uint32_t)t - 1u] + 4ll;
+                    if constexpr (sizeof(GeneT) == 2) return (long long)sge[she + (uint32_t)t - 1u] + 4ll;
+                    else return (long long)(int32_t)sge[she + (uint32_t)t - 1u] + 4ll;
                 }
                 return (t == (long long)n_emit + 1) ? 2ll : 0ll;               // SEP, then PAD
             };
@@ -1499,7 +1626,7 @@ __global__ void __launch_bounds__(kFastThreads, 2048 / kFastThreads) tokenize_ce
                 if (t < 1 || t > (long long)n_emit) return 0ll;
                 const ValT x = sv[sh + (uint32_t)t - 1u];
                 if constexpr (BINNED && U16) return ((uint32_t)x >= vstar) ? top : 0ll;
-                else if constexpr (BINNED) return (key_of(x) >= vstar) ? top : 0ll;      // vstar = s_xstar, loaded after the barrier below
+                else if constexpr (BINNED) return ((float)x >= xstar_f) ? top : 0ll;     // xstar_f: set after the barrier below
                 else return value_token<ValT, MODE>(raw_bits(x), a, m_f64, m_f32);
             };
             // Token t of the row lives at flat index A + t.  Pairs are 16-byte aligned in the flat
@@ -1512,19 +1639,22 @@ __global__ void __launch_bounds__(kFastThreads, 2048 / kFastThreads) tokenize_ce
             const uint32_t p_lo = (off + 2u) >> 1;                       // smallest p with t0 >= 1
             const uint32_t p_hi = n_emit >= 1u ? (n_emit - 1u + off) / 2u + 1u : 0u;   // one past the largest p with t0 + 1 <= n_emit
 #pragma unroll 2
-            SLAFB_CHECK(sh + n_emit <= fa.gcap && (!SCGPT || sh + n_emit <= fa.vcap), 209, sh + n_emit);
+            SLAFB_CHECK(compacted || (sh + n_emit <= fa.gcap && (!SCGPT || sh + n_emit <= fa.vcap)), 209, sh + n_emit);
             SLAFB_CHECK(j < a.n_cells && 2u * n_pairs <= L + 2u, 210, n_pairs);
             for (uint32_t p = p_lo + tid; p < p_hi; p += kFastThreads) {
-                const uint32_t gi = sh + 2u * p - off - 1u;              // stage index of token t0
-                SLAFB_CHECK(gi + 1u < fa.gcap && 2u * p + 1u - off < L, 211, gi);
+                const uint32_t gi = she + 2u * p - off - 1u;             // stage index of token t0
+                SLAFB_CHECK((compacted || gi + 1u < fa.gcap) && 2u * p + 1u - off < L, 211, gi);
                 long long x0, x1;
-                if constexpr (sizeof(GeneT) == 2) { x0 = (long long)sg[gi] + 4ll; x1 = (long long)sg[gi + 1] + 4ll; }
-                else { x0 = (long long)(int32_t)sg[gi] + 4ll; x1 = (long long)(int32_t)sg[gi + 1] + 4ll; }
+                if constexpr (sizeof(GeneT) == 2) { x0 = (long long)sge[gi] + 4ll; x1 = (long long)sge[gi + 1] + 4ll; }
+                else { x0 = (long long)(int32_t)sge[gi] + 4ll; x1 = (long long)(int32_t)sge[gi + 1] + 4ll; }
                 store_pair(ids_al + 2u * p, x0, x1);
             }
             if constexpr (BINNED && !U16) {
                 __syncthreads();                                 // the searching warp has published the bin threshold
                 vstar = s_xstar;
+                // keys order like the floats they encode, so the rows compare as floats (one instruction instead of the key
+                // transform); "no value reaches bin 1" (key 0xffffffff) decodes to a NaN, which compares false as it must
+                xstar_f = float_of_key(vstar);
             }
             if constexpr (SCGPT) {
                 // the value stream second: the bin-threshold load above has landed by now
@@ -1536,8 +1666,8 @@ __global__ void __launch_bounds__(kFastThreads, 2048 / kFastThreads) tokenize_ce
                         y0 = ((uint32_t)sv[gi] >= vstar) ? top : 0ll;
                         y1 = ((uint32_t)sv[gi + 1] >= vstar) ? top : 0ll;
                     } else if constexpr (BINNED) {
-                        y0 = (key_of(sv[gi]) >= vstar) ? top : 0ll;
-                        y1 = (key_of(sv[gi + 1]) >= vstar) ? top : 0ll;
+                        y0 = ((float)sv[gi] >= xstar_f) ? top : 0ll;
+                        y1 = ((float)sv[gi + 1] >= xstar_f) ? top : 0ll;
                     } else {
                         y0 = value_token<ValT, MODE>(raw_bits(sv[gi]), a, m_f64, m_f32);
                         y1 = value_token<ValT, MODE>(raw_bits(sv[gi + 1]), a, m_f64, m_f32);
@@ -1582,6 +1712,12 @@ __global__ void __launch_bounds__(kFastThreads, 2048 / kFastThreads) tokenize_ce
             if (tid == 0) {
                 const uint32_t cid = __ldg(a.seg_cell + d.c);
                 a.cell_ids[j] = a.cell_signed ? (long long)(int32_t)cid : (long long)cid;
+            }
+        }
+        if constexpr (PCT) {
+            if (dirty) {                                // (uniform) the next cell starts from an empty bitmap again
+                for (uint32_t w = tid; w < (uint32_t)kPctWords; w += kFastThreads) s_bitmap[w] = 0u;
+                if (tid == 0) s_dirty = 0u;
             }
         }
         __syncthreads();   // every thread is done with stage `st` and the scratch before they are reused

@@ -281,6 +281,7 @@ int launch_fast(slafb_ctx *ctx, const TokArgs &a, cudaStream_t st, bool *launche
         const long v = atol(env);
         if (v >= 1 && v <= 32) per_sm_max = (size_t)v;
     }
+    if (per_sm_max > (size_t)fast_ctas_per_sm<ValT, MODE>()) per_sm_max = (size_t)fast_ctas_per_sm<ValT, MODE>();   // what the registers allow
     if (per_sm > per_sm_max) per_sm = per_sm_max;
     if (per_sm < 1) per_sm = 1;
     uint32_t grid = (uint32_t)(ctx->n_sm * per_sm);
