@@ -567,6 +567,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-loader", action="store_true")
+    ap.add_argument("--no-packed", action="store_true", help="skip the packed-rows leg of e2e")
     ap.add_argument("--verify-cells", type=int, default=2048)
     ap.add_argument("--sharded", action="store_true", help="config 3 as the reference shards it: one table in /dev/shm, every rank reads its fragment range through the loader")
     ap.add_argument("--table-cells", type=int, default=1 << 20, help="--sharded: cells of the table")
@@ -855,6 +856,48 @@ def main():
                             "h2d_copy_gbs": (h2d_bytes * tme["timed_batches"] / max(1, tme["batches"]) / (tme["h2d_ms"] / 1e3) / 1e9) if tme["h2d_ms"] else None,
                             "route": "the reference's COO contract: all three columns cross the bus (8 B/row), K1 builds the segment table on the device"}
         eng.set_timing_interval(0)
+
+        # ---- packed wire format: the batches packed ONCE (as a converter / ingest step would), ~2 B per row on the bus
+        if args.value_dtype == "uint16" and not w.get("rank_norm") and not args.no_packed:
+            from slaf_b200.engine import pack_rows
+
+            stage("e2e: packed rows (f4)")
+            packed, pack_s, pack_in = [], 0.0, 0
+            for b in batches:
+                ids_b = b.cell[b.cell_start[:-1]]
+                t0p = time.perf_counter()
+                packed.append(pack_rows(b.gene, b.value, b.cell_start, ids_b, pin=True))
+                pack_s += time.perf_counter() - t0p
+                pack_in += b.n_rows * (gbytes + vbytes)
+            in_packed = [PreparedInput([pk]) for pk in packed]
+            pa = eng.collect(eng.submit_packed([packed[0]], shuffle_seed=7), shuffle_seed=7, **kw)
+            pb = eng.collect(eng.submit(*host_cols[0], shuffle_seed=7), shuffle_seed=7, **kw)
+            pairs = [(pa.input_ids, pb.input_ids), (pa.attention_mask, pb.attention_mask), (pa.cell_ids, pb.cell_ids)] + ([(pa.values, pb.values)] if pa.values is not None else [])
+            if not all(torch.equal(x, y) for x, y in pairs):
+                raise SystemExit("PARITY FAILURE: packed route differs from the COO route")
+            del pa, pb, pairs
+            eng.set_timing_interval(8)
+            cells_p, dtp, _, d2h_p, _, tmp_ = timed(in_packed, e2e_warm, e2e_steps, True, wall=True)
+            eng.set_timing_interval(0)
+            pk_bytes = sum(packed[i % NB].nbytes + 12 * cps + 8 for i in range(e2e_steps))
+            # the same packed blocks resident in HBM: what the decoding kernel itself sustains
+            dev_packed = []
+            for pk in packed:
+                from slaf_b200.engine import PackedRows
+
+                dev_packed.append(PreparedInput([PackedRows(torch.from_numpy(np.asarray(pk.bytes)).to(dev), pk.blk_off, pk.row_start, pk.seg_cell, pk.gene_dtype)]))
+            cells_pd, sec_pd, _, _, _, _ = timed(dev_packed, 3, max(12, min(args.steps, 40)), False, wall=False)
+            e2e["packed_route"] = {"value": sum_over_ranks(cells_p) / dtp, "unit": "cells/s", "h2d_bytes_per_step": pk_bytes // e2e_steps,
+                                   "d2h_bytes_per_step": d2h_p // e2e_steps, "ms_per_step": 1000.0 * dtp / e2e_steps, "h2d_gbs_per_gpu": pk_bytes / dtp / 1e9,
+                                   "bytes_per_row": sum(pk.nbytes for pk in packed) / sum(tot_rows),
+                                   "device_resident_cells_per_s": sum_over_ranks(cells_pd) / sec_pd,
+                                   "packer": {"gbs_of_input_per_core": pack_in / pack_s / 1e9, "rows_per_s_per_core": sum(tot_rows) / pack_s,
+                                              "note": "slafb_pack_rows, one thread, gene + value columns in, blocks out; run once per batch here "
+                                                      "(a converter / ingest step), NOT inside the timed region"},
+                                   "route": "packed wire format (include/slaf_b200.h): one block per cell, byte deltas of the ascending gene ids + byte "
+                                            "values + exception lists, decoded in the tokenizing kernel's shared-memory stage; outputs identical to "
+                                            "the COO route (checked in this run)"}
+            del dev_packed, in_packed, packed
 
         if not args.no_loader and not w.get("rank_norm"):
             stage("loader")

@@ -203,6 +203,41 @@ int slafb_submit_csi(slafb_ctx *ctx, const slafb_coo *pieces, int32_t n_pieces, 
 int slafb_csi_segments(const slafb_coo *pieces, int32_t n_pieces, const int64_t *row_lo, const int64_t *csi, int64_t n_csi,
                        int32_t check, uint32_t *seg_start, uint32_t *seg_cell, int64_t capacity_cells, int64_t *n_cells);
 
+/* ---- packed wire format (bytes not sent) -----------------------------------------------------------------
+ * End to end the path is bound by PCIe.  The expression table's rows are cell-major with gene ids ascending inside a cell and
+ * small integer values (slaf/data/converter.py:2819,3025), so a cell's rows pack losslessly into ~2 bytes per row: one 16-byte
+ * aligned block per cell = header {u32 n_rows, u32 gene id of row 0, u32 n_exc_g, u32 n_exc_v} | n_rows bytes min(delta, 255),
+ * delta_i = gene_i - gene_{i-1} - 1, zero-padded to 16 | n_rows bytes min(value, 255), padded | {u32 row, u32 delta} per delta >= 255
+ * | {u32 row, u32 value} per value >= 255 | padding to 16 (full description: csrc/pack_rows.h).  blk_off[n_cells + 1] holds the block
+ * offsets in 16-byte units.  Packing costs host cycles once (at conversion time, or in a feeder with cores to spare); every epoch then
+ * ships half of the cell-start-index route's bytes and a quarter of the COO route's, and the tokenizing kernel decodes the blocks inside
+ * its shared-memory stage.  uint16 values only (float32 tables travel unpacked).  Token tensors are identical to the other routes. */
+typedef struct {
+    const void *bytes;         /* the blocks, 16-byte aligned (host: pinned for async DMA; or device) */
+    int64_t n_bytes;           /* multiple of 16 */
+    const uint32_t *blk_off;   /* HOST [n_cells + 1]: block offsets in 16-byte units, relative to `bytes` */
+    const uint32_t *row_start; /* HOST [n_cells + 1]: row offsets of the cells (only the differences are used) */
+    int64_t n_cells;
+    int32_t location;          /* slafb_location of `bytes` */
+    int32_t gene_dtype;        /* what the gene ids decode to: SLAFB_U16 (n_genes <= 65536) | SLAFB_I32 */
+} slafb_packed;
+/* Upper bound of the packed size for typical count data (room for one exception per 16 rows); pack_rows reports SLAFB_ERR_CAPACITY
+ * if a batch needs more. */
+int64_t slafb_pack_bound(int64_t n_rows, int64_t n_cells);
+/* Host only, single threaded (callers pack disjoint cell ranges in parallel and submit them as pieces): packs the cells whose rows
+ * are gene[row_start[c] .. row_start[c + 1]) / value[...] into `out`.  SLAFB_ERR_INVALID when some cell's gene ids do not ascend
+ * strictly (such rows travel unpacked). */
+int slafb_pack_rows(const void *gene, int32_t gene_dtype, const uint16_t *value, const uint32_t *row_start, int64_t n_cells, uint8_t *out,
+                    int64_t out_capacity, uint32_t *blk_off, int64_t *out_bytes);
+/* Host only: the exact inverse (tests; callers that want the columns back). */
+int slafb_unpack_rows(const uint8_t *packed, const uint32_t *blk_off, const uint32_t *row_start, int64_t n_cells, void *gene, int32_t gene_dtype,
+                      uint16_t *value);
+/* submit() for packed rows: the pieces' blocks are copied back to back, seg_cell[sum of n_cells] (host) are the cell ids in block
+ * order; the cell boundaries are the blocks themselves, so no cell column travels and no CSR build runs (as with submit_segments).
+ * collect() tokenizes the slot exactly like any other; collect_csr / the rank-value extension take unpacked rows. */
+int slafb_submit_packed(slafb_ctx *ctx, const slafb_packed *pieces, int32_t n_pieces, const uint32_t *seg_cell, int32_t cell_dtype,
+                        void *stream, int32_t *slot);
+
 /* Blocks until the H2D copy of the batch last submitted into `slot` has finished: its host columns may be reused. */
 int slafb_wait_loaded(slafb_ctx *ctx, int32_t slot);
 
@@ -232,6 +267,8 @@ typedef struct {
 int slafb_pipe_create(slafb_ctx *ctx, const slafb_params *p, const slafb_out *ring, int32_t n_ring, int32_t depth, slafb_pipe **pipe);
 int slafb_pipe_push(slafb_pipe *pipe, const slafb_coo *pieces, int32_t n_pieces, const uint32_t *seg_start, const uint32_t *seg_cell,
                     int64_t n_seg_cells, int64_t seed, void *stream, slafb_pipe_result *done);
+int slafb_pipe_push_packed(slafb_pipe *pipe, const slafb_packed *pieces, int32_t n_pieces, const uint32_t *seg_cell, int32_t cell_dtype,
+                           int64_t seed, void *stream, slafb_pipe_result *done);
 int slafb_pipe_pop(slafb_pipe *pipe, void *stream, slafb_pipe_result *done);
 int slafb_pipe_destroy(slafb_pipe *pipe);
 

@@ -14,7 +14,8 @@ from collections import defaultdict
 src_csv, kname = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-so = os.path.join(root, "slaf_b200", "_lib", "libslaf_b200.so")
+so = os.environ.get("SLAFB_SO") or os.path.join(root, "slaf_b200", "_lib", "libslaf_b200.so")
+src_dir = os.environ.get("SLAFB_SRC") or os.path.join(root, "slaf_b200", "csrc")
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, check=True, capture_output=True)
 cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
@@ -54,7 +55,7 @@ src_cache = {}
 def text(loc):
     if loc is None: return ""
     f, l = loc
-    for cand in (os.path.join(root, "slaf_b200", "csrc", f),):
+    for cand in (os.path.join(src_dir, f),):
         if os.path.exists(cand):
             if cand not in src_cache: src_cache[cand] = open(cand).read().splitlines()
             return src_cache[cand][l - 1].strip()[:100]

@@ -17,7 +17,7 @@ from ctypes import POINTER, Structure, byref, c_char_p, c_double, c_int, c_int32
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("SLAFB_LIB") or os.path.join(_HERE, "_lib", "libslaf_b200.so")   # SLAFB_LIB: A/B builds
-SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("slaf_b200.cu", "kernels.cuh", "py_shuffle.h")]
+SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("slaf_b200.cu", "kernels.cuh", "py_shuffle.h", "pack_rows.h")]
 HEADER = os.path.join(_ROOT, "include", "slaf_b200.h")
 
 # slafb_status
@@ -38,6 +38,7 @@ EXPORTS = [
     "slafb_collect", "slafb_collect_csr", "slafb_prepare_shuffle", "slafb_segments", "slafb_window", "slafb_tokenize_lists", "slafb_shuffle_perm", "slafb_gene_stats", "slafb_gene_hist", "slafb_gene_median",
     "slafb_host_alloc", "slafb_host_free", "slafb_get_timing", "slafb_set_option",
     "slafb_submit_csi", "slafb_csi_segments", "slafb_wait_loaded", "slafb_pipe_create", "slafb_pipe_push", "slafb_pipe_pop", "slafb_pipe_destroy", "slafb_debug_check_failures",
+    "slafb_pack_bound", "slafb_pack_rows", "slafb_unpack_rows", "slafb_submit_packed", "slafb_pipe_push_packed",
 ]
 
 
@@ -62,6 +63,11 @@ class Out(Structure):
         ("input_ids", c_void_p), ("attention_mask", c_void_p), ("values", c_void_p), ("cell_ids", c_void_p),
         ("capacity_cells", c_int64),
     ]
+
+
+class Packed(Structure):
+    _fields_ = [("bytes", c_void_p), ("n_bytes", c_int64), ("blk_off", c_void_p), ("row_start", c_void_p), ("n_cells", c_int64),
+                ("location", c_int32), ("gene_dtype", c_int32)]
 
 
 class PipeResult(Structure):
@@ -162,6 +168,12 @@ def lib() -> ctypes.CDLL:
     L.slafb_pipe_pop.argtypes = [c_void_p, c_void_p, POINTER(PipeResult)]
     L.slafb_pipe_destroy.argtypes = [c_void_p]
     L.slafb_debug_check_failures.argtypes = [c_void_p]
+    L.slafb_pack_bound.restype = c_int64
+    L.slafb_pack_bound.argtypes = [c_int64, c_int64]
+    L.slafb_pack_rows.argtypes = [c_void_p, c_int32, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, POINTER(c_int64)]
+    L.slafb_unpack_rows.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_void_p]
+    L.slafb_submit_packed.argtypes = [c_void_p, POINTER(Packed), c_int32, c_void_p, c_int32, c_void_p, POINTER(c_int32)]
+    L.slafb_pipe_push_packed.argtypes = [c_void_p, POINTER(Packed), c_int32, c_void_p, c_int32, c_int64, c_void_p, POINTER(PipeResult)]
     for name in EXPORTS:
         getattr(L, name)  # AttributeError here = header and library out of sync
     _lib = L

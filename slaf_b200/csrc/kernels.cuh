@@ -1028,14 +1028,41 @@ struct FastArgs {
     uint32_t vcap;                // value stage capacity (rows, multiple of 8)
     const uint32_t *vstar_table;  // [65536] smallest uint16 value whose window bin is >= 1, per cell maximum
     uint32_t *ticket;             // dynamic row counter (zeroed by K1): rows are handed out in order
+    // packed wire format (pack_rows.h): one 16-byte aligned block per cell; blk_off[c] in 16-byte units
+    const uint8_t *packed;
+    const uint32_t *blk_off;
+    uint32_t rawcap;              // bytes of one raw-block stage (a cell whose block is larger goes to the general kernel)
 };
 
 struct CellDesc {
     uint32_t j;                   // output row (0xffffffff: no more work)
     uint32_t s, e, c, a0;
-    uint32_t g_bulk, v_bulk;      // rows staged by the bulk copies, counted from a0 (multiples of 8)
+    uint32_t g_bulk, v_bulk;      // rows staged by the bulk copies, counted from a0 (multiples of 8); packed: v_bulk = 0 marks an oversize block
     uint32_t n_g, n_v;            // rows of the cell the stages must hold (from s)
 };
+
+// packed route: the cell's block goes into the raw stage with ONE bulk copy (or not at all when it does not fit)
+__device__ __forceinline__ void packed_issue(const FastArgs &fa, uint32_t j, uint32_t c, uint32_t s, uint32_t e, uint32_t boff, uint32_t bend,
+                                             uint32_t n_g_want, CellDesc *d, uint8_t *raw, uint64_t *bar) {
+    const TokArgs &a = fa.t;
+    d->j = j;
+    if (j >= a.n_cells) { mbar_arrive(bar); return; }
+    const uint32_t n = e - s, bytes = (bend - boff) << 4;
+    const bool fits = bytes <= fa.rawcap && n + 8u <= fa.vcap && n_g_want + 8u <= fa.gcap + 8u;
+    d->s = s; d->e = e; d->c = c; d->a0 = s;
+    d->g_bulk = 0u; d->v_bulk = fits ? 1u : 0u; d->n_g = n_g_want; d->n_v = n;
+    SLAFB_CHECK(e <= a.n_rows && s <= e && bend >= boff, 221, bytes);
+    if (!fits || bytes == 0u) { mbar_arrive(bar); return; }
+    mbar_arrive_expect_tx(bar, bytes);
+    bulk_g2s(raw, fa.packed + ((size_t)boff << 4), bytes, bar);
+}
+
+// value of row `row` in an exception list {row, value} x n (ascending rows): the lists are short, a linear scan is enough
+__device__ __forceinline__ uint32_t packed_exception(const uint32_t *ex, uint32_t n, uint32_t row) {
+    for (uint32_t i = 0; i < n; i++)
+        if (ex[2u * i] == row) return ex[2u * i + 1u];
+    return 255u;      // (malformed block: the byte stands for itself)
+}
 
 template <typename GeneT, typename ValT, int MODE>
 __device__ __forceinline__ void fast_issue(const FastArgs &fa, uint32_t j, uint32_t c, uint32_t s, uint32_t e, CellDesc *d,
@@ -1076,8 +1103,9 @@ static_assert(kHashMaxDistinct + kFastThreads < kHashSlots, "the distinct-value 
 template <typename ValT, int MODE>
 constexpr int fast_ctas_per_sm() { return (sizeof(ValT) == 4 || MODE == MODE_GF_PCT) ? (1536 / kFastThreads) : (2048 / kFastThreads); }
 
-template <typename GeneT, typename ValT, int MODE>
+template <typename GeneT, typename ValT, int MODE, bool PACKED = false>
 __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm<ValT, MODE>()) tokenize_cells_kernel(const FastArgs fa) {
+    static_assert(!PACKED || sizeof(ValT) == 2, "the packed wire format carries uint16 counts");
     constexpr bool SCGPT = (MODE == MODE_SCGPT_RAW || MODE == MODE_SCGPT_BINNED);
     constexpr bool BINNED = (MODE == MODE_SCGPT_BINNED);
     constexpr bool PCT = (MODE == MODE_GF_PCT);
@@ -1116,16 +1144,23 @@ __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm<ValT, MODE>()) 
     // one step per iteration, so none of those latencies is ever waited on in line.
     const uint32_t G = gridDim.x, NONE = 0xffffffffu;
     uint32_t j1 = NONE, c1 = 0, s1 = 0, e1 = 0;   // next row: segment known, copy issued at the top of the loop
+    uint32_t b1 = 0, be1 = 0;                     // (packed route: its block bounds)
     uint32_t j2 = NONE, c2 = 0;                   // row after: permutation entry loaded
     uint32_t j3 = NONE;                           // row after that: ticket drawn
+    // packed route: [raw block stage 0][raw block stage 1][gene stage][value stage] -- the bulk copies double-buffer the raw blocks,
+    // the decoded genes / values of the CURRENT cell live in one gene and one value stage
+    auto want_genes = [&](uint32_t n) -> uint32_t { return PCT ? n : min(n, limit); };
+    (void)b1; (void)be1;
     if (tid == 0) {
         const uint32_t j0 = blockIdx.x;
         if (j0 < a.n_cells) {
             const uint32_t c0 = a.perm ? (uint32_t)__ldg(a.perm + j0) : j0;
-            fast_issue<GeneT, ValT, MODE>(fa, j0, c0, __ldg(a.seg_start + c0), __ldg(a.seg_start + c0 + 1), &s_desc[0],
-                                          smem_raw, smem_raw + gbytes, &s_bar[0]);
+            const uint32_t s0 = __ldg(a.seg_start + c0), e0 = __ldg(a.seg_start + c0 + 1);
+            if constexpr (PACKED) packed_issue(fa, j0, c0, s0, e0, __ldg(fa.blk_off + c0), __ldg(fa.blk_off + c0 + 1), want_genes(e0 - s0), &s_desc[0], smem_raw, &s_bar[0]);
+            else fast_issue<GeneT, ValT, MODE>(fa, j0, c0, s0, e0, &s_desc[0], smem_raw, smem_raw + gbytes, &s_bar[0]);
         } else {
-            fast_issue<GeneT, ValT, MODE>(fa, NONE, 0, 0, 0, &s_desc[0], smem_raw, smem_raw + gbytes, &s_bar[0]);
+            if constexpr (PACKED) packed_issue(fa, NONE, 0, 0, 0, 0, 0, 0, &s_desc[0], smem_raw, &s_bar[0]);
+            else fast_issue<GeneT, ValT, MODE>(fa, NONE, 0, 0, 0, &s_desc[0], smem_raw, smem_raw + gbytes, &s_bar[0]);
         }
         j1 = G + atomicAdd(fa.ticket, 1u);
         j2 = G + atomicAdd(fa.ticket, 1u);
@@ -1134,6 +1169,7 @@ __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm<ValT, MODE>()) 
             c1 = a.perm ? (uint32_t)__ldg(a.perm + j1) : j1;
             s1 = __ldg(a.seg_start + c1);
             e1 = __ldg(a.seg_start + c1 + 1);
+            if constexpr (PACKED) { b1 = __ldg(fa.blk_off + c1); be1 = __ldg(fa.blk_off + c1 + 1); }
         }
         if (j2 < a.n_cells) c2 = a.perm ? (uint32_t)__ldg(a.perm + j2) : j2;
     }
@@ -1143,11 +1179,18 @@ __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm<ValT, MODE>()) 
         const uint32_t st = it & 1u;
         // stage st^1 was released by the barrier that ended the previous iteration
         if (tid == 0) {
-            fast_issue<GeneT, ValT, MODE>(fa, j1 < a.n_cells ? j1 : NONE, c1, s1, e1, &s_desc[st ^ 1u],
-                                          smem_raw + (st ^ 1u) * stage_bytes, smem_raw + (st ^ 1u) * stage_bytes + gbytes,
-                                          &s_bar[st ^ 1u]);
+            if constexpr (PACKED)
+                packed_issue(fa, j1 < a.n_cells ? j1 : NONE, c1, s1, e1, b1, be1, want_genes(e1 - s1), &s_desc[st ^ 1u],
+                             smem_raw + (st ^ 1u) * fa.rawcap, &s_bar[st ^ 1u]);
+            else
+                fast_issue<GeneT, ValT, MODE>(fa, j1 < a.n_cells ? j1 : NONE, c1, s1, e1, &s_desc[st ^ 1u],
+                                              smem_raw + (st ^ 1u) * stage_bytes, smem_raw + (st ^ 1u) * stage_bytes + gbytes,
+                                              &s_bar[st ^ 1u]);
             j1 = j2; c1 = c2;
-            if (j1 < a.n_cells) { s1 = __ldg(a.seg_start + c1); e1 = __ldg(a.seg_start + c1 + 1); }
+            if (j1 < a.n_cells) {
+                s1 = __ldg(a.seg_start + c1); e1 = __ldg(a.seg_start + c1 + 1);
+                if constexpr (PACKED) { b1 = __ldg(fa.blk_off + c1); be1 = __ldg(fa.blk_off + c1 + 1); }
+            }
             j2 = j3;
             if (j2 < a.n_cells) c2 = a.perm ? (uint32_t)__ldg(a.perm + j2) : j2;
             j3 = (j3 < a.n_cells) ? G + atomicAdd(fa.ticket, 1u) : NONE;
@@ -1157,12 +1200,87 @@ __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm<ValT, MODE>()) 
         const CellDesc d = s_desc[st];
         const uint32_t j = d.j;
         if (j == NONE) break;                       // uniform: every thread reads the same descriptor
-        GeneT *sg = reinterpret_cast<GeneT *>(smem_raw + st * stage_bytes);
-        ValT *sv = reinterpret_cast<ValT *>(smem_raw + st * stage_bytes + gbytes);
+        GeneT *sg = reinterpret_cast<GeneT *>(smem_raw + (PACKED ? 2u * fa.rawcap : st * stage_bytes));
+        ValT *sv = reinterpret_cast<ValT *>(smem_raw + (PACKED ? 2u * fa.rawcap : st * stage_bytes) + gbytes);
         const uint32_t s = d.s, e = d.e, n = e - s, a0 = d.a0, sh = s - a0;
 
+        bool oversize = false;
+        if constexpr (PACKED) {
+            // ---- decode the cell's block (pack_rows.h) from the raw stage into the gene / value stages: 8 rows per thread,
+            // values widened to uint16 (byte 255 = look the row up in the exception list), gene ids = base + running sum of
+            // (delta + 1) -- a local prefix per thread and one block scan per 2,048 rows.
+            oversize = (d.v_bulk == 0u) && n > 0u;
+            if (!oversize && n > 0u) {
+                const uint8_t *rb = smem_raw + st * fa.rawcap;
+                const uint4 hdr = *reinterpret_cast<const uint4 *>(rb);
+                const uint32_t np = (n + 15u) & ~15u, base_gene = hdr.y, n_eg = hdr.z, n_ev = hdr.w;
+                const uint8_t *dl = rb + 16u, *vl = dl + np;
+                const uint32_t *exg = reinterpret_cast<const uint32_t *>(vl + np), *exv = exg + 2u * n_eg;
+                SLAFB_CHECK(hdr.x == n && 16u + 2u * np + 8u * (n_eg + n_ev) <= fa.rawcap, 222, hdr.x);
+                uint32_t carry = 0u;
+                for (uint32_t base = 0u; base < n; base += (uint32_t)kFastThreads * 8u) {
+                    const uint32_t i0 = base + (uint32_t)tid * 8u;
+                    uint32_t dd[8], vv[8], run = 0u;
+                    if (i0 < n) {
+                        const uint2 dq = *reinterpret_cast<const uint2 *>(dl + i0), vq = *reinterpret_cast<const uint2 *>(vl + i0);
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            dd[i] = ((i < 4 ? dq.x : dq.y) >> ((i & 3) * 8)) & 0xffu;
+                            vv[i] = ((i < 4 ? vq.x : vq.y) >> ((i & 3) * 8)) & 0xffu;
+                        }
+                        if (n_ev) {
+#pragma unroll
+                            for (int i = 0; i < 8; i++) if (vv[i] == 255u && i0 + i < n) vv[i] = packed_exception(exv, n_ev, i0 + i);
+                        }
+                        if (n_eg) {
+#pragma unroll
+                            for (int i = 0; i < 8; i++) if (dd[i] == 255u && i0 + i < n) dd[i] = packed_exception(exg, n_eg, i0 + i);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; i++) { run += (i0 + i < n) ? dd[i] + 1u : 0u; dd[i] = run; }    // inclusive prefix inside the thread
+                        SLAFB_CHECK(i0 + 8u <= fa.vcap, 223, i0);
+                        *reinterpret_cast<uint4 *>(sv + i0) = make_uint4(vv[0] | (vv[1] << 16), vv[2] | (vv[3] << 16), vv[4] | (vv[5] << 16), vv[6] | (vv[7] << 16));
+                    }
+                    const uint32_t inc = warp_incl_scan(run);
+                    if (lane == 31) s_ws[warp] = inc;
+                    __syncthreads();
+                    uint32_t wbase = 0u, tot = 0u;
+#pragma unroll
+                    for (int w2 = 0; w2 < kFastWarps; w2++) {
+                        const uint32_t t = s_ws[w2];
+                        if (w2 < warp) wbase += t;
+                        tot += t;
+                    }
+                    if (i0 < d.n_g) {
+                        const uint32_t g0 = base_gene + carry + wbase + inc - run - 1u;     // gene id of row i0 is g0 + dd[0]
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            if (i0 + i < d.n_g) {
+                                SLAFB_CHECK(i0 + i < fa.gcap, 224, i0 + i);
+                                sg[i0 + i] = (GeneT)(g0 + dd[i]);
+                            }
+                        }
+                    }
+                    carry += tot;
+                    __syncthreads();        // the scratch is free again; after the last chunk: both stages are complete
+                }
+            }
+        }
+
+        if constexpr (PACKED) {
+            if (oversize) {                         // a block that does not fit the raw stage: unpacked for, and tokenized by, the general kernel
+                if (tid == 0) {
+                    const uint32_t wi = atomicAdd(a.work_counters, 1u);
+                    SLAFB_CHECK(wi < a.n_cells, 208, wi);
+                    a.work_list[wi] = j;
+                }
+                __syncthreads();
+                continue;
+            }
+        }
+
         // rows in the last partial 8-group of the column arrays cannot be bulk-copied (16-byte granules)
-        const bool patch = (s + max(d.n_g, d.n_v) > R8);
+        const bool patch = !PACKED && (s + max(d.n_g, d.n_v) > R8);
         if (patch) {
             if (tid < 8) {
                 const uint32_t r = R8 + tid;
@@ -2232,6 +2350,69 @@ __global__ void gene_stats_unpack_kernel(unsigned long long *packed, uint32_t n_
         sum[g] += p >> 24;
         cnt[g] += p & 0xffffffull;
         packed[g] = 0ull;
+    }
+}
+
+// Packed route, cells the tokenizing kernel deferred (its work list: blocks larger than the raw stage, cells that need the exact
+// k-th distinct value): their blocks are decoded into plain gene / value columns at the cells' row offsets, where the general
+// kernel reads them.  One CTA per deferred cell, the same decode as in the tokenizing kernel but straight from global memory.
+template <typename GeneT>
+__global__ void __launch_bounds__(kTokThreads) unpack_deferred_kernel(const uint8_t *__restrict__ packed, const uint32_t *__restrict__ blk_off,
+                                                                      const uint32_t *__restrict__ seg_start, const int32_t *__restrict__ perm,
+                                                                      const uint32_t *__restrict__ work_list, const uint32_t *__restrict__ work_count,
+                                                                      GeneT *__restrict__ gene, uint16_t *__restrict__ value) {
+    __shared__ uint32_t s_ws[kTokThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t count = *work_count;
+    for (uint32_t it = blockIdx.x; it < count; it += gridDim.x) {
+        const uint32_t row = work_list[it];
+        const uint32_t c = perm ? (uint32_t)perm[row] : row;
+        const uint32_t s = seg_start[c], n = seg_start[c + 1] - s;
+        const uint8_t *rb = packed + ((size_t)blk_off[c] << 4);
+        const uint4 hdr = __ldg(reinterpret_cast<const uint4 *>(rb));
+        const uint32_t np = (n + 15u) & ~15u, base_gene = hdr.y, n_eg = hdr.z, n_ev = hdr.w;
+        const uint8_t *dl = rb + 16u, *vl = dl + np;
+        const uint32_t *exg = reinterpret_cast<const uint32_t *>(vl + np), *exv = exg + 2u * n_eg;
+        uint32_t carry = 0u;
+        for (uint32_t base = 0u; base < n; base += (uint32_t)kTokThreads * 8u) {
+            const uint32_t i0 = base + (uint32_t)tid * 8u;
+            uint32_t dd[8], vv[8], run = 0u;
+            if (i0 < n) {
+                const uint2 dq = __ldg(reinterpret_cast<const uint2 *>(dl + i0)), vq = __ldg(reinterpret_cast<const uint2 *>(vl + i0));
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    dd[i] = ((i < 4 ? dq.x : dq.y) >> ((i & 3) * 8)) & 0xffu;
+                    vv[i] = ((i < 4 ? vq.x : vq.y) >> ((i & 3) * 8)) & 0xffu;
+                    if (vv[i] == 255u && i0 + i < n) vv[i] = packed_exception(exv, n_ev, i0 + i);
+                    if (dd[i] == 255u && i0 + i < n) dd[i] = packed_exception(exg, n_eg, i0 + i);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; i++) { run += (i0 + i < n) ? dd[i] + 1u : 0u; dd[i] = run; }
+            }
+            const uint32_t inc = warp_incl_scan(run);
+            __syncthreads();
+            if (lane == 31) s_ws[warp] = inc;
+            __syncthreads();
+            uint32_t wbase = 0u, tot = 0u;
+#pragma unroll
+            for (int w2 = 0; w2 < kTokThreads / 32; w2++) {
+                const uint32_t t = s_ws[w2];
+                if (w2 < warp) wbase += t;
+                tot += t;
+            }
+            if (i0 < n) {
+                const uint32_t g0 = base_gene + carry + wbase + inc - run - 1u;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    if (i0 + i < n) {
+                        gene[s + i0 + i] = (GeneT)(g0 + dd[i]);
+                        value[s + i0 + i] = (uint16_t)vv[i];
+                    }
+                }
+            }
+            carry += tot;
+        }
+        __syncthreads();
     }
 }
 

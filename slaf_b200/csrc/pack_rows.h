@@ -78,6 +78,7 @@ static inline __attribute__((always_inline)) int pack_body(const GeneT *gene, co
         uint8_t *blk = out + off, *dl = blk + kHeaderBytes, *vl = dl + np;
         uint32_t eg, ev;
         pack_cell(g, v, n, dl, vl, &eg, &ev, &bad);
+        if (bad) return -1;                         // gene ids do not ascend: the exception counts of this cell mean nothing
         memset(dl + n, 0, np - n);
         memset(vl + n, 0, np - n);
         const size_t total = block_bytes(n, eg, ev);

@@ -29,6 +29,7 @@
 #include "../../include/slaf_b200.h"
 #include "kernels.cuh"
 #include "py_shuffle.h"
+#include "pack_rows.h"
 
 using namespace slafb;
 
@@ -56,6 +57,11 @@ struct Slot {
     uint32_t *h_counters_dev = nullptr;  // device-side address of h_counters
     bool all_general = false;
     bool host_segs = false;            // the segment table came from the host (submit_segments / submit_csi): the cell count is known without the GPU
+    bool packed = false;               // the rows arrived in the packed wire format (submit_packed): pk_bytes / blk_off describe them
+    uint8_t *pk_bytes = nullptr;       // device copy of the packed blocks (lazy, grow-only)
+    size_t pk_cap = 0;
+    uint32_t *blk_off = nullptr;       // device [max_cells + 2] block offsets, 16-byte units (lazy)
+    uint32_t *h_blk = nullptr;         // pinned host copy the table is assembled in (lazy)
     // permutation prepared ahead of collect() by the helper thread (slafb_prepare_shuffle)
     std::atomic<int> prep_state{0};   // 0 none, 1 queued / running, 2 ready
     int64_t prep_seed = 0;
@@ -242,8 +248,8 @@ int ensure_sort_scratch(slafb_ctx *ctx) {
 // ---- kernel dispatch over (gene dtype, value dtype, mode) -------------------------------------
 // K2 fast path.  Returns 1 when the configuration does not fit the fast kernel (then every cell
 // goes through the general kernel).
-template <typename GeneT, typename ValT, int MODE>
-int launch_fast(slafb_ctx *ctx, const TokArgs &a, cudaStream_t st, bool *launched) {
+template <typename GeneT, typename ValT, int MODE, bool PACKED = false>
+int launch_fast(slafb_ctx *ctx, const TokArgs &a, cudaStream_t st, bool *launched, const uint8_t *packed = nullptr, const uint32_t *blk_off = nullptr) {
     *launched = false;
     constexpr bool SCGPT = (MODE == MODE_SCGPT_RAW || MODE == MODE_SCGPT_BINNED);
     const uint32_t limit = SCGPT ? a.max_genes : (a.L - 1u);
@@ -261,9 +267,15 @@ int launch_fast(slafb_ctx *ctx, const TokArgs &a, cudaStream_t st, bool *launche
     if (MODE == MODE_GF_PCT) fa.gcap = fa.vcap;          // percentile mode: any row may survive the filter, so every row's gene is staged too
     fa.vstar_table = ctx->vstar_table;
     fa.ticket = a.work_counters + 2;   // slot counters[4], zeroed by K1 together with the work-list counters
-    const size_t smem = 2 * ((size_t)fa.gcap * sizeof(GeneT) + (size_t)fa.vcap * sizeof(ValT)) + (sizeof(ValT) == 4 ? (size_t)kHashSlots * 4 : 0);
+    fa.packed = packed;
+    fa.blk_off = blk_off;
+    // packed route: two raw-block stages (header + two byte streams of up to vcap - 8 rows + room for 64 exceptions) and ONE
+    // decoded gene / value stage; otherwise two gene / value stages the bulk copies fill directly
+    fa.rawcap = PACKED ? (uint32_t)((16u + 2u * (size_t)(fa.vcap - 8u) + 512u + 127u) & ~127u) : 0u;
+    const size_t smem = PACKED ? 2 * (size_t)fa.rawcap + (size_t)fa.gcap * sizeof(GeneT) + (size_t)fa.vcap * sizeof(ValT)
+                               : 2 * ((size_t)fa.gcap * sizeof(GeneT) + (size_t)fa.vcap * sizeof(ValT)) + (sizeof(ValT) == 4 ? (size_t)kHashSlots * 4 : 0);
     if (smem > 200 * 1024) return SLAFB_OK;   // very wide rows: general kernel only
-    auto kern = tokenize_cells_kernel<GeneT, ValT, MODE>;
+    auto kern = tokenize_cells_kernel<GeneT, ValT, MODE, PACKED>;
     static std::atomic<bool> attr_set[64];   // zero-initialised; setting the attribute twice is harmless
     if (!attr_set[ctx->device & 63].load(std::memory_order_acquire)) {
         CU(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -353,6 +365,15 @@ int dispatch_fast(slafb_ctx *ctx, int mode, const TokArgs &a, cudaStream_t st, b
         if constexpr (sizeof(ValT) == 2) return launch_fast<GeneT, ValT, MODE_GF_PCT>(ctx, a, st, launched);
         else { *launched = false; return SLAFB_OK; }
     default: *launched = false; return SLAFB_OK;
+    }
+}
+template <typename GeneT>
+int dispatch_fast_packed(slafb_ctx *ctx, int mode, const TokArgs &a, cudaStream_t st, bool *launched, const uint8_t *packed, const uint32_t *blk_off) {
+    switch (mode) {
+    case MODE_GF: return launch_fast<GeneT, uint16_t, MODE_GF, true>(ctx, a, st, launched, packed, blk_off);
+    case MODE_GF_PCT: return launch_fast<GeneT, uint16_t, MODE_GF_PCT, true>(ctx, a, st, launched, packed, blk_off);
+    case MODE_SCGPT_RAW: return launch_fast<GeneT, uint16_t, MODE_SCGPT_RAW, true>(ctx, a, st, launched, packed, blk_off);
+    default: return launch_fast<GeneT, uint16_t, MODE_SCGPT_BINNED, true>(ctx, a, st, launched, packed, blk_off);
     }
 }
 template <typename GeneT, typename ValT, int SINK>
@@ -502,6 +523,7 @@ int front(slafb_ctx *ctx, Slot &s, const slafb_coo *pieces, int n_pieces, cudaSt
     s.sample = ctx->timing_every > 0 && ((ctx->timing_every == 1) || (ctx->batch_seq % (uint64_t)ctx->timing_every == 0));
     ctx->batch_seq++;
     s.host_segs = false;
+    s.packed = false;
     s.n_rows = total;
     s.cell_dtype = in->cell_dtype;
     s.gene_dtype = in->gene_dtype;
@@ -757,6 +779,8 @@ int back(slafb_ctx *ctx, Slot &s, const slafb_params *p, const slafb_out *out, i
     a.cell_ids = reinterpret_cast<long long *>(out->cell_ids);
     a.host_slow = s.h_counters_dev + 2;
     WindowSink none{};
+    if (s.packed && p->mode == SLAFB_GENEFORMER && (p->order == SLAFB_ORDER_RANK || p->norm))
+        return fail(ctx, SLAFB_ERR_INVALID, "the rank-value extension takes unpacked rows");
     if (p->mode == SLAFB_GENEFORMER && (p->order == SLAFB_ORDER_RANK || p->norm)) {
         // extension path: every cell through the rank-value kernel
         if (!ctx->rank_scratch) CU(ctx, cudaMalloc(&ctx->rank_scratch, ((size_t)ctx->max_rows + 64) * sizeof(unsigned long long)));
@@ -783,8 +807,28 @@ int back(slafb_ctx *ctx, Slot &s, const slafb_params *p, const slafb_out *out, i
     }
     if (s.sample) CU(ctx, cudaEventRecord(s.t_k2a, st));
     bool fast_launched = false;
-    DISPATCH_TYPES(s.gene_dtype, s.value_dtype, rc = (dispatch_fast<GeneT, ValT>(ctx, p->mode, a, st, &fast_launched)));
-    if (rc) return rc;
+    if (s.packed) {
+        // packed rows: the tokenizing kernel decodes every cell's block in its shared-memory stage; the cells it defers are
+        // unpacked into the slot's scratch columns (a.gene / a.value) for the general kernel
+        if (s.gene_dtype == SLAFB_U16) rc = dispatch_fast_packed<uint16_t>(ctx, p->mode, a, st, &fast_launched, s.pk_bytes, s.blk_off);
+        else rc = dispatch_fast_packed<int32_t>(ctx, p->mode, a, st, &fast_launched, s.pk_bytes, s.blk_off);
+        if (rc) return rc;
+        if (!fast_launched) {                        // (rows too wide for the fast kernel) every cell is unpacked: all of them are "deferred"
+            return fail(ctx, SLAFB_ERR_INVALID, "max_genes too large for the packed route");
+        }
+        const unsigned ugrid = (unsigned)ctx->n_sm * 2u;
+        if (s.gene_dtype == SLAFB_U16)
+            unpack_deferred_kernel<uint16_t><<<ugrid, kTokThreads, 0, st>>>(s.pk_bytes, s.blk_off, s.seg_start, a.perm, s.work_list, s.counters + 2,
+                                                                           static_cast<uint16_t *>(s.in_cell), static_cast<uint16_t *>(s.in_value));
+        else
+            unpack_deferred_kernel<int32_t><<<ugrid, kTokThreads, 0, st>>>(s.pk_bytes, s.blk_off, s.seg_start, a.perm, s.work_list, s.counters + 2,
+                                                                          static_cast<int32_t *>(s.in_cell), static_cast<uint16_t *>(s.in_value));
+        CU(ctx, cudaGetLastError());
+        ctx->acc.kernel_launches++;
+    } else {
+        DISPATCH_TYPES(s.gene_dtype, s.value_dtype, rc = (dispatch_fast<GeneT, ValT>(ctx, p->mode, a, st, &fast_launched)));
+        if (rc) return rc;
+    }
     if (!fast_launched) a.all_cells = 1;
     if (s.sample) CU(ctx, cudaEventRecord(s.t_k2b, st));
     DISPATCH_TYPES(s.gene_dtype, s.value_dtype, rc = (dispatch_general<GeneT, ValT, 0>(ctx, p->mode, a, none, st)));
@@ -848,6 +892,7 @@ int submit_host_segments(slafb_ctx *ctx, const slafb_coo *pieces, int32_t n_piec
     s.sample = ctx->timing_every > 0 && ((ctx->timing_every == 1) || (ctx->batch_seq % (uint64_t)ctx->timing_every == 0));
     ctx->batch_seq++;
     s.host_segs = true;
+    s.packed = false;
     s.n_rows = total;
     s.cell_dtype = in->cell_dtype;
     s.gene_dtype = in->gene_dtype;
@@ -1033,6 +1078,8 @@ int slafb_destroy(slafb_ctx *ctx) {
         if (s.h_perm) cudaFreeHost(s.h_perm);
         if (s.h_seg) cudaFreeHost(s.h_seg);
         if (s.h_small) cudaFreeHost(s.h_small);
+        if (s.h_blk) cudaFreeHost(s.h_blk);
+        cudaFree(s.pk_bytes); cudaFree(s.blk_off);
         free(s.h_draws);
         cudaEvent_t evs[] = {s.ev_front, s.ev_done, s.ev_in, s.ev_loaded, s.ev_perm, s.t_h2d0, s.t_h2d1, s.t_k1a, s.t_k1b, s.t_k2a, s.t_k2b, s.t_k2c};
         for (auto e : evs) if (e) cudaEventDestroy(e);
@@ -1135,6 +1182,137 @@ int slafb_submit_csi(slafb_ctx *ctx, const slafb_coo *pieces, int32_t n_pieces, 
                                     if (rc) snprintf(ctx->err, sizeof ctx->err, "%s", g_err);
                                     return rc;
                                 });
+}
+
+int64_t slafb_pack_bound(int64_t n_rows, int64_t n_cells) {
+    // header + two padded byte streams per cell, plus room for one exception per 16 rows (count data needs a handful per cell)
+    if (n_rows < 0 || n_cells < 0) return -1;
+    return 2 * n_rows + 64 * n_cells + n_rows / 2 + 64;
+}
+
+int slafb_pack_rows(const void *gene, int32_t gene_dtype, const uint16_t *value, const uint32_t *row_start, int64_t n_cells, uint8_t *out,
+                    int64_t out_capacity, uint32_t *blk_off, int64_t *out_bytes) {
+    if (n_cells < 0 || !row_start || !blk_off || !out_bytes || (n_cells > 0 && (!gene || !value || !out)))
+        return fail(nullptr, SLAFB_ERR_INVALID, "NULL argument");
+    if (gene_dtype != SLAFB_U16 && gene_dtype != SLAFB_I32 && gene_dtype != SLAFB_U32) return fail(nullptr, SLAFB_ERR_INVALID, "gene dtype must be uint16, int32 or uint32");
+    if (((uintptr_t)out & 15u) != 0) return fail(nullptr, SLAFB_ERR_INVALID, "the packed buffer must be 16-byte aligned");
+    for (int64_t c = 0; c < n_cells; c++)
+        if (row_start[c] > row_start[c + 1]) return fail(nullptr, SLAFB_ERR_INVALID, "row offsets are not monotone");
+    size_t nb = 0;
+    int rc;
+    if (gene_dtype == SLAFB_U16)
+        rc = slafb_pack::pack<uint16_t>(static_cast<const uint16_t *>(gene), value, row_start, (size_t)n_cells, out, (size_t)out_capacity, blk_off, &nb);
+    else
+        rc = slafb_pack::pack<int32_t>(static_cast<const int32_t *>(gene), value, row_start, (size_t)n_cells, out, (size_t)out_capacity, blk_off, &nb);
+    *out_bytes = (int64_t)nb;
+    if (rc == -1) return fail(nullptr, SLAFB_ERR_INVALID, "gene ids do not ascend strictly inside every cell: these rows cannot be packed");
+    if (rc == -3) return fail(nullptr, SLAFB_ERR_CAPACITY, "packed buffer too small (%lld bytes)", (long long)out_capacity);
+    return SLAFB_OK;
+}
+
+int slafb_unpack_rows(const uint8_t *packed, const uint32_t *blk_off, const uint32_t *row_start, int64_t n_cells, void *gene, int32_t gene_dtype,
+                      uint16_t *value) {
+    if (n_cells < 0 || !blk_off || !row_start || (n_cells > 0 && (!packed || !gene || !value))) return fail(nullptr, SLAFB_ERR_INVALID, "NULL argument");
+    const int rc = gene_dtype == SLAFB_U16
+                       ? slafb_pack::unpack<uint16_t>(packed, blk_off, (size_t)n_cells, row_start, static_cast<uint16_t *>(gene), value)
+                       : slafb_pack::unpack<int32_t>(packed, blk_off, (size_t)n_cells, row_start, static_cast<int32_t *>(gene), value);
+    if (rc) return fail(nullptr, SLAFB_ERR_INVALID, "malformed packed block");
+    return SLAFB_OK;
+}
+
+int slafb_submit_packed(slafb_ctx *ctx, const slafb_packed *pieces, int32_t n_pieces, const uint32_t *seg_cell, int32_t cell_dtype, void *stream,
+                        int32_t *slot) {
+    if (!ctx || !slot || !pieces || n_pieces < 1) return fail(ctx, SLAFB_ERR_INVALID, "bad ctx / slot / pieces");
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (cell_dtype != SLAFB_U32 && cell_dtype != SLAFB_I32) return fail(ctx, SLAFB_ERR_INVALID, "cell dtype must be uint32 or int32");
+    int64_t C = 0, R = 0, B = 0;
+    for (int i = 0; i < n_pieces; i++) {
+        const slafb_packed &p = pieces[i];
+        if (p.n_cells < 0 || p.n_bytes < 0 || (p.n_bytes & 15) || (p.n_cells > 0 && (!p.bytes || !p.blk_off || !p.row_start)))
+            return fail(ctx, SLAFB_ERR_INVALID, "bad packed piece %d", i);
+        if (p.gene_dtype != pieces[0].gene_dtype || p.location != pieces[0].location) return fail(ctx, SLAFB_ERR_INVALID, "all pieces must share gene dtype and location");
+        if (p.n_cells > 0 && ((int64_t)p.blk_off[p.n_cells] << 4) != p.n_bytes) return fail(ctx, SLAFB_ERR_INVALID, "piece %d: block offsets do not cover the bytes", i);
+        if (((uintptr_t)p.bytes & 15u) != 0) return fail(ctx, SLAFB_ERR_INVALID, "packed bytes must be 16-byte aligned");
+        C += p.n_cells;
+        R += p.n_cells ? p.row_start[p.n_cells] - p.row_start[0] : 0;
+        B += p.n_bytes;
+    }
+    const int gdt = pieces[0].gene_dtype;
+    if (gdt != SLAFB_U16 && gdt != SLAFB_I32) return fail(ctx, SLAFB_ERR_INVALID, "packed genes decode to uint16 or int32");
+    if (C > ctx->max_cells) return fail(ctx, SLAFB_ERR_CAPACITY, "n_cells %lld exceeds context max_cells %lld", (long long)C, (long long)ctx->max_cells);
+    if (R > ctx->max_rows) return fail(ctx, SLAFB_ERR_CAPACITY, "n_rows %lld exceeds context max_rows %lld", (long long)R, (long long)ctx->max_rows);
+    if (C > 0 && !seg_cell) return fail(ctx, SLAFB_ERR_INVALID, "NULL cell ids");
+    if ((B >> 4) > 0xffffffffll) return fail(ctx, SLAFB_ERR_CAPACITY, "more than 64 GiB of packed rows in one batch");
+    const int si = pick_slot(ctx);
+    if (si < 0) return fail(ctx, SLAFB_ERR_BUSY, "all %d pipeline slots hold batches that were not collected yet", kSlots);
+    Slot &s = ctx->slot[si];
+    const double t0 = now_ms();
+    if (s.ev_done) {
+        CU(ctx, cudaEventSynchronize(s.ev_done));
+        harvest(ctx, s);
+    }
+    int rc = ensure_staging(ctx, s);                  // scratch columns the deferred cells are unpacked into
+    if (rc) return rc;
+    if (!s.blk_off) CU(ctx, cudaMalloc(&s.blk_off, ((size_t)ctx->max_cells + 2) * sizeof(uint32_t)));
+    if (!s.h_blk) CU(ctx, cudaHostAlloc(&s.h_blk, ((size_t)ctx->max_cells + 2) * sizeof(uint32_t), cudaHostAllocPortable));
+    if ((size_t)B + 16 > s.pk_cap) {
+        if (s.pk_bytes) CU(ctx, cudaFree(s.pk_bytes));
+        s.pk_bytes = nullptr; s.pk_cap = 0;
+        const size_t cap = (size_t)B + (size_t)B / 8 + 4096;
+        CU(ctx, cudaMalloc(&s.pk_bytes, cap));
+        s.pk_cap = cap;
+    }
+    // the batch's tables in the slot's pinned blocks: row offsets, cell ids, block offsets (rebased piece by piece)
+    uint32_t *st = s.h_seg, *id = s.h_seg + (size_t)ctx->max_cells + 1, *bo = s.h_blk;
+    int64_t c0 = 0, r0 = 0, b0 = 0;
+    for (int i = 0; i < n_pieces; i++) {
+        const slafb_packed &p = pieces[i];
+        for (int64_t c = 0; c < p.n_cells; c++) {
+            if (p.row_start[c] > p.row_start[c + 1] || p.blk_off[c] > p.blk_off[c + 1]) return fail(ctx, SLAFB_ERR_INVALID, "piece %d: offsets are not monotone", i);
+            st[c0 + c] = (uint32_t)(r0 + (p.row_start[c] - p.row_start[0]));
+            bo[c0 + c] = (uint32_t)((b0 >> 4) + p.blk_off[c]);
+        }
+        if (p.n_cells) { r0 += p.row_start[p.n_cells] - p.row_start[0]; }
+        c0 += p.n_cells;
+        b0 += p.n_bytes;
+    }
+    st[C] = (uint32_t)R;
+    bo[C] = (uint32_t)(B >> 4);
+    if (C) memcpy(id, seg_cell, (size_t)C * sizeof(uint32_t));
+    cudaStream_t sf = ctx->s_in;
+    s.sample = ctx->timing_every > 0 && ((ctx->timing_every == 1) || (ctx->batch_seq % (uint64_t)ctx->timing_every == 0));
+    ctx->batch_seq++;
+    s.host_segs = true;
+    s.packed = true;
+    s.n_rows = R;
+    s.cell_dtype = cell_dtype;
+    s.gene_dtype = gdt;
+    s.value_dtype = SLAFB_U16;
+    s.h_counters[0] = (uint32_t)C;
+    s.h_counters[1] = 0;
+    s.cell = nullptr; s.gene = s.in_cell; s.value = s.in_value;
+    CU(ctx, cudaEventRecord(s.ev_in, static_cast<cudaStream_t>(stream)));
+    CU(ctx, cudaStreamWaitEvent(sf, s.ev_in, 0));
+    CU(ctx, cudaMemsetAsync(s.counters, 0, 8 * sizeof(uint32_t), sf));
+    if (C > 0) {
+        CU(ctx, cudaMemcpyAsync(s.seg_start, st, (size_t)(C + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, sf));
+        CU(ctx, cudaMemcpyAsync(s.seg_cell, id, (size_t)C * sizeof(uint32_t), cudaMemcpyHostToDevice, sf));
+        CU(ctx, cudaMemcpyAsync(s.blk_off, bo, (size_t)(C + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, sf));
+    }
+    CU(ctx, cudaEventRecord(s.ev_front, sf));
+    if (s.sample) CU(ctx, cudaEventRecord(s.t_h2d0, sf));
+    const cudaMemcpyKind kind = pieces[0].location == SLAFB_LOC_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    size_t off = 0;
+    for (int i = 0; i < n_pieces; i++) {
+        if (pieces[i].n_bytes) CU(ctx, cudaMemcpyAsync(s.pk_bytes + off, pieces[i].bytes, (size_t)pieces[i].n_bytes, kind, sf));
+        off += (size_t)pieces[i].n_bytes;
+    }
+    if (s.sample) { CU(ctx, cudaEventRecord(s.t_h2d1, sf)); s.timed_h2d = true; }
+    CU(ctx, cudaEventRecord(s.ev_loaded, sf));
+    ctx->acc.host_submit_ms += now_ms() - t0;
+    s.in_flight = true;
+    *slot = si;
+    return SLAFB_OK;
 }
 
 int slafb_wait_loaded(slafb_ctx *ctx, int32_t slot) {
@@ -1251,6 +1429,23 @@ int slafb_pipe_push(slafb_pipe *pipe, const slafb_coo *pieces, int32_t n_pieces,
     return SLAFB_OK;
 }
 
+int slafb_pipe_push_packed(slafb_pipe *pipe, const slafb_packed *pieces, int32_t n_pieces, const uint32_t *seg_cell, int32_t cell_dtype,
+                           int64_t seed, void *stream, slafb_pipe_result *done) {
+    if (!pipe) return fail(nullptr, SLAFB_ERR_INVALID, "pipe is NULL");
+    slafb_ctx *ctx = pipe->ctx;
+    if (done) { done->ring_index = -1; done->n_cells = 0; done->seq = -1; }
+    int32_t slot = -1;
+    int rc = slafb_submit_packed(ctx, pieces, n_pieces, seg_cell, cell_dtype, stream, &slot);
+    if (rc) return rc;
+    if (pipe->p.shuffle == SLAFB_SHUFFLE_SEED) {
+        rc = slafb_prepare_shuffle(ctx, slot, seed);
+        if (rc) return rc;
+    }
+    pipe->q.push_back({slot, seed, pipe->next_seq++});
+    if ((int)pipe->q.size() > pipe->depth) return pipe_pop(pipe, stream, done);
+    return SLAFB_OK;
+}
+
 int slafb_pipe_pop(slafb_pipe *pipe, void *stream, slafb_pipe_result *done) {
     if (!pipe) return fail(nullptr, SLAFB_ERR_INVALID, "pipe is NULL");
     if (done) { done->ring_index = -1; done->n_cells = 0; done->seq = -1; }
@@ -1315,7 +1510,7 @@ int slafb_collect_csr(slafb_ctx *ctx, int32_t slot, const slafb_params *p, int64
     if (!s.in_flight) return fail(ctx, SLAFB_ERR_INVALID, "slot %d has no submitted batch", slot);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     bool use_perm = false;
-    int rc = middle(ctx, s, p, n_cells, st, &use_perm);
+    int rc = s.packed ? fail(ctx, SLAFB_ERR_INVALID, "packed batches are tokenized (slafb_collect), not returned as CSR") : middle(ctx, s, p, n_cells, st, &use_perm);
     const int64_t C = *n_cells;
     *n_rows = 0;
     if (rc == SLAFB_OK && C > 0) {

@@ -279,6 +279,20 @@ class HotPathEngine:
         self._took(slot.value, (cell_col, keeps[0][1], keeps[0][2]) + tuple(keeps[1:]) + (csi,), total)
         return slot.value, int(n.value)
 
+    def submit_packed(self, pieces: list["PackedRows"], shuffle_seed: int | None = None) -> int:
+        """submit() for rows in the packed wire format (``pack_rows``): ~2 bytes per row cross PCIe, the tokenizing kernel decodes
+        the blocks in its shared-memory stage.  Everything downstream (collect, the pipe) is unchanged; the token tensors are
+        identical to the unpacked routes."""
+        inp = PreparedInput(pieces)
+        slot = ctypes.c_int32(-1)
+        with torch.cuda.device(self.device):
+            N.check(self._L.slafb_submit_packed(self._ctx, inp.arr, inp.n_pieces, inp._sc, inp.cell_dtype, self._stream(), ctypes.byref(slot)), self._ctx)
+            if shuffle_seed is not None:
+                N.check(self._L.slafb_prepare_shuffle(self._ctx, slot.value, int(shuffle_seed)), self._ctx)
+        cell_col = _Column(np.zeros(1, np.int32 if pieces[0].cell_signed else np.uint32), (N.U32, N.I32), "cell_integer_id")
+        self._took(slot.value, (cell_col, inp), inp.n_rows)
+        return slot.value
+
     def wait_loaded(self, slot: int) -> None:
         """Block until the H2D copy of the batch last submitted into `slot` has finished (its host columns may be reused)."""
         with torch.cuda.device(self.device):
@@ -492,12 +506,95 @@ class HotPathEngine:
         return {f: getattr(t, f) for f, _ in N.Timing._fields_}
 
 
+class PackedRows:
+    """One batch (or a piece of one) in the packed wire format (include/slaf_b200.h, csrc/pack_rows.h): ``bytes`` uint8 (pinned when
+    made by ``pack_rows(pin=True)``), ``blk_off`` uint32 [C + 1] (16-byte units), ``row_start`` uint32 [C + 1], ``seg_cell`` [C]
+    cell ids, and the dtype the genes decode to."""
+
+    def __init__(self, data: np.ndarray, blk_off: np.ndarray, row_start: np.ndarray, seg_cell: np.ndarray, gene_dtype: int, cell_signed: bool = False):
+        self.bytes, self.blk_off, self.row_start = data, np.ascontiguousarray(blk_off, np.uint32), np.ascontiguousarray(row_start, np.uint32)
+        sc = np.asarray(seg_cell)
+        self.seg_cell = np.ascontiguousarray(sc).view(np.uint32) if sc.dtype.itemsize == 4 else np.ascontiguousarray(sc, np.uint32)
+        self.gene_dtype, self.cell_signed = gene_dtype, cell_signed
+        self.n_cells = int(self.seg_cell.size)
+        self.n_rows = int(self.row_start[-1] - self.row_start[0]) if self.n_cells else 0
+        if self.blk_off.size != self.n_cells + 1 or self.row_start.size != self.n_cells + 1:
+            raise ValueError("blk_off / row_start need one more entry than there are cells")
+
+    @property
+    def nbytes(self) -> int:
+        return int(self.bytes.nbytes)
+
+    def struct(self) -> N.Packed:
+        if isinstance(self.bytes, torch.Tensor):
+            ptr, loc = self.bytes.data_ptr(), (N.LOC_DEVICE if self.bytes.is_cuda else N.LOC_HOST)
+        else:
+            ptr, loc = self.bytes.ctypes.data, N.LOC_HOST
+        return N.Packed(ptr or None, self.nbytes, self.blk_off.ctypes.data, self.row_start.ctypes.data, self.n_cells, loc, self.gene_dtype)
+
+    def unpack(self) -> tuple[np.ndarray, np.ndarray]:
+        """(gene, value) columns back from the blocks (host; the library's reference decoder)."""
+        data = self.bytes.cpu().numpy() if isinstance(self.bytes, torch.Tensor) else self.bytes
+        gene = np.empty(self.n_rows, np.uint16 if self.gene_dtype == N.U16 else np.int32)
+        value = np.empty(self.n_rows, np.uint16)
+        rs = (self.row_start - self.row_start[0]).astype(np.uint32)
+        N.check(N.lib().slafb_unpack_rows(data.ctypes.data, self.blk_off.ctypes.data, rs.ctypes.data, self.n_cells, gene.ctypes.data,
+                                          self.gene_dtype, value.ctypes.data))
+        return gene, value
+
+
+def pack_rows(gene: np.ndarray, value: np.ndarray, row_start: np.ndarray, seg_cell: np.ndarray, pin: bool = False, cell_signed: bool = False) -> PackedRows:
+    """Pack the cells whose rows are ``gene[row_start[c]:row_start[c+1]]`` / ``value[...]`` (host arrays; gene ids ascending inside a
+    cell, uint16 values) into the packed wire format: ~2 bytes per row.  Single threaded C; pack disjoint cell ranges in parallel
+    threads and submit them as pieces.  ``pin=True`` puts the blocks into page-locked memory (async DMA source)."""
+    gene, value = np.ascontiguousarray(gene), np.ascontiguousarray(value)
+    if value.dtype != np.uint16:
+        raise TypeError("the packed format carries uint16 counts (float32 tables travel unpacked)")
+    if gene.dtype not in _NP_DT or _NP_DT[gene.dtype] not in (N.U16, N.I32, N.U32):
+        raise TypeError(f"gene_integer_id: unsupported dtype {gene.dtype}")
+    rs = np.ascontiguousarray(row_start, np.int64)
+    C = rs.size - 1
+    if C < 0 or len(gene) != len(value):
+        raise ValueError("bad row offsets / column lengths")
+    lo = int(rs[0]) if C >= 0 and rs.size else 0
+    rel = (rs - lo).astype(np.uint32)
+    n_rows = int(rel[-1]) if rel.size else 0
+    L = N.lib()
+    cap = int(L.slafb_pack_bound(n_rows, C))
+    while True:
+        out = pinned_empty(cap, np.uint8) if pin else np.empty(cap + 16, np.uint8)
+        if not pin:
+            out = out[(-out.ctypes.data) % 16:][:cap]          # 16-byte aligned view
+        blk = np.empty(C + 1, np.uint32)
+        nb = ctypes.c_int64(0)
+        g, v = gene[lo:lo + n_rows], value[lo:lo + n_rows]
+        rc = L.slafb_pack_rows(g.ctypes.data, _NP_DT[gene.dtype], v.ctypes.data, rel.ctypes.data, C, out.ctypes.data, cap, blk.ctypes.data, ctypes.byref(nb))
+        if rc == N.ERR_CAPACITY and cap < 20 * max(n_rows, 1) + 64 * max(C, 1) + 64:
+            cap = 2 * cap + 64 * max(C, 1)                      # exception-heavy rows: retry with more room
+            continue
+        N.check(rc)
+        break
+    gdt = N.U16 if gene.dtype == np.uint16 else N.I32
+    return PackedRows(out[: nb.value], blk, rel, seg_cell, gdt, cell_signed)
+
+
 class PreparedInput:
     """The ctypes description of one batch's input (COO pieces, or gene / value pieces + a host segment table), built once for
     buffers that are submitted again and again (a feeder's staging ring, bench.py's resident batches)."""
 
-    def __init__(self, pieces: list[tuple[Any, Any, Any]], seg_start: np.ndarray | None = None, seg_cell: np.ndarray | None = None,
+    def __init__(self, pieces: list, seg_start: np.ndarray | None = None, seg_cell: np.ndarray | None = None,
                  cell_signed: bool = False):
+        self.packed = bool(pieces) and isinstance(pieces[0], PackedRows)
+        if self.packed:              # packed wire format: `pieces` are PackedRows, their cell ids are concatenated
+            self.keep = list(pieces)
+            self.arr = (N.Packed * len(pieces))(*[p.struct() for p in pieces])
+            self.n_pieces = len(pieces)
+            self.n_rows = sum(p.n_rows for p in pieces)
+            self.seg_cell = np.ascontiguousarray(np.concatenate([p.seg_cell for p in pieces]))
+            self._sc = self.seg_cell.ctypes.data
+            self.cell_dtype = N.I32 if pieces[0].cell_signed else N.U32
+            self.n_bytes = sum(p.nbytes for p in pieces)
+            return
         coos, self.keep, self.n_rows = [], [], 0
         for cell, gene, value in pieces:
             if seg_start is None:
@@ -545,7 +642,7 @@ class Pipe:
         self._res = N.PipeResult()
         self._res_ref = ctypes.byref(self._res)
         self._pipe = ctypes.c_void_p()
-        self._push, self._pop = eng._L.slafb_pipe_push, eng._L.slafb_pipe_pop
+        self._push, self._pop, self._push_packed = eng._L.slafb_pipe_push, eng._L.slafb_pipe_pop, eng._L.slafb_pipe_push_packed
         N.check(eng._L.slafb_pipe_create(eng._ctx, ctypes.byref(params), self._ring, ring, depth, ctypes.byref(self._pipe)), eng._ctx)
         self._stream = eng._stream()
         self._inputs: list[PreparedInput] = []        # referenced while their copies may be in flight (bounded by the slot count)
@@ -555,7 +652,10 @@ class Pipe:
         self._stream = self.eng._stream()
 
     def push(self, inp: PreparedInput, seed: int = 0) -> tuple[int, int, int]:
-        rc = self._push(self._pipe, inp.arr, inp.n_pieces, inp._ss, inp._sc, inp.n_seg, seed, self._stream, self._res_ref)
+        if inp.packed:
+            rc = self._push_packed(self._pipe, inp.arr, inp.n_pieces, inp._sc, inp.cell_dtype, seed, self._stream, self._res_ref)
+        else:
+            rc = self._push(self._pipe, inp.arr, inp.n_pieces, inp._ss, inp._sc, inp.n_seg, seed, self._stream, self._res_ref)
         if rc:
             N.check(rc, self.eng._ctx)
         self._inputs.append(inp)

@@ -97,3 +97,43 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.replace("# oracle-free", ""), f"{f} mentions the oracle"
+
+
+def test_packed_rows_round_trip_and_refusals(lib):
+    """slafb_pack_rows / slafb_unpack_rows (host only): lossless for any ascending gene ids and any uint16 values -- big deltas and
+    big values through the exception lists, empty cells, one-row cells, int32 gene ids -- at ~2 bytes per row for count data;
+    rows whose genes do not ascend are refused, not mangled."""
+    from slaf_b200 import synthetic
+    from slaf_b200.engine import pack_rows
+
+    rng = np.random.default_rng(0)
+    for n_genes, gdt in ((60000, np.uint16), (90000, np.int32)):
+        b = synthetic.make_batch(400, n_genes, 300, seed=7, min_nnz=1)
+        assert b.gene.dtype == gdt
+        value = b.value.copy()
+        value[rng.integers(0, len(value), 300)] = rng.integers(255, 65536, 300).astype(np.uint16)      # exceptions, incl. 255 itself
+        value[7] = 255
+        value[rng.integers(0, len(value), 50)] = 0
+        starts = np.concatenate((b.cell_start[:100], [b.cell_start[100]] * 3, b.cell_start[100:]))      # three empty cells
+        ids = np.arange(len(starts) - 1, dtype=np.uint32)
+        pk = pack_rows(b.gene, value, starts, ids)
+        g, v = pk.unpack()
+        assert np.array_equal(g, b.gene) and np.array_equal(v, value)
+        assert pk.nbytes % 16 == 0 and np.all(np.diff(pk.blk_off.astype(np.int64)) >= 1)
+        assert pk.nbytes < 10 * b.n_rows + 64 * len(ids)               # 300 of 60,000+ genes per cell: many gaps need the exception list
+        sub = pack_rows(b.gene, value, b.cell_start[50:81], ids[50:80])                                  # a cell range from the middle
+        g, v = sub.unpack()
+        lo, hi = int(b.cell_start[50]), int(b.cell_start[80])
+        assert np.array_equal(g, b.gene[lo:hi]) and np.array_equal(v, value[lo:hi])
+        bad = b.gene.copy()
+        r = int(b.cell_start[5]) + 1
+        bad[r] = bad[r - 1]                                                                             # a duplicate gene inside a cell
+        with pytest.raises(_native.SlafB200Error, match="do not ascend"):
+            pack_rows(bad, value, b.cell_start, np.arange(b.n_cells, dtype=np.uint32))
+    dense = synthetic.make_batch(200, 60000, 2000, seed=8)                 # the benchmark's shape: ~2 bytes per row
+    pk = pack_rows(dense.gene, dense.value, dense.cell_start, np.arange(dense.n_cells, dtype=np.uint32))
+    assert pk.nbytes < 2.06 * dense.n_rows + 48 * dense.n_cells
+    with pytest.raises(TypeError):
+        pack_rows(b.gene, b.value.astype(np.float32), b.cell_start, np.arange(b.n_cells, dtype=np.uint32))
+    empty = pack_rows(np.zeros(0, np.uint16), np.zeros(0, np.uint16), np.zeros(1, np.int64), np.zeros(0, np.uint32))
+    assert empty.n_cells == 0 and empty.nbytes == 0

@@ -558,3 +558,59 @@ def test_pipe_host_segments_route_and_csi_submit(engine):
             engine.submit_segments([(b.gene, b.value)], table, np.arange(100, 1000, dtype=np.uint32))
     got = engine.tokenize(b.cell, b.gene, b.value, shuffle_seed=5, **kw)
     assert torch.equal(got.input_ids, ref.input_ids)
+
+
+# ------------------------------------------------------------------------ round 2: packed wire format (f4)
+@pytest.mark.parametrize("gene_dtype", ["uint16", "int32"])
+@pytest.mark.parametrize("mode,pct", MODES)
+def test_packed_route_equals_the_unpacked_routes(engine, mode, pct, gene_dtype):
+    """slafb_submit_packed: ~2 bytes per row cross the bus and the tokenizing kernel decodes the blocks in shared memory; the
+    tensors are those of the COO route and of the oracle.  Adversarial cells (more rows than the stage holds, values and gene
+    gaps beyond a byte, one-row cells, real top-k cuts) in one piece and cut into three."""
+    from slaf_b200.engine import pack_rows
+
+    k = 64
+    cell, gene, value = adversarial_batch(23, "uint16", gene_dtype, "uint32", k=k)
+    heads = np.flatnonzero(np.r_[True, cell[1:] != cell[:-1]])
+    starts = np.r_[heads, len(cell)].astype(np.int64)
+    ids = cell[heads]
+    C = len(ids)
+    kw = dict(mode=mode, max_genes=k, n_bins=51, vocab_size=65000, min_percentile=pct)
+    want = c_oracle.tokenize(cell, gene, value, mode, k, perm=py_perm(9, C), n_bins=51, vocab_size=65000, min_percentile=pct)
+    whole = pack_rows(gene, value, starts, ids)
+    got = engine.collect(engine.submit_packed([whole]), shuffle_seed=9, **kw)
+    compare(got, want, mode)
+    cuts = [0, C // 3, C // 3 + 1, C]
+    pieces = [pack_rows(gene, value, starts[a:b + 1], ids[a:b], pin=True) for a, b in zip(cuts[:-1], cuts[1:])]
+    got = engine.collect(engine.submit_packed(pieces, shuffle_seed=9), shuffle_seed=9, **kw)
+    compare(got, want, mode)
+    for mg in (1, 7, 2048):                                               # widths around the stage sizes
+        kw2 = dict(kw, max_genes=mg, max_items=k)
+        want2 = c_oracle.tokenize(cell, gene, value, mode, mg, max_items=k, perm=py_perm(9, C), n_bins=51, vocab_size=65000, min_percentile=pct)
+        compare(engine.collect(engine.submit_packed([whole]), shuffle_seed=9, **kw2), want2, mode)
+
+
+def test_packed_route_synthetic_batch_and_pipe(engine):
+    from slaf_b200.engine import PreparedInput, pack_rows
+
+    b = synthetic.make_batch(3000, 60000, 2000, seed=91)
+    ids = b.cell[b.cell_start[:-1]]
+    pk = pack_rows(b.gene, b.value, b.cell_start, ids, pin=True)
+    assert pk.nbytes < 2.1 * b.n_rows + 48 * b.n_cells
+    for mode, kw in (("scgpt_binned", dict(max_genes=1200, n_bins=51, vocab_size=65000)), ("geneformer", dict(max_genes=2048)),
+                     ("geneformer_pct", dict(max_genes=2048, min_percentile=10.0)), ("scgpt_raw", dict(max_genes=512, n_bins=10, vocab_size=50000))):
+        want = c_oracle.tokenize(b.cell, b.gene, b.value, mode, kw["max_genes"], perm=py_perm(4, b.n_cells), n_bins=kw.get("n_bins", 10),
+                                 vocab_size=kw.get("vocab_size", 50000), min_percentile=kw.get("min_percentile"))
+        compare(engine.collect(engine.submit_packed([pk]), shuffle_seed=4, mode=mode, **kw), want, mode)
+    t = engine.timing()
+    assert t["csr_ms"] == 0.0                                             # no CSR build: the blocks are the cell boundaries
+    kw = dict(mode="scgpt_binned", max_genes=1200, n_bins=51, vocab_size=65000)
+    pipe = engine.pipe(ring=2, capacity_cells=3100, depth=1, **kw)
+    inp = PreparedInput([pk])
+    assert pipe.push(inp, 4)[0] < 0
+    ri, n, seq = pipe.push(inp, 5)
+    want = c_oracle.tokenize(b.cell, b.gene, b.value, "scgpt_binned", 1200, perm=py_perm(4, b.n_cells), n_bins=51, vocab_size=65000)
+    compare(pipe.batch(ri, n), want, "scgpt_binned")
+    pipe.close()
+    with pytest.raises(_native.SlafB200Error):
+        engine.collect_csr(engine.submit_packed([pk]))
