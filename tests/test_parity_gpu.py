@@ -597,6 +597,7 @@ def test_packed_route_synthetic_batch_and_pipe(engine):
     ids = b.cell[b.cell_start[:-1]]
     pk = pack_rows(b.gene, b.value, b.cell_start, ids, pin=True)
     assert pk.nbytes < 2.1 * b.n_rows + 48 * b.n_cells
+    engine.timing()                                                       # (counters since the previous test)
     for mode, kw in (("scgpt_binned", dict(max_genes=1200, n_bins=51, vocab_size=65000)), ("geneformer", dict(max_genes=2048)),
                      ("geneformer_pct", dict(max_genes=2048, min_percentile=10.0)), ("scgpt_raw", dict(max_genes=512, n_bins=10, vocab_size=50000))):
         want = c_oracle.tokenize(b.cell, b.gene, b.value, mode, kw["max_genes"], perm=py_perm(4, b.n_cells), n_bins=kw.get("n_bins", 10),
