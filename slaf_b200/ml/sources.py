@@ -151,6 +151,63 @@ class ArrayExpressionSource(ExpressionSource):
         self.pinned = False
 
 
+class PinnedCacheSource(ExpressionSource):
+    """The rows of another source copied ONCE into page-locked host memory (``cudaHostAlloc``), fragment structure and table
+    positions kept: every later epoch then reaches the GPU by DMA straight from these arrays, with no host copy per load.  This is
+    the resident-dataset mode for sources whose own memory cannot be page-locked (the driver refuses to register read-only file
+    mappings on many hosts) and that fit in RAM -- typically one rank's shard.  ``pin_cell=False`` keeps the cell column in
+    ordinary memory (the cell-start-index route never ships it; it is only probed on the host)."""
+
+    def __init__(self, source: ExpressionSource, pin_cell: bool = False, threads: int = 4):
+        from concurrent.futures import ThreadPoolExecutor
+
+        from ..engine import pinned_empty
+
+        frags = source.get_fragments()
+        pieces_per_frag = [f.to_pieces() for f in frags]
+        rows = [sum(len(p) for p in ps) for ps in pieces_per_frag]
+        total = sum(rows)
+        first = next((p for ps in pieces_per_frag for p in ps if len(p)), None)
+        if first is None:
+            self._fragments, self.rows, self.pinned = [], 0, True
+            return
+        self._cell = pinned_empty(total, first.cell.dtype) if pin_cell else np.empty(total, first.cell.dtype)
+        self._gene = pinned_empty(total, first.gene.dtype)
+        self._value = pinned_empty(total, first.value.dtype)
+        tasks, off = [], 0
+        self._fragments = []
+        for ps, n in zip(pieces_per_frag, rows):
+            row_lo = next((p.row_lo for p in ps if len(p)), None)
+            self._fragments.append(_ArrayFragment(CooChunk(self._cell[off:off + n], self._gene[off:off + n], self._value[off:off + n], row_lo)))
+            pos = off
+            for p in ps:
+                for lo in range(0, len(p), 1 << 21):
+                    hi = min(lo + (1 << 21), len(p))
+                    tasks.append((pos + lo, p, lo, hi))
+                pos += len(p)
+            off += n
+
+        def copy(t):
+            o, p, lo, hi = t
+            np.copyto(self._cell[o:o + hi - lo], p.cell[lo:hi])
+            np.copyto(self._gene[o:o + hi - lo], p.gene[lo:hi])
+            np.copyto(self._value[o:o + hi - lo], p.value[lo:hi])
+
+        if threads > 1 and len(tasks) > 1:
+            with ThreadPoolExecutor(max_workers=threads) as pool:
+                list(pool.map(copy, tasks))
+        else:
+            for t in tasks:
+                copy(t)
+        self.rows, self.pinned = total, True
+
+    def get_fragments(self) -> list[Fragment]:
+        return list(self._fragments)
+
+    def nbytes_pinned(self) -> int:
+        return 0 if not self._fragments else int(self._gene.nbytes + self._value.nbytes)
+
+
 # ------------------------------------------------------------------------------ Arrow IPC directory
 class _ArrowFileFragment(Fragment):
     def __init__(self, path: str):
