@@ -1111,7 +1111,6 @@ __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm<ValT, MODE>()) 
     constexpr bool PCT = (MODE == MODE_GF_PCT);
     constexpr bool U16 = (sizeof(ValT) == 2);
     static_assert(!PCT || U16, "percentile mode runs in this kernel for uint16 values only (float32: general kernel)");
-    static_assert(kPctWords % kFastThreads == 0, "every thread owns a whole number of bitmap words");
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ CellDesc s_desc[2];
@@ -1524,11 +1523,17 @@ __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm<ValT, MODE>()) 
                 defer = true;
             } else {
                 const uint32_t d0 = __popc(m0);                         // distinct values below 32
-                uint32_t D = d0, pc = 0, wv = 0, inc = 0, wbase = 0;
+                constexpr int WPT = (kPctWords + kFastThreads - 1) / kFastThreads;     // bitmap words per thread (contiguous)
+                uint32_t D = d0, pc = 0, wv[WPT], inc = 0, wbase = 0;
+#pragma unroll
+                for (int q2 = 0; q2 < WPT; q2++) wv[q2] = 0u;
                 if (dirty) {                                            // some value >= 32: count the bitmap's words 1 .. hi / 32
-                    static_assert(kPctWords <= kFastThreads, "one bitmap word per thread");
-                    wv = ((uint32_t)tid >= 1u && (uint32_t)tid <= (hi >> 5)) ? s_bitmap[tid] : 0u;
-                    pc = __popc(wv);
+#pragma unroll
+                    for (int q2 = 0; q2 < WPT; q2++) {
+                        const uint32_t wi = (uint32_t)tid * WPT + q2;
+                        wv[q2] = (wi >= 1u && wi <= (hi >> 5) && wi < (uint32_t)kPctWords) ? s_bitmap[wi] : 0u;
+                        pc += __popc(wv[q2]);
+                    }
                     inc = warp_incl_scan(pc);
                     __syncthreads();                                    // (everyone has read lo / hi / m0 from the scratch)
                     if (lane == 31) s_ws[warp] = inc;
@@ -1546,23 +1551,31 @@ __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm<ValT, MODE>()) 
                     for (uint32_t i = 1u; i < astar; i++) x &= x - 1u;  // drop the lower set bits (astar is small: a percentile of D)
                     thr = (uint32_t)(__ffs(x) - 1);
                 } else {                                                // it lies in the bitmap: the (astar - d0)-th set bit of words >= 1
-                    const uint32_t want = astar - d0, ex = wbase + inc - pc;
+                    const uint32_t want = astar - d0;
+                    uint32_t ex = wbase + inc - pc;
                     if (want > ex && want <= ex + pc) {
-                        uint32_t x = wv;
-                        for (uint32_t i = ex + 1u; i < want; i++) x &= x - 1u;
-                        s_thr = ((uint32_t)tid << 5) + (uint32_t)(__ffs(x) - 1);
+#pragma unroll
+                        for (int q2 = 0; q2 < WPT; q2++) {
+                            const uint32_t c2 = __popc(wv[q2]);
+                            if (want > ex && want <= ex + c2) {
+                                uint32_t x = wv[q2];
+                                for (uint32_t i = ex + 1u; i < want; i++) x &= x - 1u;
+                                s_thr = (((uint32_t)tid * WPT + q2) << 5) + (uint32_t)(__ffs(x) - 1);
+                            }
+                            ex += c2;
+                        }
                     }
                     __syncthreads();
                     thr = s_thr;
                 }
                 if (astar == 1u) keep_all = true;                       // every distinct value passes both rules
             }
-            if (!defer && !keep_all && nst == n && limit * (uint32_t)sizeof(GeneT) <= vbytes) {
+            if (!defer && !keep_all && nst == n && Q <= 8u && limit * (uint32_t)sizeof(GeneT) <= vbytes) {
                 // Row-order compaction, whole cell staged: flags from the values (phase A), ONE block scan, then every thread gathers
                 // the kept genes of its own rows into the value stage's memory (phase B; the values are not needed any more and
                 // everybody finished reading them before the scan's barrier).  The emission then reads a dense gene list from there.
                 const uint32_t thr2 = thr | (thr << 16);
-                uint32_t fl = 0u;                                       // 4 bits per chunk, Q <= 4 chunks
+                uint32_t fl = 0u;                                       // 4 bits per chunk, Q <= 8 chunks
                 for (uint32_t q = 0; q < Q; q++) {
                     const uint32_t c = (uint32_t)tid * Q + q;
                     if (c >= nch) break;

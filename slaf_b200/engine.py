@@ -756,10 +756,15 @@ def pinned_empty(n: int, dtype) -> np.ndarray:
     N.check(N.lib().slafb_host_alloc(ctypes.byref(ptr), nbytes))
     buf = (ctypes.c_char * nbytes).from_address(ptr.value)
     weakref.finalize(buf, _free_pinned, ptr.value)
+    _PINNED_ALLOCS[ptr.value] = nbytes           # so that is_page_locked() recognises views of it
     return np.frombuffer(buf, dtype=dtype, count=n)
 
 
+_PINNED_ALLOCS: dict[int, int] = {}     # base address -> bytes of live pinned_empty() allocations
+
+
 def _free_pinned(address: int) -> None:
+    _PINNED_ALLOCS.pop(address, None)
     try:
         N.lib().slafb_host_free(ctypes.c_void_p(address))
     except Exception:
@@ -811,10 +816,11 @@ def unregister_host_range(address: int) -> None:
 
 
 def is_page_locked(arr: np.ndarray) -> bool:
-    """True when `arr` lies inside memory registered through register_host_memory."""
+    """True when `arr` lies inside memory registered through register_host_memory or allocated by pinned_empty."""
     a = arr.ctypes.data
     b = a + arr.nbytes
-    for base, size in _REGISTERED.items():
-        if a >= base and b <= base + size:
-            return True
+    for table in (_REGISTERED, _PINNED_ALLOCS):
+        for base, size in table.items():
+            if a >= base and b <= base + size:
+                return True
     return False
