@@ -179,25 +179,3 @@ class Coordinator:
     def assign_partitions(self, seed: int = 42) -> dict[str, PartitionAssignment]:
         parts = assign_fragments(self.total_partitions, self.n_workers, seed=seed, shuffle=True)
         return {f"worker_{i}": PartitionAssignment(f"worker_{i}", p) for i, p in enumerate(parts)}
-
-
-def __getattr__(name: str):
-    # BatchProcessor / GroupBoundaryHandler / Window / Shuffle / DataSchema under the reference's package name, resolved
-    # lazily (slaf_b200.ml imports this module for the sharding helpers)
-    if name in ("BatchProcessor", "GroupBoundaryHandler"):
-        from .ml import distributed as _d
-
-        return getattr(_d, name)
-    if name == "Window":
-        from .ml.aggregators import GenericWindow
-
-        return GenericWindow
-    if name == "Shuffle":
-        from .ml.samplers import GenericShuffle
-
-        return GenericShuffle
-    if name == "DataSchema":
-        from .core.tabular_schema import DataSchema
-
-        return DataSchema
-    raise AttributeError(name)

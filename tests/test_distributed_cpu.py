@@ -137,4 +137,3 @@ def test_coordinator_mirror_matches_reference_assignment():
     idx = list(range(10))
     random.shuffle(idx)
     assert [got[f"worker_{i}"].partition_indices for i in range(3)] == [idx[:4], idx[4:7], idx[7:]]
-    assert D.Window is not None and D.Shuffle is not None and D.BatchProcessor is not None and D.DataSchema is not None
