@@ -1119,6 +1119,7 @@ __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm<ValT, MODE>()) 
     __shared__ uint32_t s_bitmap[PCT ? kPctWords : 1];   // percentile mode: which values of [32, 8192) occur in the cell (bit = value)
     __shared__ uint32_t s_thr;        // percentile mode: the smallest value that is kept
     __shared__ uint32_t s_dirty;      // percentile mode: the bitmap holds bits of the current cell (wiped when the cell is done)
+    __shared__ uint32_t s_ap[PCT ? 64 : 1];   // percentile mode: ceil(p * D / 100) for D < 64 (f64, evaluated once per CTA instead of per cell and thread)
     const TokArgs &a = fa.t;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t gbytes = fa.gcap * (uint32_t)sizeof(GeneT), vbytes = fa.vcap * (uint32_t)sizeof(ValT);
@@ -1134,7 +1135,10 @@ __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm<ValT, MODE>()) 
         mbar_fence_init();
         s_dirty = 0u;
     }
-    if constexpr (PCT) for (uint32_t w = tid; w < (uint32_t)kPctWords; w += kFastThreads) s_bitmap[w] = 0u;
+    if constexpr (PCT) {
+        for (uint32_t w = tid; w < (uint32_t)kPctWords; w += kFastThreads) s_bitmap[w] = 0u;
+        if (tid < 64) s_ap[tid] = target_asc_rank((uint32_t)tid, 0xffffffffu, true, a.min_pct);    // k = "infinite": the percentile term alone (>= 1)
+    }
     __syncthreads();
     // Rows are handed out IN ORDER by an atomic ticket (first row = blockIdx.x), so the rows being
     // written at any moment form one compact window of the output tensors -- measured 6.0 TB/s
@@ -1545,7 +1549,8 @@ __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm<ValT, MODE>()) 
                         D += t;
                     }
                 }
-                const uint32_t astar = target_asc_rank(D, k, true, a.min_pct);
+                // a* = max(D - min(k, D) + 1, ceil(p * D / 100)); the second term from the per-CTA table when D is small
+                const uint32_t astar = (D < 64u) ? max(D - min(k, D) + 1u, s_ap[D]) : target_asc_rank(D, k, true, a.min_pct);
                 if (astar <= d0) {                                      // the usual case: the threshold is one of the small values
                     uint32_t x = m0;
                     for (uint32_t i = 1u; i < astar; i++) x &= x - 1u;  // drop the lower set bits (astar is small: a percentile of D)
@@ -1604,6 +1609,7 @@ __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm<ValT, MODE>()) 
                     tot += t;
                 }
                 uint32_t off = wbase + inc - pc;
+                const bool room = off + pc <= limit;                    // all of this thread's kept genes are emitted: no per-row test
                 GeneT *dst = reinterpret_cast<GeneT *>(sv);
                 for (uint32_t q = 0; q < Q && fl; q++) {
                     const uint32_t c = (uint32_t)tid * Q + q, f4 = (fl >> (4u * q)) & 15u;
@@ -1620,7 +1626,7 @@ __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm<ValT, MODE>()) 
                     for (int i = 0; i < 4; i++) {
                         if (f4 & (1u << i)) {
                             SLAFB_CHECK(off >= limit || (off + 1u) * sizeof(GeneT) <= vbytes, 207, off);
-                            if (off < limit) dst[off] = g4[i];
+                            if (room || off < limit) dst[off] = g4[i];
                             off++;
                         }
                     }

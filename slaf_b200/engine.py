@@ -379,7 +379,7 @@ class HotPathEngine:
         dev = self.device
         crow = torch.zeros(cap_cells + 1, dtype=torch.int64, device=dev)
         col = torch.empty(max(n_rows, 1), dtype=torch.int32, device=dev)
-        vdt = torch.uint16 if keep[2].code == N.U16 else torch.float32
+        vdt = torch.uint16 if (len(keep) < 3 or getattr(keep[2], "code", N.U16) == N.U16) else torch.float32     # (packed batches: refused by the library below)
         val = torch.empty(max(n_rows, 1), dtype=vdt, device=dev)
         cids = torch.empty(cap_cells, dtype=torch.int64, device=dev)
         n, r = ctypes.c_int64(0), ctypes.c_int64(0)
