@@ -1885,9 +1885,6 @@ __global__ void __launch_bounds__(kTokThreads) tokenize_general_kernel(const Tok
     __shared__ TokSmem sm;
     __shared__ uint32_t s_item;
     extern __shared__ __align__(16) uint32_t dyn[];   // bitmap (u16) or sort keys (f32)
-    // launched with programmatic stream serialization behind the fast kernel (its launch latency hides under that kernel's tail):
-    // nothing the predecessor wrote -- the work list first of all -- may be read before this returns.  A no-op otherwise.
-    asm volatile("griddepcontrol.wait;" ::: "memory");
     const uint32_t count = a.all_cells ? a.n_cells : a.work_counters[0];
     if (blockIdx.x == 0 && threadIdx.x == 0 && a.host_slow) *a.host_slow = count;
     for (;;) {
@@ -2385,7 +2382,6 @@ __global__ void __launch_bounds__(kTokThreads) unpack_deferred_kernel(const uint
                                                                       GeneT *__restrict__ gene, uint16_t *__restrict__ value) {
     __shared__ uint32_t s_ws[kTokThreads / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    asm volatile("griddepcontrol.wait;" ::: "memory");      // (see tokenize_general_kernel)
     const uint32_t count = *work_count;
     for (uint32_t it = blockIdx.x; it < count; it += gridDim.x) {
         const uint32_t row = work_list[it];

@@ -324,19 +324,7 @@ int launch_general(slafb_ctx *ctx, const TokArgs &a, const WindowSink &w, cudaSt
     uint32_t grid = (uint32_t)(ctx->n_sm * per_sm);
     if (a.n_cells < grid) grid = a.n_cells;
     if (grid == 0) grid = 1;
-    if (!a.all_cells && SINK == 0) {
-        // behind a fast kernel in the same stream: programmatic dependent launch -- the grid is set up while the fast kernel
-        // drains and waits (griddepcontrol.wait) for its completion before it reads the work list
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kTokThreads); cfg.dynamicSmemBytes = dyn; cfg.stream = st;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        CU(ctx, cudaLaunchKernelEx(&cfg, kern, a, w));
-    } else {
-        kern<<<grid, kTokThreads, dyn, st>>>(a, w);
-    }
+    kern<<<grid, kTokThreads, dyn, st>>>(a, w);
     CU(ctx, cudaGetLastError());
     ctx->acc.kernel_launches++;
     return SLAFB_OK;
@@ -829,25 +817,12 @@ int back(slafb_ctx *ctx, Slot &s, const slafb_params *p, const slafb_out *out, i
             return fail(ctx, SLAFB_ERR_INVALID, "max_genes too large for the packed route");
         }
         const unsigned ugrid = (unsigned)ctx->n_sm * 2u;
-        {
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(ugrid); cfg.blockDim = dim3(kTokThreads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-            at[0].val.programmaticStreamSerializationAllowed = 1;
-            cfg.attrs = at; cfg.numAttrs = 1;
-            const uint8_t *pk = s.pk_bytes;
-            const uint32_t *bo = s.blk_off, *ss = s.seg_start, *wl = s.work_list, *wc = s.counters + 2;
-            const int32_t *pm = a.perm;
-            uint16_t *vsc = static_cast<uint16_t *>(s.in_value);
-            if (s.gene_dtype == SLAFB_U16) {
-                uint16_t *gsc = static_cast<uint16_t *>(s.in_cell);
-                CU(ctx, cudaLaunchKernelEx(&cfg, unpack_deferred_kernel<uint16_t>, pk, bo, ss, pm, wl, wc, gsc, vsc));
-            } else {
-                int32_t *gsc = static_cast<int32_t *>(s.in_cell);
-                CU(ctx, cudaLaunchKernelEx(&cfg, unpack_deferred_kernel<int32_t>, pk, bo, ss, pm, wl, wc, gsc, vsc));
-            }
-        }
+        if (s.gene_dtype == SLAFB_U16)
+            unpack_deferred_kernel<uint16_t><<<ugrid, kTokThreads, 0, st>>>(s.pk_bytes, s.blk_off, s.seg_start, a.perm, s.work_list, s.counters + 2,
+                                                                           static_cast<uint16_t *>(s.in_cell), static_cast<uint16_t *>(s.in_value));
+        else
+            unpack_deferred_kernel<int32_t><<<ugrid, kTokThreads, 0, st>>>(s.pk_bytes, s.blk_off, s.seg_start, a.perm, s.work_list, s.counters + 2,
+                                                                          static_cast<int32_t *>(s.in_cell), static_cast<uint16_t *>(s.in_value));
         CU(ctx, cudaGetLastError());
         ctx->acc.kernel_launches++;
     } else {
