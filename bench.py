@@ -483,10 +483,13 @@ def run_sharded(args, w):
     lo_seen = torch.full((), 1 << 62, dtype=torch.int64, device=dev)
     hi_seen = torch.full((), -1, dtype=torch.int64, device=dev)
     n_timed, t0, t1, started = 0, None, None, False
+    epoch_marks: dict[int, float] = {}            # wall time at the first batch of every epoch (per-epoch rates in the line)
     stage(f"sharded: rank {rank} reads rows [{lo}, {hi}) = cells [{c_lo}, {c_hi}), {n_epochs} epochs, route {route}, source page-locked: {pinned}")
     for batch in loader:
         ep = batch["epoch"]
         ids = batch["cell_ids"]
+        if ep not in epoch_marks:
+            epoch_marks[ep] = time.perf_counter()
         if ep == 0:
             cnt += ids.numel()
             ssum += ids.sum()
@@ -548,7 +551,8 @@ def run_sharded(args, w):
                            "note": "a step is one epoch of a rank's shard; host-resident input, so `value` is an end-to-end loader number (H2D inside)"},
                 "every_cell_exactly_once": {"checked": "count, sum, sum of squares mod 2^61-1 and xor of the emitted cell ids over all ranks; min / max / count per rank against its shard",
                                             "ok": bool(ok_all), "cells": got[0]},
-                "per_rank": {"cells_per_s": [round(x, 1) for x in rates], "h2d_gbs": [round(x, 2) for x in h2d], "seconds": tmax},
+                "per_rank": {"cells_per_s": [round(x, 1) for x in rates], "h2d_gbs": [round(x, 2) for x in h2d], "seconds": tmax,
+                             "rank0_cells_per_s_by_epoch": [round(shard_cells / (epoch_marks[e + 1] - epoch_marks[e]), 1) for e in sorted(epoch_marks)[:-1] if e + 1 in epoch_marks]},
                 "e2e": {"value": tot / tmax, "unit": "cells/s", "h2d_bytes_per_step": int(rows_timed * b_row // max(1, n_epochs - 2)), "d2h_bytes_per_step": 8 * 1024}}
         print(json.dumps(line), flush=True)
     if world > 1:
