@@ -942,7 +942,9 @@ class PrefetchBatchProcessor:
             return None
         t1 = time.time()
         order = sel[shuffle_perm(rec.seed, sel.size)]              # random.seed(seed); random.shuffle(chunks), samplers.py:89-96
-        out = eng.collect(slot, perm=order, capacity_cells=int(order.size), **self._params())
+        # (capacity rounded up to a multiple of 512 cells: prefetch batches of nearly equal size then ask the caching allocator for
+        # the SAME block sizes again and again instead of a new size per load -- new sizes are device-synchronising cudaMallocs)
+        out = eng.collect(slot, perm=order, capacity_cells=(int(order.size) + 511) & ~511, **self._params())
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(eng.device))
         tokenize_time = time.time() - t1
