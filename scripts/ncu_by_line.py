@@ -60,6 +60,6 @@ def text(loc):
             if cand not in src_cache: src_cache[cand] = open(cand).read().splitlines()
             return src_cache[cand][l - 1].strip()[:100]
     return ""
-for loc, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+for loc, a in sorted(agg.items(), key=lambda kv: -kv[1][1 if os.environ.get("BY_SAMPLES") else 0])[:top]:
     st = ", ".join(f"{k[6:]}={v}" for k, v in sorted(a[2].items(), key=lambda kv: -kv[1])[:3])
     print(f"{100*a[0]/tot_i:5.1f}% inst {100*a[1]/max(1,tot_s):5.1f}% samp  {loc}  {text(loc)}   [{st}]")

@@ -589,20 +589,21 @@ __device__ __forceinline__ void fill_zero_i64(long long *base, size_t A, size_t 
     }
 }
 
-// attention mask bytes for flat range [A, A+L): 1 for the first t_len, then 0; 16-byte stores inside
-__device__ __forceinline__ void fill_mask(uint8_t *base, size_t A, uint32_t L, uint32_t t_len) {
+// attention mask bytes for flat range [A, A+L): 1 for the first t_len, then 0; 16-byte stores inside.  The work is spread over
+// `nth` threads of which the caller is number `me` (a whole CTA, or one warp).
+__device__ __forceinline__ void fill_mask_by(uint8_t *base, size_t A, uint32_t L, uint32_t t_len, uint32_t me, uint32_t nth) {
     const uint32_t lead = (uint32_t)((16u - (uint32_t)(A & 15)) & 15u);     // bytes before the first aligned chunk
     // ragged head and tail: byte stores
     const uint32_t head = lead < L ? lead : L;
     const uint32_t body = (L - head) & ~15u;
     const uint32_t tail0 = head + body;
-    for (uint32_t i = threadIdx.x; i < head + (L - tail0); i += blockDim.x) {
+    for (uint32_t i = me; i < head + (L - tail0); i += nth) {
         const uint32_t t = i < head ? i : tail0 + (i - head);
         base[A + t] = (t < t_len) ? 1 : 0;
     }
     uint4 *chunks = reinterpret_cast<uint4 *>(base + A + head);
     const uint32_t nchunks = body >> 4;
-    for (uint32_t c = threadIdx.x; c < nchunks; c += blockDim.x) {
+    for (uint32_t c = me; c < nchunks; c += nth) {
         const uint32_t t = head + (c << 4);                                   // first token of the chunk
         uint4 v;
         if (t + 16u <= t_len) v = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
@@ -620,6 +621,9 @@ __device__ __forceinline__ void fill_mask(uint8_t *base, size_t A, uint32_t L, u
         }
         chunks[c] = v;
     }
+}
+__device__ __forceinline__ void fill_mask(uint8_t *base, size_t A, uint32_t L, uint32_t t_len) {
+    fill_mask_by(base, A, L, t_len, threadIdx.x, blockDim.x);
 }
 
 // value stream token for one kept row (scGPT modes)
@@ -1858,6 +1862,268 @@ __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm<ValT, MODE>()) 
             }
         }
         __syncthreads();   // every thread is done with stage `st` and the scratch before they are reused
+    }
+}
+
+// ---- K2w: percentile mode, ONE WARP PER CELL -------------------------------------------------------------------------------
+// The CTA-per-cell kernel above is issue-bound in percentile mode: 256 threads share ~2,100 rows, so the per-cell fixed work (block
+// scans, cross-warp reductions through shared memory, barriers, ragged-chunk handling in every warp) is paid by eight warps for
+// eight rows per thread -- 7,300 warp instructions per cell.  Here a warp owns a cell: the value and gene segments are bulk-copied
+// into the warp's private stage, every reduction is a `redux` / shuffle, the row-order compaction is a warp prefix per 256 rows,
+// and the emission is the same 128-bit store pattern with a stride of 32.  Warps take output rows in order from the same ticket,
+// so the rows in flight still form one compact window of the output tensors.  Cells longer than the stage, or with a value beyond
+// the bitmap, go to the work list for the general kernel.
+constexpr int kPctWarps = 4;                        // warps per CTA (three CTAs per SM with uint16 gene ids: 12 cells in flight per SM)
+template <typename GeneT>
+__host__ __device__ constexpr uint32_t pct_warp_bytes(uint32_t vcap) { return ((vcap * 2u + 127u) & ~127u) + ((vcap * (uint32_t)sizeof(GeneT) + 127u) & ~127u) + (uint32_t)kPctWords * 4u; }
+
+template <typename GeneT>
+__global__ void __launch_bounds__(kPctWarps * 32) tokenize_pct_warp_kernel(const FastArgs fa) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t s_bar[kPctWarps];
+    const TokArgs &a = fa.t;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t vbytes = (fa.vcap * 2u + 127u) & ~127u, gbytes = (fa.vcap * (uint32_t)sizeof(GeneT) + 127u) & ~127u;
+    uint8_t *mine = smem_raw + warp * pct_warp_bytes<GeneT>(fa.vcap);
+    uint16_t *sv = reinterpret_cast<uint16_t *>(mine);
+    GeneT *sg = reinterpret_cast<GeneT *>(mine + vbytes);
+    uint32_t *bitmap = reinterpret_cast<uint32_t *>(mine + vbytes + gbytes);
+    uint64_t *bar = &s_bar[warp];
+    const GeneT *__restrict__ gene_g = static_cast<const GeneT *>(a.gene);
+    const uint16_t *__restrict__ value_g = static_cast<const uint16_t *>(a.value);
+    const uint32_t R = a.n_rows, R8 = R & ~7u, k = a.max_items, L = a.L, limit = L - 1u;
+    const uint32_t NC = a.n_cells;
+    if (lane == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+    for (uint32_t w = lane; w < (uint32_t)kPctWords; w += 32u) bitmap[w] = 0u;
+    __syncwarp();
+    const uint32_t G = gridDim.x * (uint32_t)kPctWarps;
+    // the next cell's indices are fetched one cell ahead (ticket -> permutation entry -> segment bounds), so only the bulk copy
+    // itself is waited for in line
+    uint32_t jn = blockIdx.x * (uint32_t)kPctWarps + warp, cn = 0, sn = 0, en = 0;
+    if (jn < NC) { cn = a.perm ? (uint32_t)__ldg(a.perm + jn) : jn; sn = __ldg(a.seg_start + cn); en = __ldg(a.seg_start + cn + 1); }
+    uint32_t phase = 0u;
+    while (jn < NC) {
+        const uint32_t j = jn, c = cn, s = sn, e = en, n = e - s, a0 = s & ~7u, sh = s - a0;
+        const bool fits = n + 8u <= fa.vcap;
+        const uint32_t bulk_end = min((s + n + 7u) & ~7u, R8);
+        const uint32_t bulk = (fits && n && bulk_end > a0) ? bulk_end - a0 : 0u;          // rows staged by the bulk copies (multiple of 8)
+        if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the stage was written through the generic proxy (in-place compaction)
+            if (bulk) {
+                mbar_arrive_expect_tx(bar, bulk * (2u + (uint32_t)sizeof(GeneT)));
+                bulk_g2s(sv, value_g + a0, bulk * 2u, bar);
+                bulk_g2s(sg, gene_g + a0, bulk * (uint32_t)sizeof(GeneT), bar);
+            } else {
+                mbar_arrive(bar);
+            }
+            jn = G + atomicAdd(fa.ticket, 1u);
+        }
+        jn = __shfl_sync(0xffffffffu, jn, 0);
+        if (jn < NC) cn = a.perm ? (uint32_t)__ldg(a.perm + jn) : jn;        // (its latency hides under this cell's work)
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+        bool defer = !fits, keep_all = false;
+        uint32_t n_keep = n, thr = 0u, dirty = 0u;
+        if (!defer && n) {
+            // rows of the columns' last partial 8-group cannot be bulk-copied (16-byte granules)
+            if (s + n > R8 && lane < 8u) {
+                const uint32_t r = R8 + lane;
+                if (r < R && r >= a0 && r < s + n) { sv[r - a0] = value_g[r]; sg[r - a0] = gene_g[r]; }
+            }
+            __syncwarp();
+            // ---- one pass: range, presence of the values below 32 (register mask), larger values into the warp's bitmap
+            const uint32_t ngroups = (sh + n + 7u) >> 3;
+            const uint4 *sv4 = reinterpret_cast<const uint4 *>(sv);
+            volatile uint32_t *vb = bitmap;
+            uint32_t mn2 = 0xffffffffu, mx2 = 0u, m0 = 0u;
+            auto one = [&](uint32_t v) {
+                mn2 = __vminu2(mn2, v | (v << 16));
+                mx2 = __vmaxu2(mx2, v | (v << 16));
+                m0 |= shl_clamp(1u, v);
+                if (v >= 32u && v < (uint32_t)kPctBits) {
+                    const uint32_t bit = 1u << (v & 31u);
+                    dirty = 1u;
+                    if (!(vb[v >> 5] & bit)) atomicOr(&bitmap[v >> 5], bit);
+                }
+            };
+            for (uint32_t gi = lane; gi < ngroups; gi += 32u) {
+                const uint4 q = sv4[gi];
+                const uint32_t p0 = gi << 3, w4[4] = {q.x, q.y, q.z, q.w};
+                if (p0 >= sh && p0 + 8u <= sh + n) {
+                    mn2 = __vminu2(__vminu2(mn2, __vminu2(q.x, q.y)), __vminu2(q.z, q.w));
+                    mx2 = __vmaxu2(__vmaxu2(mx2, __vmaxu2(q.x, q.y)), __vmaxu2(q.z, q.w));
+#pragma unroll
+                    for (int i = 0; i < 4; i++) m0 |= shl_clamp(1u, w4[i] & 0xffffu) | shl_clamp(1u, w4[i] >> 16);
+                    if ((q.x | q.y | q.z | q.w) & 0xffe0ffe0u) {              // rare: a value >= 32
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            const uint32_t v = (w4[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
+                            if (v >= 32u) one(v);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const uint32_t pp = p0 + (uint32_t)i;
+                        if (pp >= sh && pp < sh + n) one((w4[i >> 1] >> ((i & 1) * 16)) & 0xffffu);
+                    }
+                }
+            }
+            const uint32_t hi = __reduce_max_sync(0xffffffffu, max(mx2 & 0xffffu, mx2 >> 16));
+            m0 = __reduce_or_sync(0xffffffffu, m0);
+            dirty = __reduce_or_sync(0xffffffffu, dirty);
+            if (hi >= (uint32_t)kPctBits) {
+                defer = true;
+            } else {
+                const uint32_t d0 = __popc(m0);
+                constexpr int WPL = kPctWords / 32;                           // bitmap words per lane (contiguous)
+                uint32_t D = d0, wv[WPL], pc = 0u;
+#pragma unroll
+                for (int q2 = 0; q2 < WPL; q2++) wv[q2] = 0u;
+                if (dirty) {
+                    __syncwarp();
+#pragma unroll
+                    for (int q2 = 0; q2 < WPL; q2++) {
+                        const uint32_t wi = lane * WPL + q2;
+                        wv[q2] = (wi >= 1u && wi <= (hi >> 5)) ? bitmap[wi] : 0u;
+                        pc += __popc(wv[q2]);
+                    }
+                    D += __reduce_add_sync(0xffffffffu, pc);
+                }
+                const uint32_t astar = target_asc_rank(D, k, true, a.min_pct);
+                if (astar <= d0) {
+                    uint32_t x = m0;
+                    for (uint32_t i = 1u; i < astar; i++) x &= x - 1u;
+                    thr = (uint32_t)(__ffs(x) - 1);
+                } else {                                                      // the (astar - d0)-th set bit of the bitmap's words >= 1
+                    const uint32_t want = astar - d0, inc = warp_incl_scan(pc);
+                    uint32_t ex = inc - pc, found = 0u;
+#pragma unroll
+                    for (int q2 = 0; q2 < WPL; q2++) {
+                        const uint32_t c2 = __popc(wv[q2]);
+                        if (want > ex && want <= ex + c2) {
+                            uint32_t x = wv[q2];
+                            for (uint32_t i = ex + 1u; i < want; i++) x &= x - 1u;
+                            found = ((lane * WPL + q2) << 5) + (uint32_t)(__ffs(x) - 1);
+                        }
+                        ex += c2;
+                    }
+                    thr = __reduce_max_sync(0xffffffffu, found);
+                }
+                keep_all = (astar == 1u);
+                if (!keep_all) {
+                    // ---- row-order compaction IN PLACE in the gene stage: 256 rows per step (8 per lane), a warp prefix gives the offsets
+                    const uint32_t thr2 = thr | (thr << 16);
+                    uint32_t base = 0u;
+                    for (uint32_t g0 = 0u; g0 < ngroups && base < limit; g0 += 32u) {
+                        const uint32_t gi = g0 + lane, p0 = gi << 3;
+                        uint32_t flags = 0u;
+                        GeneT g[8];
+                        if (gi < ngroups) {
+                            const uint4 q = sv4[gi];
+                            const uint32_t cx = __vcmpgeu2(q.x, thr2), cy = __vcmpgeu2(q.y, thr2), cz = __vcmpgeu2(q.z, thr2), cw = __vcmpgeu2(q.w, thr2);
+                            flags = (cx & 1u) | ((cx >> 15) & 2u) | ((cy & 1u) << 2) | ((cy >> 13) & 8u) | ((cz & 1u) << 4) | ((cz >> 11) & 32u) |
+                                    ((cw & 1u) << 6) | ((cw >> 9) & 128u);
+                            if (!(p0 >= sh && p0 + 8u <= sh + n)) {
+#pragma unroll
+                                for (int i = 0; i < 8; i++) {
+                                    const uint32_t pp = p0 + (uint32_t)i;
+                                    if (!(pp >= sh && pp < sh + n)) flags &= ~(1u << i);
+                                }
+                            }
+                            if constexpr (sizeof(GeneT) == 2) {
+                                const uint4 gq = reinterpret_cast<const uint4 *>(sg)[gi];
+                                const uint32_t g4[4] = {gq.x, gq.y, gq.z, gq.w};
+#pragma unroll
+                                for (int i = 0; i < 8; i++) g[i] = (GeneT)((g4[i >> 1] >> ((i & 1) * 16)) & 0xffffu);
+                            } else {
+                                const uint4 ga = reinterpret_cast<const uint4 *>(sg)[2u * gi], gb = reinterpret_cast<const uint4 *>(sg)[2u * gi + 1u];
+                                g[0] = (GeneT)ga.x; g[1] = (GeneT)ga.y; g[2] = (GeneT)ga.z; g[3] = (GeneT)ga.w;
+                                g[4] = (GeneT)gb.x; g[5] = (GeneT)gb.y; g[6] = (GeneT)gb.z; g[7] = (GeneT)gb.w;
+                            }
+                        }
+                        const uint32_t pcf = __popc(flags), inc = warp_incl_scan(pcf);
+                        uint32_t off = base + inc - pcf;
+                        __syncwarp();                                         // every lane holds its genes in registers: the stage may be overwritten
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            if (flags & (1u << i)) {
+                                SLAFB_CHECK(off >= limit || sh + off < fa.vcap, 231, sh + off);
+                                if (off < limit) sg[sh + off] = g[i];
+                                off++;
+                            }
+                        }
+                        base += __shfl_sync(0xffffffffu, inc, 31);
+                    }
+                    n_keep = base;
+                    __syncwarp();
+                }
+            }
+        }
+        if (jn < NC) { sn = __ldg(a.seg_start + cn); en = __ldg(a.seg_start + cn + 1); }   // next cell's bounds (cn has arrived by now)
+        if (defer) {
+            if (lane == 0) {
+                const uint32_t wi = atomicAdd(a.work_counters, 1u);
+                SLAFB_CHECK(wi < NC, 208, wi);
+                a.work_list[wi] = j;
+            }
+        } else {
+            // ---- emission: the CTA kernel's store pattern with a stride of 32 (token t of the row at flat index A + t)
+            const uint32_t n_emit = min(n_keep, limit);
+            const size_t A = (size_t)j * L;
+            const uint32_t off = (uint32_t)(A & 1);
+            long long *ids_al = a.ids + (A - off);
+            const uint32_t n_pairs = (L + off + 1u) >> 1;
+            auto id_tok = [&](long long t) -> long long {
+                if (t == 0) return 1ll;
+                if (t <= (long long)n_emit) {
+                    if constexpr (sizeof(GeneT) == 2) return (long long)sg[sh + (uint32_t)t - 1u] + 4ll;
+                    else return (long long)(int32_t)sg[sh + (uint32_t)t - 1u] + 4ll;
+                }
+                return (t == (long long)n_emit + 1) ? 2ll : 0ll;
+            };
+            const uint32_t p_lo = (off + 2u) >> 1;
+            const uint32_t p_hi = n_emit >= 1u ? (n_emit - 1u + off) / 2u + 1u : 0u;
+            SLAFB_CHECK(j < NC && sh + n_emit <= fa.vcap, 232, sh + n_emit);
+#pragma unroll 2
+            for (uint32_t p = p_lo + lane; p < p_hi; p += 32u) {
+                const uint32_t gi = sh + 2u * p - off - 1u;
+                long long x0, x1;
+                if constexpr (sizeof(GeneT) == 2) { x0 = (long long)sg[gi] + 4ll; x1 = (long long)sg[gi + 1] + 4ll; }
+                else { x0 = (long long)(int32_t)sg[gi] + 4ll; x1 = (long long)(int32_t)sg[gi + 1] + 4ll; }
+                store_pair(ids_al + 2u * p, x0, x1);
+            }
+            const uint32_t p_pad = (n_emit + 2u + off + 1u) >> 1;
+            const uint32_t p_full_end = (L + off) >> 1;
+            for (uint32_t p = p_pad + lane; p < p_full_end; p += 32u) store_pair(ids_al + 2u * p, 0ll, 0ll);
+            {
+                const uint32_t nb_head = min(p_lo, n_pairs);
+                const uint32_t mid_lo = max(p_hi, p_lo), mid_hi = min(max(p_pad, mid_lo), n_pairs);
+                const uint32_t tail_lo = max(p_full_end, mid_hi);
+                const uint32_t n_b = nb_head + (mid_hi - mid_lo) + (n_pairs - tail_lo);
+                for (uint32_t i = lane; i < n_b; i += 32u) {
+                    uint32_t p;
+                    if (i < nb_head) p = i;
+                    else if (i < nb_head + (mid_hi - mid_lo)) p = mid_lo + (i - nb_head);
+                    else p = tail_lo + (i - nb_head - (mid_hi - mid_lo));
+                    const long long t0 = (long long)(2u * p) - (long long)off, t1 = t0 + 1;
+                    const bool v0 = t0 >= 0, v1 = t1 < (long long)L;
+                    const long long x0 = v0 ? id_tok(t0) : 0ll, x1 = v1 ? id_tok(t1) : 0ll;
+                    if (v0 && v1) *reinterpret_cast<longlong2 *>(ids_al + 2u * p) = make_longlong2(x0, x1);
+                    else if (v0) ids_al[2u * p] = x0;
+                    else if (v1) ids_al[2u * p + 1] = x1;
+                }
+            }
+            fill_mask_by(a.mask, A, L, min(n_emit + 2u, L), lane, 32u);
+            if (lane == 0) {
+                const uint32_t cid = __ldg(a.seg_cell + c);
+                a.cell_ids[j] = a.cell_signed ? (long long)(int32_t)cid : (long long)cid;
+            }
+        }
+        if (dirty) {
+            for (uint32_t w = lane; w < (uint32_t)kPctWords; w += 32u) bitmap[w] = 0u;
+        }
+        __syncwarp();          // the stage and the bitmap are free for the next cell
     }
 }
 

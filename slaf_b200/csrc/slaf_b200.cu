@@ -354,6 +354,42 @@ int launch_rank(slafb_ctx *ctx, const RankArgs &ra, cudaStream_t st) {
     return SLAFB_OK;
 }
 
+// percentile mode on uint16 values: one warp per cell (kernels.cuh, K2w)
+template <typename GeneT>
+int launch_pct_warp(slafb_ctx *ctx, const TokArgs &a, cudaStream_t st, bool *launched) {
+    *launched = false;
+    FastArgs fa;
+    memset(&fa, 0, sizeof fa);
+    fa.t = a;
+    const uint32_t limit = a.L - 1u;
+    uint32_t vcap = 4104u;
+    if (limit + 24u > vcap) vcap = (limit + 24u + 7u) & ~7u;
+    fa.vcap = fa.gcap = vcap;
+    fa.ticket = a.work_counters + 2;
+    const size_t smem = (size_t)kPctWarps * pct_warp_bytes<GeneT>(vcap);
+    if (smem > 200 * 1024) return SLAFB_OK;         // very wide rows: the CTA kernel / general kernel take them
+    auto kern = tokenize_pct_warp_kernel<GeneT>;
+    static std::atomic<int> per_sm_cached[64];
+    static std::atomic<size_t> smem_cached[64];
+    int per_sm = per_sm_cached[ctx->device & 63].load(std::memory_order_acquire);
+    if (per_sm == 0 || smem_cached[ctx->device & 63].load() != smem) {
+        CU(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPctWarps * 32, smem));
+        if (per_sm < 1) per_sm = 1;
+        smem_cached[ctx->device & 63].store(smem);
+        per_sm_cached[ctx->device & 63].store(per_sm, std::memory_order_release);
+    }
+    uint32_t grid = (uint32_t)(ctx->n_sm * per_sm);
+    const uint32_t need = (a.n_cells + kPctWarps - 1) / kPctWarps;
+    if (need < grid) grid = need;
+    if (grid == 0) grid = 1;
+    kern<<<grid, kPctWarps * 32, smem, st>>>(fa);
+    CU(ctx, cudaGetLastError());
+    ctx->acc.kernel_launches++;
+    *launched = true;
+    return SLAFB_OK;
+}
+
 template <typename GeneT, typename ValT>
 int dispatch_fast(slafb_ctx *ctx, int mode, const TokArgs &a, cudaStream_t st, bool *launched) {
     switch (mode) {
@@ -361,9 +397,16 @@ int dispatch_fast(slafb_ctx *ctx, int mode, const TokArgs &a, cudaStream_t st, b
     case MODE_SCGPT_RAW: return launch_fast<GeneT, ValT, MODE_SCGPT_RAW>(ctx, a, st, launched);
     case MODE_SCGPT_BINNED: return launch_fast<GeneT, ValT, MODE_SCGPT_BINNED>(ctx, a, st, launched);
     case MODE_GF_PCT:
-        // uint16 values: presence bitmap in shared memory; float32 values need a sort per cell (general kernel)
-        if constexpr (sizeof(ValT) == 2) return launch_fast<GeneT, ValT, MODE_GF_PCT>(ctx, a, st, launched);
-        else { *launched = false; return SLAFB_OK; }
+        // uint16 values: one warp per cell (K2w), or the CTA-per-cell variant with SLAFB_PCT_CTA=1 (A/B); float32 values need a sort
+        // per cell (general kernel)
+        if constexpr (sizeof(ValT) == 2) {
+            static const bool use_cta = [] { const char *e = getenv("SLAFB_PCT_CTA"); return e && atoi(e) != 0; }();
+            if (!use_cta) {
+                int rc = launch_pct_warp<GeneT>(ctx, a, st, launched);
+                if (rc || *launched) return rc;
+            }
+            return launch_fast<GeneT, ValT, MODE_GF_PCT>(ctx, a, st, launched);
+        } else { *launched = false; return SLAFB_OK; }
     default: *launched = false; return SLAFB_OK;
     }
 }
