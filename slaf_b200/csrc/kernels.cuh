@@ -1868,106 +1868,197 @@ __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm<ValT, MODE>()) 
 // ---- K2w: percentile mode, ONE WARP PER CELL -------------------------------------------------------------------------------
 // The CTA-per-cell kernel above is issue-bound in percentile mode: 256 threads share ~2,100 rows, so the per-cell fixed work (block
 // scans, cross-warp reductions through shared memory, barriers, ragged-chunk handling in every warp) is paid by eight warps for
-// eight rows per thread -- 7,300 warp instructions per cell.  Here a warp owns a cell: the value and gene segments are bulk-copied
-// into the warp's private stage, every reduction is a `redux` / shuffle, the row-order compaction is a warp prefix per 256 rows,
-// and the emission is the same 128-bit store pattern with a stride of 32.  Warps take output rows in order from the same ticket,
-// so the rows in flight still form one compact window of the output tensors.  Cells longer than the stage, or with a value beyond
-// the bitmap, go to the work list for the general kernel.
-constexpr int kPctWarps = 4;                        // warps per CTA (three CTAs per SM with uint16 gene ids: 12 cells in flight per SM)
-template <typename GeneT>
-__host__ __device__ constexpr uint32_t pct_warp_bytes(uint32_t vcap) { return ((vcap * 2u + 127u) & ~127u) + ((vcap * (uint32_t)sizeof(GeneT) + 127u) & ~127u) + (uint32_t)kPctWords * 4u; }
+// eight rows per thread -- 7,300 warp instructions per cell.  Here a warp owns a cell: every reduction is a `redux` / ballot, the
+// row-order compaction is a warp prefix per 256 rows with predicated (branch-free) stores, and the emission is the same 128-bit
+// store pattern with a stride of 32.  Warps take output rows in order from the same ticket, so the rows in flight still form one
+// compact window of the output tensors.
+//   The gene segment is bulk-copied into the warp's private stage (the emission reads it in place when nothing is filtered).  The
+// values are either bulk-copied as well (VSTAGE) or read with 128-bit loads straight from global memory -- twice, the second time
+// from L2 -- which halves the shared memory per warp and doubles the warps per SM.  Of a cell longer than the stage the head is
+// staged and the rows beyond it are read from global memory (two loads per lane in flight); their kept genes land behind the
+// head's survivors in the gene stage (at most L - 2 genes are ever emitted, and the stage holds that many).  Only a value beyond
+// the bitmap sends a cell to the general kernel.
+constexpr int kPctWarps = 4;                        // warps per CTA
+template <typename GeneT, bool VSTAGE>
+__host__ __device__ constexpr uint32_t pct_warp_bytes(uint32_t vcap) {
+    return (VSTAGE ? ((vcap * 2u + 127u) & ~127u) : 0u) + ((vcap * (uint32_t)sizeof(GeneT) + 127u) & ~127u) + (uint32_t)kPctWords * 4u;
+}
 
+// predicated shared-memory store of one gene id + pointer bump (no branch: the compiler turns `if (bit) { *p++ = g; }` into one)
 template <typename GeneT>
+__device__ __forceinline__ void sts_if(uint32_t &addr, GeneT g, uint32_t bit) {
+    if constexpr (sizeof(GeneT) == 2) {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.u16 [%0], %1;\n\t@p add.u32 %0, %0, 2;\n\t}"
+                     : "+r"(addr) : "h"((uint16_t)g), "r"(bit) : "memory");
+    } else {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.u32 [%0], %1;\n\t@p add.u32 %0, %0, 4;\n\t}"
+                     : "+r"(addr) : "r"((uint32_t)g), "r"(bit) : "memory");
+    }
+}
+
+template <typename GeneT, bool VSTAGE>
 __global__ void __launch_bounds__(kPctWarps * 32) tokenize_pct_warp_kernel(const FastArgs fa) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_bar[kPctWarps];
     const TokArgs &a = fa.t;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t vbytes = (fa.vcap * 2u + 127u) & ~127u, gbytes = (fa.vcap * (uint32_t)sizeof(GeneT) + 127u) & ~127u;
-    uint8_t *mine = smem_raw + warp * pct_warp_bytes<GeneT>(fa.vcap);
+    const uint32_t vbytes = VSTAGE ? ((fa.vcap * 2u + 127u) & ~127u) : 0u, gbytes = (fa.vcap * (uint32_t)sizeof(GeneT) + 127u) & ~127u;
+    uint8_t *mine = smem_raw + warp * pct_warp_bytes<GeneT, VSTAGE>(fa.vcap);
     uint16_t *sv = reinterpret_cast<uint16_t *>(mine);
     GeneT *sg = reinterpret_cast<GeneT *>(mine + vbytes);
     uint32_t *bitmap = reinterpret_cast<uint32_t *>(mine + vbytes + gbytes);
     uint64_t *bar = &s_bar[warp];
     const GeneT *__restrict__ gene_g = static_cast<const GeneT *>(a.gene);
     const uint16_t *__restrict__ value_g = static_cast<const uint16_t *>(a.value);
-    const uint32_t R = a.n_rows, R8 = R & ~7u, k = a.max_items, L = a.L, limit = L - 1u;
+    const uint32_t R = a.n_rows, k = a.max_items, L = a.L, limit = L - 1u;
     const uint32_t NC = a.n_cells;
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t gcap = (fa.vcap >> 3) & ~31u;                            // 8-row groups the stage holds (a multiple of the warp width)
     if (lane == 0) { mbar_init(bar, 1); mbar_fence_init(); }
     for (uint32_t w = lane; w < (uint32_t)kPctWords; w += 32u) bitmap[w] = 0u;
     __syncwarp();
     const uint32_t G = gridDim.x * (uint32_t)kPctWarps;
-    // the next cell's indices are fetched one cell ahead (ticket -> permutation entry -> segment bounds), so only the bulk copy
-    // itself is waited for in line
-    uint32_t jn = blockIdx.x * (uint32_t)kPctWarps + warp, cn = 0, sn = 0, en = 0;
-    if (jn < NC) { cn = a.perm ? (uint32_t)__ldg(a.perm + jn) : jn; sn = __ldg(a.seg_start + cn); en = __ldg(a.seg_start + cn + 1); }
+    // the next cell's indices are fetched one cell ahead (ticket -> permutation entry -> segment bounds and cell id), so only the
+    // bulk copy itself is waited for in line
+    uint32_t jn = blockIdx.x * (uint32_t)kPctWarps + warp, cn = 0, sn = 0, en = 0, cidn = 0;
+    if (jn < NC) {
+        cn = a.perm ? (uint32_t)__ldg(a.perm + jn) : jn;
+        sn = __ldg(a.seg_start + cn); en = __ldg(a.seg_start + cn + 1); cidn = __ldg(a.seg_cell + cn);
+    }
     uint32_t phase = 0u;
     while (jn < NC) {
-        const uint32_t j = jn, c = cn, s = sn, e = en, n = e - s, a0 = s & ~7u, sh = s - a0;
-        const bool fits = n + 8u <= fa.vcap;
-        const uint32_t bulk_end = min((s + n + 7u) & ~7u, R8);
-        const uint32_t bulk = (fits && n && bulk_end > a0) ? bulk_end - a0 : 0u;          // rows staged by the bulk copies (multiple of 8)
+        const uint32_t j = jn, s = sn, e = en, cid = cidn, n = e - s, a0 = s & ~7u, sh = s - a0;
+        // The cell's rows lie in `ngroups` aligned 8-row groups of the columns.  The hot loops below only ever touch groups that
+        // can be read with one 128-bit load: all but the column's last partial group (`colend`; it can only be the last group of
+        // the last cell), whose rows are visited one by one.  The first `ngs` groups are staged, the others read from global memory.
+        const uint32_t ngroups = (sh + n + 7u) >> 3;
+        const uint32_t colend = (n && a0 + (ngroups << 3) > R) ? 1u : 0u;
+        const uint32_t ghot = ngroups - colend;
+        const uint32_t ngs = min(ghot, gcap);
+        const uint32_t bulk = n ? (ngs << 3) : 0u;                          // rows staged by the bulk copies
         if (lane == 0) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the stage was written through the generic proxy (in-place compaction)
             if (bulk) {
-                mbar_arrive_expect_tx(bar, bulk * (2u + (uint32_t)sizeof(GeneT)));
-                bulk_g2s(sv, value_g + a0, bulk * 2u, bar);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the stage was written through the generic proxy (in-place compaction)
+                mbar_arrive_expect_tx(bar, bulk * ((VSTAGE ? 2u : 0u) + (uint32_t)sizeof(GeneT)));
+                if constexpr (VSTAGE) bulk_g2s(sv, value_g + a0, bulk * 2u, bar);
                 bulk_g2s(sg, gene_g + a0, bulk * (uint32_t)sizeof(GeneT), bar);
-            } else {
-                mbar_arrive(bar);
             }
             jn = G + atomicAdd(fa.ticket, 1u);
         }
+        const uint4 *sv4 = reinterpret_cast<const uint4 *>(sv);
+        // values of rows a0 + 8 gi .. a0 + 8 gi + 7 (two per word); gi < ghot
+        auto ldv8 = [&](uint32_t gi) -> uint4 {
+            if (VSTAGE && gi < ngs) return sv4[gi];
+            return __ldg(reinterpret_cast<const uint4 *>(value_g + a0 + (gi << 3)));
+        };
+        // gene ids of the same rows as raw words: two per word in .a (uint16), or one per word in .a and .b (int32); gi < ghot
+        struct G8 { uint4 a, b; };
+        auto ldg8 = [&](uint32_t gi) -> G8 {
+            G8 r;
+            r.b = make_uint4(0u, 0u, 0u, 0u);
+            if (gi < ngs) {
+                if constexpr (sizeof(GeneT) == 2) r.a = reinterpret_cast<const uint4 *>(sg)[gi];
+                else { r.a = reinterpret_cast<const uint4 *>(sg)[2u * gi]; r.b = reinterpret_cast<const uint4 *>(sg)[2u * gi + 1u]; }
+            } else {
+                const uint4 *gp = reinterpret_cast<const uint4 *>(gene_g + a0 + (gi << 3));
+                r.a = __ldg(gp);
+                if constexpr (sizeof(GeneT) == 4) r.b = __ldg(gp + 1);
+            }
+            return r;
+        };
+        // which of the 8 rows of the group starting at row a0 + p0 belong to the cell (bit i = row a0 + p0 + i); p0 < sh + n
+        auto group_mask = [&](uint32_t p0) -> uint32_t {
+            const int lo_i = max((int)sh - (int)p0, 0);                     // 0..7: only group 0 starts before the cell
+            const int hi_i = min((int)(sh + n) - (int)p0, 8);               // 1..8
+            return (0xffu >> (8 - hi_i)) & (0xffu << lo_i) & 0xffu;
+        };
+        bool defer = false, keep_all = false;
+        uint32_t n_keep = n, thr = 0u, dirty = 0u;
+        uint32_t mx2 = 0u, m0 = 0u, rare = 0u;
+        volatile uint32_t *vb = bitmap;
+        // one row (the slow paths): maximum, presence bit -- in the register mask below 32, in the warp's bitmap above
+        auto one = [&](uint32_t v) {
+            mx2 = __vmaxu2(mx2, v | (v << 16));
+            m0 |= shl_clamp(1u, v);
+            if (v >= 32u && v < (uint32_t)kPctBits) {
+                const uint32_t bit = 1u << (v & 31u);
+                dirty = 1u;
+                if (!(vb[v >> 5] & bit)) atomicOr(&bitmap[v >> 5], bit);
+            }
+        };
+        auto eight = [&](const uint4 q, uint32_t valid) {
+            uint64_t lo = (uint64_t)q.x | ((uint64_t)q.y << 32), hi = (uint64_t)q.z | ((uint64_t)q.w << 32);
+#pragma unroll 1
+            for (uint32_t i = 0; i < 8u; i++) {
+                const uint32_t v = (uint32_t)lo & 0xffffu;
+                lo = (lo >> 16) | (hi << 48);
+                hi >>= 16;
+                if ((valid >> i) & 1u) one(v);
+            }
+        };
+        // ---- pass 1: maximum and presence of the values.  The sweeps are branch-free and cover the groups that lie wholly inside the
+        // cell, [gw0, gw1): packed maximum, presence of the values below 32 in a register mask, and a flag if any value is larger.
+        const uint32_t gw0 = sh ? 1u : 0u, gw1 = min(ghot, (sh + n) >> 3);
+        auto sweep = [&](const uint4 q, uint32_t gi) {
+            const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+            uint32_t bits = 0u;
+#pragma unroll
+            for (int i = 0; i < 4; i++) bits |= shl_clamp(1u, w4[i] & 0xffffu) | shl_clamp(1u, w4[i] >> 16);
+            const uint32_t mx = __vmaxu2(__vmaxu2(q.x, q.y), __vmaxu2(q.z, q.w));
+            const bool in = gi >= gw0 && gi < gw1;
+            mx2 = __vmaxu2(mx2, in ? mx : 0u);
+            m0 |= in ? bits : 0u;
+            rare |= in ? ((q.x | q.y | q.z | q.w) & 0xffe0ffe0u) : 0u;
+        };
+        // the ragged first / last group of the cell goes row by row in lanes 0 / 1 (after the sweeps); without a value stage their
+        // loads are issued here, ahead of the sweep
+        const uint32_t rgi = lane ? ngroups - 1u : 0u;
+        const bool rneed = n && lane < 2u && (lane ? (rgi >= gw1 && rgi >= gw0) : (sh != 0u));
+        uint4 rq = make_uint4(0u, 0u, 0u, 0u);
+        if constexpr (!VSTAGE) { if (rneed && rgi < ghot) rq = ldv8(rgi); }
+        const uint32_t gfirst = VSTAGE ? ngs : 0u;                          // groups [gfirst, ghot): values from global memory
+        if (gfirst < ghot) {
+            // two 128-bit loads per lane are outstanding while a group is processed (clamped indices: the warp stays converged);
+            // this runs while the bulk copy is in flight
+            const uint32_t glast = ghot - 1u;
+            uint4 qn = ldv8(min(gfirst + lane, glast)), qn2 = ldv8(min(gfirst + lane + 32u, glast));
+            for (uint32_t g0 = gfirst; g0 < ghot; g0 += 32u) {
+                const uint4 q = qn;
+                qn = qn2;
+                qn2 = ldv8(min(g0 + lane + 64u, glast));
+                sweep(q, g0 + lane);
+            }
+        }
         jn = __shfl_sync(0xffffffffu, jn, 0);
         if (jn < NC) cn = a.perm ? (uint32_t)__ldg(a.perm + jn) : jn;        // (its latency hides under this cell's work)
-        mbar_wait(bar, phase);
-        phase ^= 1u;
-        bool defer = !fits, keep_all = false;
-        uint32_t n_keep = n, thr = 0u, dirty = 0u;
-        if (!defer && n) {
-            // rows of the columns' last partial 8-group cannot be bulk-copied (16-byte granules)
-            if (s + n > R8 && lane < 8u) {
-                const uint32_t r = R8 + lane;
-                if (r < R && r >= a0 && r < s + n) { sv[r - a0] = value_g[r]; sg[r - a0] = gene_g[r]; }
+        if (bulk) {
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+        }
+        if (n) {
+            if constexpr (VSTAGE) {
+                for (uint32_t g0 = 0u; g0 < ngs; g0 += 32u) sweep(sv4[min(g0 + lane, ngs - 1u)], g0 + lane);
+            }
+            // the slow paths, row by row: the ragged first / last group (lanes 0 / 1), the column's last partial group, and -- for
+            // cells that have one -- every group with a value of 32 or more
+            if (rneed) {
+                const uint32_t r0 = a0 + (rgi << 3), valid = group_mask(rgi << 3);
+                if (rgi < ghot) {
+                    eight(VSTAGE ? ldv8(rgi) : rq, valid);
+                } else {
+                    for (uint32_t i = 0; i < 8u; i++) if ((valid >> i) & 1u) one((uint32_t)__ldg(value_g + r0 + i));
+                }
             }
             __syncwarp();
-            // ---- one pass: range, presence of the values below 32 (register mask), larger values into the warp's bitmap
-            const uint32_t ngroups = (sh + n + 7u) >> 3;
-            const uint4 *sv4 = reinterpret_cast<const uint4 *>(sv);
-            volatile uint32_t *vb = bitmap;
-            uint32_t mn2 = 0xffffffffu, mx2 = 0u, m0 = 0u;
-            auto one = [&](uint32_t v) {
-                mn2 = __vminu2(mn2, v | (v << 16));
-                mx2 = __vmaxu2(mx2, v | (v << 16));
-                m0 |= shl_clamp(1u, v);
-                if (v >= 32u && v < (uint32_t)kPctBits) {
-                    const uint32_t bit = 1u << (v & 31u);
-                    dirty = 1u;
-                    if (!(vb[v >> 5] & bit)) atomicOr(&bitmap[v >> 5], bit);
-                }
-            };
-            for (uint32_t gi = lane; gi < ngroups; gi += 32u) {
-                const uint4 q = sv4[gi];
-                const uint32_t p0 = gi << 3, w4[4] = {q.x, q.y, q.z, q.w};
-                if (p0 >= sh && p0 + 8u <= sh + n) {
-                    mn2 = __vminu2(__vminu2(mn2, __vminu2(q.x, q.y)), __vminu2(q.z, q.w));
-                    mx2 = __vmaxu2(__vmaxu2(mx2, __vmaxu2(q.x, q.y)), __vmaxu2(q.z, q.w));
-#pragma unroll
-                    for (int i = 0; i < 4; i++) m0 |= shl_clamp(1u, w4[i] & 0xffffu) | shl_clamp(1u, w4[i] >> 16);
-                    if ((q.x | q.y | q.z | q.w) & 0xffe0ffe0u) {              // rare: a value >= 32
-#pragma unroll
-                        for (int i = 0; i < 8; i++) {
-                            const uint32_t v = (w4[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
-                            if (v >= 32u) one(v);
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        const uint32_t pp = p0 + (uint32_t)i;
-                        if (pp >= sh && pp < sh + n) one((w4[i >> 1] >> ((i & 1) * 16)) & 0xffffu);
+            if (__any_sync(0xffffffffu, rare != 0u)) {
+                for (uint32_t g0 = gw0; g0 < gw1; g0 += 32u) {
+                    const uint32_t gi = g0 + lane;
+                    if (gi < gw1) {
+                        const uint4 q = ldv8(gi);
+                        if ((q.x | q.y | q.z | q.w) & 0xffe0ffe0u) eight(q, 0xffu);
                     }
                 }
+                __syncwarp();
             }
             const uint32_t hi = __reduce_max_sync(0xffffffffu, max(mx2 & 0xffffu, mx2 >> 16));
             m0 = __reduce_or_sync(0xffffffffu, m0);
@@ -2011,57 +2102,84 @@ __global__ void __launch_bounds__(kPctWarps * 32) tokenize_pct_warp_kernel(const
                     thr = __reduce_max_sync(0xffffffffu, found);
                 }
                 keep_all = (astar == 1u);
-                if (!keep_all) {
-                    // ---- row-order compaction IN PLACE in the gene stage: 256 rows per step (8 per lane), a warp prefix gives the offsets
-                    const uint32_t thr2 = thr | (thr << 16);
+                if (jn < NC) { sn = __ldg(a.seg_start + cn); en = __ldg(a.seg_start + cn + 1); cidn = __ldg(a.seg_cell + cn); }   // (cn has arrived by now)
+                if (!keep_all || ngs < ngroups) {
+                    // ---- row-order compaction: 256 rows per step (8 per lane), offsets from a warp prefix over the lanes' counts,
+                    // IN PLACE in the gene stage (a kept gene never moves to a higher index; the genes of the rows beyond the stage
+                    // come from global memory and land behind the staged ones' survivors).  The loads of the next step are issued
+                    // before this step is processed: they read rows beyond everything this step writes.
+                    const uint32_t thr2 = keep_all ? 0u : (thr | (thr << 16));
+                    const uint32_t sg_addr = smem_u32(sg + sh);
                     uint32_t base = 0u;
-                    for (uint32_t g0 = 0u; g0 < ngroups && base < limit; g0 += 32u) {
-                        const uint32_t gi = g0 + lane, p0 = gi << 3;
-                        uint32_t flags = 0u;
-                        GeneT g[8];
-                        if (gi < ngroups) {
-                            const uint4 q = sv4[gi];
+                    if (ghot) {
+                        const uint32_t glast = ghot - 1u;
+                        uint4 qvn = ldv8(min(lane, glast));
+                        G8 qgn = ldg8(min(lane, glast));
+                        for (uint32_t g0 = 0u; g0 < ghot && base < limit; g0 += 32u) {
+                            const uint32_t gi = g0 + lane, p0 = gi << 3;
+                            const uint4 q = qvn;
+                            const G8 gq = qgn;
+                            qvn = ldv8(min(gi + 32u, glast));                    // (clamped, not predicated: the warp stays converged)
+                            qgn = ldg8(min(gi + 32u, glast));
                             const uint32_t cx = __vcmpgeu2(q.x, thr2), cy = __vcmpgeu2(q.y, thr2), cz = __vcmpgeu2(q.z, thr2), cw = __vcmpgeu2(q.w, thr2);
-                            flags = (cx & 1u) | ((cx >> 15) & 2u) | ((cy & 1u) << 2) | ((cy >> 13) & 8u) | ((cz & 1u) << 4) | ((cz >> 11) & 32u) |
-                                    ((cw & 1u) << 6) | ((cw >> 9) & 128u);
-                            if (!(p0 >= sh && p0 + 8u <= sh + n)) {
-#pragma unroll
-                                for (int i = 0; i < 8; i++) {
-                                    const uint32_t pp = p0 + (uint32_t)i;
-                                    if (!(pp >= sh && pp < sh + n)) flags &= ~(1u << i);
-                                }
-                            }
+                            uint32_t flags = (cx & 1u) | ((cx >> 15) & 2u) | ((cy & 1u) << 2) | ((cy >> 13) & 8u) | ((cz & 1u) << 4) | ((cz >> 11) & 32u) |
+                                             ((cw & 1u) << 6) | ((cw >> 9) & 128u);
+                            flags = gi < ghot ? (flags & group_mask(min(p0, sh + n - 1u))) : 0u;
+                            GeneT g[8];
                             if constexpr (sizeof(GeneT) == 2) {
-                                const uint4 gq = reinterpret_cast<const uint4 *>(sg)[gi];
-                                const uint32_t g4[4] = {gq.x, gq.y, gq.z, gq.w};
+                                const uint32_t g4[4] = {gq.a.x, gq.a.y, gq.a.z, gq.a.w};
 #pragma unroll
                                 for (int i = 0; i < 8; i++) g[i] = (GeneT)((g4[i >> 1] >> ((i & 1) * 16)) & 0xffffu);
                             } else {
-                                const uint4 ga = reinterpret_cast<const uint4 *>(sg)[2u * gi], gb = reinterpret_cast<const uint4 *>(sg)[2u * gi + 1u];
-                                g[0] = (GeneT)ga.x; g[1] = (GeneT)ga.y; g[2] = (GeneT)ga.z; g[3] = (GeneT)ga.w;
-                                g[4] = (GeneT)gb.x; g[5] = (GeneT)gb.y; g[6] = (GeneT)gb.z; g[7] = (GeneT)gb.w;
+                                g[0] = (GeneT)gq.a.x; g[1] = (GeneT)gq.a.y; g[2] = (GeneT)gq.a.z; g[3] = (GeneT)gq.a.w;
+                                g[4] = (GeneT)gq.b.x; g[5] = (GeneT)gq.b.y; g[6] = (GeneT)gq.b.z; g[7] = (GeneT)gq.b.w;
                             }
-                        }
-                        const uint32_t pcf = __popc(flags), inc = warp_incl_scan(pcf);
-                        uint32_t off = base + inc - pcf;
-                        __syncwarp();                                         // every lane holds its genes in registers: the stage may be overwritten
+                            // every lane holds its genes in registers and the warp is converged: the stage may be overwritten below
+                            __syncwarp();
+                            // exclusive prefix of the lanes' counts (0..8) from four ballots: no dependent shuffle chain
+                            const uint32_t pcf = __popc(flags);
+                            const uint32_t b0 = __ballot_sync(0xffffffffu, pcf & 1u), b1 = __ballot_sync(0xffffffffu, pcf & 2u),
+                                           b2 = __ballot_sync(0xffffffffu, pcf & 4u), b3 = __ballot_sync(0xffffffffu, pcf & 8u);
+                            const uint32_t off = base + __popc(b0 & lt) + 2u * __popc(b1 & lt) + 4u * __popc(b2 & lt) + 8u * __popc(b3 & lt);
+                            base += __reduce_add_sync(0xffffffffu, pcf);
+                            SLAFB_CHECK(off + pcf > limit || sh + off + pcf <= fa.vcap, 231, sh + off);
+                            if (off + pcf <= limit) {                             // (all lanes but the one that crosses the emission limit)
+                                uint32_t ad = sg_addr + off * (uint32_t)sizeof(GeneT);
 #pragma unroll
-                        for (int i = 0; i < 8; i++) {
-                            if (flags & (1u << i)) {
-                                SLAFB_CHECK(off >= limit || sh + off < fa.vcap, 231, sh + off);
-                                if (off < limit) sg[sh + off] = g[i];
-                                off++;
+                                for (int i = 0; i < 8; i++) sts_if<GeneT>(ad, g[i], flags & (1u << i));
+                            } else {
+                                uint32_t o2 = off;
+#pragma unroll
+                                for (int i = 0; i < 8; i++) {
+                                    if (flags & (1u << i)) {
+                                        if (o2 < limit) sg[sh + o2] = g[i];
+                                        o2++;
+                                    }
+                                }
                             }
                         }
-                        base += __shfl_sync(0xffffffffu, inc, 31);
+                    }
+                    if (colend && base < limit) {
+                        // the rows of the column's last partial group, one by one (the last cell of a batch only)
+                        if (lane == 0) {
+                            for (uint32_t r = max(s, a0 + (ghot << 3)); r < e; r++) {
+                                if ((uint32_t)__ldg(value_g + r) >= (keep_all ? 0u : thr)) {
+                                    if (base < limit) sg[sh + base] = __ldg(gene_g + r);
+                                    base++;
+                                }
+                            }
+                        }
+                        base = __shfl_sync(0xffffffffu, base, 0);
                     }
                     n_keep = base;
                     __syncwarp();
                 }
             }
+        } else if (jn < NC) {
+            sn = __ldg(a.seg_start + cn); en = __ldg(a.seg_start + cn + 1); cidn = __ldg(a.seg_cell + cn);
         }
-        if (jn < NC) { sn = __ldg(a.seg_start + cn); en = __ldg(a.seg_start + cn + 1); }   // next cell's bounds (cn has arrived by now)
         if (defer) {
+            if (jn < NC) { sn = __ldg(a.seg_start + cn); en = __ldg(a.seg_start + cn + 1); cidn = __ldg(a.seg_cell + cn); }
             if (lane == 0) {
                 const uint32_t wi = atomicAdd(a.work_counters, 1u);
                 SLAFB_CHECK(wi < NC, 208, wi);
@@ -2115,10 +2233,7 @@ __global__ void __launch_bounds__(kPctWarps * 32) tokenize_pct_warp_kernel(const
                 }
             }
             fill_mask_by(a.mask, A, L, min(n_emit + 2u, L), lane, 32u);
-            if (lane == 0) {
-                const uint32_t cid = __ldg(a.seg_cell + c);
-                a.cell_ids[j] = a.cell_signed ? (long long)(int32_t)cid : (long long)cid;
-            }
+            if (lane == 0) a.cell_ids[j] = a.cell_signed ? (long long)(int32_t)cid : (long long)cid;
         }
         if (dirty) {
             for (uint32_t w = lane; w < (uint32_t)kPctWords; w += 32u) bitmap[w] = 0u;

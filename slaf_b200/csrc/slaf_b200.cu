@@ -354,21 +354,18 @@ int launch_rank(slafb_ctx *ctx, const RankArgs &ra, cudaStream_t st) {
     return SLAFB_OK;
 }
 
-// percentile mode on uint16 values: one warp per cell (kernels.cuh, K2w)
-template <typename GeneT>
-int launch_pct_warp(slafb_ctx *ctx, const TokArgs &a, cudaStream_t st, bool *launched) {
-    *launched = false;
+// percentile mode on uint16 values: one warp per cell (kernels.cuh, K2w).  SLAFB_PCT_VSTAGE=0|1 and SLAFB_PCT_VCAP=<rows> select
+// the variant and the stage size for A/B runs (defaults: the measured best).
+template <typename GeneT, bool VSTAGE>
+int launch_pct_warp_v(slafb_ctx *ctx, const TokArgs &a, cudaStream_t st, uint32_t vcap, bool *launched) {
     FastArgs fa;
     memset(&fa, 0, sizeof fa);
     fa.t = a;
-    const uint32_t limit = a.L - 1u;
-    uint32_t vcap = 4104u;
-    if (limit + 24u > vcap) vcap = (limit + 24u + 7u) & ~7u;
     fa.vcap = fa.gcap = vcap;
     fa.ticket = a.work_counters + 2;
-    const size_t smem = (size_t)kPctWarps * pct_warp_bytes<GeneT>(vcap);
+    const size_t smem = (size_t)kPctWarps * pct_warp_bytes<GeneT, VSTAGE>(vcap);
     if (smem > 200 * 1024) return SLAFB_OK;         // very wide rows: the CTA kernel / general kernel take them
-    auto kern = tokenize_pct_warp_kernel<GeneT>;
+    auto kern = tokenize_pct_warp_kernel<GeneT, VSTAGE>;
     static std::atomic<int> per_sm_cached[64];
     static std::atomic<size_t> smem_cached[64];
     int per_sm = per_sm_cached[ctx->device & 63].load(std::memory_order_acquire);
@@ -388,6 +385,18 @@ int launch_pct_warp(slafb_ctx *ctx, const TokArgs &a, cudaStream_t st, bool *lau
     ctx->acc.kernel_launches++;
     *launched = true;
     return SLAFB_OK;
+}
+
+template <typename GeneT>
+int launch_pct_warp(slafb_ctx *ctx, const TokArgs &a, cudaStream_t st, bool *launched) {
+    *launched = false;
+    static const bool vstage = [] { const char *e = getenv("SLAFB_PCT_VSTAGE"); return e ? atoi(e) != 0 : true; }();
+    static const uint32_t vcap_env = [] { const char *e = getenv("SLAFB_PCT_VCAP"); return e ? (uint32_t)atoi(e) : 0u; }();
+    const uint32_t limit = a.L - 1u;
+    uint32_t vcap = vcap_env ? vcap_env : 3072u;
+    if (limit + 24u > vcap) vcap = limit + 24u;     // the stage holds every gene that can be emitted ...
+    vcap = (vcap + 255u) & ~255u;                   // ... and a whole number of 256-row steps of the warp
+    return vstage ? launch_pct_warp_v<GeneT, true>(ctx, a, st, vcap, launched) : launch_pct_warp_v<GeneT, false>(ctx, a, st, vcap, launched);
 }
 
 template <typename GeneT, typename ValT>
