@@ -1899,7 +1899,7 @@ __device__ __forceinline__ void sts_if(uint32_t &addr, GeneT g, uint32_t bit) {
 template <typename GeneT, bool VSTAGE>
 __global__ void __launch_bounds__(kPctWarps * 32) tokenize_pct_warp_kernel(const FastArgs fa) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t s_bar[kPctWarps];
+    __shared__ __align__(8) uint64_t s_bar[kPctWarps][2];
     const TokArgs &a = fa.t;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t vbytes = VSTAGE ? ((fa.vcap * 2u + 127u) & ~127u) : 0u, gbytes = (fa.vcap * (uint32_t)sizeof(GeneT) + 127u) & ~127u;
@@ -1907,14 +1907,14 @@ __global__ void __launch_bounds__(kPctWarps * 32) tokenize_pct_warp_kernel(const
     uint16_t *sv = reinterpret_cast<uint16_t *>(mine);
     GeneT *sg = reinterpret_cast<GeneT *>(mine + vbytes);
     uint32_t *bitmap = reinterpret_cast<uint32_t *>(mine + vbytes + gbytes);
-    uint64_t *bar = &s_bar[warp];
+    uint64_t *bar = &s_bar[warp][0], *bar_v = &s_bar[warp][1];       // gene stage / value stage
     const GeneT *__restrict__ gene_g = static_cast<const GeneT *>(a.gene);
     const uint16_t *__restrict__ value_g = static_cast<const uint16_t *>(a.value);
     const uint32_t R = a.n_rows, k = a.max_items, L = a.L, limit = L - 1u;
     const uint32_t NC = a.n_cells;
     const uint32_t lt = (1u << lane) - 1u;
     const uint32_t gcap = (fa.vcap >> 3) & ~31u;                            // 8-row groups the stage holds (a multiple of the warp width)
-    if (lane == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+    if (lane == 0) { mbar_init(bar, 1); mbar_init(bar_v, 1); mbar_fence_init(); }
     for (uint32_t w = lane; w < (uint32_t)kPctWords; w += 32u) bitmap[w] = 0u;
     __syncwarp();
     const uint32_t G = gridDim.x * (uint32_t)kPctWarps;
@@ -1925,7 +1925,23 @@ __global__ void __launch_bounds__(kPctWarps * 32) tokenize_pct_warp_kernel(const
         cn = a.perm ? (uint32_t)__ldg(a.perm + jn) : jn;
         sn = __ldg(a.seg_start + cn); en = __ldg(a.seg_start + cn + 1); cidn = __ldg(a.seg_cell + cn);
     }
-    uint32_t phase = 0u;
+    // rows the bulk copies stage for the cell [s_, e_): its whole 8-row groups up to the capacity of the stage
+    auto n_staged = [&](uint32_t s_, uint32_t e_) -> uint32_t {
+        const uint32_t n_ = e_ - s_, a0_ = s_ & ~7u, ng_ = ((s_ - a0_) + n_ + 7u) >> 3;
+        const uint32_t ce_ = (n_ && a0_ + (ng_ << 3) > R) ? 1u : 0u;
+        return n_ ? (min(ng_ - ce_, gcap) << 3) : 0u;
+    };
+    // The value stage is refilled for the NEXT cell as soon as the compaction has read it for the last time, so that copy flies
+    // during the emission; the gene stage is refilled at the top of the iteration and its copy flies during pass 1.
+    auto stage_values = [&](uint32_t s_, uint32_t e_) {
+        const uint32_t b = n_staged(s_, e_);
+        if (b) {
+            mbar_arrive_expect_tx(bar_v, b * 2u);
+            bulk_g2s(sv, value_g + (s_ & ~7u), b * 2u, bar_v);
+        }
+    };
+    if constexpr (VSTAGE) { if (jn < NC && lane == 0) stage_values(sn, en); }
+    uint32_t phase = 0u, phase_v = 0u;
     while (jn < NC) {
         const uint32_t j = jn, s = sn, e = en, cid = cidn, n = e - s, a0 = s & ~7u, sh = s - a0;
         // The cell's rows lie in `ngroups` aligned 8-row groups of the columns.  The hot loops below only ever touch groups that
@@ -1939,8 +1955,7 @@ __global__ void __launch_bounds__(kPctWarps * 32) tokenize_pct_warp_kernel(const
         if (lane == 0) {
             if (bulk) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the stage was written through the generic proxy (in-place compaction)
-                mbar_arrive_expect_tx(bar, bulk * ((VSTAGE ? 2u : 0u) + (uint32_t)sizeof(GeneT)));
-                if constexpr (VSTAGE) bulk_g2s(sv, value_g + a0, bulk * 2u, bar);
+                mbar_arrive_expect_tx(bar, bulk * (uint32_t)sizeof(GeneT));
                 bulk_g2s(sg, gene_g + a0, bulk * (uint32_t)sizeof(GeneT), bar);
             }
             jn = G + atomicAdd(fa.ticket, 1u);
@@ -2031,9 +2046,9 @@ __global__ void __launch_bounds__(kPctWarps * 32) tokenize_pct_warp_kernel(const
         }
         jn = __shfl_sync(0xffffffffu, jn, 0);
         if (jn < NC) cn = a.perm ? (uint32_t)__ldg(a.perm + jn) : jn;        // (its latency hides under this cell's work)
-        if (bulk) {
-            mbar_wait(bar, phase);
-            phase ^= 1u;
+        if (VSTAGE && bulk) {
+            mbar_wait(bar_v, phase_v);
+            phase_v ^= 1u;
         }
         if (n) {
             if constexpr (VSTAGE) {
@@ -2102,7 +2117,15 @@ __global__ void __launch_bounds__(kPctWarps * 32) tokenize_pct_warp_kernel(const
                     thr = __reduce_max_sync(0xffffffffu, found);
                 }
                 keep_all = (astar == 1u);
-                if (jn < NC) { sn = __ldg(a.seg_start + cn); en = __ldg(a.seg_start + cn + 1); cidn = __ldg(a.seg_cell + cn); }   // (cn has arrived by now)
+            }
+        }
+        if (jn < NC) { sn = __ldg(a.seg_start + cn); en = __ldg(a.seg_start + cn + 1); cidn = __ldg(a.seg_cell + cn); }   // (cn has arrived by now)
+        if (bulk) {
+            mbar_wait(bar, phase);                                          // the genes (their copy flew during pass 1)
+            phase ^= 1u;
+        }
+        if (n && !defer) {
+            {
                 if (!keep_all || ngs < ngroups) {
                     // ---- row-order compaction: 256 rows per step (8 per lane), offsets from a warp prefix over the lanes' counts,
                     // IN PLACE in the gene stage (a kept gene never moves to a higher index; the genes of the rows beyond the stage
@@ -2172,14 +2195,12 @@ __global__ void __launch_bounds__(kPctWarps * 32) tokenize_pct_warp_kernel(const
                         base = __shfl_sync(0xffffffffu, base, 0);
                     }
                     n_keep = base;
-                    __syncwarp();
                 }
             }
-        } else if (jn < NC) {
-            sn = __ldg(a.seg_start + cn); en = __ldg(a.seg_start + cn + 1); cidn = __ldg(a.seg_cell + cn);
         }
+        __syncwarp();                                                       // the value stage has been read for the last time
+        if constexpr (VSTAGE) { if (jn < NC && lane == 0) stage_values(sn, en); }
         if (defer) {
-            if (jn < NC) { sn = __ldg(a.seg_start + cn); en = __ldg(a.seg_start + cn + 1); cidn = __ldg(a.seg_cell + cn); }
             if (lane == 0) {
                 const uint32_t wi = atomicAdd(a.work_counters, 1u);
                 SLAFB_CHECK(wi < NC, 208, wi);
