@@ -35,7 +35,14 @@ for ln in dis:
     if re.match(r"\s+/\*[0-9a-f]{4,}\*/", ln):
         lines.append(cur)
 rows = list(csv.reader(open(src_csv)))
-hdr, data = rows[1], rows[2:]
+# an export can hold several kernels ("Kernel Name" row, header row, one row per instruction): take the LAST section whose
+# (demangled) kernel name contains $KSEL, or simply the last section
+heads = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+ksel = os.environ.get("KSEL", "")
+pick = [i for i in heads if ksel in rows[i][1]] or heads
+h0 = pick[-1]
+h1 = min([i for i in heads if i > h0] + [len(rows)])
+hdr, data = rows[h0 + 1], rows[h0 + 2:h1]
 ii, isamp, ib = hdr.index("Instructions Executed"), hdr.index("# Samples"), hdr.index("stall_barrier")
 names = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
 if len(lines) != len(data):

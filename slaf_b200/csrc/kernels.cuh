@@ -2263,6 +2263,317 @@ __global__ void __launch_bounds__(kPctWarps * 32) tokenize_pct_warp_kernel(const
     }
 }
 
+// ---- K2f: float32 values, ONE WARP PER CELL (plain Geneformer and both scGPT modes) ---------------------------------------
+// The CTA-per-cell kernel is issue-bound on float32 storage for the same reason as in percentile mode (~6,100 warp instructions per
+// cell: eight warps pay the per-cell reductions, barriers and ragged-chunk handling for eight rows per thread).  Here a warp owns a
+// cell.  Normalised expression values have no integer range to test, so a cell with more rows than max_items proves "at most
+// max_items distinct values" (then the dense-rank filter keeps every row) with an open-addressing set of the value bits in the
+// warp's shared memory: the sweep looks every value up with plain reads (eight independent loads per lane and step) and only the
+// steps in which some lane met a value that is not in the set yet -- a few per cell -- take the inserting path.  A cell with more
+// than kF32HashCap distinct values goes to the work list (general kernel); the library falls back to the CTA kernel for data where
+// that happens often (slaf_b200.cu).  The cell maximum comes from the same sweep; the binned window + tokenizer collapse to one
+// threshold per cell (see the CTA kernel), found by the warp with the same candidate round / 32-ary search.
+//   Staging: the genes of the rows that can be emitted, the values of the first `vcap` rows (the emitted rows are among them); the
+// values of longer cells' tails come from global memory with two loads per lane in flight.
+constexpr int kF32HashBits = 9;
+constexpr int kF32HashSlots = 1 << kF32HashBits;    // per warp (2 KiB)
+constexpr int kF32HashCap = 255;                    // trusted entries: one inserting step adds at most 256 more, so a free slot always exists
+static_assert(kF32HashCap + 256 < kF32HashSlots, "the distinct-value set must never fill up");
+template <typename GeneT>
+__host__ __device__ constexpr uint32_t f32_warp_bytes(uint32_t vcap, uint32_t gcap) {
+    return ((vcap * 4u + 127u) & ~127u) + ((gcap * (uint32_t)sizeof(GeneT) + 127u) & ~127u) + (uint32_t)kF32HashSlots * 4u;
+}
+
+template <typename GeneT, int MODE>
+__global__ void __launch_bounds__(kPctWarps * 32) tokenize_f32_warp_kernel(const FastArgs fa) {
+    constexpr bool SCGPT = (MODE == MODE_SCGPT_RAW || MODE == MODE_SCGPT_BINNED);
+    constexpr bool BINNED = (MODE == MODE_SCGPT_BINNED);
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t s_bar[kPctWarps][2];
+    const TokArgs &a = fa.t;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t vbytes = (fa.vcap * 4u + 127u) & ~127u, gbytes = (fa.gcap * (uint32_t)sizeof(GeneT) + 127u) & ~127u;
+    uint8_t *mine = smem_raw + warp * f32_warp_bytes<GeneT>(fa.vcap, fa.gcap);
+    float *sv = reinterpret_cast<float *>(mine);
+    GeneT *sg = reinterpret_cast<GeneT *>(mine + vbytes);
+    uint32_t *tab = reinterpret_cast<uint32_t *>(mine + vbytes + gbytes);
+    uint64_t *bar = &s_bar[warp][0], *bar_g = &s_bar[warp][1];       // value stage / gene stage
+    const GeneT *__restrict__ gene_g = static_cast<const GeneT *>(a.gene);
+    const float *__restrict__ value_g = static_cast<const float *>(a.value);
+    const uint32_t R = a.n_rows, k = a.max_items, L = a.L;
+    const uint32_t limit = SCGPT ? a.max_genes : (L - 1u);
+    const uint32_t NC = a.n_cells;
+    const uint32_t gcv = (fa.vcap >> 3) & ~31u;                             // 8-row groups the value stage holds (a multiple of the warp width)
+    if (lane == 0) { mbar_init(bar, 1); mbar_init(bar_g, 1); mbar_fence_init(); }
+    __syncwarp();
+    const uint32_t G = gridDim.x * (uint32_t)kPctWarps;
+    uint32_t jn = blockIdx.x * (uint32_t)kPctWarps + warp, cn = 0, sn = 0, en = 0, cidn = 0;
+    if (jn < NC) {
+        cn = a.perm ? (uint32_t)__ldg(a.perm + jn) : jn;
+        sn = __ldg(a.seg_start + cn); en = __ldg(a.seg_start + cn + 1); cidn = __ldg(a.seg_cell + cn);
+    }
+    uint32_t phase = 0u, phase_g = 0u;
+    while (jn < NC) {
+        const uint32_t j = jn, s = sn, e = en, cid = cidn, n = e - s, a0 = s & ~7u, sh = s - a0;
+        // (group geometry as in the percentile kernel: `colend` = the column's last partial 8-row group, visited row by row)
+        const uint32_t ngroups = (sh + n + 7u) >> 3;
+        const uint32_t colend = (n && a0 + (ngroups << 3) > R) ? 1u : 0u;
+        const uint32_t ghot = ngroups - colend;
+        const uint32_t n_emit = min(n, limit);                              // this kernel only emits cells whose every row is kept
+        const uint32_t nge = (sh + n_emit + 7u) >> 3;                       // groups that hold the rows to emit
+        bool keep_all = n <= k;
+        const bool pass1 = n && (BINNED || !keep_all);                      // the values are swept (maximum, distinct count)
+        const bool hashing = n && !keep_all;
+        const uint32_t ngg = min(ghot, nge);                                // gene groups staged
+        const uint32_t ngv = pass1 ? min(ghot, gcv) : (SCGPT ? ngg : 0u);   // value groups staged
+        if (lane == 0) {
+            if (ngv | ngg) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // (the stages' colend rows are written through the generic proxy)
+            if (ngv) { mbar_arrive_expect_tx(bar, ngv * 32u); bulk_g2s(sv, value_g + a0, ngv * 32u, bar); }
+            if (ngg) { mbar_arrive_expect_tx(bar_g, ngg * 8u * (uint32_t)sizeof(GeneT)); bulk_g2s(sg, gene_g + a0, ngg * 8u * (uint32_t)sizeof(GeneT), bar_g); }
+            jn = G + atomicAdd(fa.ticket, 1u);
+        }
+        if (hashing) {
+#pragma unroll
+            for (int i = 0; i < kF32HashSlots / 32; i++) tab[lane + 32 * i] = 0xffffffffu;
+        }
+        // rows of the column's last partial group that are emitted: into the stages one by one (the last cell of a batch only)
+        if (colend && ngroups - 1u < nge && lane < 8u) {
+            const uint32_t r = a0 + ((ngroups - 1u) << 3) + lane;
+            if (r >= s && r < s + n_emit) { sg[r - a0] = __ldg(gene_g + r); if constexpr (SCGPT) sv[r - a0] = __ldg(value_g + r); }
+        }
+        __syncwarp();
+        const float4 *sv4 = reinterpret_cast<const float4 *>(sv);
+        volatile uint32_t *vt = tab;
+        float xmax = -INFINITY;
+        uint32_t ins = 0u;                                                  // keys this lane added to the set
+        bool defer = false, live = hashing;                                 // live: the set still decides (uniform)
+        auto group_mask = [&](uint32_t p0) -> uint32_t {
+            const int lo_i = max((int)sh - (int)p0, 0);
+            const int hi_i = min((int)(sh + n) - (int)p0, 8);
+            return (0xffu >> (8 - hi_i)) & (0xffu << lo_i) & 0xffu;
+        };
+        // the inserting probe (slow paths only); set membership is about equality, so the raw bits of x + 0.0f (which folds -0.0
+        // into +0.0) are the key
+        auto insert = [&](float x) {
+            const uint32_t key = __float_as_uint(x + 0.0f);
+            uint32_t h = (key * 2654435761u) >> (32 - kF32HashBits);
+            for (;;) {
+                SLAFB_CHECK(h < (uint32_t)kF32HashSlots, 240, h);
+                uint32_t cur = vt[h];
+                if (cur == 0xffffffffu) {
+                    cur = atomicCAS(tab + h, 0xffffffffu, key);
+                    if (cur == 0xffffffffu) { ins++; break; }
+                }
+                if (cur == key) break;
+                h = (h + 1u) & (uint32_t)(kF32HashSlots - 1);
+            }
+        };
+        auto eight = [&](const float4 qa, const float4 qb, uint32_t valid, bool ins_too) {
+            const float x8[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                if ((valid >> i) & 1u) {
+                    xmax = fmaxf(xmax, x8[i]);
+                    if (ins_too) insert(x8[i]);
+                }
+            }
+        };
+        // one step of the sweep: 8 values per lane; branch-free look-ups, then -- only if some lane missed -- the inserting path
+        const uint32_t gw0 = sh ? 1u : 0u, gw1 = min(ghot, (sh + n) >> 3);  // the groups that lie wholly inside the cell
+        auto sweep = [&](const float4 qa, const float4 qb, uint32_t gi) {
+            const bool in = gi >= gw0 && gi < gw1;
+            const float mx = fmaxf(fmaxf(fmaxf(qa.x, qa.y), fmaxf(qa.z, qa.w)), fmaxf(fmaxf(qb.x, qb.y), fmaxf(qb.z, qb.w)));
+            xmax = in ? fmaxf(xmax, mx) : xmax;
+            if (live) {
+                // a value counts as seen when it sits in its HOME slot of the set.  Keys that linear probing displaced miss every time,
+                // but the frequent values of a cell arrive first, when the set is all but empty, and are hardly ever displaced.
+                const float x8[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+                uint32_t miss = 0u;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const uint32_t key = __float_as_uint(x8[i] + 0.0f);
+                    miss |= (vt[(key * 2654435761u) >> (32 - kF32HashBits)] != key) ? (1u << i) : 0u;
+                }
+                miss = in ? miss : 0u;
+                if (__any_sync(0xffffffffu, miss != 0u)) {
+#pragma unroll 1
+                    while (miss) {                                          // (one or two values in a few lanes, typically)
+                        const uint32_t i = (uint32_t)__ffs(miss) - 1u;
+                        miss &= miss - 1u;
+                        insert(i < 4u ? (i < 2u ? (i ? qa.y : qa.x) : (i == 2u ? qa.z : qa.w)) : (i < 6u ? (i == 4u ? qb.x : qb.y) : (i == 6u ? qb.z : qb.w)));
+                    }
+                    if (__reduce_add_sync(0xffffffffu, ins) > (uint32_t)kF32HashCap) live = false;   // too many distinct values for this set: deferred
+                }
+            }
+        };
+        const uint32_t rgi = lane ? ngroups - 1u : 0u;
+        const bool rneed = pass1 && lane < 2u && (lane ? (rgi >= gw1 && rgi >= gw0) : (sh != 0u));
+        if (pass1 && ngv < ghot) {
+            // values beyond the stage, from global memory while the bulk copy is in flight (clamped indices, uniform trip count)
+            const uint32_t glast = ghot - 1u;
+            auto ldv = [&](uint32_t gi, float4 &qa, float4 &qb) {
+                const float4 *pp = reinterpret_cast<const float4 *>(value_g + a0 + (min(gi, glast) << 3));
+                qa = __ldg(pp); qb = __ldg(pp + 1);
+            };
+            float4 na, nb, ma, mb;
+            ldv(ngv + lane, na, nb);
+            ldv(ngv + lane + 32u, ma, mb);
+            for (uint32_t g0 = ngv; g0 < ghot; g0 += 32u) {
+                const float4 qa = na, qb = nb;
+                na = ma; nb = mb;
+                ldv(g0 + lane + 64u, ma, mb);
+                sweep(qa, qb, g0 + lane);
+            }
+        }
+        jn = __shfl_sync(0xffffffffu, jn, 0);
+        if (jn < NC) cn = a.perm ? (uint32_t)__ldg(a.perm + jn) : jn;        // (its latency hides under this cell's work)
+        if (ngv) {
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+        }
+        uint32_t kmax = 0u;
+        if (pass1) {
+            for (uint32_t g0 = 0u; g0 < ngv; g0 += 32u) {
+                const uint32_t gi = min(g0 + lane, ngv - 1u);
+                sweep(sv4[2u * gi], sv4[2u * gi + 1u], g0 + lane);
+            }
+            // the ragged first / last group (lanes 0 / 1) and the column's last partial group, row by row
+            if (rneed) {
+                const uint32_t r0 = a0 + (rgi << 3), valid = group_mask(rgi << 3);
+                if (rgi < ngv) {
+                    eight(sv4[2u * rgi], sv4[2u * rgi + 1u], valid, live);
+                } else if (rgi < ghot) {
+                    const float4 *pp = reinterpret_cast<const float4 *>(value_g + r0);
+                    eight(__ldg(pp), __ldg(pp + 1), valid, live);
+                } else {
+                    for (uint32_t i = 0; i < 8u; i++) {
+                        if ((valid >> i) & 1u) { const float x = __ldg(value_g + r0 + i); xmax = fmaxf(xmax, x); if (live) insert(x); }
+                    }
+                }
+            }
+            __syncwarp();
+            kmax = __reduce_max_sync(0xffffffffu, key_of(xmax));
+            if (hashing) {
+                const uint32_t D = __reduce_add_sync(0xffffffffu, ins);
+                if (live && D <= min(k, (uint32_t)kF32HashCap)) keep_all = true; else defer = true;   // D <= k distinct values: every row has rank <= k
+            }
+        }
+        if (jn < NC) { sn = __ldg(a.seg_start + cn); en = __ldg(a.seg_start + cn + 1); cidn = __ldg(a.seg_cell + cn); }
+        if (ngg) {
+            mbar_wait(bar_g, phase_g);                                      // the genes (their copy flew during the sweep)
+            phase_g ^= 1u;
+        }
+        if (defer) {
+            if (lane == 0) {
+                const uint32_t wi = atomicAdd(a.work_counters, 1u);
+                SLAFB_CHECK(wi < NC, 208, wi);
+                a.work_list[wi] = j;
+            }
+        } else {
+            // ---- emission: token pairs (128-bit stores), value stream, PAD fill, mask, cell id
+            const size_t A = (size_t)j * L;
+            const long long top = a.vocab + (long long)(a.n_bins - 1);
+            float xstar_f = 0.0f;
+            (void)top; (void)xstar_f; (void)kmax;
+            if constexpr (BINNED) {
+                // token = (bin >= 1) ? top : PAD with bin(x) = floor(log1pf(x) * n / m) monotone in x: the warp finds the smallest float
+                // whose bin is >= 1 (one round of 32 candidates around a closed-form guess, a 32-ary search only if that misses)
+                const float m_f32 = log1pf_window(float_of_key(kmax));
+                const float wb = (float)a.w_bins;
+                auto pred = [&](uint32_t c) -> bool {
+                    const float lv = log1pf_window(float_of_key(c));
+                    return lv > 0.0f && __fdiv_rn(__fmul_rn(lv, wb), m_f32) >= 1.0f;
+                };
+                const uint32_t kzero = key_of(0.0f);
+                uint32_t xs = 0xffffffffu;                                  // no value reaches bin 1
+                if (a.w_bins >= 2 && kmax > kzero && pred(kmax)) {
+                    const float x0 = (float)expm1((double)m_f32 / (double)wb);
+                    uint32_t k0 = key_of(x0);
+                    k0 = min(max(k0, kzero + 1u), kmax);
+                    const uint32_t wlo = (k0 - kzero > 16u) ? k0 - 16u : kzero + 1u;
+                    const uint32_t c = min(wlo + lane, kmax);
+                    const uint32_t hit = __ballot_sync(0xffffffffu, pred(c));
+                    if (hit == 0u) xs = warp_lower_bound(wlo + 32u, kmax, pred);
+                    else if ((hit & 1u) && wlo > kzero + 1u) xs = warp_lower_bound(kzero + 1u, wlo, pred);
+                    else xs = min(wlo + (uint32_t)(__ffs(hit) - 1), kmax);
+                }
+                xstar_f = float_of_key(xs);                                 // ("no value": a NaN, which compares false as it must)
+            }
+            auto id_tok = [&](long long t) -> long long {
+                if (t == 0) return 1ll;
+                if (t <= (long long)n_emit) {
+                    if constexpr (sizeof(GeneT) == 2) return (long long)sg[sh + (uint32_t)t - 1u] + 4ll;
+                    else return (long long)(int32_t)sg[sh + (uint32_t)t - 1u] + 4ll;
+                }
+                return (t == (long long)n_emit + 1) ? 2ll : 0ll;
+            };
+            auto val_of = [&](float x) -> long long {
+                if constexpr (BINNED) return (x >= xstar_f) ? top : 0ll;
+                else return expr_bin_token(x, a.bin_size, a.n_bins, a.vocab);
+            };
+            auto val_tok = [&](long long t) -> long long {
+                if (t < 1 || t > (long long)n_emit) return 0ll;
+                return val_of(sv[sh + (uint32_t)t - 1u]);
+            };
+            const uint32_t off = (uint32_t)(A & 1);
+            long long *ids_al = a.ids + (A - off);
+            long long *vals_al = SCGPT ? a.vals + (A - off) : nullptr;
+            const uint32_t n_pairs = (L + off + 1u) >> 1;
+            const uint32_t p_lo = (off + 2u) >> 1;
+            const uint32_t p_hi = n_emit >= 1u ? (n_emit - 1u + off) / 2u + 1u : 0u;
+            SLAFB_CHECK(j < NC && sh + n_emit <= fa.gcap && (!SCGPT || sh + n_emit <= fa.vcap), 241, sh + n_emit);
+#pragma unroll 2
+            for (uint32_t p = p_lo + lane; p < p_hi; p += 32u) {
+                const uint32_t gi = sh + 2u * p - off - 1u;
+                long long x0, x1;
+                if constexpr (sizeof(GeneT) == 2) { x0 = (long long)sg[gi] + 4ll; x1 = (long long)sg[gi + 1] + 4ll; }
+                else { x0 = (long long)(int32_t)sg[gi] + 4ll; x1 = (long long)(int32_t)sg[gi + 1] + 4ll; }
+                store_pair(ids_al + 2u * p, x0, x1);
+            }
+            if constexpr (SCGPT) {
+#pragma unroll 2
+                for (uint32_t p = p_lo + lane; p < p_hi; p += 32u) {
+                    const uint32_t gi = sh + 2u * p - off - 1u;
+                    store_pair(vals_al + 2u * p, val_of(sv[gi]), val_of(sv[gi + 1]));
+                }
+            }
+            const uint32_t p_pad = (n_emit + 2u + off + 1u) >> 1;
+            const uint32_t p_full_end = (L + off) >> 1;
+            for (uint32_t p = p_pad + lane; p < p_full_end; p += 32u) {
+                store_pair(ids_al + 2u * p, 0ll, 0ll);
+                if constexpr (SCGPT) store_pair(vals_al + 2u * p, 0ll, 0ll);
+            }
+            {
+                const uint32_t nb_head = min(p_lo, n_pairs);
+                const uint32_t mid_lo = max(p_hi, p_lo), mid_hi = min(max(p_pad, mid_lo), n_pairs);
+                const uint32_t tail_lo = max(p_full_end, mid_hi);
+                const uint32_t n_b = nb_head + (mid_hi - mid_lo) + (n_pairs - tail_lo);
+                for (uint32_t i = lane; i < n_b; i += 32u) {
+                    uint32_t p;
+                    if (i < nb_head) p = i;
+                    else if (i < nb_head + (mid_hi - mid_lo)) p = mid_lo + (i - nb_head);
+                    else p = tail_lo + (i - nb_head - (mid_hi - mid_lo));
+                    const long long t0 = (long long)(2u * p) - (long long)off, t1 = t0 + 1;
+                    const bool v0 = t0 >= 0, v1 = t1 < (long long)L;
+                    const long long x0 = v0 ? id_tok(t0) : 0ll, x1 = v1 ? id_tok(t1) : 0ll;
+                    if (v0 && v1) *reinterpret_cast<longlong2 *>(ids_al + 2u * p) = make_longlong2(x0, x1);
+                    else if (v0) ids_al[2u * p] = x0;
+                    else if (v1) ids_al[2u * p + 1] = x1;
+                    if constexpr (SCGPT) {
+                        const long long y0 = v0 ? val_tok(t0) : 0ll, y1 = v1 ? val_tok(t1) : 0ll;
+                        if (v0 && v1) *reinterpret_cast<longlong2 *>(vals_al + 2u * p) = make_longlong2(y0, y1);
+                        else if (v0) vals_al[2u * p] = y0;
+                        else if (v1) vals_al[2u * p + 1] = y1;
+                    }
+                }
+            }
+            fill_mask_by(a.mask, A, L, min(n_emit + 2u, L), lane, 32u);
+            if (lane == 0) a.cell_ids[j] = a.cell_signed ? (long long)(int32_t)cid : (long long)cid;
+        }
+        __syncwarp();          // the stages and the set are free for the next cell
+    }
+}
+
 // table for the binned window on uint16 storage: for a cell whose maximum value is vmax, the
 // smallest value v with  floor(log1p(v) * n_bins / log1p(vmax)) >= 1  (f64, evaluation order of
 // aggregators.py:100-105).  Every such row gets the token vocab + n_bins - 1, every other row PAD

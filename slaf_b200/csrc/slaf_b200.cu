@@ -85,6 +85,8 @@ struct Slot {
     bool timed_front = false, timed_back = false, timed_h2d = false;
     bool sample = true;               // this batch carries the per-kernel timing events
     bool ran_back = false;
+    bool used_f32_warp = false;        // the float32 warp-per-cell kernel ran this batch (its deferral rate steers the choice of kernel)
+    int64_t back_cells = 0;
 };
 
 }  // namespace
@@ -131,6 +133,9 @@ struct slafb_ctx {
     cudaEvent_t ev_k1 = nullptr;       // end of the latest CSR build: K1 launches share the context's span ticket / tile states, so a K1
     cudaStream_t k1_stream = nullptr;  // on another stream than the previous one (SLAFB_OPT_FRONT_ON_CALLER) waits for it first
     bool k1_any = false;
+    bool f32_warp_off = false;        // float32 values: the warp-per-cell kernel deferred too many cells of a batch (more distinct values per cell
+                                      // than its set holds): this context stays with the CTA-per-cell kernel
+    bool last_fast_f32_warp = false;
     int64_t recent_slow = 1 << 20;    // decayed maximum of the cells recently deferred to the general kernel (starts pessimistic)
 };
 
@@ -226,8 +231,9 @@ void harvest(slafb_ctx *ctx, Slot &s) {
         ctx->acc.slow_cells += slow;
         // how much work the general kernel found lately (it is launched after every fast kernel, usually for nothing)
         ctx->recent_slow = slow > ctx->recent_slow ? slow : (ctx->recent_slow * 7) / 8;
+        if (s.used_f32_warp && s.back_cells >= 64 && slow * 8 > s.back_cells) ctx->f32_warp_off = true;
     }
-    s.timed_front = s.timed_back = s.timed_h2d = s.ran_back = false;
+    s.timed_front = s.timed_back = s.timed_h2d = s.ran_back = s.used_f32_warp = false;
 }
 
 int ensure_staging(slafb_ctx *ctx, Slot &s) {
@@ -399,8 +405,60 @@ int launch_pct_warp(slafb_ctx *ctx, const TokArgs &a, cudaStream_t st, bool *lau
     return vstage ? launch_pct_warp_v<GeneT, true>(ctx, a, st, vcap, launched) : launch_pct_warp_v<GeneT, false>(ctx, a, st, vcap, launched);
 }
 
+// float32 values, plain Geneformer and both scGPT modes: one warp per cell (kernels.cuh, K2f).  SLAFB_F32_CTA=1 keeps the
+// CTA-per-cell kernel (A/B runs); SLAFB_F32_VCAP=<rows> sets the value stage.
+template <typename GeneT, int MODE>
+int launch_f32_warp(slafb_ctx *ctx, const TokArgs &a, cudaStream_t st, bool *launched) {
+    *launched = false;
+    static const bool use_cta = [] { const char *e = getenv("SLAFB_F32_CTA"); return e && atoi(e) != 0; }();
+    static const uint32_t vcap_env = [] { const char *e = getenv("SLAFB_F32_VCAP"); return e ? (uint32_t)atoi(e) : 0u; }();
+    if (use_cta || ctx->f32_warp_off) return SLAFB_OK;
+    constexpr bool SCGPT = (MODE == MODE_SCGPT_RAW || MODE == MODE_SCGPT_BINNED);
+    const uint32_t limit = SCGPT ? a.max_genes : (a.L - 1u);
+    FastArgs fa;
+    memset(&fa, 0, sizeof fa);
+    fa.t = a;
+    fa.gcap = (limit + 15u + 7u) & ~7u;             // the genes of every row that can be emitted
+    uint32_t vcap = vcap_env ? vcap_env : 2304u;
+    if (fa.gcap > vcap) vcap = fa.gcap;             // the emitted rows' values are staged as well ...
+    fa.vcap = (vcap + 255u) & ~255u;                // ... in a whole number of 256-row steps of the warp
+    fa.ticket = a.work_counters + 2;
+    const size_t smem = (size_t)kPctWarps * f32_warp_bytes<GeneT>(fa.vcap, fa.gcap);
+    if (smem > 200 * 1024) return SLAFB_OK;         // very wide rows: the CTA kernel / general kernel take them
+    auto kern = tokenize_f32_warp_kernel<GeneT, MODE>;
+    static std::atomic<int> per_sm_cached[64];
+    static std::atomic<size_t> smem_cached[64];
+    int per_sm = per_sm_cached[ctx->device & 63].load(std::memory_order_acquire);
+    if (per_sm == 0 || smem_cached[ctx->device & 63].load() != smem) {
+        CU(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPctWarps * 32, smem));
+        if (per_sm < 1) per_sm = 1;
+        smem_cached[ctx->device & 63].store(smem);
+        per_sm_cached[ctx->device & 63].store(per_sm, std::memory_order_release);
+    }
+    uint32_t grid = (uint32_t)(ctx->n_sm * per_sm);
+    const uint32_t need = (a.n_cells + kPctWarps - 1) / kPctWarps;
+    if (need < grid) grid = need;
+    if (grid == 0) grid = 1;
+    kern<<<grid, kPctWarps * 32, smem, st>>>(fa);
+    CU(ctx, cudaGetLastError());
+    ctx->acc.kernel_launches++;
+    ctx->last_fast_f32_warp = true;
+    *launched = true;
+    return SLAFB_OK;
+}
+
 template <typename GeneT, typename ValT>
 int dispatch_fast(slafb_ctx *ctx, int mode, const TokArgs &a, cudaStream_t st, bool *launched) {
+    ctx->last_fast_f32_warp = false;
+    if constexpr (sizeof(ValT) == 4) {
+        int rc = SLAFB_OK;
+        *launched = false;
+        if (mode == MODE_GF) rc = launch_f32_warp<GeneT, MODE_GF>(ctx, a, st, launched);
+        else if (mode == MODE_SCGPT_RAW) rc = launch_f32_warp<GeneT, MODE_SCGPT_RAW>(ctx, a, st, launched);
+        else if (mode == MODE_SCGPT_BINNED) rc = launch_f32_warp<GeneT, MODE_SCGPT_BINNED>(ctx, a, st, launched);
+        if (rc || *launched) return rc;
+    }
     switch (mode) {
     case MODE_GF: return launch_fast<GeneT, ValT, MODE_GF>(ctx, a, st, launched);
     case MODE_SCGPT_RAW: return launch_fast<GeneT, ValT, MODE_SCGPT_RAW>(ctx, a, st, launched);
@@ -880,6 +938,8 @@ int back(slafb_ctx *ctx, Slot &s, const slafb_params *p, const slafb_out *out, i
     } else {
         DISPATCH_TYPES(s.gene_dtype, s.value_dtype, rc = (dispatch_fast<GeneT, ValT>(ctx, p->mode, a, st, &fast_launched)));
         if (rc) return rc;
+        s.used_f32_warp = ctx->last_fast_f32_warp;
+        s.back_cells = C;
     }
     if (!fast_launched) a.all_cells = 1;
     if (s.sample) CU(ctx, cudaEventRecord(s.t_k2b, st));
