@@ -953,6 +953,19 @@ def main():
            "launches": int(tiso["timed_batches"]),
            "tokenize_cells_kernel": {"avg_launch_ms": tiso["tokenize_ms"] / nti, "achieved": iso_k2, "frac": iso_k2 / peak, "frac_of_nominal_8tbs": iso_k2 / NOMINAL},
            "csr_build_kernel": {"avg_launch_ms": tiso["csr_ms"] / nti, "achieved": iso_k1, "frac": iso_k1 / peak, "frac_of_nominal_8tbs": iso_k1 / NOMINAL}}
+    # which kernel tokenizes this workload (slaf_b200.cu: dispatch_fast): one warp per cell for the percentile mode on uint16 values
+    # and for float32 values, one CTA per cell otherwise
+    if w.get("rank_norm"):
+        k2_name = "tokenize_rank_kernel (per-cell sort)"
+    elif slow_all:
+        k2_name = "tokenize_general_kernel (exact k-th distinct value for every cell)"
+    elif w.get("min_percentile") is not None and not os.environ.get("SLAFB_PCT_CTA"):
+        k2_name = "tokenize_pct_warp_kernel"
+    elif args.value_dtype == "float32" and not os.environ.get("SLAFB_F32_CTA"):
+        k2_name = "tokenize_f32_warp_kernel"
+    else:
+        k2_name = "tokenize_cells_kernel"
+    iso["kernel"] = k2_name + " (reported under the key tokenize_cells_kernel)"
     traffic = None
     try:   # dram__bytes_read.sum + dram__bytes_write.sum of K2 from the committed ncu --set full capture, per cell
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{args.workload}:{args.value_dtype}")
@@ -968,8 +981,7 @@ def main():
         "metric": "tokenized cells/sec", "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "ms_per_step_per_rank": [r[0] for r in per_rank], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
         "config": cfg,
-        "roofline": {"bound": "hbm", "kernel": ("tokenize_rank_kernel (per-cell sort)" if w.get("rank_norm") else
-                                             "tokenize_general_kernel (exact k-th distinct value for every cell)" if slow_all else "tokenize_cells_kernel"), "achieved": k2_gbs, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": k2_name, "achieved": k2_gbs, "peak": peak, "unit": "GB/s",
                      "frac": (k2_gbs / peak) if k2_gbs else None, "frac_isolated": iso["tokenize_cells_kernel"]["frac"],
                      "frac_of_nominal_8tbs": (k2_gbs / NOMINAL) if k2_gbs else None, "traffic": traffic,
                      "traffic_source": "static: profiles/traffic.json (dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture, per cell x cells per launch), not measured in this run",

@@ -34,7 +34,7 @@ if [ -z "$SKIP_NCU" ]; then
       python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-loader > $O/ncu_list_$TAG.log 2>&1; echo "list rc=$?"
   for spec in "cfg2:uint16" "cfg3p:uint16" "cfg2:float32"; do
     W=${spec%%:*}; DT=${spec##*:}; name=${W}_${DT}
-    timeout 600 ncu --set full --clock-control none --import-source on -k regex:"tokenize_cells|csr_build" -s 4 -c 2 -f -o $O/prof_${name}_$TAG \
+    timeout 600 ncu --set full --clock-control none --import-source on -k regex:"tokenize_cells|tokenize_pct_warp|tokenize_f32_warp|csr_build" -s 4 -c 2 -f -o $O/prof_${name}_$TAG \
         python scripts/prof_driver.py $W 3 32768 $DT > $O/ncu_full_${name}_$TAG.log 2>&1; echo "ncu $name rc=$?"
     ncu -i $O/prof_${name}_$TAG.ncu-rep --page raw --csv > $O/ncu_raw_${name}_$TAG.csv 2>/dev/null
     ncu -i $O/prof_${name}_$TAG.ncu-rep --page source --csv > $O/ncu_source_${name}_$TAG.csv 2>/dev/null

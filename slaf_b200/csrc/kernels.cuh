@@ -982,6 +982,27 @@ __device__ bool process_cell(const TokArgs &a, const WindowSink &wsnk, uint32_t 
 }
 
 // ---- K2 fast path: persistent CTAs, TMA-staged cell segments ------------------------------------
+// min / max of the uint16 values of rows [t0, e) of the column (the rows of a long cell beyond its value stage), read by the whole
+// CTA from global memory: 128-bit loads over the aligned middle, single rows at the ragged ends
+__device__ __forceinline__ void minmax_rows_u16(const uint16_t *__restrict__ v, uint32_t t0, uint32_t e, uint32_t &lo, uint32_t &hi) {
+    if (t0 >= e) return;
+    const uint32_t m0 = min((t0 + 7u) & ~7u, e), m1 = max(m0, e & ~7u);
+    uint32_t mn2 = 0xffffffffu, mx2 = 0u;
+    for (uint32_t g = (m0 >> 3) + threadIdx.x; g < (m1 >> 3); g += kFastThreads) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4 *>(v) + g);
+        mn2 = __vminu2(__vminu2(mn2, __vminu2(q.x, q.y)), __vminu2(q.z, q.w));
+        mx2 = __vmaxu2(__vmaxu2(mx2, __vmaxu2(q.x, q.y)), __vmaxu2(q.z, q.w));
+    }
+    const uint32_t nh = m0 - t0, nt = e - m1;
+    if (threadIdx.x < nh + nt) {
+        const uint32_t r = threadIdx.x < nh ? t0 + threadIdx.x : m1 + (threadIdx.x - nh);
+        const uint32_t x = (uint32_t)__ldg(v + r);
+        mn2 = __vminu2(mn2, x | (x << 16));
+        mx2 = __vmaxu2(mx2, x | (x << 16));
+    }
+    lo = min(lo, min(mn2 & 0xffffu, mn2 >> 16));
+    hi = max(hi, max(mx2 & 0xffffu, mx2 >> 16));
+}
 // rows of the cell [s, e) whose uint16 value exceeds T: staged rows from shared memory, the rest
 // (cells larger than the value stage) from global memory.  Kept out of line: it runs for ~2% of
 // the cells and must not cost the common path registers.
@@ -1000,7 +1021,23 @@ __device__ __noinline__ uint32_t count_above_u16(const uint16_t *sv, const uint1
             above += (r >= s && r < s + n_v && key > T) ? 1u : 0u;
         }
     }
-    for (uint32_t r = s + n_v + threadIdx.x; r < e; r += kFastThreads) above += ((uint32_t)__ldg(value_g + r) > T) ? 1u : 0u;
+    // rows beyond the stage: 128-bit loads over the aligned middle, single rows at the ragged ends
+    const uint32_t t0 = s + n_v;
+    if (t0 < e) {
+        const uint32_t m0 = min((t0 + 7u) & ~7u, e), m1 = max(m0, e & ~7u);
+        const uint32_t Tc = min(T, 0xffffu), T2 = Tc | (Tc << 16);
+        uint32_t bits = 0;                                                  // 16 set bits per row above T
+        for (uint32_t g = (m0 >> 3) + threadIdx.x; g < (m1 >> 3); g += kFastThreads) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4 *>(value_g) + g);
+            bits += __popc(__vcmpgtu2(q.x, T2)) + __popc(__vcmpgtu2(q.y, T2)) + __popc(__vcmpgtu2(q.z, T2)) + __popc(__vcmpgtu2(q.w, T2));
+        }
+        above += bits >> 4;
+        const uint32_t nh = m0 - t0, nt = e - m1;
+        if (threadIdx.x < nh + nt) {
+            const uint32_t r = threadIdx.x < nh ? t0 + threadIdx.x : m1 + (threadIdx.x - nh);
+            above += ((uint32_t)__ldg(value_g + r) > T) ? 1u : 0u;
+        }
+    }
     return above;
 }
 
@@ -1411,12 +1448,7 @@ __global__ void __launch_bounds__(kFastThreads, fast_ctas_per_sm<ValT, MODE>()) 
                 }
             }
             // rows beyond the value stage (cells larger than vcap): straight from global memory
-            for (uint32_t r = s + d.n_v + tid; r < e; r += kFastThreads) {
-                const ValT x = __ldg(value_g + r);
-                const uint32_t key = key_of(x);
-                lo = min(lo, key);
-                hi = max(hi, key);
-            }
+            if constexpr (U16) minmax_rows_u16(reinterpret_cast<const uint16_t *>(value_g), s + d.n_v, e, lo, hi);
             lo = __reduce_min_sync(0xffffffffu, lo);
             hi = __reduce_max_sync(0xffffffffu, hi);
             if (lane == 0) { s_ws[warp] = lo; s_ws[kFastWarps + warp] = hi; }

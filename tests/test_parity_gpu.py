@@ -357,6 +357,34 @@ def test_float32_distinct_count_boundaries(engine, mode):
         compare(got, want, mode)
 
 
+@pytest.mark.parametrize("mode", ["geneformer", "scgpt_binned"])
+def test_float32_many_distinct_values_switch_to_the_cta_kernel(mode):
+    """float32 storage, warp-per-cell kernel (K2f): its per-warp set holds 255 distinct values; cells with more of them (but at most
+    max_items) are deferred to the general kernel, and a batch that defers more than one cell in eight moves the context to the
+    CTA-per-cell kernel (set of 1,536) for good.  Both batches must match the oracle; the deferral count shows the switch."""
+    from slaf_b200.engine import HotPathEngine
+
+    rng = np.random.default_rng(21)
+    k, C, n, d = 350, 256, 400, 300
+    cell = np.repeat(np.arange(C, dtype=np.uint32) + 5, n)
+    gene = np.concatenate([np.sort(rng.choice(60000, n, replace=False)) for _ in range(C)]).astype(np.uint16)
+    value = np.concatenate([rng.permutation(np.concatenate([np.arange(1, d + 1), rng.integers(1, d + 1, n - d)])) for _ in range(C)])
+    value = (value * 0.37 + 0.01).astype(np.float32)
+    want = c_oracle.tokenize(cell, gene, value, mode, k, n_bins=51, vocab_size=65000)
+    eng = HotPathEngine(0, max_rows=cell.size + 1024, max_cells=C + 16)
+    try:
+        cols = (to_dev(cell), to_dev(gene), to_dev(value))
+        slow = []
+        for _ in range(3):
+            compare(eng.tokenize(*cols, mode=mode, max_genes=k, n_bins=51, vocab_size=65000), want, mode)
+            torch.cuda.synchronize()
+            slow.append(eng.timing()["slow_cells"])
+        if not os.environ.get("SLAFB_F32_CTA"):
+            assert slow == [C, 0, 0], slow          # (timing() harvests the finished batch and returns the counts since the last call)
+    finally:
+        eng.close()
+
+
 @pytest.mark.parametrize("seed", range(24))
 def test_fuzz_random_shapes_and_parameters(engine, seed):
     """Randomised parity: random cell sizes (including 1-row and multi-thousand-row cells), value distributions
