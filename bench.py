@@ -940,7 +940,7 @@ def main():
     k1_e, k2_e, _ = bytes_over(n_ev)
     nt = max(1, tev["timed_batches"])
     k2_ms, k1_ms, gen_ms = tev["tokenize_ms"] / nt, tev["csr_ms"] / nt, tev["slowpath_ms"] / nt
-    slow_all = w.get("min_percentile") is not None and args.value_dtype == "float32"     # percentile on float32: the general kernel IS the tokenizer
+    slow_all = w.get("min_percentile") is not None and args.value_dtype == "float32" and bool(os.environ.get("SLAFB_F32_CTA"))     # percentile on float32 without the warp-per-cell kernel: the general kernel IS the tokenizer
     if slow_all:
         k2_ms, gen_ms = gen_ms, 0.0
         tiso["tokenize_ms"] = tiso["slowpath_ms"]
@@ -959,7 +959,7 @@ def main():
         k2_name = "tokenize_rank_kernel (per-cell sort)"
     elif slow_all:
         k2_name = "tokenize_general_kernel (exact k-th distinct value for every cell)"
-    elif w.get("min_percentile") is not None and not os.environ.get("SLAFB_PCT_CTA"):
+    elif w.get("min_percentile") is not None and args.value_dtype != "float32" and not os.environ.get("SLAFB_PCT_CTA"):
         k2_name = "tokenize_pct_warp_kernel"
     elif args.value_dtype == "float32" and not os.environ.get("SLAFB_F32_CTA"):
         k2_name = "tokenize_f32_warp_kernel"

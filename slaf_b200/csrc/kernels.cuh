@@ -2320,6 +2320,7 @@ template <typename GeneT, int MODE>
 __global__ void __launch_bounds__(kPctWarps * 32) tokenize_f32_warp_kernel(const FastArgs fa) {
     constexpr bool SCGPT = (MODE == MODE_SCGPT_RAW || MODE == MODE_SCGPT_BINNED);
     constexpr bool BINNED = (MODE == MODE_SCGPT_BINNED);
+    constexpr bool PCT = (MODE == MODE_GF_PCT);
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_bar[kPctWarps][2];
     const TokArgs &a = fa.t;
@@ -2336,6 +2337,8 @@ __global__ void __launch_bounds__(kPctWarps * 32) tokenize_f32_warp_kernel(const
     const uint32_t limit = SCGPT ? a.max_genes : (L - 1u);
     const uint32_t NC = a.n_cells;
     const uint32_t gcv = (fa.vcap >> 3) & ~31u;                             // 8-row groups the value stage holds (a multiple of the warp width)
+    const uint32_t gcg = (fa.gcap >> 3) & ~31u;                             // percentile mode: ... and the gene stage (any row may survive the filter)
+    const uint32_t lt = (1u << lane) - 1u;
     if (lane == 0) { mbar_init(bar, 1); mbar_init(bar_g, 1); mbar_fence_init(); }
     __syncwarp();
     const uint32_t G = gridDim.x * (uint32_t)kPctWarps;
@@ -2351,12 +2354,12 @@ __global__ void __launch_bounds__(kPctWarps * 32) tokenize_f32_warp_kernel(const
         const uint32_t ngroups = (sh + n + 7u) >> 3;
         const uint32_t colend = (n && a0 + (ngroups << 3) > R) ? 1u : 0u;
         const uint32_t ghot = ngroups - colend;
-        const uint32_t n_emit = min(n, limit);                              // this kernel only emits cells whose every row is kept
+        uint32_t n_emit = min(n, limit);                                    // (outside the percentile mode this kernel only emits cells whose every row is kept)
         const uint32_t nge = (sh + n_emit + 7u) >> 3;                       // groups that hold the rows to emit
-        bool keep_all = n <= k;
+        bool keep_all = PCT ? false : (n <= k);                             // the percentile rule also filters cells with few rows
         const bool pass1 = n && (BINNED || !keep_all);                      // the values are swept (maximum, distinct count)
         const bool hashing = n && !keep_all;
-        const uint32_t ngg = min(ghot, nge);                                // gene groups staged
+        const uint32_t ngg = PCT ? min(ghot, gcg) : min(ghot, nge);         // gene groups staged
         const uint32_t ngv = pass1 ? min(ghot, gcv) : (SCGPT ? ngg : 0u);   // value groups staged
         if (lane == 0) {
             if (ngv | ngg) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // (the stages' colend rows are written through the generic proxy)
@@ -2369,7 +2372,7 @@ __global__ void __launch_bounds__(kPctWarps * 32) tokenize_f32_warp_kernel(const
             for (int i = 0; i < kF32HashSlots / 32; i++) tab[lane + 32 * i] = 0xffffffffu;
         }
         // rows of the column's last partial group that are emitted: into the stages one by one (the last cell of a batch only)
-        if (colend && ngroups - 1u < nge && lane < 8u) {
+        if (!PCT && colend && ngroups - 1u < nge && lane < 8u) {
             const uint32_t r = a0 + ((ngroups - 1u) << 3) + lane;
             if (r >= s && r < s + n_emit) { sg[r - a0] = __ldg(gene_g + r); if constexpr (SCGPT) sv[r - a0] = __ldg(value_g + r); }
         }
@@ -2379,6 +2382,8 @@ __global__ void __launch_bounds__(kPctWarps * 32) tokenize_f32_warp_kernel(const
         float xmax = -INFINITY;
         uint32_t ins = 0u;                                                  // keys this lane added to the set
         bool defer = false, live = hashing;                                 // live: the set still decides (uniform)
+        float thr_f = 0.0f;                                                 // percentile mode: the smallest value that is kept
+        (void)thr_f; (void)lt; (void)gcg;
         auto group_mask = [&](uint32_t p0) -> uint32_t {
             const int lo_i = max((int)sh - (int)p0, 0);
             const int hi_i = min((int)(sh + n) - (int)p0, 8);
@@ -2487,13 +2492,130 @@ __global__ void __launch_bounds__(kPctWarps * 32) tokenize_f32_warp_kernel(const
             kmax = __reduce_max_sync(0xffffffffu, key_of(xmax));
             if (hashing) {
                 const uint32_t D = __reduce_add_sync(0xffffffffu, ins);
-                if (live && D <= min(k, (uint32_t)kF32HashCap)) keep_all = true; else defer = true;   // D <= k distinct values: every row has rank <= k
+                if constexpr (PCT) {
+                    // Percentile branch (aggregators.py:167-196): the set holds every distinct value of the cell; keep the rows whose
+                    // value is at least the a*-th smallest of them.  That value is found by a* rounds of "smallest key not below
+                    // the bound" over the set (16 slots per lane, one warp minimum per round; a* is a percentile of D: small).
+                    if (!live || D > (uint32_t)kF32HashCap) {
+                        defer = true;
+                    } else {
+                        const uint32_t astar = target_asc_rank(D, k, true, a.min_pct);
+                        keep_all = (astar == 1u);
+                        if (!keep_all) {
+                            uint32_t ok[kF32HashSlots / 32];
+#pragma unroll
+                            for (int i = 0; i < kF32HashSlots / 32; i++) {
+                                const uint32_t bits = vt[lane + 32 * i];
+                                ok[i] = bits == 0xffffffffu ? 0xffffffffu : key_of(__uint_as_float(bits));
+                            }
+                            uint32_t lowb = 0u, sel = 0u;
+                            for (uint32_t t = 0; t < astar; t++) {
+                                uint32_t m = 0xffffffffu;
+#pragma unroll
+                                for (int i = 0; i < kF32HashSlots / 32; i++) m = ok[i] >= lowb ? min(m, ok[i]) : m;
+                                sel = __reduce_min_sync(0xffffffffu, m);
+                                lowb = sel + 1u;
+                            }
+                            thr_f = float_of_key(sel);
+                        }
+                    }
+                } else {
+                    if (live && D <= min(k, (uint32_t)kF32HashCap)) keep_all = true; else defer = true;   // D <= k distinct values: every row has rank <= k
+                }
             }
         }
         if (jn < NC) { sn = __ldg(a.seg_start + cn); en = __ldg(a.seg_start + cn + 1); cidn = __ldg(a.seg_cell + cn); }
         if (ngg) {
             mbar_wait(bar_g, phase_g);                                      // the genes (their copy flew during the sweep)
             phase_g ^= 1u;
+        }
+        if constexpr (PCT) {
+            if (n && !defer && (!keep_all || ngg < ngroups)) {
+                // ---- row-order compaction, IN PLACE in the gene stage (the percentile kernel's: 256 rows per step, offsets from a
+                // ballot prefix, predicated stores; rows beyond the stages come from global memory, next step's loads in flight)
+                struct V8 { float4 a, b; };
+                struct G8 { uint4 a, b; };
+                auto ldv8 = [&](uint32_t gi) -> V8 {
+                    V8 r;
+                    if (gi < ngv) { r.a = sv4[2u * gi]; r.b = sv4[2u * gi + 1u]; }
+                    else { const float4 *pp = reinterpret_cast<const float4 *>(value_g + a0 + (gi << 3)); r.a = __ldg(pp); r.b = __ldg(pp + 1); }
+                    return r;
+                };
+                auto ldg8 = [&](uint32_t gi) -> G8 {
+                    G8 r;
+                    r.b = make_uint4(0u, 0u, 0u, 0u);
+                    if (gi < ngg) {
+                        if constexpr (sizeof(GeneT) == 2) r.a = reinterpret_cast<const uint4 *>(sg)[gi];
+                        else { r.a = reinterpret_cast<const uint4 *>(sg)[2u * gi]; r.b = reinterpret_cast<const uint4 *>(sg)[2u * gi + 1u]; }
+                    } else {
+                        const uint4 *gp = reinterpret_cast<const uint4 *>(gene_g + a0 + (gi << 3));
+                        r.a = __ldg(gp);
+                        if constexpr (sizeof(GeneT) == 4) r.b = __ldg(gp + 1);
+                    }
+                    return r;
+                };
+                const float thr = keep_all ? -INFINITY : thr_f;
+                const uint32_t sg_addr = smem_u32(sg + sh);
+                uint32_t base = 0u;
+                if (ghot) {
+                    const uint32_t glast = ghot - 1u;
+                    V8 qvn = ldv8(min(lane, glast));
+                    G8 qgn = ldg8(min(lane, glast));
+                    for (uint32_t g0 = 0u; g0 < ghot && base < limit; g0 += 32u) {
+                        const uint32_t gi = g0 + lane, p0 = gi << 3;
+                        const V8 q = qvn;
+                        const G8 gq = qgn;
+                        qvn = ldv8(min(gi + 32u, glast));
+                        qgn = ldg8(min(gi + 32u, glast));
+                        uint32_t flags = (q.a.x >= thr ? 1u : 0u) | (q.a.y >= thr ? 2u : 0u) | (q.a.z >= thr ? 4u : 0u) | (q.a.w >= thr ? 8u : 0u) |
+                                         (q.b.x >= thr ? 16u : 0u) | (q.b.y >= thr ? 32u : 0u) | (q.b.z >= thr ? 64u : 0u) | (q.b.w >= thr ? 128u : 0u);
+                        flags = gi < ghot ? (flags & group_mask(min(p0, sh + n - 1u))) : 0u;
+                        GeneT g[8];
+                        if constexpr (sizeof(GeneT) == 2) {
+                            const uint32_t g4[4] = {gq.a.x, gq.a.y, gq.a.z, gq.a.w};
+#pragma unroll
+                            for (int i = 0; i < 8; i++) g[i] = (GeneT)((g4[i >> 1] >> ((i & 1) * 16)) & 0xffffu);
+                        } else {
+                            g[0] = (GeneT)gq.a.x; g[1] = (GeneT)gq.a.y; g[2] = (GeneT)gq.a.z; g[3] = (GeneT)gq.a.w;
+                            g[4] = (GeneT)gq.b.x; g[5] = (GeneT)gq.b.y; g[6] = (GeneT)gq.b.z; g[7] = (GeneT)gq.b.w;
+                        }
+                        __syncwarp();                                         // every lane holds its genes in registers: the stage may be overwritten
+                        const uint32_t pcf = __popc(flags);
+                        const uint32_t b0 = __ballot_sync(0xffffffffu, pcf & 1u), b1 = __ballot_sync(0xffffffffu, pcf & 2u),
+                                       b2 = __ballot_sync(0xffffffffu, pcf & 4u), b3 = __ballot_sync(0xffffffffu, pcf & 8u);
+                        const uint32_t off = base + __popc(b0 & lt) + 2u * __popc(b1 & lt) + 4u * __popc(b2 & lt) + 8u * __popc(b3 & lt);
+                        base += __reduce_add_sync(0xffffffffu, pcf);
+                        SLAFB_CHECK(off + pcf > limit || sh + off + pcf <= fa.gcap, 242, sh + off);
+                        if (off + pcf <= limit) {
+                            uint32_t ad = sg_addr + off * (uint32_t)sizeof(GeneT);
+#pragma unroll
+                            for (int i = 0; i < 8; i++) sts_if<GeneT>(ad, g[i], flags & (1u << i));
+                        } else {
+                            uint32_t o2 = off;
+#pragma unroll
+                            for (int i = 0; i < 8; i++) {
+                                if (flags & (1u << i)) {
+                                    if (o2 < limit) sg[sh + o2] = g[i];
+                                    o2++;
+                                }
+                            }
+                        }
+                    }
+                }
+                if (colend && base < limit) {
+                    if (lane == 0) {
+                        for (uint32_t r = max(s, a0 + (ghot << 3)); r < e; r++) {
+                            if (__ldg(value_g + r) >= thr) {
+                                if (base < limit) sg[sh + base] = __ldg(gene_g + r);
+                                base++;
+                            }
+                        }
+                    }
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                }
+                n_emit = min(base, limit);
+                __syncwarp();
+            }
         }
         if (defer) {
             if (lane == 0) {

@@ -422,6 +422,7 @@ int launch_f32_warp(slafb_ctx *ctx, const TokArgs &a, cudaStream_t st, bool *lau
     uint32_t vcap = vcap_env ? vcap_env : 2304u;
     if (fa.gcap > vcap) vcap = fa.gcap;             // the emitted rows' values are staged as well ...
     fa.vcap = (vcap + 255u) & ~255u;                // ... in a whole number of 256-row steps of the warp
+    if (MODE == MODE_GF_PCT) fa.gcap = fa.vcap;     // percentile mode: any row may survive the filter, the gene stage is as long as the value stage
     fa.ticket = a.work_counters + 2;
     const size_t smem = (size_t)kPctWarps * f32_warp_bytes<GeneT>(fa.vcap, fa.gcap);
     if (smem > 200 * 1024) return SLAFB_OK;         // very wide rows: the CTA kernel / general kernel take them
@@ -457,6 +458,7 @@ int dispatch_fast(slafb_ctx *ctx, int mode, const TokArgs &a, cudaStream_t st, b
         if (mode == MODE_GF) rc = launch_f32_warp<GeneT, MODE_GF>(ctx, a, st, launched);
         else if (mode == MODE_SCGPT_RAW) rc = launch_f32_warp<GeneT, MODE_SCGPT_RAW>(ctx, a, st, launched);
         else if (mode == MODE_SCGPT_BINNED) rc = launch_f32_warp<GeneT, MODE_SCGPT_BINNED>(ctx, a, st, launched);
+        else if (mode == MODE_GF_PCT) rc = launch_f32_warp<GeneT, MODE_GF_PCT>(ctx, a, st, launched);
         if (rc || *launched) return rc;
     }
     switch (mode) {

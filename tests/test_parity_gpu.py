@@ -493,10 +493,14 @@ def test_percentile_fast_kernel_shapes(engine, pct, gene_dtype):
     gene = np.concatenate([cells[j][0] for j in order]).astype(gene_dtype)
     value = np.concatenate([cells[j][1] for j in order]).astype(np.uint16)
     C = len(cells)
-    for k, max_genes in ((2048, 2048), (64, 64), (20, 300), (2048, 100)):
-        want = c_oracle.tokenize(cell, gene, value, "geneformer_pct", max_genes, max_items=k, perm=py_perm(3, C), min_percentile=pct)
-        got = engine.tokenize(cell, gene, value, mode="geneformer_pct", max_genes=max_genes, max_items=k, min_percentile=pct, shuffle_seed=3)
-        compare(got, want, "geneformer_pct")
+    # the same cells as float32 storage (a monotone, injective image of the counts: same ranks, same ties) run in the float32
+    # warp-per-cell kernel, whose set holds 255 distinct values: the wide cells are deferred to the general kernel
+    value_f32 = (value.astype(np.float64) * 0.37 + 0.01).astype(np.float32)
+    for val in (value, value_f32):
+        for k, max_genes in ((2048, 2048), (64, 64), (20, 300), (2048, 100)):
+            want = c_oracle.tokenize(cell, gene, val, "geneformer_pct", max_genes, max_items=k, perm=py_perm(3, C), min_percentile=pct)
+            got = engine.tokenize(cell, gene, val, mode="geneformer_pct", max_genes=max_genes, max_items=k, min_percentile=pct, shuffle_seed=3)
+            compare(got, want, "geneformer_pct")
     t = engine.timing()
     assert t["tokenize_ms"] > 0.0                                  # the fast kernel ran
 
