@@ -385,7 +385,7 @@ def test_float32_many_distinct_values_switch_to_the_cta_kernel(mode):
         eng.close()
 
 
-@pytest.mark.parametrize("seed", range(24))
+@pytest.mark.parametrize("seed", range(64))
 def test_fuzz_random_shapes_and_parameters(engine, seed):
     """Randomised parity: random cell sizes (including 1-row and multi-thousand-row cells), value distributions
     (ties, heavy tails, all-equal, all-distinct), dtypes, modes, k / max_genes / n_bins, shuffles and perm selections."""
