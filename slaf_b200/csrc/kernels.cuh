@@ -2781,6 +2781,7 @@ struct RankArgs {
     uint32_t n_norm;
     int rank_order;
     unsigned long long *scratch64;   // [n_rows] composites of cells larger than kRankSmemKeys
+    int from_list;                   // tokenize_rank_kernel: take the output rows from the work list (what the bucket kernel left over)
 };
 constexpr int kRankSmemKeys = 4096;       // composites sorted in registers + shared memory up to here (32 KiB per CTA: six CTAs per SM)
 
@@ -2865,6 +2866,91 @@ __device__ __forceinline__ uint32_t rank_key(const RankArgs &ra, GeneT g, ValT v
     return key_of(__fdiv_rn((float)v, d));
 }
 
+// after the sort: `keys` holds the cell's composites (~key << 32 | row) in ascending order.  Dense-rank cut, emission in rank or
+// row order, CLS / SEP / PAD / mask / cell id.  Whole CTA; s_ws = 32 words, s_bcast = 4 words of shared scratch.
+template <typename GeneT, typename ValT>
+__device__ __forceinline__ void rank_emit(const RankArgs &ra, const unsigned long long *keys, uint32_t j, uint32_t c, uint32_t s, uint32_t n,
+                                          uint32_t *s_ws, uint32_t *s_bcast) {
+    const TokArgs &a = ra.t;
+    const int tid = threadIdx.x;
+    const GeneT *__restrict__ gene = static_cast<const GeneT *>(a.gene);
+    const ValT *__restrict__ value = static_cast<const ValT *>(a.value);
+    const uint32_t k = a.max_items, L = a.L, limit = L - 1u;
+    // m = rows with dense rank <= k: the prefix before the (k+1)-th distinct key.  Thread t counts the distinct-key heads of its
+    // contiguous slice of the sorted array, ONE block scan places the slices, and the thread whose slice holds head number k
+    // (0-based) walks it once more to find the position.
+    if (tid == 0) s_bcast[0] = n;
+    const uint32_t per = (n + kTokThreads - 1u) / kTokThreads;
+    const uint32_t i0 = min((uint32_t)tid * per, n), i1 = min(i0 + per, n);
+    uint32_t heads = 0u;
+    {
+        uint32_t prev = i0 ? (uint32_t)(keys[i0 - 1u] >> 32) : 0u;
+        for (uint32_t i = i0; i < i1; i++) {
+            const uint32_t cur = (uint32_t)(keys[i] >> 32);
+            heads += (i == 0u || cur != prev) ? 1u : 0u;
+            prev = cur;
+        }
+    }
+    uint32_t tot_heads;
+    const uint32_t ex = block_excl_scan(heads, s_ws, tot_heads);           // (its barriers also publish s_bcast[0] = n)
+    if (ex <= k && k < ex + heads) {
+        uint32_t run = ex, prev = i0 ? (uint32_t)(keys[i0 - 1u] >> 32) : 0u;
+        for (uint32_t i = i0; i < i1; i++) {
+            const uint32_t cur = (uint32_t)(keys[i] >> 32);
+            if (i == 0u || cur != prev) {
+                if (run == k) { s_bcast[0] = i; break; }
+                run++;
+            }
+            prev = cur;
+        }
+    }
+    __syncthreads();
+    const uint32_t m = s_bcast[0];
+    const size_t row_base = (size_t)j * L;
+    uint32_t n_emit;
+    if (ra.rank_order) {
+        n_emit = min(m, limit);
+        for (uint32_t r = tid; r < n_emit; r += kTokThreads) {
+            const GeneT g = __ldg(gene + s + (uint32_t)(keys[r] & 0xffffffffull));
+            long long gid;
+            if constexpr (sizeof(GeneT) == 2) gid = (long long)g; else gid = (long long)(int32_t)g;
+            a.ids[row_base + 1 + r] = gid + 4;
+        }
+    } else {
+        // row order: keep rows whose key is >= the smallest kept key
+        const uint32_t thr_inv = m ? (uint32_t)(keys[m - 1] >> 32) : 0u;      // largest ~key kept
+        __syncthreads();
+        uint32_t base = 0;
+        for (uint32_t ib = 0; ib < n && base < limit; ib += kTokThreads) {
+            const uint32_t i = ib + tid;
+            GeneT g{};
+            uint32_t kp = 0;
+            if (i < n) {
+                g = __ldg(gene + s + i);
+                kp = (m && (~rank_key<GeneT, ValT>(ra, g, __ldg(value + s + i)) <= thr_inv)) ? 1u : 0u;
+            }
+            uint32_t tot;
+            const uint32_t off = base + block_excl_scan(kp, s_ws, tot);
+            if (kp && off < limit) {
+                long long gid;
+                if constexpr (sizeof(GeneT) == 2) gid = (long long)g; else gid = (long long)(int32_t)g;
+                a.ids[row_base + 1 + off] = gid + 4;
+            }
+            base += tot;
+        }
+        n_emit = min(base, limit);
+    }
+    const uint32_t sep_pos = 1u + n_emit, t_len = min(n_emit + 2u, L);
+    if (tid == 0) {
+        a.ids[row_base] = 1;
+        if (sep_pos < L) a.ids[row_base + sep_pos] = 2;
+        const uint32_t cid = __ldg(a.seg_cell + c);
+        a.cell_ids[j] = a.cell_signed ? (long long)(int32_t)cid : (long long)cid;
+    }
+    fill_zero_i64(a.ids, row_base + t_len, row_base + L);
+    fill_mask(a.mask, row_base, L, t_len);
+}
+
 template <typename GeneT, typename ValT>
 __global__ void __launch_bounds__(kTokThreads) tokenize_rank_kernel(const RankArgs ra) {
     extern __shared__ __align__(16) unsigned long long rk_keys[];
@@ -2873,13 +2959,14 @@ __global__ void __launch_bounds__(kTokThreads) tokenize_rank_kernel(const RankAr
     const int tid = threadIdx.x;
     const GeneT *__restrict__ gene = static_cast<const GeneT *>(a.gene);
     const ValT *__restrict__ value = static_cast<const ValT *>(a.value);
-    const uint32_t k = a.max_items, L = a.L, limit = L - 1u;
+    const uint32_t count = ra.from_list ? a.work_counters[0] : a.n_cells;
     for (;;) {
         __syncthreads();
         if (tid == 0) s_item = atomicAdd(a.work_counters + 1, 1u);
         __syncthreads();
-        const uint32_t j = s_item;
-        if (j >= a.n_cells) break;
+        if (s_item >= count) break;
+        const uint32_t j = ra.from_list ? a.work_list[s_item] : s_item;
+        if (j == 0xffffffffu) continue;                                     // (tokenized by the second bucket launch)
         const uint32_t c = a.perm ? (uint32_t)a.perm[j] : j;
         const uint32_t s = __ldg(a.seg_start + c), e = __ldg(a.seg_start + c + 1), n = e - s;
         unsigned long long *keys = (n <= (uint32_t)kRankSmemKeys) ? rk_keys : (ra.scratch64 + s);
@@ -2911,63 +2998,223 @@ __global__ void __launch_bounds__(kTokThreads) tokenize_rank_kernel(const RankAr
             __syncthreads();
             bitonic_sort_asc_u64(keys, n);
         }
-        // m = rows with dense rank <= k: the prefix before the (k+1)-th distinct key
-        if (tid == 0) s_bcast[0] = n;
+        rank_emit<GeneT, ValT>(ra, keys, j, c, s, n, s_ws, s_bcast);
+    }
+}
+
+// K6b (extension): the rank-value kernel without a sorting network.  The composites of a cell are DISTRIBUTED over buckets by a
+// monotone function of the key, the bucket counts are prefix-summed, every composite goes to its bucket's range, and the order
+// inside a bucket comes from every row counting the smaller composites of its own bucket (work spread by rows: a cluster of keys
+// keeps all threads busy).  The bucket function has two levels so that it adapts to the cell: 256 coarse buckets cut the range
+// [min, max] of the order-preserving key bits evenly; a coarse bucket that received c rows is cut evenly again into the power of
+// two >= c / 2 fine buckets.  Keys spread like the bits of a log-normal and keys clustered around a few values (a normaliser that
+// hardly varies between genes) both end up with one or two rows per fine bucket -- a few passes over ~2,000 rows instead of 78
+// compare-exchange stages over 4,096 slots.  E = rows per thread held in registers: the first launch (E = 16) takes the cells of
+// up to 4,096 rows, a second one (E = 32, from the work list) those of up to 8,192; what is left -- longer cells, or a fine bucket
+// of more than kRbMaxBucket rows (heavy ties: e.g. no normaliser at all) -- is drained by tokenize_rank_kernel (the sorting
+// network).  Exact: the bucket index is non-decreasing in the composite, and inside a bucket the full 64-bit composites
+// (~key, row) are compared.
+// a cell too long for the shared-memory paths: composites into the global scratch, generic bitonic sort by the whole CTA, emission
+template <typename GeneT, typename ValT>
+__device__ __noinline__ void rank_giant_cell(const RankArgs &ra, uint32_t j, uint32_t c, uint32_t s, uint32_t n, uint32_t *s_ws, uint32_t *s_bcast) {
+    const GeneT *__restrict__ gene = static_cast<const GeneT *>(ra.t.gene);
+    const ValT *__restrict__ value = static_cast<const ValT *>(ra.t.value);
+    unsigned long long *keys = ra.scratch64 + s;
+    for (uint32_t i = threadIdx.x; i < n; i += kTokThreads) {
+        const uint32_t key = rank_key<GeneT, ValT>(ra, __ldg(gene + s + i), __ldg(value + s + i));
+        keys[i] = ((unsigned long long)(~key) << 32) | (unsigned long long)i;
+    }
+    __syncthreads();
+    bitonic_sort_asc_u64(keys, n);
+    rank_emit<GeneT, ValT>(ra, keys, j, c, s, n, s_ws, s_bcast);
+}
+
+constexpr int kRbCoarse = 256;
+constexpr int kRbMaxBucket = 64;
+template <int E>
+__host__ __device__ constexpr size_t rank_bucket_smem() {
+    return (size_t)E * kTokThreads * sizeof(unsigned long long)             // composites
+           + ((size_t)E * kTokThreads + 2 * kRbCoarse) * sizeof(uint32_t)   // fine counts / offsets (sum of the fine-bucket numbers <= n + 256)
+           + 2 * (size_t)kRbCoarse * sizeof(uint32_t);                      // coarse counts -> first fine bucket, log2 of the fine-bucket number
+}
+template <typename GeneT, typename ValT, int E>
+__global__ void __launch_bounds__(kTokThreads, E == 16 ? 4 : 2) tokenize_rank_bucket_kernel(const RankArgs ra) {
+    constexpr uint32_t NK = (uint32_t)E * kTokThreads;                      // rows the shared-memory array holds
+    constexpr uint32_t NF = NK + 2u * kRbCoarse;                            // fine counters
+    constexpr int FPT = (int)(NF / kTokThreads);                            // fine counters per thread (contiguous), a multiple of 2
+    extern __shared__ __align__(16) unsigned long long rb_keys[];
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(rb_keys + NK);            // [NF]
+    uint32_t *cfirst = cnt + NF;                                            // [256] coarse count, then the first fine bucket of the coarse one
+    uint32_t *clog = cfirst + kRbCoarse;                                    // [256] log2 of its number of fine buckets
+    __shared__ uint32_t s_ws[32], s_bcast[4], s_item;
+    const TokArgs &a = ra.t;
+    const int tid = threadIdx.x;
+    const GeneT *__restrict__ gene = static_cast<const GeneT *>(a.gene);
+    const ValT *__restrict__ value = static_cast<const ValT *>(a.value);
+    const uint32_t count = ra.from_list ? a.work_counters[0] : a.n_cells;
+    uint32_t *ticket = ra.from_list ? a.work_counters + 3 : a.work_counters + 2;
+    for (;;) {
         __syncthreads();
-        uint32_t run = 0;
-        for (uint32_t ib = 0; ib < n && run <= k; ib += kTokThreads) {
-            const uint32_t i = ib + tid;
-            const uint32_t head = (i < n && (i == 0 || (uint32_t)(keys[i] >> 32) != (uint32_t)(keys[i - 1] >> 32))) ? 1u : 0u;
-            uint32_t tot;
-            const uint32_t ex = run + block_excl_scan(head, s_ws, tot);
-            if (head && ex == k) atomicMin(&s_bcast[0], i);
-            run += tot;
+        if (tid == 0) s_item = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const uint32_t item = s_item;
+        if (item >= count) break;
+        const uint32_t j = ra.from_list ? a.work_list[item] : item;
+        if (j == 0xffffffffu) continue;
+        const uint32_t c = a.perm ? (uint32_t)a.perm[j] : j;
+        const uint32_t s = __ldg(a.seg_start + c), e = __ldg(a.seg_start + c + 1), n = e - s;
+        // what this launch cannot take stays on / goes to the work list (from_list: the entry simply stays)
+        auto leave = [&]() { if (!ra.from_list && tid == 0) a.work_list[atomicAdd(a.work_counters, 1u)] = j; };
+        if (!ra.from_list && n > 2u * NK) {
+            // a giant cell (beyond the second launch as well): sorted in global scratch by this CTA right here, while the other CTAs
+            // go on -- left to the sorting kernel it would be that launch's only work item and the step's tail
+            rank_giant_cell<GeneT, ValT>(ra, j, c, s, n, s_ws, s_bcast);
+            continue;
         }
-        __syncthreads();
-        const uint32_t m = s_bcast[0];
-        const size_t row_base = (size_t)j * L;
-        uint32_t n_emit;
-        if (ra.rank_order) {
-            n_emit = min(m, limit);
-            for (uint32_t r = tid; r < n_emit; r += kTokThreads) {
-                const GeneT g = __ldg(gene + s + (uint32_t)(keys[r] & 0xffffffffull));
-                long long gid;
-                if constexpr (sizeof(GeneT) == 2) gid = (long long)g; else gid = (long long)(int32_t)g;
-                a.ids[row_base + 1 + r] = gid + 4;
+        if (n > NK) { leave(); continue; }                                  // (uniform)
+        // 1. inverted keys of the rows tid, tid + 256, ... in registers (loads in batches of eight rows: gene and value first, then
+        // the gathers of the normaliser, so that eight of each are in flight); range of the cell; counters cleared
+        uint32_t ik[E], lo = 0xffffffffu, hi = 0u;
+#pragma unroll
+        for (int r0 = 0; r0 < E; r0 += 8) {
+            GeneT g8[8];
+            ValT v8[8];
+            float d8[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const uint32_t i = (uint32_t)tid + (uint32_t)(r0 + q) * kTokThreads;
+                g8[q] = GeneT{}; v8[q] = ValT{};
+                if (i < n) { g8[q] = __ldg(gene + s + i); v8[q] = __ldg(value + s + i); }
             }
-        } else {
-            // row order: keep rows whose key is >= the smallest kept key
-            const uint32_t thr_inv = m ? (uint32_t)(keys[m - 1] >> 32) : 0u;      // largest ~key kept
-            __syncthreads();
-            uint32_t base = 0;
-            for (uint32_t ib = 0; ib < n && base < limit; ib += kTokThreads) {
-                const uint32_t i = ib + tid;
-                GeneT g{};
-                uint32_t kp = 0;
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const uint32_t i = (uint32_t)tid + (uint32_t)(r0 + q) * kTokThreads;
+                const uint32_t gi = (uint32_t)g8[q];
+                d8[q] = (i < n && ra.norm != nullptr && gi < ra.n_norm) ? __ldg(ra.norm + gi) : 1.0f;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const uint32_t i = (uint32_t)tid + (uint32_t)(r0 + q) * kTokThreads;
+                ik[r0 + q] = 0xffffffffu;
                 if (i < n) {
-                    g = __ldg(gene + s + i);
-                    kp = (m && (~rank_key<GeneT, ValT>(ra, g, __ldg(value + s + i)) <= thr_inv)) ? 1u : 0u;
+                    ik[r0 + q] = ~(ra.norm == nullptr ? key_of(v8[q]) : key_of(__fdiv_rn((float)v8[q], d8[q])));
+                    lo = min(lo, ik[r0 + q]);
+                    hi = max(hi, ik[r0 + q]);
                 }
-                uint32_t tot;
-                const uint32_t off = base + block_excl_scan(kp, s_ws, tot);
-                if (kp && off < limit) {
-                    long long gid;
-                    if constexpr (sizeof(GeneT) == 2) gid = (long long)g; else gid = (long long)(int32_t)g;
-                    a.ids[row_base + 1 + off] = gid + 4;
-                }
-                base += tot;
             }
-            n_emit = min(base, limit);
         }
-        const uint32_t sep_pos = 1u + n_emit, t_len = min(n_emit + 2u, L);
-        if (tid == 0) {
-            a.ids[row_base] = 1;
-            if (sep_pos < L) a.ids[row_base + sep_pos] = 2;
-            const uint32_t cid = __ldg(a.seg_cell + c);
-            a.cell_ids[j] = a.cell_signed ? (long long)(int32_t)cid : (long long)cid;
+        {
+            uint2 *c2 = reinterpret_cast<uint2 *>(cnt) + tid * (FPT / 2);
+#pragma unroll
+            for (int q = 0; q < FPT / 2; q++) c2[q] = make_uint2(0u, 0u);
+            cfirst[tid] = 0u;                                               // (kRbCoarse == kTokThreads)
         }
-        fill_zero_i64(a.ids, row_base + t_len, row_base + L);
-        fill_mask(a.mask, row_base, L, t_len);
+        block_minmax(lo, hi, s_ws);                                         // (two barriers: the counters are cleared for everybody after it)
+        const uint32_t range = hi - lo;
+        const uint32_t sh1 = range >= (uint32_t)kRbCoarse ? (32u - (uint32_t)__clz(range)) - 8u : 0u;      // (range >> sh1) < 256
+        // 2. coarse histogram
+#pragma unroll
+        for (int r = 0; r < E; r++) {
+            const uint32_t i = (uint32_t)tid + (uint32_t)r * kTokThreads;
+            if (i < n) atomicAdd(&cfirst[(ik[r] - lo) >> sh1], 1u);
+        }
+        __syncthreads();
+        // 3. fine buckets per coarse bucket: the power of two >= count / 2 (at most the 2^sh1 key values it spans), and their prefix
+        {
+            const uint32_t cc = cfirst[tid];
+            uint32_t lg = cc > 2u ? 32u - (uint32_t)__clz((cc - 1u) >> 1) : 0u;      // ceil(log2(cc / 2)) for cc > 2
+            lg = min(lg, sh1);
+            uint32_t tot;
+            const uint32_t fb = block_excl_scan(1u << lg, s_ws, tot);      // (barriers inside: every coarse count has been read)
+            SLAFB_CHECK(fb + (1u << lg) <= NF, 253, fb);
+            cfirst[tid] = fb;
+            clog[tid] = lg;
+        }
+        __syncthreads();
+        // fine bucket of a key: its coarse bucket's first fine bucket + the leading bits of its offset inside the coarse bucket
+        auto fine = [&](uint32_t k32) -> uint32_t {
+            const uint32_t d = k32 - lo, cb = d >> sh1;
+            return cfirst[cb] + ((d & ((1u << sh1) - 1u)) >> (sh1 - clog[cb]));
+        };
+        // 4. fine histogram; the value the atomic returns is the row's slot inside its bucket (four 8-bit slots per register; the
+        // bucket itself is recomputed where it is needed again: registers are what limits the CTAs per SM here)
+        uint32_t slot[E / 4];
+#pragma unroll
+        for (int q = 0; q < E / 4; q++) slot[q] = 0u;
+#pragma unroll
+        for (int r = 0; r < E; r++) {
+            const uint32_t i = (uint32_t)tid + (uint32_t)r * kTokThreads;
+            if (i < n) {
+                const uint32_t f = fine(ik[r]);
+                SLAFB_CHECK(f < NF, 250, f);
+                slot[r >> 2] |= min(atomicAdd(&cnt[f], 1u), 255u) << (8 * (r & 3));
+            }
+        }
+        __syncthreads();
+        // 5. exclusive prefix over the fine counts (thread t owns FPT contiguous ones); largest bucket
+        uint32_t sum = 0u, mx = 0u;
+        {
+            const uint2 *c2 = reinterpret_cast<const uint2 *>(cnt) + tid * (FPT / 2);
+#pragma unroll
+            for (int q = 0; q < FPT / 2; q++) { const uint2 v = c2[q]; sum += v.x + v.y; mx = max(mx, max(v.x, v.y)); }
+        }
+        uint32_t tot;
+        const uint32_t first = block_excl_scan(sum, s_ws, tot);
+        if (__syncthreads_or(mx > (uint32_t)kRbMaxBucket)) { leave(); continue; }     // heavy ties: the sorting kernel takes the cell
+        {
+            uint32_t run = first;
+            uint2 *c2 = reinterpret_cast<uint2 *>(cnt) + tid * (FPT / 2);
+#pragma unroll
+            for (int q = 0; q < FPT / 2; q++) {
+                const uint2 v = c2[q];
+                uint2 o;
+                o.x = run; run += v.x;
+                o.y = run; run += v.y;
+                c2[q] = o;
+            }
+        }
+        __syncthreads();
+        // 6. every composite into its bucket's range (any order inside the bucket)
+#pragma unroll
+        for (int r = 0; r < E; r++) {
+            const uint32_t i = (uint32_t)tid + (uint32_t)r * kTokThreads;
+            if (i < n) {
+                const uint32_t pos = cnt[fine(ik[r])] + ((slot[r >> 2] >> (8 * (r & 3))) & 0xffu);
+                SLAFB_CHECK(pos < n, 251, pos);
+                rb_keys[pos] = ((unsigned long long)ik[r] << 32) | (unsigned long long)i;
+            }
+        }
+        __syncthreads();
+        // 7. order inside the buckets: every row counts the composites of its bucket that are smaller than its own -- its final
+        // place.  Places first, barrier, then the composites -- still in registers -- are written to their final positions.
+        uint32_t place[E / 2];                                              // two 16-bit positions per register
+#pragma unroll
+        for (int q = 0; q < E / 2; q++) place[q] = 0u;
+#pragma unroll
+        for (int r = 0; r < E; r++) {
+            const uint32_t i = (uint32_t)tid + (uint32_t)r * kTokThreads;
+            if (i < n) {
+                const uint32_t f = fine(ik[r]);
+                const uint32_t o = cnt[f], oe = (f + 1u < NF) ? cnt[f + 1u] : n;
+                const unsigned long long mine = ((unsigned long long)ik[r] << 32) | (unsigned long long)i;
+                uint32_t rank = 0u;
+                for (uint32_t x = o; x < oe; x++) rank += rb_keys[x] < mine ? 1u : 0u;
+                place[r >> 1] |= (o + rank) << (16 * (r & 1));
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < E; r++) {
+            const uint32_t i = (uint32_t)tid + (uint32_t)r * kTokThreads;
+            if (i < n) {
+                const uint32_t pos = (place[r >> 1] >> (16 * (r & 1))) & 0xffffu;
+                SLAFB_CHECK(pos < n, 252, pos);
+                rb_keys[pos] = ((unsigned long long)ik[r] << 32) | (unsigned long long)i;
+            }
+        }
+        __syncthreads();
+        rank_emit<GeneT, ValT>(ra, rb_keys, j, c, s, n, s_ws, s_bcast);
+        if (ra.from_list && tid == 0) a.work_list[item] = 0xffffffffu;      // done: the sorting kernel skips the entry
     }
 }
 

@@ -337,7 +337,43 @@ int launch_general(slafb_ctx *ctx, const TokArgs &a, const WindowSink &w, cudaSt
 }
 
 template <typename GeneT, typename ValT>
-int launch_rank(slafb_ctx *ctx, const RankArgs &ra, cudaStream_t st) {
+int launch_rank(slafb_ctx *ctx, const RankArgs &ra0, cudaStream_t st) {
+    RankArgs ra = ra0;
+    // K6b first (bucket distribution instead of a sorting network; kernels.cuh): it tokenizes every cell it can and leaves the rest
+    // -- cells with heavy ties or more rows than its shared-memory array -- on the work list, which the sorting kernel then drains.
+    // SLAFB_RANK_SORT=1 keeps the sorting kernel for every cell (A/B runs).
+    static const bool sort_only = [] { const char *e = getenv("SLAFB_RANK_SORT"); return e && atoi(e) != 0; }();
+    ra.from_list = 0;
+    if (!sort_only) {
+        // E = 16 rows per thread over all cells, then E = 32 over what it left (cells of 4,097..8,192 rows; the others stay listed)
+        auto b16 = tokenize_rank_bucket_kernel<GeneT, ValT, 16>;
+        auto b32 = tokenize_rank_bucket_kernel<GeneT, ValT, 32>;
+        const size_t dyn16 = rank_bucket_smem<16>(), dyn32 = rank_bucket_smem<32>();
+        static std::atomic<int> b_per_sm_cached[64], b32_per_sm_cached[64];
+        int p16 = b_per_sm_cached[ctx->device & 63].load(std::memory_order_acquire), p32 = b32_per_sm_cached[ctx->device & 63].load(std::memory_order_acquire);
+        if (p16 == 0 || p32 == 0) {
+            CU(ctx, cudaFuncSetAttribute(b16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn16));
+            CU(ctx, cudaFuncSetAttribute(b32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn32));
+            CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p16, b16, kTokThreads, dyn16));
+            CU(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p32, b32, kTokThreads, dyn32));
+            if (p16 < 1) p16 = 1;
+            if (p32 < 1) p32 = 1;
+            b32_per_sm_cached[ctx->device & 63].store(p32, std::memory_order_release);
+            b_per_sm_cached[ctx->device & 63].store(p16, std::memory_order_release);
+        }
+        uint32_t g16 = (uint32_t)(ctx->n_sm * p16);
+        if (ra.t.n_cells < g16) g16 = ra.t.n_cells;
+        if (g16 == 0) g16 = 1;
+        b16<<<g16, kTokThreads, dyn16, st>>>(ra);
+        CU(ctx, cudaGetLastError());
+        ra.from_list = 1;
+        uint32_t g32 = (uint32_t)(ctx->n_sm * p32);
+        if (ra.t.n_cells < g32) g32 = ra.t.n_cells;
+        if (g32 == 0) g32 = 1;
+        b32<<<g32, kTokThreads, dyn32, st>>>(ra);
+        CU(ctx, cudaGetLastError());
+        ctx->acc.kernel_launches += 2;
+    }
     auto kern = tokenize_rank_kernel<GeneT, ValT>;
     const size_t dyn = (size_t)kRankSmemSlots * sizeof(unsigned long long);
     static std::atomic<bool> attr_set[64];   // zero-initialised; setting the attribute twice is harmless
@@ -354,6 +390,7 @@ int launch_rank(slafb_ctx *ctx, const RankArgs &ra, cudaStream_t st) {
     }
     uint32_t grid = (uint32_t)(ctx->n_sm * per_sm);
     if (ra.t.n_cells < grid) grid = ra.t.n_cells;
+    if (grid == 0) grid = 1;
     kern<<<grid, kTokThreads, dyn, st>>>(ra);
     CU(ctx, cudaGetLastError());
     ctx->acc.kernel_launches++;
@@ -902,7 +939,8 @@ int back(slafb_ctx *ctx, Slot &s, const slafb_params *p, const slafb_out *out, i
         ra.n_norm = (uint32_t)(p->n_norm > 0xffffffffll ? 0xffffffffll : p->n_norm);
         ra.rank_order = p->order == SLAFB_ORDER_RANK;
         ra.scratch64 = ctx->rank_scratch;
-        CU(ctx, cudaMemsetAsync(s.counters + 3, 0, sizeof(uint32_t), st));
+        ra.from_list = 0;
+        CU(ctx, cudaMemsetAsync(s.counters + 2, 0, 4 * sizeof(uint32_t), st));     // work-list count, head (sorting kernel), row ticket, head (second bucket launch)
         if (s.sample) CU(ctx, cudaEventRecord(s.t_k2a, st));
         DISPATCH_TYPES(s.gene_dtype, s.value_dtype, rc = (launch_rank<GeneT, ValT>(ctx, ra, st)));
         if (rc) return rc;
