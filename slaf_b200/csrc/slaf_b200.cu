@@ -1022,13 +1022,16 @@ int submit_host_segments(slafb_ctx *ctx, const slafb_coo *pieces, int32_t n_piec
     if (in->cell_dtype != SLAFB_U32 && in->cell_dtype != SLAFB_I32) return fail(ctx, SLAFB_ERR_INVALID, "cell dtype must be uint32 or int32");
     if (total > ctx->max_rows) return fail(ctx, SLAFB_ERR_CAPACITY, "n_rows %lld exceeds context max_rows %lld", (long long)total, (long long)ctx->max_rows);
     if (n_cells_max < 0 || n_cells_max > ctx->max_cells) return fail(ctx, SLAFB_ERR_CAPACITY, "n_cells %lld exceeds context max_cells %lld", (long long)n_cells_max, (long long)ctx->max_cells);
+    static const bool trace = [] { const char *e = getenv("SLAFB_SUBMIT_TRACE"); return e && atoi(e) != 0; }();   // stderr: where a submit's host time goes
     if (s.ev_done) {
         CU(ctx, cudaEventSynchronize(s.ev_done));      // the slot's tables (and h_seg) may still be in use by its previous batch
         harvest(ctx, s);
     }
+    const double t1 = now_ms();
     int64_t n_cells = 0;
     int rc = fill(s.h_seg, s.h_seg + (size_t)ctx->max_cells + 1, total, &n_cells);    // starts, ids
     if (rc) return rc;
+    const double t2 = now_ms();
     // the table must describe the rows: non-decreasing offsets from 0 to the row count (an out-of-range entry would send the
     // tokenizing kernel's bulk copies out of bounds)
     if (n_cells > 0) {
@@ -1091,6 +1094,8 @@ int submit_host_segments(slafb_ctx *ctx, const slafb_coo *pieces, int32_t n_piec
     }
     CU(ctx, cudaEventRecord(s.ev_loaded, sf));
     ctx->acc.host_submit_ms += now_ms() - t0;
+    if (trace) fprintf(stderr, "[slafb submit] slot %d: wait for the slot %.3f ms, segment table %.3f ms (%lld cells), enqueue %.3f ms (%d pieces, %lld rows)\n",
+                       si, t1 - t0, t2 - t1, (long long)n_cells, now_ms() - t2, n_pieces, (long long)total);
     s.in_flight = true;
     *slot = si;
     if (n_cells_out) *n_cells_out = n_cells;
