@@ -573,22 +573,29 @@ void fill_tok_args(slafb_ctx *ctx, Slot &s, const slafb_params *p, TokArgs &a, u
 }
 
 // The slot for the next batch: a free one whose previous tokenization has already finished (reusing it costs no wait) and,
-// among those, one that already owns staging columns (no allocation); otherwise the free slot released longest ago, which
-// submit then waits for.  A feeder that keeps one or two batches in flight therefore touches two or three slots (and their
-// 12 B/row of staging), a deep pipeline all eight.
-int pick_slot(slafb_ctx *ctx) {
-    int ready_alloc = -1, ready = -1, oldest = -1;
+// among those, one that already owns staging columns (no allocation).  When every slot with staging columns is still busy on the
+// GPU and at least three of them exist, the one released longest ago is taken and submit waits for it: the host is ahead of the
+// copy engine then anyway, and a cudaMalloc of another slot's columns in the middle of a run costs 20-30 ms (it waits for the
+// queued copies to drain).  Otherwise a free slot without columns, or the free slot released longest ago.  A feeder that keeps
+// one or two batches in flight therefore touches three slots (and their 12 B/row of staging); only a pipeline that holds more
+// uncollected batches than that gets more.
+int pick_slot(slafb_ctx *ctx, bool needs_staging = false) {
+    int ready_alloc = -1, ready = -1, oldest = -1, oldest_alloc = -1, n_alloc = 0;
     for (int i = 0; i < kSlots; i++) {
         Slot &s = ctx->slot[i];
+        if (s.in_cell) n_alloc++;
         if (s.in_flight) continue;
         if (oldest < 0 || s.freed_at < ctx->slot[oldest].freed_at) oldest = i;
+        if (s.in_cell && (oldest_alloc < 0 || s.freed_at < ctx->slot[oldest_alloc].freed_at)) oldest_alloc = i;
         bool done = true;
         if (s.ev_done && cudaEventQuery(s.ev_done) != cudaSuccess) { done = false; cudaGetLastError(); }
         if (!done) continue;
         if (s.in_cell) { if (ready_alloc < 0 || s.freed_at < ctx->slot[ready_alloc].freed_at) ready_alloc = i; }
         else if (ready < 0 || s.freed_at < ctx->slot[ready].freed_at) ready = i;
     }
-    return ready_alloc >= 0 ? ready_alloc : ready >= 0 ? ready : oldest;
+    if (ready_alloc >= 0) return ready_alloc;
+    if (needs_staging && n_alloc >= 3 && oldest_alloc >= 0) return oldest_alloc;
+    return ready >= 0 ? ready : oldest;
 }
 
 // Small host pieces in pageable memory (the host feeder's partial cells: a few thousand rows) are copied into the slot's
@@ -1003,7 +1010,7 @@ int submit_host_segments(slafb_ctx *ctx, const slafb_coo *pieces, int32_t n_piec
                          int64_t *n_cells_out, Fill fill) {
     if (!ctx || !slot || !pieces || n_pieces < 1) return fail(ctx, SLAFB_ERR_INVALID, "bad ctx / slot / pieces");
     CU(ctx, cudaSetDevice(ctx->device));
-    const int si = pick_slot(ctx);
+    const int si = pick_slot(ctx, pieces[0].location == SLAFB_LOC_HOST || n_pieces > 1);
     if (si < 0) return fail(ctx, SLAFB_ERR_BUSY, "all %d pipeline slots hold batches that were not collected yet", kSlots);
     Slot &s = ctx->slot[si];
     const double t0 = now_ms();
@@ -1255,7 +1262,7 @@ int slafb_destroy(slafb_ctx *ctx) {
 int slafb_submit_pieces(slafb_ctx *ctx, const slafb_coo *pieces, int32_t n_pieces, void *stream, int32_t *slot) {
     if (!ctx || !slot) return fail(ctx, SLAFB_ERR_INVALID, "ctx / slot is NULL");
     CU(ctx, cudaSetDevice(ctx->device));
-    const int i = pick_slot(ctx);
+    const int i = pick_slot(ctx, pieces && n_pieces >= 1 && (pieces[0].location == SLAFB_LOC_HOST || n_pieces > 1));
     if (i < 0) return fail(ctx, SLAFB_ERR_BUSY, "all %d pipeline slots hold batches that were not collected yet", kSlots);
     Slot &s = ctx->slot[i];
     const double t0 = now_ms();
