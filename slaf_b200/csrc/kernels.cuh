@@ -15,14 +15,16 @@
 //                               batch tensors with 128-bit stores.
 //                               (aggregators.py:87-134,197-214 + tokenizers.py:407-479,666-722
 //                                + datasets.py:1087-1098)
+//   K2w tokenize_pct_warp_kernel  the min_percentile branch (aggregators.py:167-196) on uint16 values, one WARP per cell.
+//   K2f tokenize_f32_warp_kernel  all four modes on float32 values, one warp per cell (exact set of the cell's distinct values).
 //   K2g tokenize_general_kernel same emission, but with the exact k-th-distinct-value machinery
 //                               (value bitmap for uint16, shared/global bitonic sort for float32);
-//                               runs over the (normally empty) work list K2 leaves behind, or over all
-//                               cells in percentile mode (aggregators.py:167-196).
+//                               runs over the (normally empty) work list K2 / K2w / K2f leave behind.
 //   K3  window_*                Window.apply facade: kept-count, offsets, flat list columns.
 //   K4  tokenize_lists_kernel   SLAFTokenizer.tokenize facade on pre-windowed lists.
 //   K5  gene_stats_kernel       per-gene nonzero sum / count (extension, BASELINE.json config 4).
-//   K6  tokenize_rank_kernel    Geneformer rank-value encoding with per-gene normalisation / rank order (extension).
+//   K6  tokenize_rank_bucket_kernel (bucket distribution), tokenize_rank_kernel (sorting network, for what the first leaves)
+//                               Geneformer rank-value encoding with per-gene normalisation / rank order (extension).
 //   K7  gene_hist / gene_median per-gene value histogram and exact nonzero medians (extension).
 //   K8  csr_lengths / csr_gather raw mode on the device: the batch as CSR in shuffled cell order
 //                               (RawPrefetchBatch, reference slaf/ml/datasets.py:958-1008).
