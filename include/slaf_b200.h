@@ -348,6 +348,14 @@ int slafb_set_option(slafb_ctx *ctx, int32_t option, int64_t value);
  * the first.  -1 = the library was not built with checks. */
 int slafb_debug_check_failures(uint32_t *info);
 
+/* The float32 log1p of the binned window on float32 storage (polars keeps Float32 and calls Rust's f32::ln_1p = the platform's
+ * log1pf, slaf/ml/aggregators.py:96-105).  The device carries two evaluations -- a restatement of the fdlibm float algorithm
+ * (what glibc <= 2.39 ships; kind 1) and the correctly rounded value (glibc >= 2.40; kind 0) -- and uses the one this host's libm
+ * matches, so its float32 bins equal the reference's on the same machine bit for bit.  slafb_debug_log1pf evaluates one of the two
+ * on the HOST for n values (no GPU needed; the device code is the same source with round-to-nearest intrinsics) and returns the
+ * kind the library selects on this host (1 or 0); kind < 0 only asks. */
+int slafb_debug_log1pf(int32_t kind, const float *x, float *y, int64_t n);
+
 /* Timing / counters since the previous call (synchronises the context's streams). */
 int slafb_get_timing(slafb_ctx *ctx, slafb_timing *t);
 

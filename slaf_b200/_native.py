@@ -38,7 +38,7 @@ EXPORTS = [
     "slafb_collect", "slafb_collect_csr", "slafb_prepare_shuffle", "slafb_segments", "slafb_window", "slafb_tokenize_lists", "slafb_shuffle_perm", "slafb_gene_stats", "slafb_gene_hist", "slafb_gene_median",
     "slafb_host_alloc", "slafb_host_free", "slafb_get_timing", "slafb_set_option",
     "slafb_submit_csi", "slafb_csi_segments", "slafb_wait_loaded", "slafb_pipe_create", "slafb_pipe_push", "slafb_pipe_pop", "slafb_pipe_destroy", "slafb_debug_check_failures",
-    "slafb_pack_bound", "slafb_pack_rows", "slafb_unpack_rows", "slafb_submit_packed", "slafb_pipe_push_packed",
+    "slafb_pack_bound", "slafb_pack_rows", "slafb_unpack_rows", "slafb_submit_packed", "slafb_pipe_push_packed", "slafb_debug_log1pf",
 ]
 
 
@@ -168,6 +168,7 @@ def lib() -> ctypes.CDLL:
     L.slafb_pipe_pop.argtypes = [c_void_p, c_void_p, POINTER(PipeResult)]
     L.slafb_pipe_destroy.argtypes = [c_void_p]
     L.slafb_debug_check_failures.argtypes = [c_void_p]
+    L.slafb_debug_log1pf.argtypes = [c_int32, c_void_p, c_void_p, c_int64]
     L.slafb_pack_bound.restype = c_int64
     L.slafb_pack_bound.argtypes = [c_int64, c_int64]
     L.slafb_pack_rows.argtypes = [c_void_p, c_int32, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, POINTER(c_int64)]

@@ -34,6 +34,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 namespace slafb {
 
@@ -209,11 +210,99 @@ __device__ __forceinline__ long long expr_bin_token(float x, float bin_size, int
     return x > 0.0f ? vocab + b : 0ll;
 }
 
-// float32 log1p used by the binned window on float32 storage (polars keeps Float32 and calls libm
-// log1pf).  Computed as the float rounding of the double log1p: differs from glibc's (<1 ulp,
-// not correctly rounded) log1pf only where glibc itself is off by an ulp -- DESIGN.md "float32
-// binned window: parity unpinned at ulp level".
-__device__ __forceinline__ float log1pf_window(float x) { return (float)log1p((double)x); }
+// float32 log1p used by the binned window on float32 storage: polars keeps Float32 and calls Rust's f32::ln_1p, i.e. the
+// platform's libm log1pf.  Two libms exist in practice: glibc up to 2.39 ships the fdlibm float algorithm (within 1 ulp, not
+// correctly rounded: it differs from the correctly rounded value on 9,149,209 of the 2,139,095,040 non-negative floats), glibc
+// from 2.40 the correctly rounded CORE-MATH one.  The device has both and uses the one the host's libm matches (probed at
+// context creation, slaf_b200.cu: c_log1pf_fdlibm), so float32 bins equal what polars computes on the same machine bit for bit
+// on every input.  log1pf_fdlibm restates the published fdlibm algorithm (s_log1pf.c, Sun Microsystems 1993; float
+// version by Ian Lance Taylor, Cygnus) operation by operation with round-to-nearest intrinsics (no FMA contraction);
+// scripts/micro/log1pf_check.c compares the same restatement with the host's log1pf on ALL non-negative floats (0 differences
+// on glibc 2.39) and checks that the host's function is monotone there (the per-cell bin threshold relies on it: 0 violations).
+__constant__ int c_log1pf_fdlibm;
+// (round-to-nearest float operations that the compiler may not contract: intrinsics on the device, plain operators on the host,
+// where x86-64 code is generated without FMA instructions)
+#ifdef __CUDA_ARCH__
+#define SLAFB_FADD(a, b) __fadd_rn((a), (b))
+#define SLAFB_FSUB(a, b) __fsub_rn((a), (b))
+#define SLAFB_FMUL(a, b) __fmul_rn((a), (b))
+#define SLAFB_FDIV(a, b) __fdiv_rn((a), (b))
+#else
+#define SLAFB_FADD(a, b) ((float)((a) + (b)))
+#define SLAFB_FSUB(a, b) ((float)((a) - (b)))
+#define SLAFB_FMUL(a, b) ((float)((a) * (b)))
+#define SLAFB_FDIV(a, b) ((float)((a) / (b)))
+#endif
+__host__ __device__ inline uint32_t slafb_f2u(float x) { uint32_t u; memcpy(&u, &x, 4); return u; }
+__host__ __device__ inline float slafb_u2f(uint32_t u) { float x; memcpy(&x, &u, 4); return x; }
+__host__ __device__ inline float log1pf_fdlibm(float x) {
+    const float ln2_hi = 6.9313812256e-01f, ln2_lo = 9.0580006145e-06f, two25 = 3.355443200e+07f;
+    const float Lp1 = 6.6666668653e-01f, Lp2 = 4.0000000596e-01f, Lp3 = 2.8571429849e-01f, Lp4 = 2.2222198546e-01f,
+                Lp5 = 1.8183572590e-01f, Lp6 = 1.5313838422e-01f, Lp7 = 1.4798198640e-01f;
+    float f = 0.0f, c = 0.0f, u;
+    int32_t hx = (int32_t)slafb_f2u(x), hu = 0, k = 1;
+    const int32_t ax = hx & 0x7fffffff;
+    if (hx < 0x3ed413d7) {                                                  // x < 0.41422
+        if (ax >= 0x3f800000) {                                             // x <= -1.0
+            if (x == -1.0f) return SLAFB_FDIV(-two25, 0.0f);
+            return SLAFB_FDIV(SLAFB_FSUB(x, x), SLAFB_FSUB(x, x));
+        }
+        if (ax < 0x31000000) {                                              // |x| < 2**-29
+            if (ax < 0x24800000) return x;                                  // |x| < 2**-54
+            return SLAFB_FSUB(x, SLAFB_FMUL(SLAFB_FMUL(x, x), 0.5f));
+        }
+        if (hx > 0 || hx <= (int32_t)0xbe95f61f) { k = 0; f = x; hu = 1; }  // -0.2929 < x < 0.41422
+    }
+    if (hx >= 0x7f800000) return SLAFB_FADD(x, x);
+    if (k != 0) {
+        if (hx < 0x5a000000) {
+            u = SLAFB_FADD(1.0f, x);
+            hu = (int32_t)slafb_f2u(u);
+            k = (hu >> 23) - 127;
+            c = (k > 0) ? SLAFB_FSUB(1.0f, SLAFB_FSUB(u, x)) : SLAFB_FSUB(x, SLAFB_FSUB(u, 1.0f));      // correction term
+            c = SLAFB_FDIV(c, u);
+        } else {
+            u = x;
+            hu = (int32_t)slafb_f2u(u);
+            k = (hu >> 23) - 127;
+            c = 0.0f;
+        }
+        hu &= 0x007fffff;
+        if (hu < 0x3504f7) {
+            u = slafb_u2f((uint32_t)(hu | 0x3f800000));               // normalize u
+        } else {
+            k += 1;
+            u = slafb_u2f((uint32_t)(hu | 0x3f000000));               // normalize u/2
+            hu = (0x00800000 - hu) >> 2;
+        }
+        f = SLAFB_FSUB(u, 1.0f);
+    }
+    const float kf = (float)k;
+    const float hfsq = SLAFB_FMUL(SLAFB_FMUL(0.5f, f), f);
+    if (hu == 0) {                                                          // |f| < 2**-20
+        if (f == 0.0f) {
+            if (k == 0) return 0.0f;
+            c = SLAFB_FADD(c, SLAFB_FMUL(kf, ln2_lo));
+            return SLAFB_FADD(SLAFB_FMUL(kf, ln2_hi), c);
+        }
+        const float R = SLAFB_FMUL(hfsq, SLAFB_FSUB(1.0f, SLAFB_FMUL(0.66666666666666666f, f)));
+        if (k == 0) return SLAFB_FSUB(f, R);
+        return SLAFB_FSUB(SLAFB_FMUL(kf, ln2_hi), SLAFB_FSUB(SLAFB_FSUB(R, SLAFB_FADD(SLAFB_FMUL(kf, ln2_lo), c)), f));
+    }
+    const float s = SLAFB_FDIV(f, SLAFB_FADD(2.0f, f));
+    const float z = SLAFB_FMUL(s, s);
+    float R = SLAFB_FADD(Lp6, SLAFB_FMUL(z, Lp7));
+    R = SLAFB_FADD(Lp5, SLAFB_FMUL(z, R));
+    R = SLAFB_FADD(Lp4, SLAFB_FMUL(z, R));
+    R = SLAFB_FADD(Lp3, SLAFB_FMUL(z, R));
+    R = SLAFB_FADD(Lp2, SLAFB_FMUL(z, R));
+    R = SLAFB_FADD(Lp1, SLAFB_FMUL(z, R));
+    R = SLAFB_FMUL(z, R);
+    if (k == 0) return SLAFB_FSUB(f, SLAFB_FSUB(hfsq, SLAFB_FMUL(s, SLAFB_FADD(hfsq, R))));
+    return SLAFB_FSUB(SLAFB_FMUL(kf, ln2_hi),
+                     SLAFB_FSUB(SLAFB_FSUB(hfsq, SLAFB_FADD(SLAFB_FMUL(s, SLAFB_FADD(hfsq, R)), SLAFB_FADD(SLAFB_FMUL(kf, ln2_lo), c))), f));
+}
+__device__ __forceinline__ float log1pf_window(float x) { return c_log1pf_fdlibm ? log1pf_fdlibm(x) : (float)log1p((double)x); }
 
 // ------------------------------------------------------------------------------------------
 // mbarrier / TMA bulk-copy primitives (PTX)

@@ -104,6 +104,7 @@ struct slafb_ctx {
     uint32_t *ticket = nullptr;
     uint32_t ticket_base = 0, epoch = 0;
     double *log1p_lut = nullptr;
+    int log1pf_fdlibm = 0;            // the host's log1pf is the fdlibm float algorithm (glibc <= 2.39): the device uses its restatement
     uint32_t *vstar_table = nullptr;  // binned window on uint16 storage: bin>=1 threshold per cell maximum
     int vstar_nbins = -1;
     uint32_t *sort_scratch = nullptr;
@@ -234,6 +235,24 @@ void harvest(slafb_ctx *ctx, Slot &s) {
         if (s.used_f32_warp && s.back_cells >= 64 && slow * 8 > s.back_cells) ctx->f32_warp_off = true;
     }
     s.timed_front = s.timed_back = s.timed_h2d = s.ran_back = s.used_f32_warp = false;
+}
+
+// Which log1pf does the host's libm ship -- the one polars calls on float32 columns (kernels.cuh: log1pf_window)?  A sweep over
+// 2^20 non-negative floats (every 2,040th bit pattern) against the fdlibm restatement and against the correctly rounded value:
+// 1 = the host matches the fdlibm algorithm everywhere (glibc <= 2.39), 0 = it matches the correctly rounded value (glibc >= 2.40)
+// or neither (an unknown libm gets the correctly rounded evaluation).  Evaluated once per process.
+int host_log1pf_kind() {
+    static const int kind = [] {
+        bool is_fdlibm = true, is_cr = true;
+        for (uint32_t b = 0; b < 0x7f800000u; b += 2040u) {
+            const float x = slafb_u2f(b), h = log1pf(x);
+            const float f = log1pf_fdlibm(x), c = (float)log1p((double)x);
+            is_fdlibm &= memcmp(&h, &f, 4) == 0;
+            is_cr &= memcmp(&h, &c, 4) == 0;
+        }
+        return (is_fdlibm && !is_cr) ? 1 : 0;
+    }();
+    return kind;
 }
 
 int ensure_staging(slafb_ctx *ctx, Slot &s) {
@@ -1191,6 +1210,12 @@ int slafb_create(slafb_ctx **out, int device, int64_t max_rows, int64_t max_cell
         free(h);
         CUC(e2);
     }
+    // which log1pf the host's libm ships (host_log1pf_kind below): the device uses the evaluation that matches it
+    {
+        const int use_fdlibm = host_log1pf_kind();
+        ctx->log1pf_fdlibm = use_fdlibm;
+        CUC(cudaMemcpyToSymbol(c_log1pf_fdlibm, &use_fdlibm, sizeof(int)));
+    }
     CUC(cudaMalloc(&ctx->kept_count, ((size_t)max_cells + 1) * sizeof(uint32_t)));
     CUC(cudaMalloc(&ctx->total_dev, sizeof(long long)));
     CUC(cudaHostAlloc(&ctx->h_total, sizeof(long long), cudaHostAllocDefault));
@@ -1874,6 +1899,12 @@ int slafb_gene_median(slafb_ctx *ctx, const uint32_t *hist, int64_t n_genes, int
     CU(ctx, cudaGetLastError());
     ctx->acc.kernel_launches++;
     return SLAFB_OK;
+}
+
+int slafb_debug_log1pf(int32_t kind, const float *x, float *y, int64_t n) {
+    if (kind >= 0 && x && y)
+        for (int64_t i = 0; i < n; i++) y[i] = kind ? log1pf_fdlibm(x[i]) : (float)log1p((double)x[i]);
+    return host_log1pf_kind();
 }
 
 int slafb_debug_check_failures(uint32_t *info) {

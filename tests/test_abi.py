@@ -137,3 +137,29 @@ def test_packed_rows_round_trip_and_refusals(lib):
         pack_rows(b.gene, b.value.astype(np.float32), b.cell_start, np.arange(b.n_cells, dtype=np.uint32))
     empty = pack_rows(np.zeros(0, np.uint16), np.zeros(0, np.uint16), np.zeros(1, np.int64), np.zeros(0, np.uint32))
     assert empty.n_cells == 0 and empty.nbytes == 0
+
+
+def test_host_log1pf_restatement_matches_libm(lib):
+    """float32 binned window (aggregators.py:96-105 on Float32 columns): polars calls the platform's log1pf.  The library carries a
+    restatement of the fdlibm float algorithm (glibc <= 2.39) and the correctly rounded value (glibc >= 2.40) and selects the one
+    this host's libm matches; the device code is the same source.  Here: the selected evaluation equals libm's log1pf on 4 M
+    floats spread over [0, inf) and on every float of [0.5, 0.5001] -- scripts/micro/log1pf_check.c does all 2^31 in C."""
+    libm = ctypes.CDLL("libm.so.6")
+    libm.log1pf.restype = ctypes.c_float
+    libm.log1pf.argtypes = [ctypes.c_float]
+    kind = lib.slafb_debug_log1pf(-1, None, None, 0)
+    assert kind in (0, 1)
+    lo, hi = int(np.float32(0.5).view(np.uint32)), int(np.float32(0.5001).view(np.uint32))
+    bits = np.concatenate([np.arange(0, 0x7F800000, 509, dtype=np.uint32), np.arange(lo, hi, dtype=np.uint32)])
+    x = bits.view(np.float32)
+    got = np.empty_like(x)
+    assert lib.slafb_debug_log1pf(kind, x.ctypes.data, got.ctypes.data, x.size) == kind
+    f = np.vectorize(lambda v: libm.log1pf(float(v)), otypes=[np.float32])
+    step = max(1, x.size // 400_000)                      # (a ctypes call per value: a 400 k sample of the set, plus the dense range)
+    idx = np.unique(np.concatenate([np.arange(0, x.size, step), np.arange(x.size - (hi - lo), x.size)]))
+    want = f(x[idx])
+    assert np.array_equal(got[idx].view(np.uint32), want.view(np.uint32))
+    # the two evaluations do differ (by one ulp, on ~0.4 % of the floats): the selection matters
+    other = np.empty_like(x)
+    lib.slafb_debug_log1pf(1 - kind, x.ctypes.data, other.ctypes.data, x.size)
+    assert 0 < np.count_nonzero(other.view(np.uint32) != got.view(np.uint32)) < x.size // 50

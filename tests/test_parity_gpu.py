@@ -211,6 +211,40 @@ def test_window_facade_vs_oracle(engine, mode, pct, value_dtype):
         assert_same(w.exprs.cpu().numpy(), exprs, "exprs")
 
 
+def test_float32_window_bins_follow_the_hosts_log1pf(engine):
+    """Binned window on float32 storage (aggregators.py:96-105): polars calls the platform's log1pf, the checker here calls the same
+    function, and the device evaluates whichever of its two log1pf versions the host's libm matches (fdlibm restatement for glibc
+    <= 2.39, correctly rounded for >= 2.40).  2^20 window bins make a one-ulp difference in log1pf visible: with the other version
+    some bins would differ (asserted), with the selected one none does."""
+    rng = np.random.default_rng(5)
+    n, C = 4000, 24
+    value = np.unique(rng.uniform(0.05, 200.0, n * C).astype(np.float32))
+    n = value.size // C
+    value = value[: n * C].copy()
+    rng.shuffle(value)
+    cell = np.repeat(np.arange(C, dtype=np.int32) + 3, n)
+    gene = np.concatenate([np.sort(rng.choice(60000, n, replace=False)) for _ in range(C)]).astype(np.int32)
+    nb = 1 << 20
+    cids, offs, genes, exprs = c_oracle.window(cell, gene, value, "scgpt_binned", n + 1, n_bins=nb)
+    w = engine.window(cell, gene, value, mode="scgpt_binned", max_items=n + 1, n_bins=nb)
+    assert_same(w.offsets.cpu().numpy(), offs, "offsets")
+    assert_same(w.genes.cpu().numpy(), genes, "genes")
+    assert_same(w.exprs.cpu().numpy(), exprs, "exprs")
+    # the test has teeth: the bins computed with the OTHER log1pf differ somewhere
+    L = _native.lib()
+    kind = L.slafb_debug_log1pf(-1, None, None, 0)
+    lv = {}
+    for kd in (0, 1):
+        y = np.empty_like(value)
+        L.slafb_debug_log1pf(kd, value.ctypes.data, y.ctypes.data, value.size)
+        lv[kd] = y.reshape(C, n)
+    def bins(v):
+        m = v.max(axis=1, keepdims=True)
+        return np.clip(np.floor((v * np.float32(nb)) / m), 0, nb - 1)
+    assert np.array_equal(bins(lv[kind]).ravel(), np.asarray(exprs, np.float32).ravel())
+    assert np.count_nonzero(bins(lv[kind]) != bins(lv[1 - kind])) > 0
+
+
 @pytest.mark.parametrize("tag", ["gf8", "gf64", "gf2048"])
 def test_tokenizer_facade_reference_golden_geneformer(engine, tag):
     offs, genes = to_dev(GOLD[f"{tag}_offsets"]), to_dev(GOLD[f"{tag}_genes"])
