@@ -302,7 +302,9 @@ __host__ __device__ inline float log1pf_fdlibm(float x) {
     return SLAFB_FSUB(SLAFB_FMUL(kf, ln2_hi),
                      SLAFB_FSUB(SLAFB_FSUB(hfsq, SLAFB_FADD(SLAFB_FMUL(s, SLAFB_FADD(hfsq, R)), SLAFB_FADD(SLAFB_FMUL(kf, ln2_lo), c))), f));
 }
-__device__ __forceinline__ float log1pf_window(float x) { return c_log1pf_fdlibm ? log1pf_fdlibm(x) : (float)log1p((double)x); }
+// (out of line on purpose: it is called from up to five places of a kernel, a few times per cell, and both evaluations are ~300
+// instructions -- inlined they doubled the float32 kernels' code and cost 15 % through the instruction cache)
+__device__ __noinline__ float log1pf_window(float x) { return c_log1pf_fdlibm ? log1pf_fdlibm(x) : (float)log1p((double)x); }
 
 // ------------------------------------------------------------------------------------------
 // mbarrier / TMA bulk-copy primitives (PTX)
