@@ -120,3 +120,68 @@ def test_percentile_threshold_from_rounds_of_minima(values, k, p):
         sel = int(cand.min())
         lowb = sel + 1
     assert sel == int(np.sort(keys)[a - 1])
+
+
+@settings(max_examples=300, deadline=None)
+@given(st.integers(0, 7), st.lists(st.booleans(), min_size=1, max_size=1500), st.integers(1, 1200))
+def test_in_place_compaction_with_prefetch_never_reads_overwritten_rows(sh, keep, limit):
+    """K2w / K2f percentile mode: the kept genes are compacted IN PLACE in the gene stage, 256 rows (32 lanes x 8) per step, and the
+    loads of step t + 1 are issued before the stores of step t.  Model of that schedule: every load must still see the original
+    gene of its row, and the result must be the first `limit` kept genes in row order."""
+    n = len(keep)
+    stage = np.full(sh + n + 8, -1, np.int64)
+    stage[sh:sh + n] = np.arange(n) + 1000                                   # gene of row i = 1000 + i
+    ngroups = (sh + n + 7) // 8
+    def load(step):                                                          # what the 32 lanes read for a step: (group, 8 genes)
+        out = []
+        for lane in range(32):
+            gi = min(step * 32 + lane, ngroups - 1)                          # clamped, as in the kernel
+            out.append((step * 32 + lane, stage[gi * 8: gi * 8 + 8].copy()))
+        return out
+    base, nxt, step = 0, load(0), 0
+    while step * 32 < ngroups and base < limit:
+        cur, nxt = nxt, load(step + 1)                                       # next step's loads first ...
+        for gi, genes in cur:                                                # ... then this step's stores, lane by lane
+            if gi >= ngroups:
+                continue
+            for i in range(8):
+                row = gi * 8 + i - sh
+                if 0 <= row < n and keep[row]:
+                    assert genes[i] == 1000 + row                            # the load saw the original gene
+                    if base < limit:
+                        stage[sh + base] = genes[i]
+                    base += 1
+        step += 1
+    want = [1000 + i for i in range(n) if keep[i]][:limit]
+    got = stage[sh: sh + min(base, limit)].tolist()
+    assert got == want[: len(got)] and (len(got) == len(want) or base >= limit)
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.lists(st.integers(0, 2**32 - 2), min_size=1, max_size=1200), st.integers(0, 3))
+def test_home_slot_lookups_count_distinct_values_exactly(keys, seed):
+    """K2f: the sweep only asks "is the key in its HOME slot"; everything else (a new key, a key that linear probing displaced)
+    takes the inserting path, which is idempotent.  The number of successful inserts is the number of distinct keys as long as
+    the 512-slot set does not fill up (the kernel stops trusting it beyond 255 entries)."""
+    SLOTS = 512
+    tab = [None] * SLOTS
+    inserted = 0
+    home = lambda k: ((k * 2654435761) & 0xFFFFFFFF) >> (32 - 9)
+    order = np.random.default_rng(seed).permutation(len(keys))
+    for i in order:
+        k = keys[i]
+        if tab[home(k)] == k:
+            continue                                                          # hot path: seen
+        h = home(k)                                                           # inserting path (also reached by displaced keys)
+        while True:
+            if tab[h] is None:
+                tab[h] = k
+                inserted += 1
+                break
+            if tab[h] == k:
+                break
+            h = (h + 1) & (SLOTS - 1)
+        if inserted > 255:
+            break
+    D = len(set(keys))
+    assert inserted == D if D <= 255 else inserted > 255
